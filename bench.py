@@ -1,0 +1,389 @@
+#!/usr/bin/env python
+"""Benchmark of the B200-native LLA-MPC look-back hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+Metric (BASELINE.json): candidate-model RK4 steps/s.  One bench "step" = one MPC tick of the look-back step =
+one pass of the hot path over the whole bank and window:
+    N = 1 : config C2  - 65,536 candidates (6 Pacejka + mass varied) x 50-step window, per-tick arg-min + top-10
+    N > 1 : config C5  - 1,048,576 candidates x 50-step window sharded by contiguous index range over N GPUs,
+            local reduce + ONE NCCL min-loc all-reduce (packed 64-bit key) per tick
+`value` is measured with the inputs resident in HBM (CUDA events on the launching stream, L2 flushed between
+ticks); `e2e` goes through the public Python API (LookBack.push) with host NumPy inputs: host packing,
+pinned H2D of the history row, kernels, D2H of the selected indices, every tick.
+`--impl reference` times the reference algorithm's CPU path (the NumPy oracle port of
+evaluate_models_vectorized + scoring, float64) on all host cores.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+F_ALG = 652.0            # FP32 flop per candidate-RK4-step (SURVEY.md 8(d) convention)
+S_ALG = 40.0             # SFU-class ops per step (same convention)
+NPARAM_PACKED = 16       # floats per candidate in the packed bank
+W_C2, N_C2 = 50, 65536
+N_C5 = 1 << 20
+TS = 0.02
+C2_VARIATION = (("Br", 0.2), ("Cr", 0.1), ("Dr", 0.5), ("Bf", 0.2), ("Cf", 0.1), ("Df", 0.5), ("mass", 0.15))
+NOMINAL = {"lf": 0.029, "lr": 0.033, "mass": 0.041, "Iz": 27.8e-6, "Bf": 2.579, "Br": 3.3852, "Cf": 1.2, "Cr": 1.2691,
+           "Df": 0.192, "Dr": 0.1737, "Cm1": 0.287, "Cm2": 0.0545, "Cr0": 0.0518, "Cr2": 0.00035}
+
+
+def make_bank(n, seed, lo=0, hi=None):
+    """Synthetic bank: nominal x (1 + sigma randn), drawn like run_nmpc_orca_llampc_rt.py:145-179 (per model,
+    per varied parameter) from a seeded RandomState; [lo, hi) selects a shard."""
+    hi = n if hi is None else hi
+    z = np.random.RandomState(seed).randn(n, len(C2_VARIATION))[lo:hi]
+    bank = dict(NOMINAL)
+    for j, (name, sigma) in enumerate(C2_VARIATION):
+        bank[name] = NOMINAL[name] * (1 + sigma * z[:, j])
+    return bank
+
+
+def synthetic_history(n_ticks, plant_step):
+    """History B of SURVEY.md 8(d): ORCA plant (RK6) from the ETHZMobil start, sinusoidal inputs, sudden
+    friction drop; `plant_step(params, x, u)` is the integrator used (GPU plant kernel or the CPU port)."""
+    x = np.array([1.2, 0.9, 0.0, 1.0, 0.0, 0.0])
+    p = dict(NOMINAL)
+    S, U = [x.copy()], []
+    for k in range(n_ticks):
+        t = k * TS
+        if 0.6 < t < 0.8:                                    # 'sudden' friction drop (avg_runs.py:163-166 shape)
+            p["Df"] *= (1 - 1 / 22.0)
+            p["Dr"] *= (1 - 1 / 22.0)
+        u = np.array([0.45 + 0.35 * np.sin(0.7 * t), 0.25 * np.sin(1.3 * t)])
+        x = plant_step(p, x, u)
+        S.append(x.copy())
+        U.append(u)
+    return np.array(S).T, np.array(U).T
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except Exception:
+                pass
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx.append(float(r[1]))
+                for n, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                continue
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# CPU reference arm: the oracle port of the reference NumPy path (float64), sharded over host processes
+# ----------------------------------------------------------------------------------------------------------
+def _cpu_worker(args):
+    bank, S, U, W = args
+    from oracle import llampc_oracle as orc
+    t0 = time.perf_counter()
+    ew = orc.window_errors(bank, S, U, W - 1, W, TS)
+    avg = ew.mean(axis=1)
+    best, topk = orc.select(avg, 10)
+    return time.perf_counter() - t0, best
+
+
+class CpuReference:
+    """The reference algorithm (NumPy port, float64) on `procs` host processes over contiguous candidate shards."""
+
+    def __init__(self, n_cand, W, procs, S, U):
+        import multiprocessing as mp
+        bank = make_bank(n_cand, seed=1)
+        self.n_cand, self.W, self.shards = n_cand, W, []
+        per = (n_cand + procs - 1) // procs
+        for r in range(procs):
+            lo, hi = r * per, min(n_cand, (r + 1) * per)
+            if lo < hi:
+                self.shards.append(({k: (v[lo:hi] if np.ndim(v) else v) for k, v in bank.items()}, S[:, :W + 1], U[:, :W], W))
+        self.pool = mp.get_context("fork").Pool(len(self.shards)) if len(self.shards) > 1 else None
+
+    def step(self):
+        """One pass over the sample; returns seconds."""
+        t0 = time.perf_counter()
+        if self.pool is None:
+            _cpu_worker(self.shards[0])
+        else:
+            self.pool.map(_cpu_worker, self.shards)
+        return time.perf_counter() - t0
+
+    def close(self):
+        if self.pool is not None:
+            self.pool.terminate()
+
+
+def cpu_reference_rate(n_cand, W, procs, S, U, repeats=1):
+    ref = CpuReference(n_cand, W, procs, S, U)
+    ref.step()                                                 # warm-up (imports, page-in)
+    best_t = min(ref.step() for _ in range(repeats))
+    ref.close()
+    return n_cand * W / best_t, best_t
+
+
+def cpu_history():
+    from oracle import llampc_oracle as orc
+    return synthetic_history(W_C2 + 2, lambda p, x, u: orc.rk6_step(p, x, u, 0, TS))
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    S, U = cpu_history()
+    n_sample = int(min(N_C2, max(16384, 2048 * cores)))
+    ref = CpuReference(n_sample, W_C2, cores, S, U)
+    for _ in range(max(args.warmup, 1)):
+        ref.step()
+    total = sum(ref.step() for _ in range(args.steps))
+    ref.close()
+    value = n_sample * W_C2 * args.steps / total
+    sample = "%d of %d candidates x %d-step window per step (bounded sample of the same bank), float64 NumPy" % (
+        n_sample, N_C2 if args.gpus == 1 else N_C5, W_C2)
+    line = {"impl": "reference", "metric": "candidate-model RK4 steps/s (look-back window)", "value": value,
+            "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args.gpus),
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(gpus):
+    if gpus == 1:
+        return {"workload": "C2: look-back, 65,536 candidates (6 Pacejka + mass varied) x 50-step window, arg-min + top-10 per tick",
+                "candidates": N_C2, "window": W_C2, "Ts": TS, "l2": "flushed between timed ticks (256 MiB write)"}
+    return {"workload": "C5: look-back sweep, 1,048,576 candidates x 50-step window sharded over %d GPUs, one NCCL min-loc all-reduce per tick" % gpus,
+            "candidates": N_C5, "window": W_C2, "Ts": TS, "l2": "flushed between timed ticks (256 MiB write)"}
+
+
+# ----------------------------------------------------------------------------------------------------------
+# GPU arm
+# ----------------------------------------------------------------------------------------------------------
+def cpu_baseline_leg():
+    """Reference algorithm on the host cores (bounded sample), run BEFORE CUDA is initialised (fork safety)."""
+    cores = os.cpu_count() or 1
+    Sc, Uc = cpu_history()
+    n_all = int(min(N_C2, max(16384, 2048 * cores)))
+    r1, _ = cpu_reference_rate(8192, W_C2, 1, Sc, Uc)
+    rall, _ = cpu_reference_rate(n_all, W_C2, cores, Sc, Uc, repeats=3)
+    return {"value": rall, "unit": "steps/s", "cores": cores, "kind": "port",
+            "sample": "%d of the 65,536 C2 candidates x 50-step window, float64 NumPy port of evaluate_models_vectorized "
+                      "+ scoring, sharded over %d processes" % (n_all, cores),
+            "value_1core_as_reference_runs_it": r1}
+
+
+def run_b200(args):
+    cpu_base = None
+    if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu:
+        cpu_base = cpu_baseline_leg()
+    import torch
+    import torch.distributed as td
+    from llampc_b200 import _lib
+    from llampc_b200.bank import ModelBank
+    from llampc_b200.models import Dynamic
+    from llampc_b200.mpc import LookBack
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        td.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+
+    # ---- synthetic inputs (plant = the product's own fp64 RK6 kernel)
+    plant = Dynamic(**NOMINAL)
+
+    def plant_step(p, x, u):
+        plant.Df, plant.Dr = p["Df"], p["Dr"]
+        return plant.plant_step(x[None], u[None], TS)[0]
+
+    S, U = synthetic_history(W_C2 + 2 + args.steps + args.warmup + 8, plant_step)
+    n_total = N_C2 if world == 1 else N_C5
+    per = (n_total + world - 1) // world
+    lo, hi = rank * per, min(n_total, (rank + 1) * per)
+    bank_p = make_bank(n_total, seed=1 if world == 1 else 5, lo=lo, hi=hi)
+    n_local = hi - lo
+    lb = LookBack(bank_p, W=W_C2, Ts=TS, K=10, refine=0, idx_offset=lo)
+    ts = np.arange(0, W_C2)
+    lb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
+    st = torch.cuda.current_stream().cuda_stream
+    bank = lb.bank
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def tick_device():
+        """One look-back tick with device-resident inputs: key reset, K1, top-10 (+ min-loc all-reduce)."""
+        L.llampc_fill_keys(lb.best_key.data_ptr(), 1, st)
+        rc = L.llampc_lookback_window_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2, TS,
+                                          lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lo, int(bank.geom_shared), 0, st)
+        _lib.check(rc, "K1")
+        _lib.check(L.llampc_topk_f32(lb.avg_err.data_ptr(), n_local, lo, 10, lb.topk_scratch.data_ptr(),
+                                     lb.topk_counter.data_ptr(), lb.topk_keys.data_ptr(), st), "K4")
+        if world > 1:
+            td.all_reduce(lb.best_key, op=td.ReduceOp.MIN)
+
+    def k1_only():
+        L.llampc_lookback_window_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2, TS,
+                                     lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lo, int(bank.geom_shared), 0, st)
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        for a, b in evs:
+            flush.fill_(1)                                     # evict L2 between timed iterations (not timed)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
+        torch.cuda.synchronize()
+        ms = np.array([a.elapsed_time(b) for a, b in evs])
+        tot = torch.tensor([ms.sum()], dtype=torch.float64, device=dev)
+        if world > 1:
+            td.all_reduce(tot, op=td.ReduceOp.MAX)
+        return float(tot.item()), ms
+
+    with ClockSampler(local) as clk:
+        total_ms, per_ms = timed(tick_device, args.steps, max(args.warmup, 3))
+        k1_total_ms, k1_ms = timed(k1_only, args.steps, 3)
+    clocks = clk.summary()
+    steps_per_tick = n_total * W_C2
+    value = steps_per_tick * args.steps / (total_ms * 1e-3)
+    k1_avg_s = float(np.mean(k1_ms)) * 1e-3
+    k1_rate = n_local * W_C2 / k1_avg_s
+
+    # ---- roofline of the dominant kernel (K1): FP32 pipe, plus the SFU and HBM readings for context
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    sm_max = float(peaks.get("sm_max_mhz", 1965.0))
+    fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12                       # TFLOP/s at the max SM clock
+    achieved = k1_rate * F_ALG / 1e12
+    hbm_bytes = n_local * (NPARAM_PACKED * 4 + 4) + W_C2 * 80
+    roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
+                "traffic": None, "kernel": "lookback_window_kernel", "kernel_us": k1_avg_s * 1e6,
+                "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json; tensor/HBM peaks do not bound this elementwise ODE kernel)" % sm_max,
+                "flop_per_step": F_ALG, "steps_per_launch": n_local * W_C2,
+                "sfu": {"achieved_Tops": k1_rate * S_ALG / 1e12, "peak_Tops": 148 * 16 * sm_max * 1e6 / 1e12},
+                "hbm": {"algorithmic_bytes": hbm_bytes, "achieved_GBs": hbm_bytes / k1_avg_s / 1e9,
+                        "peak_GBs": peaks.get("hbm_gbs", 6650.0), "peak_kind": "measured" if peaks else "fallback"}}
+    if clocks.get("sm_mhz"):
+        roofline["frac_at_observed_clock"] = achieved / (148 * 128 * 2 * clocks["sm_mhz"] * 1e6 / 1e12)
+
+    # ---- end to end through the public API (rank-local bank; host inputs every tick)
+    e2e = None
+    lat = None
+    if world == 1:
+        lbe = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=32)
+        for t in range(W_C2):
+            lbe.push(S[:, t], U[:, t], S[:, t + 1])
+        for t in range(W_C2, W_C2 + max(args.warmup, 3)):
+            lbe.push(S[:, t], U[:, t], S[:, t + 1])
+        torch.cuda.synchronize()
+        lats = []
+        t_base = W_C2 + max(args.warmup, 3)
+        t0 = time.perf_counter()
+        for i in range(args.steps):
+            t = t_base + i
+            a = time.perf_counter()
+            best, topk, err = lbe.push(S[:, t], U[:, t], S[:, t + 1])
+            lats.append(time.perf_counter() - a)
+        wall = time.perf_counter() - t0
+        h2d = _lib.HIST_ROW * 4 + _lib.HIST64_ROW * 8
+        d2h = (1 + lbe.Kt) * 8 + lbe.Kt * 8
+        e2e = {"value": steps_per_tick * args.steps / wall, "unit": "steps/s", "h2d_bytes_per_step": h2d,
+               "d2h_bytes_per_step": d2h, "api": "LookBack.push (refine=32: fp64 re-score of the finalists included)"}
+        lat = {"p50_us": float(np.percentile(lats, 50) * 1e6), "p95_us": float(np.percentile(lats, 95) * 1e6)}
+
+    if rank != 0:
+        if world > 1:
+            td.destroy_process_group()
+        return
+
+    line = {"metric": "candidate-model RK4 steps/s (look-back window)", "value": value, "unit": "steps/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
+            "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "gpu_launches": args.steps * 3, "clocks": clocks, "roofline": roofline}
+    if e2e:
+        line["e2e"] = e2e
+        line["tick_latency"] = lat
+    if cpu_base:
+        line["cpu_baseline"] = cpu_base
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        td.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,175 @@
+/* llampc_b200.h -- C ABI of the B200-native LLA-MPC look-back / look-ahead hot path.
+ *
+ * The reference (tianhao-stan-wu/LLA-MPC) is 100 % Python and has no FFI of its own; the boundary it
+ * exposes for this path is a set of Python call signatures.  Each entry point below names the
+ * reference interface it replaces (paths relative to the reference root).  The Python host in
+ * lla-mpc_b200/ binds these symbols with ctypes (see INTEGRATION.md for the reference-side stub).
+ *
+ * Conventions
+ *   - plain pointers and sizes only; pointers are DEVICE pointers unless the name ends in _h;
+ *   - the caller owns every buffer, nothing is allocated or freed inside the library;
+ *   - every device entry point is asynchronous on `stream` (a cudaStream_t passed as void*);
+ *   - return value: 0 = OK, > 0 = cudaError_t of the failing runtime call, < 0 = argument error
+ *     (LLAMPC_E_*); the library never throws and keeps no global state.
+ */
+#ifndef LLAMPC_B200_H
+#define LLAMPC_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLAMPC_ABI_VERSION 1
+
+#define LLAMPC_E_ARG   (-1)  /* null pointer / non-positive size / size not supported       */
+#define LLAMPC_E_ALIGN (-2)  /* pointer or stride not 16-byte aligned                        */
+#define LLAMPC_E_RANGE (-3)  /* W, K, H ... outside the compiled limits                      */
+
+#define LLAMPC_NPARAM        14   /* lf lr mass Iz Bf Br Cf Cr Df Dr Cm1 Cm2 Cr0 Cr2 (Dynamic.__init__, llampc/models/dynamic.py:24-57) */
+#define LLAMPC_BANK_GROUPS    4   /* packed bank = 4 float4 groups per candidate                */
+#define LLAMPC_HIST_ROW      20   /* floats per history row (80 B)                              */
+#define LLAMPC_HIST64_ROW    12   /* doubles per f64 history row: x_k[6] u_k[2] x_k1[0:4]       */
+#define LLAMPC_MAX_W       1024   /* history rows staged in shared memory per CTA               */
+#define LLAMPC_MAX_K         64   /* top-K                                                      */
+#define LLAMPC_MAX_H        256   /* look-ahead horizon                                         */
+
+typedef void* llampc_stream_t;           /* cudaStream_t */
+typedef unsigned long long llampc_key_t; /* (float_bits(avg_err) << 32) | global candidate index */
+
+int llampc_abi_version(void);
+const char* llampc_error_string(int code);
+
+/* ---------------------------------------------------------------------------------------------
+ * Host-side packing (pure C, no CUDA): fp64 reference-layout data -> the fp32 device layouts.
+ * ------------------------------------------------------------------------------------------- */
+
+/* Model bank (replaces the gather of six (N,) arrays, run_nmpc_orca_llampc_rt.py:172-179, and the
+ * array-parameter Dynamic built in llampc/mpc/evaluate_models_vectorized.py:13-22).
+ * params_h[j] points to n_j doubles, n_j = N if is_array[j] else 1, in LLAMPC_NPARAM order.
+ * packed_h receives 4 groups of Npad float4 (group-major: [g][i] at float offset (g*Npad+i)*4):
+ *   g0 = Bf Cf Df Br | g1 = Cr Dr 1/mass lf | g2 = lr lf/Iz lr/Iz Cm1 | g3 = Cm2 Cr0 Cr2 0
+ * derived quantities are formed in fp64 and rounded once.  Npad >= N; rows N..Npad-1 repeat row N-1. */
+int llampc_bank_pack_h(const double* const* params_h, const int* is_array, int N, int Npad, float* packed_h);
+
+/* One history row from one measured transition (x_k, u_k) -> x_k1 (the tick body of
+ * run_nmpc_orca_llampc_rt.py:347-349 needs exactly these three vectors).  All trigonometry and the
+ * measured increments are formed in fp64 here so the fp32 kernel never subtracts O(1) numbers.
+ * lf_shared/lr_shared: the bank-wide lf, lr when geometry is not varied (else NaN): enables the
+ * candidate-invariant stage-1 slip angles.  row32_h: LLAMPC_HIST_ROW floats, row64_h (may be NULL):
+ * LLAMPC_HIST64_ROW doubles for llampc_refine_f64. */
+int llampc_hist_row_pack_h(const double* x_k, const double* u_k, const double* x_k1, double Ts,
+                           double lf_shared, double lr_shared, float* row32_h, double* row64_h);
+
+/* ---------------------------------------------------------------------------------------------
+ * K1  look-back window: for every candidate, W one-step RK4 predictions re-anchored at the measured
+ * states, mean squared error over (x, y, psi, vx) and over the window, fused block arg-min.
+ * Replaces evaluate_models_vectorized (llampc/mpc/evaluate_models_vectorized.py:4-23) called once per
+ * tick + errors / error_windows / mean / argmin of run_nmpc_orca_llampc_rt.py:349-358.
+ *   bank      packed bank (llampc_bank_pack_h layout) on the device, 16-byte aligned
+ *   hist      [n_vehicles][hist_stride_rows][LLAMPC_HIST_ROW] floats; the first W rows of each vehicle are used
+ *   avg_err   [n_vehicles][N] or NULL
+ *   best_key  [n_vehicles]; MUST be preset to ~0ull by the caller (llampc_fill_keys); receives the
+ *             min over candidates of (float_bits(avg_err)<<32 | idx_offset+i)  (np.argmin tie-break)
+ *   geom_shared  non-zero: rows carry valid stage-1 slip angles (lf, lr identical for all candidates)
+ *   split     window splits per candidate inside a CTA (1,2,4,8) or 0 = choose from N, W
+ * ------------------------------------------------------------------------------------------- */
+int llampc_lookback_window_f32(const float* bank, int N, int Npad,
+                               const float* hist, int W, int n_vehicles, int hist_stride_rows, double Ts,
+                               float* avg_err, llampc_key_t* best_key, int idx_offset,
+                               int geom_shared, int split, llampc_stream_t stream);
+
+int llampc_fill_keys(llampc_key_t* keys, int n, llampc_stream_t stream);   /* keys[i] = ~0ull */
+
+/* K4  top-K (replaces avg_errors.argsort()[:K], run_nmpc_orca_llampc_rt.py:360).
+ *   err [N] -> out_keys [K] ascending packed keys.  scratch: [n_ctas*K] keys with
+ *   n_ctas = llampc_topk_scratch_ctas(N); counter: one unsigned, zero before the FIRST call
+ *   (the kernel resets it). */
+int llampc_topk_scratch_ctas(int N);
+int llampc_topk_f32(const float* err, int N, int idx_offset, int K,
+                    llampc_key_t* scratch, unsigned* counter, llampc_key_t* out_keys, llampc_stream_t stream);
+
+/* fp64 re-score of a few finalists (same arithmetic as the reference, IEEE double on the device):
+ *   bank64 [LLAMPC_NPARAM][N] doubles, hist64 [W][LLAMPC_HIST64_ROW], keys [n_fin] packed keys whose low
+ *   32 bits - idx_offset select the candidates; out_err64 [n_fin] receives the window-mean error. */
+int llampc_refine_f64(const double* bank64, int N, const double* hist64, int W, double Ts,
+                      const llampc_key_t* keys, int n_fin, int idx_offset, double* out_err64,
+                      llampc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One MPC tick of the look-back step in ONE call (the body of run_nmpc_orca_llampc_rt.py:347-360):
+ * upload the newest history row into ring slot `slot`, K1 over the whole window, K4 top-Kt with
+ * Kt = max(K, n_refine), optional fp64 re-score of the Kt finalists, results to pinned host memory.
+ * Every buffer is caller-owned; the struct only carries pointers (device unless suffixed _h).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct llampc_tick {
+    const float* bank; int N; int Npad;
+    float* hist;                    /* device ring [W][LLAMPC_HIST_ROW]                                  */
+    const float* row32_h;           /* pinned host row to upload into `slot`, or NULL (ring already set) */
+    int slot; int W; double Ts;
+    int geom_shared; int split; int idx_offset;
+    float* avg_err;                 /* [N]                                                               */
+    llampc_key_t* best_key;         /* [1]                                                               */
+    int K;                          /* top-K wanted by the caller (rt.py:360 uses 10)                    */
+    int n_refine;                   /* 0 = no fp64 re-score                                              */
+    llampc_key_t* topk_scratch; unsigned* topk_counter;
+    llampc_key_t* topk_keys;        /* [Kt] ascending by fp32 score                                      */
+    const double* bank64;           /* [LLAMPC_NPARAM][N] (n_refine > 0)                                 */
+    double* hist64;                 /* device ring [W][LLAMPC_HIST64_ROW] (n_refine > 0)                 */
+    const double* row64_h;          /* pinned host row for hist64, or NULL                               */
+    double* refine_err64;           /* [Kt]                                                              */
+    llampc_key_t* out_keys_h;       /* pinned [1 + Kt]: best_key, then topk_keys                         */
+    double* out_err64_h;            /* pinned [Kt] (n_refine > 0)                                        */
+    int sync;                       /* non-zero: cudaStreamSynchronize before returning                  */
+} llampc_tick_t;
+
+int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * One RK4 step for N (model, state, input) triples: Model._integrate_batch (llampc/models/model.py:32-40)
+ * -> odeintRK4_batch (llampc/utils/rk6.py:50-68) -> Dynamic._diffequation_batch (dynamic.py:98-154).
+ *   x64 [N][6] (or one row if x_shared), u64 [N][2] (or one row if u_shared), out64 [N][out_cols] with
+ *   out_cols = 6 (_integrate_batch) or 4 (evaluate_models_vectorized returns [:,0:4]).
+ *   The increment is integrated in fp32, the final x0 + increment sum is formed in fp64.
+ * ------------------------------------------------------------------------------------------- */
+int llampc_rk4_batch_f32(const float* bank, int N, int Npad, const double* x64, int x_shared,
+                         const double* u64, int u_shared, double Ts, double* out64, int out_cols,
+                         llampc_stream_t stream);
+
+/* Right-hand side only: Dynamic._diffequation_batch (dynamic.py:98-115), fp32 arithmetic, f64 in/out. */
+int llampc_rhs_batch_f32(const float* bank, int N, int Npad, const double* x64, int x_shared,
+                         const double* u64, int u_shared, double* out64, llampc_stream_t stream);
+
+/* Forces and slip angles: Dynamic.calc_forces_batch(x, u, return_slip=True) (dynamic.py:117-154).
+ * out64 [N][5] = Ffy Frx Fry alphaf alphar. */
+int llampc_forces_batch_f32(const float* bank, int N, int Npad, const double* x64, int x_shared,
+                            const double* u64, int u_shared, double* out64, llampc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * K2  look-ahead rollout: M models x K control sequences x H RK4 steps (Model._integrate_batch chained,
+ * llampc/models/model.py:32-40) scored with the NMPC objective (llampc/mpc/nmpc.py:48,66-71,111):
+ *   J = sum_{h=1..H} (p_h-xref_h)'Q(p_h-xref_h) + (p_H-xref_H)'P(p_H-xref_H) + sum_{h=0..H-1} du_h' R du_h
+ *   bank       packed bank with Mpad rows per group; model_idx [M] bank row of each model, or NULL = identity
+ *   x0         [n_x0][6] doubles (n_x0 = 1: shared start state, or M)
+ *   U          [K][H][2] floats, or [M][K][H][2] if per_model_flags & 1
+ *   xref       [H+1][2] floats (row h = reference position at step h), or [M][H+1][2] if per_model_flags & 2
+ *   uprev      [2] floats, or [M][2] if per_model_flags & 4
+ *              shared U / xref tables are fetched with 16-byte-granular bulk copies: the buffers must be
+ *              16-byte aligned and readable up to the next multiple of 16 bytes
+ *   qrp_h      HOST pointer, 6 floats = Q00 Q11 R00 R11 P00 P11
+ *   J          [M][K] floats;  best_k [M] ints (first index on ties);  x_final [M][K][6] doubles or NULL
+ * ------------------------------------------------------------------------------------------- */
+int llampc_lookahead_rollout_f32(const float* bank, int Mpad, const int* model_idx, int M,
+                                 const double* x0, int n_x0, const float* U, int K, int H,
+                                 const float* xref, const float* uprev, int per_model_flags,
+                                 const float* qrp_h, double Ts, float* J, int* best_k, double* x_final,
+                                 llampc_stream_t stream);
+
+/* K3  plant step for V independent vehicles: Model._integrate -> odeintRK6 (llampc/models/model.py:18-30,
+ * llampc/utils/rk6.py:13-28), fp64 throughout.  params64 [V][LLAMPC_NPARAM], x64 [V][6], u64 [V][2] -> out64 [V][6]. */
+int llampc_plant_rk6_f64(const double* params64, int V, const double* x64, const double* u64, double Ts,
+                         double* out64, llampc_stream_t stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLAMPC_B200_H */

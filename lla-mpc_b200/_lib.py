@@ -1,0 +1,97 @@
+"""ctypes binding of libllampc_b200.so (C ABI: include/llampc_b200.h).
+
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C lla-mpc_b200/csrc``.  There is no
+fallback of any kind: if the shared object is missing, importing a compute module raises.
+"""
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libllampc_b200.so")
+
+NPARAM = 14
+HIST_ROW = 20
+HIST64_ROW = 12
+MAX_W = 1024
+MAX_K = 64
+MAX_H = 256
+PARAM_NAMES = ("lf", "lr", "mass", "Iz", "Bf", "Br", "Cf", "Cr", "Df", "Dr", "Cm1", "Cm2", "Cr0", "Cr2")
+
+_vp, _i, _f, _d = C.c_void_p, C.c_int, C.c_float, C.c_double
+
+
+class Tick(C.Structure):
+    """llampc_tick_t"""
+    _fields_ = [("bank", _vp), ("N", _i), ("Npad", _i),
+                ("hist", _vp), ("row32_h", _vp), ("slot", _i), ("W", _i), ("Ts", _d),
+                ("geom_shared", _i), ("split", _i), ("idx_offset", _i),
+                ("avg_err", _vp), ("best_key", _vp), ("K", _i), ("n_refine", _i),
+                ("topk_scratch", _vp), ("topk_counter", _vp), ("topk_keys", _vp),
+                ("bank64", _vp), ("hist64", _vp), ("row64_h", _vp), ("refine_err64", _vp),
+                ("out_keys_h", _vp), ("out_err64_h", _vp), ("sync", _i)]
+
+
+# name -> (restype, argtypes); every symbol declared in include/llampc_b200.h
+PROTOTYPES = {
+    "llampc_abi_version": (_i, []),
+    "llampc_error_string": (C.c_char_p, [_i]),
+    "llampc_bank_pack_h": (_i, [_vp, _vp, _i, _i, _vp]),
+    "llampc_hist_row_pack_h": (_i, [_vp, _vp, _vp, _d, _d, _d, _vp, _vp]),
+    "llampc_lookback_window_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _vp, _vp, _i, _i, _i, _vp]),
+    "llampc_fill_keys": (_i, [_vp, _i, _vp]),
+    "llampc_topk_scratch_ctas": (_i, [_i]),
+    "llampc_topk_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "llampc_refine_f64": (_i, [_vp, _i, _vp, _i, _d, _vp, _i, _i, _vp, _vp]),
+    "llampc_lookback_tick": (_i, [C.POINTER(Tick), _vp]),
+    "llampc_rk4_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _d, _vp, _i, _vp]),
+    "llampc_rhs_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "llampc_forces_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
+    "llampc_lookahead_rollout_f32": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _d,
+                                          _vp, _vp, _vp, _vp]),
+    "llampc_plant_rk6_f64": (_i, [_vp, _i, _vp, _vp, _d, _vp, _vp]),
+}
+
+_lib = None
+
+
+class LlampcError(RuntimeError):
+    pass
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise LlampcError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                              "or `make -C lla-mpc_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+        handle = C.CDLL(LIB_PATH)
+        for name, (res, args) in PROTOTYPES.items():
+            fn = getattr(handle, name)           # AttributeError if the library lacks a declared symbol
+            fn.restype, fn.argtypes = res, args
+        if handle.llampc_abi_version() != 1:
+            raise LlampcError("libllampc_b200.so ABI version mismatch")
+        _lib = handle
+    return _lib
+
+
+def check(rc, what=""):
+    if rc != 0:
+        msg = lib().llampc_error_string(rc).decode()
+        if rc > 0:
+            try:
+                import torch
+                torch.cuda.synchronize()
+            except Exception as e:                # surface the asynchronous CUDA error text too
+                msg += " [%s]" % e
+        raise LlampcError("%s failed: rc=%d %s" % (what or "llampc call", rc, msg))
+
+
+def require_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        raise LlampcError("llampc_b200 needs a CUDA device (sm_100a); no CPU fallback exists")
+    return torch
+
+
+def stream_ptr(torch):
+    return torch.cuda.current_stream().cuda_stream

@@ -1,0 +1,79 @@
+"""Model bank on the device: the 14 Dynamic parameters of N candidate models, packed for the kernels.
+
+Replaces the reference's list of N ``Dynamic`` objects plus the six gathered (N,) arrays
+(run_nmpc_orca_llampc_rt.py:145-179) and the array-parameter ``Dynamic`` that
+``evaluate_models_vectorized`` rebuilds every tick (evaluate_models_vectorized.py:13-22).
+"""
+import ctypes as C
+
+import numpy as np
+
+from . import _lib
+
+PARAM_NAMES = _lib.PARAM_NAMES
+
+
+def _as_param(v):
+    a = np.asarray(v, dtype=np.float64)
+    if a.ndim > 1:
+        raise ValueError("model parameters must be scalars or 1-D arrays")
+    return np.ascontiguousarray(a) if a.ndim == 1 else a.copy()      # ascontiguousarray would promote 0-d to 1-d
+
+
+class ModelBank:
+    """params: dict with the 14 keys of ``Dynamic.__init__`` (scalars broadcast, arrays are per candidate).
+    Extra keys (limits etc.) are ignored, like ``Dynamic(**ORCA())`` ignores them."""
+
+    def __init__(self, params, device=None):
+        torch = _lib.require_cuda()
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        missing = [k for k in PARAM_NAMES if k not in params or params[k] is None]
+        if missing:
+            raise ValueError("model bank needs all Pacejka parameters; missing %s "
+                             "(the linear-tyre 'approx' branch of Dynamic is not on the LLA-MPC path)" % missing)
+        self.params = {k: _as_param(params[k]) for k in PARAM_NAMES}
+        sizes = {a.shape[0] for a in self.params.values() if a.ndim == 1}
+        if len(sizes) > 1:
+            raise ValueError("per-candidate parameter arrays differ in length: %s" % sorted(sizes))
+        self.N = sizes.pop() if sizes else 1
+        self.Npad = (self.N + 127) // 128 * 128
+        self.geom_shared = self.params["lf"].ndim == 0 and self.params["lr"].ndim == 0
+        self.lf_shared = float(self.params["lf"]) if self.geom_shared else float("nan")
+        self.lr_shared = float(self.params["lr"]) if self.geom_shared else float("nan")
+
+        ptrs = (C.c_void_p * _lib.NPARAM)(*[self.params[k].ctypes.data for k in PARAM_NAMES])
+        flags = (C.c_int * _lib.NPARAM)(*[int(self.params[k].ndim == 1) for k in PARAM_NAMES])
+        packed_h = torch.empty((4, self.Npad, 4), dtype=torch.float32, pin_memory=True)
+        _lib.check(_lib.lib().llampc_bank_pack_h(C.cast(ptrs, C.c_void_p), C.cast(flags, C.c_void_p), self.N, self.Npad,
+                                                 packed_h.data_ptr()), "llampc_bank_pack_h")
+        self.packed = packed_h.to(self.device, non_blocking=False)
+        self._bank64 = None
+
+    @property
+    def bank64(self):
+        """[14][N] doubles on the device (fp64 finalist re-score)."""
+        if self._bank64 is None:
+            torch = _lib.require_cuda()
+            full = np.stack([np.broadcast_to(self.params[k], (self.N,)) for k in PARAM_NAMES])
+            self._bank64 = torch.from_numpy(np.ascontiguousarray(full)).to(self.device)
+        return self._bank64
+
+    def param(self, name, idx):
+        a = self.params[name]
+        return a[idx] if a.ndim == 1 else np.broadcast_to(a, np.shape(idx)).copy()
+
+    def shard(self, rank, world):
+        """Contiguous candidate slice [lo, hi) of rank `rank` out of `world`."""
+        per = (self.N + world - 1) // world
+        lo = min(rank * per, self.N)
+        hi = min(lo + per, self.N)
+        return lo, hi
+
+
+def shard_params(params, lo, hi):
+    """Slice every per-candidate array of a parameter dict to [lo, hi)."""
+    out = {}
+    for k in PARAM_NAMES:
+        a = np.asarray(params[k], dtype=np.float64)
+        out[k] = a[lo:hi] if a.ndim == 1 else a
+    return out

@@ -1,0 +1,156 @@
+// K2 look-ahead rollout (M models x K control sequences x H RK4 steps + NMPC cost) and K3 plant step.
+//
+// Integrator: Model._integrate_batch chained H times (llampc/models/model.py:32-40, llampc/utils/rk6.py:50-68);
+// cost: llampc/mpc/nmpc.py:48,66-71,111 with the weights of run_nmpc_orca_llampc_rt.py:60-62;
+// plant: Model._integrate -> odeintRK6 (model.py:18-30, rk6.py:13-28).
+#include "llampc_common.cuh"
+#include "llampc_model.cuh"
+#include "llampc_model_f64.cuh"
+
+namespace llampc {
+
+constexpr int LA_THREADS = 128;
+constexpr int LA_WARPS = LA_THREADS / 32;
+
+// One warp per model, lanes over control sequences (K = 32 -> one sequence per lane, the per-model arg-min
+// is a warp shuffle).  Shared control table [K][H][2] and the reference path [H+1][2] are staged once per
+// CTA with TMA bulk copies.  Positions are integrated relative to the start position so the fp32 state
+// never carries the O(1) track coordinate.
+__global__ void __launch_bounds__(LA_THREADS)
+lookahead_kernel(const float4* __restrict__ bank, int Mpad, const int* __restrict__ model_idx, int M,
+                 const double* __restrict__ x0, int n_x0, const float* __restrict__ U, int K, int H,
+                 const float* __restrict__ xref, const float* __restrict__ uprev, int per_model,
+                 float q0, float q1, float r0, float r1, float p0, float p1, float h,
+                 float* __restrict__ J, int* __restrict__ best_k, double* __restrict__ x_final) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    const bool u_pm = per_model & 1, xref_pm = per_model & 2, uprev_pm = per_model & 4;
+    const unsigned u_bytes = u_pm ? 0u : (unsigned)(K * H * 8);
+    const unsigned u_bytes_pad = (u_bytes + 15u) & ~15u;
+    const unsigned xr_bytes = xref_pm ? 0u : (unsigned)(((H + 1) * 8 + 15) & ~15);
+    float2* sU = reinterpret_cast<float2*>(smem_raw);
+    float2* sXr = reinterpret_cast<float2*>(smem_raw + u_bytes_pad);
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&mbar, u_bytes_pad + xr_bytes);
+        if (u_bytes_pad) tma_bulk_g2s(sU, U, u_bytes_pad, &mbar);       // caller pads the table to 16 B
+        if (xr_bytes) tma_bulk_g2s(sXr, xref, xr_bytes, &mbar);
+    }
+    const int m = blockIdx.x * LA_WARPS + warp;
+    const bool m_ok = m < M;
+    const int mm = m_ok ? m : M - 1;
+    const int bi = model_idx ? model_idx[mm] : mm;
+    const Cand p = load_cand(bank, Mpad, bi);
+    const double* xs = x0 + (n_x0 > 1 ? (size_t)mm * 6 : 0);
+    const double X0 = xs[0], Y0 = xs[1], PSI0 = xs[2];
+    double s0d, c0d;
+    sincos(PSI0, &s0d, &c0d);
+    const float2 up = uprev_pm ? reinterpret_cast<const float2*>(uprev)[mm] : reinterpret_cast<const float2*>(uprev)[0];
+    const float2* Ug = reinterpret_cast<const float2*>(U) + (u_pm ? (size_t)mm * K * H : 0);
+    const float2* Xg = reinterpret_cast<const float2*>(xref) + (xref_pm ? (size_t)mm * (H + 1) : 0);
+    mbar_wait(&mbar, 0);
+    if (!m_ok) return;
+
+    u64 best = ~0ull;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int k = k0 + lane;
+        const bool k_ok = k < K;
+        const int kk = k_ok ? k : K - 1;
+        float X = 0.0f, Y = 0.0f, dpsi = 0.0f;
+        float s = (float)s0d, c = (float)c0d;
+        float vx = (float)xs[3], vy = (float)xs[4], w = (float)xs[5];
+        float2 uq = up;
+        float Jt = 0.0f, Ja = 0.0f, ex = 0.0f, ey = 0.0f;
+        for (int hh = 0; hh < H; ++hh) {
+            const float2 u = u_pm ? __ldg(Ug + (size_t)kk * H + hh) : sU[kk * H + hh];
+            const float du0 = u.x - uq.x, du1 = u.y - uq.y;       // nmpc.py:66-69 (du_0 = u_0 - uprev)
+            Ja = fmaf(r0 * du0, du0, fmaf(r1 * du1, du1, Ja));
+            uq = u;
+            Ctl ctl;
+            ctl.pwm = u.x; ctl.delta = u.y;
+            sincos_small(u.y, ctl.sd, ctl.cd);
+            float inc[6];
+            rk4_increment<false>(p, ctl, s, c, vx, vy, w, h, inc);
+            X += inc[0]; Y += inc[1]; dpsi += inc[2];
+            vx += inc[3]; vy += inc[4]; w += inc[5];
+            float sr, cr;
+            sincos_small(inc[2], sr, cr);
+            const float sn = fmaf(s, cr, c * sr), cn = fmaf(c, cr, -s * sr);
+            s = sn; c = cn;
+            const float2 xr = xref_pm ? __ldg(Xg + hh + 1) : sXr[hh + 1];
+            ex = X - (float)((double)xr.x - X0);
+            ey = Y - (float)((double)xr.y - Y0);
+            Jt = fmaf(q0 * ex, ex, fmaf(q1 * ey, ey, Jt));        // nmpc.py:70-71
+        }
+        Jt = fmaf(p0 * ex, ex, fmaf(p1 * ey, ey, Jt));            // terminal cost nmpc.py:48
+        const float Jk = Jt + Ja;
+        if (k_ok) {
+            J[(size_t)m * K + k] = Jk;
+            best = u64_min(best, pack_key(Jk, (unsigned)k));
+            if (x_final) {
+                double* o = x_final + ((size_t)m * K + k) * 6;
+                o[0] = X0 + (double)X; o[1] = Y0 + (double)Y; o[2] = PSI0 + (double)dpsi;
+                o[3] = (double)vx; o[4] = (double)vy; o[5] = (double)w;
+            }
+        }
+    }
+    best = warp_min_u64(best);
+    if (lane == 0) best_k[m] = (int)(best & 0xffffffffull);
+}
+
+__global__ void __launch_bounds__(128)
+plant_rk6_kernel(const double* __restrict__ params, int V, const double* __restrict__ x, const double* __restrict__ u,
+                 double h, double* __restrict__ out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    Params64 p;
+    double* pp = reinterpret_cast<double*>(&p);
+#pragma unroll
+    for (int j = 0; j < LLAMPC_NPARAM; ++j) pp[j] = params[(size_t)v * LLAMPC_NPARAM + j];
+    double y0[6], y1[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) y0[i] = x[(size_t)v * 6 + i];
+    rk6_step64(p, y0, u[(size_t)v * 2], u[(size_t)v * 2 + 1], h, y1);
+#pragma unroll
+    for (int i = 0; i < 6; ++i) out[(size_t)v * 6 + i] = y1[i];
+}
+
+}  // namespace llampc
+
+using namespace llampc;
+
+extern "C" int llampc_lookahead_rollout_f32(const float* bank, int Mpad, const int* model_idx, int M,
+                                            const double* x0, int n_x0, const float* U, int K, int H,
+                                            const float* xref, const float* uprev, int per_model_flags,
+                                            const float* qrp_h, double Ts, float* J, int* best_k, double* x_final,
+                                            llampc_stream_t stream) {
+    if (!bank || !x0 || !U || !xref || !uprev || !qrp_h || !J || !best_k || M <= 0 || K <= 0 || H <= 0) return LLAMPC_E_ARG;
+    if (n_x0 != 1 && n_x0 != M) return LLAMPC_E_ARG;
+    if (H > LLAMPC_MAX_H) return LLAMPC_E_RANGE;
+    if ((reinterpret_cast<uintptr_t>(bank) | reinterpret_cast<uintptr_t>(U) | reinterpret_cast<uintptr_t>(xref)) & 15u)
+        return LLAMPC_E_ALIGN;
+    const bool u_pm = per_model_flags & 1, xref_pm = per_model_flags & 2;
+    size_t smem = (u_pm ? 0 : (((size_t)K * H * 8 + 15) & ~(size_t)15)) + (xref_pm ? 0 : ((((size_t)H + 1) * 8 + 15) & ~(size_t)15));
+    if (smem > 96 * 1024) return LLAMPC_E_RANGE;
+    if (smem > 48 * 1024) {
+        static bool raised = false;
+        if (!raised) {
+            LLAMPC_CUDA_TRY(cudaFuncSetAttribute(lookahead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
+            raised = true;
+        }
+    }
+    lookahead_kernel<<<(M + LA_WARPS - 1) / LA_WARPS, LA_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(bank), Mpad, model_idx, M, x0, n_x0, U, K, H, xref, uprev, per_model_flags,
+        qrp_h[0], qrp_h[1], qrp_h[2], qrp_h[3], qrp_h[4], qrp_h[5], (float)Ts, J, best_k, x_final);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_plant_rk6_f64(const double* params64, int V, const double* x64, const double* u64v, double Ts,
+                                    double* out64, llampc_stream_t stream) {
+    if (!params64 || !x64 || !u64v || !out64 || V <= 0) return LLAMPC_E_ARG;
+    plant_rk6_kernel<<<(V + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(params64, V, x64, u64v, Ts, out64);
+    return (int)cudaGetLastError();
+}

@@ -1,0 +1,394 @@
+// K1 look-back window kernel, K4 top-K, fp64 finalist re-score, one-step batch kernels.  sm_100a.
+//
+// Reference behaviour being replaced: evaluate_models_vectorized (llampc/mpc/evaluate_models_vectorized.py:4-23)
+// + the scoring / selection block of run_nmpc_orca_llampc_rt.py:347-360.
+#include "llampc_common.cuh"
+#include "llampc_model.cuh"
+#include "llampc_model_f64.cuh"
+
+namespace llampc {
+
+constexpr int LB_THREADS = 128;
+constexpr int NUM_SMS = 148;
+
+// ---------------------------------------------------------------------------------------------------
+// K1.  grid = (ceil(N / (128/SY)), n_vehicles); block = 128 threads = (128/SY candidates) x (SY window splits).
+// The W history rows (80 B each) are staged once per CTA with one TMA bulk copy; every warp then reads
+// the same row at the same time (shared-memory broadcast).  Thread (c, sy) integrates window rows
+// sy, sy+SY, ...; partial sums are combined in a fixed order so the result is run-to-run deterministic.
+// ---------------------------------------------------------------------------------------------------
+template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
+__global__ void __launch_bounds__(LB_THREADS)
+lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
+                       long hist_stride_floats, StepSize z, float* __restrict__ avg_err, u64* __restrict__ best_key,
+                       int idx_offset) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ u64 skeys[LB_THREADS / 32 + 1];
+    float4* srow = reinterpret_cast<float4*>(smem_raw);
+    float* spart = reinterpret_cast<float*>(smem_raw + (size_t)W * (LLAMPC_HIST_ROW * 4));
+
+    constexpr int CPB = LB_THREADS / SY;
+    const int tid = threadIdx.x;
+    const int v = blockIdx.y;
+    const unsigned bytes = (unsigned)W * (LLAMPC_HIST_ROW * 4);
+
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&mbar, bytes);
+        tma_bulk_g2s(srow, hist + (size_t)v * hist_stride_floats, bytes, &mbar);
+    }
+
+    const int c = tid % CPB, sy = tid / CPB;
+    const int cand = blockIdx.x * CPB + c;
+    const bool valid = cand < N;
+    const Cand p = load_cand(bank, Npad, valid ? cand : N - 1);   // overlaps the bulk copy
+
+    mbar_wait(&mbar, 0);
+
+    float acc = 0.0f;
+    for (int w = sy; w < W; w += SY) {
+        HistRow r;
+        r.q0 = srow[w * 5 + 0];
+        r.q1 = srow[w * 5 + 1];
+        r.q2 = srow[w * 5 + 2];
+        r.q3 = srow[w * 5 + 3];
+        r.q4 = srow[w * 5 + 4];
+        acc += lookback_step<GEOM_SHARED, MUFU_SIN>(p, r, z);
+    }
+
+    if (SY > 1) {
+        spart[sy * CPB + c] = acc;
+        __syncthreads();
+        if (sy == 0) {
+#pragma unroll
+            for (int j = 1; j < SY; ++j) acc += spart[j * CPB + c];
+        }
+    }
+    // errors = mean over the 4 scored states (rt.py:349); avg = mean over the window (rt.py:357)
+    const float err = acc * (0.25f / (float)W);
+    u64 key = ~0ull;
+    if (sy == 0 && valid) {
+        if (avg_err) avg_err[(size_t)v * N + cand] = err;
+        key = pack_key(err, (unsigned)(idx_offset + cand));
+    }
+    key = block_min_u64<LB_THREADS / 32>(key, skeys);
+    if (tid == 0 && key != ~0ull) atomicMin(best_key + v, key);
+}
+
+__global__ void fill_keys_kernel(u64* keys, int n) {
+    int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) keys[i] = ~0ull;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4 top-K.  Every CTA extracts the K smallest keys of its slice by K rounds of "block-min of the keys
+// strictly above the previous winner" (keys are unique: the low word is the index); the last CTA to
+// finish (atomic ticket) merges the per-CTA lists the same way.  Ascending output.
+// ---------------------------------------------------------------------------------------------------
+constexpr int TK_THREADS = 256;
+
+template <class KeyAt>
+__device__ __forceinline__ void select_k_smallest(KeyAt key_at, int n_elems, int K, u64* out, u64* sbuf) {
+    // thread-local minimum over its strided elements that are > lower (or all of them on the first round)
+    auto scan = [&](bool first, u64 lower) {
+        u64 m = ~0ull;
+        for (int e = threadIdx.x; e < n_elems; e += TK_THREADS) {
+            u64 k = key_at(e);
+            if ((first || k > lower) && k < m) m = k;
+        }
+        return m;
+    };
+    u64 mine = scan(true, 0);
+    for (int r = 0; r < K; ++r) {
+        u64 sel = block_min_u64<TK_THREADS / 32>(mine, sbuf);
+        if (threadIdx.x == 0) out[r] = sel;
+        if (sel == ~0ull) continue;               // fewer than K elements: pad with ~0
+        if (mine == sel) mine = scan(false, sel);
+    }
+}
+
+__global__ void __launch_bounds__(TK_THREADS)
+topk_kernel(const float* __restrict__ err, int N, int idx_offset, int K, int per_cta, u64* __restrict__ scratch,
+            unsigned* __restrict__ counter, u64* __restrict__ out) {
+    __shared__ u64 sbuf[TK_THREADS / 32 + 1];
+    __shared__ bool is_last;
+    const int base = blockIdx.x * per_cta;
+    const int n = min(per_cta, N - base);
+    select_k_smallest(
+        [&](int e) { return pack_key(__ldg(err + base + e), (unsigned)(idx_offset + base + e)); }, n, K,
+        scratch + (size_t)blockIdx.x * K, sbuf);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned ticket = atomicAdd(counter, 1u);
+        is_last = (ticket == gridDim.x - 1);
+    }
+    __syncthreads();
+    if (!is_last) return;
+    __threadfence();
+    const int total = gridDim.x * K;
+    select_k_smallest([&](int e) { return __ldcg(scratch + e); }, total, K, out, sbuf);
+    if (threadIdx.x == 0) *counter = 0;           // ready for the next launch on the same stream
+}
+
+// ---------------------------------------------------------------------------------------------------
+// fp64 re-score of finalists: one warp per finalist, lanes stride over the window.
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+refine_f64_kernel(const double* __restrict__ bank64, int N, const double* __restrict__ hist64, int W, double h,
+                  const u64* __restrict__ keys, int n_fin, int idx_offset, double* __restrict__ out) {
+    const int f = blockIdx.x * 4 + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
+    if (f >= n_fin) return;
+    const long long ci = (long long)(unsigned)(keys[f] & 0xffffffffull) - idx_offset;
+    if (ci < 0 || ci >= N) {                       // padded key (~0) or foreign shard
+        if (lane == 0) out[f] = __longlong_as_double(0x7ff8000000000000ll);
+        return;
+    }
+    Params64 p;
+    double* pp = reinterpret_cast<double*>(&p);
+#pragma unroll
+    for (int j = 0; j < LLAMPC_NPARAM; ++j) pp[j] = bank64[(size_t)j * N + ci];
+    double acc = 0.0;
+    for (int w = lane; w < W; w += 32) {
+        const double* r = hist64 + (size_t)w * LLAMPC_HIST64_ROW;
+        double y0[6], y1[6];
+#pragma unroll
+        for (int i = 0; i < 6; ++i) y0[i] = r[i];
+        rk4_step64(p, y0, r[6], r[7], h, y1);
+        double e = 0.0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { double d = y1[i] - r[8 + i]; e += d * d; }
+        acc += e / 4;
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    if (lane == 0) out[f] = acc / W;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// One RK4 step / one RHS evaluation for N (model, state, input) triples, f64 in/out, fp32 increments.
+// ---------------------------------------------------------------------------------------------------
+template <int MODE>   // 0: RK4 step, 1: right-hand side, 2: forces and slip angles
+__global__ void __launch_bounds__(128)
+onestep_kernel(const float4* __restrict__ bank, int N, int Npad, const double* __restrict__ x64, int x_shared,
+               const double* __restrict__ u64v, int u_shared, float h, double* __restrict__ out, int out_cols) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= N) return;
+    const Cand p = load_cand(bank, Npad, i);
+    const double* x = x64 + (x_shared ? 0 : (size_t)i * 6);
+    const double* u = u64v + (u_shared ? 0 : (size_t)i * 2);
+    double s0d, c0d, sdd, cdd;
+    sincos(x[2], &s0d, &c0d);
+    sincos(u[1], &sdd, &cdd);
+    Ctl ctl;
+    ctl.pwm = (float)u[0]; ctl.delta = (float)u[1]; ctl.sd = (float)sdd; ctl.cd = (float)cdd;
+    const float s0 = (float)s0d, c0 = (float)c0d, vx = (float)x[3], vy = (float)x[4], w = (float)x[5];
+    if (MODE == 2) {                               // calc_forces_batch(..., return_slip=True), dynamic.py:117-154
+        float af, ar;
+        slip_angles(p, ctl.delta, vx, vy, w, af, ar);
+        double* o = out + (size_t)i * 5;
+        o[0] = (double)pacejka<false>(p.Bf, p.Cf, p.Df, af);
+        o[1] = (double)drive_force(p, ctl.pwm, vx);
+        o[2] = (double)pacejka<false>(p.Br, p.Cr, p.Dr, ar);
+        o[3] = (double)af; o[4] = (double)ar;
+    } else if (MODE == 1) {
+        Deriv a = accel<false>(p, ctl, vx, vy, w);
+        double* o = out + (size_t)i * 6;
+        o[0] = (double)fmaf(vx, c0, -vy * s0);
+        o[1] = (double)fmaf(vx, s0, vy * c0);
+        o[2] = x[5];
+        o[3] = (double)a.vx; o[4] = (double)a.vy; o[5] = (double)a.w;
+    } else {
+        float inc[6];
+        rk4_increment<false>(p, ctl, s0, c0, vx, vy, w, h, inc);
+        double* o = out + (size_t)i * out_cols;
+        for (int j = 0; j < out_cols; ++j) o[j] = x[j] + (double)inc[j];
+    }
+}
+
+}  // namespace llampc
+
+using namespace llampc;
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+static int choose_split(int N, int W) {
+    // SM time ~ (CTAs on the busiest SM) x (rows per thread) while the FMA pipe is the limiter.
+    int best = 1;
+    long best_cost = -1;
+    for (int sy = 1; sy <= 4; sy *= 2) {
+        if (sy > W) break;
+        long ctas = ((long)N * sy + LB_THREADS - 1) / LB_THREADS;
+        long cost = ((ctas + NUM_SMS - 1) / NUM_SMS) * ((W + sy - 1) / sy);
+        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sy; }
+    }
+    return best;
+}
+
+static StepSize make_step(double Ts) {
+    StepSize z;
+    z.h = (float)Ts;
+    z.hh = (float)(0.5 * Ts);
+    z.h6 = (float)(Ts / 6.0);
+    z.h6_lo = (float)(Ts / 6.0 - (double)z.h6);
+    z.hh6 = (float)(Ts * Ts / 6.0);
+    z.hh6_lo = (float)(Ts * Ts / 6.0 - (double)z.hh6);
+    return z;
+}
+
+template <int SY, bool GEOM, bool MUFU>
+static int launch_lookback(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
+                           int hist_stride_rows, double Ts, float* avg_err, u64* best_key, int idx_offset,
+                           cudaStream_t st) {
+    auto kern = lookback_window_kernel<SY, GEOM, MUFU>;
+    const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 : 0);
+    if (smem > 48 * 1024) {
+        static bool raised = false;              // idempotent attribute, benign if two threads race
+        if (!raised) {
+            LLAMPC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+            raised = true;
+        }
+    }
+    constexpr int CPB = LB_THREADS / SY;
+    dim3 grid((N + CPB - 1) / CPB, n_vehicles);
+    kern<<<grid, LB_THREADS, smem, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, hist, W,
+                                         (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key, idx_offset);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_lookback_window_f32(const float* bank, int N, int Npad, const float* hist, int W,
+                                          int n_vehicles, int hist_stride_rows, double Ts, float* avg_err,
+                                          llampc_key_t* best_key, int idx_offset, int geom_shared, int split,
+                                          llampc_stream_t stream) {
+    if (!bank || !hist || !best_key || N <= 0 || Npad < N || n_vehicles <= 0 || hist_stride_rows < W) return LLAMPC_E_ARG;
+    if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
+    if (!aligned16(bank) || !aligned16(hist) || (hist_stride_rows * LLAMPC_HIST_ROW * 4) % 16) return LLAMPC_E_ALIGN;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    int mufu = 0;
+    if (split >= 16) { mufu = 1; split -= 16; }   // experiment switch: MUFU.SIN tyre sine (not used by the host package)
+    if (split == 0) split = choose_split(N, W);
+    if (split > W) split = 1;
+#define LB_CASE(SYV)                                                                                                  \
+    case SYV:                                                                                                         \
+        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, idx_offset, st)   \
+                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, idx_offset, st); \
+        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, idx_offset, st)            \
+                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, idx_offset, st);
+    switch (split) {
+        LB_CASE(1)
+        LB_CASE(2)
+        LB_CASE(4)
+        default: return LLAMPC_E_ARG;
+    }
+#undef LB_CASE
+}
+
+extern "C" int llampc_fill_keys(llampc_key_t* keys, int n, llampc_stream_t stream) {
+    if (!keys || n <= 0) return LLAMPC_E_ARG;
+    fill_keys_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(keys, n);
+    return (int)cudaGetLastError();
+}
+
+static int topk_per_cta(int N) {
+    int per = 4096;
+    while ((long)((N + per - 1) / per) > 256) per *= 2;      // at most 256 CTAs -> the merge sees <= 256*K keys
+    return per;
+}
+
+extern "C" int llampc_topk_scratch_ctas(int N) {
+    if (N <= 0) return LLAMPC_E_ARG;
+    int per = topk_per_cta(N);
+    return (N + per - 1) / per;
+}
+
+extern "C" int llampc_topk_f32(const float* err, int N, int idx_offset, int K, llampc_key_t* scratch,
+                               unsigned* counter, llampc_key_t* out_keys, llampc_stream_t stream) {
+    if (!err || !scratch || !counter || !out_keys || N <= 0) return LLAMPC_E_ARG;
+    if (K <= 0 || K > LLAMPC_MAX_K) return LLAMPC_E_RANGE;
+    const int per = topk_per_cta(N);
+    const int ctas = (N + per - 1) / per;
+    topk_kernel<<<ctas, TK_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(err, N, idx_offset, K, per, scratch,
+                                                                            counter, out_keys);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_refine_f64(const double* bank64, int N, const double* hist64, int W, double Ts,
+                                 const llampc_key_t* keys, int n_fin, int idx_offset, double* out_err64,
+                                 llampc_stream_t stream) {
+    if (!bank64 || !hist64 || !keys || !out_err64 || N <= 0 || W <= 0 || n_fin <= 0) return LLAMPC_E_ARG;
+    refine_f64_kernel<<<(n_fin + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(bank64, N, hist64, W, Ts, keys,
+                                                                                      n_fin, idx_offset, out_err64);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_rk4_batch_f32(const float* bank, int N, int Npad, const double* x64, int x_shared,
+                                    const double* u64v, int u_shared, double Ts, double* out64, int out_cols,
+                                    llampc_stream_t stream) {
+    if (!bank || !x64 || !u64v || !out64 || N <= 0 || Npad < N) return LLAMPC_E_ARG;
+    if (out_cols < 1 || out_cols > 6) return LLAMPC_E_RANGE;
+    if (!aligned16(bank)) return LLAMPC_E_ALIGN;
+    onestep_kernel<0><<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(bank), N, Npad, x64, x_shared, u64v, u_shared, (float)Ts, out64, out_cols);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_rhs_batch_f32(const float* bank, int N, int Npad, const double* x64, int x_shared,
+                                    const double* u64v, int u_shared, double* out64, llampc_stream_t stream) {
+    if (!bank || !x64 || !u64v || !out64 || N <= 0 || Npad < N) return LLAMPC_E_ARG;
+    if (!aligned16(bank)) return LLAMPC_E_ALIGN;
+    onestep_kernel<1><<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(bank), N, Npad, x64, x_shared, u64v, u_shared, 0.0f, out64, 6);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_forces_batch_f32(const float* bank, int N, int Npad, const double* x64, int x_shared,
+                                       const double* u64v, int u_shared, double* out64, llampc_stream_t stream) {
+    if (!bank || !x64 || !u64v || !out64 || N <= 0 || Npad < N) return LLAMPC_E_ARG;
+    if (!aligned16(bank)) return LLAMPC_E_ALIGN;
+    onestep_kernel<2><<<(N + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float4*>(bank), N, Npad, x64, x_shared, u64v, u_shared, 0.0f, out64, 5);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stream) {
+    if (!t || !t->bank || !t->hist || !t->avg_err || !t->best_key || !t->out_keys_h) return LLAMPC_E_ARG;
+    if (t->slot < 0 || t->slot >= t->W || t->K < 0 || t->n_refine < 0) return LLAMPC_E_ARG;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int Kt = t->K > t->n_refine ? t->K : t->n_refine;
+    if (Kt > LLAMPC_MAX_K) return LLAMPC_E_RANGE;
+    if (t->row32_h)
+        LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->hist + (size_t)t->slot * LLAMPC_HIST_ROW, t->row32_h,
+                                        LLAMPC_HIST_ROW * sizeof(float), cudaMemcpyHostToDevice, st));
+    if (t->n_refine > 0 && t->row64_h)
+        LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->hist64 + (size_t)t->slot * LLAMPC_HIST64_ROW, t->row64_h,
+                                        LLAMPC_HIST64_ROW * sizeof(double), cudaMemcpyHostToDevice, st));
+    int rc = llampc_fill_keys(t->best_key, 1, stream);
+    if (rc) return rc;
+    rc = llampc_lookback_window_f32(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key,
+                                    t->idx_offset, t->geom_shared, t->split, stream);
+    if (rc) return rc;
+    LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->out_keys_h, t->best_key, sizeof(llampc_key_t), cudaMemcpyDeviceToHost, st));
+    if (Kt > 0) {
+        if (!t->topk_scratch || !t->topk_counter || !t->topk_keys) return LLAMPC_E_ARG;
+        rc = llampc_topk_f32(t->avg_err, t->N, t->idx_offset, Kt, t->topk_scratch, t->topk_counter, t->topk_keys, stream);
+        if (rc) return rc;
+        LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->out_keys_h + 1, t->topk_keys, Kt * sizeof(llampc_key_t),
+                                        cudaMemcpyDeviceToHost, st));
+        if (t->n_refine > 0) {
+            if (!t->bank64 || !t->hist64 || !t->refine_err64 || !t->out_err64_h) return LLAMPC_E_ARG;
+            rc = llampc_refine_f64(t->bank64, t->N, t->hist64, t->W, t->Ts, t->topk_keys, Kt, t->idx_offset,
+                                   t->refine_err64, stream);
+            if (rc) return rc;
+            LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->out_err64_h, t->refine_err64, Kt * sizeof(double),
+                                            cudaMemcpyDeviceToHost, st));
+        }
+    }
+    if (t->sync) LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
+    return 0;
+}

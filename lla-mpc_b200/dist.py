@@ -1,0 +1,51 @@
+"""Multi-GPU exchange step of the look-back: candidates are sharded by contiguous index range, every rank
+reduces locally, and ONE small collective merges the results.
+
+NCCL has no MINLOC: the packed key (float_bits(err) << 32 | global_index) is reduced with MIN as a signed
+64-bit integer, which is exact because scores are non-negative (sign bit clear) and the low word gives
+np.argmin's first-index tie-break.  The same functions run on the gloo backend with CPU tensors (tests).
+"""
+import numpy as np
+
+
+def _backend_device(group, cuda_device):
+    import torch
+    import torch.distributed as td
+    return cuda_device if td.get_backend(group) == "nccl" else torch.device("cpu")
+
+
+def minloc_allreduce(key, group=None):
+    """key: 1-element int64 tensor holding the local packed key.  In-place MIN all-reduce; returns the
+    global key as a Python int.  One collective of 8 bytes."""
+    import torch.distributed as td
+    dev = _backend_device(group, key.device)
+    buf = key if key.device == dev else key.to(dev)
+    td.all_reduce(buf, op=td.ReduceOp.MIN, group=group)
+    if buf is not key:
+        key.copy_(buf)
+    return int(buf.item()) & 0xFFFFFFFFFFFFFFFF
+
+
+def gather_finalists(scores, idx, group, cuda_device):
+    """All-gather every rank's finalists (fp64 score, global index) in one collective of 16*Kt bytes/rank."""
+    import torch
+    import torch.distributed as td
+    world = td.get_world_size(group)
+    dev = _backend_device(group, cuda_device)
+    local = np.empty((len(idx), 2), dtype=np.int64)
+    local[:, 0] = np.asarray(scores, dtype=np.float64).view(np.int64)
+    local[:, 1] = idx
+    send = torch.from_numpy(local).to(dev)
+    recv = torch.empty((world,) + tuple(send.shape), dtype=torch.int64, device=dev)
+    if td.get_backend(group) == "nccl":
+        td.all_gather_into_tensor(recv, send, group=group)
+    else:
+        td.all_gather(list(recv.unbind(0)), send, group=group)
+    out = recv.cpu().numpy().reshape(-1, 2)
+    return out[:, 0].copy().view(np.float64), out[:, 1].copy()
+
+
+def shard_range(n, rank, world):
+    per = (n + world - 1) // world
+    lo = min(rank * per, n)
+    return lo, min(lo + per, n)

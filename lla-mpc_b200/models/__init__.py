@@ -1,0 +1,1 @@
+from .dynamic import Dynamic  # noqa: F401

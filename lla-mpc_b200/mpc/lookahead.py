@@ -1,0 +1,79 @@
+"""Look-ahead horizon rollout on the GPU: M adapted models x K sampled control sequences x H RK4 steps,
+scored with the NMPC objective.
+
+The reference has no batched rollout (its look-ahead is the IPOPT NLP); the semantics here are assembled
+from reference pieces: integrator = Model._integrate_batch chained H times
+(llampc/models/model.py:32-40), cost = the NLP objective (llampc/mpc/nmpc.py:48,66-71,111) with
+Q = diag(1,1), P = 0, R = diag(5e-3, 1) (run_nmpc_orca_llampc_rt.py:60-62), xref from ConstantSpeed
+(llampc/mpc/planner.py:12-67).
+"""
+import numpy as np
+
+from .. import _lib
+from ..bank import ModelBank
+
+
+def _pad16(a_bytes):
+    return (a_bytes + 15) // 16 * 16
+
+
+class LookAhead:
+    def __init__(self, model_params, Ts=0.02, Q=(1.0, 1.0), R=(5e-3, 1.0), P=(0.0, 0.0), device=None):
+        self.torch = _lib.require_cuda()
+        self.bank = model_params if isinstance(model_params, ModelBank) else ModelBank(model_params, device)
+        self.Ts = float(Ts)
+        self.qrp = np.array([Q[0], Q[1], R[0], R[1], P[0], P[1]], dtype=np.float32)
+
+    def _padded(self, arr):
+        """float32 device copy whose allocation extends to a multiple of 16 bytes (bulk-copy granularity)."""
+        torch = self.torch
+        flat = np.ascontiguousarray(arr, dtype=np.float32).ravel()
+        n = _pad16(flat.size * 4) // 4
+        buf = torch.zeros(n, dtype=torch.float32, device=self.bank.device)
+        buf[:flat.size].copy_(torch.from_numpy(flat))
+        return buf
+
+    def rollout(self, x0, U, xref, uprev, model_idx=None, return_final=False):
+        """x0 (6,) or (M,6); U (K,H,2) shared or (M,K,H,2); xref (2,H+1) [reference layout] or (M,2,H+1);
+        uprev (2,) or (M,2); model_idx: optional (M,) rows of the bank to use (default: every model once).
+        Returns J (M,K) float32->float64, best_k (M,), and x_final (M,K,6) if return_final."""
+        torch = self.torch
+        dev = self.bank.device
+        U = np.asarray(U)
+        M = self.bank.N if model_idx is None else len(model_idx)
+        flags = 0
+        if U.ndim == 4:
+            flags |= 1
+            if U.shape[0] != M:
+                raise ValueError("per-model U must have M rows")
+        K, H = U.shape[-3], U.shape[-2]
+        xref = np.asarray(xref, dtype=np.float64)
+        if xref.ndim == 3:
+            flags |= 2
+            xr = np.ascontiguousarray(np.swapaxes(xref, 1, 2))          # (M, H+1, 2)
+        else:
+            xr = np.ascontiguousarray(xref.T)                            # (H+1, 2)
+        if xr.shape[-2] != H + 1:
+            raise ValueError("xref must have H+1 columns")
+        uprev = np.asarray(uprev, dtype=np.float64)
+        if uprev.ndim == 2:
+            flags |= 4
+        x0 = np.ascontiguousarray(x0, dtype=np.float64)
+        n_x0 = 1 if x0.ndim == 1 else x0.shape[0]
+        x0d = torch.from_numpy(x0.reshape(n_x0, 6)).to(dev)
+        Ud, xrd, upd = self._padded(U), self._padded(xr), self._padded(uprev)
+        midx = None if model_idx is None else torch.as_tensor(np.asarray(model_idx, dtype=np.int32)).to(dev)
+        J = torch.empty((M, K), dtype=torch.float32, device=dev)
+        best = torch.empty(M, dtype=torch.int32, device=dev)
+        xf = torch.empty((M, K, 6), dtype=torch.float64, device=dev) if return_final else None
+        with torch.cuda.device(dev):
+            rc = _lib.lib().llampc_lookahead_rollout_f32(
+                self.bank.packed.data_ptr(), self.bank.Npad, None if midx is None else midx.data_ptr(), M,
+                x0d.data_ptr(), n_x0, Ud.data_ptr(), K, H, xrd.data_ptr(), upd.data_ptr(), flags,
+                self.qrp.ctypes.data, self.Ts, J.data_ptr(), best.data_ptr(),
+                None if xf is None else xf.data_ptr(), _lib.stream_ptr(torch))
+        _lib.check(rc, "llampc_lookahead_rollout_f32")
+        out = (J.cpu().numpy().astype(np.float64), best.cpu().numpy().astype(np.int64))
+        if return_final:
+            out += (xf.cpu().numpy(),)
+        return out

@@ -1,0 +1,1 @@
+from .orca import ORCA  # noqa: F401

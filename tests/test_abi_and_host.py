@@ -1,0 +1,112 @@
+"""CPU-side checks: the C-ABI library loads and exports every symbol include/llampc_b200.h declares, and the
+host packing functions (no GPU needed) produce the documented layouts."""
+import ctypes as C
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from llampc_b200 import _lib
+from oracle import llampc_oracle as orc
+
+
+def _declared_symbols():
+    text = open(os.path.join(ROOT, "include", "llampc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(llampc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.lib()
+    names = _declared_symbols()
+    assert len(names) >= 14
+    for n in names:
+        assert hasattr(lib, n), n
+        assert n in _lib.PROTOTYPES, "ctypes prototype missing for %s" % n
+    assert lib.llampc_abi_version() == 1
+    assert b"aligned" in lib.llampc_error_string(-2)
+
+
+def test_no_compute_without_gpu():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from llampc_b200.mpc import LookBack
+    with pytest.raises(_lib.LlampcError):
+        LookBack(orc.make_bank(16, 0), W=4)
+
+
+def _pack(params, N, Npad):
+    ptrs = (C.c_void_p * 14)(*[params[k].ctypes.data for k in _lib.PARAM_NAMES])
+    flags = (C.c_int * 14)(*[int(params[k].ndim == 1) for k in _lib.PARAM_NAMES])
+    out = np.zeros((4, Npad, 4), dtype=np.float32)
+    rc = _lib.lib().llampc_bank_pack_h(C.cast(ptrs, C.c_void_p), C.cast(flags, C.c_void_p), N, Npad, out.ctypes.data)
+    assert rc == 0
+    return out
+
+
+def test_bank_pack_layout():
+    bank = orc.make_bank(300, seed=4)
+    params = {k: np.array(bank[k], dtype=np.float64) for k in _lib.PARAM_NAMES}
+    out = _pack(params, 300, 384)
+    f32 = lambda a: np.asarray(a, dtype=np.float64).astype(np.float32)
+    assert np.array_equal(out[0, :300, 0], f32(bank["Bf"]))
+    assert np.array_equal(out[0, :300, 3], f32(bank["Br"]))
+    assert np.array_equal(out[1, :300, 1], f32(bank["Dr"]))
+    assert np.all(out[1, :300, 2] == np.float32(1.0 / bank["mass"]))
+    assert np.all(out[2, :300, 1] == np.float32(bank["lf"] / bank["Iz"]))
+    assert np.all(out[2, :300, 2] == np.float32(bank["lr"] / bank["Iz"]))
+    assert np.all(out[3, :300, 0] == np.float32(bank["Cm2"]))
+    # padding rows repeat the last candidate
+    assert np.array_equal(out[:, 300:, :], np.broadcast_to(out[:, 299:300, :], (4, 84, 4)))
+    assert _lib.lib().llampc_bank_pack_h(None, None, 1, 1, None) == -1
+
+
+def test_hist_row_pack(history):
+    S, U, Ts = history
+    p = orc.orca_params()
+    t = 777
+    row = np.zeros(20, dtype=np.float32)
+    r64 = np.zeros(12)
+    xk, uk, xk1 = (np.ascontiguousarray(a) for a in (S[:, t], U[:, t], S[:, t + 1]))
+    rc = _lib.lib().llampc_hist_row_pack_h(xk.ctypes.data, uk.ctypes.data, xk1.ctypes.data, Ts, p["lf"], p["lr"],
+                                           row.ctypes.data, r64.ctypes.data)
+    assert rc == 0
+    psi, vx, vy, w = xk[2:6]
+    f32 = np.float32
+    assert row[0] == f32(np.sin(psi)) and row[1] == f32(np.cos(psi))
+    assert row[2] == f32(np.sin(psi + Ts * w / 2)) and row[5] == f32(np.cos(psi + Ts * w))
+    assert row[6] == f32(vx) and row[8] == f32(w) and row[9] == f32(uk[0]) and row[11] == f32(np.sin(uk[1]))
+    xd0 = vx * np.cos(psi) - vy * np.sin(psi)
+    np.testing.assert_allclose(row[13], (xk1[0] - xk[0]) - Ts / 6 * xd0, rtol=1e-6)
+    np.testing.assert_allclose(row[15], (xk1[2] - xk[2]) - Ts * w, rtol=1e-6, atol=1e-12)
+    dvx = xk1[3] - xk[3]
+    assert float(row[16]) + float(row[17]) == pytest.approx(dvx, rel=1e-13)
+    _, _, _, af, ar = orc.calc_forces_batch(p, xk[None], uk[None], return_slip=True)
+    assert row[18] == f32(af[0]) and row[19] == f32(ar[0])
+    assert np.array_equal(r64, np.concatenate([xk, uk, xk1[:4]]))
+    # geometry not shared -> slip slots zero
+    _lib.lib().llampc_hist_row_pack_h(xk.ctypes.data, uk.ctypes.data, xk1.ctypes.data, Ts, float("nan"), float("nan"),
+                                      row.ctypes.data, None)
+    assert row[18] == 0 and row[19] == 0
+
+
+def test_orca_matches_oracle_constants():
+    from llampc_b200.params import ORCA
+    p, q = ORCA(), orc.orca_params()
+    for k in q:
+        assert p[k] == q[k]
+    assert p["max_inputs"] == [1.0, 0.35] and p["min_rates"] == [None, -5.0]
+    with pytest.raises(NotImplementedError):
+        ORCA(control="torque")
+
+
+def test_mu_estimator_matches_oracle():
+    from llampc_b200.mpc.mu_estimator import MuEstimator
+    a, b = MuEstimator(mass=0.041), orc.MuEstimatorOracle(mass=0.041)
+    rng = np.random.RandomState(0)
+    for _ in range(40):
+        dr, df = 0.17 + 0.01 * rng.randn(10), 0.19 + 0.01 * rng.randn(10)
+        assert a.update(dr, df) == b.update(dr, df)

@@ -1,0 +1,325 @@
+"""Parity of the CUDA hot path (called through the C ABI via the host package) against the CPU oracle and the
+golden vectors generated from the reference.  All tests need a B200: `pytest -m gpu`.
+
+Tolerances (BASELINE.json north_star): per-candidate errors / trajectories within 1e-4 relative of the
+reference's float64 NumPy rollout; selected candidate index exact (unless the top-two scores differ by less
+than that tolerance); fp64 re-scored finalists agree to 1e-9.
+"""
+import numpy as np
+import pytest
+
+from conftest import load_golden
+from oracle import llampc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4          # fp32 score tolerance, relative
+ABS_FLOOR = 1e-13       # scores below ~1e-9 (d ~ 3e-5, the RK4-vs-RK6 floor of a perfect model) hit the fp32 noise floor
+
+
+def _assert_scores(gpu, ref, what=""):
+    err = np.abs(gpu - ref)
+    bad = err > REL_TOL * ref + ABS_FLOOR
+    assert not bad.any(), "%s: %d scores off, worst rel %.3e" % (what, bad.sum(), (err / ref).max())
+
+
+def _window(lb, S, U, t_end):
+    ts = np.arange(t_end - lb.W + 1, t_end + 1)
+    lb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
+    return lb.evaluate()
+
+
+# ------------------------------------------------------------------------------------------- one-step boundary
+def test_evaluate_models_vectorized_dropin(history):
+    """Same call as run_nmpc_orca_llampc_rt.py:349, checked against the reference's own output (golden)."""
+    from llampc_b200.params import ORCA
+    from llampc_b200.models import Dynamic
+    from llampc_b200.mpc.evaluate_models_vectorized import evaluate_models_vectorized
+    g = load_golden("lookback_c1.npz")
+    S, U, Ts = history
+    params = ORCA(control="pwm")
+    models = [Dynamic(**params)] * 1024
+    pp = tuple(g["params"][i] for i in range(6))        # Bfs, Cfs, Dfs, Brs, Crs, Drs
+    for t in g["ticks"]:
+        t = int(t)
+        pred = evaluate_models_vectorized(models, 1024, S[:, t], U[:, t], Ts, pp)
+        ref = g["pred_%d" % t]
+        assert pred.shape == (1024, 4) and pred.dtype == np.float64
+        # one-step increments are O(0.05); 1e-4 relative on the increment, i.e. ~5e-6 absolute
+        inc_ref = ref - S[:4, t]
+        np.testing.assert_allclose(pred - S[:4, t], inc_ref, rtol=1e-4, atol=2e-7)
+        np.testing.assert_allclose(pred, ref, rtol=1e-6, atol=1e-7)
+
+
+def test_dynamic_batch_methods_all_14_params(history):
+    from llampc_b200.models import Dynamic
+    g = load_golden("vary14.npz")
+    S, U, Ts = history
+    t = int(g["tick"])
+    m = Dynamic(**{k: g["p_" + k] for k in orc.PARAM_NAMES})
+    n = 256
+    xb, ub = np.tile(S[:, t], (n, 1)), np.tile(U[:, t], (n, 1))
+    out = m._integrate_batch(xb, ub, 0, Ts)
+    np.testing.assert_allclose(out, g["rk4"], rtol=1e-6, atol=2e-7)
+    f = m._diffequation_batch(None, xb, ub)
+    np.testing.assert_allclose(f, g["f"], rtol=2e-6, atol=1e-6)
+    bank = {k: g["p_" + k] for k in orc.PARAM_NAMES}
+    forces = m.calc_forces_batch(xb, ub, return_slip=True)
+    ref = orc.calc_forces_batch(bank, xb, ub, return_slip=True)
+    for a, b in zip(forces, ref):
+        np.testing.assert_allclose(a, b, rtol=2e-6, atol=1e-7)
+
+
+def test_dynamic_kat_scalar_and_plant():
+    from llampc_b200.params import ORCA
+    from llampc_b200.models import Dynamic
+    g = load_golden("kat_nominal.npz")
+    m = Dynamic(**ORCA())
+    x, u, Ts = g["x"], g["u"], float(g["Ts"])
+    np.testing.assert_allclose(m._diffequation(None, x, u), g["f"], rtol=2e-6, atol=1e-6)
+    np.testing.assert_allclose(np.array(m.calc_forces(x, u, return_slip=True)), g["forces"], rtol=2e-6, atol=1e-8)
+    np.testing.assert_allclose(m._integrate_batch(x[None], u[None], 0, Ts)[0], g["rk4"], rtol=1e-6, atol=1e-7)
+    # plant: fp64 RK6 on the device, same operation order as the reference
+    np.testing.assert_allclose(m._integrate(x, u, 0, Ts), g["rk6"], rtol=0, atol=1e-13)
+
+
+def test_plant_sim_continuous(history):
+    from llampc_b200.params import ORCA
+    from llampc_b200.models import Dynamic
+    g = load_golden("kat_nominal.npz")
+    S, U, Ts = history
+    xs, dxs = Dynamic(**ORCA()).sim_continuous(S[:, 600], U[:, 600:605], np.arange(6) * Ts)
+    np.testing.assert_allclose(xs, g["sim_x"], rtol=0, atol=1e-12)
+    np.testing.assert_allclose(dxs, g["sim_dxdt"], rtol=5e-6, atol=5e-6)       # dxdt comes from the fp32 RHS
+
+
+# ------------------------------------------------------------------------------------------- look-back
+def test_lookback_c1_golden(history):
+    """Config C1 (1,024 candidates x 20-step window) against the reference's own avg_errors / argmin / top-10."""
+    from llampc_b200.mpc import LookBack
+    g = load_golden("lookback_c1.npz")
+    S, U, Ts = history
+    bank = orc.make_bank(1024, seed=0)
+    for refine in (0, 32):
+        lb = LookBack(bank, W=int(g["W"]), Ts=Ts, K=int(g["K"]), refine=refine)
+        for t_end in g["ticks"]:
+            t_end = int(t_end)
+            best, topk, best_err = _window(lb, S, U, t_end)
+            ref = g["avg_%d" % t_end]
+            _assert_scores(lb.avg_errors(), ref, "C1 t=%d" % t_end)
+            assert best == int(g["best_%d" % t_end])
+            assert list(topk) == list(g["topk_%d" % t_end])
+            if refine:
+                assert abs(best_err - ref[best]) <= 1e-9 * ref[best]
+
+
+def test_lookback_push_sequence_matches_reference_loop(history):
+    """Tick-by-tick replay of rt.py:347-366: no decision before the window is full, then every tick."""
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    bank = orc.make_bank(512, seed=8)
+    W, K = 10, 10
+    lb = LookBack(bank, W=W, Ts=Ts, K=K, refine=16)
+    ref = orc.LookBackOracle(bank, W, Ts, K)
+    for t in range(300, 300 + 3 * W):
+        got = lb.push(S[:, t], U[:, t], S[:, t + 1])
+        rbest, rtopk, ravg = ref.push(S[:, t], U[:, t], S[:, t + 1])
+        if rbest is None:
+            assert got == (None, None, None)
+            continue
+        assert got[0] == rbest and list(got[1]) == list(rtopk)
+        _assert_scores(lb.avg_errors(), ravg, "tick %d" % t)
+
+
+@pytest.mark.parametrize("split", [1, 2, 4])
+def test_lookback_window_splits_agree(history, split):
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    bank = orc.make_bank(777, seed=2)                     # ragged: not a multiple of the CTA tile
+    lb = LookBack(bank, W=23, Ts=Ts, K=10, refine=0, split=split)
+    best, topk, _ = _window(lb, S, U, 900)
+    ref = np.mean(orc.window_errors(bank, S, U, 900, 23, Ts), axis=1)
+    _assert_scores(lb.avg_errors(), ref, "split %d" % split)
+    rbest, rtopk = orc.select(ref, 10)
+    assert best == rbest and list(topk) == list(rtopk)
+
+
+def test_lookback_c2_full_size(history):
+    """Config C2: 65,536 candidates (6 Pacejka + mass varied) x 50-step window."""
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    var = orc.RT_VARIATION + (("mass", 0.15),)
+    bank = orc.make_bank(65536, seed=1, variation=var)
+    lb = LookBack(bank, W=50, Ts=Ts, K=10, refine=32)
+    for t_end in (600, 1600):
+        best, topk, best_err = _window(lb, S, U, t_end)
+        ref = np.mean(orc.window_errors(bank, S, U, t_end, 50, Ts), axis=1)
+        _assert_scores(lb.avg_errors(), ref, "C2 t=%d" % t_end)
+        rbest, rtopk = orc.select(ref, 10)
+        assert best == rbest and list(topk) == list(rtopk)
+        assert abs(best_err - ref[rbest]) <= 1e-9 * ref[rbest]
+
+
+def test_lookback_wide_bank_and_geometry_varied(history):
+    """sigma = 2.0 bank of plot_comp_time.py:178-192 (negative / huge B, C, D) and a bank varying all 14
+    parameters (lf, lr varied -> generic stage-1 slip path)."""
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    wide = tuple((k, 2.0) for k in ("Br", "Cr", "Dr", "Bf", "Cf", "Df"))
+    rng = np.random.RandomState(9)
+    p = orc.orca_params()
+    all14 = {k: p[k] * (1 + 0.1 * rng.randn(4096)) for k in orc.PARAM_NAMES}
+    for bank, W, t_end in ((orc.make_bank(4096, 3, variation=wide), 10, 900), (all14, 50, 1200)):
+        lb = LookBack(bank, W=W, Ts=Ts, K=10, refine=32)
+        best, topk, _ = _window(lb, S, U, t_end)
+        ref = np.mean(orc.window_errors(bank, S, U, t_end, W, Ts), axis=1)
+        _assert_scores(lb.avg_errors(), ref)
+        rbest, rtopk = orc.select(ref, 10)
+        assert best == rbest and list(topk) == list(rtopk)
+
+
+def test_lookback_edge_cases(history):
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    # single candidate, W = 1
+    one = orc.orca_params()
+    lb = LookBack(one, W=1, Ts=Ts, K=1, refine=1)
+    best, topk, err = lb.push(S[:, 600], U[:, 600], S[:, 601])
+    assert best == 0 and list(topk) == [0]
+    np.testing.assert_allclose(err, 4.6925049599691874e-11, rtol=1e-8)      # SURVEY section 4 KAT
+    # K larger than N: the surplus is dropped
+    lb = LookBack(orc.make_bank(5, 1), W=3, Ts=Ts, K=10, refine=0)
+    best, topk, _ = _window(lb, S, U, 500)
+    ref = np.mean(orc.window_errors(orc.make_bank(5, 1), S, U, 500, 3, Ts), axis=1)
+    assert best == int(np.argmin(ref))
+    assert list(topk[:5]) == list(np.argsort(ref))
+    # standstill (vx = 0, vy = 0): atan2(0, 0) = 0 like NumPy, scores stay finite
+    x0 = np.array([0.0, 0.0, 0.3, 0.0, 0.0, 0.0])
+    u0 = np.array([0.5, 0.1])
+    bank = orc.make_bank(64, 4)
+    x1 = orc.rk6_step(orc.orca_params(), x0, u0, 0, Ts)
+    lb = LookBack(bank, W=1, Ts=Ts, K=3, refine=0)
+    lb.push(x0, u0, x1)
+    ref = orc.onestep_errors(bank, x0, u0, x1, Ts)
+    assert np.isfinite(lb.avg_errors()).all()
+    _assert_scores(lb.avg_errors(), ref, "standstill")
+
+
+def test_topk_kernel_vs_argsort():
+    import torch
+    from llampc_b200 import _lib
+    L = _lib.lib()
+    rng = np.random.RandomState(0)
+    for n, k in ((1, 1), (37, 10), (4096, 10), (4097, 64), (300001, 10), (1 << 20, 32)):
+        err = rng.rand(n).astype(np.float32)
+        if n > 100:
+            err[rng.randint(0, n, 50)] = err.min()              # ties -> lower index first
+        d = torch.from_numpy(err).cuda()
+        ctas = L.llampc_topk_scratch_ctas(n)
+        scratch = torch.empty(ctas * k, dtype=torch.int64, device="cuda")
+        counter = torch.zeros(1, dtype=torch.int32, device="cuda")
+        out = torch.empty(k, dtype=torch.int64, device="cuda")
+        for _ in range(2):                                       # second launch reuses the self-resetting counter
+            _lib.check(L.llampc_topk_f32(d.data_ptr(), n, 7, k, scratch.data_ptr(), counter.data_ptr(), out.data_ptr(),
+                                         torch.cuda.current_stream().cuda_stream))
+        keys = out.cpu().numpy().view(np.uint64)
+        idx = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64) - 7
+        want = np.argsort(err, kind="stable")[:k]
+        m = min(n, k)
+        assert list(idx[:m]) == list(want[:m])
+        assert (keys[m:] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+
+
+def test_multi_vehicle_histories(history):
+    """Monte-Carlo layout: V vehicles share one bank, each with its own history window (grid.y = vehicle)."""
+    import torch
+    from llampc_b200 import _lib
+    from llampc_b200.bank import ModelBank
+    S, U, Ts = history
+    L = _lib.lib()
+    bank_p = orc.make_bank(1024, seed=0)
+    bank = ModelBank(bank_p)
+    V, W = 5, 20
+    t_ends = [100, 400, 800, 1200, 1700]
+    rows = np.zeros((V, W, 20), dtype=np.float32)
+    for v, te in enumerate(t_ends):
+        for j, t in enumerate(range(te - W + 1, te + 1)):
+            xk, uk, xk1 = (np.ascontiguousarray(a) for a in (S[:, t], U[:, t], S[:, t + 1]))
+            L.llampc_hist_row_pack_h(xk.ctypes.data, uk.ctypes.data, xk1.ctypes.data, Ts, bank.lf_shared, bank.lr_shared,
+                                     rows[v, j].ctypes.data, None)
+    hist = torch.from_numpy(rows).cuda()
+    avg = torch.empty((V, 1024), dtype=torch.float32, device="cuda")
+    keys = torch.empty(V, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    _lib.check(L.llampc_fill_keys(keys.data_ptr(), V, st))
+    _lib.check(L.llampc_lookback_window_f32(bank.packed.data_ptr(), 1024, bank.Npad, hist.data_ptr(), W, V, W, Ts,
+                                            avg.data_ptr(), keys.data_ptr(), 0, 1, 0, st))
+    avg = avg.cpu().numpy().astype(np.float64)
+    kk = keys.cpu().numpy().view(np.uint64)
+    for v, te in enumerate(t_ends):
+        ref = np.mean(orc.window_errors(bank_p, S, U, te, W, Ts), axis=1)
+        _assert_scores(avg[v], ref, "vehicle %d" % v)
+        assert int(kk[v] & np.uint64(0xFFFFFFFF)) == int(np.argmin(ref))
+
+
+# ------------------------------------------------------------------------------------------- look-ahead
+def test_lookahead_golden():
+    from llampc_b200.mpc import LookAhead
+    g = load_golden("lookahead_kat.npz")
+    bank = orc.orca_params()
+    for row, k in enumerate(("Bf", "Cf", "Df", "Br", "Cr", "Dr")):
+        bank[k] = g["params"][row]
+    la = LookAhead(bank, Ts=float(g["Ts"]))
+    J, best_k, xf = la.rollout(g["x0"], g["U"], g["xref"], g["uprev"], return_final=True)
+    np.testing.assert_allclose(J, g["J"], rtol=1e-4)
+    np.testing.assert_allclose(xf, g["x_final"], rtol=1e-4, atol=1e-5)
+    ref_best = np.argmin(g["J"], axis=1)
+    srt = np.sort(g["J"], axis=1)
+    clear = (srt[:, 1] - srt[:, 0]) > 1e-4 * srt[:, 0]
+    assert np.array_equal(best_k[clear], ref_best[clear])
+
+
+def test_lookahead_c3_shape_per_model_inputs(history):
+    """M x K = 2,048 x 32 rollouts with per-model controls, start states, references and previous inputs."""
+    from llampc_b200.mpc import LookAhead
+    S, U, Ts = history
+    rng = np.random.RandomState(3)
+    M, K, H = 96, 32, 20
+    bank = orc.make_bank(M, seed=2)
+    la = LookAhead(bank, Ts=Ts)
+    t0s = rng.randint(100, 1700, M)
+    x0 = S[:, t0s].T.copy()
+    Um = np.stack([U[:, t:t + H].T for t in t0s])[:, None] + np.stack(
+        [0.1 * rng.randn(M, K, H), 0.05 * rng.randn(M, K, H)], axis=-1)
+    Um[..., 0] = np.clip(Um[..., 0], -0.1, 1.0)
+    Um[..., 1] = np.clip(Um[..., 1], -0.35, 0.35)
+    xref = np.stack([S[:2, t:t + H + 1] for t in t0s])                 # (M, 2, H+1)
+    uprev = U[:, t0s - 1].T.copy()
+    J, best_k = la.rollout(x0, Um, xref, uprev)
+    for m in range(0, M, 7):
+        pm = {k: (bank[k][m:m + 1] if np.ndim(bank[k]) else bank[k]) for k in orc.PARAM_NAMES}
+        Jr, bkr = orc.lookahead_rollout(pm, x0[m], Um[m], xref[m], uprev[m], Ts)
+        np.testing.assert_allclose(J[m], Jr[0], rtol=1e-4, atol=1e-9)
+        srt = np.sort(Jr[0])
+        if srt[1] - srt[0] > 1e-4 * srt[0]:
+            assert best_k[m] == bkr[0]
+    # model_idx indirection: roll only the models in `sel`, shared inputs
+    sel = np.array([5, 17, 5, 90])
+    J2, _ = la.rollout(x0[0], Um[0], xref[0], uprev[0], model_idx=sel)
+    for j, m in enumerate(sel):
+        pm = {k: (bank[k][m:m + 1] if np.ndim(bank[k]) else bank[k]) for k in orc.PARAM_NAMES}
+        Jr, _ = orc.lookahead_rollout(pm, x0[0], Um[0], xref[0], uprev[0], Ts)
+        np.testing.assert_allclose(J2[j], Jr[0], rtol=1e-4, atol=1e-9)
+
+
+def test_error_codes_without_launch():
+    import torch
+    from llampc_b200 import _lib
+    L = _lib.lib()
+    d = torch.zeros(1024, dtype=torch.float32, device="cuda")
+    k = torch.zeros(1, dtype=torch.int64, device="cuda")
+    st = torch.cuda.current_stream().cuda_stream
+    assert L.llampc_lookback_window_f32(None, 1, 1, d.data_ptr(), 1, 1, 1, 0.02, None, k.data_ptr(), 0, 1, 0, st) == -1
+    assert L.llampc_lookback_window_f32(d.data_ptr(), 8, 8, d.data_ptr(), 2000, 1, 2000, 0.02, None, k.data_ptr(), 0, 1, 0, st) == -3
+    assert L.llampc_lookback_window_f32(d.data_ptr() + 4, 8, 8, d.data_ptr(), 2, 1, 2, 0.02, None, k.data_ptr(), 0, 1, 0, st) == -2
+    assert L.llampc_topk_f32(d.data_ptr(), 10, 0, 100, k.data_ptr(), k.data_ptr(), k.data_ptr(), st) == -3
