@@ -69,51 +69,53 @@ def synthetic_history(n_ticks, plant_step):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
-    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    """SM clock and throttle reasons sampled with NVML (every ~2 ms) during the timed region."""
 
     def __init__(self, index=0):
-        self.rows, self.proc, self.index = [], None, index
+        self.index, self.sm, self.mx, self.reasons, self.stop = index, [], None, set(), False
+        self.th = None
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
-            self.th = threading.Thread(target=self._read, daemon=True)
+            import pynvml as nv
+            nv.nvmlInit()
+            self.nv = nv
+            self.h = nv.nvmlDeviceGetHandleByIndex(self.index)
+            self.mx = float(nv.nvmlDeviceGetMaxClockInfo(self.h, nv.NVML_CLOCK_SM))
+            self.th = threading.Thread(target=self._loop, daemon=True)
             self.th.start()
-        except Exception:
-            self.proc = None
+        except Exception as e:                                   # no NVML: report an empty record
+            self.err = repr(e)
         return self
 
-    def _read(self):
-        for line in self.proc.stdout:
-            self.rows.append([c.strip() for c in line.split(",")])
-
-    def __exit__(self, *a):
-        if self.proc is not None:
-            self.proc.terminate()
+    def _loop(self):
+        nv = self.nv
+        names = {"hw_slowdown": 0x8, "sw_power_cap": 0x4, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40,
+                 "hw_power_brake_slowdown": 0x80}
+        while not self.stop:
             try:
-                self.proc.wait(timeout=5)
+                self.sm.append(float(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for n, bit in names.items():
+                    if r & bit:
+                        self.reasons.add(n)
             except Exception:
                 pass
+            time.sleep(0.002)
+
+    def __exit__(self, *a):
+        self.stop = True
+        if self.th is not None:
+            self.th.join(timeout=2)
 
     def summary(self):
-        sm, mx, reasons = [], [], set()
-        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for r in self.rows:
-            try:
-                sm.append(float(r[0]))
-                mx.append(float(r[1]))
-                for n, v in zip(names, r[3:7]):
-                    if v.lower().startswith("active"):
-                        reasons.add(n)
-            except Exception:
-                continue
-        if not sm:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        if not self.sm:
+            return {"sm_mhz": None, "sm_max_mhz": self.mx, "reasons": [], "samples": 0, "error": getattr(self, "err", None)}
+        return {"sm_mhz": float(np.median(self.sm)), "sm_max_mhz": self.mx, "reasons": sorted(self.reasons),
+                "samples": len(self.sm)}
 
 
 # ----------------------------------------------------------------------------------------------------------
@@ -259,20 +261,25 @@ def run_b200(args):
     bank = lb.bank
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
+    n_lists = L.llampc_lookback_num_lists(n_local, W_C2, 0)
+    assert lb.fused and n_lists > 0
+
     def tick_device():
-        """One look-back tick with device-resident inputs: key reset, K1, top-10 (+ min-loc all-reduce)."""
-        L.llampc_fill_keys(lb.best_key.data_ptr(), 1, st)
+        """One look-back tick with device-resident inputs: K1 (scores, block arg-min, per-CTA sorted lists) and
+        the list merge (top-10; moves the arg-min key to topk_keys[0]) (+ the min-loc all-reduce for N > 1)."""
         rc = L.llampc_lookback_window_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2, TS,
-                                          lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lo, int(bank.geom_shared), 0, st)
+                                          lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), lo,
+                                          int(bank.geom_shared), 0, st)
         _lib.check(rc, "K1")
-        _lib.check(L.llampc_topk_f32(lb.avg_err.data_ptr(), n_local, lo, 10, lb.topk_scratch.data_ptr(),
-                                     lb.topk_counter.data_ptr(), lb.topk_keys.data_ptr(), st), "K4")
+        _lib.check(L.llampc_topk_merge_lists(lb.cta_lists.data_ptr(), n_lists, 1, 10, lb.best_key.data_ptr(),
+                                             lb.topk_keys.data_ptr(), st), "K4'")
         if world > 1:
-            td.all_reduce(lb.best_key, op=td.ReduceOp.MIN)
+            td.all_reduce(lb.topk_keys[:1], op=td.ReduceOp.MIN)
 
     def k1_only():
         L.llampc_lookback_window_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2, TS,
-                                     lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lo, int(bank.geom_shared), 0, st)
+                                     lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), lo,
+                                     int(bank.geom_shared), 0, st)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -330,7 +337,7 @@ def run_b200(args):
     e2e = None
     lat = None
     if world == 1:
-        lbe = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=32)
+        lbe = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=16)
         for t in range(W_C2):
             lbe.push(S[:, t], U[:, t], S[:, t + 1])
         for t in range(W_C2, W_C2 + max(args.warmup, 3)):
@@ -348,7 +355,7 @@ def run_b200(args):
         h2d = _lib.HIST_ROW * 4 + _lib.HIST64_ROW * 8
         d2h = (1 + lbe.Kt) * 8 + lbe.Kt * 8
         e2e = {"value": steps_per_tick * args.steps / wall, "unit": "steps/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "api": "LookBack.push (refine=32: fp64 re-score of the finalists included)"}
+               "d2h_bytes_per_step": d2h, "api": "LookBack.push (refine=16: fp64 re-score of the 16 finalists included)"}
         lat = {"p50_us": float(np.percentile(lats, 50) * 1e6), "p95_us": float(np.percentile(lats, 95) * 1e6)}
 
     if rank != 0:
@@ -360,7 +367,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
-            "gpu_launches": args.steps * 3, "clocks": clocks, "roofline": roofline}
+            "gpu_launches": args.steps * 2, "clocks": clocks, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e
         line["tick_latency"] = lat

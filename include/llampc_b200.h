@@ -30,7 +30,8 @@ extern "C" {
 #define LLAMPC_HIST_ROW      20   /* floats per history row (80 B)                              */
 #define LLAMPC_HIST64_ROW    12   /* doubles per f64 history row: x_k[6] u_k[2] x_k1[0:4]       */
 #define LLAMPC_MAX_W       1024   /* history rows staged in shared memory per CTA               */
-#define LLAMPC_MAX_K         64   /* top-K                                                      */
+#define LLAMPC_MAX_K         64   /* top-K (llampc_topk_f32)                                    */
+#define LLAMPC_LIST_LEN      16   /* keys per CTA list written by K1; top-K of the fused path   */
 #define LLAMPC_MAX_H        256   /* look-ahead horizon                                         */
 
 typedef void* llampc_stream_t;           /* cudaStream_t */
@@ -68,15 +69,25 @@ int llampc_hist_row_pack_h(const double* x_k, const double* u_k, const double* x
  *   bank      packed bank (llampc_bank_pack_h layout) on the device, 16-byte aligned
  *   hist      [n_vehicles][hist_stride_rows][LLAMPC_HIST_ROW] floats; the first W rows of each vehicle are used
  *   avg_err   [n_vehicles][N] or NULL
- *   best_key  [n_vehicles]; MUST be preset to ~0ull by the caller (llampc_fill_keys); receives the
+ *   best_key  [n_vehicles] or NULL; MUST be preset to ~0ull by the caller (llampc_fill_keys); receives the
  *             min over candidates of (float_bits(avg_err)<<32 | idx_offset+i)  (np.argmin tie-break)
+ *   cta_lists [n_vehicles][n_lists][LLAMPC_LIST_LEN] or NULL, n_lists = llampc_lookback_num_lists(N, W, split):
+ *             the ascending LLAMPC_LIST_LEN smallest keys of every CTA (input of llampc_topk_merge_lists)
  *   geom_shared  non-zero: rows carry valid stage-1 slip angles (lf, lr identical for all candidates)
  *   split     window splits per candidate inside a CTA (1,2,4,8) or 0 = choose from N, W
  * ------------------------------------------------------------------------------------------- */
 int llampc_lookback_window_f32(const float* bank, int N, int Npad,
                                const float* hist, int W, int n_vehicles, int hist_stride_rows, double Ts,
-                               float* avg_err, llampc_key_t* best_key, int idx_offset,
+                               float* avg_err, llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
                                int geom_shared, int split, llampc_stream_t stream);
+int llampc_lookback_num_lists(int N, int W, int split);
+
+/* Fused top-K (K <= LLAMPC_LIST_LEN): K-way merge of the per-CTA lists of K1.  Per vehicle v:
+ *   out[v][0] = best_key[v] (which is then re-armed to ~0ull for the next tick; skipped if best_key is NULL),
+ *   out[v][1..K] = ascending top-K keys; out has LLAMPC_LIST_LEN + 1 keys per vehicle.
+ * Replaces avg_errors.argsort()[:K] (run_nmpc_orca_llampc_rt.py:360) without re-reading avg_err. */
+int llampc_topk_merge_lists(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K,
+                            llampc_key_t* best_key, llampc_key_t* out, llampc_stream_t stream);
 
 int llampc_fill_keys(llampc_key_t* keys, int n, llampc_stream_t stream);   /* keys[i] = ~0ull */
 
@@ -111,8 +122,11 @@ typedef struct llampc_tick {
     llampc_key_t* best_key;         /* [1]                                                               */
     int K;                          /* top-K wanted by the caller (rt.py:360 uses 10)                    */
     int n_refine;                   /* 0 = no fp64 re-score                                              */
-    llampc_key_t* topk_scratch; unsigned* topk_counter;
-    llampc_key_t* topk_keys;        /* [Kt] ascending by fp32 score                                      */
+    llampc_key_t* cta_lists;        /* [n_lists][LLAMPC_LIST_LEN] or NULL; with Kt <= LLAMPC_LIST_LEN selects the
+                                       fused path (K1 + list merge: two launches per tick, best_key must have
+                                       been armed once with llampc_fill_keys)                               */
+    llampc_key_t* topk_scratch; unsigned* topk_counter;   /* only for the unfused path (Kt > LLAMPC_LIST_LEN)    */
+    llampc_key_t* topk_keys;        /* [LLAMPC_LIST_LEN + 1 or 1 + Kt]: best key, then Kt keys ascending   */
     const double* bank64;           /* [LLAMPC_NPARAM][N] (n_refine > 0)                                 */
     double* hist64;                 /* device ring [W][LLAMPC_HIST64_ROW] (n_refine > 0)                 */
     const double* row64_h;          /* pinned host row for hist64, or NULL                               */

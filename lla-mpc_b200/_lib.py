@@ -7,13 +7,14 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libllampc_b200.so")
+LIB_PATH = os.environ.get("LLAMPC_LIB") or os.path.join(_HERE, "libllampc_b200.so")   # env override: kernel experiments
 
 NPARAM = 14
 HIST_ROW = 20
 HIST64_ROW = 12
 MAX_W = 1024
 MAX_K = 64
+LIST_LEN = 16
 MAX_H = 256
 PARAM_NAMES = ("lf", "lr", "mass", "Iz", "Bf", "Br", "Cf", "Cr", "Df", "Dr", "Cm1", "Cm2", "Cr0", "Cr2")
 
@@ -26,7 +27,7 @@ class Tick(C.Structure):
                 ("hist", _vp), ("row32_h", _vp), ("slot", _i), ("W", _i), ("Ts", _d),
                 ("geom_shared", _i), ("split", _i), ("idx_offset", _i),
                 ("avg_err", _vp), ("best_key", _vp), ("K", _i), ("n_refine", _i),
-                ("topk_scratch", _vp), ("topk_counter", _vp), ("topk_keys", _vp),
+                ("cta_lists", _vp), ("topk_scratch", _vp), ("topk_counter", _vp), ("topk_keys", _vp),
                 ("bank64", _vp), ("hist64", _vp), ("row64_h", _vp), ("refine_err64", _vp),
                 ("out_keys_h", _vp), ("out_err64_h", _vp), ("sync", _i)]
 
@@ -37,7 +38,9 @@ PROTOTYPES = {
     "llampc_error_string": (C.c_char_p, [_i]),
     "llampc_bank_pack_h": (_i, [_vp, _vp, _i, _i, _vp]),
     "llampc_hist_row_pack_h": (_i, [_vp, _vp, _vp, _d, _d, _d, _vp, _vp]),
-    "llampc_lookback_window_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _vp, _vp, _i, _i, _i, _vp]),
+    "llampc_lookback_window_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _i, _i, _i, _vp]),
+    "llampc_lookback_num_lists": (_i, [_i, _i, _i]),
+    "llampc_topk_merge_lists": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "llampc_fill_keys": (_i, [_vp, _i, _vp]),
     "llampc_topk_scratch_ctas": (_i, [_i]),
     "llampc_topk_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),

@@ -41,6 +41,35 @@ __device__ __forceinline__ u64 block_min_u64(u64 k, u64* sbuf) {
     return r;
 }
 
+__device__ __forceinline__ u64 u64_max(u64 a, u64 b) { return a > b ? a : b; }
+
+// ascending bitonic sort of one key per lane (15 compare-exchange stages of 2 shuffles each)
+__device__ __forceinline__ u64 warp_sort_u64(u64 key, int lane) {
+#pragma unroll
+    for (int k = 2; k <= 32; k <<= 1) {
+#pragma unroll
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            const u64 other = __shfl_xor_sync(0xffffffffu, key, j);
+            const bool up = (lane & k) == 0 || k == 32;
+            const bool lower = (lane & j) == 0;
+            key = (lower == up) ? u64_min(key, other) : u64_max(key, other);
+        }
+    }
+    return key;
+}
+
+// a: this warp's ascending keys (lane i = i-th smallest); b_rev: the other sorted list read in REVERSED lane
+// order.  Returns the 32 smallest of the union, ascending (bitonic merge, 5 stages).
+__device__ __forceinline__ u64 warp_merge_low32(u64 a, u64 b_rev, int lane) {
+    u64 m = u64_min(a, b_rev);
+#pragma unroll
+    for (int j = 16; j > 0; j >>= 1) {
+        const u64 other = __shfl_xor_sync(0xffffffffu, m, j);
+        m = ((lane & j) == 0) ? u64_min(m, other) : u64_max(m, other);
+    }
+    return m;
+}
+
 // ---- mbarrier + cp.async.bulk (TMA 1-D bulk copy global -> shared; SASS: UBLKCP) ---------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -86,6 +86,46 @@ __device__ __forceinline__ float sin_any(float t) {
     return __uint_as_float(__float_as_uint(v) ^ (kbits << 31));
 }
 
+// atan(z) for ANY z, branch-free: q = z for |z| <= 1, q = sign(z)/|z| otherwise (one MUFU.RCP),
+// atan z = sign(z) pi/2 - atan(q) in the second case.  +-inf -> +-pi/2, NaN -> NaN.
+__device__ __forceinline__ float atan_full(float z) {
+    const float az = fabsf(z);
+    const float r = rcp_approx(fmaxf(az, 1.0f));
+    const bool big = az > 1.0f;
+    const float q = big ? copysignf(r, z) : z;
+    const float a = atan_unit(q);
+    const float c = copysignf(LLAMPC_PIO2_HI, z);
+    return big ? (c - a) : a;
+}
+
+// sin(t) with a 4-coefficient polynomial (2.7e-8) after the same reduction as sin_any: used on the tyre
+// curve, where the fp32 evaluation error (1.2e-7) dominates the polynomial error anyway.
+__device__ __forceinline__ float sin_tyre(float t) {
+    const float MAGIC = 12582912.0f;
+    float kf = fmaf(t, 0.318309886183790671538f, MAGIC);
+    unsigned kbits = __float_as_uint(kf);
+    kf -= MAGIC;
+    float r = fmaf(kf, -3.1415927410125732421875f, t);
+    r = fmaf(kf, 8.74227765734758577e-8f, r);
+    float s = r * r;
+    float p = 2.6348915076e-06f;
+    p = fmaf(p, s, -1.9822790564e-04f);
+    p = fmaf(p, s, 8.3332426307e-03f);
+    p = fmaf(p, s, -1.6666665972e-01f);
+    float v = fmaf(r * s, p, r);
+    return __uint_as_float(__float_as_uint(v) ^ (kbits << 31));
+}
+
+// sin/cos of a tiny angle |e| <= 0.125 (RK stage heading offsets of the look-back, O(h^2 * yaw acceleration)):
+// truncation errors e^7/5040 < 1e-10 and e^6/720 < 6e-9.  No range check here: the caller tracks max |e|.
+__device__ __forceinline__ void sincos_tiny(float e, float& sn, float& cs) {
+    float s = e * e;
+    float ps = fmaf(s, 8.3333333e-03f, -1.6666667e-01f);
+    sn = fmaf(e * s, ps, e);
+    float pc = fmaf(s, 4.1666668e-02f, -0.5f);
+    cs = fmaf(s, pc, 1.0f);
+}
+
 // MUFU variant (2 instructions); measured against the polynomial in tests/bench, not the default.
 __device__ __forceinline__ float sin_mufu(float t) { return __sinf(t); }
 

@@ -90,6 +90,35 @@ __device__ __forceinline__ float accel_vx_only(const Cand& p, const Ctl& u, floa
 }
 
 // ---------------------------------------------------------------------------------------------------
+// Straight-line ("fast") variants for the look-back kernel: no branches inside the step.  The tyre atan is
+// branch-free for any argument; the slip-angle atan and the tiny heading rotations are only valid on
+// |t| <= 1 and |e| <= 0.125, and `guard` accumulates max(|t|, 8|e|) so that the caller can redo the whole
+// step with the general routines in the rare case the guard exceeds 1 (or is NaN).
+// ---------------------------------------------------------------------------------------------------
+template <bool MUFU_SIN>
+__device__ __forceinline__ float pacejka_fast(float B, float C, float D, float alpha) {
+    const float t = C * atan_full(B * alpha);
+    return D * (MUFU_SIN ? sin_mufu(t) : sin_tyre(t));
+}
+
+template <bool MUFU_SIN>
+__device__ __forceinline__ Deriv accel_fast(const Cand& p, const Ctl& u, float vx, float vy, float w, float& guard) {
+    const float inv = rcp_newton(fabsf(vx));
+    const float tf = fmaf(p.lf, w, vy) * inv, tr = fmaf(p.lr, w, -vy) * inv;
+    guard = fmaxf(guard, fmaxf(fabsf(tf), fabsf(tr)));
+    const float af = u.delta - atan_unit(tf), ar = atan_unit(tr);
+    const float Frx = drive_force(p, u.pwm, vx);
+    const float Ffy = pacejka_fast<MUFU_SIN>(p.Bf, p.Cf, p.Df, af);
+    const float Fry = pacejka_fast<MUFU_SIN>(p.Br, p.Cr, p.Dr, ar);
+    const float Fc = Ffy * u.cd;
+    Deriv d;
+    d.vx = fmaf(fmaf(-Ffy, u.sd, Frx), p.inv_m, vy * w);
+    d.vy = fmaf(Fry + Fc, p.inv_m, -vx * w);
+    d.w = fmaf(Fc, p.lf_Iz, -Fry * p.lr_Iz);
+    return d;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // Generic RK4 step in increment form.  (s0, c0) = sin/cos of the heading at the start of the step.
 // inc[] = y(t+h) - y(t) for (x, y, psi, vx, vy, omega).
 // ---------------------------------------------------------------------------------------------------
@@ -182,6 +211,75 @@ __device__ __forceinline__ float lookback_step(const Cand& p, const HistRow& r, 
     float epsi = fmaf(z.hh6_lo, sw, fmaf(z.hh6, sw, -r.q3.w));
     float evx = fmaf(z.h6_lo, sv, fmaf(z.h6, sv, -r.q4.x)) - r.q4.y;
     return fmaf(ex, ex, fmaf(ey, ey, fmaf(epsi, epsi, evx * evx)));
+}
+
+// Fast look-back step (same arithmetic, straight-line code).  Returns the squared increment error and sets
+// `ok` to false when a guard tripped (caller falls back to lookback_step).
+template <bool GEOM_SHARED, bool MUFU_SIN>
+__device__ __forceinline__ float lookback_step_fast(const Cand& p, const HistRow& r, const StepSize& z, bool& ok) {
+    const float h = z.h, hh = z.hh;
+    const float vx0 = r.q1.z, vy0 = r.q1.w, w0 = r.q2.x;
+    Ctl u;
+    u.pwm = r.q2.y; u.delta = r.q2.z; u.sd = r.q2.w; u.cd = r.q3.x;
+    float guard = 0.0f;
+    // stage 1
+    Deriv a1;
+    if (GEOM_SHARED) {
+        const float Frx = drive_force(p, u.pwm, vx0);
+        const float Ffy = pacejka_fast<MUFU_SIN>(p.Bf, p.Cf, p.Df, r.q4.z);
+        const float Fry = pacejka_fast<MUFU_SIN>(p.Br, p.Cr, p.Dr, r.q4.w);
+        const float Fc = Ffy * u.cd;
+        a1.vx = fmaf(fmaf(-Ffy, u.sd, Frx), p.inv_m, vy0 * w0);
+        a1.vy = fmaf(Fry + Fc, p.inv_m, -vx0 * w0);
+        a1.w = fmaf(Fc, p.lf_Iz, -Fry * p.lr_Iz);
+    } else {
+        a1 = accel_fast<MUFU_SIN>(p, u, vx0, vy0, w0, guard);
+    }
+    // stage 2
+    const float vx2 = fmaf(hh, a1.vx, vx0), vy2 = fmaf(hh, a1.vy, vy0), w2 = fmaf(hh, a1.w, w0);
+    const Deriv a2 = accel_fast<MUFU_SIN>(p, u, vx2, vy2, w2, guard);
+    float xs = fmaf(vx2, r.q0.w, -vy2 * r.q0.z), ys = fmaf(vx2, r.q0.z, vy2 * r.q0.w);
+    // stage 3
+    const float vx3 = fmaf(hh, a2.vx, vx0), vy3 = fmaf(hh, a2.vy, vy0), w3 = fmaf(hh, a2.w, w0);
+    const float e3 = hh * (hh * a1.w);
+    float sd, cd;
+    sincos_tiny(e3, sd, cd);
+    const float s3 = fmaf(r.q0.z, cd, r.q0.w * sd), c3 = fmaf(r.q0.w, cd, -r.q0.z * sd);
+    const Deriv a3 = accel_fast<MUFU_SIN>(p, u, vx3, vy3, w3, guard);
+    xs += fmaf(vx3, c3, -vy3 * s3);
+    ys += fmaf(vx3, s3, vy3 * c3);
+    // stage 4 (front tyre and drivetrain only)
+    const float vx4 = fmaf(h, a3.vx, vx0), vy4 = fmaf(h, a3.vy, vy0), w4 = fmaf(h, a3.w, w0);
+    const float e4 = h * (hh * a2.w);
+    sincos_tiny(e4, sd, cd);
+    const float s4 = fmaf(r.q1.x, cd, r.q1.y * sd), c4 = fmaf(r.q1.y, cd, -r.q1.x * sd);
+    guard = fmaxf(guard, 8.0f * fmaxf(fabsf(e3), fabsf(e4)));
+    const float inv4 = rcp_newton(fabsf(vx4));
+    const float tf4 = fmaf(p.lf, w4, vy4) * inv4;
+    guard = fmaxf(guard, fabsf(tf4));
+    const float Ffy4 = pacejka_fast<MUFU_SIN>(p.Bf, p.Cf, p.Df, u.delta - atan_unit(tf4));
+    const float a4vx = fmaf(fmaf(-Ffy4, u.sd, drive_force(p, u.pwm, vx4)), p.inv_m, vy4 * w4);
+    const float xd4 = fmaf(vx4, c4, -vy4 * s4), yd4 = fmaf(vx4, s4, vy4 * c4);
+    // increment errors
+    const float sx = fmaf(2.0f, xs, xd4), sy = fmaf(2.0f, ys, yd4);
+    const float sw = (a1.w + a2.w) + a3.w, sv = (a1.vx + a4vx) + 2.0f * (a2.vx + a3.vx);
+    const float ex = fmaf(z.h6_lo, sx, fmaf(z.h6, sx, -r.q3.y));
+    const float ey = fmaf(z.h6_lo, sy, fmaf(z.h6, sy, -r.q3.z));
+    const float epsi = fmaf(z.hh6_lo, sw, fmaf(z.hh6, sw, -r.q3.w));
+    const float evx = fmaf(z.h6_lo, sv, fmaf(z.h6, sv, -r.q4.x)) - r.q4.y;
+    ok = guard <= 1.0f;                       // false for NaN as well
+    return fmaf(ex, ex, fmaf(ey, ey, fmaf(epsi, epsi, evx * evx)));
+}
+
+// out-of-line general step for the rare fallback: reloads the candidate and the history row itself so that
+// the hot loop does not have to keep them addressable (no local-memory traffic on the fast path)
+template <bool GEOM_SHARED, bool MUFU_SIN>
+__device__ __noinline__ float lookback_step_general(const float4* __restrict__ bank, int Npad, int cand,
+                                                    const float4* srow_w, StepSize z) {
+    const Cand p = load_cand(bank, Npad, cand);
+    HistRow r;
+    r.q0 = srow_w[0]; r.q1 = srow_w[1]; r.q2 = srow_w[2]; r.q3 = srow_w[3]; r.q4 = srow_w[4];
+    return lookback_step<GEOM_SHARED, MUFU_SIN>(p, r, z);
 }
 
 }  // namespace llampc

@@ -17,14 +17,17 @@ constexpr int NUM_SMS = 148;
 // the same row at the same time (shared-memory broadcast).  Thread (c, sy) integrates window rows
 // sy, sy+SY, ...; partial sums are combined in a fixed order so the result is run-to-run deterministic.
 // ---------------------------------------------------------------------------------------------------
+#ifndef LLAMPC_LB_MIN_BLOCKS
+#define LLAMPC_LB_MIN_BLOCKS 1
+#endif
 template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
-__global__ void __launch_bounds__(LB_THREADS)
+__global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB_MIN_BLOCKS)
 lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
                        long hist_stride_floats, StepSize z, float* __restrict__ avg_err, u64* __restrict__ best_key,
-                       int idx_offset) {
+                       u64* __restrict__ cta_lists, int idx_offset) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
-    __shared__ u64 skeys[LB_THREADS / 32 + 1];
+    __shared__ u64 skeys[LB_THREADS];
     float4* srow = reinterpret_cast<float4*>(smem_raw);
     float* spart = reinterpret_cast<float*>(smem_raw + (size_t)W * (LLAMPC_HIST_ROW * 4));
 
@@ -55,7 +58,10 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
         r.q2 = srow[w * 5 + 2];
         r.q3 = srow[w * 5 + 3];
         r.q4 = srow[w * 5 + 4];
-        acc += lookback_step<GEOM_SHARED, MUFU_SIN>(p, r, z);
+        bool ok;
+        float e = lookback_step_fast<GEOM_SHARED, MUFU_SIN>(p, r, z, ok);
+        if (!ok) e = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, valid ? cand : N - 1, srow + w * 5, z);
+        acc += e;
     }
 
     if (SY > 1) {
@@ -73,8 +79,80 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
         if (avg_err) avg_err[(size_t)v * N + cand] = err;
         key = pack_key(err, (unsigned)(idx_offset + cand));
     }
-    key = block_min_u64<LB_THREADS / 32>(key, skeys);
-    if (tid == 0 && key != ~0ull) atomicMin(best_key + v, key);
+    // CTA-level selection: every key-holding warp sorts its 32 keys (registers + shuffles), sorted runs are
+    // merged pairwise through shared memory; warp 0 ends up with the CTA's 32 smallest keys in ascending lane
+    // order.  Lane 0 = block arg-min (one atomicMin per CTA); lanes 0..15 = this CTA's list for the top-K merge.
+    constexpr int KW = CPB / 32;                   // warps that hold final scores: 4, 2 or 1
+    const int lane = tid & 31, warp = tid >> 5;
+    if (warp < KW) key = warp_sort_u64(key, lane);
+    if (KW == 4) {
+        if (warp == 1 || warp == 3) skeys[warp * 32 + lane] = key;
+        __syncthreads();
+        if (warp == 0 || warp == 2) key = warp_merge_low32(key, skeys[(warp + 1) * 32 + 31 - lane], lane);
+        __syncthreads();
+        if (warp == 2) skeys[lane] = key;
+        __syncthreads();
+        if (warp == 0) key = warp_merge_low32(key, skeys[31 - lane], lane);
+    } else if (KW == 2) {
+        if (warp == 1) skeys[lane] = key;
+        __syncthreads();
+        if (warp == 0) key = warp_merge_low32(key, skeys[31 - lane], lane);
+    }
+    if (warp == 0) {
+        if (cta_lists && lane < LLAMPC_LIST_LEN)
+            cta_lists[((size_t)v * gridDim.x + blockIdx.x) * LLAMPC_LIST_LEN + lane] = key;
+        if (lane == 0 && best_key && key != ~0ull) atomicMin(best_key + v, key);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K4' merge of the per-CTA sorted lists written by K1 into the global top-K (K <= LLAMPC_LIST_LEN): a K-way
+// merge by K rounds of "block-min over the list heads"; each thread owns up to MERGE_LPT lists and keeps their
+// head and next key in registers so that the load of a popped list's successor is off the critical path.
+// out[0] = *best_key (then re-armed to ~0 for the next tick), out[1..K] = ascending top-K.
+// ---------------------------------------------------------------------------------------------------
+constexpr int MERGE_THREADS = 1024;
+constexpr int MERGE_LPT = 8;
+
+__global__ void __launch_bounds__(MERGE_THREADS)
+topk_merge_lists_kernel(const u64* __restrict__ lists, int n_lists, int K, u64* __restrict__ best_key,
+                        u64* __restrict__ out) {
+    __shared__ u64 sbuf[MERGE_THREADS / 32 + 1];
+    const int v = blockIdx.x;                      // vehicle
+    lists += (size_t)v * n_lists * LLAMPC_LIST_LEN;
+    out += (size_t)v * (LLAMPC_LIST_LEN + 1);
+    u64 head[MERGE_LPT], next[MERGE_LPT];
+    int pos[MERGE_LPT];
+#pragma unroll
+    for (int j = 0; j < MERGE_LPT; ++j) {
+        const int l = threadIdx.x + j * MERGE_THREADS;
+        head[j] = ~0ull; next[j] = ~0ull; pos[j] = 1;
+        if (l < n_lists) {
+            head[j] = __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN);
+            next[j] = __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN + 1);
+        }
+    }
+    if (threadIdx.x == 0 && best_key) {
+        out[0] = best_key[v];
+        best_key[v] = ~0ull;
+    }
+    for (int r = 0; r < K; ++r) {
+        u64 mine = head[0];
+#pragma unroll
+        for (int j = 1; j < MERGE_LPT; ++j) mine = u64_min(mine, head[j]);
+        const u64 sel = block_min_u64<MERGE_THREADS / 32>(mine, sbuf);
+        if (threadIdx.x == 0) out[1 + r] = sel;
+        if (sel == ~0ull || mine != sel) continue;
+#pragma unroll
+        for (int j = 0; j < MERGE_LPT; ++j) {
+            if (head[j] == sel) {                  // pop: successor becomes the head, prefetch the one after
+                head[j] = next[j];
+                pos[j] += 1;
+                const int l = threadIdx.x + j * MERGE_THREADS;
+                next[j] = pos[j] < LLAMPC_LIST_LEN ? __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN + pos[j]) : ~0ull;
+            }
+        }
+    }
 }
 
 __global__ void fill_keys_kernel(u64* keys, int n) {
@@ -244,8 +322,8 @@ static StepSize make_step(double Ts) {
 
 template <int SY, bool GEOM, bool MUFU>
 static int launch_lookback(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
-                           int hist_stride_rows, double Ts, float* avg_err, u64* best_key, int idx_offset,
-                           cudaStream_t st) {
+                           int hist_stride_rows, double Ts, float* avg_err, u64* best_key, u64* cta_lists,
+                           int idx_offset, cudaStream_t st) {
     auto kern = lookback_window_kernel<SY, GEOM, MUFU>;
     const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 : 0);
     if (smem > 48 * 1024) {
@@ -258,15 +336,16 @@ static int launch_lookback(const float* bank, int N, int Npad, const float* hist
     constexpr int CPB = LB_THREADS / SY;
     dim3 grid((N + CPB - 1) / CPB, n_vehicles);
     kern<<<grid, LB_THREADS, smem, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, hist, W,
-                                         (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key, idx_offset);
+                                         (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key, cta_lists,
+                                         idx_offset);
     return (int)cudaGetLastError();
 }
 
 extern "C" int llampc_lookback_window_f32(const float* bank, int N, int Npad, const float* hist, int W,
                                           int n_vehicles, int hist_stride_rows, double Ts, float* avg_err,
-                                          llampc_key_t* best_key, int idx_offset, int geom_shared, int split,
-                                          llampc_stream_t stream) {
-    if (!bank || !hist || !best_key || N <= 0 || Npad < N || n_vehicles <= 0 || hist_stride_rows < W) return LLAMPC_E_ARG;
+                                          llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
+                                          int geom_shared, int split, llampc_stream_t stream) {
+    if (!bank || !hist || (!best_key && !cta_lists && !avg_err) || N <= 0 || Npad < N || n_vehicles <= 0 || hist_stride_rows < W) return LLAMPC_E_ARG;
     if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
     if (!aligned16(bank) || !aligned16(hist) || (hist_stride_rows * LLAMPC_HIST_ROW * 4) % 16) return LLAMPC_E_ALIGN;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -276,10 +355,10 @@ extern "C" int llampc_lookback_window_f32(const float* bank, int N, int Npad, co
     if (split > W) split = 1;
 #define LB_CASE(SYV)                                                                                                  \
     case SYV:                                                                                                         \
-        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, idx_offset, st)   \
-                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, idx_offset, st); \
-        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, idx_offset, st)            \
-                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, idx_offset, st);
+        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, st)   \
+                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, st); \
+        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, st)            \
+                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, st);
     switch (split) {
         LB_CASE(1)
         LB_CASE(2)
@@ -287,6 +366,25 @@ extern "C" int llampc_lookback_window_f32(const float* bank, int N, int Npad, co
         default: return LLAMPC_E_ARG;
     }
 #undef LB_CASE
+}
+
+extern "C" int llampc_lookback_num_lists(int N, int W, int split) {
+    if (N <= 0 || W <= 0) return LLAMPC_E_ARG;
+    if (split >= 16) split -= 16;
+    if (split == 0) split = choose_split(N, W);
+    if (split > W) split = 1;
+    if (split != 1 && split != 2 && split != 4) return LLAMPC_E_ARG;
+    const int cpb = LB_THREADS / split;
+    return (N + cpb - 1) / cpb;
+}
+
+extern "C" int llampc_topk_merge_lists(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K,
+                                       llampc_key_t* best_key, llampc_key_t* out, llampc_stream_t stream) {
+    if (!cta_lists || !out || n_lists <= 0 || n_vehicles <= 0) return LLAMPC_E_ARG;
+    if (K < 0 || K > LLAMPC_LIST_LEN || n_lists > MERGE_THREADS * MERGE_LPT) return LLAMPC_E_RANGE;
+    topk_merge_lists_kernel<<<n_vehicles, MERGE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(cta_lists, n_lists, K,
+                                                                                               best_key, out);
+    return (int)cudaGetLastError();
 }
 
 extern "C" int llampc_fill_keys(llampc_key_t* keys, int n, llampc_stream_t stream) {
@@ -368,26 +466,39 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
     if (t->n_refine > 0 && t->row64_h)
         LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->hist64 + (size_t)t->slot * LLAMPC_HIST64_ROW, t->row64_h,
                                         LLAMPC_HIST64_ROW * sizeof(double), cudaMemcpyHostToDevice, st));
-    int rc = llampc_fill_keys(t->best_key, 1, stream);
-    if (rc) return rc;
-    rc = llampc_lookback_window_f32(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key,
-                                    t->idx_offset, t->geom_shared, t->split, stream);
-    if (rc) return rc;
-    LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->out_keys_h, t->best_key, sizeof(llampc_key_t), cudaMemcpyDeviceToHost, st));
-    if (Kt > 0) {
-        if (!t->topk_scratch || !t->topk_counter || !t->topk_keys) return LLAMPC_E_ARG;
-        rc = llampc_topk_f32(t->avg_err, t->N, t->idx_offset, Kt, t->topk_scratch, t->topk_counter, t->topk_keys, stream);
+    int rc;
+    const bool fused = t->cta_lists != nullptr && Kt <= LLAMPC_LIST_LEN;
+    if (!t->topk_keys) return LLAMPC_E_ARG;
+    if (fused) {
+        // K1 (block arg-min + per-CTA sorted lists) -> list merge (also moves best_key to topk_keys[0] and re-arms it)
+        rc = llampc_lookback_window_f32(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key,
+                                        t->cta_lists, t->idx_offset, t->geom_shared, t->split, stream);
         if (rc) return rc;
-        LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->out_keys_h + 1, t->topk_keys, Kt * sizeof(llampc_key_t),
-                                        cudaMemcpyDeviceToHost, st));
-        if (t->n_refine > 0) {
-            if (!t->bank64 || !t->hist64 || !t->refine_err64 || !t->out_err64_h) return LLAMPC_E_ARG;
-            rc = llampc_refine_f64(t->bank64, t->N, t->hist64, t->W, t->Ts, t->topk_keys, Kt, t->idx_offset,
-                                   t->refine_err64, stream);
+        const int n_lists = llampc_lookback_num_lists(t->N, t->W, t->split);
+        rc = llampc_topk_merge_lists(t->cta_lists, n_lists, 1, Kt, t->best_key, t->topk_keys, stream);
+        if (rc) return rc;
+    } else {
+        rc = llampc_fill_keys(t->best_key, 1, stream);
+        if (rc) return rc;
+        rc = llampc_lookback_window_f32(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key,
+                                        nullptr, t->idx_offset, t->geom_shared, t->split, stream);
+        if (rc) return rc;
+        LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->topk_keys, t->best_key, sizeof(llampc_key_t), cudaMemcpyDeviceToDevice, st));
+        if (Kt > 0) {
+            if (!t->topk_scratch || !t->topk_counter) return LLAMPC_E_ARG;
+            rc = llampc_topk_f32(t->avg_err, t->N, t->idx_offset, Kt, t->topk_scratch, t->topk_counter, t->topk_keys + 1,
+                                 stream);
             if (rc) return rc;
-            LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->out_err64_h, t->refine_err64, Kt * sizeof(double),
-                                            cudaMemcpyDeviceToHost, st));
         }
+    }
+    LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->out_keys_h, t->topk_keys, (1 + Kt) * sizeof(llampc_key_t),
+                                    cudaMemcpyDeviceToHost, st));
+    if (Kt > 0 && t->n_refine > 0) {
+        if (!t->bank64 || !t->hist64 || !t->refine_err64 || !t->out_err64_h) return LLAMPC_E_ARG;
+        rc = llampc_refine_f64(t->bank64, t->N, t->hist64, t->W, t->Ts, t->topk_keys + 1, Kt, t->idx_offset,
+                               t->refine_err64, stream);
+        if (rc) return rc;
+        LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->out_err64_h, t->refine_err64, Kt * sizeof(double), cudaMemcpyDeviceToHost, st));
     }
     if (t->sync) LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
     return 0;

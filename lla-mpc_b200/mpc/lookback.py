@@ -31,12 +31,13 @@ class LookBack:
     K        number of best candidates returned (smoothing_mu_over_mod = 10, rt.py:69,360)
     refine   re-score the max(K, refine) best fp32 candidates in fp64 on the device and order them by the
              fp64 score: the returned indices and errors are then exact in the reference's arithmetic
-             (0 = fp32 scores only)
+             (0 = fp32 scores only).  max(K, refine) <= 16 uses the fused two-launch tick (K1 writes per-CTA
+             sorted lists, a K-way merge kernel finishes); larger values use the stand-alone top-K kernel.
     idx_offset / group   multi-GPU: this rank's bank is the slice starting at global index idx_offset;
              `group` is a torch.distributed process group (None = single GPU)
     """
 
-    def __init__(self, bank_params, W, Ts=0.02, K=10, refine=32, device=None, idx_offset=0, group=None, split=0):
+    def __init__(self, bank_params, W, Ts=0.02, K=10, refine=16, device=None, idx_offset=0, group=None, split=0):
         torch = _lib.require_cuda()
         self.torch = torch
         self.bank = bank_params if isinstance(bank_params, ModelBank) else ModelBank(bank_params, device)
@@ -57,7 +58,11 @@ class LookBack:
         ctas = L.llampc_topk_scratch_ctas(N)
         self.topk_scratch = torch.empty(max(1, ctas * max(self.Kt, 1)), dtype=torch.int64, device=dev)
         self.topk_counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.topk_keys = torch.empty(max(self.Kt, 1), dtype=torch.int64, device=dev)
+        self.topk_keys = torch.empty(1 + max(self.Kt, _lib.LIST_LEN), dtype=torch.int64, device=dev)
+        n_lists = L.llampc_lookback_num_lists(N, self.W, self.split)
+        self.fused = self.Kt <= _lib.LIST_LEN and 0 < n_lists <= 8192
+        self.cta_lists = torch.empty(max(1, n_lists) * _lib.LIST_LEN, dtype=torch.int64, device=dev) if self.fused else None
+        self.best_key.fill_(-1)                                   # armed once; the merge kernel re-arms it every tick
         self.refine_err = torch.empty(max(self.Kt, 1), dtype=torch.float64, device=dev)
         self.rows32_h = torch.zeros((self.W, _lib.HIST_ROW), dtype=torch.float32, pin_memory=True)
         self.rows64_h = torch.zeros((self.W, _lib.HIST64_ROW), dtype=torch.float64, pin_memory=True)
@@ -73,6 +78,7 @@ class LookBack:
         t.geom_shared, t.split, t.idx_offset = int(self.bank.geom_shared), self.split, self.idx_offset
         t.avg_err, t.best_key = self.avg_err.data_ptr(), self.best_key.data_ptr()
         t.K, t.n_refine = self.K, self.n_refine
+        t.cta_lists = self.cta_lists.data_ptr() if self.fused else None
         t.topk_scratch, t.topk_counter = self.topk_scratch.data_ptr(), self.topk_counter.data_ptr()
         t.topk_keys = self.topk_keys.data_ptr()
         if self.n_refine > 0:
@@ -141,7 +147,7 @@ class LookBack:
             err, idx = decode_keys(keys[:1])
             best, topk, best_err = int(idx[0]), idx[:0], float(err[0])
             if self.group is not None:
-                k = _dist.minloc_allreduce(self.best_key, self.group)
+                k = _dist.minloc_allreduce(self.topk_keys[:1], self.group)
                 err, idx = decode_keys(np.array([k], dtype=np.uint64))
                 best, best_err = int(idx[0]), float(err[0])
             return best, topk, best_err

@@ -23,6 +23,15 @@ def _assert_scores(gpu, ref, what=""):
     assert not bad.any(), "%s: %d scores off, worst rel %.3e" % (what, bad.sum(), (err / ref).max())
 
 
+# fp32 right-hand side: the accelerations are differences of force terms amplified by 1/m = 24 and
+# lf/Iz = 1043, so the absolute tolerance scales with those terms (|F/m| ~ 5, |F lf/Iz| ~ 200), not with the result
+RHS_ATOL = np.array([1e-6, 1e-6, 1e-6, 2e-5, 2e-5, 5e-4])
+
+
+def _assert_rhs(f, ref):
+    assert np.all(np.abs(f - ref) <= 1e-6 * np.abs(ref) + RHS_ATOL), np.abs(f - ref).max(axis=0)
+
+
 def _window(lb, S, U, t_end):
     ts = np.arange(t_end - lb.W + 1, t_end + 1)
     lb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
@@ -62,7 +71,7 @@ def test_dynamic_batch_methods_all_14_params(history):
     out = m._integrate_batch(xb, ub, 0, Ts)
     np.testing.assert_allclose(out, g["rk4"], rtol=1e-6, atol=2e-7)
     f = m._diffequation_batch(None, xb, ub)
-    np.testing.assert_allclose(f, g["f"], rtol=2e-6, atol=1e-6)
+    _assert_rhs(f, g["f"])
     bank = {k: g["p_" + k] for k in orc.PARAM_NAMES}
     forces = m.calc_forces_batch(xb, ub, return_slip=True)
     ref = orc.calc_forces_batch(bank, xb, ub, return_slip=True)
@@ -76,7 +85,7 @@ def test_dynamic_kat_scalar_and_plant():
     g = load_golden("kat_nominal.npz")
     m = Dynamic(**ORCA())
     x, u, Ts = g["x"], g["u"], float(g["Ts"])
-    np.testing.assert_allclose(m._diffequation(None, x, u), g["f"], rtol=2e-6, atol=1e-6)
+    _assert_rhs(m._diffequation(None, x, u)[None], g["f"][None])
     np.testing.assert_allclose(np.array(m.calc_forces(x, u, return_slip=True)), g["forces"], rtol=2e-6, atol=1e-8)
     np.testing.assert_allclose(m._integrate_batch(x[None], u[None], 0, Ts)[0], g["rk4"], rtol=1e-6, atol=1e-7)
     # plant: fp64 RK6 on the device, same operation order as the reference
@@ -90,7 +99,7 @@ def test_plant_sim_continuous(history):
     S, U, Ts = history
     xs, dxs = Dynamic(**ORCA()).sim_continuous(S[:, 600], U[:, 600:605], np.arange(6) * Ts)
     np.testing.assert_allclose(xs, g["sim_x"], rtol=0, atol=1e-12)
-    np.testing.assert_allclose(dxs, g["sim_dxdt"], rtol=5e-6, atol=5e-6)       # dxdt comes from the fp32 RHS
+    _assert_rhs(dxs.T, g["sim_dxdt"].T)                                        # dxdt comes from the fp32 RHS
 
 
 # ------------------------------------------------------------------------------------------- look-back
@@ -100,7 +109,7 @@ def test_lookback_c1_golden(history):
     g = load_golden("lookback_c1.npz")
     S, U, Ts = history
     bank = orc.make_bank(1024, seed=0)
-    for refine in (0, 32):
+    for refine in (0, 16, 32):                                 # 0/16: fused K1 + list merge; 32: stand-alone top-K
         lb = LookBack(bank, W=int(g["W"]), Ts=Ts, K=int(g["K"]), refine=refine)
         for t_end in g["ticks"]:
             t_end = int(t_end)
@@ -252,14 +261,20 @@ def test_multi_vehicle_histories(history):
     keys = torch.empty(V, dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
     _lib.check(L.llampc_fill_keys(keys.data_ptr(), V, st))
+    n_lists = L.llampc_lookback_num_lists(1024, W, 0)
+    lists = torch.empty((V, n_lists, 16), dtype=torch.int64, device="cuda")
+    out = torch.empty((V, 17), dtype=torch.int64, device="cuda")
     _lib.check(L.llampc_lookback_window_f32(bank.packed.data_ptr(), 1024, bank.Npad, hist.data_ptr(), W, V, W, Ts,
-                                            avg.data_ptr(), keys.data_ptr(), 0, 1, 0, st))
+                                            avg.data_ptr(), keys.data_ptr(), lists.data_ptr(), 0, 1, 0, st))
+    _lib.check(L.llampc_topk_merge_lists(lists.data_ptr(), n_lists, V, 10, keys.data_ptr(), out.data_ptr(), st))
     avg = avg.cpu().numpy().astype(np.float64)
-    kk = keys.cpu().numpy().view(np.uint64)
+    oo = out.cpu().numpy().view(np.uint64)
+    assert (keys.cpu().numpy() == -1).all()                     # re-armed for the next tick
     for v, te in enumerate(t_ends):
         ref = np.mean(orc.window_errors(bank_p, S, U, te, W, Ts), axis=1)
         _assert_scores(avg[v], ref, "vehicle %d" % v)
-        assert int(kk[v] & np.uint64(0xFFFFFFFF)) == int(np.argmin(ref))
+        assert int(oo[v, 0] & np.uint64(0xFFFFFFFF)) == int(np.argmin(ref))
+        assert list((oo[v, 1:11] & np.uint64(0xFFFFFFFF)).astype(np.int64)) == list(np.argsort(ref)[:10])
 
 
 # ------------------------------------------------------------------------------------------- look-ahead
@@ -319,7 +334,7 @@ def test_error_codes_without_launch():
     d = torch.zeros(1024, dtype=torch.float32, device="cuda")
     k = torch.zeros(1, dtype=torch.int64, device="cuda")
     st = torch.cuda.current_stream().cuda_stream
-    assert L.llampc_lookback_window_f32(None, 1, 1, d.data_ptr(), 1, 1, 1, 0.02, None, k.data_ptr(), 0, 1, 0, st) == -1
-    assert L.llampc_lookback_window_f32(d.data_ptr(), 8, 8, d.data_ptr(), 2000, 1, 2000, 0.02, None, k.data_ptr(), 0, 1, 0, st) == -3
-    assert L.llampc_lookback_window_f32(d.data_ptr() + 4, 8, 8, d.data_ptr(), 2, 1, 2, 0.02, None, k.data_ptr(), 0, 1, 0, st) == -2
+    assert L.llampc_lookback_window_f32(None, 1, 1, d.data_ptr(), 1, 1, 1, 0.02, None, k.data_ptr(), None, 0, 1, 0, st) == -1
+    assert L.llampc_lookback_window_f32(d.data_ptr(), 8, 8, d.data_ptr(), 2000, 1, 2000, 0.02, None, k.data_ptr(), None, 0, 1, 0, st) == -3
+    assert L.llampc_lookback_window_f32(d.data_ptr() + 4, 8, 8, d.data_ptr(), 2, 1, 2, 0.02, None, k.data_ptr(), None, 0, 1, 0, st) == -2
     assert L.llampc_topk_f32(d.data_ptr(), 10, 0, 100, k.data_ptr(), k.data_ptr(), k.data_ptr(), st) == -3

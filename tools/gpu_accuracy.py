@@ -19,7 +19,7 @@ L = _lib.lib()
 
 
 def run_case(name, bank, W, t_end, split=0):
-    lb = LookBack(bank, W=W, Ts=Ts, K=10, refine=32, split=split)
+    lb = LookBack(bank, W=W, Ts=Ts, K=10, refine=16, split=split)
     ts = np.arange(t_end - W + 1, t_end + 1)
     lb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
     best, topk, berr = lb.evaluate()
@@ -41,12 +41,12 @@ def time_kernel(lb, split, reps=50):
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     for _ in range(5):
         L.llampc_lookback_window_f32(lb.bank.packed.data_ptr(), lb.bank.N, lb.bank.Npad, lb.hist.data_ptr(), lb.W, 1, lb.W,
-                                     lb.Ts, lb.avg_err.data_ptr(), lb.best_key.data_ptr(), 0, int(lb.bank.geom_shared), split, st)
+                                     lb.Ts, lb.avg_err.data_ptr(), lb.best_key.data_ptr(), None, 0, int(lb.bank.geom_shared), split, st)
     torch.cuda.synchronize()
     ev[0].record()
     for _ in range(reps):
         L.llampc_lookback_window_f32(lb.bank.packed.data_ptr(), lb.bank.N, lb.bank.Npad, lb.hist.data_ptr(), lb.W, 1, lb.W,
-                                     lb.Ts, lb.avg_err.data_ptr(), lb.best_key.data_ptr(), 0, int(lb.bank.geom_shared), split, st)
+                                     lb.Ts, lb.avg_err.data_ptr(), lb.best_key.data_ptr(), None, 0, int(lb.bank.geom_shared), split, st)
     ev[1].record()
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1]) / reps
@@ -70,7 +70,7 @@ if __name__ == "__main__":
     all14 = {k: p[k] * (1 + 0.1 * rng.randn(8192)) for k in orc.PARAM_NAMES}
     run_case("all 14 varied", all14, 50, 1200)
     big = orc.make_bank(1 << 20, 5, variation=c2var)
-    lbb = LookBack(big, W=50, Ts=Ts, K=10, refine=32)
+    lbb = LookBack(big, W=50, Ts=Ts, K=10, refine=16)
     ts = np.arange(551, 601)
     lbb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
     print("1M bank evaluate:", lbb.evaluate()[0])
@@ -84,4 +84,4 @@ if __name__ == "__main__":
         t = 700 + i
         lb.push(S[:, t], U[:, t], S[:, t + 1])
     dt = (time.perf_counter() - t0) / n
-    print("LookBack.push N=65536 W=50 K=10 refine=32: %.1f us per tick" % (dt * 1e6))
+    print("LookBack.push N=65536 W=50 K=10 refine=16: %.1f us per tick" % (dt * 1e6))
