@@ -260,6 +260,8 @@ def run_b200(args):
     st = torch.cuda.current_stream().cuda_stream
     bank = lb.bank
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    flush_sink = torch.zeros((), dtype=torch.int64, device=dev)
+    clean_l2 = os.environ.get("LLAMPC_BENCH_CLEAN_L2", "0") == "1"
 
     n_lists = L.llampc_lookback_num_lists(n_local, W_C2, 0)
     assert lb.fused and n_lists > 0
@@ -290,7 +292,9 @@ def run_b200(args):
         torch.cuda.synchronize()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for a, b in evs:
-            flush.fill_(1)                                     # evict L2 between timed iterations (not timed)
+            flush.fill_(1)                                     # evict L2 between timed iterations (not timed) ...
+            if clean_l2:
+                flush_sink.copy_(flush[:1 << 20].sum())        # ... and read it back so the lines left in L2 are clean
             a.record()
             fn()
             b.record()

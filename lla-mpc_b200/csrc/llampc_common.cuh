@@ -43,6 +43,25 @@ __device__ __forceinline__ u64 block_min_u64(u64 k, u64* sbuf) {
 
 __device__ __forceinline__ u64 u64_max(u64 a, u64 b) { return a > b ? a : b; }
 
+// block min for the selection kernels: the second stage is done by warp 0 alone (32 partials, one per lane),
+// so a round costs two barriers and ~60 instructions per thread instead of a 32-way scan in every thread.
+template <int NWARPS>
+__device__ __forceinline__ u64 block_min_u64_w0(u64 k, u64* sbuf) {
+    k = warp_min_u64(k);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) sbuf[warp] = k;
+    __syncthreads();
+    if (warp == 0) {
+        u64 r = lane < NWARPS ? sbuf[lane] : ~0ull;
+        r = warp_min_u64(r);
+        if (lane == 0) sbuf[NWARPS] = r;
+    }
+    __syncthreads();
+    const u64 r = sbuf[NWARPS];
+    __syncthreads();                       // sbuf is rewritten by the next round
+    return r;
+}
+
 // ascending bitonic sort of one key per lane (15 compare-exchange stages of 2 shuffles each)
 __device__ __forceinline__ u64 warp_sort_u64(u64 key, int lane) {
 #pragma unroll

@@ -37,6 +37,17 @@ __device__ __forceinline__ float atan_unit(float q) {
     return fmaf(q * s, p, q);
 }
 
+// atan(t) for |t| <= 0.5 (slip-angle tangents of a car that is not spinning): 5 coefficients, 1.0e-8.
+__device__ __forceinline__ float atan_half(float t) {
+    float s = t * t;
+    float p = -5.6081126704e-02f;
+    p = fmaf(p, s, 1.0436029272e-01f);
+    p = fmaf(p, s, -1.4229306540e-01f);
+    p = fmaf(p, s, 1.9998319291e-01f);
+    p = fmaf(p, s, -3.3333325341e-01f);
+    return fmaf(t * s, p, t);
+}
+
 #define LLAMPC_PIO2_HI 1.57079637050628662109375f
 #define LLAMPC_PIO2_LO (-4.37113900018624283e-8f)
 

@@ -92,7 +92,7 @@ __device__ __forceinline__ float accel_vx_only(const Cand& p, const Ctl& u, floa
 // ---------------------------------------------------------------------------------------------------
 // Straight-line ("fast") variants for the look-back kernel: no branches inside the step.  The tyre atan is
 // branch-free for any argument; the slip-angle atan and the tiny heading rotations are only valid on
-// |t| <= 1 and |e| <= 0.125, and `guard` accumulates max(|t|, 8|e|) so that the caller can redo the whole
+// |t| <= 0.5 and |e| <= 0.125, and `guard` accumulates max(2|t|, 8|e|) so that the caller can redo the whole
 // step with the general routines in the rare case the guard exceeds 1 (or is NaN).
 // ---------------------------------------------------------------------------------------------------
 template <bool MUFU_SIN>
@@ -103,10 +103,10 @@ __device__ __forceinline__ float pacejka_fast(float B, float C, float D, float a
 
 template <bool MUFU_SIN>
 __device__ __forceinline__ Deriv accel_fast(const Cand& p, const Ctl& u, float vx, float vy, float w, float& guard) {
-    const float inv = rcp_newton(fabsf(vx));
+    const float inv = rcp_approx(fabsf(vx));            // 1 ulp: the tangents are small, |error| <= 1.2e-7 |t|
     const float tf = fmaf(p.lf, w, vy) * inv, tr = fmaf(p.lr, w, -vy) * inv;
-    guard = fmaxf(guard, fmaxf(fabsf(tf), fabsf(tr)));
-    const float af = u.delta - atan_unit(tf), ar = atan_unit(tr);
+    guard = fmaxf(guard, 2.0f * fmaxf(fabsf(tf), fabsf(tr)));
+    const float af = u.delta - atan_half(tf), ar = atan_half(tr);
     const float Frx = drive_force(p, u.pwm, vx);
     const float Ffy = pacejka_fast<MUFU_SIN>(p.Bf, p.Cf, p.Df, af);
     const float Fry = pacejka_fast<MUFU_SIN>(p.Br, p.Cr, p.Dr, ar);
@@ -254,10 +254,10 @@ __device__ __forceinline__ float lookback_step_fast(const Cand& p, const HistRow
     sincos_tiny(e4, sd, cd);
     const float s4 = fmaf(r.q1.x, cd, r.q1.y * sd), c4 = fmaf(r.q1.y, cd, -r.q1.x * sd);
     guard = fmaxf(guard, 8.0f * fmaxf(fabsf(e3), fabsf(e4)));
-    const float inv4 = rcp_newton(fabsf(vx4));
+    const float inv4 = rcp_approx(fabsf(vx4));
     const float tf4 = fmaf(p.lf, w4, vy4) * inv4;
-    guard = fmaxf(guard, fabsf(tf4));
-    const float Ffy4 = pacejka_fast<MUFU_SIN>(p.Bf, p.Cf, p.Df, u.delta - atan_unit(tf4));
+    guard = fmaxf(guard, 2.0f * fabsf(tf4));
+    const float Ffy4 = pacejka_fast<MUFU_SIN>(p.Bf, p.Cf, p.Df, u.delta - atan_half(tf4));
     const float a4vx = fmaf(fmaf(-Ffy4, u.sd, drive_force(p, u.pwm, vx4)), p.inv_m, vy4 * w4);
     const float xd4 = fmaf(vx4, c4, -vy4 * s4), yd4 = fmaf(vx4, s4, vy4 * c4);
     // increment errors

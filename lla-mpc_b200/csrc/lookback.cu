@@ -18,7 +18,7 @@ constexpr int NUM_SMS = 148;
 // sy, sy+SY, ...; partial sums are combined in a fixed order so the result is run-to-run deterministic.
 // ---------------------------------------------------------------------------------------------------
 #ifndef LLAMPC_LB_MIN_BLOCKS
-#define LLAMPC_LB_MIN_BLOCKS 1
+#define LLAMPC_LB_MIN_BLOCKS 6
 #endif
 template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
 __global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB_MIN_BLOCKS)
@@ -111,9 +111,9 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
 // head and next key in registers so that the load of a popped list's successor is off the critical path.
 // out[0] = *best_key (then re-armed to ~0 for the next tick), out[1..K] = ascending top-K.
 // ---------------------------------------------------------------------------------------------------
-constexpr int MERGE_THREADS = 1024;
 constexpr int MERGE_LPT = 8;
 
+template <int MERGE_THREADS>
 __global__ void __launch_bounds__(MERGE_THREADS)
 topk_merge_lists_kernel(const u64* __restrict__ lists, int n_lists, int K, u64* __restrict__ best_key,
                         u64* __restrict__ out) {
@@ -140,7 +140,7 @@ topk_merge_lists_kernel(const u64* __restrict__ lists, int n_lists, int K, u64* 
         u64 mine = head[0];
 #pragma unroll
         for (int j = 1; j < MERGE_LPT; ++j) mine = u64_min(mine, head[j]);
-        const u64 sel = block_min_u64<MERGE_THREADS / 32>(mine, sbuf);
+        const u64 sel = block_min_u64_w0<MERGE_THREADS / 32>(mine, sbuf);
         if (threadIdx.x == 0) out[1 + r] = sel;
         if (sel == ~0ull || mine != sel) continue;
 #pragma unroll
@@ -381,9 +381,14 @@ extern "C" int llampc_lookback_num_lists(int N, int W, int split) {
 extern "C" int llampc_topk_merge_lists(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K,
                                        llampc_key_t* best_key, llampc_key_t* out, llampc_stream_t stream) {
     if (!cta_lists || !out || n_lists <= 0 || n_vehicles <= 0) return LLAMPC_E_ARG;
-    if (K < 0 || K > LLAMPC_LIST_LEN || n_lists > MERGE_THREADS * MERGE_LPT) return LLAMPC_E_RANGE;
-    topk_merge_lists_kernel<<<n_vehicles, MERGE_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(cta_lists, n_lists, K,
-                                                                                               best_key, out);
+    if (K < 0 || K > LLAMPC_LIST_LEN || n_lists > 1024 * MERGE_LPT) return LLAMPC_E_RANGE;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (n_lists <= 128 * MERGE_LPT)
+        topk_merge_lists_kernel<128><<<n_vehicles, 128, 0, st>>>(cta_lists, n_lists, K, best_key, out);
+    else if (n_lists <= 256 * MERGE_LPT)
+        topk_merge_lists_kernel<256><<<n_vehicles, 256, 0, st>>>(cta_lists, n_lists, K, best_key, out);
+    else
+        topk_merge_lists_kernel<1024><<<n_vehicles, 1024, 0, st>>>(cta_lists, n_lists, K, best_key, out);
     return (int)cudaGetLastError();
 }
 
