@@ -274,9 +274,9 @@ def run_b200(args):
                                           int(bank.geom_shared), 0, st)
         _lib.check(rc, "K1")
         _lib.check(L.llampc_topk_merge_lists(lb.cta_lists.data_ptr(), n_lists, 1, 10, lb.best_key.data_ptr(),
-                                             lb.topk_keys.data_ptr(), st), "K4'")
+                                             lb.result.data_ptr(), st), "K4'")
         if world > 1:
-            td.all_reduce(lb.topk_keys[:1], op=td.ReduceOp.MIN)
+            td.all_reduce(lb.result[:1], op=td.ReduceOp.MIN)
 
     def k1_only():
         L.llampc_lookback_window_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2, TS,
@@ -340,13 +340,15 @@ def run_b200(args):
     # ---- end to end through the public API (rank-local bank; host inputs every tick)
     e2e = None
     lat = None
-    if world == 1:
-        lbe = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=16)
+    if True:
+        lbe = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=16, idx_offset=lo, group=(td.group.WORLD if world > 1 else None))
         for t in range(W_C2):
             lbe.push(S[:, t], U[:, t], S[:, t + 1])
         for t in range(W_C2, W_C2 + max(args.warmup, 3)):
             lbe.push(S[:, t], U[:, t], S[:, t + 1])
         torch.cuda.synchronize()
+        if world > 1:
+            td.barrier()
         lats = []
         t_base = W_C2 + max(args.warmup, 3)
         t0 = time.perf_counter()
@@ -356,11 +358,19 @@ def run_b200(args):
             best, topk, err = lbe.push(S[:, t], U[:, t], S[:, t + 1])
             lats.append(time.perf_counter() - a)
         wall = time.perf_counter() - t0
-        h2d = _lib.HIST_ROW * 4 + _lib.HIST64_ROW * 8
-        d2h = (1 + lbe.Kt) * 8 + lbe.Kt * 8
+        if world > 1:
+            wt = torch.tensor([wall], dtype=torch.float64, device=dev)
+            td.all_reduce(wt, op=td.ReduceOp.MAX)
+            wall = float(wt.item())
+        h2d = _lib.HIST_ROW * 4 + _lib.HIST64_ROW * 8          # the row travels as kernel parameters
+        d2h = (1 + 2 * lbe.Kt) * 8
         e2e = {"value": steps_per_tick * args.steps / wall, "unit": "steps/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "api": "LookBack.push (refine=16: fp64 re-score of the 16 finalists included)"}
+               "d2h_bytes_per_step": d2h, "api": "LookBack.push (host NumPy transition in; fp64 re-score of the 16 finalists and, for N > 1, the finalist all-gather included; arg-min + top-10 indices out)"}
         lat = {"p50_us": float(np.percentile(lats, 50) * 1e6), "p95_us": float(np.percentile(lats, 95) * 1e6)}
+
+    extras = {}
+    if world == 1 and not args.no_extras:
+        extras = secondary_configs(torch, L, _lib, S, U, st, flush)
 
     if rank != 0:
         if world > 1:
@@ -375,11 +385,76 @@ def run_b200(args):
     if e2e:
         line["e2e"] = e2e
         line["tick_latency"] = lat
+    if extras:
+        line["other_configs"] = extras
     if cpu_base:
         line["cpu_baseline"] = cpu_base
     print(json.dumps(line), flush=True)
     if world > 1:
         td.destroy_process_group()
+
+
+def secondary_configs(torch, L, _lib, S, U, st, flush):
+    """Device-timed throughput of the other BASELINE configs on one GPU (same units: RK4 steps/s)."""
+    from llampc_b200.mpc import LookBack, LookAhead
+    out = {}
+
+    def time_it(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+        for a, b in evs:
+            flush.fill_(1)
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        return float(np.mean([a.elapsed_time(b) for a, b in evs])) * 1e-3
+
+    # C5 on one GPU: 1,048,576 candidates x 50 (the sharded sweep's single-GPU reference point)
+    lb = LookBack(make_bank(N_C5, seed=5), W=W_C2, Ts=TS, K=10, refine=0)
+    ts = np.arange(0, W_C2)
+    lb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
+    n_lists = L.llampc_lookback_num_lists(N_C5, W_C2, 0)
+
+    def c5():
+        L.llampc_lookback_window_f32(lb.bank.packed.data_ptr(), N_C5, lb.bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2, TS,
+                                     lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), 0,
+                                     int(lb.bank.geom_shared), 0, st)
+        L.llampc_topk_merge_lists(lb.cta_lists.data_ptr(), n_lists, 1, 10, lb.best_key.data_ptr(), lb.result.data_ptr(), st)
+    dt = time_it(c5, 20)
+    out["C5_1gpu_lookback_1048576x50"] = {"steps_per_s": N_C5 * W_C2 / dt, "ms_per_tick": dt * 1e3}
+    del lb
+
+    # C1: 1,024 candidates x 20 (the reference's own CPU-runnable case): latency-bound
+    lb1 = LookBack(make_bank(1024, seed=0), W=20, Ts=TS, K=10, refine=0)
+    ts = np.arange(0, 20)
+    lb1.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
+    nl1 = L.llampc_lookback_num_lists(1024, 20, 0)
+
+    def c1():
+        L.llampc_lookback_window_f32(lb1.bank.packed.data_ptr(), 1024, lb1.bank.Npad, lb1.hist.data_ptr(), 20, 1, 20, TS,
+                                     lb1.avg_err.data_ptr(), lb1.best_key.data_ptr(), lb1.cta_lists.data_ptr(), 0,
+                                     int(lb1.bank.geom_shared), 0, st)
+        L.llampc_topk_merge_lists(lb1.cta_lists.data_ptr(), nl1, 1, 10, lb1.best_key.data_ptr(), lb1.result.data_ptr(), st)
+    dt = time_it(c1, 50)
+    out["C1_lookback_1024x20"] = {"steps_per_s": 1024 * 20 / dt, "us_per_tick": dt * 1e6}
+
+    # C3 look-ahead: 16,384 models x 32 control sequences x 20-step horizon with the raceline-tracking cost
+    M, K, H = 16384, 32, 20
+    rng = np.random.RandomState(3)
+    t0 = W_C2
+    u_nom = U[:, t0:t0 + H].T
+    Useq = u_nom[None] + np.stack([0.1 * rng.randn(K, H), 0.05 * rng.randn(K, H)], axis=-1)
+    Useq[..., 0] = np.clip(Useq[..., 0], -0.1, 1.0)
+    Useq[..., 1] = np.clip(Useq[..., 1], -0.35, 0.35)
+    xref = S[:2, t0:t0 + H + 1]
+    la = LookAhead(make_bank(M, seed=2), Ts=TS)
+    plan = la.plan(S[:, t0], Useq, xref, U[:, t0 - 1])
+    dt = time_it(plan.run, 20)
+    out["C3_lookahead_16384x32x20"] = {"steps_per_s": M * K * H / dt, "ms_per_call": dt * 1e3}
+    return out
 
 
 def main():
@@ -389,6 +464,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
+    ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs (C1, C3, C5 on one GPU)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

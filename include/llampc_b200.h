@@ -114,26 +114,25 @@ int llampc_refine_f64(const double* bank64, int N, const double* hist64, int W, 
  * ------------------------------------------------------------------------------------------- */
 typedef struct llampc_tick {
     const float* bank; int N; int Npad;
-    float* hist;                    /* device ring [W][LLAMPC_HIST_ROW]                                  */
-    const float* row32_h;           /* pinned host row to upload into `slot`, or NULL (ring already set) */
+    float* hist;                    /* device ring [W][LLAMPC_HIST_ROW]                                    */
+    const float* row32_h;           /* HOST row (LLAMPC_HIST_ROW floats) for ring slot `slot`, or NULL: it is
+                                       passed to K1 as a kernel parameter (no separate H2D copy)           */
     int slot; int W; double Ts;
     int geom_shared; int split; int idx_offset;
-    float* avg_err;                 /* [N]                                                               */
-    llampc_key_t* best_key;         /* [1]                                                               */
-    int K;                          /* top-K wanted by the caller (rt.py:360 uses 10)                    */
-    int n_refine;                   /* 0 = no fp64 re-score                                              */
+    float* avg_err;                 /* [N] or NULL (fused path only)                                       */
+    llampc_key_t* best_key;         /* [1]; armed (~0ull) once by the caller with llampc_fill_keys         */
+    int K;                          /* top-K wanted by the caller (rt.py:360 uses 10)                      */
+    int n_refine;                   /* 0 = no fp64 re-score; Kt = max(K, n_refine) finalists are produced  */
     llampc_key_t* cta_lists;        /* [n_lists][LLAMPC_LIST_LEN] or NULL; with Kt <= LLAMPC_LIST_LEN selects the
-                                       fused path (K1 + list merge: two launches per tick, best_key must have
-                                       been armed once with llampc_fill_keys)                               */
+                                       fused path (K1 + list merge: two launches per tick)                 */
     llampc_key_t* topk_scratch; unsigned* topk_counter;   /* only for the unfused path (Kt > LLAMPC_LIST_LEN)    */
-    llampc_key_t* topk_keys;        /* [LLAMPC_LIST_LEN + 1 or 1 + Kt]: best key, then Kt keys ascending   */
-    const double* bank64;           /* [LLAMPC_NPARAM][N] (n_refine > 0)                                 */
-    double* hist64;                 /* device ring [W][LLAMPC_HIST64_ROW] (n_refine > 0)                 */
-    const double* row64_h;          /* pinned host row for hist64, or NULL                               */
-    double* refine_err64;           /* [Kt]                                                              */
-    llampc_key_t* out_keys_h;       /* pinned [1 + Kt]: best_key, then topk_keys                         */
-    double* out_err64_h;            /* pinned [Kt] (n_refine > 0)                                        */
-    int sync;                       /* non-zero: cudaStreamSynchronize before returning                  */
+    const double* bank64;           /* [LLAMPC_NPARAM][N] (n_refine > 0)                                   */
+    double* hist64;                 /* device ring [W][LLAMPC_HIST64_ROW] (n_refine > 0)                   */
+    const double* row64_h;          /* HOST row for hist64 (kernel parameter of the re-score), or NULL     */
+    llampc_key_t* result;           /* device, 1 + 2*Kt words: best key | Kt finalist keys | Kt fp64 scores */
+    llampc_key_t* result_h;         /* pinned host, same layout; with sync != 0 the finalists come back
+                                       ordered by score (fp64 if re-scored), ties by lower index           */
+    int sync;                       /* non-zero: cudaStreamSynchronize + host ordering before returning    */
 } llampc_tick_t;
 
 int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stream);

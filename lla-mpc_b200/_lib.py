@@ -27,9 +27,9 @@ class Tick(C.Structure):
                 ("hist", _vp), ("row32_h", _vp), ("slot", _i), ("W", _i), ("Ts", _d),
                 ("geom_shared", _i), ("split", _i), ("idx_offset", _i),
                 ("avg_err", _vp), ("best_key", _vp), ("K", _i), ("n_refine", _i),
-                ("cta_lists", _vp), ("topk_scratch", _vp), ("topk_counter", _vp), ("topk_keys", _vp),
-                ("bank64", _vp), ("hist64", _vp), ("row64_h", _vp), ("refine_err64", _vp),
-                ("out_keys_h", _vp), ("out_err64_h", _vp), ("sync", _i)]
+                ("cta_lists", _vp), ("topk_scratch", _vp), ("topk_counter", _vp),
+                ("bank64", _vp), ("hist64", _vp), ("row64_h", _vp),
+                ("result", _vp), ("result_h", _vp), ("sync", _i)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/llampc_b200.h

@@ -5,6 +5,8 @@
 #include "llampc_common.cuh"
 #include "llampc_model.cuh"
 #include "llampc_model_f64.cuh"
+#include <math.h>
+#include <string.h>
 
 namespace llampc {
 
@@ -20,11 +22,15 @@ constexpr int NUM_SMS = 148;
 #ifndef LLAMPC_LB_MIN_BLOCKS
 #define LLAMPC_LB_MIN_BLOCKS 6
 #endif
+// The newest history row can travel with the launch as a kernel parameter (80 bytes) instead of a separate
+// H2D copy: every CTA patches its shared-memory copy of ring slot `slot`, CTA 0 also stores it to the ring.
+struct NewRow { float v[LLAMPC_HIST_ROW]; int slot; };
+
 template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
 __global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB_MIN_BLOCKS)
 lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
                        long hist_stride_floats, StepSize z, float* __restrict__ avg_err, u64* __restrict__ best_key,
-                       u64* __restrict__ cta_lists, int idx_offset) {
+                       u64* __restrict__ cta_lists, int idx_offset, NewRow nr) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ u64 skeys[LB_THREADS];
@@ -49,6 +55,15 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
     const Cand p = load_cand(bank, Npad, valid ? cand : N - 1);   // overlaps the bulk copy
 
     mbar_wait(&mbar, 0);
+    if (nr.slot >= 0) {                            // uniform over the grid
+        if (tid < LLAMPC_HIST_ROW / 4) {
+            const float4 q = make_float4(nr.v[4 * tid], nr.v[4 * tid + 1], nr.v[4 * tid + 2], nr.v[4 * tid + 3]);
+            srow[nr.slot * 5 + tid] = q;
+            if (blockIdx.x == 0 && blockIdx.y == 0)
+                reinterpret_cast<float4*>(const_cast<float*>(hist))[nr.slot * 5 + tid] = q;
+        }
+        __syncthreads();
+    }
 
     float acc = 0.0f;
     for (int w = sy; w < W; w += SY) {
@@ -214,15 +229,17 @@ topk_kernel(const float* __restrict__ err, int N, int idx_offset, int K, int per
 // ---------------------------------------------------------------------------------------------------
 // fp64 re-score of finalists: one warp per finalist, lanes stride over the window.
 // ---------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128)
-refine_f64_kernel(const double* __restrict__ bank64, int N, const double* __restrict__ hist64, int W, double h,
-                  const u64* __restrict__ keys, int n_fin, int idx_offset, double* __restrict__ out) {
-    const int f = blockIdx.x * 4 + (threadIdx.x >> 5);
-    const int lane = threadIdx.x & 31;
-    if (f >= n_fin) return;
+struct NewRow64 { double v[LLAMPC_HIST64_ROW]; int slot; };
+
+__global__ void __launch_bounds__(64)
+refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__ hist64, int W, double h,
+                  const u64* __restrict__ keys, int idx_offset, double* __restrict__ out, NewRow64 nr) {
+    __shared__ double spart[2];
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    if (nr.slot >= 0 && f == 0 && tid < LLAMPC_HIST64_ROW) hist64[(size_t)nr.slot * LLAMPC_HIST64_ROW + tid] = nr.v[tid];
     const long long ci = (long long)(unsigned)(keys[f] & 0xffffffffull) - idx_offset;
     if (ci < 0 || ci >= N) {                       // padded key (~0) or foreign shard
-        if (lane == 0) out[f] = __longlong_as_double(0x7ff8000000000000ll);
+        if (tid == 0) out[f] = __longlong_as_double(0x7ff8000000000000ll);
         return;
     }
     Params64 p;
@@ -230,12 +247,13 @@ refine_f64_kernel(const double* __restrict__ bank64, int N, const double* __rest
 #pragma unroll
     for (int j = 0; j < LLAMPC_NPARAM; ++j) pp[j] = bank64[(size_t)j * N + ci];
     double acc = 0.0;
-    for (int w = lane; w < W; w += 32) {
-        const double* r = hist64 + (size_t)w * LLAMPC_HIST64_ROW;
-        double y0[6], y1[6];
+    for (int w = tid; w < W; w += 64) {
+        double r[LLAMPC_HIST64_ROW];
 #pragma unroll
-        for (int i = 0; i < 6; ++i) y0[i] = r[i];
-        rk4_step64(p, y0, r[6], r[7], h, y1);
+        for (int i = 0; i < LLAMPC_HIST64_ROW; ++i)
+            r[i] = (w == nr.slot) ? nr.v[i] : hist64[(size_t)w * LLAMPC_HIST64_ROW + i];
+        double y1[6];
+        rk4_step64(p, r, r[6], r[7], h, y1);
         double e = 0.0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) { double d = y1[i] - r[8 + i]; e += d * d; }
@@ -243,7 +261,9 @@ refine_f64_kernel(const double* __restrict__ bank64, int N, const double* __rest
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) out[f] = acc / W;
+    if (lane == 0) spart[tid >> 5] = acc;
+    __syncthreads();
+    if (tid == 0) out[f] = (spart[0] + spart[1]) / W;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -323,7 +343,7 @@ static StepSize make_step(double Ts) {
 template <int SY, bool GEOM, bool MUFU>
 static int launch_lookback(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
                            int hist_stride_rows, double Ts, float* avg_err, u64* best_key, u64* cta_lists,
-                           int idx_offset, cudaStream_t st) {
+                           int idx_offset, const NewRow& nr, cudaStream_t st) {
     auto kern = lookback_window_kernel<SY, GEOM, MUFU>;
     const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 : 0);
     if (smem > 48 * 1024) {
@@ -337,14 +357,14 @@ static int launch_lookback(const float* bank, int N, int Npad, const float* hist
     dim3 grid((N + CPB - 1) / CPB, n_vehicles);
     kern<<<grid, LB_THREADS, smem, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, hist, W,
                                          (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key, cta_lists,
-                                         idx_offset);
+                                         idx_offset, nr);
     return (int)cudaGetLastError();
 }
 
-extern "C" int llampc_lookback_window_f32(const float* bank, int N, int Npad, const float* hist, int W,
-                                          int n_vehicles, int hist_stride_rows, double Ts, float* avg_err,
-                                          llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
-                                          int geom_shared, int split, llampc_stream_t stream) {
+static int lookback_window_impl(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
+                                int hist_stride_rows, double Ts, float* avg_err, llampc_key_t* best_key,
+                                llampc_key_t* cta_lists, int idx_offset, int geom_shared, int split,
+                                const NewRow& nr, llampc_stream_t stream) {
     if (!bank || !hist || (!best_key && !cta_lists && !avg_err) || N <= 0 || Npad < N || n_vehicles <= 0 || hist_stride_rows < W) return LLAMPC_E_ARG;
     if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
     if (!aligned16(bank) || !aligned16(hist) || (hist_stride_rows * LLAMPC_HIST_ROW * 4) % 16) return LLAMPC_E_ALIGN;
@@ -355,10 +375,10 @@ extern "C" int llampc_lookback_window_f32(const float* bank, int N, int Npad, co
     if (split > W) split = 1;
 #define LB_CASE(SYV)                                                                                                  \
     case SYV:                                                                                                         \
-        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, st)   \
-                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, st); \
-        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, st)            \
-                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, st);
+        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, st)   \
+                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, st); \
+        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, st)            \
+                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, st);
     switch (split) {
         LB_CASE(1)
         LB_CASE(2)
@@ -366,6 +386,16 @@ extern "C" int llampc_lookback_window_f32(const float* bank, int N, int Npad, co
         default: return LLAMPC_E_ARG;
     }
 #undef LB_CASE
+}
+
+extern "C" int llampc_lookback_window_f32(const float* bank, int N, int Npad, const float* hist, int W,
+                                          int n_vehicles, int hist_stride_rows, double Ts, float* avg_err,
+                                          llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
+                                          int geom_shared, int split, llampc_stream_t stream) {
+    NewRow nr;
+    nr.slot = -1;
+    return lookback_window_impl(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists,
+                                idx_offset, geom_shared, split, nr, stream);
 }
 
 extern "C" int llampc_lookback_num_lists(int N, int W, int split) {
@@ -425,8 +455,10 @@ extern "C" int llampc_refine_f64(const double* bank64, int N, const double* hist
                                  const llampc_key_t* keys, int n_fin, int idx_offset, double* out_err64,
                                  llampc_stream_t stream) {
     if (!bank64 || !hist64 || !keys || !out_err64 || N <= 0 || W <= 0 || n_fin <= 0) return LLAMPC_E_ARG;
-    refine_f64_kernel<<<(n_fin + 3) / 4, 128, 0, static_cast<cudaStream_t>(stream)>>>(bank64, N, hist64, W, Ts, keys,
-                                                                                      n_fin, idx_offset, out_err64);
+    NewRow64 nr;
+    nr.slot = -1;
+    refine_f64_kernel<<<n_fin, 64, 0, static_cast<cudaStream_t>(stream)>>>(bank64, N, const_cast<double*>(hist64), W, Ts,
+                                                                           keys, idx_offset, out_err64, nr);
     return (int)cudaGetLastError();
 }
 
@@ -460,51 +492,84 @@ extern "C" int llampc_forces_batch_f32(const float* bank, int N, int Npad, const
 }
 
 extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stream) {
-    if (!t || !t->bank || !t->hist || !t->avg_err || !t->best_key || !t->out_keys_h) return LLAMPC_E_ARG;
+    if (!t || !t->bank || !t->hist || !t->best_key || !t->result || !t->result_h) return LLAMPC_E_ARG;
     if (t->slot < 0 || t->slot >= t->W || t->K < 0 || t->n_refine < 0) return LLAMPC_E_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     const int Kt = t->K > t->n_refine ? t->K : t->n_refine;
     if (Kt > LLAMPC_MAX_K) return LLAMPC_E_RANGE;
-    if (t->row32_h)
-        LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->hist + (size_t)t->slot * LLAMPC_HIST_ROW, t->row32_h,
-                                        LLAMPC_HIST_ROW * sizeof(float), cudaMemcpyHostToDevice, st));
-    if (t->n_refine > 0 && t->row64_h)
-        LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->hist64 + (size_t)t->slot * LLAMPC_HIST64_ROW, t->row64_h,
-                                        LLAMPC_HIST64_ROW * sizeof(double), cudaMemcpyHostToDevice, st));
-    int rc;
     const bool fused = t->cta_lists != nullptr && Kt <= LLAMPC_LIST_LEN;
-    if (!t->topk_keys) return LLAMPC_E_ARG;
+    llampc_key_t* keys = t->result;                                  // [0] best, [1..Kt] finalists
+    double* errs = reinterpret_cast<double*>(t->result + 1 + Kt);    // [Kt] fp64 scores
+    NewRow nr;
+    nr.slot = -1;
+    if (t->row32_h) {                                                // the row rides in the kernel parameters
+        for (int i = 0; i < LLAMPC_HIST_ROW; ++i) nr.v[i] = t->row32_h[i];
+        nr.slot = t->slot;
+    }
+    int rc;
     if (fused) {
-        // K1 (block arg-min + per-CTA sorted lists) -> list merge (also moves best_key to topk_keys[0] and re-arms it)
-        rc = llampc_lookback_window_f32(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key,
-                                        t->cta_lists, t->idx_offset, t->geom_shared, t->split, stream);
+        // K1 (block arg-min + per-CTA sorted lists) -> list merge (also moves best_key to keys[0] and re-arms it)
+        rc = lookback_window_impl(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key,
+                                  t->cta_lists, t->idx_offset, t->geom_shared, t->split, nr, stream);
         if (rc) return rc;
         const int n_lists = llampc_lookback_num_lists(t->N, t->W, t->split);
-        rc = llampc_topk_merge_lists(t->cta_lists, n_lists, 1, Kt, t->best_key, t->topk_keys, stream);
+        rc = llampc_topk_merge_lists(t->cta_lists, n_lists, 1, Kt, t->best_key, keys, stream);
         if (rc) return rc;
     } else {
+        if (!t->avg_err) return LLAMPC_E_ARG;
         rc = llampc_fill_keys(t->best_key, 1, stream);
         if (rc) return rc;
-        rc = llampc_lookback_window_f32(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key,
-                                        nullptr, t->idx_offset, t->geom_shared, t->split, stream);
+        rc = lookback_window_impl(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key, nullptr,
+                                  t->idx_offset, t->geom_shared, t->split, nr, stream);
         if (rc) return rc;
-        LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->topk_keys, t->best_key, sizeof(llampc_key_t), cudaMemcpyDeviceToDevice, st));
+        LLAMPC_CUDA_TRY(cudaMemcpyAsync(keys, t->best_key, sizeof(llampc_key_t), cudaMemcpyDeviceToDevice, st));
         if (Kt > 0) {
             if (!t->topk_scratch || !t->topk_counter) return LLAMPC_E_ARG;
-            rc = llampc_topk_f32(t->avg_err, t->N, t->idx_offset, Kt, t->topk_scratch, t->topk_counter, t->topk_keys + 1,
-                                 stream);
+            rc = llampc_topk_f32(t->avg_err, t->N, t->idx_offset, Kt, t->topk_scratch, t->topk_counter, keys + 1, stream);
             if (rc) return rc;
         }
     }
-    LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->out_keys_h, t->topk_keys, (1 + Kt) * sizeof(llampc_key_t),
-                                    cudaMemcpyDeviceToHost, st));
-    if (Kt > 0 && t->n_refine > 0) {
-        if (!t->bank64 || !t->hist64 || !t->refine_err64 || !t->out_err64_h) return LLAMPC_E_ARG;
-        rc = llampc_refine_f64(t->bank64, t->N, t->hist64, t->W, t->Ts, t->topk_keys + 1, Kt, t->idx_offset,
-                               t->refine_err64, stream);
-        if (rc) return rc;
-        LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->out_err64_h, t->refine_err64, Kt * sizeof(double), cudaMemcpyDeviceToHost, st));
+    const bool refine = Kt > 0 && t->n_refine > 0;
+    if (refine) {
+        if (!t->bank64 || !t->hist64) return LLAMPC_E_ARG;
+        NewRow64 nr64;
+        nr64.slot = -1;
+        if (t->row64_h) {
+            for (int i = 0; i < LLAMPC_HIST64_ROW; ++i) nr64.v[i] = t->row64_h[i];
+            nr64.slot = t->slot;
+        }
+        refine_f64_kernel<<<Kt, 64, 0, st>>>(t->bank64, t->N, t->hist64, t->W, t->Ts, keys + 1, t->idx_offset, errs, nr64);
+        LLAMPC_CUDA_TRY(cudaGetLastError());
     }
-    if (t->sync) LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
+    LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->result_h, t->result, (size_t)(1 + Kt + (refine ? Kt : 0)) * 8,
+                                    cudaMemcpyDeviceToHost, st));
+    if (!t->sync) return 0;
+    LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
+    // order the finalists on the host: by fp64 score (ties: lower index), NaN / padded entries last
+    llampc_key_t* hk = t->result_h + 1;
+    double* he = reinterpret_cast<double*>(t->result_h + 1 + Kt);
+    if (!refine) {
+        for (int i = 0; i < Kt; ++i) {
+            const unsigned bits = (unsigned)(hk[i] >> 32);
+            float f;
+            memcpy(&f, &bits, 4);
+            he[i] = hk[i] == ~0ull ? NAN : (double)f;
+        }
+    }
+    for (int i = 1; i < Kt; ++i) {                                   // insertion sort, Kt <= 64
+        const llampc_key_t k = hk[i];
+        const double e = he[i];
+        const unsigned idx = (unsigned)(k & 0xffffffffull);
+        int j = i - 1;
+        while (j >= 0) {
+            const bool after = (he[j] != he[j]) ? (e == e) : (e == e && (e < he[j] || (e == he[j] && idx < (unsigned)(hk[j] & 0xffffffffull))));
+            if (!after) break;
+            hk[j + 1] = hk[j];
+            he[j + 1] = he[j];
+            --j;
+        }
+        hk[j + 1] = k;
+        he[j + 1] = e;
+    }
     return 0;
 }

@@ -37,6 +37,13 @@ class LookAhead:
         """x0 (6,) or (M,6); U (K,H,2) shared or (M,K,H,2); xref (2,H+1) [reference layout] or (M,2,H+1);
         uprev (2,) or (M,2); model_idx: optional (M,) rows of the bank to use (default: every model once).
         Returns J (M,K) float32->float64, best_k (M,), and x_final (M,K,6) if return_final."""
+        plan = self.plan(x0, U, xref, uprev, model_idx=model_idx, return_final=return_final)
+        plan.run()
+        return plan.fetch()
+
+    def plan(self, x0, U, xref, uprev, model_idx=None, return_final=False):
+        """Upload the inputs once and return a `RolloutPlan`: `.run()` enqueues the kernel on the current
+        stream (device-resident inputs), `.fetch()` copies J / best_k (/ x_final) back."""
         torch = self.torch
         dev = self.bank.device
         U = np.asarray(U)
@@ -60,20 +67,31 @@ class LookAhead:
             flags |= 4
         x0 = np.ascontiguousarray(x0, dtype=np.float64)
         n_x0 = 1 if x0.ndim == 1 else x0.shape[0]
-        x0d = torch.from_numpy(x0.reshape(n_x0, 6)).to(dev)
-        Ud, xrd, upd = self._padded(U), self._padded(xr), self._padded(uprev)
-        midx = None if model_idx is None else torch.as_tensor(np.asarray(model_idx, dtype=np.int32)).to(dev)
-        J = torch.empty((M, K), dtype=torch.float32, device=dev)
-        best = torch.empty(M, dtype=torch.int32, device=dev)
-        xf = torch.empty((M, K, 6), dtype=torch.float64, device=dev) if return_final else None
-        with torch.cuda.device(dev):
+        plan = RolloutPlan()
+        plan.owner, plan.M, plan.K, plan.H, plan.flags, plan.n_x0 = self, M, K, H, flags, n_x0
+        plan.x0 = torch.from_numpy(x0.reshape(n_x0, 6)).to(dev)
+        plan.U, plan.xref, plan.uprev = self._padded(U), self._padded(xr), self._padded(uprev)
+        plan.midx = None if model_idx is None else torch.as_tensor(np.asarray(model_idx, dtype=np.int32)).to(dev)
+        plan.J = torch.empty((M, K), dtype=torch.float32, device=dev)
+        plan.best = torch.empty(M, dtype=torch.int32, device=dev)
+        plan.xf = torch.empty((M, K, 6), dtype=torch.float64, device=dev) if return_final else None
+        return plan
+
+
+class RolloutPlan:
+    def run(self):
+        o = self.owner
+        torch = o.torch
+        with torch.cuda.device(o.bank.device):
             rc = _lib.lib().llampc_lookahead_rollout_f32(
-                self.bank.packed.data_ptr(), self.bank.Npad, None if midx is None else midx.data_ptr(), M,
-                x0d.data_ptr(), n_x0, Ud.data_ptr(), K, H, xrd.data_ptr(), upd.data_ptr(), flags,
-                self.qrp.ctypes.data, self.Ts, J.data_ptr(), best.data_ptr(),
-                None if xf is None else xf.data_ptr(), _lib.stream_ptr(torch))
+                o.bank.packed.data_ptr(), o.bank.Npad, None if self.midx is None else self.midx.data_ptr(), self.M,
+                self.x0.data_ptr(), self.n_x0, self.U.data_ptr(), self.K, self.H, self.xref.data_ptr(),
+                self.uprev.data_ptr(), self.flags, o.qrp.ctypes.data, o.Ts, self.J.data_ptr(), self.best.data_ptr(),
+                None if self.xf is None else self.xf.data_ptr(), _lib.stream_ptr(torch))
         _lib.check(rc, "llampc_lookahead_rollout_f32")
-        out = (J.cpu().numpy().astype(np.float64), best.cpu().numpy().astype(np.int64))
-        if return_final:
-            out += (xf.cpu().numpy(),)
+
+    def fetch(self):
+        out = (self.J.cpu().numpy().astype(np.float64), self.best.cpu().numpy().astype(np.int64))
+        if self.xf is not None:
+            out += (self.xf.cpu().numpy(),)
         return out

@@ -9,6 +9,8 @@ Window semantics (= the reference): W independent one-step RK4 predictions, each
 state; no decision until W transitions have been seen (rt.py:354-357).  The window is recomputed from the
 device-resident history ring every tick (stateless w.r.t. the bank, so the bank may be replaced at any time).
 """
+import ctypes as C
+
 import numpy as np
 
 from .. import _lib
@@ -55,21 +57,26 @@ class LookBack:
         self.hist64 = torch.zeros((self.W, _lib.HIST64_ROW), dtype=torch.float64, device=dev)
         self.avg_err = torch.empty(N, dtype=torch.float32, device=dev)
         self.best_key = torch.empty(1, dtype=torch.int64, device=dev)
-        ctas = L.llampc_topk_scratch_ctas(N)
-        self.topk_scratch = torch.empty(max(1, ctas * max(self.Kt, 1)), dtype=torch.int64, device=dev)
-        self.topk_counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        self.topk_keys = torch.empty(1 + max(self.Kt, _lib.LIST_LEN), dtype=torch.int64, device=dev)
+        self.best_key.fill_(-1)                                   # armed once; the merge kernel re-arms it every tick
         n_lists = L.llampc_lookback_num_lists(N, self.W, self.split)
         self.fused = self.Kt <= _lib.LIST_LEN and 0 < n_lists <= 8192
+        self.n_lists = n_lists
         self.cta_lists = torch.empty(max(1, n_lists) * _lib.LIST_LEN, dtype=torch.int64, device=dev) if self.fused else None
-        self.best_key.fill_(-1)                                   # armed once; the merge kernel re-arms it every tick
-        self.refine_err = torch.empty(max(self.Kt, 1), dtype=torch.float64, device=dev)
-        self.rows32_h = torch.zeros((self.W, _lib.HIST_ROW), dtype=torch.float32, pin_memory=True)
-        self.rows64_h = torch.zeros((self.W, _lib.HIST64_ROW), dtype=torch.float64, pin_memory=True)
-        self.out_keys_h = torch.zeros(1 + max(self.Kt, 1), dtype=torch.int64, pin_memory=True)
-        self.out_err_h = torch.zeros(max(self.Kt, 1), dtype=torch.float64, pin_memory=True)
-        self._out_keys_np = self.out_keys_h.numpy().view(np.uint64)
-        self._out_err_np = self.out_err_h.numpy()
+        if not self.fused:
+            ctas = L.llampc_topk_scratch_ctas(N)
+            self.topk_scratch = torch.empty(max(1, ctas * max(self.Kt, 1)), dtype=torch.int64, device=dev)
+            self.topk_counter = torch.zeros(1, dtype=torch.int32, device=dev)
+        # result: best key | Kt finalist keys | Kt fp64 scores  (the merge kernel writes LIST_LEN + 1 words)
+        words = max(1 + 2 * self.Kt, _lib.LIST_LEN + 1)
+        self.result = torch.zeros(words, dtype=torch.int64, device=dev)
+        self.result_h = torch.zeros(words, dtype=torch.int64, pin_memory=True)
+        self._res_keys = self.result_h.numpy().view(np.uint64)
+        self._res_errs = self.result_h.numpy().view(np.float64)
+        self.rows32_h = np.zeros((self.W, _lib.HIST_ROW), dtype=np.float32)
+        self.rows64_h = np.zeros((self.W, _lib.HIST64_ROW), dtype=np.float64)
+        self._r32_base, self._r64_base = self.rows32_h.ctypes.data, self.rows64_h.ctypes.data
+        self._xk, self._uk, self._xk1 = np.zeros(6), np.zeros(2), np.zeros(6)
+        self._xk_p, self._uk_p, self._xk1_p = self._xk.ctypes.data, self._uk.ctypes.data, self._xk1.ctypes.data
         self.window_count = 0
         self._next_slot = 0
         t = _lib.Tick()
@@ -79,28 +86,28 @@ class LookBack:
         t.avg_err, t.best_key = self.avg_err.data_ptr(), self.best_key.data_ptr()
         t.K, t.n_refine = self.K, self.n_refine
         t.cta_lists = self.cta_lists.data_ptr() if self.fused else None
-        t.topk_scratch, t.topk_counter = self.topk_scratch.data_ptr(), self.topk_counter.data_ptr()
-        t.topk_keys = self.topk_keys.data_ptr()
+        if not self.fused:
+            t.topk_scratch, t.topk_counter = self.topk_scratch.data_ptr(), self.topk_counter.data_ptr()
         if self.n_refine > 0:
             t.bank64, t.hist64 = self.bank.bank64.data_ptr(), self.hist64.data_ptr()
-            t.refine_err64, t.out_err64_h = self.refine_err.data_ptr(), self.out_err_h.data_ptr()
-        t.out_keys_h = self.out_keys_h.data_ptr()
+        t.result, t.result_h = self.result.data_ptr(), self.result_h.data_ptr()
         t.sync = 1
         self._tick = t
+        self._tick_ref = C.byref(t)
         self._L = L
+        self._stream_dev = torch.cuda.device(dev)
 
     # ------------------------------------------------------------------ history ring
     def _pack_row(self, slot, x_k, u_k, x_k1):
-        x_k = np.ascontiguousarray(x_k, dtype=np.float64)
-        u_k = np.ascontiguousarray(u_k, dtype=np.float64)
-        x_k1 = np.ascontiguousarray(x_k1, dtype=np.float64)
-        if x_k.shape != (6,) or u_k.shape != (2,) or x_k1.shape[0] < 4:
-            raise ValueError("push expects x_k (6,), u_k (2,), x_k1 (>=4,)")
-        r32 = self.rows32_h.data_ptr() + slot * _lib.HIST_ROW * 4
-        r64 = self.rows64_h.data_ptr() + slot * _lib.HIST64_ROW * 8
-        _lib.check(self._L.llampc_hist_row_pack_h(x_k.ctypes.data, u_k.ctypes.data, x_k1.ctypes.data, self.Ts,
-                                                  self.bank.lf_shared, self.bank.lr_shared, r32, r64),
-                   "llampc_hist_row_pack_h")
+        self._xk[:] = x_k
+        self._uk[:] = u_k
+        self._xk1[:4] = np.asarray(x_k1)[:4]
+        r32 = self._r32_base + slot * (_lib.HIST_ROW * 4)
+        r64 = self._r64_base + slot * (_lib.HIST64_ROW * 8)
+        rc = self._L.llampc_hist_row_pack_h(self._xk_p, self._uk_p, self._xk1_p, self.Ts, self.bank.lf_shared,
+                                            self.bank.lr_shared, r32, r64)
+        if rc:
+            _lib.check(rc, "llampc_hist_row_pack_h")
         return r32, r64
 
     def load_window(self, x_k, u_k, x_k1):
@@ -110,8 +117,9 @@ class LookBack:
             raise ValueError("load_window needs exactly W transitions")
         for j in range(self.W):
             self._pack_row(j, x_k[j], u_k[j], x_k1[j])
-        self.hist.copy_(self.rows32_h, non_blocking=True)
-        self.hist64.copy_(self.rows64_h, non_blocking=True)
+        torch = self.torch
+        self.hist.copy_(torch.from_numpy(self.rows32_h))
+        self.hist64.copy_(torch.from_numpy(self.rows64_h))
         self.window_count, self._next_slot = self.W, 0
 
     # ------------------------------------------------------------------ per-tick API
@@ -123,8 +131,9 @@ class LookBack:
         self._next_slot = (slot + 1) % self.W
         self.window_count = min(self.window_count + 1, self.W)
         if self.window_count < self.W:
-            self.hist[slot].copy_(self.rows32_h[slot], non_blocking=True)
-            self.hist64[slot].copy_(self.rows64_h[slot], non_blocking=True)
+            torch = self.torch
+            self.hist[slot].copy_(torch.from_numpy(self.rows32_h[slot]))
+            self.hist64[slot].copy_(torch.from_numpy(self.rows64_h[slot]))
             return None, None, None
         t = self._tick
         t.row32_h, t.row64_h, t.slot = r32, (r64 if self.n_refine > 0 else None), slot
@@ -140,26 +149,29 @@ class LookBack:
 
     def _run_tick(self):
         torch = self.torch
-        with torch.cuda.device(self.bank.device):
-            _lib.check(self._L.llampc_lookback_tick(self._tick, _lib.stream_ptr(torch)), "llampc_lookback_tick")
-        keys = self._out_keys_np
-        if self.Kt == 0:
+        with self._stream_dev:
+            rc = self._L.llampc_lookback_tick(self._tick_ref, torch.cuda.current_stream().cuda_stream)
+        if rc:
+            _lib.check(rc, "llampc_lookback_tick")
+        Kt = self.Kt
+        keys = self._res_keys
+        if Kt == 0:
             err, idx = decode_keys(keys[:1])
-            best, topk, best_err = int(idx[0]), idx[:0], float(err[0])
+            best, best_err = int(idx[0]), float(err[0])
             if self.group is not None:
-                k = _dist.minloc_allreduce(self.topk_keys[:1], self.group)
+                k = _dist.minloc_allreduce(self.result[:1], self.group)
                 err, idx = decode_keys(np.array([k], dtype=np.uint64))
                 best, best_err = int(idx[0]), float(err[0])
-            return best, topk, best_err
-        err32, idx = decode_keys(keys[1:1 + self.Kt])
-        scores = self._out_err_np[:self.Kt].copy() if self.n_refine > 0 else err32.astype(np.float64)
+            return best, np.zeros(0, dtype=np.int64), best_err
+        # finalists arrive ordered by score (fp64 when re-scored), ties by index, NaN / padding last
+        idx = (keys[1:1 + Kt] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        scores = self._res_errs[1 + Kt:1 + 2 * Kt]
         if self.group is not None:
             scores, idx = _dist.gather_finalists(scores, idx, self.group, self.bank.device)
-        order = np.lexsort((idx, scores))            # by score, ties by index (np.argmin / stable argsort)
-        order = order[~np.isnan(scores[order])] if np.isnan(scores).any() else order
-        topk = idx[order[:self.K]] if self.K > 0 else idx[:0]
-        b = order[0]
-        return int(idx[b]), topk, float(scores[b])
+            order = np.lexsort((idx, scores))
+            scores, idx = scores[order], idx[order]
+        n_ok = int(np.count_nonzero(scores == scores))
+        return int(idx[0]), idx[:min(self.K, n_ok)].copy(), float(scores[0])
 
     # ------------------------------------------------------------------ inspection
     def avg_errors(self):
@@ -167,4 +179,5 @@ class LookBack:
         return self.avg_err.cpu().numpy().astype(np.float64)
 
     def best_key_value(self):
-        return int(np.uint64(self._out_keys_np[0]))
+        """Packed fp32 key (float_bits(avg_err) << 32 | index) of the block arg-min of the last tick."""
+        return int(self._res_keys[0])
