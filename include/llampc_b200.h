@@ -82,6 +82,15 @@ int llampc_lookback_window_f32(const float* bank, int N, int Npad,
                                int geom_shared, int split, llampc_stream_t stream);
 int llampc_lookback_num_lists(int N, int W, int split);
 
+/* K1r  rolling window, the reference's own bookkeeping (error_windows = np.roll(...); [:, -1] = errors; mean,
+ * run_nmpc_orca_llampc_rt.py:349-358): one RK4 step per candidate for the newest transition (row32_h, HOST pointer,
+ * passed as kernel parameter), error column `slot` of err_ring [W][Npad] replaced, window mean re-summed from the
+ * ring.  emit = 0: only store the column (window not full yet).  CTA lists: ceil(N/128) lists. */
+int llampc_lookback_rolling_f32(const float* bank, int N, int Npad, const float* row32_h, int slot, int W,
+                                double Ts, float* err_ring, float* avg_err, llampc_key_t* best_key,
+                                llampc_key_t* cta_lists, int idx_offset, int geom_shared, int emit,
+                                llampc_stream_t stream);
+
 /* Fused top-K (K <= LLAMPC_LIST_LEN): K-way merge of the per-CTA lists of K1.  Per vehicle v:
  *   out[v][0] = best_key[v] (which is then re-armed to ~0ull for the next tick; skipped if best_key is NULL),
  *   out[v][1..K] = ascending top-K keys; out has LLAMPC_LIST_LEN + 1 keys per vehicle.
@@ -133,6 +142,12 @@ typedef struct llampc_tick {
     llampc_key_t* result_h;         /* pinned host, same layout; with sync != 0 the finalists come back
                                        ordered by score (fp64 if re-scored), ties by lower index           */
     int sync;                       /* non-zero: cudaStreamSynchronize + host ordering before returning    */
+    float* err_ring;                /* [W][Npad] per-tick error columns (rolling mode only)                */
+    int rolling;                    /* 0: recompute the whole window from the history ring (K1);
+                                       1: rolling mode (K1r): integrate only the newest row, replace ring column
+                                          `slot`, re-sum the ring; needs row32_h, cta_lists and Kt <= LLAMPC_LIST_LEN
+                                          (the fp64 re-score still walks the whole hist64 ring);
+                                       2: rolling mode while the window is filling: store the column, no decision */
 } llampc_tick_t;
 
 int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stream);

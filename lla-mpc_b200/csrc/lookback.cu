@@ -22,6 +22,35 @@ constexpr int NUM_SMS = 148;
 #ifndef LLAMPC_LB_MIN_BLOCKS
 #define LLAMPC_LB_MIN_BLOCKS 6
 #endif
+// CTA-level selection shared by K1 and the rolling kernel: every key-holding warp (the first KW warps) sorts its
+// 32 keys (registers + shuffles), sorted runs are merged pairwise through shared memory; warp 0 ends up with the
+// CTA's 32 smallest keys in ascending lane order.  Lane 0 = block arg-min (one atomicMin per CTA); lanes 0..15 =
+// this CTA's list for the top-K merge.
+template <int KW>
+__device__ __forceinline__ void cta_select_emit(u64 key, u64* skeys, int v, u64* __restrict__ best_key,
+                                                u64* __restrict__ cta_lists) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (warp < KW) key = warp_sort_u64(key, lane);
+    if (KW == 4) {
+        if (warp == 1 || warp == 3) skeys[warp * 32 + lane] = key;
+        __syncthreads();
+        if (warp == 0 || warp == 2) key = warp_merge_low32(key, skeys[(warp + 1) * 32 + 31 - lane], lane);
+        __syncthreads();
+        if (warp == 2) skeys[lane] = key;
+        __syncthreads();
+        if (warp == 0) key = warp_merge_low32(key, skeys[31 - lane], lane);
+    } else if (KW == 2) {
+        if (warp == 1) skeys[lane] = key;
+        __syncthreads();
+        if (warp == 0) key = warp_merge_low32(key, skeys[31 - lane], lane);
+    }
+    if (warp == 0) {
+        if (cta_lists && lane < LLAMPC_LIST_LEN)
+            cta_lists[((size_t)v * gridDim.x + blockIdx.x) * LLAMPC_LIST_LEN + lane] = key;
+        if (lane == 0 && best_key && key != ~0ull) atomicMin(best_key + v, key);
+    }
+}
+
 // The newest history row can travel with the launch as a kernel parameter (80 bytes) instead of a separate
 // H2D copy: every CTA patches its shared-memory copy of ring slot `slot`, CTA 0 also stores it to the ring.
 struct NewRow { float v[LLAMPC_HIST_ROW]; int slot; };
@@ -94,30 +123,47 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
         if (avg_err) avg_err[(size_t)v * N + cand] = err;
         key = pack_key(err, (unsigned)(idx_offset + cand));
     }
-    // CTA-level selection: every key-holding warp sorts its 32 keys (registers + shuffles), sorted runs are
-    // merged pairwise through shared memory; warp 0 ends up with the CTA's 32 smallest keys in ascending lane
-    // order.  Lane 0 = block arg-min (one atomicMin per CTA); lanes 0..15 = this CTA's list for the top-K merge.
-    constexpr int KW = CPB / 32;                   // warps that hold final scores: 4, 2 or 1
-    const int lane = tid & 31, warp = tid >> 5;
-    if (warp < KW) key = warp_sort_u64(key, lane);
-    if (KW == 4) {
-        if (warp == 1 || warp == 3) skeys[warp * 32 + lane] = key;
-        __syncthreads();
-        if (warp == 0 || warp == 2) key = warp_merge_low32(key, skeys[(warp + 1) * 32 + 31 - lane], lane);
-        __syncthreads();
-        if (warp == 2) skeys[lane] = key;
-        __syncthreads();
-        if (warp == 0) key = warp_merge_low32(key, skeys[31 - lane], lane);
-    } else if (KW == 2) {
-        if (warp == 1) skeys[lane] = key;
-        __syncthreads();
-        if (warp == 0) key = warp_merge_low32(key, skeys[31 - lane], lane);
+    cta_select_emit<CPB / 32>(key, skeys, v, best_key, cta_lists);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1r rolling window (the reference's own bookkeeping, rt.py:349-358): only the newest transition is integrated
+// (one RK4 step per candidate), its error replaces ring column `slot` of err_ring [W][Npad] (np.roll + write of
+// the last column), and the window mean is re-summed from the ring -- N steps and N*W*4 bytes per tick instead
+// of N*W steps.  emit = 0 while the window is filling (columns stored, no decision).
+// ---------------------------------------------------------------------------------------------------
+template <bool GEOM_SHARED>
+__global__ void __launch_bounds__(LB_THREADS)
+lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W, StepSize z, NewRow nr,
+                        float* __restrict__ err_ring, float* __restrict__ avg_err, u64* __restrict__ best_key,
+                        u64* __restrict__ cta_lists, int idx_offset, int emit) {
+    __shared__ u64 skeys[LB_THREADS];
+    const int tid = threadIdx.x;
+    const int cand = blockIdx.x * LB_THREADS + tid;
+    const bool valid = cand < N;
+    const int ci = valid ? cand : N - 1;
+    const Cand p = load_cand(bank, Npad, ci);
+    HistRow r;
+    r.q0 = make_float4(nr.v[0], nr.v[1], nr.v[2], nr.v[3]);
+    r.q1 = make_float4(nr.v[4], nr.v[5], nr.v[6], nr.v[7]);
+    r.q2 = make_float4(nr.v[8], nr.v[9], nr.v[10], nr.v[11]);
+    r.q3 = make_float4(nr.v[12], nr.v[13], nr.v[14], nr.v[15]);
+    r.q4 = make_float4(nr.v[16], nr.v[17], nr.v[18], nr.v[19]);
+    bool ok;
+    float e = lookback_step_fast<GEOM_SHARED, false>(p, r, z, ok);
+    if (!ok) e = lookback_step<GEOM_SHARED, false>(p, r, z);
+    e *= 0.25f;                                    // errors of rt.py:349 (mean over the 4 scored states)
+    if (valid) err_ring[(size_t)nr.slot * Npad + cand] = e;
+    if (!emit) return;                             // uniform
+    float sum = 0.0f;
+    for (int w = 0; w < W; ++w) sum += (w == nr.slot) ? e : __ldcg(err_ring + (size_t)w * Npad + ci);
+    const float err = sum / (float)W;
+    u64 key = ~0ull;
+    if (valid) {
+        if (avg_err) avg_err[cand] = err;
+        key = pack_key(err, (unsigned)(idx_offset + cand));
     }
-    if (warp == 0) {
-        if (cta_lists && lane < LLAMPC_LIST_LEN)
-            cta_lists[((size_t)v * gridDim.x + blockIdx.x) * LLAMPC_LIST_LEN + lane] = key;
-        if (lane == 0 && best_key && key != ~0ull) atomicMin(best_key + v, key);
-    }
+    cta_select_emit<LB_THREADS / 32>(key, skeys, 0, best_key, cta_lists);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -324,7 +370,8 @@ static int choose_split(int N, int W) {
         if (sy > W) break;
         long ctas = ((long)N * sy + LB_THREADS - 1) / LB_THREADS;
         long cost = ((ctas + NUM_SMS - 1) / NUM_SMS) * ((W + sy - 1) / sy);
-        if (best_cost < 0 || cost < best_cost) { best_cost = cost; best = sy; }
+        // a finer split must win by > 3 %: it doubles the number of per-CTA lists the top-K merge has to read
+        if (best_cost < 0 || cost * 100 < best_cost * 97) { best_cost = cost; best = sy; }
     }
     return best;
 }
@@ -396,6 +443,29 @@ extern "C" int llampc_lookback_window_f32(const float* bank, int N, int Npad, co
     nr.slot = -1;
     return lookback_window_impl(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists,
                                 idx_offset, geom_shared, split, nr, stream);
+}
+
+extern "C" int llampc_lookback_rolling_f32(const float* bank, int N, int Npad, const float* row32_h, int slot, int W,
+                                           double Ts, float* err_ring, float* avg_err, llampc_key_t* best_key,
+                                           llampc_key_t* cta_lists, int idx_offset, int geom_shared, int emit,
+                                           llampc_stream_t stream) {
+    if (!bank || !row32_h || !err_ring || N <= 0 || Npad < N || slot < 0 || slot >= W) return LLAMPC_E_ARG;
+    if (W <= 0 || W > LLAMPC_MAX_W) return LLAMPC_E_RANGE;
+    if (!aligned16(bank)) return LLAMPC_E_ALIGN;
+    NewRow nr;
+    for (int i = 0; i < LLAMPC_HIST_ROW; ++i) nr.v[i] = row32_h[i];
+    nr.slot = slot;
+    const int grid = (N + LB_THREADS - 1) / LB_THREADS;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    if (geom_shared)
+        lookback_rolling_kernel<true><<<grid, LB_THREADS, 0, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, W,
+                                                                   make_step(Ts), nr, err_ring, avg_err, best_key,
+                                                                   cta_lists, idx_offset, emit);
+    else
+        lookback_rolling_kernel<false><<<grid, LB_THREADS, 0, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, W,
+                                                                    make_step(Ts), nr, err_ring, avg_err, best_key,
+                                                                    cta_lists, idx_offset, emit);
+    return (int)cudaGetLastError();
 }
 
 extern "C" int llampc_lookback_num_lists(int N, int W, int split) {
@@ -507,7 +577,22 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
         nr.slot = t->slot;
     }
     int rc;
-    if (fused) {
+    if (t->rolling) {
+        // the reference's rolling bookkeeping: one new error column + ring re-sum, then the list merge
+        if (!t->err_ring || !t->row32_h || !fused) return LLAMPC_E_ARG;
+        rc = llampc_lookback_rolling_f32(t->bank, t->N, t->Npad, t->row32_h, t->slot, t->W, t->Ts, t->err_ring, t->avg_err,
+                                         t->best_key, t->cta_lists, t->idx_offset, t->geom_shared, t->rolling > 1 ? 0 : 1,
+                                         stream);
+        if (rc) return rc;
+        if (t->rolling > 1) {                                        // window still filling: column stored, no decision
+            if (t->n_refine > 0 && t->row64_h && t->hist64)
+                LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->hist64 + (size_t)t->slot * LLAMPC_HIST64_ROW, t->row64_h,
+                                                LLAMPC_HIST64_ROW * sizeof(double), cudaMemcpyHostToDevice, st));
+            return 0;
+        }
+        rc = llampc_topk_merge_lists(t->cta_lists, (t->N + LB_THREADS - 1) / LB_THREADS, 1, Kt, t->best_key, keys, stream);
+        if (rc) return rc;
+    } else if (fused) {
         // K1 (block arg-min + per-CTA sorted lists) -> list merge (also moves best_key to keys[0] and re-arms it)
         rc = lookback_window_impl(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key,
                                   t->cta_lists, t->idx_offset, t->geom_shared, t->split, nr, stream);

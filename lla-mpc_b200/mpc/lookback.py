@@ -35,11 +35,16 @@ class LookBack:
              fp64 score: the returned indices and errors are then exact in the reference's arithmetic
              (0 = fp32 scores only).  max(K, refine) <= 16 uses the fused two-launch tick (K1 writes per-CTA
              sorted lists, a K-way merge kernel finishes); larger values use the stand-alone top-K kernel.
+    mode     "recompute" (default): every tick re-integrates the whole W-row window from the history ring (N*W RK4
+             steps, stateless w.r.t. the bank); "rolling": the reference's own bookkeeping (rt.py:352-354) -- only the
+             newest transition is integrated and its error column replaces the oldest one in a device-resident
+             (W, N) ring, the window mean is re-summed (N steps + N*W*4 bytes per tick)
     idx_offset / group   multi-GPU: this rank's bank is the slice starting at global index idx_offset;
              `group` is a torch.distributed process group (None = single GPU)
     """
 
-    def __init__(self, bank_params, W, Ts=0.02, K=10, refine=16, device=None, idx_offset=0, group=None, split=0):
+    def __init__(self, bank_params, W, Ts=0.02, K=10, refine=16, device=None, idx_offset=0, group=None, split=0,
+                 mode="recompute"):
         torch = _lib.require_cuda()
         self.torch = torch
         self.bank = bank_params if isinstance(bank_params, ModelBank) else ModelBank(bank_params, device)
@@ -51,6 +56,9 @@ class LookBack:
         if self.Kt > _lib.MAX_K:
             raise ValueError("max(K, refine) must be <= %d" % _lib.MAX_K)
         self.idx_offset, self.group, self.split = int(idx_offset), group, int(split)
+        if mode not in ("recompute", "rolling"):
+            raise ValueError("mode must be 'recompute' or 'rolling'")
+        self.rolling = mode == "rolling"
         N = self.bank.N
         L = _lib.lib()
         self.hist = torch.zeros((self.W, _lib.HIST_ROW), dtype=torch.float32, device=dev)
@@ -59,7 +67,12 @@ class LookBack:
         self.best_key = torch.empty(1, dtype=torch.int64, device=dev)
         self.best_key.fill_(-1)                                   # armed once; the merge kernel re-arms it every tick
         n_lists = L.llampc_lookback_num_lists(N, self.W, self.split)
+        if self.rolling:
+            n_lists = max(n_lists, (N + 127) // 128)
         self.fused = self.Kt <= _lib.LIST_LEN and 0 < n_lists <= 8192
+        if self.rolling and not self.fused:
+            raise ValueError("rolling mode needs max(K, refine) <= %d and N <= 1,048,576" % _lib.LIST_LEN)
+        self.err_ring = torch.zeros((self.W, self.bank.Npad), dtype=torch.float32, device=dev) if self.rolling else None
         self.n_lists = n_lists
         self.cta_lists = torch.empty(max(1, n_lists) * _lib.LIST_LEN, dtype=torch.int64, device=dev) if self.fused else None
         if not self.fused:
@@ -92,6 +105,8 @@ class LookBack:
             t.bank64, t.hist64 = self.bank.bank64.data_ptr(), self.hist64.data_ptr()
         t.result, t.result_h = self.result.data_ptr(), self.result_h.data_ptr()
         t.sync = 1
+        if self.rolling:
+            t.err_ring, t.rolling = self.err_ring.data_ptr(), 1
         self._tick = t
         self._tick_ref = C.byref(t)
         self._L = L
@@ -130,17 +145,28 @@ class LookBack:
         r32, r64 = self._pack_row(slot, x_k, u_k, x_k1)
         self._next_slot = (slot + 1) % self.W
         self.window_count = min(self.window_count + 1, self.W)
+        t = self._tick
         if self.window_count < self.W:
             torch = self.torch
             self.hist[slot].copy_(torch.from_numpy(self.rows32_h[slot]))
-            self.hist64[slot].copy_(torch.from_numpy(self.rows64_h[slot]))
+            if self.rolling:                                     # store the error column, no decision yet
+                t.row32_h, t.row64_h, t.slot, t.rolling = r32, (r64 if self.n_refine > 0 else None), slot, 2
+                with self._stream_dev:
+                    rc = self._L.llampc_lookback_tick(self._tick_ref, torch.cuda.current_stream().cuda_stream)
+                t.rolling = 1
+                if rc:
+                    _lib.check(rc, "llampc_lookback_tick")
+                torch.cuda.current_stream().synchronize()        # row64_h is reused by the next push
+            else:
+                self.hist64[slot].copy_(torch.from_numpy(self.rows64_h[slot]))
             return None, None, None
-        t = self._tick
         t.row32_h, t.row64_h, t.slot = r32, (r64 if self.n_refine > 0 else None), slot
         return self._run_tick()
 
     def evaluate(self):
         """Score the window currently in the ring (after load_window); same return as push."""
+        if self.rolling:
+            raise _lib.LlampcError("evaluate()/load_window() re-integrate the window: use mode='recompute'")
         if self.window_count < self.W:
             return None, None, None
         t = self._tick

@@ -338,3 +338,48 @@ def test_error_codes_without_launch():
     assert L.llampc_lookback_window_f32(d.data_ptr(), 8, 8, d.data_ptr(), 2000, 1, 2000, 0.02, None, k.data_ptr(), None, 0, 1, 0, st) == -3
     assert L.llampc_lookback_window_f32(d.data_ptr() + 4, 8, 8, d.data_ptr(), 2, 1, 2, 0.02, None, k.data_ptr(), None, 0, 1, 0, st) == -2
     assert L.llampc_topk_f32(d.data_ptr(), 10, 0, 100, k.data_ptr(), k.data_ptr(), k.data_ptr(), st) == -3
+
+
+def test_lookback_rolling_mode_matches_reference_loop(history):
+    """mode='rolling' = the reference's np.roll bookkeeping (rt.py:352-358): one new error column per tick."""
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    bank = orc.make_bank(3000, seed=12)
+    W, K = 10, 10
+    for refine in (0, 16):
+        lb = LookBack(bank, W=W, Ts=Ts, K=K, refine=refine, mode="rolling")
+        ref = orc.LookBackOracle(bank, W, Ts, K)
+        for t in range(500, 500 + 4 * W):
+            got = lb.push(S[:, t], U[:, t], S[:, t + 1])
+            rbest, rtopk, ravg = ref.push(S[:, t], U[:, t], S[:, t + 1])
+            if rbest is None:
+                assert got == (None, None, None)
+                continue
+            assert got[0] == rbest and list(got[1]) == list(rtopk), t
+            _assert_scores(lb.avg_errors(), ravg, "rolling tick %d" % t)
+            if refine:
+                assert abs(got[2] - ravg[rbest]) <= 1e-9 * ravg[rbest]
+
+
+def test_refine_and_topk_c_abi_direct(history):
+    """llampc_refine_f64 and llampc_lookback_tick's unfused path (Kt > 16) through raw pointers."""
+    import torch
+    from llampc_b200 import _lib
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    bank = orc.make_bank(2000, seed=21)
+    lb = LookBack(bank, W=20, Ts=Ts, K=40, refine=0)            # Kt = 40 -> stand-alone top-K kernel
+    assert not lb.fused
+    best, topk, _ = _window(lb, S, U, 1000)
+    ref = np.mean(orc.window_errors(bank, S, U, 1000, 20, Ts), axis=1)
+    assert best == int(np.argmin(ref)) and list(topk) == list(np.argsort(ref, kind="stable")[:40])
+    # re-score arbitrary candidates in fp64
+    L = _lib.lib()
+    pick = np.array([7, 1999, 0, 512, 1234], dtype=np.uint64) + np.uint64(100)      # idx_offset = 100
+    keys = torch.from_numpy(pick.view(np.int64)).cuda()
+    out = torch.empty(5, dtype=torch.float64, device="cuda")
+    lb2 = LookBack(bank, W=20, Ts=Ts, K=10, refine=16)
+    _window(lb2, S, U, 1000)
+    _lib.check(L.llampc_refine_f64(lb2.bank.bank64.data_ptr(), 2000, lb2.hist64.data_ptr(), 20, Ts, keys.data_ptr(), 5, 100,
+                                   out.data_ptr(), torch.cuda.current_stream().cuda_stream))
+    np.testing.assert_allclose(out.cpu().numpy(), ref[[7, 1999, 0, 512, 1234]], rtol=1e-11)
