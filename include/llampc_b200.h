@@ -180,7 +180,8 @@ int llampc_forces_batch_f32(const float* bank, int N, int Npad, const double* x6
  *   x0         [n_x0][6] doubles (n_x0 = 1: shared start state, or M)
  *   U          [K][H][2] floats, or [M][K][H][2] if per_model_flags & 1
  *   xref       [H+1][2] floats (row h = reference position at step h), or [M][H+1][2] if per_model_flags & 2
- *   uprev      [2] floats, or [M][2] if per_model_flags & 4
+ *   uprev      [2] floats, or [M][2] if per_model_flags & 4   (per_model_flags & 8: diagnostics, force the
+ *              general branchy step instead of the straight-line one)
  *              shared U / xref tables are fetched with 16-byte-granular bulk copies: the buffers must be
  *              16-byte aligned and readable up to the next multiple of 16 bytes
  *   qrp_h      HOST pointer, 6 floats = Q00 Q11 R00 R11 P00 P11
@@ -191,6 +192,23 @@ int llampc_lookahead_rollout_f32(const float* bank, int Mpad, const int* model_i
                                  const float* xref, const float* uprev, int per_model_flags,
                                  const float* qrp_h, double Ts, float* J, int* best_k, double* x_final,
                                  llampc_stream_t stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Planner: ConstantSpeed (llampc/mpc/planner.py:12-67) for V vehicles, fp64.  Tables (device, doubles) come from
+ * a raceline (Track._load_raceline, llampc/tracks/track.py:52-83):
+ *   s    [n]      cumulative arc length of the raceline points (Spline2D.s)
+ *   xy   [n][2]   raceline points
+ *   coef [n-1][4*(2+n_mu)]  per segment: a b c d of x(s), of y(s), then of each speed profile v_j(s)
+ *   mus  [n_mu]   friction level of each speed profile (ascending)
+ * states [V][6] (x, y and vx are used), projidx_in [V], curr_mu [V] (or one value if mu_shared).
+ * Outputs (any may be NULL): xref32 [V][N+1][2] floats (feeds llampc_lookahead_rollout_f32 with
+ * per_model_flags & 2), xref64 [V][N+1][2] doubles, projidx_out [V], vr_out [V].
+ * ------------------------------------------------------------------------------------------- */
+int llampc_planner_constant_speed_f64(const double* s, const double* xy, const double* coef, const double* mus,
+                                      int n, int n_mu, const double* states, int V, const int* projidx_in,
+                                      const double* curr_mu, int mu_shared, int N, double Ts, double scale,
+                                      float* xref32, double* xref64, int* projidx_out, double* vr_out,
+                                      llampc_stream_t stream);
 
 /* K3  plant step for V independent vehicles: Model._integrate -> odeintRK6 (llampc/models/model.py:18-30,
  * llampc/utils/rk6.py:13-28), fp64 throughout.  params64 [V][LLAMPC_NPARAM], x64 [V][6], u64 [V][2] -> out64 [V][6]. */

@@ -52,6 +52,8 @@ PROTOTYPES = {
     "llampc_forces_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "llampc_lookahead_rollout_f32": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _d,
                                           _vp, _vp, _vp, _vp]),
+    "llampc_planner_constant_speed_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _i, _d, _d,
+                                               _vp, _vp, _vp, _vp, _vp]),
     "llampc_plant_rk6_f64": (_i, [_vp, _i, _vp, _vp, _d, _vp, _vp]),
 }
 

@@ -137,6 +137,20 @@ __device__ __forceinline__ void sincos_tiny(float e, float& sn, float& cs) {
     cs = fmaf(s, pc, 1.0f);
 }
 
+// sincos_small without the range branch (|d| <= 0.5 is the caller's guard)
+__device__ __forceinline__ void sincos_half(float d, float& sn, float& cs) {
+    float s = d * d;
+    float ps = -1.9736421589e-04f;
+    ps = fmaf(ps, s, 8.3332314830e-03f);
+    ps = fmaf(ps, s, -1.6666666503e-01f);
+    sn = fmaf(d * s, ps, d);
+    float pc = 2.4801587e-05f;
+    pc = fmaf(pc, s, -1.3888889e-03f);
+    pc = fmaf(pc, s, 4.1666668e-02f);
+    pc = fmaf(pc, s, -0.5f);
+    cs = fmaf(s, pc, 1.0f);
+}
+
 // MUFU variant (2 instructions); measured against the polynomial in tests/bench, not the default.
 __device__ __forceinline__ float sin_mufu(float t) { return __sinf(t); }
 

@@ -157,6 +157,67 @@ __device__ __forceinline__ void rk4_increment(const Cand& p, const Ctl& u, float
     inc[5] = h6 * ((a1.w + a4.w) + 2.0f * (a2.w + a3.w));
 }
 
+// Straight-line generic RK4 step (look-ahead rollouts): same arithmetic as rk4_increment, no branches.  `guard`
+// accumulates max(2|slip tangent|, 2|heading offset|); the step is only valid while guard <= 1.
+template <bool MUFU_SIN>
+__device__ __forceinline__ void rk4_increment_fast(const Cand& p, const Ctl& u, float s0, float c0, float vx0, float vy0,
+                                                   float w0, float h, float inc[6], float& guard) {
+    const float hh = 0.5f * h, h6 = h * (1.0f / 6.0f);
+    // weighted sums (k1 + 2 k2 + 2 k3 + k4) are accumulated stage by stage to keep few values live
+    Deriv a = accel_fast<MUFU_SIN>(p, u, vx0, vy0, w0, guard);
+    float sx = fmaf(vx0, c0, -vy0 * s0), sy = fmaf(vx0, s0, vy0 * c0);
+    float sw = w0, svx = a.vx, svy = a.vy, sdw = a.w;
+    float vx = fmaf(hh, a.vx, vx0), vy = fmaf(hh, a.vy, vy0), w = fmaf(hh, a.w, w0);
+    float sd, cd, d = hh * w0, dmax = fabsf(d);
+    sincos_half(d, sd, cd);
+    float sn = fmaf(s0, cd, c0 * sd), cs = fmaf(c0, cd, -s0 * sd);
+    // stage 2
+    a = accel_fast<MUFU_SIN>(p, u, vx, vy, w, guard);
+    sx = fmaf(2.0f, fmaf(vx, cs, -vy * sn), sx);
+    sy = fmaf(2.0f, fmaf(vx, sn, vy * cs), sy);
+    sw = fmaf(2.0f, w, sw); svx = fmaf(2.0f, a.vx, svx); svy = fmaf(2.0f, a.vy, svy); sdw = fmaf(2.0f, a.w, sdw);
+    d = hh * w;
+    dmax = fmaxf(dmax, fabsf(d));
+    vx = fmaf(hh, a.vx, vx0); vy = fmaf(hh, a.vy, vy0); w = fmaf(hh, a.w, w0);
+    sincos_half(d, sd, cd);
+    sn = fmaf(s0, cd, c0 * sd); cs = fmaf(c0, cd, -s0 * sd);
+    // stage 3
+    a = accel_fast<MUFU_SIN>(p, u, vx, vy, w, guard);
+    sx = fmaf(2.0f, fmaf(vx, cs, -vy * sn), sx);
+    sy = fmaf(2.0f, fmaf(vx, sn, vy * cs), sy);
+    sw = fmaf(2.0f, w, sw); svx = fmaf(2.0f, a.vx, svx); svy = fmaf(2.0f, a.vy, svy); sdw = fmaf(2.0f, a.w, sdw);
+    d = h * w;
+    dmax = fmaxf(dmax, fabsf(d));
+    vx = fmaf(h, a.vx, vx0); vy = fmaf(h, a.vy, vy0); w = fmaf(h, a.w, w0);
+    sincos_half(d, sd, cd);
+    sn = fmaf(s0, cd, c0 * sd); cs = fmaf(c0, cd, -s0 * sd);
+    // stage 4
+    a = accel_fast<MUFU_SIN>(p, u, vx, vy, w, guard);
+    sx += fmaf(vx, cs, -vy * sn);
+    sy += fmaf(vx, sn, vy * cs);
+    guard = fmaxf(guard, 2.0f * dmax);
+    inc[0] = h6 * sx;
+    inc[1] = h6 * sy;
+    inc[2] = h6 * (sw + w);
+    inc[3] = h6 * (svx + a.vx);
+    inc[4] = h6 * (svy + a.vy);
+    inc[5] = h6 * (sdw + a.w);
+}
+
+// out-of-line general step for the rare fallback of the rollout kernel
+struct Inc6 { float v[6]; };
+static __device__ __noinline__ Inc6 rk4_increment_general(const float4* __restrict__ bank, int Npad, int cand, float pwm,
+                                                          float delta, float s0, float c0, float vx0, float vy0,
+                                                          float w0, float h) {
+    const Cand p = load_cand(bank, Npad, cand);
+    Ctl u;
+    u.pwm = pwm; u.delta = delta;
+    sincos_small(delta, u.sd, u.cd);
+    Inc6 r;
+    rk4_increment<false>(p, u, s0, c0, vx0, vy0, w0, h, r.v);
+    return r;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // Look-back step.  All candidates start the step from the SAME measured state, so everything that does
 // not depend on the candidate was computed once on the host in fp64 and sits in the history row:
@@ -267,8 +328,9 @@ __device__ __forceinline__ float lookback_step_fast(const Cand& p, const HistRow
     const float ey = fmaf(z.h6_lo, sy, fmaf(z.h6, sy, -r.q3.z));
     const float epsi = fmaf(z.hh6_lo, sw, fmaf(z.hh6, sw, -r.q3.w));
     const float evx = fmaf(z.h6_lo, sv, fmaf(z.h6, sv, -r.q4.x)) - r.q4.y;
-    ok = guard <= 1.0f;                       // false for NaN as well
-    return fmaf(ex, ex, fmaf(ey, ey, fmaf(epsi, epsi, evx * evx)));
+    const float e2 = fmaf(ex, ex, fmaf(ey, ey, fmaf(epsi, epsi, evx * evx)));
+    ok = (guard <= 1.0f) && (e2 == e2);       // fmaxf drops NaN operands, so a NaN result is checked explicitly
+    return e2;
 }
 
 // out-of-line general step for the rare fallback: reloads the candidate and the history row itself so that

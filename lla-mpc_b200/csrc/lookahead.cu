@@ -9,6 +9,9 @@
 
 namespace llampc {
 
+#ifndef LLAMPC_LA_MIN_BLOCKS
+#define LLAMPC_LA_MIN_BLOCKS 4
+#endif
 constexpr int LA_THREADS = 128;
 constexpr int LA_WARPS = LA_THREADS / 32;
 
@@ -16,7 +19,7 @@ constexpr int LA_WARPS = LA_THREADS / 32;
 // is a warp shuffle).  Shared control table [K][H][2] and the reference path [H+1][2] are staged once per
 // CTA with TMA bulk copies.  Positions are integrated relative to the start position so the fp32 state
 // never carries the O(1) track coordinate.
-__global__ void __launch_bounds__(LA_THREADS)
+__global__ void __launch_bounds__(LA_THREADS, LLAMPC_LA_MIN_BLOCKS)
 lookahead_kernel(const float4* __restrict__ bank, int Mpad, const int* __restrict__ model_idx, int M,
                  const double* __restrict__ x0, int n_x0, const float* __restrict__ U, int K, int H,
                  const float* __restrict__ xref, const float* __restrict__ uprev, int per_model,
@@ -24,12 +27,14 @@ lookahead_kernel(const float4* __restrict__ bank, int Mpad, const int* __restric
                  float* __restrict__ J, int* __restrict__ best_k, double* __restrict__ x_final) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
-    const bool u_pm = per_model & 1, xref_pm = per_model & 2, uprev_pm = per_model & 4;
+    const bool u_pm = per_model & 1, xref_pm = per_model & 2, uprev_pm = per_model & 4, force_general = per_model & 8;
     const unsigned u_bytes = u_pm ? 0u : (unsigned)(K * H * 8);
     const unsigned u_bytes_pad = (u_bytes + 15u) & ~15u;
     const unsigned xr_bytes = xref_pm ? 0u : (unsigned)(((H + 1) * 8 + 15) & ~15);
     float2* sU = reinterpret_cast<float2*>(smem_raw);
     float2* sXr = reinterpret_cast<float2*>(smem_raw + u_bytes_pad);
+    // per-warp reference path relative to the warp's start position (formed in fp64 once, used as fp32)
+    float2* sRel = reinterpret_cast<float2*>(smem_raw + u_bytes_pad + xr_bytes) + (threadIdx.x >> 5) * (H + 1);
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     if (tid == 0) mbar_init(&mbar, 1);
@@ -45,14 +50,22 @@ lookahead_kernel(const float4* __restrict__ bank, int Mpad, const int* __restric
     const int bi = model_idx ? model_idx[mm] : mm;
     const Cand p = load_cand(bank, Mpad, bi);
     const double* xs = x0 + (n_x0 > 1 ? (size_t)mm * 6 : 0);
-    const double X0 = xs[0], Y0 = xs[1], PSI0 = xs[2];
     double s0d, c0d;
-    sincos(PSI0, &s0d, &c0d);
+    sincos(xs[2], &s0d, &c0d);
+    const float s_start = (float)s0d, c_start = (float)c0d;
     const float2 up = uprev_pm ? reinterpret_cast<const float2*>(uprev)[mm] : reinterpret_cast<const float2*>(uprev)[0];
     const float2* Ug = reinterpret_cast<const float2*>(U) + (u_pm ? (size_t)mm * K * H : 0);
     const float2* Xg = reinterpret_cast<const float2*>(xref) + (xref_pm ? (size_t)mm * (H + 1) : 0);
     mbar_wait(&mbar, 0);
     if (!m_ok) return;
+    {
+        const double X0 = xs[0], Y0 = xs[1];
+        for (int j = lane; j <= H; j += 32) {
+            const float2 xr = xref_pm ? __ldg(Xg + j) : sXr[j];
+            sRel[j] = make_float2((float)((double)xr.x - X0), (float)((double)xr.y - Y0));
+        }
+        __syncwarp();
+    }
 
     u64 best = ~0ull;
     for (int k0 = 0; k0 < K; k0 += 32) {
@@ -60,7 +73,7 @@ lookahead_kernel(const float4* __restrict__ bank, int Mpad, const int* __restric
         const bool k_ok = k < K;
         const int kk = k_ok ? k : K - 1;
         float X = 0.0f, Y = 0.0f, dpsi = 0.0f;
-        float s = (float)s0d, c = (float)c0d;
+        float s = s_start, c = c_start;
         float vx = (float)xs[3], vy = (float)xs[4], w = (float)xs[5];
         float2 uq = up;
         float Jt = 0.0f, Ja = 0.0f, ex = 0.0f, ey = 0.0f;
@@ -71,18 +84,28 @@ lookahead_kernel(const float4* __restrict__ bank, int Mpad, const int* __restric
             uq = u;
             Ctl ctl;
             ctl.pwm = u.x; ctl.delta = u.y;
-            sincos_small(u.y, ctl.sd, ctl.cd);
+            sincos_half(u.y, ctl.sd, ctl.cd);
             float inc[6];
-            rk4_increment<false>(p, ctl, s, c, vx, vy, w, h, inc);
+            float guard = 2.0f * fabsf(u.y);
+            rk4_increment_fast<false>(p, ctl, s, c, vx, vy, w, h, inc, guard);
+            guard = fmaxf(guard, 2.0f * fabsf(inc[2]));
+            if (force_general) guard = 2.0f;
+            if (!(guard <= 1.0f) || !(inc[3] + inc[5] == inc[3] + inc[5])) {   // rare: spinning, huge steering / yaw rate, NaN
+                guard = 2.0f;
+                const Inc6 g = rk4_increment_general(bank, Mpad, bi, u.x, u.y, s, c, vx, vy, w, h);
+#pragma unroll
+                for (int i = 0; i < 6; ++i) inc[i] = g.v[i];
+            }
             X += inc[0]; Y += inc[1]; dpsi += inc[2];
             vx += inc[3]; vy += inc[4]; w += inc[5];
             float sr, cr;
-            sincos_small(inc[2], sr, cr);
+            if (guard <= 1.0f) sincos_half(inc[2], sr, cr);
+            else sincos_small(inc[2], sr, cr);
             const float sn = fmaf(s, cr, c * sr), cn = fmaf(c, cr, -s * sr);
             s = sn; c = cn;
-            const float2 xr = xref_pm ? __ldg(Xg + hh + 1) : sXr[hh + 1];
-            ex = X - (float)((double)xr.x - X0);
-            ey = Y - (float)((double)xr.y - Y0);
+            const float2 xr = sRel[hh + 1];
+            ex = X - xr.x;
+            ey = Y - xr.y;
             Jt = fmaf(q0 * ex, ex, fmaf(q1 * ey, ey, Jt));        // nmpc.py:70-71
         }
         Jt = fmaf(p0 * ex, ex, fmaf(p1 * ey, ey, Jt));            // terminal cost nmpc.py:48
@@ -92,7 +115,7 @@ lookahead_kernel(const float4* __restrict__ bank, int Mpad, const int* __restric
             best = u64_min(best, pack_key(Jk, (unsigned)k));
             if (x_final) {
                 double* o = x_final + ((size_t)m * K + k) * 6;
-                o[0] = X0 + (double)X; o[1] = Y0 + (double)Y; o[2] = PSI0 + (double)dpsi;
+                o[0] = xs[0] + (double)X; o[1] = xs[1] + (double)Y; o[2] = xs[2] + (double)dpsi;
                 o[3] = (double)vx; o[4] = (double)vy; o[5] = (double)w;
             }
         }
@@ -133,7 +156,8 @@ extern "C" int llampc_lookahead_rollout_f32(const float* bank, int Mpad, const i
     if ((reinterpret_cast<uintptr_t>(bank) | reinterpret_cast<uintptr_t>(U) | reinterpret_cast<uintptr_t>(xref)) & 15u)
         return LLAMPC_E_ALIGN;
     const bool u_pm = per_model_flags & 1, xref_pm = per_model_flags & 2;
-    size_t smem = (u_pm ? 0 : (((size_t)K * H * 8 + 15) & ~(size_t)15)) + (xref_pm ? 0 : ((((size_t)H + 1) * 8 + 15) & ~(size_t)15));
+    size_t smem = (u_pm ? 0 : (((size_t)K * H * 8 + 15) & ~(size_t)15)) + (xref_pm ? 0 : ((((size_t)H + 1) * 8 + 15) & ~(size_t)15)) +
+                  (size_t)LA_WARPS * (H + 1) * 8;
     if (smem > 96 * 1024) return LLAMPC_E_RANGE;
     if (smem > 48 * 1024) {
         static bool raised = false;

@@ -41,14 +41,14 @@ class LookAhead:
         plan.run()
         return plan.fetch()
 
-    def plan(self, x0, U, xref, uprev, model_idx=None, return_final=False):
+    def plan(self, x0, U, xref, uprev, model_idx=None, return_final=False, _force_general=False):
         """Upload the inputs once and return a `RolloutPlan`: `.run()` enqueues the kernel on the current
         stream (device-resident inputs), `.fetch()` copies J / best_k (/ x_final) back."""
         torch = self.torch
         dev = self.bank.device
         U = np.asarray(U)
         M = self.bank.N if model_idx is None else len(model_idx)
-        flags = 0
+        flags = 8 if _force_general else 0
         if U.ndim == 4:
             flags |= 1
             if U.shape[0] != M:

@@ -1,0 +1,135 @@
+"""CPU oracle for the look-ahead reference generator (planner) and its raceline tables.  TEST INFRASTRUCTURE ONLY.
+
+Restates, in float64 NumPy / plain Python, the reference's
+  * natural cubic spline     llampc/utils/pycubicspline.py:17-132  (Spline),  :135-162 (Spline2D)
+  * point-to-segment projection   llampc/utils/projection.py:11-38
+  * Track.project_fast       llampc/tracks/track.py:147-160
+  * Track._load_raceline     llampc/tracks/track.py:52-83 (spline over the raceline + one speed spline per mu)
+  * ConstantSpeed            llampc/mpc/planner.py:12-67
+Pinned by tests/golden/planner_kat.npz (outputs of the reference's own ConstantSpeed, made by
+tests/golden/make_golden_planner.py) and, when /root/reference is present, bit-for-bit against the imported
+reference (tests/test_planner_oracle.py).
+"""
+import bisect
+import math
+
+import numpy as np
+
+
+class Spline:
+    """pycubicspline.py:17-132"""
+
+    def __init__(self, x, y):
+        self.x, self.y = x, y
+        self.nx = len(x)
+        h = np.diff(x)
+        self.a = [iy for iy in y]
+        A = np.zeros((self.nx, self.nx))                       # :107-122
+        A[0, 0] = 1.0
+        for i in range(self.nx - 1):
+            if i != (self.nx - 2):
+                A[i + 1, i + 1] = 2.0 * (h[i] + h[i + 1])
+            A[i + 1, i] = h[i]
+            A[i, i + 1] = h[i]
+        A[0, 1] = 0.0
+        A[self.nx - 1, self.nx - 2] = 0.0
+        A[self.nx - 1, self.nx - 1] = 1.0
+        B = np.zeros(self.nx)                                  # :124-132
+        for i in range(self.nx - 2):
+            B[i + 1] = 3.0 * (self.a[i + 2] - self.a[i + 1]) / h[i + 1] - 3.0 * (self.a[i + 1] - self.a[i]) / h[i]
+        self.c = np.linalg.solve(A, B)
+        self.b, self.d = [], []
+        for i in range(self.nx - 1):                           # :40-45
+            self.d.append((self.c[i + 1] - self.c[i]) / (3.0 * h[i]))
+            self.b.append((self.a[i + 1] - self.a[i]) / h[i] - h[i] * (self.c[i + 1] + 2.0 * self.c[i]) / 3.0)
+
+    def calc(self, t):                                         # :47-65
+        if t < self.x[0] or t > self.x[-1]:
+            return None
+        i = bisect.bisect(self.x, t) - 1
+        dx = t - self.x[i]
+        return self.a[i] + self.b[i] * dx + self.c[i] * dx ** 2.0 + self.d[i] * dx ** 3.0
+
+
+class Spline2D:
+    """pycubicspline.py:135-162"""
+
+    def __init__(self, x, y):
+        dx, dy = np.diff(x), np.diff(y)
+        self.ds = [math.sqrt(idx ** 2 + idy ** 2) for (idx, idy) in zip(dx, dy)]
+        s = [0]
+        s.extend(np.cumsum(self.ds))
+        self.s = s
+        self.sx, self.sy = Spline(s, x), Spline(s, y)
+
+    def calc_position(self, s):
+        return self.sx.calc(s), self.sy.calc(s)
+
+
+def projection(point, line):
+    """projection.py:11-38"""
+    x, x1, x2 = np.array(point[0]), np.array(line[0]), np.array(line[len(line) - 1])
+    dir1 = x2 - x1
+    dir1 /= np.linalg.norm(dir1, 2)
+    proj = x1 + dir1 * np.dot(x - x1, dir1)
+    dir2, dir3 = (proj - x1), (proj - x2)
+    if np.linalg.norm(dir2, 2) > 0 and np.linalg.norm(dir3, 2) > 0:
+        dir2 /= np.linalg.norm(dir2)
+        dir3 /= np.linalg.norm(dir3)
+        is_on_line = np.linalg.norm(dir2 - dir3, 2) > 1e-10
+        if not is_on_line:
+            proj = x1 if np.linalg.norm(x1 - proj, 2) < np.linalg.norm(x2 - proj, 2) else x2
+    return proj, np.linalg.norm(x - proj, 2)
+
+
+def project_fast(x, y, raceline):
+    """track.py:147-160"""
+    n = raceline.shape[1]
+    proj, dist = np.empty([2, n - 1]), np.empty([n - 1])
+    for idl in range(n - 1):
+        proj[:, idl], dist[idl] = projection([(x, y)], [raceline[:, idl], raceline[:, idl + 1]])
+    optidx = np.argmin(dist)
+    return proj[:, optidx], optidx
+
+
+class RacelineOracle:
+    """What Track._load_raceline builds (track.py:52-83): raceline (2, n), Spline2D over it, one speed spline per mu."""
+
+    def __init__(self, x, y, speeds, mus):
+        self.raceline = np.array([x, y])
+        self.spline = Spline2D(x, y)
+        self.mus = mus
+        self.spline_v = [Spline(self.spline.s, vi) for vi in speeds]
+
+
+def constant_speed(x0, v0, track, N, Ts, projidx, scale=1., curr_mu=1.):
+    """planner.py:12-67"""
+    raceline = track.raceline
+    xy, idx = project_fast(x=x0[0], y=x0[1], raceline=raceline[:, projidx:projidx + 10])
+    projidx = idx + projidx
+    start = track.raceline[:, :projidx + 2]
+    xref = np.zeros([2, N + 1])
+    xref[:2, 0] = x0
+    dist = np.sum(np.linalg.norm(np.diff(start), 2, axis=0))
+    v = max(v0, .01)
+    vr = 0.
+    for idh in range(1, N + 1):
+        dist += scale * v * Ts
+        dist = dist % track.spline.s[-1]
+        xref[:2, idh] = track.spline.calc_position(dist)
+        if curr_mu < track.mus[0]:
+            v = track.spline_v[0].calc(dist)
+        elif curr_mu > track.mus[-1]:
+            v = track.spline_v[-1].calc(dist)
+        else:
+            i = 0
+            for i in range(len(track.mus)):
+                if track.mus[i] >= curr_mu:
+                    break
+            vb = track.spline_v[i - 1].calc(dist)
+            va = track.spline_v[i].calc(dist)
+            v = vb * (track.mus[i] - curr_mu) / (track.mus[i] - track.mus[i - 1]) + va * (curr_mu - track.mus[i - 1]) / (
+                track.mus[i] - track.mus[i - 1])
+        if idh == 1:
+            vr = v * scale
+    return xref, projidx, vr

@@ -110,3 +110,20 @@ def test_mu_estimator_matches_oracle():
     for _ in range(40):
         dr, df = 0.17 + 0.01 * rng.randn(10), 0.19 + 0.01 * rng.randn(10)
         assert a.update(dr, df) == b.update(dr, df)
+
+
+def test_raceline_table_coefficients_match_reference_splines():
+    """Thomas-algorithm spline tables == the reference's dense-solve Spline coefficients (golden, from the reference)."""
+    from conftest import load_golden
+    from llampc_b200.tracks import RacelineTable
+    g = load_golden("planner_kat.npz")
+    for name in ("ethz", "ethzmobil"):
+        r = load_golden("raceline_%s.npz" % name)
+        tab = RacelineTable(r["x"], r["y"], r["speeds"], r["mus"])
+        np.testing.assert_allclose(tab.s, r["s"], rtol=0, atol=1e-13)
+        np.testing.assert_allclose(tab.coef[:, 1], g[name + "_sx_b"], rtol=1e-9, atol=1e-11)
+        np.testing.assert_allclose(tab.coef[:, 2], g[name + "_sx_c"][:-1], rtol=1e-9, atol=1e-9)
+        np.testing.assert_allclose(tab.coef[:, 3], g[name + "_sx_d"], rtol=1e-9, atol=1e-8)
+        np.testing.assert_allclose(tab.coef[:, 8 + 1], g[name + "_v0_b"], rtol=1e-9, atol=1e-10)
+        nmu = len(r["mus"])
+        np.testing.assert_allclose(tab.coef[:, 8 + 4 * (nmu - 1) + 2], g[name + "_vlast_c"][:-1], rtol=1e-9, atol=1e-8)
