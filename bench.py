@@ -50,6 +50,15 @@ def make_bank(n, seed, lo=0, hi=None):
     return bank
 
 
+def make_bank_rt(n, seed):
+    """C1-style bank: the six Pacejka parameters varied (run_nmpc_orca_llampc_rt.py:153-158), shared mass."""
+    z = np.random.RandomState(seed).randn(n, 6)
+    bank = dict(NOMINAL)
+    for j, (name, sigma) in enumerate(C2_VARIATION[:6]):
+        bank[name] = NOMINAL[name] * (1 + sigma * z[:, j])
+    return bank
+
+
 def synthetic_history(n_ticks, plant_step):
     """History B of SURVEY.md 8(d): ORCA plant (RK6) from the ETHZMobil start, sinusoidal inputs, sudden
     friction drop; `plant_step(params, x, u)` is the integrator used (GPU plant kernel or the CPU port)."""
@@ -454,6 +463,40 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
     plan = la.plan(S[:, t0], Useq, xref, U[:, t0 - 1])
     dt = time_it(plan.run, 20)
     out["C3_lookahead_16384x32x20"] = {"steps_per_s": M * K * H / dt, "ms_per_call": dt * 1e3}
+    del la, plan
+
+    # C4 Monte-Carlo closed loop: 4,096 vehicles x (look-back 1,024 candidates x 20 window + look-ahead 32 x 20 + planner,
+    # plant, friction estimate) per tick, everything device-resident
+    try:
+        from llampc_b200.mpc.montecarlo import MonteCarlo
+        from llampc_b200.tracks import RacelineTable
+        rl = np.load(os.path.join(ROOT, "tests", "golden", "raceline_ethzmobil.npz"))
+        tab = RacelineTable(rl["x"], rl["y"], rl["speeds"], rl["mus"])
+        Vn = 4096
+        r4 = np.random.RandomState(4)
+        start = r4.randint(0, 400, Vn)
+        x_init = np.zeros((Vn, 6))
+        x_init[:, 0] = 0.6 * rl["x"][start + 1] + 0.4 * rl["x"][start + 2]
+        x_init[:, 1] = 0.6 * rl["y"][start + 1] + 0.4 * rl["y"][start + 2]
+        x_init[:, 2] = np.arctan2(rl["y"][start + 2] - rl["y"][start + 1], rl["x"][start + 2] - rl["x"][start + 1])
+        x_init[:, 3] = 1.0
+        mc = MonteCarlo(make_bank_rt(1024, seed=0), tab, x_init, start, NOMINAL, r4.uniform(3.0, 15.0, Vn), W=20, K_models=10,
+                        K_seq=32, H=20, Ts=TS, seed=4)
+        mc.run(25)                                               # fill the windows, warm up
+        torch.cuda.synchronize()
+        n_t = 20
+        s0_lb, s0_la = mc.lookback_steps, mc.lookahead_steps
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record()
+        mc.run(n_t)
+        b.record()
+        torch.cuda.synchronize()
+        dt = a.elapsed_time(b) * 1e-3 / n_t
+        steps = (mc.lookback_steps - s0_lb + mc.lookahead_steps - s0_la) / n_t
+        out["C4_montecarlo_4096veh"] = {"steps_per_s": steps / dt, "ms_per_tick": dt * 1e3, "rk4_steps_per_tick": steps,
+                                        "vehicle_ticks_per_s": Vn / dt}
+    except Exception as e:                                       # the secondary configs never block the main line
+        out["C4_montecarlo_4096veh"] = {"error": repr(e)}
     return out
 
 

@@ -215,6 +215,35 @@ int llampc_planner_constant_speed_f64(const double* s, const double* xy, const d
 int llampc_plant_rk6_f64(const double* params64, int V, const double* x64, const double* u64, double Ts,
                          double* out64, llampc_stream_t stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Monte-Carlo closed loop (thousands of independent vehicles, everything device-resident, no host round trip
+ * per tick).  Layouts: per-vehicle history rings hist [V][W][LLAMPC_HIST_ROW] / hist64 [V][W][LLAMPC_HIST64_ROW]
+ * (use llampc_lookback_window_f32 with n_vehicles = V, hist_stride_rows = W).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Device twin of llampc_hist_row_pack_h for V vehicles: x_k [V][6], u_k [V][2], x_k1 [V][6] -> ring slot `slot`. */
+int llampc_pack_rows_f64(const double* x_k, const double* u_k, const double* x_k1, int V, double Ts,
+                         double lf_shared, double lr_shared, int slot, int W, float* hist, double* hist64,
+                         llampc_stream_t stream);
+
+/* Friction estimate from the K best candidates (run_nmpc_orca_llampc_rt.py:326-344): mean Dr, Df of the top-K,
+ * `smoothing`-tick moving average, / (g m), exponential smoother alpha, x gain.
+ *   topk [V][topk_stride] keys as written by llampc_topk_merge_lists ([0] arg-min, [1..K] top-K)
+ *   state [V][2*smoothing+3] doubles, zero-initialised by the caller; mu_out [V]. */
+int llampc_mu_estimate_f64(const llampc_key_t* topk, int topk_stride, int K, int idx_offset,
+                           const double* bank64, int N, int V, int smoothing, double alpha, double gain,
+                           double g, double* state, double* mu_out, llampc_stream_t stream);
+
+/* Control samples U [V][K][H][2] = clip(nominal [V][H][2] + eps [K][H][2]); box_h (HOST) = pwm_min pwm_max steer_min steer_max
+ * (limits of llampc/params/orca.py:29-35). */
+int llampc_sample_controls_f32(const float* nominal, const float* eps, int V, int K, int H, const float* box_h,
+                               float* U, llampc_stream_t stream);
+
+/* Best-of-K controller step: u_applied [V][2] (doubles) = U[v][best_k[v]][0]; uprev [V][2] likewise (floats);
+ * nominal [V][H][2] = that sequence shifted by one step (last input repeated). */
+int llampc_apply_best_f32(const float* U, const int* best_k, int V, int K, int H, float* nominal, float* uprev,
+                          double* u_applied, llampc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

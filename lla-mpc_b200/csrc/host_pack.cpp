@@ -3,6 +3,7 @@
 #include <stddef.h>
 
 #include "../../include/llampc_b200.h"
+#include "llampc_rowpack.cuh"
 
 extern "C" int llampc_abi_version(void) { return LLAMPC_ABI_VERSION; }
 
@@ -42,37 +43,6 @@ extern "C" int llampc_bank_pack_h(const double* const* params_h, const int* is_a
 extern "C" int llampc_hist_row_pack_h(const double* x_k, const double* u_k, const double* x_k1, double Ts,
                                       double lf_shared, double lr_shared, float* r, double* row64_h) {
     if (!x_k || !u_k || !x_k1 || !r || !(Ts > 0.0)) return LLAMPC_E_ARG;
-    const double psi = x_k[2], vx = x_k[3], vy = x_k[4], w = x_k[5];
-    const double pwm = u_k[0], delta = u_k[1];
-    const double h = Ts;
-    // q0: heading at stage 1 and at stages 2/3 (psi + h w/2);  q1: heading base of stage 4 (psi + h w), vx, vy
-    r[0] = (float)sin(psi);               r[1] = (float)cos(psi);
-    r[2] = (float)sin(psi + 0.5 * h * w); r[3] = (float)cos(psi + 0.5 * h * w);
-    r[4] = (float)sin(psi + h * w);       r[5] = (float)cos(psi + h * w);
-    r[6] = (float)vx;                     r[7] = (float)vy;
-    // q2
-    r[8] = (float)w; r[9] = (float)pwm; r[10] = (float)delta; r[11] = (float)sin(delta);
-    // q3: cos(delta) and the measured increments minus their candidate-invariant parts
-    const double xd0 = vx * cos(psi) - vy * sin(psi), yd0 = vx * sin(psi) + vy * cos(psi);
-    r[12] = (float)cos(delta);
-    r[13] = (float)((x_k1[0] - x_k[0]) - h / 6.0 * xd0);
-    r[14] = (float)((x_k1[1] - x_k[1]) - h / 6.0 * yd0);
-    r[15] = (float)((x_k1[2] - x_k[2]) - h * w);
-    // q4: measured vx increment as hi + lo, stage-1 slip angles for bank-wide geometry
-    const double dvx = x_k1[3] - x_k[3];
-    const float hi = (float)dvx;
-    r[16] = hi;
-    r[17] = (float)(dvx - (double)hi);
-    if (lf_shared == lf_shared && lr_shared == lr_shared) {
-        r[18] = (float)(delta - atan2(lf_shared * w + vy, fabs(vx)));
-        r[19] = (float)atan2(lr_shared * w - vy, fabs(vx));
-    } else {
-        r[18] = 0.0f; r[19] = 0.0f;
-    }
-    if (row64_h) {
-        for (int i = 0; i < 6; ++i) row64_h[i] = x_k[i];
-        row64_h[6] = pwm; row64_h[7] = delta;
-        for (int i = 0; i < 4; ++i) row64_h[8 + i] = x_k1[i];
-    }
+    llampc::pack_hist_row(x_k, u_k, x_k1, Ts, lf_shared, lr_shared, r, row64_h);
     return 0;
 }

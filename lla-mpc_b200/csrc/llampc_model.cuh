@@ -101,12 +101,14 @@ __device__ __forceinline__ float pacejka_fast(float B, float C, float D, float a
     return D * (MUFU_SIN ? sin_mufu(t) : sin_tyre(t));
 }
 
-template <bool MUFU_SIN>
+// WIDE_SLIP = false: slip tangents up to 0.5 (5-coefficient atan); true: up to 1 (9 coefficients) -- used by the
+// look-ahead rollouts, where unstable candidate models reach large slip angles within the horizon.
+template <bool MUFU_SIN, bool WIDE_SLIP = false>
 __device__ __forceinline__ Deriv accel_fast(const Cand& p, const Ctl& u, float vx, float vy, float w, float& guard) {
     const float inv = rcp_approx(fabsf(vx));            // 1 ulp: the tangents are small, |error| <= 1.2e-7 |t|
     const float tf = fmaf(p.lf, w, vy) * inv, tr = fmaf(p.lr, w, -vy) * inv;
-    guard = fmaxf(guard, 2.0f * fmaxf(fabsf(tf), fabsf(tr)));
-    const float af = u.delta - atan_half(tf), ar = atan_half(tr);
+    guard = fmaxf(guard, (WIDE_SLIP ? 1.0f : 2.0f) * fmaxf(fabsf(tf), fabsf(tr)));
+    const float af = u.delta - (WIDE_SLIP ? atan_unit(tf) : atan_half(tf)), ar = WIDE_SLIP ? atan_unit(tr) : atan_half(tr);
     const float Frx = drive_force(p, u.pwm, vx);
     const float Ffy = pacejka_fast<MUFU_SIN>(p.Bf, p.Cf, p.Df, af);
     const float Fry = pacejka_fast<MUFU_SIN>(p.Br, p.Cr, p.Dr, ar);
@@ -164,7 +166,7 @@ __device__ __forceinline__ void rk4_increment_fast(const Cand& p, const Ctl& u, 
                                                    float w0, float h, float inc[6], float& guard) {
     const float hh = 0.5f * h, h6 = h * (1.0f / 6.0f);
     // weighted sums (k1 + 2 k2 + 2 k3 + k4) are accumulated stage by stage to keep few values live
-    Deriv a = accel_fast<MUFU_SIN>(p, u, vx0, vy0, w0, guard);
+    Deriv a = accel_fast<MUFU_SIN, true>(p, u, vx0, vy0, w0, guard);
     float sx = fmaf(vx0, c0, -vy0 * s0), sy = fmaf(vx0, s0, vy0 * c0);
     float sw = w0, svx = a.vx, svy = a.vy, sdw = a.w;
     float vx = fmaf(hh, a.vx, vx0), vy = fmaf(hh, a.vy, vy0), w = fmaf(hh, a.w, w0);
@@ -172,7 +174,7 @@ __device__ __forceinline__ void rk4_increment_fast(const Cand& p, const Ctl& u, 
     sincos_half(d, sd, cd);
     float sn = fmaf(s0, cd, c0 * sd), cs = fmaf(c0, cd, -s0 * sd);
     // stage 2
-    a = accel_fast<MUFU_SIN>(p, u, vx, vy, w, guard);
+    a = accel_fast<MUFU_SIN, true>(p, u, vx, vy, w, guard);
     sx = fmaf(2.0f, fmaf(vx, cs, -vy * sn), sx);
     sy = fmaf(2.0f, fmaf(vx, sn, vy * cs), sy);
     sw = fmaf(2.0f, w, sw); svx = fmaf(2.0f, a.vx, svx); svy = fmaf(2.0f, a.vy, svy); sdw = fmaf(2.0f, a.w, sdw);
@@ -182,7 +184,7 @@ __device__ __forceinline__ void rk4_increment_fast(const Cand& p, const Ctl& u, 
     sincos_half(d, sd, cd);
     sn = fmaf(s0, cd, c0 * sd); cs = fmaf(c0, cd, -s0 * sd);
     // stage 3
-    a = accel_fast<MUFU_SIN>(p, u, vx, vy, w, guard);
+    a = accel_fast<MUFU_SIN, true>(p, u, vx, vy, w, guard);
     sx = fmaf(2.0f, fmaf(vx, cs, -vy * sn), sx);
     sy = fmaf(2.0f, fmaf(vx, sn, vy * cs), sy);
     sw = fmaf(2.0f, w, sw); svx = fmaf(2.0f, a.vx, svx); svy = fmaf(2.0f, a.vy, svy); sdw = fmaf(2.0f, a.w, sdw);
@@ -192,7 +194,7 @@ __device__ __forceinline__ void rk4_increment_fast(const Cand& p, const Ctl& u, 
     sincos_half(d, sd, cd);
     sn = fmaf(s0, cd, c0 * sd); cs = fmaf(c0, cd, -s0 * sd);
     // stage 4
-    a = accel_fast<MUFU_SIN>(p, u, vx, vy, w, guard);
+    a = accel_fast<MUFU_SIN, true>(p, u, vx, vy, w, guard);
     sx += fmaf(vx, cs, -vy * sn);
     sy += fmaf(vx, sn, vy * cs);
     guard = fmaxf(guard, 2.0f * dmax);

@@ -1,0 +1,134 @@
+// Device-side glue of the Monte-Carlo closed loop (BASELINE config 4: thousands of independent vehicles, each running
+// look-back + look-ahead per tick with no host round trip): history-row packing, the friction estimate of
+// run_nmpc_orca_llampc_rt.py:326-344, control-sequence sampling and the best-of-K controller step.
+#include "llampc_common.cuh"
+#include "llampc_rowpack.cuh"
+
+namespace llampc {
+
+// one thread per vehicle: (x_k, u_k, x_k1) -> ring slot of that vehicle's history [V][W][20] (+ [V][W][12] doubles)
+__global__ void __launch_bounds__(128)
+pack_rows_kernel(const double* __restrict__ x_k, const double* __restrict__ u_k, const double* __restrict__ x_k1, int V,
+                 double h, double lf, double lr, int slot, int W, float* __restrict__ hist, double* __restrict__ hist64) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    float r[LLAMPC_HIST_ROW];
+    double r64[LLAMPC_HIST64_ROW];
+    pack_hist_row(x_k + (size_t)v * 6, u_k + (size_t)v * 2, x_k1 + (size_t)v * 6, h, lf, lr, r, r64);
+    float4* dst = reinterpret_cast<float4*>(hist + ((size_t)v * W + slot) * LLAMPC_HIST_ROW);
+#pragma unroll
+    for (int i = 0; i < LLAMPC_HIST_ROW / 4; ++i) dst[i] = make_float4(r[4 * i], r[4 * i + 1], r[4 * i + 2], r[4 * i + 3]);
+    if (hist64) {
+        double* d64 = hist64 + ((size_t)v * W + slot) * LLAMPC_HIST64_ROW;
+#pragma unroll
+        for (int i = 0; i < LLAMPC_HIST64_ROW; ++i) d64[i] = r64[i];
+    }
+}
+
+// Friction estimate, one thread per vehicle (rt.py:326-344 + ExponentialSmoother rt.py:100-110):
+//   mean Dr, Df of the K best candidates -> per-vehicle rings of the last `smoothing` ticks ->
+//   mu = (mean(Dr ring) + mean(Df ring)) / (g m) -> exponential smoother (alpha) -> x gain.
+// state [V][2*smoothing + 3] doubles: Dr ring, Df ring, count, smooth value, initialised flag (all zero at start).
+__global__ void __launch_bounds__(128)
+mu_estimate_kernel(const u64* __restrict__ topk, int topk_stride, int K, int idx_offset, const double* __restrict__ bank64,
+                   int N, int V, int smoothing, double alpha, double gain, double g, double* __restrict__ state,
+                   double* __restrict__ mu_out) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const u64* keys = topk + (size_t)v * topk_stride + 1;          // [0] is the arg-min key
+    const double* Dr = bank64 + (size_t)9 * N;                     // LLAMPC_NPARAM order: ... Df = 8, Dr = 9
+    const double* Df = bank64 + (size_t)8 * N;
+    const double mass = bank64[(size_t)2 * N];                     // bank-wide mass (models[0].mass in the reference)
+    double sdr = 0.0, sdf = 0.0;
+    int cnt = 0;
+    for (int j = 0; j < K; ++j) {
+        if (keys[j] == ~0ull) continue;
+        const long long ci = (long long)(unsigned)(keys[j] & 0xffffffffull) - idx_offset;
+        if (ci < 0 || ci >= N) continue;
+        sdr += Dr[ci]; sdf += Df[ci]; ++cnt;
+    }
+    if (cnt == 0) return;
+    double* st = state + (size_t)v * (2 * smoothing + 3);
+    const int n = (int)st[2 * smoothing];
+    st[n % smoothing] = sdr / cnt;
+    st[smoothing + n % smoothing] = sdf / cnt;
+    st[2 * smoothing] = (double)(n + 1);
+    const int have = min(n + 1, smoothing);
+    double mdr = 0.0, mdf = 0.0;
+    for (int j = 0; j < have; ++j) { mdr += st[j]; mdf += st[smoothing + j]; }
+    const double mu = (mdr / have + mdf / have) / (g * mass);
+    double sm = st[2 * smoothing + 1];
+    sm = (st[2 * smoothing + 2] == 0.0) ? mu : alpha * mu + (1.0 - alpha) * sm;
+    st[2 * smoothing + 1] = sm;
+    st[2 * smoothing + 2] = 1.0;
+    mu_out[v] = sm * gain;
+}
+
+// U[v][k][h] = clip(nominal[v][h] + eps[k][h], box)   (control samples around each vehicle's nominal sequence)
+__global__ void __launch_bounds__(256)
+sample_controls_kernel(const float2* __restrict__ nominal, const float2* __restrict__ eps, int V, int K, int H,
+                       float pwm_min, float pwm_max, float st_min, float st_max, float2* __restrict__ U) {
+    const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t total = (size_t)V * K * H;
+    if (i >= total) return;
+    const int h = (int)(i % H);
+    const int k = (int)((i / H) % K);
+    const int v = (int)(i / ((size_t)H * K));
+    const float2 n = nominal[(size_t)v * H + h], e = eps[(size_t)k * H + h];
+    U[i] = make_float2(fminf(fmaxf(n.x + e.x, pwm_min), pwm_max), fminf(fmaxf(n.y + e.y, st_min), st_max));
+}
+
+// best-of-K controller: apply the first input of the best sequence, shift it into the next nominal sequence
+__global__ void __launch_bounds__(128)
+apply_best_kernel(const float2* __restrict__ U, const int* __restrict__ best_k, int V, int K, int H,
+                  float2* __restrict__ nominal, float2* __restrict__ uprev, double* __restrict__ u_applied) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const float2* seq = U + ((size_t)v * K + best_k[v]) * H;
+    const float2 u0 = seq[0];
+    uprev[v] = u0;
+    u_applied[(size_t)v * 2] = (double)u0.x;
+    u_applied[(size_t)v * 2 + 1] = (double)u0.y;
+    for (int h = 0; h < H; ++h) nominal[(size_t)v * H + h] = seq[min(h + 1, H - 1)];
+}
+
+}  // namespace llampc
+
+using namespace llampc;
+
+extern "C" int llampc_pack_rows_f64(const double* x_k, const double* u_k, const double* x_k1, int V, double Ts,
+                                    double lf_shared, double lr_shared, int slot, int W, float* hist, double* hist64,
+                                    llampc_stream_t stream) {
+    if (!x_k || !u_k || !x_k1 || !hist || V <= 0 || slot < 0 || slot >= W) return LLAMPC_E_ARG;
+    pack_rows_kernel<<<(V + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(x_k, u_k, x_k1, V, Ts, lf_shared,
+                                                                                     lr_shared, slot, W, hist, hist64);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_mu_estimate_f64(const llampc_key_t* topk, int topk_stride, int K, int idx_offset,
+                                      const double* bank64, int N, int V, int smoothing, double alpha, double gain,
+                                      double g, double* state, double* mu_out, llampc_stream_t stream) {
+    if (!topk || !bank64 || !state || !mu_out || V <= 0 || K <= 0 || smoothing <= 0 || N <= 0) return LLAMPC_E_ARG;
+    mu_estimate_kernel<<<(V + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        topk, topk_stride, K, idx_offset, bank64, N, V, smoothing, alpha, gain, g, state, mu_out);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_sample_controls_f32(const float* nominal, const float* eps, int V, int K, int H, const float* box_h,
+                                          float* U, llampc_stream_t stream) {
+    if (!nominal || !eps || !box_h || !U || V <= 0 || K <= 0 || H <= 0) return LLAMPC_E_ARG;
+    const size_t total = (size_t)V * K * H;
+    sample_controls_kernel<<<(unsigned)((total + 255) / 256), 256, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(nominal), reinterpret_cast<const float2*>(eps), V, K, H, box_h[0], box_h[1],
+        box_h[2], box_h[3], reinterpret_cast<float2*>(U));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_apply_best_f32(const float* U, const int* best_k, int V, int K, int H, float* nominal, float* uprev,
+                                     double* u_applied, llampc_stream_t stream) {
+    if (!U || !best_k || !nominal || !uprev || !u_applied || V <= 0 || K <= 0 || H <= 0) return LLAMPC_E_ARG;
+    apply_best_kernel<<<(V + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
+        reinterpret_cast<const float2*>(U), best_k, V, K, H, reinterpret_cast<float2*>(nominal),
+        reinterpret_cast<float2*>(uprev), u_applied);
+    return (int)cudaGetLastError();
+}

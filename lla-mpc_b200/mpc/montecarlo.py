@@ -1,0 +1,143 @@
+"""Monte-Carlo closed loop on the device: V independent vehicles / friction scenarios, each running the LLA-MPC
+tick -- planner, look-ahead over sampled control sequences, plant step, look-back adaptation, friction estimate --
+with every array resident in HBM and no host round trip inside a tick (BASELINE config 4).
+
+Per tick and vehicle (reference loop: run_nmpc_orca_llampc_rt.py:269-389):
+  1. xref   = ConstantSpeed(x[:2], vx, track, H, Ts, projidx, curr_mu, scale)          planner.py:12-67   (rt.py:278-282)
+  2. U      = clip(nominal + eps)                K sampled control sequences around the previous best one
+  3. J, k*  = look-ahead rollout of the vehicle's CURRENT best model over U, NMPC cost  (replaces the IPOPT solve rt.py:305:
+              there is no NLP solver on this path; the controller is best-of-K)
+  4. u      = U[k*][0]; nominal = shift(U[k*])
+  5. plant: x+ = RK6(x, u; true parameters with the vehicle's friction schedule)         rt.py:274,311
+  6. push (x, u, x+) into the vehicle's history ring; once W transitions are in: score the whole bank over the
+     window, arg-min + top-K per vehicle                                                 rt.py:347-366
+  7. mu estimate from the top-K models                                                   rt.py:326-344
+"""
+import numpy as np
+
+from .. import _lib
+from ..bank import ModelBank, PARAM_NAMES
+from ..tracks import RacelineTable
+
+
+class MonteCarlo:
+    def __init__(self, bank_params, table, x_init, projidx_init, plant_params, drop_start, V=None, W=20, K_models=10,
+                 K_seq=32, H=20, Ts=0.02, scale=0.9, mu_init=1.0, seed=4, sigma_pwm=0.1, sigma_steer=0.05,
+                 drop_rate=1.0 / 22.0, drop_len=0.2, initial_model=0, smoothing_mu=20, mu_alpha=0.08, limits=None):
+        torch = _lib.require_cuda()
+        self.torch, self.L = torch, _lib.lib()
+        self.bank = bank_params if isinstance(bank_params, ModelBank) else ModelBank(bank_params)
+        if not isinstance(table, RacelineTable):
+            table = RacelineTable.from_track(table)
+        self.table = table
+        dev = self.bank.device
+        self.dev = dev
+        x_init = np.atleast_2d(np.asarray(x_init, dtype=np.float64))
+        self.V = V = x_init.shape[0] if V is None else V
+        x_init = np.ascontiguousarray(np.broadcast_to(x_init, (V, 6)))
+        self.W, self.Km, self.Ks, self.H, self.Ts, self.scale = W, K_models, K_seq, H, float(Ts), float(scale)
+        if K_models > _lib.LIST_LEN:
+            raise ValueError("K_models <= %d" % _lib.LIST_LEN)
+        N = self.bank.N
+        f64, f32, i32, i64 = torch.float64, torch.float32, torch.int32, torch.int64
+        dv = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
+        self.x = dv(x_init, f64)
+        self.x_next = torch.empty_like(self.x)
+        pp = np.stack([np.broadcast_to(np.asarray(plant_params[k], dtype=np.float64), (V,)) for k in PARAM_NAMES], axis=1)
+        self.plant = dv(pp, f64)                                   # [V][14] true parameters (friction evolves)
+        self.drop_start = dv(np.broadcast_to(np.asarray(drop_start, dtype=np.float64), (V,)), f64)
+        self.drop_rate, self.drop_len = float(drop_rate), float(drop_len)
+        self.projidx = dv(np.broadcast_to(np.asarray(projidx_init), (V,)).astype(np.int32), i32)
+        self.curr_mu = torch.full((V,), float(mu_init), dtype=f64, device=dev)
+        self.smoothing = int(smoothing_mu)
+        self.mu_alpha = float(mu_alpha)
+        self.mu_state = torch.zeros((V, 2 * self.smoothing + 3), dtype=f64, device=dev)
+        lim = limits or {"min_pwm": -0.1, "max_pwm": 1.0, "min_steer": -0.35, "max_steer": 0.35}
+        self.box = np.array([lim["min_pwm"], lim["max_pwm"], lim["min_steer"], lim["max_steer"]], dtype=np.float32)
+        rng = np.random.RandomState(seed)
+        eps = np.stack([sigma_pwm * rng.randn(K_seq, H), sigma_steer * rng.randn(K_seq, H)], axis=-1)
+        eps[0] = 0.0                                               # sequence 0 = the unperturbed nominal
+        self.eps = dv(eps, f32)
+        self.nominal = torch.zeros((V, H, 2), dtype=f32, device=dev)
+        self.nominal[:, :, 0] = 0.5
+        self.uprev = torch.zeros((V, 2), dtype=f32, device=dev)
+        self.uprev[:, 0] = 0.5
+        pad = 4                                                    # bulk-copy granularity of the shared-table path
+        self.U = torch.zeros(V * K_seq * H * 2 + pad, dtype=f32, device=dev)
+        self.xref32 = torch.zeros(V * (H + 1) * 2 + pad, dtype=f32, device=dev)
+        self.J = torch.empty((V, K_seq), dtype=f32, device=dev)
+        self.best_k = torch.zeros(V, dtype=i32, device=dev)
+        self.u_applied = torch.zeros((V, 2), dtype=f64, device=dev)
+        self.model_idx = torch.full((V,), int(initial_model), dtype=i32, device=dev)
+        self.hist = torch.zeros((V, W, _lib.HIST_ROW), dtype=f32, device=dev)
+        self.n_lists = self.L.llampc_lookback_num_lists(N, W, 0)
+        self.cta_lists = torch.empty((V, self.n_lists, _lib.LIST_LEN), dtype=i64, device=dev)
+        self.best_key = torch.full((V,), -1, dtype=i64, device=dev)
+        self.topk = torch.zeros((V, _lib.LIST_LEN + 1), dtype=i64, device=dev)
+        self.qrp = np.array([1.0, 1.0, 5e-3, 1.0, 0.0, 0.0], dtype=np.float32)
+        self.tick_count = 0
+        self.lookback_steps = 0
+        self.lookahead_steps = 0
+
+    # ------------------------------------------------------------------ one tick, asynchronous on the current stream
+    def tick(self):
+        torch, L, V = self.torch, self.L, self.V
+        st = torch.cuda.current_stream().cuda_stream
+        dev, s, xy, coef, mus = self.table.device_tables()
+        bank = self.bank
+        chk = _lib.check
+        with torch.cuda.device(self.dev):
+            chk(L.llampc_planner_constant_speed_f64(s.data_ptr(), xy.data_ptr(), coef.data_ptr(), mus.data_ptr(), self.table.n,
+                                                    self.table.n_mu, self.x.data_ptr(), V, self.projidx.data_ptr(),
+                                                    self.curr_mu.data_ptr(), 0, self.H, self.Ts, self.scale,
+                                                    self.xref32.data_ptr(), None, self.projidx.data_ptr(), None, st), "planner")
+            chk(L.llampc_sample_controls_f32(self.nominal.data_ptr(), self.eps.data_ptr(), V, self.Ks, self.H,
+                                             self.box.ctypes.data, self.U.data_ptr(), st), "sample_controls")
+            chk(L.llampc_lookahead_rollout_f32(bank.packed.data_ptr(), bank.Npad, self.model_idx.data_ptr(), V,
+                                               self.x.data_ptr(), V, self.U.data_ptr(), self.Ks, self.H,
+                                               self.xref32.data_ptr(), self.uprev.data_ptr(), 1 | 2 | 4, self.qrp.ctypes.data,
+                                               self.Ts, self.J.data_ptr(), self.best_k.data_ptr(), None, st), "lookahead")
+            chk(L.llampc_apply_best_f32(self.U.data_ptr(), self.best_k.data_ptr(), V, self.Ks, self.H, self.nominal.data_ptr(),
+                                        self.uprev.data_ptr(), self.u_applied.data_ptr(), st), "apply_best")
+            # friction schedule ('sudden' style of run_nmpc_orca_llampc_nrt_avg_runs.py:163-166): Df, Dr decay while the
+            # vehicle's drop interval is active
+            t = self.tick_count * self.Ts
+            active = ((self.drop_start < t) & (t < self.drop_start + self.drop_len)).to(torch.float64)
+            self.plant[:, 8:10] *= (1.0 - self.drop_rate * active)[:, None]
+            chk(L.llampc_plant_rk6_f64(self.plant.data_ptr(), V, self.x.data_ptr(), self.u_applied.data_ptr(), self.Ts,
+                                       self.x_next.data_ptr(), st), "plant")
+            slot = self.tick_count % self.W
+            chk(L.llampc_pack_rows_f64(self.x.data_ptr(), self.u_applied.data_ptr(), self.x_next.data_ptr(), V, self.Ts,
+                                       bank.lf_shared, bank.lr_shared, slot, self.W, self.hist.data_ptr(), None, st), "pack_rows")
+            if self.tick_count + 1 >= self.W:
+                chk(L.llampc_lookback_window_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), self.W, V,
+                                                 self.W, self.Ts, None, self.best_key.data_ptr(), self.cta_lists.data_ptr(), 0,
+                                                 int(bank.geom_shared), 0, st), "lookback")
+                chk(L.llampc_topk_merge_lists(self.cta_lists.data_ptr(), self.n_lists, V, self.Km, self.best_key.data_ptr(),
+                                              self.topk.data_ptr(), st), "merge")
+                chk(L.llampc_mu_estimate_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.Km, 0, bank.bank64.data_ptr(),
+                                             bank.N, V, self.smoothing, self.mu_alpha, 0.95, 9.81, self.mu_state.data_ptr(),
+                                             self.curr_mu.data_ptr(), st), "mu_estimate")
+                self.model_idx.copy_((self.topk[:, 0] & 0xFFFFFFFF).to(torch.int32))
+                self.lookback_steps += V * bank.N * self.W
+            self.lookahead_steps += V * self.Ks * self.H
+            self.x, self.x_next = self.x_next, self.x
+        self.tick_count += 1
+
+    def run(self, n):
+        for _ in range(n):
+            self.tick()
+
+    # ------------------------------------------------------------------ host views (tests, logging)
+    def host(self):
+        V, H, Ks = self.V, self.H, self.Ks
+        c = lambda t: t.cpu().numpy()
+        keys = c(self.topk).view(np.uint64)
+        return {
+            "x": c(self.x), "projidx": c(self.projidx), "curr_mu": c(self.curr_mu), "model_idx": c(self.model_idx),
+            "xref": np.swapaxes(c(self.xref32)[:V * (H + 1) * 2].reshape(V, H + 1, 2), 1, 2),
+            "U": c(self.U)[:V * Ks * H * 2].reshape(V, Ks, H, 2), "J": c(self.J), "best_k": c(self.best_k),
+            "u_applied": c(self.u_applied), "nominal": c(self.nominal), "uprev": c(self.uprev), "plant": c(self.plant),
+            "hist": c(self.hist), "topk_idx": (keys[:, 1:] & np.uint64(0xFFFFFFFF)).astype(np.int64),
+            "best_idx": (keys[:, 0] & np.uint64(0xFFFFFFFF)).astype(np.int64),
+        }

@@ -441,3 +441,80 @@ def test_lookahead_tolerance_tracks_conditioning(history):
     srt = np.sort(Jr, axis=1)
     clear = (srt[:, 1] - srt[:, 0]) > 1e-3 * srt[:, 0]
     assert np.array_equal(bk[clear], bkr[clear])
+
+
+# ------------------------------------------------------------------------------------------- Monte-Carlo closed loop
+def test_montecarlo_closed_loop_stagewise_parity():
+    """Config C4 at test size: every stage of the device-resident tick is checked against the oracle on the same
+    inputs (planner, control sampling, look-ahead cost, controller step, plant RK6, history rows -> look-back
+    arg-min / top-K, friction estimate)."""
+    from llampc_b200.mpc.montecarlo import MonteCarlo
+    from llampc_b200.tracks import RacelineTable
+    from oracle import planner_oracle as po
+    r = load_golden("raceline_ethzmobil.npz")
+    tab = RacelineTable(r["x"], r["y"], r["speeds"], r["mus"])
+    trk = po.RacelineOracle(r["x"], r["y"], r["speeds"], r["mus"])
+    V, N, W, Ks, H, Km, Ts = 24, 512, 5, 8, 10, 10, 0.02
+    bank = orc.make_bank(N, seed=0)
+    rng = np.random.RandomState(4)
+    start = rng.randint(0, 400, V)
+    x_init = np.zeros((V, 6))
+    # between two raceline vertices, slightly off the line (a point exactly ON a vertex ties two segments at distance
+    # ~1e-17 and the arg-min then depends on the last bit of np.dot)
+    x_init[:, 0] = 0.6 * r["x"][start + 1] + 0.4 * r["x"][start + 2] + 0.004
+    x_init[:, 1] = 0.6 * r["y"][start + 1] + 0.4 * r["y"][start + 2] - 0.003
+    x_init[:, 2] = np.arctan2(r["y"][start + 2] - r["y"][start + 1], r["x"][start + 2] - r["x"][start + 1])
+    x_init[:, 3] = rng.uniform(0.8, 1.6, V)
+    nominal = orc.orca_params()
+    drop = rng.uniform(0.0, 0.1, V)
+    mc = MonteCarlo(bank, tab, x_init, start, nominal, drop, W=W, K_models=Km, K_seq=Ks, H=H, Ts=Ts, seed=4)
+    eps = mc.eps.cpu().numpy().astype(np.float64)
+    mus = [orc.MuEstimatorOracle(mass=nominal["mass"]) for _ in range(V)]
+    trans = []
+    for tick in range(W + 3):
+        pre = mc.host()
+        mc.tick()
+        post = mc.host()
+        x_pre, x_post = pre["x"], post["x"]
+        for v in range(V):
+            # 1 planner (float32 output of a float64 computation)
+            xref, pout, _ = po.constant_speed(x_pre[v, :2], x_pre[v, 3], trk, H, Ts, int(pre["projidx"][v]), scale=0.9,
+                                              curr_mu=float(pre["curr_mu"][v]))
+            np.testing.assert_allclose(post["xref"][v], xref, rtol=0, atol=3e-7)
+            assert post["projidx"][v] == pout
+            # 2 control samples
+            Uv = pre["nominal"][v].astype(np.float64)[None] + eps
+            Uv[..., 0] = np.clip(Uv[..., 0], -0.1, 1.0)
+            Uv[..., 1] = np.clip(Uv[..., 1], -0.35, 0.35)
+            np.testing.assert_allclose(post["U"][v], Uv, rtol=0, atol=1e-6)
+            # 3 look-ahead cost of the vehicle's current model (inputs as the kernel saw them: float32 tables)
+            m = int(pre["model_idx"][v])
+            pm = {k: (bank[k][m:m + 1] if np.ndim(bank[k]) else bank[k]) for k in orc.PARAM_NAMES}
+            Jr, bkr = orc.lookahead_rollout(pm, x_pre[v], post["U"][v].astype(np.float64), post["xref"][v].astype(np.float64),
+                                            pre["uprev"][v].astype(np.float64), Ts)
+            np.testing.assert_allclose(post["J"][v], Jr[0], rtol=2e-4, atol=1e-9)
+            bk = int(post["best_k"][v])
+            assert post["J"][v][bk] == post["J"][v].min()
+            # 4 controller step
+            np.testing.assert_allclose(post["u_applied"][v], post["U"][v][bk][0], rtol=0, atol=0)
+            np.testing.assert_allclose(post["nominal"][v][:-1], post["U"][v][bk][1:], rtol=0, atol=0)
+            # 5 plant (true parameters after this tick's friction update)
+            pl = dict(zip(orc.PARAM_NAMES, post["plant"][v]))
+            np.testing.assert_allclose(x_post[v], orc.rk6_step(pl, x_pre[v], post["u_applied"][v], 0, Ts), rtol=0, atol=1e-12)
+        t = tick * Ts
+        act = (drop < t) & (t < drop + 0.2)
+        np.testing.assert_allclose(post["plant"][:, 8], pre["plant"][:, 8] * np.where(act, 1 - 1 / 22.0, 1.0), rtol=1e-15)
+        trans.append((x_pre.copy(), post["u_applied"].copy(), x_post.copy()))
+        # 6-7 look-back and friction estimate once the window is full
+        if tick + 1 >= W:
+            for v in range(V):
+                errs = np.stack([orc.onestep_errors(bank, a[v], b[v], c[v], Ts) for a, b, c in trans[-W:]], axis=1)
+                avg = errs.mean(axis=1)
+                order = np.argsort(avg, kind="stable")
+                assert post["best_idx"][v] == order[0]
+                assert list(post["topk_idx"][v][:Km]) == list(order[:Km])
+                assert post["model_idx"][v] == order[0]
+                mu_ref = mus[v].update(bank["Dr"][order[:Km]], bank["Df"][order[:Km]])
+                np.testing.assert_allclose(post["curr_mu"][v], mu_ref, rtol=1e-12)
+        else:
+            assert np.array_equal(post["model_idx"], pre["model_idx"])
