@@ -280,7 +280,7 @@ def run_b200(args):
         the list merge (top-10; moves the arg-min key to topk_keys[0]) (+ the min-loc all-reduce for N > 1)."""
         rc = L.llampc_lookback_window_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2, TS,
                                           lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), lo,
-                                          int(bank.geom_shared), 0, st)
+                                          int(bank.geom_shared), lb.split, st)
         _lib.check(rc, "K1")
         _lib.check(L.llampc_topk_merge_lists(lb.cta_lists.data_ptr(), n_lists, 1, 10, lb.best_key.data_ptr(),
                                              lb.result.data_ptr(), st), "K4'")
@@ -290,7 +290,7 @@ def run_b200(args):
     def k1_only():
         L.llampc_lookback_window_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2, TS,
                                      lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), lo,
-                                     int(bank.geom_shared), 0, st)
+                                     int(bank.geom_shared), lb.split, st)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -389,7 +389,7 @@ def run_b200(args):
     line = {"metric": "candidate-model RK4 steps/s (look-back window)", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(world), tyre_sine="MUFU.SIN (default; strict polynomial mode reported under other_configs)"),
             "gpu_launches": args.steps * 2, "clocks": clocks, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e
@@ -421,6 +421,21 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
         torch.cuda.synchronize()
         return float(np.mean([a.elapsed_time(b) for a, b in evs])) * 1e-3
 
+    # strict mode of the headline config: FMA-pipe polynomial tyre sine instead of MUFU.SIN
+    lbs = LookBack(make_bank(N_C2, seed=1), W=W_C2, Ts=TS, K=10, refine=0, fast_sin=False)
+    ts = np.arange(0, W_C2)
+    lbs.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
+    nls = L.llampc_lookback_num_lists(N_C2, W_C2, 0)
+
+    def c2_strict():
+        L.llampc_lookback_window_f32(lbs.bank.packed.data_ptr(), N_C2, lbs.bank.Npad, lbs.hist.data_ptr(), W_C2, 1, W_C2, TS,
+                                     lbs.avg_err.data_ptr(), lbs.best_key.data_ptr(), lbs.cta_lists.data_ptr(), 0,
+                                     int(lbs.bank.geom_shared), 0, st)
+        L.llampc_topk_merge_lists(lbs.cta_lists.data_ptr(), nls, 1, 10, lbs.best_key.data_ptr(), lbs.result.data_ptr(), st)
+    dt = time_it(c2_strict, 50)
+    out["C2_strict_polynomial_sin"] = {"steps_per_s": N_C2 * W_C2 / dt, "us_per_tick": dt * 1e6}
+    del lbs
+
     # C5 on one GPU: 1,048,576 candidates x 50 (the sharded sweep's single-GPU reference point)
     lb = LookBack(make_bank(N_C5, seed=5), W=W_C2, Ts=TS, K=10, refine=0)
     ts = np.arange(0, W_C2)
@@ -430,7 +445,7 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
     def c5():
         L.llampc_lookback_window_f32(lb.bank.packed.data_ptr(), N_C5, lb.bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2, TS,
                                      lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), 0,
-                                     int(lb.bank.geom_shared), 0, st)
+                                     int(lb.bank.geom_shared), lb.split, st)
         L.llampc_topk_merge_lists(lb.cta_lists.data_ptr(), n_lists, 1, 10, lb.best_key.data_ptr(), lb.result.data_ptr(), st)
     dt = time_it(c5, 20)
     out["C5_1gpu_lookback_1048576x50"] = {"steps_per_s": N_C5 * W_C2 / dt, "ms_per_tick": dt * 1e3}
@@ -445,7 +460,7 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
     def c1():
         L.llampc_lookback_window_f32(lb1.bank.packed.data_ptr(), 1024, lb1.bank.Npad, lb1.hist.data_ptr(), 20, 1, 20, TS,
                                      lb1.avg_err.data_ptr(), lb1.best_key.data_ptr(), lb1.cta_lists.data_ptr(), 0,
-                                     int(lb1.bank.geom_shared), 0, st)
+                                     int(lb1.bank.geom_shared), lb1.split, st)
         L.llampc_topk_merge_lists(lb1.cta_lists.data_ptr(), nl1, 1, 10, lb1.best_key.data_ptr(), lb1.result.data_ptr(), st)
     dt = time_it(c1, 50)
     out["C1_lookback_1024x20"] = {"steps_per_s": 1024 * 20 / dt, "us_per_tick": dt * 1e6}
@@ -459,7 +474,14 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
     Useq[..., 0] = np.clip(Useq[..., 0], -0.1, 1.0)
     Useq[..., 1] = np.clip(Useq[..., 1], -0.35, 0.35)
     xref = S[:2, t0:t0 + H + 1]
-    la = LookAhead(make_bank(M, seed=2), Ts=TS)
+    big = make_bank(N_C2, seed=2)
+    lbm = LookBack(big, W=W_C2, Ts=TS, K=10, refine=0)
+    ts = np.arange(0, W_C2)
+    lbm.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
+    lbm.evaluate()
+    keep = np.argsort(lbm.avg_errors(), kind="stable")[:M]          # the 16,384 best-adapted models
+    la = LookAhead({k: (v[keep] if np.ndim(v) else v) for k, v in big.items()}, Ts=TS)
+    del lbm
     plan = la.plan(S[:, t0], Useq, xref, U[:, t0 - 1])
     dt = time_it(plan.run, 20)
     out["C3_lookahead_16384x32x20"] = {"steps_per_s": M * K * H / dt, "ms_per_call": dt * 1e3}

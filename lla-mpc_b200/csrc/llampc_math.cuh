@@ -109,6 +109,18 @@ __device__ __forceinline__ float atan_full(float z) {
     return big ? (c - a) : a;
 }
 
+// np.arctan2(y, avx) for avx >= 0, ANY magnitudes, branch-free: q = min/max in [0, 1] (one MUFU.RCP),
+// octant fix-up, sign of y.  atan2(0, 0) = 0 like NumPy; a NaN input gives NaN.
+__device__ __forceinline__ float atan2_pos_full(float y, float avx) {
+    const float ay = fabsf(y);
+    const float mx = fmaxf(fmaxf(ay, avx), 1e-30f), mn = fminf(ay, avx);
+    const float q = mn * rcp_approx(mx);
+    float a = atan_unit(q);
+    a = (ay > avx) ? (LLAMPC_PIO2_HI - a) : a;
+    a = copysignf(a, y);
+    return (y != y || avx != avx) ? (y + avx) : a;             // fmaxf/fminf drop NaN operands: restore them
+}
+
 // sin(t) with a 4-coefficient polynomial (2.7e-8) after the same reduction as sin_any: used on the tyre
 // curve, where the fp32 evaluation error (1.2e-7) dominates the polynomial error anyway.
 __device__ __forceinline__ float sin_tyre(float t) {

@@ -95,21 +95,43 @@ __device__ __forceinline__ float accel_vx_only(const Cand& p, const Ctl& u, floa
 // |t| <= 0.5 and |e| <= 0.125, and `guard` accumulates max(2|t|, 8|e|) so that the caller can redo the whole
 // step with the general routines in the rare case the guard exceeds 1 (or is NaN).
 // ---------------------------------------------------------------------------------------------------
+// Drivetrain force with the per-step constants hoisted: Frx = (Cm1 pwm - Cr0) - vx (Cm2 pwm + Cr2 vx)
+struct Drive { float A, Bq; };
+__device__ __forceinline__ Drive prep_drive(const Cand& p, float pwm) {
+    Drive d;
+    d.A = fmaf(p.Cm1, pwm, -p.Cr0);
+    d.Bq = p.Cm2 * pwm;
+    return d;
+}
+__device__ __forceinline__ float drive_force_fast(const Cand& p, const Drive& d, float vx) {
+    return fmaf(-vx, fmaf(p.Cr2, vx, d.Bq), d.A);
+}
+
 template <bool MUFU_SIN>
 __device__ __forceinline__ float pacejka_fast(float B, float C, float D, float alpha) {
     const float t = C * atan_full(B * alpha);
     return D * (MUFU_SIN ? sin_mufu(t) : sin_tyre(t));
 }
 
-// WIDE_SLIP = false: slip tangents up to 0.5 (5-coefficient atan); true: up to 1 (9 coefficients) -- used by the
-// look-ahead rollouts, where unstable candidate models reach large slip angles within the horizon.
-template <bool MUFU_SIN, bool WIDE_SLIP = false>
-__device__ __forceinline__ Deriv accel_fast(const Cand& p, const Ctl& u, float vx, float vy, float w, float& guard) {
-    const float inv = rcp_approx(fabsf(vx));            // 1 ulp: the tangents are small, |error| <= 1.2e-7 |t|
-    const float tf = fmaf(p.lf, w, vy) * inv, tr = fmaf(p.lr, w, -vy) * inv;
-    guard = fmaxf(guard, (WIDE_SLIP ? 1.0f : 2.0f) * fmaxf(fabsf(tf), fabsf(tr)));
-    const float af = u.delta - (WIDE_SLIP ? atan_unit(tf) : atan_half(tf)), ar = WIDE_SLIP ? atan_unit(tr) : atan_half(tr);
-    const float Frx = drive_force(p, u.pwm, vx);
+// FULL_SLIP = false: slip tangents up to 0.5 (5-coefficient atan, guarded) -- the look-back, where every step
+// starts from a measured, non-spinning state; true: branch-free atan2 for any slip angle -- the look-ahead rollouts,
+// where unstable candidate models spin within the horizon (30 % of the warp-steps of config C3 see |t| > 0.5).
+template <bool MUFU_SIN, bool FULL_SLIP = false>
+__device__ __forceinline__ Deriv accel_fast(const Cand& p, const Ctl& u, const Drive& drv, float vx, float vy, float w,
+                                            float& guard) {
+    float af, ar;
+    if (FULL_SLIP) {
+        const float avx = fabsf(vx);
+        af = u.delta - atan2_pos_full(fmaf(p.lf, w, vy), avx);
+        ar = atan2_pos_full(fmaf(p.lr, w, -vy), avx);
+    } else {
+        const float inv = rcp_approx(fabsf(vx));        // 1 ulp: the tangents are small, |error| <= 1.2e-7 |t|
+        const float tf = fmaf(p.lf, w, vy) * inv, tr = fmaf(p.lr, w, -vy) * inv;
+        guard = fmaxf(guard, 2.0f * fmaxf(fabsf(tf), fabsf(tr)));
+        af = u.delta - atan_half(tf);
+        ar = atan_half(tr);
+    }
+    const float Frx = drive_force_fast(p, drv, vx);
     const float Ffy = pacejka_fast<MUFU_SIN>(p.Bf, p.Cf, p.Df, af);
     const float Fry = pacejka_fast<MUFU_SIN>(p.Br, p.Cr, p.Dr, ar);
     const float Fc = Ffy * u.cd;
@@ -166,7 +188,8 @@ __device__ __forceinline__ void rk4_increment_fast(const Cand& p, const Ctl& u, 
                                                    float w0, float h, float inc[6], float& guard) {
     const float hh = 0.5f * h, h6 = h * (1.0f / 6.0f);
     // weighted sums (k1 + 2 k2 + 2 k3 + k4) are accumulated stage by stage to keep few values live
-    Deriv a = accel_fast<MUFU_SIN, true>(p, u, vx0, vy0, w0, guard);
+    const Drive drv = prep_drive(p, u.pwm);
+    Deriv a = accel_fast<MUFU_SIN, true>(p, u, drv, vx0, vy0, w0, guard);
     float sx = fmaf(vx0, c0, -vy0 * s0), sy = fmaf(vx0, s0, vy0 * c0);
     float sw = w0, svx = a.vx, svy = a.vy, sdw = a.w;
     float vx = fmaf(hh, a.vx, vx0), vy = fmaf(hh, a.vy, vy0), w = fmaf(hh, a.w, w0);
@@ -174,7 +197,7 @@ __device__ __forceinline__ void rk4_increment_fast(const Cand& p, const Ctl& u, 
     sincos_half(d, sd, cd);
     float sn = fmaf(s0, cd, c0 * sd), cs = fmaf(c0, cd, -s0 * sd);
     // stage 2
-    a = accel_fast<MUFU_SIN, true>(p, u, vx, vy, w, guard);
+    a = accel_fast<MUFU_SIN, true>(p, u, drv, vx, vy, w, guard);
     sx = fmaf(2.0f, fmaf(vx, cs, -vy * sn), sx);
     sy = fmaf(2.0f, fmaf(vx, sn, vy * cs), sy);
     sw = fmaf(2.0f, w, sw); svx = fmaf(2.0f, a.vx, svx); svy = fmaf(2.0f, a.vy, svy); sdw = fmaf(2.0f, a.w, sdw);
@@ -184,7 +207,7 @@ __device__ __forceinline__ void rk4_increment_fast(const Cand& p, const Ctl& u, 
     sincos_half(d, sd, cd);
     sn = fmaf(s0, cd, c0 * sd); cs = fmaf(c0, cd, -s0 * sd);
     // stage 3
-    a = accel_fast<MUFU_SIN, true>(p, u, vx, vy, w, guard);
+    a = accel_fast<MUFU_SIN, true>(p, u, drv, vx, vy, w, guard);
     sx = fmaf(2.0f, fmaf(vx, cs, -vy * sn), sx);
     sy = fmaf(2.0f, fmaf(vx, sn, vy * cs), sy);
     sw = fmaf(2.0f, w, sw); svx = fmaf(2.0f, a.vx, svx); svy = fmaf(2.0f, a.vy, svy); sdw = fmaf(2.0f, a.w, sdw);
@@ -194,7 +217,7 @@ __device__ __forceinline__ void rk4_increment_fast(const Cand& p, const Ctl& u, 
     sincos_half(d, sd, cd);
     sn = fmaf(s0, cd, c0 * sd); cs = fmaf(c0, cd, -s0 * sd);
     // stage 4
-    a = accel_fast<MUFU_SIN, true>(p, u, vx, vy, w, guard);
+    a = accel_fast<MUFU_SIN, true>(p, u, drv, vx, vy, w, guard);
     sx += fmaf(vx, cs, -vy * sn);
     sy += fmaf(vx, sn, vy * cs);
     guard = fmaxf(guard, 2.0f * dmax);
@@ -285,10 +308,11 @@ __device__ __forceinline__ float lookback_step_fast(const Cand& p, const HistRow
     Ctl u;
     u.pwm = r.q2.y; u.delta = r.q2.z; u.sd = r.q2.w; u.cd = r.q3.x;
     float guard = 0.0f;
+    const Drive drv = prep_drive(p, u.pwm);
     // stage 1
     Deriv a1;
     if (GEOM_SHARED) {
-        const float Frx = drive_force(p, u.pwm, vx0);
+        const float Frx = drive_force_fast(p, drv, vx0);
         const float Ffy = pacejka_fast<MUFU_SIN>(p.Bf, p.Cf, p.Df, r.q4.z);
         const float Fry = pacejka_fast<MUFU_SIN>(p.Br, p.Cr, p.Dr, r.q4.w);
         const float Fc = Ffy * u.cd;
@@ -296,11 +320,11 @@ __device__ __forceinline__ float lookback_step_fast(const Cand& p, const HistRow
         a1.vy = fmaf(Fry + Fc, p.inv_m, -vx0 * w0);
         a1.w = fmaf(Fc, p.lf_Iz, -Fry * p.lr_Iz);
     } else {
-        a1 = accel_fast<MUFU_SIN>(p, u, vx0, vy0, w0, guard);
+        a1 = accel_fast<MUFU_SIN>(p, u, drv, vx0, vy0, w0, guard);
     }
     // stage 2
     const float vx2 = fmaf(hh, a1.vx, vx0), vy2 = fmaf(hh, a1.vy, vy0), w2 = fmaf(hh, a1.w, w0);
-    const Deriv a2 = accel_fast<MUFU_SIN>(p, u, vx2, vy2, w2, guard);
+    const Deriv a2 = accel_fast<MUFU_SIN>(p, u, drv, vx2, vy2, w2, guard);
     float xs = fmaf(vx2, r.q0.w, -vy2 * r.q0.z), ys = fmaf(vx2, r.q0.z, vy2 * r.q0.w);
     // stage 3
     const float vx3 = fmaf(hh, a2.vx, vx0), vy3 = fmaf(hh, a2.vy, vy0), w3 = fmaf(hh, a2.w, w0);
@@ -308,7 +332,7 @@ __device__ __forceinline__ float lookback_step_fast(const Cand& p, const HistRow
     float sd, cd;
     sincos_tiny(e3, sd, cd);
     const float s3 = fmaf(r.q0.z, cd, r.q0.w * sd), c3 = fmaf(r.q0.w, cd, -r.q0.z * sd);
-    const Deriv a3 = accel_fast<MUFU_SIN>(p, u, vx3, vy3, w3, guard);
+    const Deriv a3 = accel_fast<MUFU_SIN>(p, u, drv, vx3, vy3, w3, guard);
     xs += fmaf(vx3, c3, -vy3 * s3);
     ys += fmaf(vx3, s3, vy3 * c3);
     // stage 4 (front tyre and drivetrain only)
@@ -321,7 +345,7 @@ __device__ __forceinline__ float lookback_step_fast(const Cand& p, const HistRow
     const float tf4 = fmaf(p.lf, w4, vy4) * inv4;
     guard = fmaxf(guard, 2.0f * fabsf(tf4));
     const float Ffy4 = pacejka_fast<MUFU_SIN>(p.Bf, p.Cf, p.Df, u.delta - atan_half(tf4));
-    const float a4vx = fmaf(fmaf(-Ffy4, u.sd, drive_force(p, u.pwm, vx4)), p.inv_m, vy4 * w4);
+    const float a4vx = fmaf(fmaf(-Ffy4, u.sd, drive_force_fast(p, drv, vx4)), p.inv_m, vy4 * w4);
     const float xd4 = fmaf(vx4, c4, -vy4 * s4), yd4 = fmaf(vx4, s4, vy4 * c4);
     // increment errors
     const float sx = fmaf(2.0f, xs, xd4), sy = fmaf(2.0f, ys, yd4);

@@ -417,7 +417,7 @@ static int lookback_window_impl(const float* bank, int N, int Npad, const float*
     if (!aligned16(bank) || !aligned16(hist) || (hist_stride_rows * LLAMPC_HIST_ROW * 4) % 16) return LLAMPC_E_ALIGN;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int mufu = 0;
-    if (split >= 16) { mufu = 1; split -= 16; }   // experiment switch: MUFU.SIN tyre sine (not used by the host package)
+    if (split >= 16) { mufu = 1; split -= 16; }   // bit 4: MUFU.SIN tyre sine (LookBack(fast_sin=True))
     if (split == 0) split = choose_split(N, W);
     if (split > W) split = 1;
 #define LB_CASE(SYV)                                                                                                  \

@@ -109,8 +109,8 @@ def test_lookback_c1_golden(history):
     g = load_golden("lookback_c1.npz")
     S, U, Ts = history
     bank = orc.make_bank(1024, seed=0)
-    for refine in (0, 16, 32):                                 # 0/16: fused K1 + list merge; 32: stand-alone top-K
-        lb = LookBack(bank, W=int(g["W"]), Ts=Ts, K=int(g["K"]), refine=refine)
+    for refine, fast_sin in ((0, True), (16, True), (32, True), (16, False)):   # 0/16: fused K1 + list merge; 32: stand-alone top-K
+        lb = LookBack(bank, W=int(g["W"]), Ts=Ts, K=int(g["K"]), refine=refine, fast_sin=fast_sin)
         for t_end in g["ticks"]:
             t_end = int(t_end)
             best, topk, best_err = _window(lb, S, U, t_end)
@@ -159,14 +159,15 @@ def test_lookback_c2_full_size(history):
     S, U, Ts = history
     var = orc.RT_VARIATION + (("mass", 0.15),)
     bank = orc.make_bank(65536, seed=1, variation=var)
-    lb = LookBack(bank, W=50, Ts=Ts, K=10, refine=32)
-    for t_end in (600, 1600):
-        best, topk, best_err = _window(lb, S, U, t_end)
-        ref = np.mean(orc.window_errors(bank, S, U, t_end, 50, Ts), axis=1)
-        _assert_scores(lb.avg_errors(), ref, "C2 t=%d" % t_end)
-        rbest, rtopk = orc.select(ref, 10)
-        assert best == rbest and list(topk) == list(rtopk)
-        assert abs(best_err - ref[rbest]) <= 1e-9 * ref[rbest]
+    refs = {t_end: np.mean(orc.window_errors(bank, S, U, t_end, 50, Ts), axis=1) for t_end in (600, 1600)}
+    for fast_sin, refine in ((True, 16), (False, 32)):            # default (MUFU.SIN tyre sine) and strict polynomial mode
+        lb = LookBack(bank, W=50, Ts=Ts, K=10, refine=refine, fast_sin=fast_sin)
+        for t_end, ref in refs.items():
+            best, topk, best_err = _window(lb, S, U, t_end)
+            _assert_scores(lb.avg_errors(), ref, "C2 t=%d fast_sin=%s" % (t_end, fast_sin))
+            rbest, rtopk = orc.select(ref, 10)
+            assert best == rbest and list(topk) == list(rtopk)
+            assert abs(best_err - ref[rbest]) <= 1e-9 * ref[rbest]
 
 
 def test_lookback_wide_bank_and_geometry_varied(history):
