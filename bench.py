@@ -375,7 +375,22 @@ def run_b200(args):
         d2h = (1 + 2 * lbe.Kt) * 8
         e2e = {"value": steps_per_tick * args.steps / wall, "unit": "steps/s", "h2d_bytes_per_step": h2d,
                "d2h_bytes_per_step": d2h, "api": "LookBack.push (host NumPy transition in; fp64 re-score of the 16 finalists and, for N > 1, the finalist all-gather included; arg-min + top-10 indices out)"}
-        lat = {"p50_us": float(np.percentile(lats, 50) * 1e6), "p95_us": float(np.percentile(lats, 95) * 1e6)}
+        lat = {"p50_us": float(np.percentile(lats, 50) * 1e6), "p95_us": float(np.percentile(lats, 95) * 1e6),
+               "mode": "recompute (the whole 50-row window re-integrated every tick)"}
+        if world == 1:
+            # the reference's own rolling bookkeeping (one new error column per tick): same decisions, 1/W of the work
+            lbr = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=16, mode="rolling")
+            for t in range(W_C2 + 5):
+                lbr.push(S[:, t], U[:, t], S[:, t + 1])
+            lr = []
+            for i in range(args.steps):
+                t = W_C2 + 5 + i
+                a = time.perf_counter()
+                lbr.push(S[:, t], U[:, t], S[:, t + 1])
+                lr.append(time.perf_counter() - a)
+            lat["rolling_mode_p50_us"] = float(np.percentile(lr, 50) * 1e6)
+            lat["rolling_mode_p95_us"] = float(np.percentile(lr, 95) * 1e6)
+            del lbr
 
     extras = {}
     if world == 1 and not args.no_extras:

@@ -40,7 +40,7 @@ class MonteCarlo:
             raise ValueError("K_models <= %d" % _lib.LIST_LEN)
         N = self.bank.N
         f64, f32, i32, i64 = torch.float64, torch.float32, torch.int32, torch.int64
-        dv = lambda a, dt: torch.from_numpy(np.ascontiguousarray(a)).to(dev).to(dt)
+        dv = lambda a, dt: torch.from_numpy(np.array(a, copy=True, order="C")).to(dev).to(dt)
         self.x = dv(x_init, f64)
         self.x_next = torch.empty_like(self.x)
         pp = np.stack([np.broadcast_to(np.asarray(plant_params[k], dtype=np.float64), (V,)) for k in PARAM_NAMES], axis=1)
