@@ -275,15 +275,16 @@ def run_b200(args):
     n_lists = L.llampc_lookback_num_lists(n_local, W_C2, 0)
     assert lb.fused and n_lists > 0
 
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    one_launch = n_lists <= 1024
+
     def tick_device():
-        """One look-back tick with device-resident inputs: K1 (scores, block arg-min, per-CTA sorted lists) and
-        the list merge (top-10; moves the arg-min key to topk_keys[0]) (+ the min-loc all-reduce for N > 1)."""
-        rc = L.llampc_lookback_window_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2, TS,
-                                          lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), lo,
-                                          int(bank.geom_shared), lb.split, st)
-        _lib.check(rc, "K1")
-        _lib.check(L.llampc_topk_merge_lists(lb.cta_lists.data_ptr(), n_lists, 1, 10, lb.best_key.data_ptr(),
-                                             lb.result.data_ptr(), st), "K4'")
+        """One look-back tick with device-resident inputs: K1 (scores, block arg-min, per-CTA sorted lists) with the
+        top-10 merge finished by the last CTA inside the same launch (+ the min-loc all-reduce for N > 1)."""
+        rc = L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2,
+                                               TS, lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), lo,
+                                               int(bank.geom_shared), lb.split, 10, ticket.data_ptr(), lb.result.data_ptr(), st)
+        _lib.check(rc, "K1+K4'")
         if world > 1:
             td.all_reduce(lb.result[:1], op=td.ReduceOp.MIN)
 
@@ -405,7 +406,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": dict(workload_config(world), tyre_sine="MUFU.SIN (default; strict polynomial mode reported under other_configs)"),
-            "gpu_launches": args.steps * 2, "clocks": clocks, "roofline": roofline}
+            "gpu_launches": args.steps * (1 if one_launch else 2), "clocks": clocks, "roofline": roofline}
     if e2e:
         line["e2e"] = e2e
         line["tick_latency"] = lat

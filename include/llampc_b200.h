@@ -83,6 +83,16 @@ int llampc_lookback_window_f32(const float* bank, int N, int Npad,
                                int geom_shared, int split, llampc_stream_t stream);
 int llampc_lookback_num_lists(int N, int W, int split);
 
+/* K1 with the top-K finished inside the same launch: the last CTA of each vehicle to retire (atomic ticket) merges
+ * the per-CTA lists.  ticket [n_vehicles] unsigned, zero before the first call (self-resetting);
+ * out [n_vehicles][LLAMPC_LIST_LEN + 1] as llampc_topk_merge_lists.  With more than 1,024 lists per vehicle the call
+ * falls back to two launches (K1 + llampc_topk_merge_lists). */
+int llampc_lookback_window_topk_f32(const float* bank, int N, int Npad, const float* hist, int W,
+                                    int n_vehicles, int hist_stride_rows, double Ts, float* avg_err,
+                                    llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
+                                    int geom_shared, int split, int K, unsigned* ticket, llampc_key_t* out,
+                                    llampc_stream_t stream);
+
 /* K1r  rolling window, the reference's own bookkeeping (error_windows = np.roll(...); [:, -1] = errors; mean,
  * run_nmpc_orca_llampc_rt.py:349-358): one RK4 step per candidate for the newest transition (row32_h, HOST pointer,
  * passed as kernel parameter), error column `slot` of err_ring [W][Npad] replaced, window mean re-summed from the
@@ -143,6 +153,8 @@ typedef struct llampc_tick {
     llampc_key_t* result_h;         /* pinned host, same layout; with sync != 0 the finalists come back
                                        ordered by score (fp64 if re-scored), ties by lower index           */
     int sync;                       /* non-zero: cudaStreamSynchronize + host ordering before returning    */
+    unsigned* ticket;               /* [1], zero-initialised: finish the top-K inside K1 (one launch per tick) when
+                                       the bank yields <= 1,024 per-CTA lists; NULL = always use the merge kernel */
     float* err_ring;                /* [W][Npad] per-tick error columns (rolling mode only)                */
     int rolling;                    /* 0: recompute the whole window from the history ring (K1);
                                        1: rolling mode (K1r): integrate only the newest row, replace ring column

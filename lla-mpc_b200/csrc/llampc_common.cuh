@@ -89,6 +89,49 @@ __device__ __forceinline__ u64 warp_merge_low32(u64 a, u64 b_rev, int lane) {
     return m;
 }
 
+// K-way merge of n_lists ascending lists of LLAMPC_LIST_LEN keys into the K smallest keys overall (K <= LLAMPC_LIST_LEN):
+// K rounds of "block-min over the list heads"; each thread owns up to MERGE_LPT lists and keeps their head and
+// next key in registers so that the load of a popped list's successor is off the critical path.
+// out[0] = *best_key (then re-armed to ~0 for the next tick), out[1..K] = ascending top-K.  sbuf: THREADS/32+1 keys.
+constexpr int MERGE_LPT = 8;
+
+template <int THREADS>
+__device__ __forceinline__ void merge_lists_device(const u64* __restrict__ lists, int n_lists, int K,
+                                                   u64* __restrict__ best_key, u64* __restrict__ out, u64* sbuf) {
+    u64 head[MERGE_LPT], next[MERGE_LPT];
+    int pos[MERGE_LPT];
+#pragma unroll
+    for (int j = 0; j < MERGE_LPT; ++j) {
+        const int l = threadIdx.x + j * THREADS;
+        head[j] = ~0ull; next[j] = ~0ull; pos[j] = 1;
+        if (l < n_lists) {
+            head[j] = __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN);
+            next[j] = __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN + 1);
+        }
+    }
+    if (threadIdx.x == 0 && best_key) {
+        out[0] = __ldcg(best_key);
+        *best_key = ~0ull;
+    }
+    for (int r = 0; r < K; ++r) {
+        u64 mine = head[0];
+#pragma unroll
+        for (int j = 1; j < MERGE_LPT; ++j) mine = u64_min(mine, head[j]);
+        const u64 sel = block_min_u64_w0<THREADS / 32>(mine, sbuf);
+        if (threadIdx.x == 0) out[1 + r] = sel;
+        if (sel == ~0ull || mine != sel) continue;
+#pragma unroll
+        for (int j = 0; j < MERGE_LPT; ++j) {
+            if (head[j] == sel) {                  // pop: successor becomes the head, prefetch the one after
+                head[j] = next[j];
+                pos[j] += 1;
+                const int l = threadIdx.x + j * THREADS;
+                next[j] = pos[j] < LLAMPC_LIST_LEN ? __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN + pos[j]) : ~0ull;
+            }
+        }
+    }
+}
+
 // ---- mbarrier + cp.async.bulk (TMA 1-D bulk copy global -> shared; SASS: UBLKCP) ---------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 

@@ -55,11 +55,15 @@ __device__ __forceinline__ void cta_select_emit(u64 key, u64* skeys, int v, u64*
 // H2D copy: every CTA patches its shared-memory copy of ring slot `slot`, CTA 0 also stores it to the ring.
 struct NewRow { float v[LLAMPC_HIST_ROW]; int slot; };
 
+// Optional in-kernel finish of the top-K: the last CTA of a vehicle to retire (atomic ticket) merges the per-CTA
+// lists itself, so a tick is ONE launch.  Needs gridDim.x <= 128 * MERGE_LPT lists; K = 0 disables it.
+struct FusedMerge { unsigned* ticket; u64* out; int K; };
+
 template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
 __global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB_MIN_BLOCKS)
 lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
                        long hist_stride_floats, StepSize z, float* __restrict__ avg_err, u64* __restrict__ best_key,
-                       u64* __restrict__ cta_lists, int idx_offset, NewRow nr) {
+                       u64* __restrict__ cta_lists, int idx_offset, NewRow nr, FusedMerge fm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ u64 skeys[LB_THREADS];
@@ -124,6 +128,18 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
         key = pack_key(err, (unsigned)(idx_offset + cand));
     }
     cta_select_emit<CPB / 32>(key, skeys, v, best_key, cta_lists);
+    if (fm.K > 0) {                                // uniform over the grid
+        __shared__ bool is_last;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) is_last = atomicAdd(fm.ticket + v, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        merge_lists_device<LB_THREADS>(cta_lists + (size_t)v * gridDim.x * LLAMPC_LIST_LEN, gridDim.x, fm.K,
+                                       best_key ? best_key + v : nullptr, fm.out + (size_t)v * (LLAMPC_LIST_LEN + 1), skeys);
+        if (tid == 0) fm.ticket[v] = 0;            // ready for the next launch on the same stream
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -172,48 +188,14 @@ lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W,
 // head and next key in registers so that the load of a popped list's successor is off the critical path.
 // out[0] = *best_key (then re-armed to ~0 for the next tick), out[1..K] = ascending top-K.
 // ---------------------------------------------------------------------------------------------------
-constexpr int MERGE_LPT = 8;
-
 template <int MERGE_THREADS>
 __global__ void __launch_bounds__(MERGE_THREADS)
 topk_merge_lists_kernel(const u64* __restrict__ lists, int n_lists, int K, u64* __restrict__ best_key,
                         u64* __restrict__ out) {
     __shared__ u64 sbuf[MERGE_THREADS / 32 + 1];
     const int v = blockIdx.x;                      // vehicle
-    lists += (size_t)v * n_lists * LLAMPC_LIST_LEN;
-    out += (size_t)v * (LLAMPC_LIST_LEN + 1);
-    u64 head[MERGE_LPT], next[MERGE_LPT];
-    int pos[MERGE_LPT];
-#pragma unroll
-    for (int j = 0; j < MERGE_LPT; ++j) {
-        const int l = threadIdx.x + j * MERGE_THREADS;
-        head[j] = ~0ull; next[j] = ~0ull; pos[j] = 1;
-        if (l < n_lists) {
-            head[j] = __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN);
-            next[j] = __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN + 1);
-        }
-    }
-    if (threadIdx.x == 0 && best_key) {
-        out[0] = best_key[v];
-        best_key[v] = ~0ull;
-    }
-    for (int r = 0; r < K; ++r) {
-        u64 mine = head[0];
-#pragma unroll
-        for (int j = 1; j < MERGE_LPT; ++j) mine = u64_min(mine, head[j]);
-        const u64 sel = block_min_u64_w0<MERGE_THREADS / 32>(mine, sbuf);
-        if (threadIdx.x == 0) out[1 + r] = sel;
-        if (sel == ~0ull || mine != sel) continue;
-#pragma unroll
-        for (int j = 0; j < MERGE_LPT; ++j) {
-            if (head[j] == sel) {                  // pop: successor becomes the head, prefetch the one after
-                head[j] = next[j];
-                pos[j] += 1;
-                const int l = threadIdx.x + j * MERGE_THREADS;
-                next[j] = pos[j] < LLAMPC_LIST_LEN ? __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN + pos[j]) : ~0ull;
-            }
-        }
-    }
+    merge_lists_device<MERGE_THREADS>(lists + (size_t)v * n_lists * LLAMPC_LIST_LEN, n_lists, K,
+                                      best_key ? best_key + v : nullptr, out + (size_t)v * (LLAMPC_LIST_LEN + 1), sbuf);
 }
 
 __global__ void fill_keys_kernel(u64* keys, int n) {
@@ -390,7 +372,7 @@ static StepSize make_step(double Ts) {
 template <int SY, bool GEOM, bool MUFU>
 static int launch_lookback(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
                            int hist_stride_rows, double Ts, float* avg_err, u64* best_key, u64* cta_lists,
-                           int idx_offset, const NewRow& nr, cudaStream_t st) {
+                           int idx_offset, const NewRow& nr, const FusedMerge& fm, cudaStream_t st) {
     auto kern = lookback_window_kernel<SY, GEOM, MUFU>;
     const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 : 0);
     if (smem > 48 * 1024) {
@@ -404,14 +386,14 @@ static int launch_lookback(const float* bank, int N, int Npad, const float* hist
     dim3 grid((N + CPB - 1) / CPB, n_vehicles);
     kern<<<grid, LB_THREADS, smem, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, hist, W,
                                          (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key, cta_lists,
-                                         idx_offset, nr);
+                                         idx_offset, nr, fm);
     return (int)cudaGetLastError();
 }
 
 static int lookback_window_impl(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
                                 int hist_stride_rows, double Ts, float* avg_err, llampc_key_t* best_key,
                                 llampc_key_t* cta_lists, int idx_offset, int geom_shared, int split,
-                                const NewRow& nr, llampc_stream_t stream) {
+                                const NewRow& nr, const FusedMerge& fm, llampc_stream_t stream) {
     if (!bank || !hist || (!best_key && !cta_lists && !avg_err) || N <= 0 || Npad < N || n_vehicles <= 0 || hist_stride_rows < W) return LLAMPC_E_ARG;
     if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
     if (!aligned16(bank) || !aligned16(hist) || (hist_stride_rows * LLAMPC_HIST_ROW * 4) % 16) return LLAMPC_E_ALIGN;
@@ -422,10 +404,10 @@ static int lookback_window_impl(const float* bank, int N, int Npad, const float*
     if (split > W) split = 1;
 #define LB_CASE(SYV)                                                                                                  \
     case SYV:                                                                                                         \
-        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, st)   \
-                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, st); \
-        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, st)            \
-                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, st);
+        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, st)   \
+                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, st); \
+        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, st)            \
+                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, st);
     switch (split) {
         LB_CASE(1)
         LB_CASE(2)
@@ -441,8 +423,32 @@ extern "C" int llampc_lookback_window_f32(const float* bank, int N, int Npad, co
                                           int geom_shared, int split, llampc_stream_t stream) {
     NewRow nr;
     nr.slot = -1;
+    FusedMerge fm = {nullptr, nullptr, 0};
     return lookback_window_impl(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists,
-                                idx_offset, geom_shared, split, nr, stream);
+                                idx_offset, geom_shared, split, nr, fm, stream);
+}
+
+extern "C" int llampc_lookback_window_topk_f32(const float* bank, int N, int Npad, const float* hist, int W,
+                                               int n_vehicles, int hist_stride_rows, double Ts, float* avg_err,
+                                               llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
+                                               int geom_shared, int split, int K, unsigned* ticket, llampc_key_t* out,
+                                               llampc_stream_t stream) {
+    if (!cta_lists || !out || !ticket || !best_key) return LLAMPC_E_ARG;
+    if (K <= 0 || K > LLAMPC_LIST_LEN) return LLAMPC_E_RANGE;
+    const int n_lists = llampc_lookback_num_lists(N, W, split);
+    if (n_lists <= 0) return LLAMPC_E_ARG;
+    NewRow nr;
+    nr.slot = -1;
+    if (n_lists > LB_THREADS * MERGE_LPT) {          // too many lists for one CTA: K1, then the stand-alone merge kernel
+        FusedMerge none = {nullptr, nullptr, 0};
+        int rc = lookback_window_impl(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists,
+                                      idx_offset, geom_shared, split, nr, none, stream);
+        if (rc) return rc;
+        return llampc_topk_merge_lists(cta_lists, n_lists, n_vehicles, K, best_key, out, stream);
+    }
+    FusedMerge fm = {ticket, out, K};
+    return lookback_window_impl(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists,
+                                idx_offset, geom_shared, split, nr, fm, stream);
 }
 
 extern "C" int llampc_lookback_rolling_f32(const float* bank, int N, int Npad, const float* row32_h, int slot, int W,
@@ -594,18 +600,23 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
         if (rc) return rc;
     } else if (fused) {
         // K1 (block arg-min + per-CTA sorted lists) -> list merge (also moves best_key to keys[0] and re-arms it)
-        rc = lookback_window_impl(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key,
-                                  t->cta_lists, t->idx_offset, t->geom_shared, t->split, nr, stream);
-        if (rc) return rc;
         const int n_lists = llampc_lookback_num_lists(t->N, t->W, t->split);
-        rc = llampc_topk_merge_lists(t->cta_lists, n_lists, 1, Kt, t->best_key, keys, stream);
+        const bool in_kernel = t->ticket != nullptr && Kt > 0 && n_lists <= LB_THREADS * MERGE_LPT;
+        FusedMerge fm = {in_kernel ? t->ticket : nullptr, in_kernel ? keys : nullptr, in_kernel ? Kt : 0};
+        rc = lookback_window_impl(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key,
+                                  t->cta_lists, t->idx_offset, t->geom_shared, t->split, nr, fm, stream);
         if (rc) return rc;
+        if (!in_kernel) {
+            rc = llampc_topk_merge_lists(t->cta_lists, n_lists, 1, Kt, t->best_key, keys, stream);
+            if (rc) return rc;
+        }
     } else {
         if (!t->avg_err) return LLAMPC_E_ARG;
         rc = llampc_fill_keys(t->best_key, 1, stream);
         if (rc) return rc;
+        FusedMerge none = {nullptr, nullptr, 0};
         rc = lookback_window_impl(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key, nullptr,
-                                  t->idx_offset, t->geom_shared, t->split, nr, stream);
+                                  t->idx_offset, t->geom_shared, t->split, nr, none, stream);
         if (rc) return rc;
         LLAMPC_CUDA_TRY(cudaMemcpyAsync(keys, t->best_key, sizeof(llampc_key_t), cudaMemcpyDeviceToDevice, st));
         if (Kt > 0) {

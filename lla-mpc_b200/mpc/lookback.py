@@ -114,6 +114,8 @@ class LookBack:
             t.bank64, t.hist64 = self.bank.bank64.data_ptr(), self.hist64.data_ptr()
         t.result, t.result_h = self.result.data_ptr(), self.result_h.data_ptr()
         t.sync = 1
+        self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        t.ticket = self.ticket.data_ptr()
         if self.rolling:
             t.err_ring, t.rolling = self.err_ring.data_ptr(), 1
         self._tick = t
@@ -184,27 +186,48 @@ class LookBack:
 
     def _run_tick(self):
         torch = self.torch
+        Kt = self.Kt
+        dist = self.group is not None
+        self._tick.sync = 0 if dist else 1
         with self._stream_dev:
             rc = self._L.llampc_lookback_tick(self._tick_ref, torch.cuda.current_stream().cuda_stream)
         if rc:
             _lib.check(rc, "llampc_lookback_tick")
-        Kt = self.Kt
+        if dist:
+            return self._finish_distributed()
         keys = self._res_keys
         if Kt == 0:
             err, idx = decode_keys(keys[:1])
-            best, best_err = int(idx[0]), float(err[0])
-            if self.group is not None:
-                k = _dist.minloc_allreduce(self.result[:1], self.group)
-                err, idx = decode_keys(np.array([k], dtype=np.uint64))
-                best, best_err = int(idx[0]), float(err[0])
-            return best, np.zeros(0, dtype=np.int64), best_err
+            return int(idx[0]), np.zeros(0, dtype=np.int64), float(err[0])
         # finalists arrive ordered by score (fp64 when re-scored), ties by index, NaN / padding last
         idx = (keys[1:1 + Kt] & np.uint64(0xFFFFFFFF)).astype(np.int64)
         scores = self._res_errs[1 + Kt:1 + 2 * Kt]
-        if self.group is not None:
-            scores, idx = _dist.gather_finalists(scores, idx, self.group, self.bank.device)
-            order = np.lexsort((idx, scores))
-            scores, idx = scores[order], idx[order]
+        n_ok = int(np.count_nonzero(scores == scores))
+        return int(idx[0]), idx[:min(self.K, n_ok)].copy(), float(scores[0])
+
+    def _finish_distributed(self):
+        """Multi-GPU exchange, on the device: one MIN all-reduce of the packed key (K = 0) or one all-gather of every
+        rank's finalists (keys + fp64 scores), then a single copy to the host."""
+        import torch.distributed as td
+        torch, Kt = self.torch, self.Kt
+        if Kt == 0:
+            k = _dist.minloc_allreduce(self.result[:1], self.group)
+            err, idx = decode_keys(np.array([k], dtype=np.uint64))
+            return int(idx[0]), np.zeros(0, dtype=np.int64), float(err[0])
+        world = td.get_world_size(self.group)
+        if getattr(self, "_gather_buf", None) is None:
+            self._gather_buf = torch.empty((world, 2 * Kt), dtype=torch.int64, device=self.bank.device)
+        td.all_gather_into_tensor(self._gather_buf, self.result[1:1 + 2 * Kt], group=self.group)
+        allr = self._gather_buf.cpu().numpy()                      # synchronises the stream
+        keys = allr[:, :Kt].reshape(-1).view(np.uint64)
+        idx = (keys & np.uint64(0xFFFFFFFF)).astype(np.int64)
+        if self.n_refine > 0:
+            scores = allr[:, Kt:].reshape(-1).view(np.float64)
+        else:
+            scores = (keys >> np.uint64(32)).astype(np.uint32).view(np.float32).astype(np.float64)
+            scores[keys == np.uint64(0xFFFFFFFFFFFFFFFF)] = np.nan
+        order = np.lexsort((idx, scores))                          # NaN sorts last
+        scores, idx = scores[order], idx[order]
         n_ok = int(np.count_nonzero(scores == scores))
         return int(idx[0]), idx[:min(self.K, n_ok)].copy(), float(scores[0])
 

@@ -74,6 +74,7 @@ class MonteCarlo:
         self.cta_lists = torch.empty((V, self.n_lists, _lib.LIST_LEN), dtype=i64, device=dev)
         self.best_key = torch.full((V,), -1, dtype=i64, device=dev)
         self.topk = torch.zeros((V, _lib.LIST_LEN + 1), dtype=i64, device=dev)
+        self.ticket = torch.zeros(V, dtype=i32, device=dev)
         self.qrp = np.array([1.0, 1.0, 5e-3, 1.0, 0.0, 0.0], dtype=np.float32)
         self.tick_count = 0
         self.lookback_steps = 0
@@ -110,11 +111,10 @@ class MonteCarlo:
             chk(L.llampc_pack_rows_f64(self.x.data_ptr(), self.u_applied.data_ptr(), self.x_next.data_ptr(), V, self.Ts,
                                        bank.lf_shared, bank.lr_shared, slot, self.W, self.hist.data_ptr(), None, st), "pack_rows")
             if self.tick_count + 1 >= self.W:
-                chk(L.llampc_lookback_window_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), self.W, V,
-                                                 self.W, self.Ts, None, self.best_key.data_ptr(), self.cta_lists.data_ptr(), 0,
-                                                 int(bank.geom_shared), 0, st), "lookback")
-                chk(L.llampc_topk_merge_lists(self.cta_lists.data_ptr(), self.n_lists, V, self.Km, self.best_key.data_ptr(),
-                                              self.topk.data_ptr(), st), "merge")
+                chk(L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), self.W,
+                                                      V, self.W, self.Ts, None, self.best_key.data_ptr(),
+                                                      self.cta_lists.data_ptr(), 0, int(bank.geom_shared), 16, self.Km,
+                                                      self.ticket.data_ptr(), self.topk.data_ptr(), st), "lookback+merge")
                 chk(L.llampc_mu_estimate_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.Km, 0, bank.bank64.data_ptr(),
                                              bank.N, V, self.smoothing, self.mu_alpha, 0.95, 9.81, self.mu_state.data_ptr(),
                                              self.curr_mu.data_ptr(), st), "mu_estimate")

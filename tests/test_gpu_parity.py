@@ -523,3 +523,42 @@ def test_montecarlo_closed_loop_stagewise_parity():
                 np.testing.assert_allclose(post["curr_mu"][v], mu_ref, rtol=1e-12)
         else:
             assert np.array_equal(post["model_idx"], pre["model_idx"])
+
+
+def test_one_launch_tick_matches_two_launch(history):
+    """llampc_lookback_window_topk_f32 (last-CTA merge inside K1) == K1 + llampc_topk_merge_lists, several vehicles."""
+    import torch
+    from llampc_b200 import _lib
+    from llampc_b200.bank import ModelBank
+    S, U, Ts = history
+    L = _lib.lib()
+    bank = ModelBank(orc.make_bank(5000, seed=6))
+    V, W, K = 3, 12, 16
+    rows = np.zeros((V, W, 20), dtype=np.float32)
+    for v, te in enumerate((300, 900, 1500)):
+        for j, t in enumerate(range(te - W + 1, te + 1)):
+            xk, uk, xk1 = (np.ascontiguousarray(a) for a in (S[:, t], U[:, t], S[:, t + 1]))
+            L.llampc_hist_row_pack_h(xk.ctypes.data, uk.ctypes.data, xk1.ctypes.data, Ts, bank.lf_shared, bank.lr_shared,
+                                     rows[v, j].ctypes.data, None)
+    hist = torch.from_numpy(rows).cuda()
+    st = torch.cuda.current_stream().cuda_stream
+    n_lists = L.llampc_lookback_num_lists(5000, W, 0)
+    outs = []
+    for fused in (False, True):
+        keys = torch.full((V,), -1, dtype=torch.int64, device="cuda")
+        lists = torch.empty((V, n_lists, 16), dtype=torch.int64, device="cuda")
+        out = torch.zeros((V, 17), dtype=torch.int64, device="cuda")
+        ticket = torch.zeros(V, dtype=torch.int32, device="cuda")
+        for _ in range(2):                                        # twice: the ticket and best_key re-arm themselves
+            if fused:
+                _lib.check(L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), 5000, bank.Npad, hist.data_ptr(), W, V, W,
+                                                             Ts, None, keys.data_ptr(), lists.data_ptr(), 0, 1, 0, K,
+                                                             ticket.data_ptr(), out.data_ptr(), st))
+            else:
+                _lib.check(L.llampc_lookback_window_f32(bank.packed.data_ptr(), 5000, bank.Npad, hist.data_ptr(), W, V, W, Ts,
+                                                        None, keys.data_ptr(), lists.data_ptr(), 0, 1, 0, st))
+                _lib.check(L.llampc_topk_merge_lists(lists.data_ptr(), n_lists, V, K, keys.data_ptr(), out.data_ptr(), st))
+        assert (keys.cpu().numpy() == -1).all() and (ticket.cpu().numpy() == 0).all()
+        outs.append(out.cpu().numpy())
+    assert np.array_equal(outs[0], outs[1])
+    assert (outs[0][:, 0] == outs[0][:, 1]).all()                 # arg-min key == first of the top-K
