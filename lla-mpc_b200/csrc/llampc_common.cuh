@@ -89,44 +89,99 @@ __device__ __forceinline__ u64 warp_merge_low32(u64 a, u64 b_rev, int lane) {
     return m;
 }
 
-// K-way merge of n_lists ascending lists of LLAMPC_LIST_LEN keys into the K smallest keys overall (K <= LLAMPC_LIST_LEN):
-// K rounds of "block-min over the list heads"; each thread owns up to MERGE_LPT lists and keeps their head and
-// next key in registers so that the load of a popped list's successor is off the critical path.
-// out[0] = *best_key (then re-armed to ~0 for the next tick), out[1..K] = ascending top-K.  sbuf: THREADS/32+1 keys.
+// warp-wide minimum of a packed key with the hardware integer reduction (REDUX): high word first, then the low word
+// among the lanes that hold the winning high word -- two reductions instead of a five-step shuffle ladder.
+__device__ __forceinline__ u64 warp_min_key(u64 k) {
+    const unsigned hi = (unsigned)(k >> 32), lo = (unsigned)k;
+    const unsigned mh = __reduce_min_sync(0xffffffffu, hi);
+    const unsigned ml = __reduce_min_sync(0xffffffffu, hi == mh ? lo : 0xffffffffu);
+    return ((u64)mh << 32) | ml;
+}
+
+// Global top-K (K <= LLAMPC_LIST_LEN) of n_lists ascending lists of LLAMPC_LIST_LEN keys, without a memory load
+// inside any selection round.  Key fact: a key that is not the head of its list can only be in the global top-K if
+// the head of that list is too, so only the K lists with the smallest heads can contribute.
+//   A1  every warp selects the K smallest heads of the lists it owns (heads in registers, K REDUX rounds);
+//   A2  warp 0 merges the per-warp selections -> the K lists with the globally smallest heads;
+//   B   warp 0 loads those <= K lists (one coalesced wave of loads) and K-way merges them from shared memory.
+// out[0] = *best_key (then re-armed to ~0 for the next tick), out[1..K] = ascending top-K.
+// Capacity: THREADS * MERGE_LPT lists.  Shared memory: MergeSmem<THREADS>.
 constexpr int MERGE_LPT = 8;
 
 template <int THREADS>
+struct MergeSmem {
+    u64 wkey[THREADS / 32][LLAMPC_LIST_LEN];
+    int wid[THREADS / 32][LLAMPC_LIST_LEN];
+    int sel_list[LLAMPC_LIST_LEN];
+    u64 rows[LLAMPC_LIST_LEN][LLAMPC_LIST_LEN];
+};
+
+template <int THREADS>
 __device__ __forceinline__ void merge_lists_device(const u64* __restrict__ lists, int n_lists, int K,
-                                                   u64* __restrict__ best_key, u64* __restrict__ out, u64* sbuf) {
-    u64 head[MERGE_LPT], next[MERGE_LPT];
-    int pos[MERGE_LPT];
+                                                   u64* __restrict__ best_key, u64* __restrict__ out,
+                                                   MergeSmem<THREADS>& sm) {
+    constexpr int NW = THREADS / 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    u64 head[MERGE_LPT];
 #pragma unroll
     for (int j = 0; j < MERGE_LPT; ++j) {
         const int l = threadIdx.x + j * THREADS;
-        head[j] = ~0ull; next[j] = ~0ull; pos[j] = 1;
-        if (l < n_lists) {
-            head[j] = __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN);
-            next[j] = __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN + 1);
-        }
+        head[j] = l < n_lists ? __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN) : ~0ull;
     }
     if (threadIdx.x == 0 && best_key) {
         out[0] = __ldcg(best_key);
         *best_key = ~0ull;
     }
-    for (int r = 0; r < K; ++r) {
-        u64 mine = head[0];
+    // A1: per-warp K smallest heads
+    for (int r = 0; r < LLAMPC_LIST_LEN; ++r) {
+        u64 sel = ~0ull;
+        if (r < K) {
+            u64 mine = head[0];
 #pragma unroll
-        for (int j = 1; j < MERGE_LPT; ++j) mine = u64_min(mine, head[j]);
-        const u64 sel = block_min_u64_w0<THREADS / 32>(mine, sbuf);
-        if (threadIdx.x == 0) out[1 + r] = sel;
-        if (sel == ~0ull || mine != sel) continue;
+            for (int j = 1; j < MERGE_LPT; ++j) mine = u64_min(mine, head[j]);
+            sel = warp_min_key(mine);
+            if (sel != ~0ull && mine == sel) {
 #pragma unroll
-        for (int j = 0; j < MERGE_LPT; ++j) {
-            if (head[j] == sel) {                  // pop: successor becomes the head, prefetch the one after
-                head[j] = next[j];
-                pos[j] += 1;
-                const int l = threadIdx.x + j * THREADS;
-                next[j] = pos[j] < LLAMPC_LIST_LEN ? __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN + pos[j]) : ~0ull;
+                for (int j = 0; j < MERGE_LPT; ++j)
+                    if (head[j] == sel) { head[j] = ~0ull; sm.wid[warp][r] = threadIdx.x + j * THREADS; }
+            }
+        }
+        if (lane == 0) sm.wkey[warp][r] = sel;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    // A2: the K lists with the globally smallest heads
+    {
+        int p = 0;
+        u64 h = lane < NW ? sm.wkey[lane][0] : ~0ull;
+        for (int r = 0; r < LLAMPC_LIST_LEN; ++r) {
+            u64 sel = ~0ull;
+            if (r < K) sel = warp_min_key(h);
+            if (sel == ~0ull) {
+                if (lane == 0) sm.sel_list[r] = -1;
+            } else if (h == sel) {
+                sm.sel_list[r] = sm.wid[lane][p];
+                ++p;
+                h = p < LLAMPC_LIST_LEN ? sm.wkey[lane][p] : ~0ull;
+            }
+        }
+    }
+    __syncwarp();
+    // B: fetch the selected lists, then merge them from shared memory
+    for (int i = lane; i < LLAMPC_LIST_LEN * LLAMPC_LIST_LEN; i += 32) {
+        const int l = sm.sel_list[i / LLAMPC_LIST_LEN];
+        (&sm.rows[0][0])[i] = l >= 0 ? __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN + (i % LLAMPC_LIST_LEN)) : ~0ull;
+    }
+    __syncwarp();
+    {
+        int p = 0;
+        u64 h = lane < LLAMPC_LIST_LEN ? sm.rows[lane][0] : ~0ull;
+        for (int r = 0; r < K; ++r) {
+            const u64 sel = warp_min_key(h);
+            if (lane == 0) out[1 + r] = sel;
+            if (sel != ~0ull && h == sel) {
+                ++p;
+                h = p < LLAMPC_LIST_LEN ? sm.rows[lane][p] : ~0ull;
             }
         }
     }

@@ -130,6 +130,7 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
     cta_select_emit<CPB / 32>(key, skeys, v, best_key, cta_lists);
     if (fm.K > 0) {                                // uniform over the grid
         __shared__ bool is_last;
+        __shared__ MergeSmem<LB_THREADS> msm;
         __threadfence();
         __syncthreads();
         if (tid == 0) is_last = atomicAdd(fm.ticket + v, 1u) == gridDim.x - 1;
@@ -137,7 +138,7 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
         if (!is_last) return;
         __threadfence();
         merge_lists_device<LB_THREADS>(cta_lists + (size_t)v * gridDim.x * LLAMPC_LIST_LEN, gridDim.x, fm.K,
-                                       best_key ? best_key + v : nullptr, fm.out + (size_t)v * (LLAMPC_LIST_LEN + 1), skeys);
+                                       best_key ? best_key + v : nullptr, fm.out + (size_t)v * (LLAMPC_LIST_LEN + 1), msm);
         if (tid == 0) fm.ticket[v] = 0;            // ready for the next launch on the same stream
     }
 }
@@ -192,10 +193,10 @@ template <int MERGE_THREADS>
 __global__ void __launch_bounds__(MERGE_THREADS)
 topk_merge_lists_kernel(const u64* __restrict__ lists, int n_lists, int K, u64* __restrict__ best_key,
                         u64* __restrict__ out) {
-    __shared__ u64 sbuf[MERGE_THREADS / 32 + 1];
+    __shared__ MergeSmem<MERGE_THREADS> sm;
     const int v = blockIdx.x;                      // vehicle
     merge_lists_device<MERGE_THREADS>(lists + (size_t)v * n_lists * LLAMPC_LIST_LEN, n_lists, K,
-                                      best_key ? best_key + v : nullptr, out + (size_t)v * (LLAMPC_LIST_LEN + 1), sbuf);
+                                      best_key ? best_key + v : nullptr, out + (size_t)v * (LLAMPC_LIST_LEN + 1), sm);
 }
 
 __global__ void fill_keys_kernel(u64* keys, int n) {
