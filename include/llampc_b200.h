@@ -153,8 +153,11 @@ typedef struct llampc_tick {
     llampc_key_t* result_h;         /* pinned host, same layout; with sync != 0 the finalists come back
                                        ordered by score (fp64 if re-scored), ties by lower index           */
     int sync;                       /* non-zero: cudaStreamSynchronize + host ordering before returning    */
-    unsigned* ticket;               /* [1], zero-initialised: finish the top-K inside K1 (one launch per tick) when
+    unsigned* ticket;               /* [2], zero-initialised: finish the top-K inside K1 (one launch per tick) when
                                        the bank yields <= 1,024 per-CTA lists; NULL = always use the merge kernel */
+    int zero_copy;                  /* non-zero (with sync, n_refine > 0, ticket): the last re-score block writes the
+                                       result straight into result_h (mapped pinned memory, 2 + 2*Kt words) and the
+                                       host polls a sequence word instead of a D2H copy + stream synchronisation  */
     float* err_ring;                /* [W][Npad] per-tick error columns (rolling mode only)                */
     int rolling;                    /* 0: recompute the whole window from the history ring (K1);
                                        1: rolling mode (K1r): integrate only the newest row, replace ring column
@@ -164,6 +167,14 @@ typedef struct llampc_tick {
 } llampc_tick_t;
 
 int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stream);
+
+/* The whole body of run_nmpc_orca_llampc_rt.py:347-360 in one call from three fp64 host vectors: packs the
+ * transition (x_k, u_k) -> x_k1 into t->row32_h / t->row64_h (which must point to writable host scratch), runs
+ * llampc_lookback_tick with sync, and decodes the ordered finalists: idx_out / score_out [max(K, n_refine) or 1],
+ * *n_valid = number of valid entries (0 while a rolling window is still filling). */
+int llampc_lookback_push(llampc_tick_t* t, const double* x_k, const double* u_k, const double* x_k1,
+                         double lf_shared, double lr_shared, long long* idx_out, double* score_out, int* n_valid,
+                         llampc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * One RK4 step for N (model, state, input) triples: Model._integrate_batch (llampc/models/model.py:32-40)

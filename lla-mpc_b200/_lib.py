@@ -29,7 +29,7 @@ class Tick(C.Structure):
                 ("avg_err", _vp), ("best_key", _vp), ("K", _i), ("n_refine", _i),
                 ("cta_lists", _vp), ("topk_scratch", _vp), ("topk_counter", _vp),
                 ("bank64", _vp), ("hist64", _vp), ("row64_h", _vp),
-                ("result", _vp), ("result_h", _vp), ("sync", _i), ("ticket", _vp), ("err_ring", _vp), ("rolling", _i)]
+                ("result", _vp), ("result_h", _vp), ("sync", _i), ("ticket", _vp), ("zero_copy", _i), ("err_ring", _vp), ("rolling", _i)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/llampc_b200.h
@@ -48,6 +48,7 @@ PROTOTYPES = {
     "llampc_topk_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "llampc_refine_f64": (_i, [_vp, _i, _vp, _i, _d, _vp, _i, _i, _vp, _vp]),
     "llampc_lookback_tick": (_i, [C.POINTER(Tick), _vp]),
+    "llampc_lookback_push": (_i, [C.POINTER(Tick), _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp]),
     "llampc_rk4_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _d, _vp, _i, _vp]),
     "llampc_rhs_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "llampc_forces_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),

@@ -153,7 +153,7 @@ template <bool GEOM_SHARED>
 __global__ void __launch_bounds__(LB_THREADS)
 lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W, StepSize z, NewRow nr,
                         float* __restrict__ err_ring, float* __restrict__ avg_err, u64* __restrict__ best_key,
-                        u64* __restrict__ cta_lists, int idx_offset, int emit) {
+                        u64* __restrict__ cta_lists, int idx_offset, int emit, FusedMerge fm) {
     __shared__ u64 skeys[LB_THREADS];
     const int tid = threadIdx.x;
     const int cand = blockIdx.x * LB_THREADS + tid;
@@ -181,6 +181,18 @@ lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W,
         key = pack_key(err, (unsigned)(idx_offset + cand));
     }
     cta_select_emit<LB_THREADS / 32>(key, skeys, 0, best_key, cta_lists);
+    if (fm.K > 0) {                                // last CTA merges the lists (one launch per tick)
+        __shared__ bool is_last;
+        __shared__ MergeSmem<LB_THREADS> msm;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) is_last = atomicAdd(fm.ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        merge_lists_device<LB_THREADS>(cta_lists, gridDim.x, fm.K, best_key, fm.out, msm);
+        if (tid == 0) *fm.ticket = 0;
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -260,39 +272,61 @@ topk_kernel(const float* __restrict__ err, int N, int idx_offset, int K, int per
 // ---------------------------------------------------------------------------------------------------
 struct NewRow64 { double v[LLAMPC_HIST64_ROW]; int slot; };
 
+// Optional zero-copy hand-off of the tick result: the last re-score block to retire copies `words` result words to
+// mapped pinned host memory and then publishes `seq` in the word after them; the host polls that word instead of
+// paying for a D2H copy launch plus a stream synchronisation.
+struct FinalCopy { const u64* src; volatile u64* dst_host; unsigned* ticket; int words; u64 seq; };
+
 __global__ void __launch_bounds__(64)
 refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__ hist64, int W, double h,
-                  const u64* __restrict__ keys, int idx_offset, double* __restrict__ out, NewRow64 nr) {
+                  const u64* __restrict__ keys, int idx_offset, double* __restrict__ out, NewRow64 nr, FinalCopy fc) {
     __shared__ double spart[2];
+    __shared__ bool last_block;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     if (nr.slot >= 0 && f == 0 && tid < LLAMPC_HIST64_ROW) hist64[(size_t)nr.slot * LLAMPC_HIST64_ROW + tid] = nr.v[tid];
     const long long ci = (long long)(unsigned)(keys[f] & 0xffffffffull) - idx_offset;
-    if (ci < 0 || ci >= N) {                       // padded key (~0) or foreign shard
-        if (tid == 0) out[f] = __longlong_as_double(0x7ff8000000000000ll);
-        return;
+    double result = __longlong_as_double(0x7ff8000000000000ll);       // padded key (~0) or foreign shard -> NaN
+    if (ci >= 0 && ci < N) {                       // uniform over the block
+        Params64 p;
+        double* pp = reinterpret_cast<double*>(&p);
+#pragma unroll
+        for (int j = 0; j < LLAMPC_NPARAM; ++j) pp[j] = bank64[(size_t)j * N + ci];
+        double acc = 0.0;
+        for (int w = tid; w < W; w += 64) {
+            double r[LLAMPC_HIST64_ROW];
+#pragma unroll
+            for (int i = 0; i < LLAMPC_HIST64_ROW; ++i)
+                r[i] = (w == nr.slot) ? nr.v[i] : hist64[(size_t)w * LLAMPC_HIST64_ROW + i];
+            double y1[6];
+            rk4_step64(p, r, r[6], r[7], h, y1);
+            double e = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { double d = y1[i] - r[8 + i]; e += d * d; }
+            acc += e / 4;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) spart[tid >> 5] = acc;
+        __syncthreads();
+        result = (spart[0] + spart[1]) / W;
     }
-    Params64 p;
-    double* pp = reinterpret_cast<double*>(&p);
-#pragma unroll
-    for (int j = 0; j < LLAMPC_NPARAM; ++j) pp[j] = bank64[(size_t)j * N + ci];
-    double acc = 0.0;
-    for (int w = tid; w < W; w += 64) {
-        double r[LLAMPC_HIST64_ROW];
-#pragma unroll
-        for (int i = 0; i < LLAMPC_HIST64_ROW; ++i)
-            r[i] = (w == nr.slot) ? nr.v[i] : hist64[(size_t)w * LLAMPC_HIST64_ROW + i];
-        double y1[6];
-        rk4_step64(p, r, r[6], r[7], h, y1);
-        double e = 0.0;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) { double d = y1[i] - r[8 + i]; e += d * d; }
-        acc += e / 4;
+    if (tid == 0) out[f] = result;
+    if (fc.dst_host) {                             // uniform over the grid
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last_block = atomicAdd(fc.ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!last_block) return;
+        __threadfence();
+        for (int i = tid; i < fc.words; i += 64) fc.dst_host[i] = __ldcg(fc.src + i);
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            *fc.ticket = 0;
+            fc.dst_host[fc.words] = fc.seq;
+            __threadfence_system();
+        }
     }
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    if (lane == 0) spart[tid >> 5] = acc;
-    __syncthreads();
-    if (tid == 0) out[f] = (spart[0] + spart[1]) / W;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -452,10 +486,9 @@ extern "C" int llampc_lookback_window_topk_f32(const float* bank, int N, int Npa
                                 idx_offset, geom_shared, split, nr, fm, stream);
 }
 
-extern "C" int llampc_lookback_rolling_f32(const float* bank, int N, int Npad, const float* row32_h, int slot, int W,
-                                           double Ts, float* err_ring, float* avg_err, llampc_key_t* best_key,
-                                           llampc_key_t* cta_lists, int idx_offset, int geom_shared, int emit,
-                                           llampc_stream_t stream) {
+static int lookback_rolling_impl(const float* bank, int N, int Npad, const float* row32_h, int slot, int W, double Ts,
+                                 float* err_ring, float* avg_err, llampc_key_t* best_key, llampc_key_t* cta_lists,
+                                 int idx_offset, int geom_shared, int emit, const FusedMerge& fm, llampc_stream_t stream) {
     if (!bank || !row32_h || !err_ring || N <= 0 || Npad < N || slot < 0 || slot >= W) return LLAMPC_E_ARG;
     if (W <= 0 || W > LLAMPC_MAX_W) return LLAMPC_E_RANGE;
     if (!aligned16(bank)) return LLAMPC_E_ALIGN;
@@ -467,12 +500,21 @@ extern "C" int llampc_lookback_rolling_f32(const float* bank, int N, int Npad, c
     if (geom_shared)
         lookback_rolling_kernel<true><<<grid, LB_THREADS, 0, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, W,
                                                                    make_step(Ts), nr, err_ring, avg_err, best_key,
-                                                                   cta_lists, idx_offset, emit);
+                                                                   cta_lists, idx_offset, emit, fm);
     else
         lookback_rolling_kernel<false><<<grid, LB_THREADS, 0, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, W,
                                                                     make_step(Ts), nr, err_ring, avg_err, best_key,
-                                                                    cta_lists, idx_offset, emit);
+                                                                    cta_lists, idx_offset, emit, fm);
     return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_lookback_rolling_f32(const float* bank, int N, int Npad, const float* row32_h, int slot, int W,
+                                           double Ts, float* err_ring, float* avg_err, llampc_key_t* best_key,
+                                           llampc_key_t* cta_lists, int idx_offset, int geom_shared, int emit,
+                                           llampc_stream_t stream) {
+    FusedMerge none = {nullptr, nullptr, 0};
+    return lookback_rolling_impl(bank, N, Npad, row32_h, slot, W, Ts, err_ring, avg_err, best_key, cta_lists, idx_offset,
+                                 geom_shared, emit, none, stream);
 }
 
 extern "C" int llampc_lookback_num_lists(int N, int W, int split) {
@@ -534,8 +576,9 @@ extern "C" int llampc_refine_f64(const double* bank64, int N, const double* hist
     if (!bank64 || !hist64 || !keys || !out_err64 || N <= 0 || W <= 0 || n_fin <= 0) return LLAMPC_E_ARG;
     NewRow64 nr;
     nr.slot = -1;
+    FinalCopy fc = {nullptr, nullptr, nullptr, 0, 0};
     refine_f64_kernel<<<n_fin, 64, 0, static_cast<cudaStream_t>(stream)>>>(bank64, N, const_cast<double*>(hist64), W, Ts,
-                                                                           keys, idx_offset, out_err64, nr);
+                                                                           keys, idx_offset, out_err64, nr, fc);
     return (int)cudaGetLastError();
 }
 
@@ -587,9 +630,12 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
     if (t->rolling) {
         // the reference's rolling bookkeeping: one new error column + ring re-sum, then the list merge
         if (!t->err_ring || !t->row32_h || !fused) return LLAMPC_E_ARG;
-        rc = llampc_lookback_rolling_f32(t->bank, t->N, t->Npad, t->row32_h, t->slot, t->W, t->Ts, t->err_ring, t->avg_err,
-                                         t->best_key, t->cta_lists, t->idx_offset, t->geom_shared, t->rolling > 1 ? 0 : 1,
-                                         stream);
+        const int n_lists_r = (t->N + LB_THREADS - 1) / LB_THREADS;
+        const bool in_kernel_r = t->rolling == 1 && t->ticket != nullptr && Kt > 0 && n_lists_r <= LB_THREADS * MERGE_LPT;
+        FusedMerge fmr = {in_kernel_r ? t->ticket : nullptr, in_kernel_r ? keys : nullptr, in_kernel_r ? Kt : 0};
+        rc = lookback_rolling_impl(t->bank, t->N, t->Npad, t->row32_h, t->slot, t->W, t->Ts, t->err_ring, t->avg_err,
+                                   t->best_key, t->cta_lists, t->idx_offset, t->geom_shared, t->rolling > 1 ? 0 : 1, fmr,
+                                   stream);
         if (rc) return rc;
         if (t->rolling > 1) {                                        // window still filling: column stored, no decision
             if (t->n_refine > 0 && t->row64_h && t->hist64)
@@ -597,8 +643,10 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
                                                 LLAMPC_HIST64_ROW * sizeof(double), cudaMemcpyHostToDevice, st));
             return 0;
         }
-        rc = llampc_topk_merge_lists(t->cta_lists, (t->N + LB_THREADS - 1) / LB_THREADS, 1, Kt, t->best_key, keys, stream);
-        if (rc) return rc;
+        if (!in_kernel_r) {
+            rc = llampc_topk_merge_lists(t->cta_lists, n_lists_r, 1, Kt, t->best_key, keys, stream);
+            if (rc) return rc;
+        }
     } else if (fused) {
         // K1 (block arg-min + per-CTA sorted lists) -> list merge (also moves best_key to keys[0] and re-arms it)
         const int n_lists = llampc_lookback_num_lists(t->N, t->W, t->split);
@@ -635,13 +683,49 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
             for (int i = 0; i < LLAMPC_HIST64_ROW; ++i) nr64.v[i] = t->row64_h[i];
             nr64.slot = t->slot;
         }
-        refine_f64_kernel<<<Kt, 64, 0, st>>>(t->bank64, t->N, t->hist64, t->W, t->Ts, keys + 1, t->idx_offset, errs, nr64);
+        // zero-copy hand-off: needs the ticket word after the K1 ticket and a host buffer with one spare word
+        const int words = 1 + 2 * Kt;
+        bool polled = false;
+        FinalCopy fc = {nullptr, nullptr, nullptr, 0, 0};
+        if (t->sync && t->zero_copy && t->ticket) {
+            void* dptr = nullptr;
+            if (cudaHostGetDevicePointer(&dptr, t->result_h, 0) == cudaSuccess && dptr) {
+                static unsigned long long seq_counter = 1;
+                fc.src = t->result;
+                fc.dst_host = static_cast<volatile u64*>(dptr);
+                fc.ticket = t->ticket + 1;
+                fc.words = words;
+                fc.seq = ++seq_counter;
+                reinterpret_cast<volatile llampc_key_t*>(t->result_h)[words] = 0;
+                polled = true;
+            } else {
+                (void)cudaGetLastError();
+            }
+        }
+        refine_f64_kernel<<<Kt, 64, 0, st>>>(t->bank64, t->N, t->hist64, t->W, t->Ts, keys + 1, t->idx_offset, errs, nr64, fc);
         LLAMPC_CUDA_TRY(cudaGetLastError());
+        if (polled) {
+            volatile llampc_key_t* flag = reinterpret_cast<volatile llampc_key_t*>(t->result_h) + words;
+            long spins = 0;
+            while (*flag != fc.seq) {
+                if (++spins > 20000000L) {                           // ~ tens of ms: something is wrong, fall back
+                    LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
+                    if (*flag != fc.seq) return (int)cudaErrorUnknown;
+                    break;
+                }
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
+            __asm__ __volatile__("" ::: "memory");                     // the result words are read after the flag
+            goto have_result;
+        }
     }
     LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->result_h, t->result, (size_t)(1 + Kt + (refine ? Kt : 0)) * 8,
                                     cudaMemcpyDeviceToHost, st));
     if (!t->sync) return 0;
     LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
+have_result:
     // order the finalists on the host: by fp64 score (ties: lower index), NaN / padded entries last
     llampc_key_t* hk = t->result_h + 1;
     double* he = reinterpret_cast<double*>(t->result_h + 1 + Kt);
@@ -668,5 +752,45 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
         hk[j + 1] = k;
         he[j + 1] = e;
     }
+    return 0;
+}
+
+// One FFI crossing per MPC tick for a host that holds the transition as three fp64 vectors: packs the history
+// row(s) into the caller's scratch (t->row32_h / t->row64_h must point to writable host buffers), runs the tick
+// (sync forced) and decodes the ordered finalists into plain index / score arrays.
+extern "C" int llampc_lookback_push(llampc_tick_t* t, const double* x_k, const double* u_k, const double* x_k1,
+                                    double lf_shared, double lr_shared, long long* idx_out, double* score_out,
+                                    int* n_valid, llampc_stream_t stream) {
+    if (!t || !x_k || !u_k || !x_k1 || !idx_out || !score_out || !n_valid || !t->row32_h) return LLAMPC_E_ARG;
+    int rc = llampc_hist_row_pack_h(x_k, u_k, x_k1, t->Ts, lf_shared, lr_shared, const_cast<float*>(t->row32_h),
+                                    const_cast<double*>(t->row64_h));
+    if (rc) return rc;
+    const int sync_was = t->sync;
+    t->sync = 1;
+    rc = llampc_lookback_tick(t, stream);
+    t->sync = sync_was;
+    if (rc) return rc;
+    *n_valid = 0;
+    if (t->rolling > 1) return 0;                                    // window still filling
+    const int Kt = t->K > t->n_refine ? t->K : t->n_refine;
+    const llampc_key_t* hk = t->result_h + 1;
+    const double* he = reinterpret_cast<const double*>(t->result_h + 1 + Kt);
+    if (Kt == 0) {                                                   // arg-min only
+        const unsigned bits = (unsigned)(t->result_h[0] >> 32);
+        float f;
+        memcpy(&f, &bits, 4);
+        idx_out[0] = (long long)(t->result_h[0] & 0xffffffffull);
+        score_out[0] = (double)f;
+        *n_valid = 1;
+        return 0;
+    }
+    int n = 0;
+    for (int i = 0; i < Kt; ++i) {
+        if (hk[i] == ~0ull || he[i] != he[i]) break;                 // ordered: NaN / padding last
+        idx_out[n] = (long long)(hk[i] & 0xffffffffull);
+        score_out[n] = he[i];
+        ++n;
+    }
+    *n_valid = n;
     return 0;
 }

@@ -89,7 +89,7 @@ class LookBack:
             self.topk_scratch = torch.empty(max(1, ctas * max(self.Kt, 1)), dtype=torch.int64, device=dev)
             self.topk_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         # result: best key | Kt finalist keys | Kt fp64 scores  (the merge kernel writes LIST_LEN + 1 words)
-        words = max(1 + 2 * self.Kt, _lib.LIST_LEN + 1)
+        words = max(2 + 2 * self.Kt, _lib.LIST_LEN + 2)           # + 1 spare word: zero-copy sequence flag
         self.result = torch.zeros(words, dtype=torch.int64, device=dev)
         self.result_h = torch.zeros(words, dtype=torch.int64, pin_memory=True)
         self._res_keys = self.result_h.numpy().view(np.uint64)
@@ -114,14 +114,21 @@ class LookBack:
             t.bank64, t.hist64 = self.bank.bank64.data_ptr(), self.hist64.data_ptr()
         t.result, t.result_h = self.result.data_ptr(), self.result_h.data_ptr()
         t.sync = 1
-        self.ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+        self.ticket = torch.zeros(2, dtype=torch.int32, device=dev)
         t.ticket = self.ticket.data_ptr()
+        t.zero_copy = int(os.environ.get("LLAMPC_ZERO_COPY", "1") == "1")
         if self.rolling:
             t.err_ring, t.rolling = self.err_ring.data_ptr(), 1
         self._tick = t
         self._tick_ref = C.byref(t)
         self._L = L
         self._stream_dev = torch.cuda.device(dev)
+        self._dev_index = dev.index if dev.index is not None else torch.cuda.current_device()
+        self._idx_out = np.zeros(max(self.Kt, 1), dtype=np.int64)
+        self._score_out = np.zeros(max(self.Kt, 1), dtype=np.float64)
+        self._nvalid = C.c_int(0)
+        self._idx_out_p, self._score_out_p = self._idx_out.ctypes.data, self._score_out.ctypes.data
+        self._nvalid_p = C.addressof(self._nvalid)
 
     # ------------------------------------------------------------------ history ring
     def _pack_row(self, slot, x_k, u_k, x_k1):
@@ -153,26 +160,48 @@ class LookBack:
         """One MPC tick: (x_k, u_k) -> measured x_k1.  Returns (best_idx, topk_idx, best_err); all None
         while fewer than W transitions have been pushed (rt.py:357)."""
         slot = self._next_slot
-        r32, r64 = self._pack_row(slot, x_k, u_k, x_k1)
         self._next_slot = (slot + 1) % self.W
         self.window_count = min(self.window_count + 1, self.W)
         t = self._tick
-        if self.window_count < self.W:
-            torch = self.torch
-            self.hist[slot].copy_(torch.from_numpy(self.rows32_h[slot]))
-            if self.rolling:                                     # store the error column, no decision yet
-                t.row32_h, t.row64_h, t.slot, t.rolling = r32, (r64 if self.n_refine > 0 else None), slot, 2
-                with self._stream_dev:
-                    rc = self._L.llampc_lookback_tick(self._tick_ref, torch.cuda.current_stream().cuda_stream)
-                t.rolling = 1
-                if rc:
-                    _lib.check(rc, "llampc_lookback_tick")
-                torch.cuda.current_stream().synchronize()        # row64_h is reused by the next push
-            else:
-                self.hist64[slot].copy_(torch.from_numpy(self.rows64_h[slot]))
-            return None, None, None
-        t.row32_h, t.row64_h, t.slot = r32, (r64 if self.n_refine > 0 else None), slot
-        return self._run_tick()
+        filling = self.window_count < self.W
+        if filling or self.group is not None:
+            r32, r64 = self._pack_row(slot, x_k, u_k, x_k1)
+            if filling:
+                torch = self.torch
+                self.hist[slot].copy_(torch.from_numpy(self.rows32_h[slot]))
+                if self.rolling:                                 # store the error column, no decision yet
+                    t.row32_h, t.row64_h, t.slot, t.rolling = r32, (r64 if self.n_refine > 0 else None), slot, 2
+                    with self._stream_dev:
+                        rc = self._L.llampc_lookback_tick(self._tick_ref, torch.cuda.current_stream().cuda_stream)
+                    t.rolling = 1
+                    if rc:
+                        _lib.check(rc, "llampc_lookback_tick")
+                    torch.cuda.current_stream().synchronize()    # row64_h is reused by the next push
+                else:
+                    self.hist64[slot].copy_(torch.from_numpy(self.rows64_h[slot]))
+                return None, None, None
+            t.row32_h, t.row64_h, t.slot = r32, (r64 if self.n_refine > 0 else None), slot
+            return self._run_tick()
+        # single-GPU steady state: one FFI crossing (row packing, tick, decode all happen in C)
+        self._xk[:] = x_k
+        self._uk[:] = u_k
+        self._xk1[:4] = x_k1[:4]
+        t.row32_h = self._r32_base + slot * (_lib.HIST_ROW * 4)
+        t.row64_h = self._r64_base + slot * (_lib.HIST64_ROW * 8)     # scratch even without re-score
+        t.slot = slot
+        torch = self.torch
+        if torch.cuda.current_device() != self._dev_index:
+            torch.cuda.set_device(self._dev_index)
+        rc = self._L.llampc_lookback_push(self._tick_ref, self._xk_p, self._uk_p, self._xk1_p, self.bank.lf_shared,
+                                          self.bank.lr_shared, self._idx_out_p, self._score_out_p, self._nvalid_p,
+                                          torch.cuda.current_stream().cuda_stream)
+        if rc:
+            _lib.check(rc, "llampc_lookback_push")
+        n = self._nvalid.value
+        if n == 0:                                               # every score is NaN (np.argmin would return the first NaN)
+            return None, np.zeros(0, dtype=np.int64), float("nan")
+        idx = self._idx_out[:n]
+        return int(idx[0]), idx[:self.K].copy(), float(self._score_out[0])
 
     def evaluate(self):
         """Score the window currently in the ring (after load_window); same return as push."""

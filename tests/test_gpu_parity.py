@@ -562,3 +562,33 @@ def test_one_launch_tick_matches_two_launch(history):
         outs.append(out.cpu().numpy())
     assert np.array_equal(outs[0], outs[1])
     assert (outs[0][:, 0] == outs[0][:, 1]).all()                 # arg-min key == first of the top-K
+
+
+def test_large_window_and_zero_copy_paths(history, monkeypatch):
+    """W = 200 (the reference's largest ablation window, plot_banks.py:71) and W = 1,024 (the compiled limit: 80 KB of
+    history staged per CTA); the result hand-off with and without the zero-copy path must agree."""
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    bank = orc.make_bank(300, seed=30)
+    ref200 = np.mean(orc.window_errors(bank, S, U, 1200, 200, Ts), axis=1)
+    outs = []
+    for zc in ("1", "0"):
+        monkeypatch.setenv("LLAMPC_ZERO_COPY", zc)
+        lb = LookBack(bank, W=200, Ts=Ts, K=10, refine=16)
+        ts = np.arange(1200 - 200, 1200)
+        for t in ts:
+            lb.push(S[:, t], U[:, t], S[:, t + 1])
+        got = lb.push(S[:, 1200], U[:, 1200], S[:, 1201])
+        outs.append(got)
+        _assert_scores(lb.avg_errors(), ref200, "W=200")
+        order = np.argsort(ref200, kind="stable")
+        assert got[0] == order[0] and list(got[1]) == list(order[:10])
+        assert abs(got[2] - ref200[order[0]]) <= 1e-9 * ref200[order[0]]
+    assert outs[0][0] == outs[1][0] and list(outs[0][1]) == list(outs[1][1]) and outs[0][2] == outs[1][2]
+    lb = LookBack(bank, W=1024, Ts=Ts, K=5, refine=0)
+    best, topk, _ = _window(lb, S, U, 1500)
+    ref = np.mean(orc.window_errors(bank, S, U, 1500, 1024, Ts), axis=1)
+    _assert_scores(lb.avg_errors(), ref, "W=1024")
+    assert best == int(np.argmin(ref)) and list(topk) == list(np.argsort(ref, kind="stable")[:5])
+    with pytest.raises(ValueError):
+        LookBack(bank, W=1025, Ts=Ts)
