@@ -77,3 +77,20 @@ def shard_params(params, lo, hi):
         a = np.asarray(params[k], dtype=np.float64)
         out[k] = a[lo:hi] if a.ndim == 1 else a
     return out
+
+
+# variation of run_nmpc_orca_llampc_rt.py:153-158 (name, sigma) in the reference's dict order
+RT_VARIATION = (("Br", 0.2), ("Cr", 0.1), ("Dr", 0.5), ("Bf", 0.2), ("Cf", 0.1), ("Df", 0.5))
+
+
+def make_bank(nominal, n_models, variation=RT_VARIATION, rng=None):
+    """Model-bank construction of run_nmpc_orca_llampc_rt.py:145-179: every varied parameter of every model is the
+    nominal value times (1 + sigma * randn), drawn model by model in the order of `variation` (the reference's dict
+    order), so a seeded ``np.random.RandomState`` reproduces the reference's bank draw for draw.  Returns a parameter
+    dict for ``LookBack`` / ``ModelBank`` (varied entries are (n_models,) arrays, the rest scalars)."""
+    rng = np.random if rng is None else rng
+    z = rng.randn(n_models, len(variation))
+    bank = {k: nominal[k] for k in PARAM_NAMES}
+    for j, (name, sigma) in enumerate(variation):
+        bank[name] = nominal[name] * (1 + sigma * z[:, j])
+    return bank

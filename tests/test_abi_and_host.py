@@ -127,3 +127,15 @@ def test_raceline_table_coefficients_match_reference_splines():
         np.testing.assert_allclose(tab.coef[:, 8 + 1], g[name + "_v0_b"], rtol=1e-9, atol=1e-10)
         nmu = len(r["mus"])
         np.testing.assert_allclose(tab.coef[:, 8 + 4 * (nmu - 1) + 2], g[name + "_vlast_c"][:-1], rtol=1e-9, atol=1e-8)
+
+
+def test_make_bank_draw_order_matches_reference_golden():
+    """Product-side bank construction == the reference's loop (golden params of lookback_c1.npz, seed 0)."""
+    from conftest import load_golden
+    from llampc_b200.bank import make_bank
+    from llampc_b200.params import ORCA
+    g = load_golden("lookback_c1.npz")
+    bank = make_bank(ORCA(), 1024, rng=np.random.RandomState(0))
+    for row, k in enumerate(("Bf", "Cf", "Df", "Br", "Cr", "Dr")):
+        assert np.array_equal(bank[k], g["params"][row]), k
+    assert bank["mass"] == 0.041
