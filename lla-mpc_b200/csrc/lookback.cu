@@ -675,6 +675,7 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
         }
     }
     const bool refine = Kt > 0 && t->n_refine > 0;
+    bool have_result = false;                                        // set when the zero-copy hand-off delivered it
     if (refine) {
         if (!t->bank64 || !t->hist64) return LLAMPC_E_ARG;
         NewRow64 nr64;
@@ -685,7 +686,6 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
         }
         // zero-copy hand-off: needs the ticket word after the K1 ticket and a host buffer with one spare word
         const int words = 1 + 2 * Kt;
-        bool polled = false;
         FinalCopy fc = {nullptr, nullptr, nullptr, 0, 0};
         if (t->sync && t->zero_copy && t->ticket) {
             void* dptr = nullptr;
@@ -697,18 +697,17 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
                 fc.words = words;
                 fc.seq = ++seq_counter;
                 reinterpret_cast<volatile llampc_key_t*>(t->result_h)[words] = 0;
-                polled = true;
             } else {
-                (void)cudaGetLastError();
+                (void)cudaGetLastError();                            // result_h is not mapped: use the copy path
             }
         }
         refine_f64_kernel<<<Kt, 64, 0, st>>>(t->bank64, t->N, t->hist64, t->W, t->Ts, keys + 1, t->idx_offset, errs, nr64, fc);
         LLAMPC_CUDA_TRY(cudaGetLastError());
-        if (polled) {
+        if (fc.dst_host) {
             volatile llampc_key_t* flag = reinterpret_cast<volatile llampc_key_t*>(t->result_h) + words;
             long spins = 0;
             while (*flag != fc.seq) {
-                if (++spins > 20000000L) {                           // ~ tens of ms: something is wrong, fall back
+                if (++spins > 20000000L) {                           // tens of ms: something is wrong, stop spinning
                     LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
                     if (*flag != fc.seq) return (int)cudaErrorUnknown;
                     break;
@@ -718,14 +717,15 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
 #endif
             }
             __asm__ __volatile__("" ::: "memory");                     // the result words are read after the flag
-            goto have_result;
+            have_result = true;
         }
     }
-    LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->result_h, t->result, (size_t)(1 + Kt + (refine ? Kt : 0)) * 8,
-                                    cudaMemcpyDeviceToHost, st));
-    if (!t->sync) return 0;
-    LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
-have_result:
+    if (!have_result) {
+        LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->result_h, t->result, (size_t)(1 + Kt + (refine ? Kt : 0)) * 8,
+                                        cudaMemcpyDeviceToHost, st));
+        if (!t->sync) return 0;
+        LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
+    }
     // order the finalists on the host: by fp64 score (ties: lower index), NaN / padded entries last
     llampc_key_t* hk = t->result_h + 1;
     double* he = reinterpret_cast<double*>(t->result_h + 1 + Kt);

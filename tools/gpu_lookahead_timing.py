@@ -12,7 +12,7 @@ rng = np.random.RandomState(3)
 Useq = U[:, t0:t0 + H].T[None] + np.stack([0.1 * rng.randn(K, H), 0.05 * rng.randn(K, H)], axis=-1)
 Useq[..., 0] = np.clip(Useq[..., 0], -0.1, 1.0); Useq[..., 1] = np.clip(Useq[..., 1], -0.35, 0.35)
 xref = S[:2, t0:t0 + H + 1]
-bank = orc.make_bank(M, seed=2)
+bank = orc.make_bank(M, seed=2)  # raw bank (includes spinning candidates); bench.py uses adapted models
 la = LookAhead(bank, Ts=Ts)
 plan = la.plan(S[:, t0], Useq, xref, U[:, t0 - 1])
 for _ in range(3): plan.run()
