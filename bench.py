@@ -221,12 +221,13 @@ def cpu_baseline_leg():
     """Reference algorithm on the host cores (bounded sample), run BEFORE CUDA is initialised (fork safety)."""
     cores = os.cpu_count() or 1
     Sc, Uc = cpu_history()
-    n_all = int(min(N_C2, max(16384, 2048 * cores)))
-    r1, _ = cpu_reference_rate(8192, W_C2, 1, Sc, Uc)
-    rall, _ = cpu_reference_rate(n_all, W_C2, cores, Sc, Uc, repeats=3)
+    n_all = N_C2 if cores >= 8 else int(max(16384, 2048 * cores))      # ~10-30 s of CPU work in total
+    r1, _ = cpu_reference_rate(16384, W_C2, 1, Sc, Uc, repeats=2)
+    rall, _ = cpu_reference_rate(n_all, W_C2, cores, Sc, Uc, repeats=8)
     return {"value": rall, "unit": "steps/s", "cores": cores, "kind": "port",
-            "sample": "%d of the 65,536 C2 candidates x 50-step window, float64 NumPy port of evaluate_models_vectorized "
-                      "+ scoring, sharded over %d processes" % (n_all, cores),
+            "sample": "%d of the 65,536 C2 candidates x 50-step window (best of 8 passes), float64 NumPy port of "
+                      "evaluate_models_vectorized + scoring, sharded over %d processes; 1-core figure: 16,384 candidates"
+                      % (n_all, cores),
             "value_1core_as_reference_runs_it": r1}
 
 
