@@ -210,7 +210,8 @@ def workload_config(gpus):
     if gpus == 1:
         return {"workload": "C2: look-back, 65,536 candidates (6 Pacejka + mass varied) x 50-step window, arg-min + top-10 per tick",
                 "candidates": N_C2, "window": W_C2, "Ts": TS, "l2": "flushed between timed ticks (256 MiB write)"}
-    return {"workload": "C5: look-back sweep, 1,048,576 candidates x 50-step window sharded over %d GPUs, one NCCL min-loc all-reduce per tick" % gpus,
+    return {"workload": "C5: look-back sweep, 1,048,576 candidates x 50-step window sharded over %d GPUs, one min-loc exchange per tick "
+                        "(fused into the kernels over NVLink peer memory; LLAMPC_BENCH_NCCL=1 = NCCL MIN all-reduce)" % gpus,
             "candidates": N_C5, "window": W_C2, "Ts": TS, "l2": "flushed between timed ticks (256 MiB write)"}
 
 
@@ -278,10 +279,24 @@ def run_b200(args):
 
     ticket = torch.zeros(1, dtype=torch.int32, device=dev)
     one_launch = n_lists <= 1024
+    # N > 1: the min-loc across GPUs is fused into the same kernels over NVLink peer memory (symmetric buffers);
+    # LLAMPC_BENCH_NCCL=1 times the NCCL MIN all-reduce variant instead
+    peer = None
+    if world > 1 and os.environ.get("LLAMPC_BENCH_NCCL", "0") != "1":
+        from llampc_b200.dist import PeerExchange
+        peer = PeerExchange(device=dev)
 
     def tick_device():
         """One look-back tick with device-resident inputs: K1 (scores, block arg-min, per-CTA sorted lists) with the
         top-10 merge finished by the last CTA inside the same launch (+ the min-loc all-reduce for N > 1)."""
+        if peer is not None:
+            rc = L.llampc_lookback_window_topk_peer_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2,
+                                                        W_C2, TS, lb.avg_err.data_ptr(), lb.best_key.data_ptr(),
+                                                        lb.cta_lists.data_ptr(), lo, int(bank.geom_shared), lb.split, 10,
+                                                        ticket.data_ptr(), lb.result.data_ptr(), peer.peer_ptrs.data_ptr(),
+                                                        world, rank, peer.next_seq(), st)
+            _lib.check(rc, "K1+K4'+NVLink min-loc")
+            return
         rc = L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2,
                                                TS, lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), lo,
                                                int(bank.geom_shared), lb.split, 10, ticket.data_ptr(), lb.result.data_ptr(), st)
@@ -410,6 +425,8 @@ def run_b200(args):
             "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
             "dtype": "f32", "data": "synthetic", "config": dict(workload_config(world), tyre_sine="MUFU.SIN (default; strict polynomial mode reported under other_configs)"),
             "gpu_launches": args.steps * (1 if one_launch else 2), "clocks": clocks, "roofline": roofline}
+    if world > 1:
+        line["exchange"] = "nvlink-peer-memory min-loc inside the kernel" if peer is not None else "nccl all_reduce(MIN) of the packed key"
     if e2e:
         line["e2e"] = e2e
         line["tick_latency"] = lat

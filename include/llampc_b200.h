@@ -93,6 +93,20 @@ int llampc_lookback_window_topk_f32(const float* bank, int N, int Npad, const fl
                                     int geom_shared, int split, int K, unsigned* ticket, llampc_key_t* out,
                                     llampc_stream_t stream);
 
+/* K1 + top-K + multi-GPU min-loc in ONE launch per rank, over NVLink peer memory (no NCCL on the path).
+ *   peer_bufs  device array [world] of pointers: peer_bufs[q] = rank q's symmetric exchange buffer of
+ *              4 * world u64 words ([2 parities][world][key, sequence]), zero-initialised, mapped into this process
+ *              (CUDA IPC / torch symmetric memory); peer_bufs[rank] is this rank's own buffer
+ *   seq        tick counter, identical on every rank, incremented by the caller every call (>= 1)
+ * After the launch out[0] holds the GLOBAL arg-min key on every rank (0 if a peer did not arrive within ~1 s);
+ * out[1..K] stay the rank-local top-K.  Needs <= 1,024 per-CTA lists (N <= 131,072 x split). */
+int llampc_lookback_window_topk_peer_f32(const float* bank, int N, int Npad, const float* hist, int W,
+                                         int hist_stride_rows, double Ts, float* avg_err,
+                                         llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
+                                         int geom_shared, int split, int K, unsigned* ticket,
+                                         llampc_key_t* out, llampc_key_t* const* peer_bufs, int world,
+                                         int rank, unsigned seq, llampc_stream_t stream);
+
 /* K1r  rolling window, the reference's own bookkeeping (error_windows = np.roll(...); [:, -1] = errors; mean,
  * run_nmpc_orca_llampc_rt.py:349-358): one RK4 step per candidate for the newest transition (row32_h, HOST pointer,
  * passed as kernel parameter), error column `slot` of err_ring [W][Npad] replaced, window mean re-summed from the

@@ -41,6 +41,8 @@ PROTOTYPES = {
     "llampc_lookback_window_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "llampc_lookback_num_lists": (_i, [_i, _i, _i]),
     "llampc_lookback_window_topk_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
+    "llampc_lookback_window_topk_peer_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp,
+                                                  _vp, _i, _i, C.c_uint, _vp]),
     "llampc_lookback_rolling_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "llampc_topk_merge_lists": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "llampc_fill_keys": (_i, [_vp, _i, _vp]),

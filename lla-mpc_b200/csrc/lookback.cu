@@ -59,11 +59,39 @@ struct NewRow { float v[LLAMPC_HIST_ROW]; int slot; };
 // lists itself, so a tick is ONE launch.  Needs gridDim.x <= 128 * MERGE_LPT lists; K = 0 disables it.
 struct FusedMerge { unsigned* ticket; u64* out; int K; };
 
+// Optional multi-GPU min-loc fused into the same launch, over NVLink peer memory (no NCCL call on the path): every
+// rank owns a small symmetric buffer [2 parities][world][2] of u64 (key, sequence); the last CTA of rank r stores its
+// packed arg-min key into slot r of EVERY peer's buffer (remote 8-byte stores), then spins on its own buffer until all
+// `world` slots carry the current sequence number and reduces them.  Double-buffered by the parity of `seq`, which the
+// host increments identically on every rank each tick.  world = 0 disables it.
+struct PeerXchg { u64* const* peers; int world; int rank; unsigned seq; };
+
+__device__ __forceinline__ u64 peer_minloc(const PeerXchg& px, u64 my_key, int lane) {
+    const int parity = px.seq & 1;
+    u64 got = ~0ull;
+    if (lane < px.world) {
+        volatile u64* dst = px.peers[lane] + ((size_t)parity * px.world + px.rank) * 2;
+        dst[0] = my_key;
+        __threadfence_system();
+        dst[1] = (u64)px.seq;
+        volatile u64* src = px.peers[px.rank] + ((size_t)parity * px.world + lane) * 2;
+        const long long t0 = clock64();
+        bool ok = true;
+        while (src[1] != (u64)px.seq) {
+            if (clock64() - t0 > 2000000000ll) { ok = false; break; }     // ~1 s: a peer never arrived; poison the result
+            __nanosleep(64);
+        }
+        __threadfence_system();
+        got = ok ? src[0] : 0ull;
+    }
+    return warp_min_key(got);
+}
+
 template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
 __global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB_MIN_BLOCKS)
 lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
                        long hist_stride_floats, StepSize z, float* __restrict__ avg_err, u64* __restrict__ best_key,
-                       u64* __restrict__ cta_lists, int idx_offset, NewRow nr, FusedMerge fm) {
+                       u64* __restrict__ cta_lists, int idx_offset, NewRow nr, FusedMerge fm, PeerXchg px) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ u64 skeys[LB_THREADS];
@@ -137,9 +165,16 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
         __syncthreads();
         if (!is_last) return;
         __threadfence();
+        u64* outv = fm.out + (size_t)v * (LLAMPC_LIST_LEN + 1);
         merge_lists_device<LB_THREADS>(cta_lists + (size_t)v * gridDim.x * LLAMPC_LIST_LEN, gridDim.x, fm.K,
-                                       best_key ? best_key + v : nullptr, fm.out + (size_t)v * (LLAMPC_LIST_LEN + 1), msm);
+                                       best_key ? best_key + v : nullptr, outv, msm);
         if (tid == 0) fm.ticket[v] = 0;            // ready for the next launch on the same stream
+        if (px.world > 1 && tid < 32) {            // warp 0: min-loc across the GPUs of the box, in this launch
+            __syncwarp();
+            const u64 mine = __shfl_sync(0xffffffffu, tid == 0 ? *reinterpret_cast<volatile u64*>(outv) : 0ull, 0);
+            const u64 g = peer_minloc(px, mine, tid);
+            if (tid == 0) outv[0] = g;
+        }
     }
 }
 
@@ -204,11 +239,18 @@ lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W,
 template <int MERGE_THREADS>
 __global__ void __launch_bounds__(MERGE_THREADS)
 topk_merge_lists_kernel(const u64* __restrict__ lists, int n_lists, int K, u64* __restrict__ best_key,
-                        u64* __restrict__ out) {
+                        u64* __restrict__ out, PeerXchg px) {
     __shared__ MergeSmem<MERGE_THREADS> sm;
     const int v = blockIdx.x;                      // vehicle
+    u64* outv = out + (size_t)v * (LLAMPC_LIST_LEN + 1);
     merge_lists_device<MERGE_THREADS>(lists + (size_t)v * n_lists * LLAMPC_LIST_LEN, n_lists, K,
-                                      best_key ? best_key + v : nullptr, out + (size_t)v * (LLAMPC_LIST_LEN + 1), sm);
+                                      best_key ? best_key + v : nullptr, outv, sm);
+    if (px.world > 1 && threadIdx.x < 32) {        // warp 0: min-loc across the GPUs of the box (single vehicle)
+        __syncwarp();
+        const u64 mine = __shfl_sync(0xffffffffu, threadIdx.x == 0 ? *reinterpret_cast<volatile u64*>(outv) : 0ull, 0);
+        const u64 g = peer_minloc(px, mine, threadIdx.x);
+        if (threadIdx.x == 0) outv[0] = g;
+    }
 }
 
 __global__ void fill_keys_kernel(u64* keys, int n) {
@@ -407,7 +449,7 @@ static StepSize make_step(double Ts) {
 template <int SY, bool GEOM, bool MUFU>
 static int launch_lookback(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
                            int hist_stride_rows, double Ts, float* avg_err, u64* best_key, u64* cta_lists,
-                           int idx_offset, const NewRow& nr, const FusedMerge& fm, cudaStream_t st) {
+                           int idx_offset, const NewRow& nr, const FusedMerge& fm, const PeerXchg& px, cudaStream_t st) {
     auto kern = lookback_window_kernel<SY, GEOM, MUFU>;
     const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 : 0);
     if (smem > 48 * 1024) {
@@ -421,14 +463,15 @@ static int launch_lookback(const float* bank, int N, int Npad, const float* hist
     dim3 grid((N + CPB - 1) / CPB, n_vehicles);
     kern<<<grid, LB_THREADS, smem, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, hist, W,
                                          (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key, cta_lists,
-                                         idx_offset, nr, fm);
+                                         idx_offset, nr, fm, px);
     return (int)cudaGetLastError();
 }
 
 static int lookback_window_impl(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
                                 int hist_stride_rows, double Ts, float* avg_err, llampc_key_t* best_key,
                                 llampc_key_t* cta_lists, int idx_offset, int geom_shared, int split,
-                                const NewRow& nr, const FusedMerge& fm, llampc_stream_t stream) {
+                                const NewRow& nr, const FusedMerge& fm, llampc_stream_t stream,
+                                const PeerXchg& px = PeerXchg{nullptr, 0, 0, 0}) {
     if (!bank || !hist || (!best_key && !cta_lists && !avg_err) || N <= 0 || Npad < N || n_vehicles <= 0 || hist_stride_rows < W) return LLAMPC_E_ARG;
     if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
     if (!aligned16(bank) || !aligned16(hist) || (hist_stride_rows * LLAMPC_HIST_ROW * 4) % 16) return LLAMPC_E_ALIGN;
@@ -439,10 +482,10 @@ static int lookback_window_impl(const float* bank, int N, int Npad, const float*
     if (split > W) split = 1;
 #define LB_CASE(SYV)                                                                                                  \
     case SYV:                                                                                                         \
-        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, st)   \
-                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, st); \
-        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, st)            \
-                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, st);
+        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, st)   \
+                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, st); \
+        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, st)            \
+                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, st);
     switch (split) {
         LB_CASE(1)
         LB_CASE(2)
@@ -508,6 +551,34 @@ static int lookback_rolling_impl(const float* bank, int N, int Npad, const float
     return (int)cudaGetLastError();
 }
 
+static int merge_lists_impl(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K, llampc_key_t* best_key,
+                            llampc_key_t* out, const PeerXchg& px, llampc_stream_t stream);
+
+extern "C" int llampc_lookback_window_topk_peer_f32(const float* bank, int N, int Npad, const float* hist, int W,
+                                                    int hist_stride_rows, double Ts, float* avg_err,
+                                                    llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
+                                                    int geom_shared, int split, int K, unsigned* ticket,
+                                                    llampc_key_t* out, llampc_key_t* const* peer_bufs, int world,
+                                                    int rank, unsigned seq, llampc_stream_t stream) {
+    if (!cta_lists || !out || !ticket || !best_key || !peer_bufs) return LLAMPC_E_ARG;
+    if (K <= 0 || K > LLAMPC_LIST_LEN || world < 2 || world > 32 || rank < 0 || rank >= world) return LLAMPC_E_RANGE;
+    const int n_lists = llampc_lookback_num_lists(N, W, split);
+    if (n_lists <= 0) return LLAMPC_E_ARG;
+    NewRow nr;
+    nr.slot = -1;
+    PeerXchg px = {peer_bufs, world, rank, seq};
+    if (n_lists > LB_THREADS * MERGE_LPT) {          // big shard: K1, then the merge kernel carries the exchange
+        FusedMerge none = {nullptr, nullptr, 0};
+        int rc = lookback_window_impl(bank, N, Npad, hist, W, 1, hist_stride_rows, Ts, avg_err, best_key, cta_lists,
+                                      idx_offset, geom_shared, split, nr, none, stream);
+        if (rc) return rc;
+        return merge_lists_impl(cta_lists, n_lists, 1, K, best_key, out, px, stream);
+    }
+    FusedMerge fm = {ticket, out, K};
+    return lookback_window_impl(bank, N, Npad, hist, W, 1, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset,
+                                geom_shared, split, nr, fm, stream, px);
+}
+
 extern "C" int llampc_lookback_rolling_f32(const float* bank, int N, int Npad, const float* row32_h, int slot, int W,
                                            double Ts, float* err_ring, float* avg_err, llampc_key_t* best_key,
                                            llampc_key_t* cta_lists, int idx_offset, int geom_shared, int emit,
@@ -527,18 +598,23 @@ extern "C" int llampc_lookback_num_lists(int N, int W, int split) {
     return (N + cpb - 1) / cpb;
 }
 
-extern "C" int llampc_topk_merge_lists(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K,
-                                       llampc_key_t* best_key, llampc_key_t* out, llampc_stream_t stream) {
+static int merge_lists_impl(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K, llampc_key_t* best_key,
+                            llampc_key_t* out, const PeerXchg& px, llampc_stream_t stream) {
     if (!cta_lists || !out || n_lists <= 0 || n_vehicles <= 0) return LLAMPC_E_ARG;
     if (K < 0 || K > LLAMPC_LIST_LEN || n_lists > 1024 * MERGE_LPT) return LLAMPC_E_RANGE;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (n_lists <= 128 * MERGE_LPT)
-        topk_merge_lists_kernel<128><<<n_vehicles, 128, 0, st>>>(cta_lists, n_lists, K, best_key, out);
+        topk_merge_lists_kernel<128><<<n_vehicles, 128, 0, st>>>(cta_lists, n_lists, K, best_key, out, px);
     else if (n_lists <= 256 * MERGE_LPT)
-        topk_merge_lists_kernel<256><<<n_vehicles, 256, 0, st>>>(cta_lists, n_lists, K, best_key, out);
+        topk_merge_lists_kernel<256><<<n_vehicles, 256, 0, st>>>(cta_lists, n_lists, K, best_key, out, px);
     else
-        topk_merge_lists_kernel<1024><<<n_vehicles, 1024, 0, st>>>(cta_lists, n_lists, K, best_key, out);
+        topk_merge_lists_kernel<1024><<<n_vehicles, 1024, 0, st>>>(cta_lists, n_lists, K, best_key, out, px);
     return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_topk_merge_lists(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K,
+                                       llampc_key_t* best_key, llampc_key_t* out, llampc_stream_t stream) {
+    return merge_lists_impl(cta_lists, n_lists, n_vehicles, K, best_key, out, PeerXchg{nullptr, 0, 0, 0}, stream);
 }
 
 extern "C" int llampc_fill_keys(llampc_key_t* keys, int n, llampc_stream_t stream) {

@@ -49,3 +49,29 @@ def shard_range(n, rank, world):
     per = (n + world - 1) // world
     lo = min(rank * per, n)
     return lo, min(lo + per, n)
+
+
+class PeerExchange:
+    """Symmetric NVLink exchange buffers for the in-kernel min-loc (llampc_lookback_window_topk_peer_f32): one small
+    buffer per rank, mapped into every process of the group with torch symmetric memory (CUDA IPC underneath).
+    `peer_ptrs` is the device array of the `world` buffer addresses; `next_seq()` is the per-tick sequence number
+    (every rank must call it the same number of times)."""
+
+    def __init__(self, group=None, device=None):
+        import torch
+        import torch.distributed as td
+        import torch.distributed._symmetric_memory as symm_mem
+        self.group = td.group.WORLD if group is None else group
+        self.world, self.rank = td.get_world_size(self.group), td.get_rank(self.group)
+        dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.buf = symm_mem.empty(4 * self.world, dtype=torch.int64, device=dev)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group=self.group)
+        self.peer_ptrs = torch.tensor(list(self.handle.buffer_ptrs), dtype=torch.int64, device=dev)
+        torch.cuda.synchronize()
+        td.barrier(self.group)
+        self.seq = 0
+
+    def next_seq(self):
+        self.seq += 1
+        return self.seq
