@@ -319,10 +319,12 @@ struct NewRow64 { double v[LLAMPC_HIST64_ROW]; int slot; };
 // paying for a D2H copy launch plus a stream synchronisation.
 struct FinalCopy { const u64* src; volatile u64* dst_host; unsigned* ticket; int words; u64 seq; };
 
-__global__ void __launch_bounds__(64)
+constexpr int RF_THREADS = 128;                   // 64 window rows at a time x 2 lanes (front / rear tyre) per row
+
+__global__ void __launch_bounds__(RF_THREADS)
 refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__ hist64, int W, double h,
                   const u64* __restrict__ keys, int idx_offset, double* __restrict__ out, NewRow64 nr, FinalCopy fc) {
-    __shared__ double spart[2];
+    __shared__ double spart[RF_THREADS / 32];
     __shared__ bool last_block;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     if (nr.slot >= 0 && f == 0 && tid < LLAMPC_HIST64_ROW) hist64[(size_t)nr.slot * LLAMPC_HIST64_ROW + tid] = nr.v[tid];
@@ -334,23 +336,26 @@ refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__
 #pragma unroll
         for (int j = 0; j < LLAMPC_NPARAM; ++j) pp[j] = bank64[(size_t)j * N + ci];
         double acc = 0.0;
-        for (int w = tid; w < W; w += 64) {
+        const bool rear = tid & 1;                 // lane pair (2k, 2k+1) shares window row w
+        for (int w0 = 0; w0 < W; w0 += RF_THREADS / 2) {      // uniform trip count: the pair shuffles need full warps
+            const int w = w0 + (tid >> 1);
+            const int wc = w < W ? w : W - 1;
             double r[LLAMPC_HIST64_ROW];
 #pragma unroll
             for (int i = 0; i < LLAMPC_HIST64_ROW; ++i)
-                r[i] = (w == nr.slot) ? nr.v[i] : hist64[(size_t)w * LLAMPC_HIST64_ROW + i];
+                r[i] = (wc == nr.slot) ? nr.v[i] : hist64[(size_t)wc * LLAMPC_HIST64_ROW + i];
             double y1[6];
-            rk4_step64(p, r, r[6], r[7], h, y1);
+            rk4_step64_pair(p, r, r[6], r[7], h, rear, y1);
             double e = 0.0;
 #pragma unroll
             for (int i = 0; i < 4; ++i) { double d = y1[i] - r[8 + i]; e += d * d; }
-            acc += e / 4;
+            if (w < W && !rear) acc += e / 4;
         }
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
         if (lane == 0) spart[tid >> 5] = acc;
         __syncthreads();
-        result = (spart[0] + spart[1]) / W;
+        result = ((spart[0] + spart[1]) + (spart[2] + spart[3])) / W;
     }
     if (tid == 0) out[f] = result;
     if (fc.dst_host) {                             // uniform over the grid
@@ -360,7 +365,7 @@ refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__
         __syncthreads();
         if (!last_block) return;
         __threadfence();
-        for (int i = tid; i < fc.words; i += 64) fc.dst_host[i] = __ldcg(fc.src + i);
+        for (int i = tid; i < fc.words; i += RF_THREADS) fc.dst_host[i] = __ldcg(fc.src + i);
         __threadfence_system();
         __syncthreads();
         if (tid == 0) {
@@ -653,7 +658,7 @@ extern "C" int llampc_refine_f64(const double* bank64, int N, const double* hist
     NewRow64 nr;
     nr.slot = -1;
     FinalCopy fc = {nullptr, nullptr, nullptr, 0, 0};
-    refine_f64_kernel<<<n_fin, 64, 0, static_cast<cudaStream_t>(stream)>>>(bank64, N, const_cast<double*>(hist64), W, Ts,
+    refine_f64_kernel<<<n_fin, RF_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(bank64, N, const_cast<double*>(hist64), W, Ts,
                                                                            keys, idx_offset, out_err64, nr, fc);
     return (int)cudaGetLastError();
 }
@@ -777,7 +782,7 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
                 (void)cudaGetLastError();                            // result_h is not mapped: use the copy path
             }
         }
-        refine_f64_kernel<<<Kt, 64, 0, st>>>(t->bank64, t->N, t->hist64, t->W, t->Ts, keys + 1, t->idx_offset, errs, nr64, fc);
+        refine_f64_kernel<<<Kt, RF_THREADS, 0, st>>>(t->bank64, t->N, t->hist64, t->W, t->Ts, keys + 1, t->idx_offset, errs, nr64, fc);
         LLAMPC_CUDA_TRY(cudaGetLastError());
         if (fc.dst_host) {
             volatile llampc_key_t* flag = reinterpret_cast<volatile llampc_key_t*>(t->result_h) + words;

@@ -698,3 +698,19 @@ def test_c4_full_size_properties():
     part = mc2.host()
     for k in ("x", "projidx", "curr_mu", "model_idx", "u_applied"):
         assert np.array_equal(part[k], full[k][sel]), k
+
+
+def test_peer_minloc_two_gpus():
+    """In-kernel NVLink min-loc vs NCCL on 2 GPUs (skipped on single-GPU boxes)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29571", os.path.join(root, "tools", "gpu_peer_minloc.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count(": OK") == 2
