@@ -172,6 +172,12 @@ typedef struct llampc_tick {
     int zero_copy;                  /* non-zero (with sync, n_refine > 0, ticket): the last re-score block writes the
                                        result straight into result_h (mapped pinned memory, 2 + 2*Kt words) and the
                                        host polls a sequence word instead of a D2H copy + stream synchronisation  */
+    llampc_key_t* const* peer_bufs; /* multi-GPU finalist all-gather over NVLink peer memory (needs n_refine > 0, sync,
+                                       zero_copy): device array [peer_world] of every rank's symmetric buffer of
+                                       2 * peer_world * (2*Kt + 1) zeroed words; result_h then needs 2 + 2*Kt*peer_world
+                                       words.  The ordered finalists returned are the GLOBAL ones.  NULL = single GPU */
+    int peer_world; int peer_rank;
+    unsigned peer_seq;              /* tick counter >= 1, identical on all ranks, incremented by the caller  */
     float* err_ring;                /* [W][Npad] per-tick error columns (rolling mode only)                */
     int rolling;                    /* 0: recompute the whole window from the history ring (K1);
                                        1: rolling mode (K1r): integrate only the newest row, replace ring column

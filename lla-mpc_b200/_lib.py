@@ -29,7 +29,9 @@ class Tick(C.Structure):
                 ("avg_err", _vp), ("best_key", _vp), ("K", _i), ("n_refine", _i),
                 ("cta_lists", _vp), ("topk_scratch", _vp), ("topk_counter", _vp),
                 ("bank64", _vp), ("hist64", _vp), ("row64_h", _vp),
-                ("result", _vp), ("result_h", _vp), ("sync", _i), ("ticket", _vp), ("zero_copy", _i), ("err_ring", _vp), ("rolling", _i)]
+                ("result", _vp), ("result_h", _vp), ("sync", _i), ("ticket", _vp), ("zero_copy", _i),
+                ("peer_bufs", _vp), ("peer_world", _i), ("peer_rank", _i), ("peer_seq", C.c_uint),
+                ("err_ring", _vp), ("rolling", _i)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/llampc_b200.h

@@ -319,11 +319,18 @@ struct NewRow64 { double v[LLAMPC_HIST64_ROW]; int slot; };
 // paying for a D2H copy launch plus a stream synchronisation.
 struct FinalCopy { const u64* src; volatile u64* dst_host; unsigned* ticket; int words; u64 seq; };
 
+// Optional multi-GPU finalist all-gather over NVLink peer memory, carried by the last re-score block: every rank
+// owns a symmetric buffer [2 parities][world][wpr] (wpr = 2 Kt + 1: Kt keys, Kt fp64 scores, sequence word); the block
+// stores its finalists into slot `rank` of every peer, waits until its own buffer holds all `world` contributions of
+// this tick, and hands the whole set (world * 2 Kt words after the local arg-min key) to the host.
+struct PeerGather { u64* const* peers; int world; int rank; unsigned seq; int kt; };
+
 constexpr int RF_THREADS = 128;                   // 64 window rows at a time x 2 lanes (front / rear tyre) per row
 
 __global__ void __launch_bounds__(RF_THREADS)
 refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__ hist64, int W, double h,
-                  const u64* __restrict__ keys, int idx_offset, double* __restrict__ out, NewRow64 nr, FinalCopy fc) {
+                  const u64* __restrict__ keys, int idx_offset, double* __restrict__ out, NewRow64 nr, FinalCopy fc,
+                  PeerGather pg) {
     __shared__ double spart[RF_THREADS / 32];
     __shared__ bool last_block;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
@@ -365,12 +372,43 @@ refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__
         __syncthreads();
         if (!last_block) return;
         __threadfence();
-        for (int i = tid; i < fc.words; i += RF_THREADS) fc.dst_host[i] = __ldcg(fc.src + i);
+        int words = fc.words;
+        if (pg.world > 1) {
+            // fc.src = [arg-min key | Kt keys | Kt scores]; exchange the 2 Kt finalist words with every peer
+            const int wpr = 2 * pg.kt + 1, parity = pg.seq & 1;
+            const size_t my_slot = ((size_t)parity * pg.world + pg.rank) * wpr;
+            for (int i = tid; i < 2 * pg.kt * pg.world; i += RF_THREADS) {
+                const int q = i / (2 * pg.kt), j = i % (2 * pg.kt);
+                reinterpret_cast<volatile u64*>(pg.peers[q])[my_slot + j] = __ldcg(fc.src + 1 + j);
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid < pg.world) {
+                reinterpret_cast<volatile u64*>(pg.peers[tid])[my_slot + 2 * pg.kt] = (u64)pg.seq;
+                volatile u64* own = pg.peers[pg.rank] + ((size_t)parity * pg.world + tid) * wpr;
+                const long long t0 = clock64();
+                while (own[2 * pg.kt] != (u64)pg.seq) {
+                    if (clock64() - t0 > 2000000000ll) break;         // ~1 s: give up, the host sees a stale slot
+                    __nanosleep(64);
+                }
+            }
+            __threadfence_system();
+            __syncthreads();
+            fc.dst_host[0] = __ldcg(fc.src);
+            volatile u64* own = pg.peers[pg.rank] + (size_t)parity * pg.world * wpr;
+            for (int i = tid; i < 2 * pg.kt * pg.world; i += RF_THREADS) {
+                const int q = i / (2 * pg.kt), j = i % (2 * pg.kt);
+                fc.dst_host[1 + i] = own[(size_t)q * wpr + j];
+            }
+            words = 1 + 2 * pg.kt * pg.world;
+        } else {
+            for (int i = tid; i < words; i += RF_THREADS) fc.dst_host[i] = __ldcg(fc.src + i);
+        }
         __threadfence_system();
         __syncthreads();
         if (tid == 0) {
             *fc.ticket = 0;
-            fc.dst_host[fc.words] = fc.seq;
+            fc.dst_host[words] = fc.seq;
             __threadfence_system();
         }
     }
@@ -658,8 +696,9 @@ extern "C" int llampc_refine_f64(const double* bank64, int N, const double* hist
     NewRow64 nr;
     nr.slot = -1;
     FinalCopy fc = {nullptr, nullptr, nullptr, 0, 0};
+    PeerGather pg = {nullptr, 0, 0, 0, 0};
     refine_f64_kernel<<<n_fin, RF_THREADS, 0, static_cast<cudaStream_t>(stream)>>>(bank64, N, const_cast<double*>(hist64), W, Ts,
-                                                                           keys, idx_offset, out_err64, nr, fc);
+                                                                           keys, idx_offset, out_err64, nr, fc, pg);
     return (int)cudaGetLastError();
 }
 
@@ -766,8 +805,14 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
             nr64.slot = t->slot;
         }
         // zero-copy hand-off: needs the ticket word after the K1 ticket and a host buffer with one spare word
-        const int words = 1 + 2 * Kt;
+        const bool gather = t->peer_world > 1 && t->peer_bufs != nullptr;
+        const int words = gather ? 1 + 2 * Kt * t->peer_world : 1 + 2 * Kt;
         FinalCopy fc = {nullptr, nullptr, nullptr, 0, 0};
+        PeerGather pg = {nullptr, 0, 0, 0, 0};
+        if (gather) {
+            if (!(t->sync && t->zero_copy && t->ticket)) return LLAMPC_E_ARG;   // the gather rides on the zero-copy hand-off
+            pg.peers = t->peer_bufs; pg.world = t->peer_world; pg.rank = t->peer_rank; pg.seq = t->peer_seq; pg.kt = Kt;
+        }
         if (t->sync && t->zero_copy && t->ticket) {
             void* dptr = nullptr;
             if (cudaHostGetDevicePointer(&dptr, t->result_h, 0) == cudaSuccess && dptr) {
@@ -775,14 +820,16 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
                 fc.src = t->result;
                 fc.dst_host = static_cast<volatile u64*>(dptr);
                 fc.ticket = t->ticket + 1;
-                fc.words = words;
+                fc.words = 1 + 2 * Kt;
                 fc.seq = ++seq_counter;
                 reinterpret_cast<volatile llampc_key_t*>(t->result_h)[words] = 0;
             } else {
                 (void)cudaGetLastError();                            // result_h is not mapped: use the copy path
+                if (gather) return LLAMPC_E_ARG;
             }
         }
-        refine_f64_kernel<<<Kt, RF_THREADS, 0, st>>>(t->bank64, t->N, t->hist64, t->W, t->Ts, keys + 1, t->idx_offset, errs, nr64, fc);
+        refine_f64_kernel<<<Kt, RF_THREADS, 0, st>>>(t->bank64, t->N, t->hist64, t->W, t->Ts, keys + 1, t->idx_offset, errs, nr64, fc,
+                                                     pg);
         LLAMPC_CUDA_TRY(cudaGetLastError());
         if (fc.dst_host) {
             volatile llampc_key_t* flag = reinterpret_cast<volatile llampc_key_t*>(t->result_h) + words;
@@ -799,6 +846,36 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
             }
             __asm__ __volatile__("" ::: "memory");                     // the result words are read after the flag
             have_result = true;
+            if (gather) {
+                // host: pick the Kt best of the world * Kt finalists (fp64 score, ties by index; NaN / padding last)
+                // and compact them into the single-GPU layout [arg-min | Kt keys | Kt scores]
+                const int total = Kt * t->peer_world;
+                llampc_key_t* raw = t->result_h + 1;
+                llampc_key_t ak[LLAMPC_MAX_K * 32];
+                double ae[LLAMPC_MAX_K * 32];
+                if (total > LLAMPC_MAX_K * 32) return LLAMPC_E_RANGE;
+                for (int q = 0; q < t->peer_world; ++q)
+                    for (int j = 0; j < Kt; ++j) {
+                        ak[q * Kt + j] = raw[(size_t)q * 2 * Kt + j];
+                        memcpy(&ae[q * Kt + j], &raw[(size_t)q * 2 * Kt + Kt + j], 8);
+                    }
+                llampc_key_t* hk2 = t->result_h + 1;
+                double* he2 = reinterpret_cast<double*>(t->result_h + 1 + Kt);
+                for (int i = 0; i < Kt; ++i) {                       // partial selection sort
+                    int best = -1;
+                    for (int j = i; j < total; ++j) {
+                        if (ak[j] == ~0ull || ae[j] != ae[j]) continue;
+                        if (best < 0 || ae[j] < ae[best] ||
+                            (ae[j] == ae[best] && (unsigned)(ak[j] & 0xffffffffull) < (unsigned)(ak[best] & 0xffffffffull)))
+                            best = j;
+                    }
+                    if (best < 0) { for (int r = i; r < Kt; ++r) { hk2[r] = ~0ull; he2[r] = NAN; } break; }
+                    const llampc_key_t tk = ak[best]; const double te = ae[best];
+                    ak[best] = ak[i]; ae[best] = ae[i];
+                    ak[i] = tk; ae[i] = te;
+                    hk2[i] = tk; he2[i] = te;
+                }
+            }
         }
     }
     if (!have_result) {

@@ -57,14 +57,15 @@ class PeerExchange:
     `peer_ptrs` is the device array of the `world` buffer addresses; `next_seq()` is the per-tick sequence number
     (every rank must call it the same number of times)."""
 
-    def __init__(self, group=None, device=None):
+    def __init__(self, group=None, device=None, words=None):
         import torch
         import torch.distributed as td
         import torch.distributed._symmetric_memory as symm_mem
         self.group = td.group.WORLD if group is None else group
         self.world, self.rank = td.get_world_size(self.group), td.get_rank(self.group)
         dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
-        self.buf = symm_mem.empty(4 * self.world, dtype=torch.int64, device=dev)
+        # default size: the min-loc layout [2 parities][world][key, sequence]
+        self.buf = symm_mem.empty(4 * self.world if words is None else int(words), dtype=torch.int64, device=dev)
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, group=self.group)
         self.peer_ptrs = torch.tensor(list(self.handle.buffer_ptrs), dtype=torch.int64, device=dev)

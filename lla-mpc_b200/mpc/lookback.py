@@ -90,6 +90,16 @@ class LookBack:
             self.topk_counter = torch.zeros(1, dtype=torch.int32, device=dev)
         # result: best key | Kt finalist keys | Kt fp64 scores  (the merge kernel writes LIST_LEN + 1 words)
         words = max(2 + 2 * self.Kt, _lib.LIST_LEN + 2)           # + 1 spare word: zero-copy sequence flag
+        self._peer = None
+        if group is not None and self.n_refine > 0 and os.environ.get("LLAMPC_PEER_GATHER", "1") == "1":
+            import torch.distributed as td
+            if td.get_backend(group) == "nccl":
+                try:                                             # NVLink peer-memory finalist gather (no NCCL per tick)
+                    w = td.get_world_size(group)
+                    self._peer = _dist.PeerExchange(group, dev, words=2 * w * (2 * self.Kt + 1))
+                    words = max(words, 2 + 2 * self.Kt * w)
+                except Exception:                                # symmetric memory unavailable: NCCL all-gather path
+                    self._peer = None
         self.result = torch.zeros(words, dtype=torch.int64, device=dev)
         self.result_h = torch.zeros(words, dtype=torch.int64, pin_memory=True)
         self._res_keys = self.result_h.numpy().view(np.uint64)
@@ -117,6 +127,9 @@ class LookBack:
         self.ticket = torch.zeros(2, dtype=torch.int32, device=dev)
         t.ticket = self.ticket.data_ptr()
         t.zero_copy = int(os.environ.get("LLAMPC_ZERO_COPY", "1") == "1")
+        if self._peer is not None:
+            t.zero_copy = 1
+            t.peer_bufs, t.peer_world, t.peer_rank = self._peer.peer_ptrs.data_ptr(), self._peer.world, self._peer.rank
         if self.rolling:
             t.err_ring, t.rolling = self.err_ring.data_ptr(), 1
         self._tick = t
@@ -164,7 +177,7 @@ class LookBack:
         self.window_count = min(self.window_count + 1, self.W)
         t = self._tick
         filling = self.window_count < self.W
-        if filling or self.group is not None:
+        if filling or (self.group is not None and self._peer is None):
             r32, r64 = self._pack_row(slot, x_k, u_k, x_k1)
             if filling:
                 torch = self.torch
@@ -189,6 +202,8 @@ class LookBack:
         t.row32_h = self._r32_base + slot * (_lib.HIST_ROW * 4)
         t.row64_h = self._r64_base + slot * (_lib.HIST64_ROW * 8)     # scratch even without re-score
         t.slot = slot
+        if self._peer is not None:
+            t.peer_seq = self._peer.next_seq()                   # same count on every rank: one per decided tick
         torch = self.torch
         if torch.cuda.current_device() != self._dev_index:
             torch.cuda.set_device(self._dev_index)
@@ -216,8 +231,10 @@ class LookBack:
     def _run_tick(self):
         torch = self.torch
         Kt = self.Kt
-        dist = self.group is not None
+        dist = self.group is not None and self._peer is None     # NCCL exchange after the tick
         self._tick.sync = 0 if dist else 1
+        if self._peer is not None:                               # NVLink exchange inside the tick's last kernel
+            self._tick.peer_seq = self._peer.next_seq()
         with self._stream_dev:
             rc = self._L.llampc_lookback_tick(self._tick_ref, torch.cuda.current_stream().cuda_stream)
         if rc:
