@@ -188,6 +188,11 @@ typedef struct llampc_tick {
 
 int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stream);
 
+/* Layout probes for bindings that mirror llampc_tick_t by hand: sizeof, and offsetof of
+ * Ts (0), cta_lists (1), result_h (2), peer_seq (3), rolling (4). */
+int llampc_tick_sizeof(void);
+int llampc_tick_offsetof(int which);
+
 /* The whole body of run_nmpc_orca_llampc_rt.py:347-360 in one call from three fp64 host vectors: packs the
  * transition (x_k, u_k) -> x_k1 into t->row32_h / t->row64_h (which must point to writable host scratch), runs
  * llampc_lookback_tick with sync, and decodes the ordered finalists: idx_out / score_out [max(K, n_refine) or 1],

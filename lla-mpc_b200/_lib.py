@@ -52,6 +52,8 @@ PROTOTYPES = {
     "llampc_topk_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "llampc_refine_f64": (_i, [_vp, _i, _vp, _i, _d, _vp, _i, _i, _vp, _vp]),
     "llampc_lookback_tick": (_i, [C.POINTER(Tick), _vp]),
+    "llampc_tick_sizeof": (_i, []),
+    "llampc_tick_offsetof": (_i, [_i]),
     "llampc_lookback_push": (_i, [C.POINTER(Tick), _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp]),
     "llampc_rk4_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _d, _vp, _i, _vp]),
     "llampc_rhs_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
@@ -86,6 +88,8 @@ def lib():
             fn.restype, fn.argtypes = res, args
         if handle.llampc_abi_version() != 1:
             raise LlampcError("libllampc_b200.so ABI version mismatch")
+        if handle.llampc_tick_sizeof() != C.sizeof(Tick):
+            raise LlampcError("llampc_tick_t layout mismatch between _lib.py and libllampc_b200.so (rebuild the library)")
         _lib = handle
     return _lib
 

@@ -6,6 +6,7 @@
 #include "llampc_model.cuh"
 #include "llampc_model_f64.cuh"
 #include <math.h>
+#include <stddef.h>
 #include <string.h>
 
 namespace llampc {
@@ -951,4 +952,17 @@ extern "C" int llampc_lookback_push(llampc_tick_t* t, const double* x_k, const d
     }
     *n_valid = n;
     return 0;
+}
+
+// layout probes for FFI bindings that mirror llampc_tick_t by hand
+extern "C" int llampc_tick_sizeof(void) { return (int)sizeof(llampc_tick_t); }
+extern "C" int llampc_tick_offsetof(int which) {
+    switch (which) {
+        case 0: return (int)offsetof(llampc_tick_t, Ts);
+        case 1: return (int)offsetof(llampc_tick_t, cta_lists);
+        case 2: return (int)offsetof(llampc_tick_t, result_h);
+        case 3: return (int)offsetof(llampc_tick_t, peer_seq);
+        case 4: return (int)offsetof(llampc_tick_t, rolling);
+        default: return -1;
+    }
 }

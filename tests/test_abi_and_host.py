@@ -139,3 +139,22 @@ def test_make_bank_draw_order_matches_reference_golden():
     for row, k in enumerate(("Bf", "Cf", "Df", "Br", "Cr", "Dr")):
         assert np.array_equal(bank[k], g["params"][row]), k
     assert bank["mass"] == 0.041
+
+
+def test_ctypes_prototypes_match_header_arity():
+    """Every prototype in _lib.PROTOTYPES has as many arguments as the declaration in include/llampc_b200.h."""
+    text = open(os.path.join(ROOT, "include", "llampc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    decls = dict(re.findall(r"\b(llampc_[a-z0-9_]+)\s*\(([^;{}]*?)\)\s*;", text, flags=re.S))
+    assert set(decls) == set(_lib.PROTOTYPES)
+    for name, params in decls.items():
+        params = params.strip()
+        n = 0 if params in ("", "void") else params.count(",") + 1
+        assert n == len(_lib.PROTOTYPES[name][1]), (name, n, len(_lib.PROTOTYPES[name][1]))
+
+
+def test_tick_struct_layout_matches_c():
+    lib = _lib.lib()
+    assert lib.llampc_tick_sizeof() == C.sizeof(_lib.Tick)
+    for which, field in enumerate(("Ts", "cta_lists", "result_h", "peer_seq", "rolling")):
+        assert lib.llampc_tick_offsetof(which) == getattr(_lib.Tick, field).offset, field
