@@ -714,3 +714,31 @@ def test_peer_minloc_two_gpus():
     res = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
     assert res.stdout.count(": OK") == 2
+
+
+def test_replay_reference_loop_settings(history):
+    """The reference script's own settings (N_MODELS 5000, W 10, top-10 mu estimate) replayed over 400 recorded ticks:
+    identical model-selection sequence and friction-estimate sequence as the NumPy loop."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    import replay_lookback as rp
+    from llampc_b200.mpc import LookBack, MuEstimator
+    S, U, Ts = history
+    bank = orc.make_bank(rp.N_MODELS, seed=0)
+    S2, U2 = S[:, 900:], U[:, 900:]
+
+    class OracleLB:
+        def __init__(self, b, W, ts, K):
+            self.o = orc.LookBackOracle(b, W, ts, K)
+
+        def push(self, a, b, c):
+            best, topk, avg = self.o.push(a, b, c)
+            return best, topk, None
+
+    gi, gm = rp.replay(S2, U2, Ts, bank, 400, lambda b, W, ts, K: LookBack(b, W=W, Ts=ts, K=K),
+                       lambda m: MuEstimator(mass=m, smoothing_mu=rp.smoothing_mu, alpha=rp.mu_alpha))
+    ri, rm = rp.replay(S2, U2, Ts, bank, 400, OracleLB,
+                       lambda m: orc.MuEstimatorOracle(mass=m, smoothing_mu=rp.smoothing_mu, alpha=rp.mu_alpha))
+    assert np.array_equal(gi, ri)
+    np.testing.assert_allclose(gm, rm, rtol=1e-13)
+    assert len(np.unique(gi)) > 3                                   # the friction decay makes the loop switch models
