@@ -97,16 +97,29 @@ __device__ __forceinline__ float sin_any(float t) {
     return __uint_as_float(__float_as_uint(v) ^ (kbits << 31));
 }
 
-// atan(z) for ANY z, branch-free: q = z for |z| <= 1, q = sign(z)/|z| otherwise (one MUFU.RCP),
-// atan z = sign(z) pi/2 - atan(q) in the second case.  +-inf -> +-pi/2, NaN -> NaN.
+// atan(q) for |q| <= 1 with 8 coefficients (7.7e-8): used with the SFU tyre sine, whose own error (2^-21.4) is larger.
+__device__ __forceinline__ float atan_unit7(float q) {
+    float s = q * q;
+    float p = 4.0598551869e-03f;
+    p = fmaf(p, s, -2.0706461466e-02f);
+    p = fmaf(p, s, 4.9855267454e-02f);
+    p = fmaf(p, s, -8.0743718081e-02f);
+    p = fmaf(p, s, 1.0888638420e-01f);
+    p = fmaf(p, s, -1.4260910336e-01f);
+    p = fmaf(p, s, 1.9998927280e-01f);
+    p = fmaf(p, s, -3.3333325682e-01f);
+    return fmaf(q * s, p, q);
+}
+
+// atan(z) for ANY z, branch-free: q = z / max(z^2, 1) is z for |z| <= 1 and 1/z otherwise (one MUFU.RCP, the sign
+// rides along), atan z = sign(z) pi/2 - atan(q) in the second case.  +-inf -> +-pi/2, NaN -> NaN.
+template <bool SHORT_POLY>
 __device__ __forceinline__ float atan_full(float z) {
-    const float az = fabsf(z);
-    const float r = rcp_approx(fmaxf(az, 1.0f));
-    const bool big = az > 1.0f;
-    const float q = big ? copysignf(r, z) : z;
-    const float a = atan_unit(q);
+    const float zz = z * z;
+    const float q = z * rcp_approx(fmaxf(zz, 1.0f));
+    const float a = SHORT_POLY ? atan_unit7(q) : atan_unit(q);
     const float c = copysignf(LLAMPC_PIO2_HI, z);
-    return big ? (c - a) : a;
+    return (zz > 1.0f) ? (c - a) : a;                        // a NaN z gives q = NaN, hence a = NaN
 }
 
 // np.arctan2(y, avx) for avx >= 0, ANY magnitudes, branch-free: q = min/max in [0, 1] (one MUFU.RCP),

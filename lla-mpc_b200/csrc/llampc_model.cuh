@@ -109,7 +109,7 @@ __device__ __forceinline__ float drive_force_fast(const Cand& p, const Drive& d,
 
 template <bool MUFU_SIN>
 __device__ __forceinline__ float pacejka_fast(float B, float C, float D, float alpha) {
-    const float t = C * atan_full(B * alpha);
+    const float t = C * atan_full<MUFU_SIN>(B * alpha);
     return D * (MUFU_SIN ? sin_mufu(t) : sin_tyre(t));
 }
 
