@@ -87,7 +87,7 @@ lookahead_kernel(const float4* __restrict__ bank, int Mpad, const int* __restric
             sincos_half(u.y, ctl.sd, ctl.cd);
             float inc[6];
             float guard = 2.0f * fabsf(u.y);
-            rk4_increment_fast<false>(p, ctl, s, c, vx, vy, w, h, inc, guard);
+            rk4_increment_fast<true>(p, ctl, s, c, vx, vy, w, h, inc, guard);   // SFU tyre sine: far below the cost tolerance
             guard = fmaxf(guard, 2.0f * fabsf(inc[2]));
             if (force_general) guard = 2.0f;
             if (!(guard <= 1.0f) || !(inc[3] + inc[5] == inc[3] + inc[5])) {   // rare: spinning, huge steering / yaw rate, NaN
