@@ -284,7 +284,15 @@ def run_b200(args):
     peer = None
     if world > 1 and os.environ.get("LLAMPC_BENCH_NCCL", "0") != "1":
         from llampc_b200.dist import PeerExchange
-        peer = PeerExchange(device=dev)
+        try:
+            peer = PeerExchange(device=dev)
+        except Exception as e:                                  # symmetric memory unavailable: NCCL min-loc instead
+            peer = None
+            sys.stderr.write("peer exchange unavailable (%r), using NCCL\n" % (e,))
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        td.all_reduce(ok, op=td.ReduceOp.MIN)                   # every rank must take the same path
+        if int(ok.item()) == 0:
+            peer = None
 
     def tick_device():
         """One look-back tick with device-resident inputs: K1 (scores, block arg-min, per-CTA sorted lists) with the
@@ -364,6 +372,19 @@ def run_b200(args):
                         "peak_GBs": peaks.get("hbm_gbs", 6650.0), "peak_kind": "measured" if peaks else "fallback"}}
     if clocks.get("sm_mhz"):
         roofline["frac_at_observed_clock"] = achieved / (148 * 128 * 2 * clocks["sm_mhz"] * 1e6 / 1e12)
+    # SM clock sustained under an FMA-bound load (clock64 against globaltimer, ~300 us of work on every SM)
+    try:
+        probe = torch.zeros(2, dtype=torch.int64, device=dev)
+        sink = torch.zeros(1, dtype=torch.float32, device=dev)
+        for _ in range(3):
+            _lib.check(L.llampc_clock_probe(40000, probe.data_ptr(), sink.data_ptr(), st), "clock_probe")
+        torch.cuda.synchronize()
+        cyc, ns = (int(v) for v in probe.cpu().numpy())
+        mhz = cyc / ns * 1e3
+        roofline["sm_clock_under_fma_load_mhz"] = mhz
+        roofline["frac_at_measured_clock"] = achieved / (148 * 128 * 2 * mhz * 1e6 / 1e12)
+    except Exception as e:
+        roofline["sm_clock_under_fma_load_mhz"] = repr(e)
 
     # ---- end to end through the public API (rank-local bank; host inputs every tick)
     e2e = None

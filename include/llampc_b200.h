@@ -293,6 +293,11 @@ int llampc_sample_controls_f32(const float* nominal, const float* eps, int V, in
 int llampc_apply_best_f32(const float* U, const int* best_k, int V, int K, int H, float* nominal, float* uprev,
                           double* u_applied, llampc_stream_t stream);
 
+/* Measurement helper: runs an FMA-bound loop of `iters` iterations on every SM and stores, for one thread,
+ * out2[0] = elapsed SM cycles (clock64) and out2[1] = elapsed nanoseconds (globaltimer): the SM clock actually
+ * sustained under load, used for the roofline denominator "at the measured clock".  sink: one device float. */
+int llampc_clock_probe(int iters, unsigned long long* out2, float* sink, llampc_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

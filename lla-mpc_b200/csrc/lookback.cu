@@ -104,12 +104,12 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
     const int v = blockIdx.y;
     const unsigned bytes = (unsigned)W * (LLAMPC_HIST_ROW * 4);
 
-    if (tid == 0) mbar_init(&mbar, 1);
-    __syncthreads();
-    if (tid == 0) {
+    if (tid == 0) {                                // one thread arms the barrier and starts the bulk copy right away
+        mbar_init(&mbar, 1);
         mbar_expect_tx(&mbar, bytes);
         tma_bulk_g2s(srow, hist + (size_t)v * hist_stride_floats, bytes, &mbar);
     }
+    __syncthreads();                               // the initialised barrier is visible to the waiting threads
 
     const int c = tid % CPB, sy = tid / CPB;
     const int cand = blockIdx.x * CPB + c;

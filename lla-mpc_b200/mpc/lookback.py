@@ -100,6 +100,11 @@ class LookBack:
                     words = max(words, 2 + 2 * self.Kt * w)
                 except Exception:                                # symmetric memory unavailable: NCCL all-gather path
                     self._peer = None
+                agree = torch.tensor([1 if self._peer is not None else 0], device=dev)
+                td.all_reduce(agree, op=td.ReduceOp.MIN, group=group)      # every rank must take the same path
+                if int(agree.item()) == 0:
+                    self._peer = None
+                    words = max(2 + 2 * self.Kt, _lib.LIST_LEN + 2)
         self.result = torch.zeros(words, dtype=torch.int64, device=dev)
         self.result_h = torch.zeros(words, dtype=torch.int64, pin_memory=True)
         self._res_keys = self.result_h.numpy().view(np.uint64)
