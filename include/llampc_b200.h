@@ -235,12 +235,14 @@ int llampc_forces_batch_f32(const float* bank, int N, int Npad, const double* x6
  *              16-byte aligned and readable up to the next multiple of 16 bytes
  *   qrp_h      HOST pointer, 6 floats = Q00 Q11 R00 R11 P00 P11
  *   J          [M][K] floats;  best_k [M] ints (first index on ties);  x_final [M][K][6] doubles or NULL
+ *   x_traj     [M][K][H+1][6] doubles or NULL: every state of every rollout (meant for small K, e.g. the best
+ *              sequence per model as a warm start of the NLP: xvars = [x(:,0..H); u(:,0..H-1)], llampc/mpc/nmpc.py:113-117)
  * ------------------------------------------------------------------------------------------- */
 int llampc_lookahead_rollout_f32(const float* bank, int Mpad, const int* model_idx, int M,
                                  const double* x0, int n_x0, const float* U, int K, int H,
                                  const float* xref, const float* uprev, int per_model_flags,
                                  const float* qrp_h, double Ts, float* J, int* best_k, double* x_final,
-                                 llampc_stream_t stream);
+                                 double* x_traj, llampc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Planner: ConstantSpeed (llampc/mpc/planner.py:12-67) for V vehicles, fp64.  Tables (device, doubles) come from

@@ -59,7 +59,7 @@ PROTOTYPES = {
     "llampc_rhs_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "llampc_forces_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "llampc_lookahead_rollout_f32": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _d,
-                                          _vp, _vp, _vp, _vp]),
+                                          _vp, _vp, _vp, _vp, _vp]),
     "llampc_planner_constant_speed_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _i, _d, _d,
                                                _vp, _vp, _vp, _vp, _vp]),
     "llampc_pack_rows_f64": (_i, [_vp, _vp, _vp, _i, _d, _d, _d, _i, _i, _vp, _vp, _vp]),

@@ -24,7 +24,8 @@ lookahead_kernel(const float4* __restrict__ bank, int Mpad, const int* __restric
                  const double* __restrict__ x0, int n_x0, const float* __restrict__ U, int K, int H,
                  const float* __restrict__ xref, const float* __restrict__ uprev, int per_model,
                  float q0, float q1, float r0, float r1, float p0, float p1, float h,
-                 float* __restrict__ J, int* __restrict__ best_k, double* __restrict__ x_final) {
+                 float* __restrict__ J, int* __restrict__ best_k, double* __restrict__ x_final,
+                 double* __restrict__ x_traj) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     const bool u_pm = per_model & 1, xref_pm = per_model & 2, uprev_pm = per_model & 4, force_general = per_model & 8;
@@ -77,6 +78,11 @@ lookahead_kernel(const float4* __restrict__ bank, int Mpad, const int* __restric
         float vx = (float)xs[3], vy = (float)xs[4], w = (float)xs[5];
         float2 uq = up;
         float Jt = 0.0f, Ja = 0.0f, ex = 0.0f, ey = 0.0f;
+        double* tr = (x_traj && k_ok) ? x_traj + ((size_t)m * K + k) * (size_t)(H + 1) * 6 : nullptr;
+        if (tr) {
+#pragma unroll
+            for (int i = 0; i < 6; ++i) tr[i] = xs[i];
+        }
         for (int hh = 0; hh < H; ++hh) {
             const float2 u = u_pm ? __ldg(Ug + (size_t)kk * H + hh) : sU[kk * H + hh];
             const float du0 = u.x - uq.x, du1 = u.y - uq.y;       // nmpc.py:66-69 (du_0 = u_0 - uprev)
@@ -103,6 +109,11 @@ lookahead_kernel(const float4* __restrict__ bank, int Mpad, const int* __restric
             else sincos_small(inc[2], sr, cr);
             const float sn = fmaf(s, cr, c * sr), cn = fmaf(c, cr, -s * sr);
             s = sn; c = cn;
+            if (tr) {                                             // state after step hh (trajectory output, small K only)
+                double* o = tr + (size_t)(hh + 1) * 6;
+                o[0] = xs[0] + (double)X; o[1] = xs[1] + (double)Y; o[2] = xs[2] + (double)dpsi;
+                o[3] = (double)vx; o[4] = (double)vy; o[5] = (double)w;
+            }
             const float2 xr = sRel[hh + 1];
             ex = X - xr.x;
             ey = Y - xr.y;
@@ -149,7 +160,7 @@ extern "C" int llampc_lookahead_rollout_f32(const float* bank, int Mpad, const i
                                             const double* x0, int n_x0, const float* U, int K, int H,
                                             const float* xref, const float* uprev, int per_model_flags,
                                             const float* qrp_h, double Ts, float* J, int* best_k, double* x_final,
-                                            llampc_stream_t stream) {
+                                            double* x_traj, llampc_stream_t stream) {
     if (!bank || !x0 || !U || !xref || !uprev || !qrp_h || !J || !best_k || M <= 0 || K <= 0 || H <= 0) return LLAMPC_E_ARG;
     if (n_x0 != 1 && n_x0 != M) return LLAMPC_E_ARG;
     if (H > LLAMPC_MAX_H) return LLAMPC_E_RANGE;
@@ -168,7 +179,7 @@ extern "C" int llampc_lookahead_rollout_f32(const float* bank, int Mpad, const i
     }
     lookahead_kernel<<<(M + LA_WARPS - 1) / LA_WARPS, LA_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float4*>(bank), Mpad, model_idx, M, x0, n_x0, U, K, H, xref, uprev, per_model_flags,
-        qrp_h[0], qrp_h[1], qrp_h[2], qrp_h[3], qrp_h[4], qrp_h[5], (float)Ts, J, best_k, x_final);
+        qrp_h[0], qrp_h[1], qrp_h[2], qrp_h[3], qrp_h[4], qrp_h[5], (float)Ts, J, best_k, x_final, x_traj);
     return (int)cudaGetLastError();
 }
 

@@ -41,7 +41,24 @@ class LookAhead:
         plan.run()
         return plan.fetch()
 
-    def plan(self, x0, U, xref, uprev, model_idx=None, return_final=False, _force_general=False):
+    def warm_start(self, x0, U, xref, uprev, model_idx=None):
+        """Best sampled sequence of every model in the layout of the reference NLP's decision vector
+        (llampc/mpc/nmpc.py:113-117,196-197: xvars = [x(:,0), ..., x(:,H), u(:,0), ..., u(:,H-1)]), to be passed as
+        the solver's initial guess ``arg['x0']`` (``setupNLP.solve`` currently starts IPOPT from zeros).
+        Returns (J_best (M,), umpc (M,2,H), xmpc (M,6,H+1), guess (M, 6(H+1)+2H))."""
+        J, best_k = self.rollout(x0, U, xref, uprev, model_idx=model_idx)
+        U = np.asarray(U, dtype=np.float64)
+        M = len(best_k)
+        Ub = (U[np.arange(M), best_k] if U.ndim == 4 else U[best_k])[:, None]            # (M,1,H,2)
+        plan = self.plan(x0, Ub, xref, uprev, model_idx=model_idx, return_traj=True)
+        plan.run()
+        traj = plan.traj.cpu().numpy()[:, 0]                                               # (M,H+1,6)
+        umpc = np.swapaxes(Ub[:, 0], 1, 2)                                                 # (M,2,H)
+        xmpc = np.swapaxes(traj, 1, 2)                                                     # (M,6,H+1)
+        guess = np.concatenate([traj.reshape(M, -1), Ub[:, 0].reshape(M, -1)], axis=1)
+        return J[np.arange(M), best_k], umpc, xmpc, guess
+
+    def plan(self, x0, U, xref, uprev, model_idx=None, return_final=False, _force_general=False, return_traj=False):
         """Upload the inputs once and return a `RolloutPlan`: `.run()` enqueues the kernel on the current
         stream (device-resident inputs), `.fetch()` copies J / best_k (/ x_final) back."""
         torch = self.torch
@@ -75,6 +92,7 @@ class LookAhead:
         plan.J = torch.empty((M, K), dtype=torch.float32, device=dev)
         plan.best = torch.empty(M, dtype=torch.int32, device=dev)
         plan.xf = torch.empty((M, K, 6), dtype=torch.float64, device=dev) if return_final else None
+        plan.traj = torch.empty((M, K, H + 1, 6), dtype=torch.float64, device=dev) if return_traj else None
         return plan
 
 
@@ -87,7 +105,8 @@ class RolloutPlan:
                 o.bank.packed.data_ptr(), o.bank.Npad, None if self.midx is None else self.midx.data_ptr(), self.M,
                 self.x0.data_ptr(), self.n_x0, self.U.data_ptr(), self.K, self.H, self.xref.data_ptr(),
                 self.uprev.data_ptr(), self.flags, o.qrp.ctypes.data, o.Ts, self.J.data_ptr(), self.best.data_ptr(),
-                None if self.xf is None else self.xf.data_ptr(), _lib.stream_ptr(torch))
+                None if self.xf is None else self.xf.data_ptr(), None if self.traj is None else self.traj.data_ptr(),
+                _lib.stream_ptr(torch))
         _lib.check(rc, "llampc_lookahead_rollout_f32")
 
     def fetch(self):

@@ -97,7 +97,7 @@ class MonteCarlo:
             chk(L.llampc_lookahead_rollout_f32(bank.packed.data_ptr(), bank.Npad, self.model_idx.data_ptr(), V,
                                                self.x.data_ptr(), V, self.U.data_ptr(), self.Ks, self.H,
                                                self.xref32.data_ptr(), self.uprev.data_ptr(), 1 | 2 | 4, self.qrp.ctypes.data,
-                                               self.Ts, self.J.data_ptr(), self.best_k.data_ptr(), None, st), "lookahead")
+                                               self.Ts, self.J.data_ptr(), self.best_k.data_ptr(), None, None, st), "lookahead")
             chk(L.llampc_apply_best_f32(self.U.data_ptr(), self.best_k.data_ptr(), V, self.Ks, self.H, self.nominal.data_ptr(),
                                         self.uprev.data_ptr(), self.u_applied.data_ptr(), st), "apply_best")
             # friction schedule ('sudden' style of run_nmpc_orca_llampc_nrt_avg_runs.py:163-166): Df, Dr decay while the

@@ -742,3 +742,28 @@ def test_replay_reference_loop_settings(history):
     assert np.array_equal(gi, ri)
     np.testing.assert_allclose(gm, rm, rtol=1e-13)
     assert len(np.unique(gi)) > 3                                   # the friction decay makes the loop switch models
+
+
+def test_lookahead_warm_start_layout(history):
+    """Best sequence per model + its state trajectory in the reference NLP's decision-vector layout
+    (nmpc.py:113-117,196-197), against the oracle's trajectories."""
+    from llampc_b200.mpc import LookAhead
+    S, U, Ts = history
+    M, K, H, t0 = 40, 16, 20, 700
+    rng = np.random.RandomState(8)
+    Useq = U[:, t0:t0 + H].T[None] + np.stack([0.08 * rng.randn(K, H), 0.04 * rng.randn(K, H)], axis=-1)
+    Useq[..., 0] = np.clip(Useq[..., 0], -0.1, 1.0)
+    Useq[..., 1] = np.clip(Useq[..., 1], -0.35, 0.35)
+    xref = S[:2, t0:t0 + H + 1]
+    bank = orc.make_bank(M, seed=2, variation=tuple((k, 0.3 * s) for k, s in orc.RT_VARIATION))
+    Jb, umpc, xmpc, guess = LookAhead(bank, Ts=Ts).warm_start(S[:, t0], Useq, xref, U[:, t0 - 1])
+    Jr, bkr, traj = orc.lookahead_rollout(bank, S[:, t0], Useq, xref, U[:, t0 - 1], Ts, return_traj=True)
+    assert umpc.shape == (M, 2, H) and xmpc.shape == (M, 6, H + 1) and guess.shape == (M, 6 * (H + 1) + 2 * H)
+    for m in range(M):
+        k = int(np.argmin(Jr[m]))
+        np.testing.assert_allclose(Jb[m], Jr[m, k], rtol=1e-4)
+        np.testing.assert_allclose(umpc[m], Useq[k].T, rtol=0, atol=1e-7)
+        np.testing.assert_allclose(xmpc[m], traj[m, k].T, rtol=2e-4, atol=2e-5)
+        # layout of res['x'] in nmpc.solve: x reshaped (H+1, n_states) row by row, then u (H, n_inputs)
+        np.testing.assert_array_equal(guess[m, :6 * (H + 1)].reshape(H + 1, 6).T, xmpc[m])
+        np.testing.assert_array_equal(guess[m, 6 * (H + 1):].reshape(H, 2).T, umpc[m])
