@@ -295,6 +295,14 @@ int llampc_sample_controls_f32(const float* nominal, const float* eps, int V, in
 int llampc_apply_best_f32(const float* U, const int* best_k, int V, int K, int H, float* nominal, float* uprev,
                           double* u_applied, llampc_stream_t stream);
 
+/* Bank generation / resampling on the device (run_nmpc_orca_llampc_rt.py:145-179: parameter = centre x (1 + sigma
+ * randn) for every varied parameter of every model).  center_h / sigma_h: HOST arrays of LLAMPC_NPARAM doubles
+ * (sigma = 0: parameter not varied).  Counter-based Philox4x32-10 + Box-Muller: candidate i / parameter j get the same
+ * draw for a given seed whatever the launch.  Writes the packed bank [4][Npad] float4 and, if not NULL, bank64
+ * [LLAMPC_NPARAM][N].  Re-centring the bank on a selected candidate = calling it with that candidate's parameters. */
+int llampc_bank_generate_f32(const double* center_h, const double* sigma_h, int N, int Npad,
+                             unsigned long long seed, float* packed, double* bank64, llampc_stream_t stream);
+
 /* Measurement helper: runs an FMA-bound loop of `iters` iterations on every SM and stores, for one thread,
  * out2[0] = elapsed SM cycles (clock64) and out2[1] = elapsed nanoseconds (globaltimer): the SM clock actually
  * sustained under load, used for the roofline denominator "at the measured clock".  sink: one device float. */

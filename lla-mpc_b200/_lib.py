@@ -66,6 +66,7 @@ PROTOTYPES = {
     "llampc_mu_estimate_f64": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp]),
     "llampc_sample_controls_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "llampc_apply_best_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "llampc_bank_generate_f32": (_i, [_vp, _vp, _i, _i, C.c_ulonglong, _vp, _vp, _vp]),
     "llampc_clock_probe": (_i, [_i, _vp, _vp, _vp]),
     "llampc_plant_rk6_f64": (_i, [_vp, _i, _vp, _vp, _d, _vp, _vp]),
 }

@@ -24,6 +24,43 @@ class ModelBank:
     """params: dict with the 14 keys of ``Dynamic.__init__`` (scalars broadcast, arrays are per candidate).
     Extra keys (limits etc.) are ignored, like ``Dynamic(**ORCA())`` ignores them."""
 
+    @classmethod
+    def generate(cls, center, sigmas, n_models, seed=0, device=None):
+        """Draw a bank ON THE DEVICE: every parameter named in `sigmas` (dict name -> relative sigma) of every model is
+        centre x (1 + sigma randn) (the construction of run_nmpc_orca_llampc_rt.py:145-179 with a counter-based
+        Philox generator); `center` is a parameter dict (e.g. ``ORCA()`` or one selected candidate, which re-centres
+        the bank on it).  Nothing is materialised on the host until ``.params`` is read."""
+        torch = _lib.require_cuda()
+        self = cls.__new__(cls)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        unknown = set(sigmas) - set(PARAM_NAMES)
+        if unknown:
+            raise ValueError("unknown parameters in sigmas: %s" % sorted(unknown))
+        c = np.array([float(center[k]) for k in PARAM_NAMES], dtype=np.float64)
+        sg = np.array([float(sigmas.get(k, 0.0)) for k in PARAM_NAMES], dtype=np.float64)
+        self.N = int(n_models)
+        self.Npad = (self.N + 127) // 128 * 128
+        self.geom_shared = sg[0] == 0.0 and sg[1] == 0.0
+        self.lf_shared = float(c[0]) if self.geom_shared else float("nan")
+        self.lr_shared = float(c[1]) if self.geom_shared else float("nan")
+        self.packed = torch.empty((4, self.Npad, 4), dtype=torch.float32, device=self.device)
+        self._bank64 = torch.empty((_lib.NPARAM, self.N), dtype=torch.float64, device=self.device)
+        with torch.cuda.device(self.device):
+            _lib.check(_lib.lib().llampc_bank_generate_f32(c.ctypes.data, sg.ctypes.data, self.N, self.Npad, int(seed),
+                                                           self.packed.data_ptr(), self._bank64.data_ptr(),
+                                                           _lib.stream_ptr(torch)), "llampc_bank_generate_f32")
+        self._params = None
+        self._varied = sg != 0.0
+        return self
+
+    @property
+    def params(self):
+        if self._params is None:                                 # generated on the device: fetch on first use
+            full = self._bank64.cpu().numpy()
+            self._params = {k: (full[j].copy() if self._varied[j] else np.array(full[j, 0]))
+                            for j, k in enumerate(PARAM_NAMES)}
+        return self._params
+
     def __init__(self, params, device=None):
         torch = _lib.require_cuda()
         self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
@@ -31,8 +68,8 @@ class ModelBank:
         if missing:
             raise ValueError("model bank needs all Pacejka parameters; missing %s "
                              "(the linear-tyre 'approx' branch of Dynamic is not on the LLA-MPC path)" % missing)
-        self.params = {k: _as_param(params[k]) for k in PARAM_NAMES}
-        sizes = {a.shape[0] for a in self.params.values() if a.ndim == 1}
+        self._params = {k: _as_param(params[k]) for k in PARAM_NAMES}
+        sizes = {a.shape[0] for a in self._params.values() if a.ndim == 1}
         if len(sizes) > 1:
             raise ValueError("per-candidate parameter arrays differ in length: %s" % sorted(sizes))
         self.N = sizes.pop() if sizes else 1

@@ -47,4 +47,17 @@ LLAMPC_HD inline void pack_hist_row(const double* x_k, const double* u_k, const 
     }
 }
 
+// One candidate of the packed bank (layout in include/llampc_b200.h, llampc_bank_pack_h) from its 14 fp64
+// parameters in LLAMPC_NPARAM order: lf lr mass Iz Bf Br Cf Cr Df Dr Cm1 Cm2 Cr0 Cr2.
+LLAMPC_HD inline void pack_candidate(const double* v, float* packed, int Npad, int i) {
+    float* g0 = packed + ((size_t)0 * Npad + i) * 4;
+    float* g1 = packed + ((size_t)1 * Npad + i) * 4;
+    float* g2 = packed + ((size_t)2 * Npad + i) * 4;
+    float* g3 = packed + ((size_t)3 * Npad + i) * 4;
+    g0[0] = (float)v[4]; g0[1] = (float)v[6]; g0[2] = (float)v[8]; g0[3] = (float)v[5];          // Bf Cf Df Br
+    g1[0] = (float)v[7]; g1[1] = (float)v[9]; g1[2] = (float)(1.0 / v[2]); g1[3] = (float)v[0];  // Cr Dr 1/m lf
+    g2[0] = (float)v[1]; g2[1] = (float)(v[0] / v[3]); g2[2] = (float)(v[1] / v[3]); g2[3] = (float)v[10];   // lr lf/Iz lr/Iz Cm1
+    g3[0] = (float)v[11]; g3[1] = (float)v[12]; g3[2] = (float)v[13]; g3[3] = 0.0f;              // Cm2 Cr0 Cr2
+}
+
 }  // namespace llampc

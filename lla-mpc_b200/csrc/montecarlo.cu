@@ -92,6 +92,58 @@ apply_best_kernel(const float2* __restrict__ U, const int* __restrict__ best_k, 
     for (int h = 0; h < H; ++h) nominal[(size_t)v * H + h] = seq[min(h + 1, H - 1)];
 }
 
+// Bank generation / resampling on the device (run_nmpc_orca_llampc_rt.py:145-179: every varied parameter of every
+// model = centre x (1 + sigma randn)), counter-based so that candidate i, parameter j always gets the same draw for a
+// given seed, whatever the launch shape: Philox4x32-10 keyed by the seed, counter = (i, j / 4), Box-Muller in fp64.
+struct BankGenArgs { double center[LLAMPC_NPARAM]; double sigma[LLAMPC_NPARAM]; };
+
+__device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned c2, unsigned c3, unsigned k0, unsigned k1,
+                                              unsigned out[4]) {
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const unsigned hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const unsigned hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const unsigned n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+__global__ void __launch_bounds__(128)
+bank_generate_kernel(BankGenArgs a, int N, int Npad, unsigned long long seed, float* __restrict__ packed,
+                     double* __restrict__ bank64) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= Npad) return;
+    const int src = i < N ? i : N - 1;             // padding rows repeat the last candidate
+    double v[LLAMPC_NPARAM];
+#pragma unroll
+    for (int q = 0; q < (LLAMPC_NPARAM + 3) / 4; ++q) {
+        unsigned r[4];
+        philox4x32_10((unsigned)src, (unsigned)q, 0x4c4c414du, 0x50433230u, (unsigned)seed, (unsigned)(seed >> 32), r);
+        double z[4];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {              // Box-Muller: two normals from two uniforms
+            const double u1 = ((double)r[2 * h] + 0.5) * (1.0 / 4294967296.0);
+            const double u2 = ((double)r[2 * h + 1] + 0.5) * (1.0 / 4294967296.0);
+            const double rad = sqrt(-2.0 * log(u1));
+            double sn, cs;
+            sincospi(2.0 * u2, &sn, &cs);
+            z[2 * h] = rad * cs; z[2 * h + 1] = rad * sn;
+        }
+#pragma unroll
+        for (int h = 0; h < 4; ++h) {
+            const int j = 4 * q + h;
+            if (j < LLAMPC_NPARAM) v[j] = a.sigma[j] != 0.0 ? a.center[j] * (1.0 + a.sigma[j] * z[h]) : a.center[j];
+        }
+    }
+    pack_candidate(v, packed, Npad, i);
+    if (bank64 && i < N) {
+#pragma unroll
+        for (int j = 0; j < LLAMPC_NPARAM; ++j) bank64[(size_t)j * N + i] = v[j];
+    }
+}
+
 // SM clock actually sustained under an FMA-bound load: cycles (clock64) against wall nanoseconds (globaltimer).
 __global__ void __launch_bounds__(128)
 clock_probe_kernel(int iters, unsigned long long* out, float* sink) {
@@ -116,6 +168,16 @@ clock_probe_kernel(int iters, unsigned long long* out, float* sink) {
 }  // namespace llampc
 
 using namespace llampc;
+
+extern "C" int llampc_bank_generate_f32(const double* center_h, const double* sigma_h, int N, int Npad,
+                                        unsigned long long seed, float* packed, double* bank64, llampc_stream_t stream) {
+    if (!center_h || !sigma_h || !packed || N <= 0 || Npad < N) return LLAMPC_E_ARG;
+    if (reinterpret_cast<uintptr_t>(packed) & 15u) return LLAMPC_E_ALIGN;
+    BankGenArgs a;
+    for (int j = 0; j < LLAMPC_NPARAM; ++j) { a.center[j] = center_h[j]; a.sigma[j] = sigma_h[j]; }
+    bank_generate_kernel<<<(Npad + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, N, Npad, seed, packed, bank64);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int llampc_clock_probe(int iters, unsigned long long* out2, float* sink, llampc_stream_t stream) {
     if (!out2 || !sink || iters <= 0) return LLAMPC_E_ARG;

@@ -767,3 +767,56 @@ def test_lookahead_warm_start_layout(history):
         # layout of res['x'] in nmpc.solve: x reshaped (H+1, n_states) row by row, then u (H, n_inputs)
         np.testing.assert_array_equal(guess[m, :6 * (H + 1)].reshape(H + 1, 6).T, xmpc[m])
         np.testing.assert_array_equal(guess[m, 6 * (H + 1):].reshape(H, 2).T, umpc[m])
+
+
+def test_device_bank_generation(history):
+    """llampc_bank_generate_f32: distribution of the draws, exact non-varied parameters, packed layout identical to the
+    host packer applied to the fp64 bank, determinism in the seed, and usability by the look-back."""
+    import ctypes as C
+    import torch
+    from llampc_b200 import _lib
+    from llampc_b200.bank import ModelBank
+    from llampc_b200.mpc import LookBack
+    from llampc_b200.params import ORCA
+    S, U, Ts = history
+    sig = {"Br": 0.2, "Cr": 0.1, "Dr": 0.5, "Bf": 0.2, "Cf": 0.1, "Df": 0.5, "mass": 0.15}
+    N = 200000
+    b = ModelBank.generate(ORCA(), sig, N, seed=11)
+    p = b.params
+    nominal = ORCA()
+    for k in _lib.PARAM_NAMES:
+        if k in sig:
+            z = (p[k] / nominal[k] - 1.0) / sig[k]
+            assert abs(z.mean()) < 0.01 and abs(z.std() - 1.0) < 0.01, k
+            assert abs(np.mean(z ** 4) - 3.0) < 0.1, k                    # normal kurtosis
+        else:
+            assert np.ndim(p[k]) == 0 and float(p[k]) == nominal[k], k
+    zs = np.stack([(p[k] / nominal[k] - 1.0) / sig[k] for k in sig])
+    assert np.abs(np.corrcoef(zs) - np.eye(len(sig))).max() < 0.01         # independent draws per parameter
+    # packed layout == host packer on the same fp64 values
+    full = b.bank64.cpu().numpy()
+    ptrs = (C.c_void_p * 14)(*[np.ascontiguousarray(full[j]).ctypes.data for j in range(14)])
+    cols = [np.ascontiguousarray(full[j]) for j in range(14)]
+    ptrs = (C.c_void_p * 14)(*[c.ctypes.data for c in cols])
+    flags = (C.c_int * 14)(*([1] * 14))
+    host = np.zeros((4, b.Npad, 4), dtype=np.float32)
+    assert _lib.lib().llampc_bank_pack_h(C.cast(ptrs, C.c_void_p), C.cast(flags, C.c_void_p), N, b.Npad, host.ctypes.data) == 0
+    assert np.array_equal(b.packed.cpu().numpy(), host)
+    # determinism / seed dependence
+    b2 = ModelBank.generate(ORCA(), sig, N, seed=11)
+    b3 = ModelBank.generate(ORCA(), sig, N, seed=12)
+    assert torch.equal(b.packed, b2.packed) and not torch.equal(b.packed, b3.packed)
+    # a generated bank drives the look-back like a host-built one
+    lb = LookBack(b, W=20, Ts=Ts, K=10, refine=16)
+    best, topk, err = _window(lb, S, U, 800)
+    sub_idx = np.concatenate([topk, np.arange(0, N, 997)])
+    sub = {k: (p[k][sub_idx] if np.ndim(p[k]) else p[k]) for k in orc.PARAM_NAMES}
+    ref = np.mean(orc.window_errors(sub, S, U, 800, 20, Ts), axis=1)
+    _assert_scores(lb.avg_errors()[sub_idx], ref, "generated bank")
+    assert abs(err - ref[0]) <= 1e-9 * ref[0] and np.argmin(ref) == 0
+    # re-centre on the winner with a tighter spread: the new bank's best score is at least as good
+    center = {k: (float(p[k][best]) if np.ndim(p[k]) else float(p[k])) for k in orc.PARAM_NAMES}
+    tight = ModelBank.generate(center, {k: 0.1 * v for k, v in sig.items()}, 50000, seed=5)
+    lb2 = LookBack(tight, W=20, Ts=Ts, K=10, refine=16)
+    _, _, err2 = _window(lb2, S, U, 800)
+    assert err2 <= err * 1.0000001
