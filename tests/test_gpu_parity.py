@@ -820,3 +820,43 @@ def test_device_bank_generation(history):
     lb2 = LookBack(tight, W=20, Ts=Ts, K=10, refine=16)
     _, _, err2 = _window(lb2, S, U, 800)
     assert err2 <= err * 1.0000001
+
+
+def test_guard_fallback_paths_extreme_states():
+    """States outside the straight-line kernel's guards (slip tangents > 0.5 up to sideways sliding, yaw rates of tens
+    of rad/s, near-standstill, reversing) must take the general fallback and still match the oracle: look-back scores
+    in both sine modes and in rolling mode, look-ahead costs."""
+    from llampc_b200.mpc import LookBack, LookAhead
+    rng = np.random.RandomState(77)
+    Ts, W, N = 0.02, 16, 700
+    bank = orc.make_bank(N, seed=9)
+    nominal = orc.orca_params()
+    xs = np.column_stack([rng.uniform(-1, 1, W), rng.uniform(-1, 1, W), rng.uniform(-20, 20, W),
+                          rng.choice([-1.0, 1.0], W) * rng.uniform(0.03, 0.6, W), rng.uniform(-1.2, 1.2, W),
+                          rng.uniform(-40, 40, W)])
+    us = np.column_stack([rng.uniform(-0.1, 1.0, W), rng.uniform(-0.35, 0.35, W)])
+    x1 = np.array([orc.rk6_step(nominal, xs[j], us[j], 0, Ts) for j in range(W)])
+    errs = np.stack([orc.onestep_errors(bank, xs[j], us[j], x1[j], Ts) for j in range(W)], axis=1)
+    ref = errs.mean(axis=1)
+    assert np.isfinite(ref).all()
+    for kw in (dict(fast_sin=True), dict(fast_sin=False), dict(mode="rolling")):
+        lb = LookBack(bank, W=W, Ts=Ts, K=10, refine=16, **kw)
+        out = None
+        for j in range(W):
+            out = lb.push(xs[j], us[j], x1[j])
+        _assert_scores(lb.avg_errors(), ref, str(kw))
+        order = np.argsort(ref, kind="stable")
+        assert out[0] == order[0] and list(out[1]) == list(order[:10])
+    # look-ahead from a sliding start state with large steering and yaw rate
+    M, K, H = 48, 32, 12
+    la = LookAhead({k: (bank[k][:M] if np.ndim(bank[k]) else bank[k]) for k in orc.PARAM_NAMES}, Ts=Ts)
+    x0 = np.array([0.2, -0.1, 11.0, 0.4, 0.5, 25.0])
+    Useq = np.stack([rng.uniform(-0.1, 1.0, (K, H)), rng.uniform(-0.35, 0.35, (K, H))], axis=-1)
+    xref = np.stack([np.linspace(0.2, 0.5, H + 1), np.linspace(-0.1, 0.1, H + 1)])
+    J, bk = la.rollout(x0, Useq, xref, np.array([0.3, 0.0]))
+    sub = {k: (bank[k][:M] if np.ndim(bank[k]) else bank[k]) for k in orc.PARAM_NAMES}
+    Jr, _ = orc.lookahead_rollout(sub, x0, Useq, xref, np.array([0.3, 0.0]), Ts)
+    Jp, _ = orc.lookahead_rollout(sub, x0 * (1 + 1e-7), Useq, xref, np.array([0.3, 0.0]), Ts)
+    sens = np.abs(Jp - Jr) / Jr
+    rel = np.abs(J - Jr) / Jr
+    assert np.all(rel < np.maximum(1e-4, 50 * sens)), (rel.max(), sens.max())
