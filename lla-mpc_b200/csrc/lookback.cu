@@ -232,10 +232,10 @@ lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W,
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K4' merge of the per-CTA sorted lists written by K1 into the global top-K (K <= LLAMPC_LIST_LEN): a K-way
-// merge by K rounds of "block-min over the list heads"; each thread owns up to MERGE_LPT lists and keeps their
-// head and next key in registers so that the load of a popped list's successor is off the critical path.
-// out[0] = *best_key (then re-armed to ~0 for the next tick), out[1..K] = ascending top-K.
+// K4' stand-alone merge of the per-CTA sorted lists written by K1 / K1r into the global top-K (K <= LLAMPC_LIST_LEN),
+// one CTA per vehicle; the algorithm is merge_lists_device (llampc_common.cuh).  Used when a launch produces more
+// than 1,024 lists (otherwise the last CTA of K1 runs the same routine itself); optionally carries the NVLink
+// min-loc exchange.  out[0] = *best_key (then re-armed to ~0 for the next tick), out[1..K] = ascending top-K.
 // ---------------------------------------------------------------------------------------------------
 template <int MERGE_THREADS>
 __global__ void __launch_bounds__(MERGE_THREADS)
