@@ -559,21 +559,23 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
         x_init[:, 1] = 0.6 * rl["y"][start + 1] + 0.4 * rl["y"][start + 2]
         x_init[:, 2] = np.arctan2(rl["y"][start + 2] - rl["y"][start + 1], rl["x"][start + 2] - rl["x"][start + 1])
         x_init[:, 3] = 1.0
-        mc = MonteCarlo(make_bank_rt(1024, seed=0), tab, x_init, start, NOMINAL, r4.uniform(3.0, 15.0, Vn), W=20, K_models=10,
-                        K_seq=32, H=20, Ts=TS, seed=4)
-        mc.run(25)                                               # fill the windows, warm up
-        torch.cuda.synchronize()
-        n_t = 20
-        s0_lb, s0_la = mc.lookback_steps, mc.lookahead_steps
-        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a.record()
-        mc.run(n_t)
-        b.record()
-        torch.cuda.synchronize()
-        dt = a.elapsed_time(b) * 1e-3 / n_t
-        steps = (mc.lookback_steps - s0_lb + mc.lookahead_steps - s0_la) / n_t
-        out["C4_montecarlo_4096veh"] = {"steps_per_s": steps / dt, "ms_per_tick": dt * 1e3, "rk4_steps_per_tick": steps,
-                                        "vehicle_ticks_per_s": Vn / dt}
+        for mode in ("rolling", "recompute"):
+            mc = MonteCarlo(make_bank_rt(1024, seed=0), tab, x_init, start, NOMINAL, r4.uniform(3.0, 15.0, Vn), W=20,
+                            K_models=10, K_seq=32, H=20, Ts=TS, seed=4, lookback_mode=mode)
+            mc.run(25)                                           # fill the windows, warm up
+            torch.cuda.synchronize()
+            n_t = 20
+            s0_lb, s0_la = mc.lookback_steps, mc.lookahead_steps
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            mc.run(n_t)
+            b.record()
+            torch.cuda.synchronize()
+            dt = a.elapsed_time(b) * 1e-3 / n_t
+            steps = (mc.lookback_steps - s0_lb + mc.lookahead_steps - s0_la) / n_t
+            out["C4_montecarlo_4096veh_" + mode] = {"steps_per_s": steps / dt, "ms_per_tick": dt * 1e3,
+                                                     "rk4_steps_per_tick": steps, "vehicle_ticks_per_s": Vn / dt}
+            del mc
     except Exception as e:                                       # the secondary configs never block the main line
         out["C4_montecarlo_4096veh"] = {"error": repr(e)}
     return out

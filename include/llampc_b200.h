@@ -93,6 +93,16 @@ int llampc_lookback_window_topk_f32(const float* bank, int N, int Npad, const fl
                                     int geom_shared, int split, int K, unsigned* ticket, llampc_key_t* out,
                                     llampc_stream_t stream);
 
+/* K1r for many vehicles (Monte-Carlo layout): the newest row of vehicle v is ring slot `slot` of hist [V][W][20]
+ * (written by llampc_pack_rows_f64), err_ring is [V][W][Npad], avg_err [V][N] or NULL, best_key [V] (armed),
+ * cta_lists [V][ceil(N/128)][LLAMPC_LIST_LEN], ticket [V] zeroed, out [V][LLAMPC_LIST_LEN + 1].  emit = 0 only stores
+ * the error columns (windows still filling); K = 0 skips the top-K. */
+int llampc_lookback_rolling_multi_f32(const float* bank, int N, int Npad, const float* hist, int n_vehicles,
+                                      int slot, int W, double Ts, float* err_ring, float* avg_err,
+                                      llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
+                                      int geom_shared, int emit, int K, unsigned* ticket, llampc_key_t* out,
+                                      llampc_stream_t stream);
+
 /* K1 + top-K + multi-GPU min-loc in ONE launch per rank, over NVLink peer memory (no NCCL on the path).
  *   peer_bufs  device array [world] of pointers: peer_bufs[q] = rank q's symmetric exchange buffer of
  *              4 * world u64 words ([2 parities][world][key, sequence]), zero-initialised, mapped into this process

@@ -45,6 +45,8 @@ PROTOTYPES = {
     "llampc_lookback_window_topk_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "llampc_lookback_window_topk_peer_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp,
                                                   _vp, _i, _i, C.c_uint, _vp]),
+    "llampc_lookback_rolling_multi_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
+                                               _vp, _vp, _vp]),
     "llampc_lookback_rolling_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
     "llampc_topk_merge_lists": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
     "llampc_fill_keys": (_i, [_vp, _i, _vp]),

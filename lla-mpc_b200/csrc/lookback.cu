@@ -188,20 +188,27 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
 template <bool GEOM_SHARED>
 __global__ void __launch_bounds__(LB_THREADS)
 lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W, StepSize z, NewRow nr,
-                        float* __restrict__ err_ring, float* __restrict__ avg_err, u64* __restrict__ best_key,
-                        u64* __restrict__ cta_lists, int idx_offset, int emit, FusedMerge fm) {
+                        const float* __restrict__ hist, float* __restrict__ err_ring, float* __restrict__ avg_err,
+                        u64* __restrict__ best_key, u64* __restrict__ cta_lists, int idx_offset, int emit, FusedMerge fm) {
     __shared__ u64 skeys[LB_THREADS];
     const int tid = threadIdx.x;
+    const int v = blockIdx.y;                      // vehicle (Monte-Carlo layout); 0 for a single loop
     const int cand = blockIdx.x * LB_THREADS + tid;
     const bool valid = cand < N;
     const int ci = valid ? cand : N - 1;
     const Cand p = load_cand(bank, Npad, ci);
     HistRow r;
-    r.q0 = make_float4(nr.v[0], nr.v[1], nr.v[2], nr.v[3]);
-    r.q1 = make_float4(nr.v[4], nr.v[5], nr.v[6], nr.v[7]);
-    r.q2 = make_float4(nr.v[8], nr.v[9], nr.v[10], nr.v[11]);
-    r.q3 = make_float4(nr.v[12], nr.v[13], nr.v[14], nr.v[15]);
-    r.q4 = make_float4(nr.v[16], nr.v[17], nr.v[18], nr.v[19]);
+    if (hist) {                                    // rows of many vehicles: ring slot `slot` of hist [V][W][20]
+        const float4* hr = reinterpret_cast<const float4*>(hist + ((size_t)v * W + nr.slot) * LLAMPC_HIST_ROW);
+        r.q0 = __ldg(hr); r.q1 = __ldg(hr + 1); r.q2 = __ldg(hr + 2); r.q3 = __ldg(hr + 3); r.q4 = __ldg(hr + 4);
+    } else {                                       // single loop: the row rides in the kernel parameters
+        r.q0 = make_float4(nr.v[0], nr.v[1], nr.v[2], nr.v[3]);
+        r.q1 = make_float4(nr.v[4], nr.v[5], nr.v[6], nr.v[7]);
+        r.q2 = make_float4(nr.v[8], nr.v[9], nr.v[10], nr.v[11]);
+        r.q3 = make_float4(nr.v[12], nr.v[13], nr.v[14], nr.v[15]);
+        r.q4 = make_float4(nr.v[16], nr.v[17], nr.v[18], nr.v[19]);
+    }
+    err_ring += (size_t)v * W * Npad;
     bool ok;
     float e = lookback_step_fast<GEOM_SHARED, false>(p, r, z, ok);
     if (!ok) e = lookback_step<GEOM_SHARED, false>(p, r, z);
@@ -213,21 +220,22 @@ lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W,
     const float err = sum / (float)W;
     u64 key = ~0ull;
     if (valid) {
-        if (avg_err) avg_err[cand] = err;
+        if (avg_err) avg_err[(size_t)v * N + cand] = err;
         key = pack_key(err, (unsigned)(idx_offset + cand));
     }
-    cta_select_emit<LB_THREADS / 32>(key, skeys, 0, best_key, cta_lists);
-    if (fm.K > 0) {                                // last CTA merges the lists (one launch per tick)
+    cta_select_emit<LB_THREADS / 32>(key, skeys, v, best_key, cta_lists);
+    if (fm.K > 0) {                                // last CTA of the vehicle merges its lists (one launch per tick)
         __shared__ bool is_last;
         __shared__ MergeSmem<LB_THREADS> msm;
         __threadfence();
         __syncthreads();
-        if (tid == 0) is_last = atomicAdd(fm.ticket, 1u) == gridDim.x - 1;
+        if (tid == 0) is_last = atomicAdd(fm.ticket + v, 1u) == gridDim.x - 1;
         __syncthreads();
         if (!is_last) return;
         __threadfence();
-        merge_lists_device<LB_THREADS>(cta_lists, gridDim.x, fm.K, best_key, fm.out, msm);
-        if (tid == 0) *fm.ticket = 0;
+        merge_lists_device<LB_THREADS>(cta_lists + (size_t)v * gridDim.x * LLAMPC_LIST_LEN, gridDim.x, fm.K,
+                                       best_key ? best_key + v : nullptr, fm.out + (size_t)v * (LLAMPC_LIST_LEN + 1), msm);
+        if (tid == 0) fm.ticket[v] = 0;
     }
 }
 
@@ -573,24 +581,27 @@ extern "C" int llampc_lookback_window_topk_f32(const float* bank, int N, int Npa
                                 idx_offset, geom_shared, split, nr, fm, stream);
 }
 
-static int lookback_rolling_impl(const float* bank, int N, int Npad, const float* row32_h, int slot, int W, double Ts,
-                                 float* err_ring, float* avg_err, llampc_key_t* best_key, llampc_key_t* cta_lists,
-                                 int idx_offset, int geom_shared, int emit, const FusedMerge& fm, llampc_stream_t stream) {
-    if (!bank || !row32_h || !err_ring || N <= 0 || Npad < N || slot < 0 || slot >= W) return LLAMPC_E_ARG;
-    if (W <= 0 || W > LLAMPC_MAX_W) return LLAMPC_E_RANGE;
-    if (!aligned16(bank)) return LLAMPC_E_ALIGN;
+static int lookback_rolling_impl(const float* bank, int N, int Npad, const float* row32_h, const float* hist, int n_vehicles,
+                                 int slot, int W, double Ts, float* err_ring, float* avg_err, llampc_key_t* best_key,
+                                 llampc_key_t* cta_lists, int idx_offset, int geom_shared, int emit, const FusedMerge& fm,
+                                 llampc_stream_t stream) {
+    if (!bank || (!row32_h && !hist) || !err_ring || N <= 0 || Npad < N || slot < 0 || slot >= W || n_vehicles <= 0)
+        return LLAMPC_E_ARG;
+    if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
+    if (!aligned16(bank) || (hist && !aligned16(hist))) return LLAMPC_E_ALIGN;
     NewRow nr;
-    for (int i = 0; i < LLAMPC_HIST_ROW; ++i) nr.v[i] = row32_h[i];
+    if (!hist)
+        for (int i = 0; i < LLAMPC_HIST_ROW; ++i) nr.v[i] = row32_h[i];
     nr.slot = slot;
-    const int grid = (N + LB_THREADS - 1) / LB_THREADS;
+    const dim3 grid((N + LB_THREADS - 1) / LB_THREADS, n_vehicles);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (geom_shared)
         lookback_rolling_kernel<true><<<grid, LB_THREADS, 0, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, W,
-                                                                   make_step(Ts), nr, err_ring, avg_err, best_key,
+                                                                   make_step(Ts), nr, hist, err_ring, avg_err, best_key,
                                                                    cta_lists, idx_offset, emit, fm);
     else
         lookback_rolling_kernel<false><<<grid, LB_THREADS, 0, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, W,
-                                                                    make_step(Ts), nr, err_ring, avg_err, best_key,
+                                                                    make_step(Ts), nr, hist, err_ring, avg_err, best_key,
                                                                     cta_lists, idx_offset, emit, fm);
     return (int)cudaGetLastError();
 }
@@ -628,8 +639,25 @@ extern "C" int llampc_lookback_rolling_f32(const float* bank, int N, int Npad, c
                                            llampc_key_t* cta_lists, int idx_offset, int geom_shared, int emit,
                                            llampc_stream_t stream) {
     FusedMerge none = {nullptr, nullptr, 0};
-    return lookback_rolling_impl(bank, N, Npad, row32_h, slot, W, Ts, err_ring, avg_err, best_key, cta_lists, idx_offset,
-                                 geom_shared, emit, none, stream);
+    return lookback_rolling_impl(bank, N, Npad, row32_h, nullptr, 1, slot, W, Ts, err_ring, avg_err, best_key, cta_lists,
+                                 idx_offset, geom_shared, emit, none, stream);
+}
+
+extern "C" int llampc_lookback_rolling_multi_f32(const float* bank, int N, int Npad, const float* hist, int n_vehicles,
+                                                 int slot, int W, double Ts, float* err_ring, float* avg_err,
+                                                 llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
+                                                 int geom_shared, int emit, int K, unsigned* ticket, llampc_key_t* out,
+                                                 llampc_stream_t stream) {
+    if (!hist) return LLAMPC_E_ARG;
+    if (emit && (K < 0 || K > LLAMPC_LIST_LEN)) return LLAMPC_E_RANGE;
+    const int n_lists = (N + LB_THREADS - 1) / LB_THREADS;
+    const bool in_kernel = emit && K > 0 && ticket && out && cta_lists && best_key && n_lists <= LB_THREADS * MERGE_LPT;
+    FusedMerge fm = {in_kernel ? ticket : nullptr, in_kernel ? out : nullptr, in_kernel ? K : 0};
+    int rc = lookback_rolling_impl(bank, N, Npad, nullptr, hist, n_vehicles, slot, W, Ts, err_ring, avg_err, best_key,
+                                   cta_lists, idx_offset, geom_shared, emit, fm, stream);
+    if (rc || !emit || K == 0 || in_kernel) return rc;
+    if (!cta_lists || !out) return LLAMPC_E_ARG;
+    return llampc_topk_merge_lists(cta_lists, n_lists, n_vehicles, K, best_key, out, stream);
 }
 
 extern "C" int llampc_lookback_num_lists(int N, int W, int split) {
@@ -754,9 +782,9 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
         const int n_lists_r = (t->N + LB_THREADS - 1) / LB_THREADS;
         const bool in_kernel_r = t->rolling == 1 && t->ticket != nullptr && Kt > 0 && n_lists_r <= LB_THREADS * MERGE_LPT;
         FusedMerge fmr = {in_kernel_r ? t->ticket : nullptr, in_kernel_r ? keys : nullptr, in_kernel_r ? Kt : 0};
-        rc = lookback_rolling_impl(t->bank, t->N, t->Npad, t->row32_h, t->slot, t->W, t->Ts, t->err_ring, t->avg_err,
-                                   t->best_key, t->cta_lists, t->idx_offset, t->geom_shared, t->rolling > 1 ? 0 : 1, fmr,
-                                   stream);
+        rc = lookback_rolling_impl(t->bank, t->N, t->Npad, t->row32_h, nullptr, 1, t->slot, t->W, t->Ts, t->err_ring,
+                                   t->avg_err, t->best_key, t->cta_lists, t->idx_offset, t->geom_shared,
+                                   t->rolling > 1 ? 0 : 1, fmr, stream);
         if (rc) return rc;
         if (t->rolling > 1) {                                        // window still filling: column stored, no decision
             if (t->n_refine > 0 && t->row64_h && t->hist64)

@@ -23,7 +23,8 @@ from ..tracks import RacelineTable
 class MonteCarlo:
     def __init__(self, bank_params, table, x_init, projidx_init, plant_params, drop_start, V=None, W=20, K_models=10,
                  K_seq=32, H=20, Ts=0.02, scale=0.9, mu_init=1.0, seed=4, sigma_pwm=0.1, sigma_steer=0.05,
-                 drop_rate=1.0 / 22.0, drop_len=0.2, initial_model=0, smoothing_mu=20, mu_alpha=0.08, limits=None):
+                 drop_rate=1.0 / 22.0, drop_len=0.2, initial_model=0, smoothing_mu=20, mu_alpha=0.08, limits=None,
+                 lookback_mode="rolling"):
         torch = _lib.require_cuda()
         self.torch, self.L = torch, _lib.lib()
         self.bank = bank_params if isinstance(bank_params, ModelBank) else ModelBank(bank_params)
@@ -70,7 +71,13 @@ class MonteCarlo:
         self.u_applied = torch.zeros((V, 2), dtype=f64, device=dev)
         self.model_idx = torch.full((V,), int(initial_model), dtype=i32, device=dev)
         self.hist = torch.zeros((V, W, _lib.HIST_ROW), dtype=f32, device=dev)
-        self.n_lists = self.L.llampc_lookback_num_lists(N, W, 0)
+        if lookback_mode not in ("rolling", "recompute"):
+            raise ValueError("lookback_mode must be 'rolling' or 'recompute'")
+        # "rolling" = the reference's own bookkeeping (rt.py:352-354): per-vehicle (W, N) error ring, one new column per
+        # tick; "recompute" re-integrates every vehicle's whole window every tick (W times the look-back work)
+        self.rolling = lookback_mode == "rolling"
+        self.err_ring = torch.zeros((V, W, self.bank.Npad), dtype=f32, device=dev) if self.rolling else None
+        self.n_lists = (N + 127) // 128 if self.rolling else self.L.llampc_lookback_num_lists(N, W, 0)
         self.cta_lists = torch.empty((V, self.n_lists, _lib.LIST_LEN), dtype=i64, device=dev)
         self.best_key = torch.full((V,), -1, dtype=i64, device=dev)
         self.topk = torch.zeros((V, _lib.LIST_LEN + 1), dtype=i64, device=dev)
@@ -110,16 +117,25 @@ class MonteCarlo:
             slot = self.tick_count % self.W
             chk(L.llampc_pack_rows_f64(self.x.data_ptr(), self.u_applied.data_ptr(), self.x_next.data_ptr(), V, self.Ts,
                                        bank.lf_shared, bank.lr_shared, slot, self.W, self.hist.data_ptr(), None, st), "pack_rows")
-            if self.tick_count + 1 >= self.W:
+            full = self.tick_count + 1 >= self.W
+            if self.rolling:
+                chk(L.llampc_lookback_rolling_multi_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), V, slot,
+                                                        self.W, self.Ts, self.err_ring.data_ptr(), None,
+                                                        self.best_key.data_ptr(), self.cta_lists.data_ptr(), 0,
+                                                        int(bank.geom_shared), int(full), self.Km, self.ticket.data_ptr(),
+                                                        self.topk.data_ptr(), st), "lookback (rolling)")
+                self.lookback_steps += V * bank.N
+            elif full:
                 chk(L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), self.W,
                                                       V, self.W, self.Ts, None, self.best_key.data_ptr(),
                                                       self.cta_lists.data_ptr(), 0, int(bank.geom_shared), 16, self.Km,
                                                       self.ticket.data_ptr(), self.topk.data_ptr(), st), "lookback+merge")
+                self.lookback_steps += V * bank.N * self.W
+            if full:
                 chk(L.llampc_mu_estimate_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.Km, 0, bank.bank64.data_ptr(),
                                              bank.N, V, self.smoothing, self.mu_alpha, 0.95, 9.81, self.mu_state.data_ptr(),
                                              self.curr_mu.data_ptr(), st), "mu_estimate")
                 self.model_idx.copy_((self.topk[:, 0] & 0xFFFFFFFF).to(torch.int32))
-                self.lookback_steps += V * bank.N * self.W
             self.lookahead_steps += V * self.Ks * self.H
             self.x, self.x_next = self.x_next, self.x
         self.tick_count += 1

@@ -449,7 +449,8 @@ def test_lookahead_tolerance_tracks_conditioning(history):
 
 
 # ------------------------------------------------------------------------------------------- Monte-Carlo closed loop
-def test_montecarlo_closed_loop_stagewise_parity():
+@pytest.mark.parametrize("lookback_mode", ["rolling", "recompute"])
+def test_montecarlo_closed_loop_stagewise_parity(lookback_mode):
     """Config C4 at test size: every stage of the device-resident tick is checked against the oracle on the same
     inputs (planner, control sampling, look-ahead cost, controller step, plant RK6, history rows -> look-back
     arg-min / top-K, friction estimate)."""
@@ -472,7 +473,8 @@ def test_montecarlo_closed_loop_stagewise_parity():
     x_init[:, 3] = rng.uniform(0.8, 1.6, V)
     nominal = orc.orca_params()
     drop = rng.uniform(0.0, 0.1, V)
-    mc = MonteCarlo(bank, tab, x_init, start, nominal, drop, W=W, K_models=Km, K_seq=Ks, H=H, Ts=Ts, seed=4)
+    mc = MonteCarlo(bank, tab, x_init, start, nominal, drop, W=W, K_models=Km, K_seq=Ks, H=H, Ts=Ts, seed=4,
+                    lookback_mode=lookback_mode)
     eps = mc.eps.cpu().numpy().astype(np.float64)
     mus = [orc.MuEstimatorOracle(mass=nominal["mass"]) for _ in range(V)]
     trans = []
