@@ -561,8 +561,8 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
         x_init[:, 3] = 1.0
         for mode in ("rolling", "recompute"):
             mc = MonteCarlo(make_bank_rt(1024, seed=0), tab, x_init, start, NOMINAL, r4.uniform(3.0, 15.0, Vn), W=20,
-                            K_models=10, K_seq=32, H=20, Ts=TS, seed=4, lookback_mode=mode)
-            mc.run(25)                                           # fill the windows, warm up
+                            K_models=10, K_seq=32, H=20, Ts=TS, seed=4, lookback_mode=mode, use_graphs=True)
+            mc.run(48)                                           # fill the windows, capture the per-slot tick graphs
             torch.cuda.synchronize()
             n_t = 20
             s0_lb, s0_la = mc.lookback_steps, mc.lookahead_steps

@@ -24,7 +24,7 @@ class MonteCarlo:
     def __init__(self, bank_params, table, x_init, projidx_init, plant_params, drop_start, V=None, W=20, K_models=10,
                  K_seq=32, H=20, Ts=0.02, scale=0.9, mu_init=1.0, seed=4, sigma_pwm=0.1, sigma_steer=0.05,
                  drop_rate=1.0 / 22.0, drop_len=0.2, initial_model=0, smoothing_mu=20, mu_alpha=0.08, limits=None,
-                 lookback_mode="rolling"):
+                 lookback_mode="rolling", use_graphs=False):
         torch = _lib.require_cuda()
         self.torch, self.L = torch, _lib.lib()
         self.bank = bank_params if isinstance(bank_params, ModelBank) else ModelBank(bank_params)
@@ -86,9 +86,41 @@ class MonteCarlo:
         self.tick_count = 0
         self.lookback_steps = 0
         self.lookahead_steps = 0
+        # the time of the friction schedule lives on the device so that a whole tick can be replayed as a CUDA graph
+        self.t_dev = torch.zeros((), dtype=f64, device=dev)
+        self.use_graphs = bool(use_graphs)
+        self._graphs = {}                                          # ring slot -> captured tick (steady state only)
 
     # ------------------------------------------------------------------ one tick, asynchronous on the current stream
     def tick(self):
+        """One closed-loop tick for all vehicles.  Once the windows are full the tick for each of the W ring slots is
+        captured once as a CUDA graph (all arguments are then static) and replayed: one graph launch per tick."""
+        if self.use_graphs and self.tick_count >= self.W + 2:
+            torch = self.torch
+            slot = self.tick_count % self.W
+            g = self._graphs.get(slot)
+            if g is None:
+                torch.cuda.synchronize()
+                g = torch.cuda.CUDAGraph()
+                with torch.cuda.graph(g):
+                    self._tick_body()
+                self._graphs[slot] = g                             # capture does not execute: replay runs the tick
+            g.replay()
+            self._after_tick()
+            return
+        self._tick_body()
+        self._after_tick()
+
+    def _after_tick(self):
+        V, bank = self.V, self.bank
+        if self.rolling:
+            self.lookback_steps += V * bank.N
+        elif self.tick_count + 1 >= self.W:
+            self.lookback_steps += V * bank.N * self.W
+        self.lookahead_steps += V * self.Ks * self.H
+        self.tick_count += 1
+
+    def _tick_body(self):
         torch, L, V = self.torch, self.L, self.V
         st = torch.cuda.current_stream().cuda_stream
         dev, s, xy, coef, mus = self.table.device_tables()
@@ -109,7 +141,7 @@ class MonteCarlo:
                                         self.uprev.data_ptr(), self.u_applied.data_ptr(), st), "apply_best")
             # friction schedule ('sudden' style of run_nmpc_orca_llampc_nrt_avg_runs.py:163-166): Df, Dr decay while the
             # vehicle's drop interval is active
-            t = self.tick_count * self.Ts
+            t = self.t_dev
             active = ((self.drop_start < t) & (t < self.drop_start + self.drop_len)).to(torch.float64)
             self.plant[:, 8:10] *= (1.0 - self.drop_rate * active)[:, None]
             chk(L.llampc_plant_rk6_f64(self.plant.data_ptr(), V, self.x.data_ptr(), self.u_applied.data_ptr(), self.Ts,
@@ -124,21 +156,18 @@ class MonteCarlo:
                                                         self.best_key.data_ptr(), self.cta_lists.data_ptr(), 0,
                                                         int(bank.geom_shared), int(full), self.Km, self.ticket.data_ptr(),
                                                         self.topk.data_ptr(), st), "lookback (rolling)")
-                self.lookback_steps += V * bank.N
             elif full:
                 chk(L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), self.W,
                                                       V, self.W, self.Ts, None, self.best_key.data_ptr(),
                                                       self.cta_lists.data_ptr(), 0, int(bank.geom_shared), 16, self.Km,
                                                       self.ticket.data_ptr(), self.topk.data_ptr(), st), "lookback+merge")
-                self.lookback_steps += V * bank.N * self.W
             if full:
                 chk(L.llampc_mu_estimate_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.Km, 0, bank.bank64.data_ptr(),
                                              bank.N, V, self.smoothing, self.mu_alpha, 0.95, 9.81, self.mu_state.data_ptr(),
                                              self.curr_mu.data_ptr(), st), "mu_estimate")
                 self.model_idx.copy_((self.topk[:, 0] & 0xFFFFFFFF).to(torch.int32))
-            self.lookahead_steps += V * self.Ks * self.H
-            self.x, self.x_next = self.x_next, self.x
-        self.tick_count += 1
+            self.x.copy_(self.x_next)                             # fixed addresses (graph replay)
+            self.t_dev += self.Ts
 
     def run(self, n):
         for _ in range(n):

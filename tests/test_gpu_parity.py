@@ -695,8 +695,11 @@ def test_c4_full_size_properties():
     assert (full["plant"][:, 8] < 0.192).all()                     # every vehicle went through its friction drop
     assert ((full["curr_mu"] > 0.2) & (full["curr_mu"] < 1.5)).all()
     sel = np.arange(0, V, 137)
-    mc2 = MonteCarlo(bank, tab, x_init[sel], start[sel], orc.orca_params(), drop[sel], W=20, K_models=10, K_seq=32, H=20)
+    # ... and replaying the tick as CUDA graphs (one per ring slot) changes nothing
+    mc2 = MonteCarlo(bank, tab, x_init[sel], start[sel], orc.orca_params(), drop[sel], W=20, K_models=10, K_seq=32, H=20,
+                     use_graphs=True)
     mc2.run(30)
+    assert len(mc2._graphs) == 8
     part = mc2.host()
     for k in ("x", "projidx", "curr_mu", "model_idx", "u_applied"):
         assert np.array_equal(part[k], full[k][sel]), k
