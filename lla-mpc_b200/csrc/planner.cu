@@ -88,10 +88,16 @@ planner_kernel(const double* __restrict__ s, const double* __restrict__ xy, cons
     if (xref32) { xref32[(size_t)v * (N + 1) * 2] = (float)px; xref32[(size_t)v * (N + 1) * 2 + 1] = (float)py; }
     if (xref64) { xref64[(size_t)v * (N + 1) * 2] = px; xref64[(size_t)v * (N + 1) * 2 + 1] = py; }
     double vel = fmax(v0, .01), vr = 0.0;
+    // segment index = bisect(s, dist) - 1 (pycubicspline.py:104).  dist starts at s[pid+1] and advances by a few
+    // centimetres per step, so the index is tracked incrementally (same result as the bisection, a couple of loads
+    // instead of ~10 dependent ones); a wrap past the end of the table restarts the scan with a bisection.
+    int seg = min(pid + 1, n - 1);
     for (int idh = 1; idh <= N; ++idh) {
         dist = __dadd_rn(dist, __dmul_rn(__dmul_rn(scale, vel), Ts));
         dist = fmod(dist, s_last);
-        int seg = seg_index(s, n, dist);
+        if (dist < s[seg]) seg = seg_index(s, n, dist);
+        else if (seg + 8 < n && s[seg + 8] <= dist) seg = seg_index(s, n, dist);          // large jump (huge speed)
+        else while (seg + 1 < n && s[seg + 1] <= dist) ++seg;
         seg = min(max(seg, 0), n - 2);
         const double dx = dist - s[seg];
         const double* c = coef + (size_t)seg * stride;
