@@ -364,7 +364,7 @@ def run_b200(args):
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch at C2 from the committed ncu --set full
                 # capture (profiles/r01_k1_final_ncu.md); not captured for the sharded C5 launches
-                "traffic": 4250880 if world == 1 else None, "kernel": "lookback_window_kernel", "kernel_us": k1_avg_s * 1e6,
+                "traffic": 4261632 if world == 1 else None, "kernel": "lookback_window_kernel", "kernel_us": k1_avg_s * 1e6,
                 "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json; tensor/HBM peaks do not bound this elementwise ODE kernel)" % sm_max,
                 "flop_per_step": F_ALG, "steps_per_launch": n_local * W_C2,
                 "sfu": {"achieved_Tops": k1_rate * S_ALG / 1e12, "peak_Tops": 148 * 16 * sm_max * 1e6 / 1e12},

@@ -865,3 +865,30 @@ def test_guard_fallback_paths_extreme_states():
     sens = np.abs(Jp - Jr) / Jr
     rel = np.abs(J - Jr) / Jr
     assert np.all(rel < np.maximum(1e-4, 50 * sens)), (rel.max(), sens.max())
+
+
+def test_argument_errors_raise(history):
+    """Error behaviour of the host layer: empty / inconsistent banks, out-of-range window and K, wrong shapes."""
+    from llampc_b200 import _lib
+    from llampc_b200.bank import ModelBank
+    from llampc_b200.mpc import LookBack, LookAhead
+    S, U, Ts = history
+    p = orc.orca_params()
+    with pytest.raises((ValueError, _lib.LlampcError)):
+        ModelBank(dict(p, Bf=np.zeros(0), Df=np.zeros(0)))                   # empty bank
+    with pytest.raises(ValueError):
+        ModelBank(dict(p, Bf=np.ones(3), Df=np.ones(4)))                     # ragged per-candidate arrays
+    with pytest.raises(ValueError):
+        ModelBank({k: v for k, v in p.items() if k != "Dr"})                # linear-tyre ('approx') models are not on the path
+    bank = orc.make_bank(100, 0)
+    for bad in (dict(W=0), dict(W=2000), dict(W=5, K=100), dict(W=5, K=20, mode="rolling"), dict(W=5, mode="nope")):
+        with pytest.raises(ValueError):
+            LookBack(bank, Ts=Ts, **bad)
+    lb = LookBack(bank, W=3, Ts=Ts)
+    with pytest.raises(ValueError):
+        lb.load_window(S[:, :2].T, U[:, :2].T, S[:, 1:3].T)                  # not W transitions
+    with pytest.raises(ValueError):
+        lb.push(S[:5, 0], U[:, 0], S[:, 1])                                  # state must have 6 entries
+    la = LookAhead(bank, Ts=Ts)
+    with pytest.raises(ValueError):
+        la.rollout(S[:, 0], np.zeros((4, 10, 2)), np.zeros((2, 5)), U[:, 0])  # xref needs H+1 columns
