@@ -521,6 +521,17 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
         L.llampc_topk_merge_lists(lb1.cta_lists.data_ptr(), nl1, 1, 10, lb1.best_key.data_ptr(), lb1.result.data_ptr(), st)
     dt = time_it(c1, 50)
     out["C1_lookback_1024x20"] = {"steps_per_s": 1024 * 20 / dt, "us_per_tick": dt * 1e6}
+    for mode in ("recompute", "rolling"):                        # the same case end to end (LookBack.push, host in / out)
+        lbp = LookBack(make_bank_rt(1024, seed=0), W=20, Ts=TS, K=10, refine=16, mode=mode)
+        for t in range(30):
+            lbp.push(S[:, t], U[:, t], S[:, t + 1])
+        lat = []
+        for t in range(30, 60):
+            a0 = time.perf_counter()
+            lbp.push(S[:, t % 60], U[:, t % 60], S[:, t % 60 + 1])
+            lat.append(time.perf_counter() - a0)
+        out["C1_lookback_1024x20"]["push_p50_us_" + mode] = float(np.percentile(lat, 50) * 1e6)
+        del lbp
 
     # C3 look-ahead: 16,384 models x 32 control sequences x 20-step horizon with the raceline-tracking cost
     M, K, H = 16384, 32, 20
