@@ -74,7 +74,7 @@ int llampc_hist_row_pack_h(const double* x_k, const double* u_k, const double* x
  *   cta_lists [n_vehicles][n_lists][LLAMPC_LIST_LEN] or NULL, n_lists = llampc_lookback_num_lists(N, W, split):
  *             the ascending LLAMPC_LIST_LEN smallest keys of every CTA (input of llampc_topk_merge_lists)
  *   geom_shared  non-zero: rows carry valid stage-1 slip angles (lf, lr identical for all candidates)
- *   split     window splits per candidate inside a CTA (1, 2, 4) or 0 = choose from N, W; + 16 selects the
+ *   split     window splits per candidate inside a CTA (1, 2, 4, 8, 16) or 0 = choose from N, W; + 32 selects the
  *             MUFU.SIN (SFU) tyre sine instead of the FMA-pipe polynomial (faster, ~2x the fp32 score error)
  * ------------------------------------------------------------------------------------------- */
 int llampc_lookback_window_f32(const float* bank, int N, int Npad,

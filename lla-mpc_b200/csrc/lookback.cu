@@ -156,7 +156,7 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
         if (avg_err) avg_err[(size_t)v * N + cand] = err;
         key = pack_key(err, (unsigned)(idx_offset + cand));
     }
-    cta_select_emit<CPB / 32>(key, skeys, v, best_key, cta_lists);
+    cta_select_emit<(CPB >= 32 ? CPB / 32 : 1)>(key, skeys, v, best_key, cta_lists);   // CPB < 32: part of warp 0 holds keys
     if (fm.K > 0) {                                // uniform over the grid
         __shared__ bool is_last;
         __shared__ MergeSmem<LB_THREADS> msm;
@@ -477,7 +477,7 @@ static int choose_split(int N, int W) {
     // SM time ~ (CTAs on the busiest SM) x (rows per thread) while the FMA pipe is the limiter.
     int best = 1;
     long best_cost = -1;
-    for (int sy = 1; sy <= 4; sy *= 2) {
+    for (int sy = 1; sy <= 16; sy *= 2) {          // 8 and 16 only pay off for banks too small to fill the GPU
         if (sy > W) break;
         long ctas = ((long)N * sy + LB_THREADS - 1) / LB_THREADS;
         long cost = ((ctas + NUM_SMS - 1) / NUM_SMS) * ((W + sy - 1) / sy);
@@ -529,7 +529,7 @@ static int lookback_window_impl(const float* bank, int N, int Npad, const float*
     if (!aligned16(bank) || !aligned16(hist) || (hist_stride_rows * LLAMPC_HIST_ROW * 4) % 16) return LLAMPC_E_ALIGN;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     int mufu = 0;
-    if (split >= 16) { mufu = 1; split -= 16; }   // bit 4: MUFU.SIN tyre sine (LookBack(fast_sin=True))
+    if (split >= 32) { mufu = 1; split -= 32; }   // bit 5: MUFU.SIN tyre sine (LookBack(fast_sin=True))
     if (split == 0) split = choose_split(N, W);
     if (split > W) split = 1;
 #define LB_CASE(SYV)                                                                                                  \
@@ -542,6 +542,8 @@ static int lookback_window_impl(const float* bank, int N, int Npad, const float*
         LB_CASE(1)
         LB_CASE(2)
         LB_CASE(4)
+        LB_CASE(8)
+        LB_CASE(16)
         default: return LLAMPC_E_ARG;
     }
 #undef LB_CASE
@@ -662,10 +664,10 @@ extern "C" int llampc_lookback_rolling_multi_f32(const float* bank, int N, int N
 
 extern "C" int llampc_lookback_num_lists(int N, int W, int split) {
     if (N <= 0 || W <= 0) return LLAMPC_E_ARG;
-    if (split >= 16) split -= 16;
+    if (split >= 32) split -= 32;
     if (split == 0) split = choose_split(N, W);
     if (split > W) split = 1;
-    if (split != 1 && split != 2 && split != 4) return LLAMPC_E_ARG;
+    if (split != 1 && split != 2 && split != 4 && split != 8 && split != 16) return LLAMPC_E_ARG;
     const int cpb = LB_THREADS / split;
     return (N + cpb - 1) / cpb;
 }

@@ -63,8 +63,8 @@ class LookBack:
         if fast_sin is None:
             fast_sin = os.environ.get("LLAMPC_FAST_SIN", "1") == "1"
         self.fast_sin = bool(fast_sin)
-        # bit 4 of `split` selects the MUFU.SIN tyre sine in K1 (include/llampc_b200.h)
-        self.idx_offset, self.group, self.split = int(idx_offset), group, int(split) | (16 if self.fast_sin else 0)
+        # bit 5 (+32) of `split` selects the MUFU.SIN tyre sine in K1 (include/llampc_b200.h)
+        self.idx_offset, self.group, self.split = int(idx_offset), group, int(split) | (32 if self.fast_sin else 0)
         if mode not in ("recompute", "rolling"):
             raise ValueError("mode must be 'recompute' or 'rolling'")
         self.rolling = mode == "rolling"

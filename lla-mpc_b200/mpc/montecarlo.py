@@ -159,7 +159,7 @@ class MonteCarlo:
             elif full:
                 chk(L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), self.W,
                                                       V, self.W, self.Ts, None, self.best_key.data_ptr(),
-                                                      self.cta_lists.data_ptr(), 0, int(bank.geom_shared), 16, self.Km,
+                                                      self.cta_lists.data_ptr(), 0, int(bank.geom_shared), 32, self.Km,
                                                       self.ticket.data_ptr(), self.topk.data_ptr(), st), "lookback+merge")
             if full:
                 chk(L.llampc_mu_estimate_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.Km, 0, bank.bank64.data_ptr(),

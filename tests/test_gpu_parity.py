@@ -140,7 +140,7 @@ def test_lookback_push_sequence_matches_reference_loop(history):
         _assert_scores(lb.avg_errors(), ravg, "tick %d" % t)
 
 
-@pytest.mark.parametrize("split", [1, 2, 4])
+@pytest.mark.parametrize("split", [1, 2, 4, 8, 16])
 def test_lookback_window_splits_agree(history, split):
     from llampc_b200.mpc import LookBack
     S, U, Ts = history

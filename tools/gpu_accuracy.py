@@ -61,14 +61,14 @@ if __name__ == "__main__":
     for t_end in (600, 1600):
         lb = run_case("C2 +mass", orc.make_bank(65536, 1, variation=c2var), 50, t_end)
     for t_end in (600, 1600):
-        run_case("C2 +mass  MUFU.SIN tyre", orc.make_bank(65536, 1, variation=c2var), 50, t_end, split=16 + 2)
-    for split in (1, 2, 4, 16 + 1, 16 + 2):
+        run_case("C2 +mass  MUFU.SIN tyre", orc.make_bank(65536, 1, variation=c2var), 50, t_end, split=32 + 2)
+    for split in (1, 2, 4, 32 + 1, 32 + 2):
         ms = time_kernel(lb, split)
         print("K1 N=65536 W=50 split=%2d: %.1f us  -> %.3e steps/s" % (split, ms * 1e3, 65536 * 50 / ms * 1e3), flush=True)
     wide = (("Br", 2.0), ("Cr", 2.0), ("Dr", 2.0), ("Bf", 2.0), ("Cf", 2.0), ("Df", 2.0))
     run_case("sigma=2.0 (plot_comp_time)", orc.make_bank(8192, 3, variation=wide), 10, 900)
-    run_case("sigma=2.0 MUFU.SIN", orc.make_bank(8192, 3, variation=wide), 10, 900, split=16 + 1)
-    run_case("C1 MUFU.SIN", orc.make_bank(1024, 0), 20, 1600, split=16 + 4)
+    run_case("sigma=2.0 MUFU.SIN", orc.make_bank(8192, 3, variation=wide), 10, 900, split=32 + 1)
+    run_case("C1 MUFU.SIN", orc.make_bank(1024, 0), 20, 1600, split=32 + 4)
     rng = np.random.RandomState(9)
     p = orc.orca_params()
     all14 = {k: p[k] * (1 + 0.1 * rng.randn(8192)) for k in orc.PARAM_NAMES}
@@ -78,7 +78,7 @@ if __name__ == "__main__":
     ts = np.arange(551, 601)
     lbb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
     print("1M bank evaluate:", lbb.evaluate()[0])
-    for split in (1, 2, 17):
+    for split in (1, 2, 33):
         ms = time_kernel(lbb, split, reps=10)
         print("K1 N=1M W=50 split=%2d: %.1f us  -> %.3e steps/s" % (split, ms * 1e3, (1 << 20) * 50 / ms * 1e3), flush=True)
     # tick latency through the public API
