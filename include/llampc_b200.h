@@ -109,7 +109,9 @@ int llampc_lookback_rolling_multi_f32(const float* bank, int N, int Npad, const 
  *              (CUDA IPC / torch symmetric memory); peer_bufs[rank] is this rank's own buffer
  *   seq        tick counter, identical on every rank, incremented by the caller every call (>= 1)
  * After the launch out[0] holds the GLOBAL arg-min key on every rank (0 if a peer did not arrive within ~1 s);
- * out[1..K] stay the rank-local top-K.  Needs <= 1,024 per-CTA lists (N <= 131,072 x split). */
+ * out[1..K] stay the rank-local top-K.  With more than 1,024 per-CTA lists (shards above 131,072 candidates per
+ * split) the exchange is carried by the stand-alone merge kernel instead (two launches, still no NCCL call); the
+ * limit is 8,192 lists. */
 int llampc_lookback_window_topk_peer_f32(const float* bank, int N, int Npad, const float* hist, int W,
                                          int hist_stride_rows, double Ts, float* avg_err,
                                          llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
