@@ -116,6 +116,7 @@ class LookBack:
         self._xk_p, self._uk_p, self._xk1_p = self._xk.ctypes.data, self._uk.ctypes.data, self._xk1.ctypes.data
         self.window_count = 0
         self._next_slot = 0
+        self._geom = (self.bank.lf_shared, self.bank.lr_shared)
         t = _lib.Tick()
         t.bank, t.N, t.Npad = self.bank.packed.data_ptr(), N, self.bank.Npad
         t.hist, t.W, t.Ts = self.hist.data_ptr(), self.W, self.Ts
@@ -281,6 +282,29 @@ class LookBack:
         scores, idx = scores[order], idx[order]
         n_ok = int(np.count_nonzero(scores == scores))
         return int(idx[0]), idx[:min(self.K, n_ok)].copy(), float(scores[0])
+
+    # ------------------------------------------------------------------ bank replacement
+    def set_bank(self, bank_params):
+        """Swap the model bank (same number of candidates), e.g. after ``ModelBank.generate`` re-centred it on the
+        current best model.  In recompute mode the next tick simply scores the new bank over the window already in the
+        history ring; in rolling mode the per-tick error ring belongs to the old bank, so the window refills."""
+        bank = bank_params if isinstance(bank_params, ModelBank) else ModelBank(bank_params, self.bank.device)
+        if bank.N != self.bank.N or bank.device != self.bank.device:
+            raise ValueError("set_bank needs a bank of the same size on the same device")
+        self.bank = bank
+        t = self._tick
+        t.bank, t.geom_shared = bank.packed.data_ptr(), int(bank.geom_shared)
+        if self.n_refine > 0:
+            t.bank64 = bank.bank64.data_ptr()
+        if self.rolling:
+            self.err_ring.zero_()
+            self.window_count = 0
+        elif self.window_count:
+            # the history rows carry stage-1 slip angles computed with the OLD bank's lf, lr: re-pack them
+            raise_if = bank.geom_shared and (bank.lf_shared, bank.lr_shared) != (self._geom[0], self._geom[1])
+            if raise_if or not bank.geom_shared:
+                self.window_count = 0                            # geometry changed: start a fresh window
+        self._geom = (bank.lf_shared, bank.lr_shared)
 
     # ------------------------------------------------------------------ inspection
     def avg_errors(self):

@@ -892,3 +892,32 @@ def test_argument_errors_raise(history):
     la = LookAhead(bank, Ts=Ts)
     with pytest.raises(ValueError):
         la.rollout(S[:, 0], np.zeros((4, 10, 2)), np.zeros((2, 5)), U[:, 0])  # xref needs H+1 columns
+
+
+def test_set_bank_swaps_models_in_place(history):
+    """Recompute mode is stateless w.r.t. the bank: after set_bank the next tick scores the new bank over the window
+    already in the ring; rolling mode refills its error ring."""
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    W = 12
+    b1, b2 = orc.make_bank(900, seed=1), orc.make_bank(900, seed=2)
+    lb = LookBack(b1, W=W, Ts=Ts, K=10, refine=16)
+    for t in range(600, 600 + W):
+        lb.push(S[:, t], U[:, t], S[:, t + 1])
+    lb.set_bank(b2)
+    t = 600 + W
+    got = lb.push(S[:, t], U[:, t], S[:, t + 1])
+    ref = np.mean(orc.window_errors(b2, S, U, t, W, Ts), axis=1)
+    order = np.argsort(ref, kind="stable")
+    assert got[0] == order[0] and list(got[1]) == list(order[:10])
+    _assert_scores(lb.avg_errors(), ref, "after set_bank")
+    lr = LookBack(b1, W=W, Ts=Ts, K=10, refine=16, mode="rolling")
+    for t in range(600, 600 + W):
+        lr.push(S[:, t], U[:, t], S[:, t + 1])
+    lr.set_bank(b2)
+    outs = [lr.push(S[:, t], U[:, t], S[:, t + 1]) for t in range(700, 700 + W)]
+    assert all(o == (None, None, None) for o in outs[:-1])
+    ref = np.mean(orc.window_errors(b2, S, U, 700 + W - 1, W, Ts), axis=1)
+    assert outs[-1][0] == int(np.argmin(ref))
+    with pytest.raises(ValueError):
+        lb.set_bank(orc.make_bank(901, seed=3))
