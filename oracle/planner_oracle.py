@@ -17,38 +17,40 @@ import numpy as np
 
 
 class Spline:
-    """pycubicspline.py:17-132"""
+    """Natural cubic spline through (x_i, y_i) -- the arithmetic of pycubicspline.py:17-132, written with array
+    operations: same tridiagonal system (first/last row = identity, i.e. c_0 = c_{n-1} = 0), same dense solve, same
+    per-segment formulas, so the coefficients are bit-identical to the reference's."""
 
     def __init__(self, x, y):
-        self.x, self.y = x, y
-        self.nx = len(x)
+        self.x = x
+        self.nx = n = len(x)
         h = np.diff(x)
-        self.a = [iy for iy in y]
-        A = np.zeros((self.nx, self.nx))                       # :107-122
-        A[0, 0] = 1.0
-        for i in range(self.nx - 1):
-            if i != (self.nx - 2):
-                A[i + 1, i + 1] = 2.0 * (h[i] + h[i + 1])
-            A[i + 1, i] = h[i]
-            A[i, i + 1] = h[i]
-        A[0, 1] = 0.0
-        A[self.nx - 1, self.nx - 2] = 0.0
-        A[self.nx - 1, self.nx - 1] = 1.0
-        B = np.zeros(self.nx)                                  # :124-132
-        for i in range(self.nx - 2):
-            B[i + 1] = 3.0 * (self.a[i + 2] - self.a[i + 1]) / h[i + 1] - 3.0 * (self.a[i + 1] - self.a[i]) / h[i]
-        self.c = np.linalg.solve(A, B)
-        self.b, self.d = [], []
-        for i in range(self.nx - 1):                           # :40-45
-            self.d.append((self.c[i + 1] - self.c[i]) / (3.0 * h[i]))
-            self.b.append((self.a[i + 1] - self.a[i]) / h[i] - h[i] * (self.c[i + 1] + 2.0 * self.c[i]) / 3.0)
+        self.a = [v for v in y]
+        a = np.asarray(self.a, dtype=np.float64)
+        # system matrix (:107-122): interior rows h_{i-1}, 2(h_{i-1}+h_i), h_i; boundary rows pin c to zero
+        M = np.zeros((n, n))
+        rows = np.arange(1, n - 1)
+        M[rows, rows - 1] = h[:-1]
+        M[rows, rows] = 2.0 * (h[:-1] + h[1:])
+        M[rows, rows + 1] = h[1:]
+        M[0, 0] = 1.0
+        M[n - 1, n - 1] = 1.0
+        # right-hand side (:124-132)
+        rhs = np.zeros(n)
+        rhs[1:n - 1] = 3.0 * (a[2:] - a[1:-1]) / h[1:] - 3.0 * (a[1:-1] - a[:-2]) / h[:-1]
+        self.c = np.linalg.solve(M, rhs)
+        c = self.c
+        # remaining coefficients per segment (:40-45)
+        self.d = list((c[1:] - c[:-1]) / (3.0 * h))
+        self.b = list((a[1:] - a[:-1]) / h - h * (c[1:] + 2.0 * c[:-1]) / 3.0)
 
-    def calc(self, t):                                         # :47-65
+    def calc(self, t):
+        """Value at t, None outside the knot range (:47-65); segment = bisect(x, t) - 1 (:104)."""
         if t < self.x[0] or t > self.x[-1]:
             return None
-        i = bisect.bisect(self.x, t) - 1
-        dx = t - self.x[i]
-        return self.a[i] + self.b[i] * dx + self.c[i] * dx ** 2.0 + self.d[i] * dx ** 3.0
+        k = bisect.bisect(self.x, t) - 1
+        u = t - self.x[k]
+        return self.a[k] + self.b[k] * u + self.c[k] * u ** 2.0 + self.d[k] * u ** 3.0
 
 
 class Spline2D:
