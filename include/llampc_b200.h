@@ -190,6 +190,8 @@ typedef struct llampc_tick {
                                        words.  The ordered finalists returned are the GLOBAL ones.  NULL = single GPU */
     int peer_world; int peer_rank;
     unsigned peer_seq;              /* tick counter >= 1, identical on all ranks, incremented by the caller  */
+    unsigned long long pending_seq; /* internal: state between llampc_lookback_tick (sync = 0) and ..._finish        */
+    int pending_words;
     float* err_ring;                /* [W][Npad] per-tick error columns (rolling mode only)                */
     int rolling;                    /* 0: recompute the whole window from the history ring (K1);
                                        1: rolling mode (K1r): integrate only the newest row, replace ring column
@@ -198,7 +200,14 @@ typedef struct llampc_tick {
                                        2: rolling mode while the window is filling: store the column, no decision */
 } llampc_tick_t;
 
-int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stream);
+int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream);
+
+/* Asynchronous use: llampc_lookback_tick with t->sync = 0 only enqueues the work; llampc_lookback_finish waits for
+ * the result (polling the zero-copy sequence word, else synchronising the stream) and orders the finalists;
+ * llampc_lookback_decode turns them into plain arrays (idx_out / score_out [max(K, n_refine) or 1], *n_valid = 0 while
+ * a rolling window is filling).  The host is free between tick and finish, e.g. for the next NMPC solve. */
+int llampc_lookback_finish(llampc_tick_t* t, llampc_stream_t stream);
+int llampc_lookback_decode(const llampc_tick_t* t, long long* idx_out, double* score_out, int* n_valid);
 
 /* Layout probes for bindings that mirror llampc_tick_t by hand: sizeof, and offsetof of
  * Ts (0), cta_lists (1), result_h (2), peer_seq (3), rolling (4). */

@@ -31,6 +31,7 @@ class Tick(C.Structure):
                 ("bank64", _vp), ("hist64", _vp), ("row64_h", _vp),
                 ("result", _vp), ("result_h", _vp), ("sync", _i), ("ticket", _vp), ("zero_copy", _i),
                 ("peer_bufs", _vp), ("peer_world", _i), ("peer_rank", _i), ("peer_seq", C.c_uint),
+                ("pending_seq", C.c_ulonglong), ("pending_words", _i),
                 ("err_ring", _vp), ("rolling", _i)]
 
 
@@ -54,6 +55,8 @@ PROTOTYPES = {
     "llampc_topk_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "llampc_refine_f64": (_i, [_vp, _i, _vp, _i, _d, _vp, _i, _i, _vp, _vp]),
     "llampc_lookback_tick": (_i, [C.POINTER(Tick), _vp]),
+    "llampc_lookback_finish": (_i, [C.POINTER(Tick), _vp]),
+    "llampc_lookback_decode": (_i, [C.POINTER(Tick), _vp, _vp, _vp]),
     "llampc_tick_sizeof": (_i, []),
     "llampc_tick_offsetof": (_i, [_i]),
     "llampc_lookback_push": (_i, [C.POINTER(Tick), _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp]),

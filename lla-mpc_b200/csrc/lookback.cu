@@ -762,7 +762,9 @@ extern "C" int llampc_forces_batch_f32(const float* bank, int N, int Npad, const
     return (int)cudaGetLastError();
 }
 
-extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stream) {
+extern "C" int llampc_lookback_finish(llampc_tick_t* t, llampc_stream_t stream);
+
+extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
     if (!t || !t->bank || !t->hist || !t->best_key || !t->result || !t->result_h) return LLAMPC_E_ARG;
     if (t->slot < 0 || t->slot >= t->W || t->K < 0 || t->n_refine < 0) return LLAMPC_E_ARG;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -826,7 +828,8 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
         }
     }
     const bool refine = Kt > 0 && t->n_refine > 0;
-    bool have_result = false;                                        // set when the zero-copy hand-off delivered it
+    t->pending_seq = 0;
+    t->pending_words = 0;
     if (refine) {
         if (!t->bank64 || !t->hist64) return LLAMPC_E_ARG;
         NewRow64 nr64;
@@ -841,10 +844,10 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
         FinalCopy fc = {nullptr, nullptr, nullptr, 0, 0};
         PeerGather pg = {nullptr, 0, 0, 0, 0};
         if (gather) {
-            if (!(t->sync && t->zero_copy && t->ticket)) return LLAMPC_E_ARG;   // the gather rides on the zero-copy hand-off
+            if (!(t->zero_copy && t->ticket)) return LLAMPC_E_ARG;     // the gather rides on the zero-copy hand-off
             pg.peers = t->peer_bufs; pg.world = t->peer_world; pg.rank = t->peer_rank; pg.seq = t->peer_seq; pg.kt = Kt;
         }
-        if (t->sync && t->zero_copy && t->ticket) {
+        if (t->zero_copy && t->ticket) {
             void* dptr = nullptr;
             if (cudaHostGetDevicePointer(&dptr, t->result_h, 0) == cudaSuccess && dptr) {
                 static unsigned long long seq_counter = 1;
@@ -854,6 +857,8 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
                 fc.words = 1 + 2 * Kt;
                 fc.seq = ++seq_counter;
                 reinterpret_cast<volatile llampc_key_t*>(t->result_h)[words] = 0;
+                t->pending_seq = fc.seq;
+                t->pending_words = words;
             } else {
                 (void)cudaGetLastError();                            // result_h is not mapped: use the copy path
                 if (gather) return LLAMPC_E_ARG;
@@ -862,57 +867,70 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
         refine_f64_kernel<<<Kt, RF_THREADS, 0, st>>>(t->bank64, t->N, t->hist64, t->W, t->Ts, keys + 1, t->idx_offset, errs, nr64, fc,
                                                      pg);
         LLAMPC_CUDA_TRY(cudaGetLastError());
-        if (fc.dst_host) {
-            volatile llampc_key_t* flag = reinterpret_cast<volatile llampc_key_t*>(t->result_h) + words;
-            long spins = 0;
-            while (*flag != fc.seq) {
-                if (++spins > 20000000L) {                           // tens of ms: something is wrong, stop spinning
-                    LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
-                    if (*flag != fc.seq) return (int)cudaErrorUnknown;
-                    break;
-                }
-#if defined(__x86_64__)
-                __builtin_ia32_pause();
-#endif
-            }
-            __asm__ __volatile__("" ::: "memory");                     // the result words are read after the flag
-            have_result = true;
-            if (gather) {
-                // host: pick the Kt best of the world * Kt finalists (fp64 score, ties by index; NaN / padding last)
-                // and compact them into the single-GPU layout [arg-min | Kt keys | Kt scores]
-                const int total = Kt * t->peer_world;
-                llampc_key_t* raw = t->result_h + 1;
-                llampc_key_t ak[LLAMPC_MAX_K * 32];
-                double ae[LLAMPC_MAX_K * 32];
-                if (total > LLAMPC_MAX_K * 32) return LLAMPC_E_RANGE;
-                for (int q = 0; q < t->peer_world; ++q)
-                    for (int j = 0; j < Kt; ++j) {
-                        ak[q * Kt + j] = raw[(size_t)q * 2 * Kt + j];
-                        memcpy(&ae[q * Kt + j], &raw[(size_t)q * 2 * Kt + Kt + j], 8);
-                    }
-                llampc_key_t* hk2 = t->result_h + 1;
-                double* he2 = reinterpret_cast<double*>(t->result_h + 1 + Kt);
-                for (int i = 0; i < Kt; ++i) {                       // partial selection sort
-                    int best = -1;
-                    for (int j = i; j < total; ++j) {
-                        if (ak[j] == ~0ull || ae[j] != ae[j]) continue;
-                        if (best < 0 || ae[j] < ae[best] ||
-                            (ae[j] == ae[best] && (unsigned)(ak[j] & 0xffffffffull) < (unsigned)(ak[best] & 0xffffffffull)))
-                            best = j;
-                    }
-                    if (best < 0) { for (int r = i; r < Kt; ++r) { hk2[r] = ~0ull; he2[r] = NAN; } break; }
-                    const llampc_key_t tk = ak[best]; const double te = ae[best];
-                    ak[best] = ak[i]; ae[best] = ae[i];
-                    ak[i] = tk; ae[i] = te;
-                    hk2[i] = tk; he2[i] = te;
-                }
-            }
-        }
     }
-    if (!have_result) {
+    if (t->pending_seq == 0)
         LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->result_h, t->result, (size_t)(1 + Kt + (refine ? Kt : 0)) * 8,
                                         cudaMemcpyDeviceToHost, st));
-        if (!t->sync) return 0;
+    if (!t->sync) return 0;                                          // the caller finishes with llampc_lookback_finish
+    return llampc_lookback_finish(t, stream);
+}
+
+// Second half of a tick: waits for the result (polls the zero-copy sequence word, or synchronises the stream) and
+// orders the finalists on the host.  llampc_lookback_tick calls it itself when t->sync != 0; with sync = 0 the caller
+// may do unrelated host work (the NMPC solve of the next tick) between the two calls.
+extern "C" int llampc_lookback_finish(llampc_tick_t* t, llampc_stream_t stream) {
+    if (!t || !t->result_h) return LLAMPC_E_ARG;
+    if (t->rolling > 1) return 0;                                    // a filling tick produced no result
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    const int Kt = t->K > t->n_refine ? t->K : t->n_refine;
+    const bool refine = Kt > 0 && t->n_refine > 0;
+    const bool gather = refine && t->peer_world > 1 && t->peer_bufs != nullptr;
+    if (t->pending_seq != 0) {
+        volatile llampc_key_t* flag = reinterpret_cast<volatile llampc_key_t*>(t->result_h) + t->pending_words;
+        long spins = 0;
+        while (*flag != t->pending_seq) {
+            if (++spins > 20000000L) {                               // tens of ms: something is wrong, stop spinning
+                LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
+                if (*flag != t->pending_seq) return (int)cudaErrorUnknown;
+                break;
+            }
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+        __asm__ __volatile__("" ::: "memory");                         // the result words are read after the flag
+        t->pending_seq = 0;
+        if (gather) {
+            // host: pick the Kt best of the world * Kt finalists (fp64 score, ties by index; NaN / padding last)
+            // and compact them into the single-GPU layout [arg-min | Kt keys | Kt scores]
+            const int total = Kt * t->peer_world;
+            llampc_key_t* raw = t->result_h + 1;
+            llampc_key_t ak[LLAMPC_MAX_K * 32];
+            double ae[LLAMPC_MAX_K * 32];
+            if (total > LLAMPC_MAX_K * 32) return LLAMPC_E_RANGE;
+            for (int q = 0; q < t->peer_world; ++q)
+                for (int j = 0; j < Kt; ++j) {
+                    ak[q * Kt + j] = raw[(size_t)q * 2 * Kt + j];
+                    memcpy(&ae[q * Kt + j], &raw[(size_t)q * 2 * Kt + Kt + j], 8);
+                }
+            llampc_key_t* hk2 = t->result_h + 1;
+            double* he2 = reinterpret_cast<double*>(t->result_h + 1 + Kt);
+            for (int i = 0; i < Kt; ++i) {                           // partial selection sort
+                int best = -1;
+                for (int j = i; j < total; ++j) {
+                    if (ak[j] == ~0ull || ae[j] != ae[j]) continue;
+                    if (best < 0 || ae[j] < ae[best] ||
+                        (ae[j] == ae[best] && (unsigned)(ak[j] & 0xffffffffull) < (unsigned)(ak[best] & 0xffffffffull)))
+                        best = j;
+                }
+                if (best < 0) { for (int r = i; r < Kt; ++r) { hk2[r] = ~0ull; he2[r] = NAN; } break; }
+                const llampc_key_t tk = ak[best]; const double te = ae[best];
+                ak[best] = ak[i]; ae[best] = ae[i];
+                ak[i] = tk; ae[i] = te;
+                hk2[i] = tk; he2[i] = te;
+            }
+        }
+    } else {
         LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
     }
     // order the finalists on the host: by fp64 score (ties: lower index), NaN / padded entries last
@@ -944,21 +962,9 @@ extern "C" int llampc_lookback_tick(const llampc_tick_t* t, llampc_stream_t stre
     return 0;
 }
 
-// One FFI crossing per MPC tick for a host that holds the transition as three fp64 vectors: packs the history
-// row(s) into the caller's scratch (t->row32_h / t->row64_h must point to writable host buffers), runs the tick
-// (sync forced) and decodes the ordered finalists into plain index / score arrays.
-extern "C" int llampc_lookback_push(llampc_tick_t* t, const double* x_k, const double* u_k, const double* x_k1,
-                                    double lf_shared, double lr_shared, long long* idx_out, double* score_out,
-                                    int* n_valid, llampc_stream_t stream) {
-    if (!t || !x_k || !u_k || !x_k1 || !idx_out || !score_out || !n_valid || !t->row32_h) return LLAMPC_E_ARG;
-    int rc = llampc_hist_row_pack_h(x_k, u_k, x_k1, t->Ts, lf_shared, lr_shared, const_cast<float*>(t->row32_h),
-                                    const_cast<double*>(t->row64_h));
-    if (rc) return rc;
-    const int sync_was = t->sync;
-    t->sync = 1;
-    rc = llampc_lookback_tick(t, stream);
-    t->sync = sync_was;
-    if (rc) return rc;
+// Decodes the ordered finalists left in t->result_h by llampc_lookback_finish into plain index / score arrays.
+extern "C" int llampc_lookback_decode(const llampc_tick_t* t, long long* idx_out, double* score_out, int* n_valid) {
+    if (!t || !idx_out || !score_out || !n_valid || !t->result_h) return LLAMPC_E_ARG;
     *n_valid = 0;
     if (t->rolling > 1) return 0;                                    // window still filling
     const int Kt = t->K > t->n_refine ? t->K : t->n_refine;
@@ -982,6 +988,24 @@ extern "C" int llampc_lookback_push(llampc_tick_t* t, const double* x_k, const d
     }
     *n_valid = n;
     return 0;
+}
+
+// One FFI crossing per MPC tick for a host that holds the transition as three fp64 vectors: packs the history
+// row(s) into the caller's scratch (t->row32_h / t->row64_h must point to writable host buffers), runs the tick
+// (sync forced) and decodes the ordered finalists into plain index / score arrays.
+extern "C" int llampc_lookback_push(llampc_tick_t* t, const double* x_k, const double* u_k, const double* x_k1,
+                                    double lf_shared, double lr_shared, long long* idx_out, double* score_out,
+                                    int* n_valid, llampc_stream_t stream) {
+    if (!t || !x_k || !u_k || !x_k1 || !idx_out || !score_out || !n_valid || !t->row32_h) return LLAMPC_E_ARG;
+    int rc = llampc_hist_row_pack_h(x_k, u_k, x_k1, t->Ts, lf_shared, lr_shared, const_cast<float*>(t->row32_h),
+                                    const_cast<double*>(t->row64_h));
+    if (rc) return rc;
+    const int sync_was = t->sync;
+    t->sync = 1;
+    rc = llampc_lookback_tick(t, stream);
+    t->sync = sync_was;
+    if (rc) return rc;
+    return llampc_lookback_decode(t, idx_out, score_out, n_valid);
 }
 
 // layout probes for FFI bindings that mirror llampc_tick_t by hand

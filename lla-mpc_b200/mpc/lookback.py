@@ -116,6 +116,7 @@ class LookBack:
         self._xk_p, self._uk_p, self._xk1_p = self._xk.ctypes.data, self._uk.ctypes.data, self._xk1.ctypes.data
         self.window_count = 0
         self._next_slot = 0
+        self._async_pending, self._async_out = False, None
         self._geom = (self.bank.lf_shared, self.bank.lr_shared)
         t = _lib.Tick()
         t.bank, t.N, t.Npad = self.bank.packed.data_ptr(), N, self.bank.Npad
@@ -220,6 +221,52 @@ class LookBack:
             _lib.check(rc, "llampc_lookback_push")
         n = self._nvalid.value
         if n == 0:                                               # every score is NaN (np.argmin would return the first NaN)
+            return None, np.zeros(0, dtype=np.int64), float("nan")
+        idx = self._idx_out[:n]
+        return int(idx[0]), idx[:self.K].copy(), float(self._score_out[0])
+
+    def push_async(self, x_k, u_k, x_k1):
+        """Enqueue one tick and return immediately; fetch the decision later with ``collect()``.  The host is free in
+        between (in the reference loop: the next tick's planner + NMPC solve), so the look-back latency leaves the
+        critical path.  Single GPU or NVLink peer exchange only; while the window fills it degrades to ``push``."""
+        if self.group is not None and self._peer is None:
+            raise _lib.LlampcError("push_async needs the peer-memory exchange (or a single GPU)")
+        self._async_out = None
+        if self.window_count + 1 < self.W:
+            self._async_out = self.push(x_k, u_k, x_k1)
+            return
+        slot = self._next_slot
+        self._next_slot = (slot + 1) % self.W
+        self.window_count = min(self.window_count + 1, self.W)
+        r32, r64 = self._pack_row(slot, x_k, u_k, x_k1)
+        t = self._tick
+        t.row32_h, t.row64_h, t.slot = r32, r64, slot
+        if self._peer is not None:
+            t.peer_seq = self._peer.next_seq()
+        t.sync = 0
+        torch = self.torch
+        with self._stream_dev:
+            rc = self._L.llampc_lookback_tick(self._tick_ref, torch.cuda.current_stream().cuda_stream)
+        t.sync = 1
+        if rc:
+            _lib.check(rc, "llampc_lookback_tick")
+        self._async_pending = True
+
+    def collect(self):
+        """Decision of the tick enqueued by ``push_async``: (best_idx, topk_idx, best_err)."""
+        if not getattr(self, "_async_pending", False):
+            return self._async_out if self._async_out is not None else (None, None, None)
+        self._async_pending = False
+        torch = self.torch
+        with self._stream_dev:
+            rc = self._L.llampc_lookback_finish(self._tick_ref, torch.cuda.current_stream().cuda_stream)
+        if rc:
+            _lib.check(rc, "llampc_lookback_finish")
+        rc = self._L.llampc_lookback_decode(self._tick_ref, self._idx_out_p, self._score_out_p, self._nvalid_p)
+        if rc:
+            _lib.check(rc, "llampc_lookback_decode")
+        n = self._nvalid.value
+        if n == 0:
             return None, np.zeros(0, dtype=np.int64), float("nan")
         idx = self._idx_out[:n]
         return int(idx[0]), idx[:self.K].copy(), float(self._score_out[0])

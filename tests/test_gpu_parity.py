@@ -921,3 +921,26 @@ def test_set_bank_swaps_models_in_place(history):
     assert outs[-1][0] == int(np.argmin(ref))
     with pytest.raises(ValueError):
         lb.set_bank(orc.make_bank(901, seed=3))
+
+
+def test_push_async_overlaps_host_work(history):
+    """push_async / collect: same decisions as push; the host does unrelated work while the tick runs."""
+    import time
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    bank = orc.make_bank(65536, seed=1)
+    for mode in ("recompute", "rolling"):
+        a = LookBack(bank, W=20, Ts=Ts, K=10, refine=16, mode=mode)
+        b = LookBack(bank, W=20, Ts=Ts, K=10, refine=16, mode=mode)
+        hidden = []
+        for t in range(300, 345):
+            ra = a.push(S[:, t], U[:, t], S[:, t + 1])
+            b.push_async(S[:, t], U[:, t], S[:, t + 1])
+            t0 = time.perf_counter()
+            while time.perf_counter() - t0 < 200e-6:             # stands in for the NMPC solve of the next tick
+                pass
+            t1 = time.perf_counter()
+            rb = b.collect()
+            hidden.append(time.perf_counter() - t1)
+            assert (ra[0] is None and rb[0] is None) or (ra[0] == rb[0] and list(ra[1]) == list(rb[1]) and ra[2] == rb[2])
+        assert np.median(hidden[25:]) < 30e-6                    # the result was already there: only decode time left
