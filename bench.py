@@ -278,7 +278,9 @@ def run_b200(args):
     assert lb.fused and n_lists > 0
 
     ticket = torch.zeros(1, dtype=torch.int32, device=dev)
-    one_launch = n_lists <= 1024
+    one_launch = True                                            # K1 + in-kernel tree merge: one launch per tick at any N
+    tree_ws = lb.workspace
+    peer_ptrs = lambda: None
     # N > 1: the min-loc across GPUs is fused into the same kernels over NVLink peer memory (symmetric buffers);
     # LLAMPC_BENCH_NCCL=1 times the NCCL MIN all-reduce variant instead
     peer = None
@@ -294,22 +296,27 @@ def run_b200(args):
         if int(ok.item()) == 0:
             peer = None
 
+    legacy_tick = os.environ.get("LLAMPC_BENCH_LEGACY_TICK", "0") == "1"   # K1 + last-CTA list merge (the earlier tick)
+
     def tick_device():
-        """One look-back tick with device-resident inputs: K1 (scores, block arg-min, per-CTA sorted lists) with the
-        top-10 merge finished by the last CTA inside the same launch (+ the min-loc all-reduce for N > 1)."""
-        if peer is not None:
-            rc = L.llampc_lookback_window_topk_peer_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2,
-                                                        W_C2, TS, lb.avg_err.data_ptr(), lb.best_key.data_ptr(),
-                                                        lb.cta_lists.data_ptr(), lo, int(bank.geom_shared), lb.split, 10,
-                                                        ticket.data_ptr(), lb.result.data_ptr(), peer.peer_ptrs.data_ptr(),
-                                                        world, rank, peer.next_seq(), st)
-            _lib.check(rc, "K1+K4'+NVLink min-loc")
-            return
-        rc = L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2,
-                                               TS, lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), lo,
-                                               int(bank.geom_shared), lb.split, 10, ticket.data_ptr(), lb.result.data_ptr(), st)
-        _lib.check(rc, "K1+K4'")
-        if world > 1:
+        """One look-back tick with device-resident inputs, ONE launch: K1 (scores + per-CTA sorted lists) with the
+        top-10 finished by the in-kernel tree of warp merges (+ for N > 1 the min-loc across GPUs, written by the
+        root of the tree over NVLink peer memory, or an NCCL MIN all-reduce)."""
+        if legacy_tick:
+            rc = L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1,
+                                                   W_C2, TS, lb.avg_err.data_ptr(), lb.best_key.data_ptr(),
+                                                   lb.cta_lists.data_ptr(), lo, int(bank.geom_shared), lb.split, 10,
+                                                   ticket.data_ptr(), lb.result.data_ptr(), st)
+            _lib.check(rc, "K1+K4'")
+        else:
+            rc = L.llampc_lookback_window_balanced_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, TS,
+                                                       lb.avg_err.data_ptr(), lo, int(bank.geom_shared), int(lb.fast_sin), 10,
+                                                       tree_ws.data_ptr(), tree_ws.numel(), lb.result.data_ptr(),
+                                                       peer.peer_ptrs.data_ptr() if peer is not None else None,
+                                                       world if peer is not None else 0, rank,
+                                                       peer.next_seq() if peer is not None else 0, st)
+            _lib.check(rc, "K1 + tree merge" + (" + NVLink min-loc" if peer is not None else ""))
+        if world > 1 and peer is None:
             td.all_reduce(lb.result[:1], op=td.ReduceOp.MIN)
 
     def k1_only():
@@ -342,9 +349,17 @@ def run_b200(args):
             td.all_reduce(tot, op=td.ReduceOp.MAX)
         return float(tot.item()), ms
 
+    def tick_kernel_only():
+        """the same launch without the cross-GPU exchange: the kernel the roofline is quoted on"""
+        rc = L.llampc_lookback_window_balanced_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, TS,
+                                                   lb.avg_err.data_ptr(), lo, int(bank.geom_shared), int(lb.fast_sin), 10,
+                                                   tree_ws.data_ptr(), tree_ws.numel(), lb.result.data_ptr(), None, 0, 0, 0, st)
+        _lib.check(rc, "K1 + tree merge")
+
     with ClockSampler(local) as clk:
         total_ms, per_ms = timed(tick_device, args.steps, max(args.warmup, 3))
-        k1_total_ms, k1_ms = timed(k1_only, args.steps, 3)
+        k1_total_ms, k1_ms = timed(tick_kernel_only, args.steps, 3)
+        _, k1_bare_ms = timed(k1_only, args.steps, 3)
     clocks = clk.summary()
     steps_per_tick = n_total * W_C2
     value = steps_per_tick * args.steps / (total_ms * 1e-3)
@@ -364,7 +379,8 @@ def run_b200(args):
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
                 # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch at C2 from the committed ncu --set full
                 # capture (profiles/r01_k1_final_ncu.md); not captured for the sharded C5 launches
-                "traffic": 4261632 if world == 1 else None, "kernel": "lookback_window_kernel", "kernel_us": k1_avg_s * 1e6,
+                "traffic": 4261632 if world == 1 else None, "kernel": "lookback_window_kernel (scores + selection + tree merge: the whole tick)",
+                "kernel_us": k1_avg_s * 1e6, "kernel_us_scores_only": float(np.mean(k1_bare_ms)) * 1e3,
                 "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json; tensor/HBM peaks do not bound this elementwise ODE kernel)" % sm_max,
                 "flop_per_step": F_ALG, "steps_per_launch": n_local * W_C2,
                 "sfu": {"achieved_Tops": k1_rate * S_ALG / 1e12, "peak_Tops": 148 * 16 * sm_max * 1e6 / 1e12},
@@ -485,10 +501,10 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
     nls = L.llampc_lookback_num_lists(N_C2, W_C2, 0)
 
     def c2_strict():
-        L.llampc_lookback_window_f32(lbs.bank.packed.data_ptr(), N_C2, lbs.bank.Npad, lbs.hist.data_ptr(), W_C2, 1, W_C2, TS,
-                                     lbs.avg_err.data_ptr(), lbs.best_key.data_ptr(), lbs.cta_lists.data_ptr(), 0,
-                                     int(lbs.bank.geom_shared), 0, st)
-        L.llampc_topk_merge_lists(lbs.cta_lists.data_ptr(), nls, 1, 10, lbs.best_key.data_ptr(), lbs.result.data_ptr(), st)
+        L.llampc_lookback_window_balanced_f32(lbs.bank.packed.data_ptr(), N_C2, lbs.bank.Npad, lbs.hist.data_ptr(), W_C2, TS,
+                                              lbs.avg_err.data_ptr(), 0, int(lbs.bank.geom_shared), 0, 10,
+                                              lbs.workspace.data_ptr(), lbs.workspace.numel(), lbs.result.data_ptr(),
+                                              None, 0, 0, 0, st)
     dt = time_it(c2_strict, 50)
     out["C2_strict_polynomial_sin"] = {"steps_per_s": N_C2 * W_C2 / dt, "us_per_tick": dt * 1e6}
     del lbs
@@ -500,10 +516,10 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
     n_lists = L.llampc_lookback_num_lists(N_C5, W_C2, 0)
 
     def c5():
-        L.llampc_lookback_window_f32(lb.bank.packed.data_ptr(), N_C5, lb.bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2, TS,
-                                     lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), 0,
-                                     int(lb.bank.geom_shared), lb.split, st)
-        L.llampc_topk_merge_lists(lb.cta_lists.data_ptr(), n_lists, 1, 10, lb.best_key.data_ptr(), lb.result.data_ptr(), st)
+        L.llampc_lookback_window_balanced_f32(lb.bank.packed.data_ptr(), N_C5, lb.bank.Npad, lb.hist.data_ptr(), W_C2, TS,
+                                              lb.avg_err.data_ptr(), 0, int(lb.bank.geom_shared), int(lb.fast_sin), 10,
+                                              lb.workspace.data_ptr(), lb.workspace.numel(), lb.result.data_ptr(),
+                                              None, 0, 0, 0, st)
     dt = time_it(c5, 20)
     out["C5_1gpu_lookback_1048576x50"] = {"steps_per_s": N_C5 * W_C2 / dt, "ms_per_tick": dt * 1e3}
     del lb
@@ -515,10 +531,10 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
     nl1 = L.llampc_lookback_num_lists(1024, 20, 0)
 
     def c1():
-        L.llampc_lookback_window_f32(lb1.bank.packed.data_ptr(), 1024, lb1.bank.Npad, lb1.hist.data_ptr(), 20, 1, 20, TS,
-                                     lb1.avg_err.data_ptr(), lb1.best_key.data_ptr(), lb1.cta_lists.data_ptr(), 0,
-                                     int(lb1.bank.geom_shared), lb1.split, st)
-        L.llampc_topk_merge_lists(lb1.cta_lists.data_ptr(), nl1, 1, 10, lb1.best_key.data_ptr(), lb1.result.data_ptr(), st)
+        L.llampc_lookback_window_balanced_f32(lb1.bank.packed.data_ptr(), 1024, lb1.bank.Npad, lb1.hist.data_ptr(), 20, TS,
+                                              lb1.avg_err.data_ptr(), 0, int(lb1.bank.geom_shared), int(lb1.fast_sin), 10,
+                                              lb1.workspace.data_ptr(), lb1.workspace.numel(), lb1.result.data_ptr(),
+                                              None, 0, 0, 0, st)
     dt = time_it(c1, 50)
     out["C1_lookback_1024x20"] = {"steps_per_s": 1024 * 20 / dt, "us_per_tick": dt * 1e6}
     for mode in ("recompute", "rolling"):                        # the same case end to end (LookBack.push, host in / out)

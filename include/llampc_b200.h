@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LLAMPC_ABI_VERSION 1
+#define LLAMPC_ABI_VERSION 2
 
 #define LLAMPC_E_ARG   (-1)  /* null pointer / non-positive size / size not supported       */
 #define LLAMPC_E_ALIGN (-2)  /* pointer or stride not 16-byte aligned                        */
@@ -119,6 +119,27 @@ int llampc_lookback_window_topk_peer_f32(const float* bank, int N, int Npad, con
                                          llampc_key_t* out, llampc_key_t* const* peer_bufs, int world,
                                          int rank, unsigned seq, llampc_stream_t stream);
 
+/* K1b  work-balanced look-back window (single history, any N and W): same scores and same selection as
+ * llampc_lookback_window_topk_f32, but the N x W candidate-steps are cut into equal contiguous ranges over exactly
+ * (SMs x resident CTAs) persistent CTAs, groups of 128 candidates whose window is shared between CTAs are combined in
+ * row order by the last CTA to arrive, and the top-K is finished by a tree of 32-way warp merges that overlaps the
+ * integration (one launch per tick, no per-launch list limit).
+ *   workspace  llampc_lookback_balanced_workspace_bytes(N, W) bytes of device memory, 16-byte aligned, ZEROED once by
+ *              the caller before the first call (the kernel leaves its counters at zero); one workspace per stream
+ *   fast_sin   non-zero: MUFU.SIN tyre sine (as split + 32 of llampc_lookback_window_f32)
+ *   K          0..LLAMPC_LIST_LEN;  out [LLAMPC_LIST_LEN + 1]: out[0] = arg-min key, out[1..K] = ascending top-K,
+ *              the remaining slots ~0ull
+ *   peer_bufs / world / rank / seq   as llampc_lookback_window_topk_peer_f32 (NVLink min-loc of out[0] inside the
+ *              launch); peer_bufs = NULL: single GPU
+ * Replaces evaluate_models_vectorized (llampc/mpc/evaluate_models_vectorized.py:4-23) + errors / mean / argmin /
+ * argsort[:K] of run_nmpc_orca_llampc_rt.py:349-360. */
+long long llampc_lookback_balanced_workspace_bytes(int N, int W);
+int llampc_lookback_window_balanced_f32(const float* bank, int N, int Npad, const float* hist, int W, double Ts,
+                                        float* avg_err, int idx_offset, int geom_shared, int fast_sin, int K,
+                                        void* workspace, unsigned long long workspace_bytes, llampc_key_t* out,
+                                        llampc_key_t* const* peer_bufs, int world, int rank, unsigned seq,
+                                        llampc_stream_t stream);
+
 /* K1r  rolling window, the reference's own bookkeeping (error_windows = np.roll(...); [:, -1] = errors; mean,
  * run_nmpc_orca_llampc_rt.py:349-358): one RK4 step per candidate for the newest transition (row32_h, HOST pointer,
  * passed as kernel parameter), error column `slot` of err_ring [W][Npad] replaced, window mean re-summed from the
@@ -198,6 +219,11 @@ typedef struct llampc_tick {
                                           `slot`, re-sum the ring; needs row32_h, cta_lists and Kt <= LLAMPC_LIST_LEN
                                           (the fp64 re-score still walks the whole hist64 ring);
                                        2: rolling mode while the window is filling: store the column, no decision */
+    void* workspace;                /* device scratch of llampc_lookback_balanced_workspace_bytes(N, W) bytes, zeroed once by
+                                       the caller, or NULL.  Non-NULL (with cta_lists, rolling = 0, 0 < Kt <=
+                                       LLAMPC_LIST_LEN) runs the work-balanced kernel K1b with the in-kernel tree merge
+                                       (llampc_lookback_window_balanced_f32) instead of K1 + list merge            */
+    unsigned long long workspace_bytes;
 } llampc_tick_t;
 
 int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream);

@@ -32,7 +32,8 @@ class Tick(C.Structure):
                 ("result", _vp), ("result_h", _vp), ("sync", _i), ("ticket", _vp), ("zero_copy", _i),
                 ("peer_bufs", _vp), ("peer_world", _i), ("peer_rank", _i), ("peer_seq", C.c_uint),
                 ("pending_seq", C.c_ulonglong), ("pending_words", _i),
-                ("err_ring", _vp), ("rolling", _i)]
+                ("err_ring", _vp), ("rolling", _i),
+                ("workspace", _vp), ("workspace_bytes", C.c_ulonglong)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/llampc_b200.h
@@ -46,6 +47,9 @@ PROTOTYPES = {
     "llampc_lookback_window_topk_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
     "llampc_lookback_window_topk_peer_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp,
                                                   _vp, _i, _i, C.c_uint, _vp]),
+    "llampc_lookback_balanced_workspace_bytes": (C.c_longlong, [_i, _i]),
+    "llampc_lookback_window_balanced_f32": (_i, [_vp, _i, _i, _vp, _i, _d, _vp, _i, _i, _i, _i, _vp, C.c_ulonglong, _vp,
+                                                 _vp, _i, _i, C.c_uint, _vp]),
     "llampc_lookback_rolling_multi_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
                                                _vp, _vp, _vp]),
     "llampc_lookback_rolling_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
@@ -93,7 +97,7 @@ def lib():
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(handle, name)           # AttributeError if the library lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if handle.llampc_abi_version() != 1:
+        if handle.llampc_abi_version() != 2:
             raise LlampcError("libllampc_b200.so ABI version mismatch")
         if handle.llampc_tick_sizeof() != C.sizeof(Tick):
             raise LlampcError("llampc_tick_t layout mismatch between _lib.py and libllampc_b200.so (rebuild the library)")

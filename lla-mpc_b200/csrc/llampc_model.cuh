@@ -261,6 +261,17 @@ struct HistRow { float4 q0, q1, q2, q3, q4; };
 // 1e-4-sized differences being squared).
 struct StepSize { float h, hh, h6, h6_lo, hh6, hh6_lo; };
 
+static inline StepSize make_step(double Ts) {
+    StepSize z;
+    z.h = (float)Ts;
+    z.hh = (float)(0.5 * Ts);
+    z.h6 = (float)(Ts / 6.0);
+    z.h6_lo = (float)(Ts / 6.0 - (double)z.h6);
+    z.hh6 = (float)(Ts * Ts / 6.0);
+    z.hh6_lo = (float)(Ts * Ts / 6.0 - (double)z.hh6);
+    return z;
+}
+
 template <bool GEOM_SHARED, bool MUFU_SIN>
 __device__ __forceinline__ float lookback_step(const Cand& p, const HistRow& r, const StepSize& z) {
     const float h = z.h, hh = z.hh;

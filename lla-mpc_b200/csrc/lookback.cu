@@ -5,13 +5,14 @@
 #include "llampc_common.cuh"
 #include "llampc_model.cuh"
 #include "llampc_model_f64.cuh"
+#include "lookback_select.cuh"
 #include <math.h>
 #include <stddef.h>
 #include <string.h>
+#include <stdlib.h>
 
 namespace llampc {
 
-constexpr int LB_THREADS = 128;
 constexpr int NUM_SMS = 148;
 
 // ---------------------------------------------------------------------------------------------------
@@ -19,80 +20,13 @@ constexpr int NUM_SMS = 148;
 // The W history rows (80 B each) are staged once per CTA with one TMA bulk copy; every warp then reads
 // the same row at the same time (shared-memory broadcast).  Thread (c, sy) integrates window rows
 // sy, sy+SY, ...; partial sums are combined in a fixed order so the result is run-to-run deterministic.
+// (CTA-level selection, NewRow, FusedMerge, PeerXchg: lookback_select.cuh)
 // ---------------------------------------------------------------------------------------------------
-#ifndef LLAMPC_LB_MIN_BLOCKS
-#define LLAMPC_LB_MIN_BLOCKS 6
-#endif
-// CTA-level selection shared by K1 and the rolling kernel: every key-holding warp (the first KW warps) sorts its
-// 32 keys (registers + shuffles), sorted runs are merged pairwise through shared memory; warp 0 ends up with the
-// CTA's 32 smallest keys in ascending lane order.  Lane 0 = block arg-min (one atomicMin per CTA); lanes 0..15 =
-// this CTA's list for the top-K merge.
-template <int KW>
-__device__ __forceinline__ void cta_select_emit(u64 key, u64* skeys, int v, u64* __restrict__ best_key,
-                                                u64* __restrict__ cta_lists) {
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (warp < KW) key = warp_sort_u64(key, lane);
-    if (KW == 4) {
-        if (warp == 1 || warp == 3) skeys[warp * 32 + lane] = key;
-        __syncthreads();
-        if (warp == 0 || warp == 2) key = warp_merge_low32(key, skeys[(warp + 1) * 32 + 31 - lane], lane);
-        __syncthreads();
-        if (warp == 2) skeys[lane] = key;
-        __syncthreads();
-        if (warp == 0) key = warp_merge_low32(key, skeys[31 - lane], lane);
-    } else if (KW == 2) {
-        if (warp == 1) skeys[lane] = key;
-        __syncthreads();
-        if (warp == 0) key = warp_merge_low32(key, skeys[31 - lane], lane);
-    }
-    if (warp == 0) {
-        if (cta_lists && lane < LLAMPC_LIST_LEN)
-            cta_lists[((size_t)v * gridDim.x + blockIdx.x) * LLAMPC_LIST_LEN + lane] = key;
-        if (lane == 0 && best_key && key != ~0ull) atomicMin(best_key + v, key);
-    }
-}
-
-// The newest history row can travel with the launch as a kernel parameter (80 bytes) instead of a separate
-// H2D copy: every CTA patches its shared-memory copy of ring slot `slot`, CTA 0 also stores it to the ring.
-struct NewRow { float v[LLAMPC_HIST_ROW]; int slot; };
-
-// Optional in-kernel finish of the top-K: the last CTA of a vehicle to retire (atomic ticket) merges the per-CTA
-// lists itself, so a tick is ONE launch.  Needs gridDim.x <= 128 * MERGE_LPT lists; K = 0 disables it.
-struct FusedMerge { unsigned* ticket; u64* out; int K; };
-
-// Optional multi-GPU min-loc fused into the same launch, over NVLink peer memory (no NCCL call on the path): every
-// rank owns a small symmetric buffer [2 parities][world][2] of u64 (key, sequence); the last CTA of rank r stores its
-// packed arg-min key into slot r of EVERY peer's buffer (remote 8-byte stores), then spins on its own buffer until all
-// `world` slots carry the current sequence number and reduces them.  Double-buffered by the parity of `seq`, which the
-// host increments identically on every rank each tick.  world = 0 disables it.
-struct PeerXchg { u64* const* peers; int world; int rank; unsigned seq; };
-
-__device__ __forceinline__ u64 peer_minloc(const PeerXchg& px, u64 my_key, int lane) {
-    const int parity = px.seq & 1;
-    u64 got = ~0ull;
-    if (lane < px.world) {
-        volatile u64* dst = px.peers[lane] + ((size_t)parity * px.world + px.rank) * 2;
-        dst[0] = my_key;
-        __threadfence_system();
-        dst[1] = (u64)px.seq;
-        volatile u64* src = px.peers[px.rank] + ((size_t)parity * px.world + lane) * 2;
-        const long long t0 = clock64();
-        bool ok = true;
-        while (src[1] != (u64)px.seq) {
-            if (clock64() - t0 > 2000000000ll) { ok = false; break; }     // ~1 s: a peer never arrived; poison the result
-            __nanosleep(64);
-        }
-        __threadfence_system();
-        got = ok ? src[0] : 0ull;
-    }
-    return warp_min_key(got);
-}
-
 template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
 __global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB_MIN_BLOCKS)
 lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
                        long hist_stride_floats, StepSize z, float* __restrict__ avg_err, u64* __restrict__ best_key,
-                       u64* __restrict__ cta_lists, int idx_offset, NewRow nr, FusedMerge fm, PeerXchg px) {
+                       u64* __restrict__ cta_lists, int idx_offset, NewRow nr, FusedMerge fm, PeerXchg px, TreeMerge tm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ u64 skeys[LB_THREADS];
@@ -155,6 +89,12 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
     if (sy == 0 && valid) {
         if (avg_err) avg_err[(size_t)v * N + cand] = err;
         key = pack_key(err, (unsigned)(idx_offset + cand));
+    }
+    if (tm.K > 0) {                                // uniform over the grid: tree finish (single history), one launch per tick
+        __shared__ u64 mrows[BAL_FAN][BAL_ROW_PAD];
+        key = cta_select32<(CPB >= 32 ? CPB / 32 : 1)>(key, skeys);
+        if (tid < 32) tree_merge(key, tid, (int)blockIdx.x, (int)gridDim.x, tm.K, tm.ws, mrows, tm.out, px);
+        return;
     }
     cta_select_emit<(CPB >= 32 ? CPB / 32 : 1)>(key, skeys, v, best_key, cta_lists);   // CPB < 32: part of warp 0 holds keys
     if (fm.K > 0) {                                // uniform over the grid
@@ -487,21 +427,11 @@ static int choose_split(int N, int W) {
     return best;
 }
 
-static StepSize make_step(double Ts) {
-    StepSize z;
-    z.h = (float)Ts;
-    z.hh = (float)(0.5 * Ts);
-    z.h6 = (float)(Ts / 6.0);
-    z.h6_lo = (float)(Ts / 6.0 - (double)z.h6);
-    z.hh6 = (float)(Ts * Ts / 6.0);
-    z.hh6_lo = (float)(Ts * Ts / 6.0 - (double)z.hh6);
-    return z;
-}
-
 template <int SY, bool GEOM, bool MUFU>
 static int launch_lookback(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
                            int hist_stride_rows, double Ts, float* avg_err, u64* best_key, u64* cta_lists,
-                           int idx_offset, const NewRow& nr, const FusedMerge& fm, const PeerXchg& px, cudaStream_t st) {
+                           int idx_offset, const NewRow& nr, const FusedMerge& fm, const PeerXchg& px, const TreeMerge& tm,
+                           cudaStream_t st) {
     auto kern = lookback_window_kernel<SY, GEOM, MUFU>;
     const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 : 0);
     if (smem > 48 * 1024) {
@@ -515,7 +445,7 @@ static int launch_lookback(const float* bank, int N, int Npad, const float* hist
     dim3 grid((N + CPB - 1) / CPB, n_vehicles);
     kern<<<grid, LB_THREADS, smem, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, hist, W,
                                          (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key, cta_lists,
-                                         idx_offset, nr, fm, px);
+                                         idx_offset, nr, fm, px, tm);
     return (int)cudaGetLastError();
 }
 
@@ -523,8 +453,9 @@ static int lookback_window_impl(const float* bank, int N, int Npad, const float*
                                 int hist_stride_rows, double Ts, float* avg_err, llampc_key_t* best_key,
                                 llampc_key_t* cta_lists, int idx_offset, int geom_shared, int split,
                                 const NewRow& nr, const FusedMerge& fm, llampc_stream_t stream,
-                                const PeerXchg& px = PeerXchg{nullptr, 0, 0, 0}) {
-    if (!bank || !hist || (!best_key && !cta_lists && !avg_err) || N <= 0 || Npad < N || n_vehicles <= 0 || hist_stride_rows < W) return LLAMPC_E_ARG;
+                                const PeerXchg& px = PeerXchg{nullptr, 0, 0, 0},
+                                const TreeMerge& tm = TreeMerge{{nullptr, nullptr, nullptr, nullptr, nullptr}, nullptr, 0}) {
+    if (!bank || !hist || (!best_key && !cta_lists && !avg_err && tm.K <= 0) || N <= 0 || Npad < N || n_vehicles <= 0 || hist_stride_rows < W) return LLAMPC_E_ARG;
     if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
     if (!aligned16(bank) || !aligned16(hist) || (hist_stride_rows * LLAMPC_HIST_ROW * 4) % 16) return LLAMPC_E_ALIGN;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
@@ -534,10 +465,10 @@ static int lookback_window_impl(const float* bank, int N, int Npad, const float*
     if (split > W) split = 1;
 #define LB_CASE(SYV)                                                                                                  \
     case SYV:                                                                                                         \
-        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, st)   \
-                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, st); \
-        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, st)            \
-                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, st);
+        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, st)   \
+                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, st); \
+        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, st)            \
+                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, st);
     switch (split) {
         LB_CASE(1)
         LB_CASE(2)
@@ -762,6 +693,58 @@ extern "C" int llampc_forces_batch_f32(const float* bank, int N, int Npad, const
     return (int)cudaGetLastError();
 }
 
+// One-launch tick with the tree finish: K1b (persistent warp tasks) when K1's tiling cannot fill the SMs (fewer CTAs
+// than SMs: small banks, or few candidates with a long window), else K1 with the tree merge.
+static int lookback_tree_dispatch(const float* bank, int N, int Npad, const float* hist, int W, double Ts, float* avg_err,
+                                  int idx_offset, int geom_shared, int split, int K, void* workspace,
+                                  unsigned long long workspace_bytes, llampc_key_t* out, const NewRow& nr,
+                                  const PeerXchg& px, llampc_stream_t stream) {
+    if (!workspace || !out) return LLAMPC_E_ARG;
+    if (K <= 0 || K > LLAMPC_LIST_LEN) return LLAMPC_E_RANGE;
+    const int n_lists = llampc_lookback_num_lists(N, W, split);
+    if (n_lists <= 0) return n_lists ? n_lists : LLAMPC_E_ARG;
+    // K1b pays off only where K1 leaves SMs idle AND every K1 thread has a long serial walk (measured on B200: 4,096
+    // candidates x 1,024 rows 115 us against 133 us; everywhere else K1 + tree is equal or faster)
+    int sy = split & 31;
+    if (sy == 0) sy = choose_split(N, W);
+    if (sy > W) sy = 1;
+    const char* force = getenv("LLAMPC_TREE_KERNEL");            // experiments: "k1" / "k1b"
+    const bool k1b = force ? (force[0] == 'k' && force[1] == '1' && force[2] == 'b')
+                           : (n_lists < device_sms() && (W + sy - 1) / sy >= 64);
+    if (k1b)
+        return lookback_balanced_launch(bank, N, Npad, hist, W, Ts, avg_err, idx_offset, geom_shared, (split & 32) != 0, K,
+                                        workspace, workspace_bytes, out, nr, px, static_cast<cudaStream_t>(stream));
+    if (reinterpret_cast<uintptr_t>(workspace) & 15u) return LLAMPC_E_ALIGN;
+    const TreeLayout lay = tree_layout(N, 0);
+    if (workspace_bytes < lay.bytes) return LLAMPC_E_ARG;
+    TreeMerge tm = {tree_workspace(static_cast<unsigned char*>(workspace), lay), out, K};
+    FusedMerge none = {nullptr, nullptr, 0};
+    return lookback_window_impl(bank, N, Npad, hist, W, 1, W, Ts, avg_err, nullptr, nullptr, idx_offset, geom_shared, split,
+                                nr, none, stream, px, tm);
+}
+
+extern "C" long long llampc_lookback_balanced_workspace_bytes(int N, int W) {
+    if (N <= 0 || W <= 0) return LLAMPC_E_ARG;
+    if (W > LLAMPC_MAX_W) return LLAMPC_E_RANGE;
+    return lookback_balanced_workspace_bytes(N, W);
+}
+
+extern "C" int llampc_lookback_window_balanced_f32(const float* bank, int N, int Npad, const float* hist, int W, double Ts,
+                                                   float* avg_err, int idx_offset, int geom_shared, int fast_sin, int K,
+                                                   void* workspace, unsigned long long workspace_bytes, llampc_key_t* out,
+                                                   llampc_key_t* const* peer_bufs, int world, int rank, unsigned seq,
+                                                   llampc_stream_t stream) {
+    NewRow nr;
+    nr.slot = -1;
+    PeerXchg px = {nullptr, 0, 0, 0};
+    if (peer_bufs) {
+        if (world < 2 || world > 32 || rank < 0 || rank >= world) return LLAMPC_E_RANGE;
+        px.peers = peer_bufs; px.world = world; px.rank = rank; px.seq = seq;
+    }
+    return lookback_tree_dispatch(bank, N, Npad, hist, W, Ts, avg_err, idx_offset, geom_shared, fast_sin ? 32 : 0, K,
+                                  workspace, workspace_bytes, out, nr, px, stream);
+}
+
 extern "C" int llampc_lookback_finish(llampc_tick_t* t, llampc_stream_t stream);
 
 extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
@@ -800,6 +783,12 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
             rc = llampc_topk_merge_lists(t->cta_lists, n_lists_r, 1, Kt, t->best_key, keys, stream);
             if (rc) return rc;
         }
+    } else if (fused && t->workspace && Kt > 0) {
+        // K1 (or K1b for small grids) with the tree merge, one launch; writes keys[0..LIST_LEN] itself (best_key stays armed)
+        rc = lookback_tree_dispatch(t->bank, t->N, t->Npad, t->hist, t->W, t->Ts, t->avg_err, t->idx_offset,
+                                    t->geom_shared, t->split, Kt, t->workspace, t->workspace_bytes, keys, nr,
+                                    PeerXchg{nullptr, 0, 0, 0}, stream);
+        if (rc) return rc;
     } else if (fused) {
         // K1 (block arg-min + per-CTA sorted lists) -> list merge (also moves best_key to keys[0] and re-arms it)
         const int n_lists = llampc_lookback_num_lists(t->N, t->W, t->split);

@@ -44,12 +44,15 @@ class LookBack:
              steps, stateless w.r.t. the bank); "rolling": the reference's own bookkeeping (rt.py:352-354) -- only the
              newest transition is integrated and its error column replaces the oldest one in a device-resident
              (W, N) ring, the window mean is re-summed (N steps + N*W*4 bytes per tick)
+    balanced recompute mode with max(K, refine) <= 16: run the work-balanced kernel K1b (equal contiguous ranges of
+             (candidate group, window row) units over exactly SMs x resident CTAs persistent CTAs, top-K finished by an
+             in-kernel tree of warp merges) instead of K1 + list merge.  Default: on (LLAMPC_BALANCED=0 disables).
     idx_offset / group   multi-GPU: this rank's bank is the slice starting at global index idx_offset;
              `group` is a torch.distributed process group (None = single GPU)
     """
 
     def __init__(self, bank_params, W, Ts=0.02, K=10, refine=16, device=None, idx_offset=0, group=None, split=0,
-                 mode="recompute", fast_sin=None):
+                 mode="recompute", fast_sin=None, balanced=None):
         torch = _lib.require_cuda()
         self.torch = torch
         self.bank = bank_params if isinstance(bank_params, ModelBank) else ModelBank(bank_params, device)
@@ -63,6 +66,8 @@ class LookBack:
         if fast_sin is None:
             fast_sin = os.environ.get("LLAMPC_FAST_SIN", "1") == "1"
         self.fast_sin = bool(fast_sin)
+        if balanced is None:
+            balanced = os.environ.get("LLAMPC_BALANCED", "1") == "1"
         # bit 5 (+32) of `split` selects the MUFU.SIN tyre sine in K1 (include/llampc_b200.h)
         self.idx_offset, self.group, self.split = int(idx_offset), group, int(split) | (32 if self.fast_sin else 0)
         if mode not in ("recompute", "rolling"):
@@ -139,6 +144,14 @@ class LookBack:
             t.peer_bufs, t.peer_world, t.peer_rank = self._peer.peer_ptrs.data_ptr(), self._peer.world, self._peer.rank
         if self.rolling:
             t.err_ring, t.rolling = self.err_ring.data_ptr(), 1
+        # K1b: work-balanced persistent kernel with the in-kernel tree merge (one launch per tick)
+        self.balanced = bool(balanced) and self.fused and not self.rolling and self.Kt > 0
+        if self.balanced:
+            nbytes = int(L.llampc_lookback_balanced_workspace_bytes(N, self.W))
+            if nbytes <= 0:
+                _lib.check(nbytes if nbytes > -1000 else -1000 - nbytes, "llampc_lookback_balanced_workspace_bytes")
+            self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+            t.workspace, t.workspace_bytes = self.workspace.data_ptr(), nbytes
         self._tick = t
         self._tick_ref = C.byref(t)
         self._L = L

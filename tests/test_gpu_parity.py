@@ -566,6 +566,74 @@ def test_one_launch_tick_matches_two_launch(history):
     assert (outs[0][:, 0] == outs[0][:, 1]).all()                 # arg-min key == first of the top-K
 
 
+@pytest.mark.parametrize("kernel", ["k1", "k1b"])
+@pytest.mark.parametrize("N,W,K,t_end", [(1, 1, 10, 600), (5, 3, 10, 100), (300, 7, 16, 600), (777, 1, 10, 1100),
+                                         (3000, 50, 10, 1600), (5000, 10, 16, 600), (2049, 33, 1, 900),
+                                         (4096, 256, 10, 1200), (40000, 20, 10, 600)])
+def test_tree_tick_kernels_match_oracle(history, monkeypatch, kernel, N, W, K, t_end):
+    """llampc_lookback_window_balanced_f32 (one launch: K1 with the tree merge, or the persistent warp-task kernel
+    K1b) at ragged sizes: scores within tolerance of the float64 oracle, out[0] == out[1], the top-K is exactly the K
+    smallest (score, index) pairs of the kernel's own scores, and a second launch on the same workspace (self-
+    resetting counters) reproduces the first bit for bit."""
+    import torch
+    from llampc_b200 import _lib
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    monkeypatch.setenv("LLAMPC_TREE_KERNEL", kernel)
+    L = _lib.lib()
+    bank = orc.make_bank(N, seed=40 + N % 7, variation=orc.RT_VARIATION + (("mass", 0.15),))
+    lb = LookBack(bank, W=W, Ts=Ts, K=min(K, 10), refine=0)
+    assert lb.balanced
+    ts = np.arange(t_end - W + 1, t_end + 1)
+    lb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
+    st = torch.cuda.current_stream().cuda_stream
+    out = torch.zeros(_lib.LIST_LEN + 1, dtype=torch.int64, device="cuda")
+    avg = torch.empty(N, dtype=torch.float32, device="cuda")
+    res = []
+    for _ in range(3):
+        out.zero_()
+        _lib.check(L.llampc_lookback_window_balanced_f32(lb.bank.packed.data_ptr(), N, lb.bank.Npad, lb.hist.data_ptr(), W, Ts,
+                                                         avg.data_ptr(), 0, int(lb.bank.geom_shared), 1, K,
+                                                         lb.workspace.data_ptr(), lb.workspace.numel(), out.data_ptr(),
+                                                         None, 0, 0, 0, st))
+        res.append((out.cpu().numpy().view(np.uint64).copy(), avg.cpu().numpy().copy()))
+    keys, a = res[0]
+    for k2, a2 in res[1:]:
+        assert np.array_equal(keys, k2) and np.array_equal(a, a2)
+    ref = np.mean(orc.window_errors(bank, S, U, t_end, W, Ts), axis=1)
+    _assert_scores(a.astype(np.float64), ref, "%s N=%d W=%d" % (kernel, N, W))
+    own = np.sort((a.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.arange(N, dtype=np.uint64))
+    n = min(K, N)
+    assert keys[0] == own[0]
+    assert np.array_equal(keys[1:1 + n], own[:n])
+    assert (keys[1 + n:] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+    # and through the public object (tick path)
+    best, topk, _ = lb.evaluate()
+    order = np.argsort(a, kind="stable")
+    assert best == int(own[0] & np.uint64(0xFFFFFFFF))
+    assert list(topk) == [int(k & np.uint64(0xFFFFFFFF)) for k in own[:min(lb.K, N)]]
+    del order
+
+
+def test_tree_tick_equals_two_launch_tick(history, monkeypatch):
+    """LookBack with the tree tick (default) and with K1 + list merge (balanced=False) return the same decisions and
+    bit-identical fp32 scores over a replay of the recorded loop (K1 arithmetic is shared)."""
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    bank = orc.make_bank(4096, seed=11)
+    a = LookBack(bank, W=10, Ts=Ts, K=10, refine=16, balanced=True)
+    b = LookBack(bank, W=10, Ts=Ts, K=10, refine=16, balanced=False)
+    assert a.balanced and not b.balanced
+    for t in range(500, 560):
+        ra = a.push(S[:, t], U[:, t], S[:, t + 1])
+        rb = b.push(S[:, t], U[:, t], S[:, t + 1])
+        if ra[0] is None:
+            assert rb[0] is None
+            continue
+        assert ra[0] == rb[0] and list(ra[1]) == list(rb[1]) and ra[2] == rb[2]
+        assert np.array_equal(a.avg_errors(), b.avg_errors())
+
+
 def test_large_window_and_zero_copy_paths(history, monkeypatch):
     """W = 200 (the reference's largest ablation window, plot_banks.py:71) and W = 1,024 (the compiled limit: 80 KB of
     history staged per CTA); the result hand-off with and without the zero-copy path must agree."""

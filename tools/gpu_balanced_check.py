@@ -1,0 +1,116 @@
+"""GPU diagnostic (run under gpurun): K1b (work-balanced kernel + tree merge) against K1 + list merge on the same
+inputs -- scores, arg-min and top-K agreement, self-resetting counters over repeated launches, and device timings
+(L2 flushed between launches) for several (N, W).  Prints one line per case."""
+import os
+import sys
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from llampc_b200 import _lib                       # noqa: E402
+from llampc_b200.mpc import LookBack                # noqa: E402
+from oracle import llampc_oracle as orc             # noqa: E402
+
+g = np.load(os.path.join(ROOT, "tests", "golden", "ethz_history.npz"))
+S, U, Ts = g["states"], g["inputs"], float(g["Ts"])
+L = _lib.lib()
+flush = None
+
+
+def timed(fn, reps=40):
+    global flush
+    if flush is None:
+        flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(5):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        flush.fill_(1)
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return float(np.median([a.elapsed_time(b) for a, b in evs])) * 1e3
+
+
+def case(N, W, t_end=600, K=10, check_oracle=False, kernel="k1"):
+    var = orc.RT_VARIATION + (("mass", 0.15),)
+    bank = orc.make_bank(N, 1, variation=var)
+    lb = LookBack(bank, W=W, Ts=Ts, K=K, refine=0, balanced=True)
+    ts = np.arange(t_end - W + 1, t_end + 1)
+    lb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
+    st = torch.cuda.current_stream().cuda_stream
+    dev = lb.bank.device
+    out_b = torch.zeros(_lib.LIST_LEN + 1, dtype=torch.int64, device=dev)
+    out_l = torch.zeros(_lib.LIST_LEN + 1, dtype=torch.int64, device=dev)
+    avg_b = torch.empty(N, dtype=torch.float32, device=dev)
+    avg_l = torch.empty(N, dtype=torch.float32, device=dev)
+    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
+    n_lists = L.llampc_lookback_num_lists(N, W, lb.split)
+
+    def bal():
+        rc = L.llampc_lookback_window_balanced_f32(lb.bank.packed.data_ptr(), N, lb.bank.Npad, lb.hist.data_ptr(), W, Ts,
+                                                   avg_b.data_ptr(), 0, int(lb.bank.geom_shared), 1, K,
+                                                   lb.workspace.data_ptr(), lb.workspace.numel(), out_b.data_ptr(),
+                                                   None, 0, 0, 0, st)
+        _lib.check(rc, "balanced")
+
+    def leg():
+        rc = L.llampc_lookback_window_topk_f32(lb.bank.packed.data_ptr(), N, lb.bank.Npad, lb.hist.data_ptr(), W, 1, W, Ts,
+                                               avg_l.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), 0,
+                                               int(lb.bank.geom_shared), lb.split, K, ticket.data_ptr(), out_l.data_ptr(), st)
+        _lib.check(rc, "legacy")
+
+    os.environ["LLAMPC_TREE_KERNEL"] = kernel
+    bal()
+    leg()
+    torch.cuda.synchronize()
+    kb = out_b.cpu().numpy().view(np.uint64)
+    kl = out_l.cpu().numpy().view(np.uint64)
+    ab, al = avg_b.cpu().numpy(), avg_l.cpu().numpy()
+    # the balanced top-K must be exactly the K smallest (score, index) pairs of its own scores
+    keys = (ab.view(np.uint32).astype(np.uint64) << np.uint64(32)) | np.arange(N, dtype=np.uint64)
+    want = np.sort(keys)[:K]
+    ok_self = bool(np.array_equal(kb[1:1 + min(K, N)], want[:min(K, N)])) and kb[0] == want[0]
+    rel = float(np.max(np.abs(ab - al) / al))
+    same_idx = bool(np.array_equal(kb[1:1 + min(K, N)] & np.uint64(0xFFFFFFFF), kl[1:1 + min(K, N)] & np.uint64(0xFFFFFFFF)))
+    # repeated launches: counters reset themselves, results are bit-identical
+    rep_ok = True
+    for _ in range(20):
+        bal()
+    torch.cuda.synchronize()
+    rep_ok = bool(np.array_equal(out_b.cpu().numpy().view(np.uint64), kb)) and bool(np.array_equal(avg_b.cpu().numpy(), ab))
+    ws_zero = int(lb.workspace[lb.workspace.numel() // 2:].view(torch.int32).abs().max().item()) if False else -1
+    msg = ""
+    if check_oracle:
+        ref = np.mean(orc.window_errors(bank, S, U, t_end, W, Ts), axis=1)
+        relo = np.abs(ab.astype(np.float64) - ref) / ref
+        rbest, rtopk = orc.select(ref, K)
+        msg = " | oracle rel max %.2e argmin %s topk %s" % (relo.max(), int(kb[0] & np.uint64(0xFFFFFFFF)) == rbest,
+                                                             list((kb[1:1 + K] & np.uint64(0xFFFFFFFF)).astype(np.int64)) == list(rtopk))
+    tb, tl = timed(bal), timed(leg)
+    print("%-3s N=%8d W=%4d K=%2d | self-consistent %s same idx as K1 %s repeat %s | max rel diff vs K1 %.1e | tree %7.1f us (%.3e steps/s)  "
+          "K1+merge %7.1f us (lists %d)%s" % (kernel, N, W, K, ok_self, same_idx, rep_ok, rel, tb, N * W / tb * 1e6, tl, n_lists, msg),
+          flush=True)
+
+
+if __name__ == "__main__":
+    print(torch.cuda.get_device_name(0))
+    for kern in ("k1", "k1b"):
+        case(65536, 50, check_oracle=True, kernel=kern)
+        case(1024, 20, check_oracle=True, kernel=kern)
+        case(1, 1, kernel=kern)
+        case(5, 3, kernel=kern)
+        case(300, 7, kernel=kern)
+        case(777, 1, kernel=kern)
+        case(3000, 50, kernel=kern)
+        case(5000, 10, K=16, kernel=kern)
+        case(4096, 1024, t_end=1200, kernel=kern)
+        case(20000, 10, kernel=kern)
+        case(30000, 200, t_end=900, kernel=kern)
+        case(131072, 50, kernel=kern)
+        case(1048576, 50, kernel=kern)
+        case(65536, 50, K=16, kernel=kern)
