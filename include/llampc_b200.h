@@ -119,18 +119,24 @@ int llampc_lookback_window_topk_peer_f32(const float* bank, int N, int Npad, con
                                          llampc_key_t* out, llampc_key_t* const* peer_bufs, int world,
                                          int rank, unsigned seq, llampc_stream_t stream);
 
-/* K1b  work-balanced look-back window (single history, any N and W): same scores and same selection as
- * llampc_lookback_window_topk_f32, but the N x W candidate-steps are cut into equal contiguous ranges over exactly
- * (SMs x resident CTAs) persistent CTAs, groups of 128 candidates whose window is shared between CTAs are combined in
- * row order by the last CTA to arrive, and the top-K is finished by a tree of 32-way warp merges that overlaps the
- * integration (one launch per tick, no per-launch list limit).
+/* One-launch look-back tick (single history, any N and W): same scores and same selection as
+ * llampc_lookback_window_topk_f32, with the top-K finished INSIDE the launch by a tree of 32-way warp merges: warp 0 of
+ * every CTA publishes the CTA's 16 smallest keys, the last arrival of every 32 lists merges them (heads in registers,
+ * REDUX minima) and climbs one level, the warp that produces the root writes `out`.  The merges overlap the
+ * integration; the serial tail after the last RK4 step is the two or three merges on the path to the root instead of
+ * one CTA walking every list, and there is no list-count limit (1,048,576 candidates: one launch).
+ * The kernel underneath is chosen from the shape: K1 (llampc_lookback_window_f32's kernel, bit-identical scores), or
+ * K1b when K1's tiling would leave SMs idle while every thread walks a long window (fewer CTAs than SMs and >= 64 rows
+ * per thread): K1b runs persistent CTAs whose warps pull warp-tasks (32 candidates x R window rows) from an atomic
+ * counter; the row chunks of a warp-group are combined in row order by the last task to arrive (deterministic).
  *   workspace  llampc_lookback_balanced_workspace_bytes(N, W) bytes of device memory, 16-byte aligned, ZEROED once by
- *              the caller before the first call (the kernel leaves its counters at zero); one workspace per stream
+ *              the caller before the first call (the kernels leave their counters at zero; the counter offsets depend
+ *              on N only, so W may change between calls); one workspace per stream
  *   fast_sin   non-zero: MUFU.SIN tyre sine (as split + 32 of llampc_lookback_window_f32)
- *   K          0..LLAMPC_LIST_LEN;  out [LLAMPC_LIST_LEN + 1]: out[0] = arg-min key, out[1..K] = ascending top-K,
+ *   K          1..LLAMPC_LIST_LEN;  out [LLAMPC_LIST_LEN + 1]: out[0] = arg-min key, out[1..K] = ascending top-K,
  *              the remaining slots ~0ull
- *   peer_bufs / world / rank / seq   as llampc_lookback_window_topk_peer_f32 (NVLink min-loc of out[0] inside the
- *              launch); peer_bufs = NULL: single GPU
+ *   peer_bufs / world / rank / seq   as llampc_lookback_window_topk_peer_f32 (NVLink min-loc of out[0], done by the
+ *              root warp inside the launch); peer_bufs = NULL: single GPU
  * Replaces evaluate_models_vectorized (llampc/mpc/evaluate_models_vectorized.py:4-23) + errors / mean / argmin /
  * argsort[:K] of run_nmpc_orca_llampc_rt.py:349-360. */
 long long llampc_lookback_balanced_workspace_bytes(int N, int W);
@@ -221,7 +227,7 @@ typedef struct llampc_tick {
                                        2: rolling mode while the window is filling: store the column, no decision */
     void* workspace;                /* device scratch of llampc_lookback_balanced_workspace_bytes(N, W) bytes, zeroed once by
                                        the caller, or NULL.  Non-NULL (with cta_lists, rolling = 0, 0 < Kt <=
-                                       LLAMPC_LIST_LEN) runs the work-balanced kernel K1b with the in-kernel tree merge
+                                       LLAMPC_LIST_LEN) runs the one-launch tick with the in-kernel tree merge
                                        (llampc_lookback_window_balanced_f32) instead of K1 + list merge            */
     unsigned long long workspace_bytes;
 } llampc_tick_t;

@@ -5,6 +5,7 @@
 #include "llampc_common.cuh"
 #include "llampc_model.cuh"
 #include "llampc_model_f64.cuh"
+#include "llampc_packed.cuh"
 #include "lookback_select.cuh"
 #include <math.h>
 #include <stddef.h>
@@ -111,6 +112,136 @@ lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const f
                                        best_key ? best_key + v : nullptr, outv, msm);
         if (tid == 0) fm.ticket[v] = 0;            // ready for the next launch on the same stream
         if (px.world > 1 && tid < 32) {            // warp 0: min-loc across the GPUs of the box, in this launch
+            __syncwarp();
+            const u64 mine = __shfl_sync(0xffffffffu, tid == 0 ? *reinterpret_cast<volatile u64*>(outv) : 0ull, 0);
+            const u64 g = peer_minloc(px, mine, tid);
+            if (tid == 0) outv[0] = g;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K1p.  K1 with TWO candidates per thread in packed f32x2 arithmetic (llampc_packed.cuh): FFMA2 / FMUL2 / FADD2 carry
+// both candidates through one issue slot, the history-row values are broadcast scalar operands.  Same tiling as K1
+// with twice the candidates per CTA: block = 128 threads = (128/SY candidate pairs) x (SY window splits); thread
+// (c, sy) owns candidates base + c and base + 128/SY + c (both bank loads stay coalesced).
+// ---------------------------------------------------------------------------------------------------
+#ifndef LLAMPC_LB2_MIN_BLOCKS
+#define LLAMPC_LB2_MIN_BLOCKS 4
+#endif
+template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
+__global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB2_MIN_BLOCKS)
+lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
+                        long hist_stride_floats, StepSize z, float* __restrict__ avg_err, u64* __restrict__ best_key,
+                        u64* __restrict__ cta_lists, int idx_offset, NewRow nr, FusedMerge fm, PeerXchg px, TreeMerge tm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ u64 skeys[LB_THREADS];
+    float4* srow = reinterpret_cast<float4*>(smem_raw);
+    float* spart = reinterpret_cast<float*>(smem_raw + (size_t)W * (LLAMPC_HIST_ROW * 4));
+
+    constexpr int CPB = LB_THREADS / SY;           // candidate pairs per CTA
+    const int tid = threadIdx.x;
+    const int v = blockIdx.y;
+    const unsigned bytes = (unsigned)W * (LLAMPC_HIST_ROW * 4);
+
+    if (tid == 0) {
+        mbar_init(&mbar, 1);
+        mbar_expect_tx(&mbar, bytes);
+        tma_bulk_g2s(srow, hist + (size_t)v * hist_stride_floats, bytes, &mbar);
+    }
+    __syncthreads();
+
+    const int c = tid % CPB, sy = tid / CPB;
+    const int cand0 = blockIdx.x * (2 * CPB) + c, cand1 = cand0 + CPB;
+    const bool valid0 = cand0 < N, valid1 = cand1 < N;
+    const int i0 = valid0 ? cand0 : N - 1, i1 = valid1 ? cand1 : N - 1;
+    const Cand2 p = load_cand2(bank, Npad, i0, i1);              // overlaps the bulk copy
+
+    mbar_wait(&mbar, 0);
+    if (nr.slot >= 0) {                            // uniform over the grid
+        if (tid < LLAMPC_HIST_ROW / 4) {
+            const float4 q = make_float4(nr.v[4 * tid], nr.v[4 * tid + 1], nr.v[4 * tid + 2], nr.v[4 * tid + 3]);
+            srow[nr.slot * 5 + tid] = q;
+            if (blockIdx.x == 0 && blockIdx.y == 0)
+                reinterpret_cast<float4*>(const_cast<float*>(hist))[nr.slot * 5 + tid] = q;
+        }
+        __syncthreads();
+    }
+
+    float acc0 = 0.0f, acc1 = 0.0f;
+    for (int w = sy; w < W; w += SY) {
+        HistRow r;
+        r.q0 = srow[w * 5 + 0];
+        r.q1 = srow[w * 5 + 1];
+        r.q2 = srow[w * 5 + 2];
+        r.q3 = srow[w * 5 + 3];
+        r.q4 = srow[w * 5 + 4];
+        bool ok0, ok1;
+        const F2 e = lookback_step_fast2<GEOM_SHARED, MUFU_SIN>(p, r, z, ok0, ok1);
+        float e0, e1;
+        up(e, e0, e1);
+        if (!ok0) e0 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i0, srow + w * 5, z);
+        if (!ok1) e1 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i1, srow + w * 5, z);
+        acc0 += e0;
+        acc1 += e1;
+    }
+
+    if (SY > 1) {
+        spart[(sy * 2) * CPB + c] = acc0;
+        spart[(sy * 2 + 1) * CPB + c] = acc1;
+        __syncthreads();
+        if (sy == 0) {
+#pragma unroll
+            for (int j = 1; j < SY; ++j) {
+                acc0 += spart[(j * 2) * CPB + c];
+                acc1 += spart[(j * 2 + 1) * CPB + c];
+            }
+        }
+    }
+    // errors = mean over the 4 scored states (rt.py:349); avg = mean over the window (rt.py:357)
+    const float scale = 0.25f / (float)W;
+    const float err0 = acc0 * scale, err1 = acc1 * scale;
+    u64 k0 = ~0ull, k1 = ~0ull;
+    if (sy == 0) {
+        if (valid0) {
+            if (avg_err) avg_err[(size_t)v * N + cand0] = err0;
+            k0 = pack_key(err0, (unsigned)(idx_offset + cand0));
+        }
+        if (valid1) {
+            if (avg_err) avg_err[(size_t)v * N + cand1] = err1;
+            k1 = pack_key(err1, (unsigned)(idx_offset + cand1));
+        }
+    }
+    constexpr int KW = CPB >= 32 ? CPB / 32 : 1;   // CPB < 32: part of warp 0 holds keys
+    u64 key = ~0ull;
+    if ((tid >> 5) < KW) {                         // two keys per lane -> the 32 smallest of the warp's 64
+        const int lane = tid & 31;
+        k0 = warp_sort_u64(k0, lane);
+        k1 = warp_sort_u64(k1, lane);
+        key = warp_merge_low32(k0, __shfl_sync(0xffffffffu, k1, 31 - lane), lane);
+    }
+    if (tm.K > 0) {                                // uniform over the grid: tree finish (single history), one launch per tick
+        __shared__ u64 mrows[BAL_FAN][BAL_ROW_PAD];
+        key = cta_select32<KW, true>(key, skeys);
+        if (tid < 32) tree_merge(key, tid, (int)blockIdx.x, (int)gridDim.x, tm.K, tm.ws, mrows, tm.out, px);
+        return;
+    }
+    cta_select_emit<KW, true>(key, skeys, v, best_key, cta_lists);
+    if (fm.K > 0) {                                // uniform over the grid
+        __shared__ bool is_last;
+        __shared__ MergeSmem<LB_THREADS> msm;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) is_last = atomicAdd(fm.ticket + v, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        u64* outv = fm.out + (size_t)v * (LLAMPC_LIST_LEN + 1);
+        merge_lists_device<LB_THREADS>(cta_lists + (size_t)v * gridDim.x * LLAMPC_LIST_LEN, gridDim.x, fm.K,
+                                       best_key ? best_key + v : nullptr, outv, msm);
+        if (tid == 0) fm.ticket[v] = 0;
+        if (px.world > 1 && tid < 32) {
             __syncwarp();
             const u64 mine = __shfl_sync(0xffffffffu, tid == 0 ? *reinterpret_cast<volatile u64*>(outv) : 0ull, 0);
             const u64 g = peer_minloc(px, mine, tid);
@@ -413,13 +544,24 @@ using namespace llampc;
 // ===================================================================================================
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// K1p (two candidates per thread, packed f32x2) is the default; LLAMPC_K1_PACKED=0 selects the scalar K1.
+static bool k1_packed() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LLAMPC_K1_PACKED");
+        v = (e && e[0] == '0') ? 0 : 1;
+    }
+    return v != 0;
+}
+static inline int k1_cands_per_cta() { return k1_packed() ? 2 * LB_THREADS : LB_THREADS; }
+
 static int choose_split(int N, int W) {
     // SM time ~ (CTAs on the busiest SM) x (rows per thread) while the FMA pipe is the limiter.
     int best = 1;
     long best_cost = -1;
     for (int sy = 1; sy <= 16; sy *= 2) {          // 8 and 16 only pay off for banks too small to fill the GPU
         if (sy > W) break;
-        long ctas = ((long)N * sy + LB_THREADS - 1) / LB_THREADS;
+        long ctas = ((long)N * sy + k1_cands_per_cta() - 1) / k1_cands_per_cta();
         long cost = ((ctas + NUM_SMS - 1) / NUM_SMS) * ((W + sy - 1) / sy);
         // a finer split must win by > 3 %: it doubles the number of per-CTA lists the top-K merge has to read
         if (best_cost < 0 || cost * 100 < best_cost * 97) { best_cost = cost; best = sy; }
@@ -432,8 +574,9 @@ static int launch_lookback(const float* bank, int N, int Npad, const float* hist
                            int hist_stride_rows, double Ts, float* avg_err, u64* best_key, u64* cta_lists,
                            int idx_offset, const NewRow& nr, const FusedMerge& fm, const PeerXchg& px, const TreeMerge& tm,
                            cudaStream_t st) {
-    auto kern = lookback_window_kernel<SY, GEOM, MUFU>;
-    const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 : 0);
+    const bool packed = k1_packed();
+    auto kern = packed ? lookback_window2_kernel<SY, GEOM, MUFU> : lookback_window_kernel<SY, GEOM, MUFU>;
+    const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 * (packed ? 2 : 1) : 0);
     if (smem > 48 * 1024) {
         static bool raised = false;              // idempotent attribute, benign if two threads race
         if (!raised) {
@@ -441,7 +584,7 @@ static int launch_lookback(const float* bank, int N, int Npad, const float* hist
             raised = true;
         }
     }
-    constexpr int CPB = LB_THREADS / SY;
+    const int CPB = (packed ? 2 * LB_THREADS : LB_THREADS) / SY;
     dim3 grid((N + CPB - 1) / CPB, n_vehicles);
     kern<<<grid, LB_THREADS, smem, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, hist, W,
                                          (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key, cta_lists,
@@ -599,7 +742,7 @@ extern "C" int llampc_lookback_num_lists(int N, int W, int split) {
     if (split == 0) split = choose_split(N, W);
     if (split > W) split = 1;
     if (split != 1 && split != 2 && split != 4 && split != 8 && split != 16) return LLAMPC_E_ARG;
-    const int cpb = LB_THREADS / split;
+    const int cpb = k1_cands_per_cta() / split;
     return (N + cpb - 1) / cpb;
 }
 

@@ -15,10 +15,10 @@ constexpr int LB_THREADS = 128;
 // CTA-level selection: every key-holding warp (the first KW warps) sorts its 32 keys (registers + shuffles), sorted
 // runs are merged pairwise through shared memory; warp 0 ends up with the CTA's 32 smallest keys in ascending lane
 // order (the return value is meaningful in warp 0 only).  skeys: LB_THREADS keys of shared memory.
-template <int KW>
+template <int KW, bool PRESORTED = false>
 __device__ __forceinline__ u64 cta_select32(u64 key, u64* skeys) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    if (warp < KW) key = warp_sort_u64(key, lane);
+    if (!PRESORTED && warp < KW) key = warp_sort_u64(key, lane);
     if (KW == 4) {
         if (warp == 1 || warp == 3) skeys[warp * 32 + lane] = key;
         __syncthreads();
@@ -36,10 +36,10 @@ __device__ __forceinline__ u64 cta_select32(u64 key, u64* skeys) {
 }
 
 // K1 / K1r: lane 0 of warp 0 = block arg-min (one atomicMin per CTA); lanes 0..15 = this CTA's list for the top-K merge.
-template <int KW>
+template <int KW, bool PRESORTED = false>
 __device__ __forceinline__ void cta_select_emit(u64 key, u64* skeys, int v, u64* __restrict__ best_key,
                                                 u64* __restrict__ cta_lists) {
-    key = cta_select32<KW>(key, skeys);
+    key = cta_select32<KW, PRESORTED>(key, skeys);
     if ((threadIdx.x >> 5) == 0) {
         const int lane = threadIdx.x & 31;
         if (cta_lists && lane < LLAMPC_LIST_LEN)

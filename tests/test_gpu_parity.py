@@ -705,7 +705,11 @@ def test_c5_full_size_properties(history):
         shard_top.append(ls._res_keys[1:11].copy())
         assert lo <= b < hi
         del ls
-    assert min(shard_keys) == lb.best_key_value()
+    # the window split (hence the fp32 summation order) is chosen per bank size: the winning INDEX is shard-invariant,
+    # the fp32 score agrees to rounding
+    e_sh, i_sh = decode_keys(np.array([min(shard_keys)], dtype=np.uint64))
+    e_1, i_1 = decode_keys(np.array([lb.best_key_value()], dtype=np.uint64))
+    assert int(i_sh[0]) == int(i_1[0]) and abs(float(e_sh[0]) - float(e_1[0])) <= 2e-6 * float(e_1[0])
     merged = np.sort(np.concatenate(shard_top))[:10]
     assert list(decode_keys(merged)[1]) == list(order)
 
