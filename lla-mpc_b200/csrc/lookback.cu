@@ -544,16 +544,19 @@ using namespace llampc;
 // ===================================================================================================
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// K1p (two candidates per thread, packed f32x2) is the default; LLAMPC_K1_PACKED=0 selects the scalar K1.
-static bool k1_packed() {
+// K1p (two candidates per thread, packed f32x2) is the default for banks that can fill the GPU with pair-threads;
+// small banks keep one candidate per thread (twice the threads: measured 12.4 us against 14.2 us per tick at
+// 1,024 x 20).  LLAMPC_K1_PACKED=0 / 1 forces the scalar / packed kernel for every size.
+constexpr int K1P_MIN_CANDIDATES = 8192;
+static bool k1_packed(int N) {
     static int v = -1;
     if (v < 0) {
         const char* e = getenv("LLAMPC_K1_PACKED");
-        v = (e && e[0] == '0') ? 0 : 1;
+        v = !e ? 2 : (e[0] == '0' ? 0 : 1);
     }
-    return v != 0;
+    return v == 2 ? N >= K1P_MIN_CANDIDATES : v != 0;
 }
-static inline int k1_cands_per_cta() { return k1_packed() ? 2 * LB_THREADS : LB_THREADS; }
+static inline int k1_cands_per_cta(int N) { return k1_packed(N) ? 2 * LB_THREADS : LB_THREADS; }
 
 static int choose_split(int N, int W) {
     // SM time ~ (CTAs on the busiest SM) x (rows per thread) while the FMA pipe is the limiter.
@@ -561,7 +564,7 @@ static int choose_split(int N, int W) {
     long best_cost = -1;
     for (int sy = 1; sy <= 16; sy *= 2) {          // 8 and 16 only pay off for banks too small to fill the GPU
         if (sy > W) break;
-        long ctas = ((long)N * sy + k1_cands_per_cta() - 1) / k1_cands_per_cta();
+        long ctas = ((long)N * sy + k1_cands_per_cta(N) - 1) / k1_cands_per_cta(N);
         long cost = ((ctas + NUM_SMS - 1) / NUM_SMS) * ((W + sy - 1) / sy);
         // a finer split must win by > 3 %: it doubles the number of per-CTA lists the top-K merge has to read
         if (best_cost < 0 || cost * 100 < best_cost * 97) { best_cost = cost; best = sy; }
@@ -574,14 +577,14 @@ static int launch_lookback(const float* bank, int N, int Npad, const float* hist
                            int hist_stride_rows, double Ts, float* avg_err, u64* best_key, u64* cta_lists,
                            int idx_offset, const NewRow& nr, const FusedMerge& fm, const PeerXchg& px, const TreeMerge& tm,
                            cudaStream_t st) {
-    const bool packed = k1_packed();
+    const bool packed = k1_packed(N);
     auto kern = packed ? lookback_window2_kernel<SY, GEOM, MUFU> : lookback_window_kernel<SY, GEOM, MUFU>;
     const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 * (packed ? 2 : 1) : 0);
     if (smem > 48 * 1024) {
-        static bool raised = false;              // idempotent attribute, benign if two threads race
-        if (!raised) {
+        static bool raised[2] = {false, false};  // per kernel (scalar / packed); idempotent attribute, benign if two threads race
+        if (!raised[packed]) {
             LLAMPC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            raised = true;
+            raised[packed] = true;
         }
     }
     const int CPB = (packed ? 2 * LB_THREADS : LB_THREADS) / SY;
@@ -742,7 +745,7 @@ extern "C" int llampc_lookback_num_lists(int N, int W, int split) {
     if (split == 0) split = choose_split(N, W);
     if (split > W) split = 1;
     if (split != 1 && split != 2 && split != 4 && split != 8 && split != 16) return LLAMPC_E_ARG;
-    const int cpb = k1_cands_per_cta() / split;
+    const int cpb = k1_cands_per_cta(N) / split;
     return (N + cpb - 1) / cpb;
 }
 
