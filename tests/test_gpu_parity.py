@@ -939,6 +939,48 @@ def test_guard_fallback_paths_extreme_states():
     assert np.all(rel < np.maximum(1e-4, 50 * sens)), (rel.max(), sens.max())
 
 
+@pytest.mark.parametrize("fast_sin", [True, False])
+def test_packed_kernel_all_variants(history, fast_sin):
+    """K1p (two candidates per thread, packed f32x2; banks of >= 8,192 candidates): shared and varied geometry, both
+    tyre-sine modes, a bank size that leaves the last thread with one candidate and the last CTA ragged, every window
+    split, the sigma = 2 bank, and states outside the guards (per-candidate fallback inside a packed pair)."""
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    rng = np.random.RandomState(21)
+    p = orc.orca_params()
+    N = 8192 + 77
+    all14 = {k: p[k] * (1 + 0.1 * rng.randn(N)) for k in orc.PARAM_NAMES}
+    wide = orc.make_bank(N, 3, variation=tuple((k, 2.0) for k in ("Br", "Cr", "Dr", "Bf", "Cf", "Df")))
+    shared = orc.make_bank(N, 4, variation=orc.RT_VARIATION + (("mass", 0.15),))
+    for bank, W, t_end in ((all14, 20, 1200), (wide, 10, 900), (shared, 33, 600)):
+        ref = np.mean(orc.window_errors(bank, S, U, t_end, W, Ts), axis=1)
+        rbest, rtopk = orc.select(ref, 10)
+        for split in (0, 1, 2, 4, 8, 16):
+            if split > W:
+                continue
+            lb = LookBack(bank, W=W, Ts=Ts, K=10, refine=32, fast_sin=fast_sin, split=split)
+            best, topk, _ = _window(lb, S, U, t_end)
+            _assert_scores(lb.avg_errors(), ref, "split %d" % split)
+            assert best == rbest and list(topk) == list(rtopk)
+            del lb
+    # guard fallbacks: sliding / spinning / near-standstill / reversing states
+    W = 16
+    bank = orc.make_bank(N, seed=9)
+    xs = np.column_stack([rng.uniform(-1, 1, W), rng.uniform(-1, 1, W), rng.uniform(-20, 20, W),
+                          rng.choice([-1.0, 1.0], W) * rng.uniform(0.03, 0.6, W), rng.uniform(-1.2, 1.2, W),
+                          rng.uniform(-40, 40, W)])
+    us = np.column_stack([rng.uniform(-0.1, 1.0, W), rng.uniform(-0.35, 0.35, W)])
+    x1 = np.array([orc.rk6_step(p, xs[j], us[j], 0, Ts) for j in range(W)])
+    ref = np.stack([orc.onestep_errors(bank, xs[j], us[j], x1[j], Ts) for j in range(W)], axis=1).mean(axis=1)
+    lb = LookBack(bank, W=W, Ts=Ts, K=10, refine=16, fast_sin=fast_sin)
+    out = None
+    for j in range(W):
+        out = lb.push(xs[j], us[j], x1[j])
+    _assert_scores(lb.avg_errors(), ref, "guards")
+    order = np.argsort(ref, kind="stable")
+    assert out[0] == order[0] and list(out[1]) == list(order[:10])
+
+
 def test_argument_errors_raise(history):
     """Error behaviour of the host layer: empty / inconsistent banks, out-of-range window and K, wrong shapes."""
     from llampc_b200 import _lib
