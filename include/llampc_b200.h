@@ -230,6 +230,7 @@ typedef struct llampc_tick {
                                        LLAMPC_LIST_LEN) runs the one-launch tick with the in-kernel tree merge
                                        (llampc_lookback_window_balanced_f32) instead of K1 + list merge            */
     unsigned long long workspace_bytes;
+    void* mapped_dev; const void* mapped_for;   /* internal: device alias of result_h (cudaHostGetDevicePointer), cached */
 } llampc_tick_t;
 
 int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream);

@@ -33,7 +33,8 @@ class Tick(C.Structure):
                 ("peer_bufs", _vp), ("peer_world", _i), ("peer_rank", _i), ("peer_seq", C.c_uint),
                 ("pending_seq", C.c_ulonglong), ("pending_words", _i),
                 ("err_ring", _vp), ("rolling", _i),
-                ("workspace", _vp), ("workspace_bytes", C.c_ulonglong)]
+                ("workspace", _vp), ("workspace_bytes", C.c_ulonglong),
+                ("mapped_dev", _vp), ("mapped_for", _vp)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/llampc_b200.h

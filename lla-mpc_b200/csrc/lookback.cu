@@ -983,8 +983,12 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
             pg.peers = t->peer_bufs; pg.world = t->peer_world; pg.rank = t->peer_rank; pg.seq = t->peer_seq; pg.kt = Kt;
         }
         if (t->zero_copy && t->ticket) {
-            void* dptr = nullptr;
-            if (cudaHostGetDevicePointer(&dptr, t->result_h, 0) == cudaSuccess && dptr) {
+            void* dptr = t->mapped_for == t->result_h ? t->mapped_dev : nullptr;
+            if (!dptr && cudaHostGetDevicePointer(&dptr, t->result_h, 0) == cudaSuccess && dptr) {
+                t->mapped_dev = dptr;
+                t->mapped_for = t->result_h;
+            }
+            if (dptr) {
                 static unsigned long long seq_counter = 1;
                 fc.src = t->result;
                 fc.dst_host = static_cast<volatile u64*>(dptr);

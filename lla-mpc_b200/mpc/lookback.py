@@ -162,6 +162,11 @@ class LookBack:
         self._nvalid = C.c_int(0)
         self._idx_out_p, self._score_out_p = self._idx_out.ctypes.data, self._score_out.ctypes.data
         self._nvalid_p = C.addressof(self._nvalid)
+        self._lf_shared, self._lr_shared = float(self.bank.lf_shared), float(self.bank.lr_shared)
+        get_dev = getattr(torch._C, "_cuda_getDevice", None)
+        get_raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
+        self._get_device = get_dev if get_dev is not None else torch.cuda.current_device
+        self._get_raw_stream = get_raw if get_raw is not None else (lambda i: torch.cuda.current_stream(i).cuda_stream)
 
     # ------------------------------------------------------------------ history ring
     def _pack_row(self, slot, x_k, u_k, x_k1):
@@ -224,12 +229,12 @@ class LookBack:
         t.slot = slot
         if self._peer is not None:
             t.peer_seq = self._peer.next_seq()                   # same count on every rank: one per decided tick
-        torch = self.torch
-        if torch.cuda.current_device() != self._dev_index:
-            torch.cuda.set_device(self._dev_index)
-        rc = self._L.llampc_lookback_push(self._tick_ref, self._xk_p, self._uk_p, self._xk1_p, self.bank.lf_shared,
-                                          self.bank.lr_shared, self._idx_out_p, self._score_out_p, self._nvalid_p,
-                                          torch.cuda.current_stream().cuda_stream)
+        # raw accessors: torch.cuda.current_device() / current_stream() cost several microseconds of a ~75 us tick
+        if self._get_device() != self._dev_index:
+            self.torch.cuda.set_device(self._dev_index)
+        rc = self._L.llampc_lookback_push(self._tick_ref, self._xk_p, self._uk_p, self._xk1_p, self._lf_shared,
+                                          self._lr_shared, self._idx_out_p, self._score_out_p, self._nvalid_p,
+                                          self._get_raw_stream(self._dev_index))
         if rc:
             _lib.check(rc, "llampc_lookback_push")
         n = self._nvalid.value
@@ -365,6 +370,7 @@ class LookBack:
             if raise_if or not bank.geom_shared:
                 self.window_count = 0                            # geometry changed: start a fresh window
         self._geom = (bank.lf_shared, bank.lr_shared)
+        self._lf_shared, self._lr_shared = float(bank.lf_shared), float(bank.lr_shared)
 
     # ------------------------------------------------------------------ inspection
     def avg_errors(self):
