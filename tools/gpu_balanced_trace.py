@@ -56,4 +56,6 @@ def trace(N, W, ctas_x100=600):
 
 
 if __name__ == "__main__":
+    os.environ["LLAMPC_TREE_KERNEL"] = "k1b"      # the timeline is compiled into K1b only
     trace(65536, 50)
+    trace(1048576, 50)
