@@ -76,6 +76,10 @@ int llampc_hist_row_pack_h(const double* x_k, const double* u_k, const double* x
  *   geom_shared  non-zero: rows carry valid stage-1 slip angles (lf, lr identical for all candidates)
  *   split     window splits per candidate inside a CTA (1, 2, 4, 8, 16) or 0 = choose from N, W; + 32 selects the
  *             MUFU.SIN (SFU) tyre sine instead of the FMA-pipe polynomial (faster, ~2x the fp32 score error)
+ * Banks of >= 8,192 candidates run the packed kernel K1p: two candidates per thread in f32x2 arithmetic (FFMA2 /
+ * FMUL2 / FADD2), i.e. 256 / split candidates per CTA instead of 128 / split; llampc_lookback_num_lists accounts for
+ * it.  Same operations per candidate, so the scores differ from the scalar kernel's only by re-association of a few
+ * signs (LLAMPC_K1_PACKED=0 / 1 in the environment forces the scalar / packed kernel for every size).
  * ------------------------------------------------------------------------------------------- */
 int llampc_lookback_window_f32(const float* bank, int N, int Npad,
                                const float* hist, int W, int n_vehicles, int hist_stride_rows, double Ts,

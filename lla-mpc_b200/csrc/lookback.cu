@@ -286,8 +286,19 @@ lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W,
     e *= 0.25f;                                    // errors of rt.py:349 (mean over the 4 scored states)
     if (valid) err_ring[(size_t)nr.slot * Npad + cand] = e;
     if (!emit) return;                             // uniform
+    // window re-sum in ring order (deterministic); the loads of 8 columns are issued before the first add so that
+    // enough bytes are in flight per SM for HBM (the ring of 4,096 vehicles is 335 MB: this kernel is HBM-bound there)
     float sum = 0.0f;
-    for (int w = 0; w < W; ++w) sum += (w == nr.slot) ? e : __ldcg(err_ring + (size_t)w * Npad + ci);
+    const float* col = err_ring + ci;
+    int w = 0;
+    for (; w + 8 <= W; w += 8) {
+        float vq[8];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) vq[j] = __ldcg(col + (size_t)(w + j) * Npad);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) sum += (w + j == nr.slot) ? e : vq[j];
+    }
+    for (; w < W; ++w) sum += (w == nr.slot) ? e : __ldcg(col + (size_t)w * Npad);
     const float err = sum / (float)W;
     u64 key = ~0ull;
     if (valid) {
