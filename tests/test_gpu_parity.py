@@ -963,6 +963,15 @@ def test_packed_kernel_all_variants(history, fast_sin):
             _assert_scores(lb.avg_errors(), ref, "split %d" % split)
             assert best == rbest and list(topk) == list(rtopk)
             del lb
+    if fast_sin:                                   # long window: > 48 KB of history staged per CTA (opt-in shared memory)
+        W, t_end = 640, 1300
+        ref = np.mean(orc.window_errors(shared, S, U, t_end, W, Ts), axis=1)
+        lb = LookBack(shared, W=W, Ts=Ts, K=10, refine=16)
+        best, topk, _ = _window(lb, S, U, t_end)
+        _assert_scores(lb.avg_errors(), ref, "W=640")
+        rbest, rtopk = orc.select(ref, 10)
+        assert best == rbest and list(topk) == list(rtopk)
+        del lb
     # guard fallbacks: sliding / spinning / near-standstill / reversing states
     W = 16
     bank = orc.make_bank(N, seed=9)
