@@ -33,7 +33,8 @@ def timed(fn, reps=40):
         fn()
         b.record()
     torch.cuda.synchronize()
-    return float(np.median([a.elapsed_time(b) for a, b in evs])) * 1e3
+    ts = np.sort([a.elapsed_time(b) for a, b in evs])
+    return float(np.mean(ts[:max(1, int(0.9 * len(ts)))])) * 1e3      # mean of the fastest 90 %: the event timer resolves ~2 us
 
 
 def case(N, W, t_end=600, K=10, check_oracle=False, kernel="k1"):

@@ -26,7 +26,7 @@ if __name__ == "__main__":
             def tick():
                 lb._tick.row32_h, lb._tick.row64_h, lb._tick.slot, lb._tick.sync = None, None, 0, 0
                 L.llampc_lookback_tick(lb._tick_ref, st)
-            t = timed(tick, 40)
+            t = timed(tick, 200)
             res.append("N=%d W=%d split=%d: %.1f us (%.3e steps/s)" % (N, W, split, t, N * W / t * 1e6))
             del lb
     print(os.environ.get("LLAMPC_LIB", "default"), os.environ.get("LLAMPC_K1_PACKED", "1"), " | ".join(res), flush=True)
