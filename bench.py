@@ -377,9 +377,11 @@ def run_b200(args):
     achieved = k1_rate * F_ALG / 1e12
     hbm_bytes = n_local * (NPARAM_PACKED * 4 + 4) + W_C2 * 80
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one K1 launch at C2 from the committed ncu --set full
-                # capture (profiles/r01_k1_final_ncu.md); not captured for the sharded C5 launches
-                "traffic": 4261632 if world == 1 else None, "kernel": "lookback_window_kernel (scores + selection + tree merge: the whole tick)",
+                # dram__bytes_read.sum + dram__bytes_write.sum of one tick launch at C2 from the committed ncu --set full
+                # capture (profiles/r01_k1p_ncu.md: 4,264,448 B read, 0 B written back within the launch -- the scores
+                # stay in L2); not captured for the sharded C5 launches
+                "traffic": 4264448 if world == 1 else None,
+                "kernel": "lookback_window2_kernel (K1p: scores + selection + in-kernel tree merge = the whole tick)",
                 "kernel_us": k1_avg_s * 1e6, "kernel_us_scores_only": float(np.mean(k1_bare_ms)) * 1e3,
                 "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json; tensor/HBM peaks do not bound this elementwise ODE kernel)" % sm_max,
                 "flop_per_step": F_ALG, "steps_per_launch": n_local * W_C2,
