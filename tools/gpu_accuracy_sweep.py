@@ -9,7 +9,7 @@ from llampc_b200.mpc import LookBack
 from oracle import llampc_oracle as orc
 g = np.load(os.path.join(ROOT, "tests", "golden", "ethz_history.npz"))
 S, U, Ts = g["states"], g["inputs"], float(g["Ts"])
-N = 4096
+N = int(os.environ.get("SWEEP_N", "4096"))      # >= 8192 exercises the packed kernel K1p
 bank = orc.make_bank(N, seed=21, variation=orc.RT_VARIATION + (("mass", 0.15),))
 for W in (10, 50):
     worst = {True: 0.0, False: 0.0}
@@ -29,5 +29,5 @@ for W in (10, 50):
                 worst[fs], where[fs] = rel.max(), (t_end, int(np.argmax(rel)), ref[np.argmax(rel)], ref.min())
             bad_rank[fs] += int(best != order[0] or list(topk) != list(order))
     for fs in (True, False):
-        print("W=%2d %-28s windows %d  worst rel err %.2e at (tick, cand, score, best score) %s  fp32-ranking mismatches %d" % (
-            W, "SFU sine (default)" if fs else "strict polynomial", len(ticks), worst[fs], where[fs], bad_rank[fs]), flush=True)
+        print("N=%d W=%2d %-28s windows %d  worst rel err %.2e at (tick, cand, score, best score) %s  fp32-ranking mismatches %d" % (
+            N, W, "SFU sine (default)" if fs else "strict polynomial", len(ticks), worst[fs], where[fs], bad_rank[fs]), flush=True)
