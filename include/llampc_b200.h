@@ -184,8 +184,7 @@ int llampc_refine_f64(const double* bank64, int N, const double* hist64, int W, 
                       llampc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * One MPC tick of the look-back step in ONE call (the body of run_nmpc_orca_llampc_rt.py:347-360); with `workspace`
- * set and a bank of >= 8,192 candidates it is also ONE launch (scoring, tree merge and the fp64 re-score workers):
+ * One MPC tick of the look-back step in ONE call (the body of run_nmpc_orca_llampc_rt.py:347-360):
  * upload the newest history row into ring slot `slot`, K1 over the whole window, K4 top-Kt with
  * Kt = max(K, n_refine), optional fp64 re-score of the Kt finalists, results to pinned host memory.
  * Every buffer is caller-owned; the struct only carries pointers (device unless suffixed _h).

@@ -10,136 +10,11 @@
 #include <math.h>
 #include <stddef.h>
 #include <string.h>
-#include <stdio.h>
-#include <time.h>
 #include <stdlib.h>
 
 namespace llampc {
 
 constexpr int NUM_SMS = 148;
-
-// ---------------------------------------------------------------------------------------------------
-// fp64 re-score of finalists: one warp per finalist, lanes stride over the window.
-// ---------------------------------------------------------------------------------------------------
-struct NewRow64 { double v[LLAMPC_HIST64_ROW]; int slot; };
-
-// Optional zero-copy hand-off of the tick result: the last re-score block to retire copies `words` result words to
-// mapped pinned host memory and then publishes `seq` in the word after them; the host polls that word instead of
-// paying for a D2H copy launch plus a stream synchronisation.
-struct FinalCopy { const u64* src; volatile u64* dst_host; unsigned* ticket; int words; u64 seq; };
-
-// Optional multi-GPU finalist all-gather over NVLink peer memory, carried by the last re-score block: every rank
-// owns a symmetric buffer [2 parities][world][wpr] (wpr = 2 Kt + 1: Kt keys, Kt fp64 scores, sequence word); the block
-// stores its finalists into slot `rank` of every peer, waits until its own buffer holds all `world` contributions of
-// this tick, and hands the whole set (world * 2 Kt words after the local arg-min key) to the host.
-struct PeerGather { u64* const* peers; int world; int rank; unsigned seq; int kt; };
-
-constexpr int RF_THREADS = 128;                   // 64 window rows at a time x 2 lanes (front / rear tyre) per row
-
-// The work of one 128-thread block for finalist f of n_fin; shared by refine_f64_kernel and by the worker CTAs that the
-// packed look-back kernel K1p appends to its own grid (one launch per tick, no kernel boundary before the re-score).
-static __device__ __noinline__ void refine_block(int f, int n_fin, const double* __restrict__ bank64, int N,
-                                                 double* __restrict__ hist64, int W, double h, const u64* __restrict__ keys,
-                                                 int idx_offset, double* __restrict__ out, const NewRow64& nr,
-                                                 const FinalCopy& fc, const PeerGather& pg, double* spart, bool* last_block_p) {
-    const int tid = threadIdx.x, lane = tid & 31;
-    if (nr.slot >= 0 && f == 0 && tid < LLAMPC_HIST64_ROW) hist64[(size_t)nr.slot * LLAMPC_HIST64_ROW + tid] = nr.v[tid];
-    const long long ci = (long long)(unsigned)(__ldcg(keys + f) & 0xffffffffull) - idx_offset;   // L2: written by this or the previous launch
-    double result = __longlong_as_double(0x7ff8000000000000ll);       // padded key (~0) or foreign shard -> NaN
-    if (ci >= 0 && ci < N) {                       // uniform over the block
-        Params64 p;
-        double* pp = reinterpret_cast<double*>(&p);
-#pragma unroll
-        for (int j = 0; j < LLAMPC_NPARAM; ++j) pp[j] = bank64[(size_t)j * N + ci];
-        double acc = 0.0;
-        const bool rear = tid & 1;                 // lane pair (2k, 2k+1) shares window row w
-        for (int w0 = 0; w0 < W; w0 += RF_THREADS / 2) {      // uniform trip count: the pair shuffles need full warps
-            const int w = w0 + (tid >> 1);
-            const int wc = w < W ? w : W - 1;
-            double r[LLAMPC_HIST64_ROW];
-#pragma unroll
-            for (int i = 0; i < LLAMPC_HIST64_ROW; ++i)
-                r[i] = (wc == nr.slot) ? nr.v[i] : hist64[(size_t)wc * LLAMPC_HIST64_ROW + i];
-            double y1[6];
-            rk4_step64_pair(p, r, r[6], r[7], h, rear, y1);
-            double e = 0.0;
-#pragma unroll
-            for (int i = 0; i < 4; ++i) { double d = y1[i] - r[8 + i]; e += d * d; }
-            if (w < W && !rear) acc += e / 4;
-        }
-#pragma unroll
-        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-        if (lane == 0) spart[tid >> 5] = acc;
-        __syncthreads();
-        result = ((spart[0] + spart[1]) + (spart[2] + spart[3])) / W;
-    }
-    if (tid == 0) out[f] = result;
-    if (fc.dst_host) {                             // uniform over the grid
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) *last_block_p = atomicAdd(fc.ticket, 1u) == (unsigned)(n_fin - 1);
-        __syncthreads();
-        if (!*last_block_p) return;
-        __threadfence();
-        int words = fc.words;
-        if (pg.world > 1) {
-            // fc.src = [arg-min key | Kt keys | Kt scores]; exchange the 2 Kt finalist words with every peer
-            const int wpr = 2 * pg.kt + 1, parity = pg.seq & 1;
-            const size_t my_slot = ((size_t)parity * pg.world + pg.rank) * wpr;
-            for (int i = tid; i < 2 * pg.kt * pg.world; i += RF_THREADS) {
-                const int q = i / (2 * pg.kt), j = i % (2 * pg.kt);
-                reinterpret_cast<volatile u64*>(pg.peers[q])[my_slot + j] = __ldcg(fc.src + 1 + j);
-            }
-            __threadfence_system();
-            __syncthreads();
-            if (tid < pg.world) {
-                reinterpret_cast<volatile u64*>(pg.peers[tid])[my_slot + 2 * pg.kt] = (u64)pg.seq;
-                volatile u64* own = pg.peers[pg.rank] + ((size_t)parity * pg.world + tid) * wpr;
-                const long long t0 = clock64();
-                while (own[2 * pg.kt] != (u64)pg.seq) {
-                    if (clock64() - t0 > 2000000000ll) break;         // ~1 s: give up, the host sees a stale slot
-                    __nanosleep(64);
-                }
-            }
-            __threadfence_system();
-            __syncthreads();
-            fc.dst_host[0] = __ldcg(fc.src);
-            volatile u64* own = pg.peers[pg.rank] + (size_t)parity * pg.world * wpr;
-            for (int i = tid; i < 2 * pg.kt * pg.world; i += RF_THREADS) {
-                const int q = i / (2 * pg.kt), j = i % (2 * pg.kt);
-                fc.dst_host[1 + i] = own[(size_t)q * wpr + j];
-            }
-            words = 1 + 2 * pg.kt * pg.world;
-        } else {
-            for (int i = tid; i < words; i += RF_THREADS) fc.dst_host[i] = __ldcg(fc.src + i);
-        }
-        __threadfence_system();
-        __syncthreads();
-        if (tid == 0) {
-            *fc.ticket = 0;
-            fc.dst_host[words] = fc.seq;
-            __threadfence_system();
-        }
-    }
-}
-
-__global__ void __launch_bounds__(RF_THREADS)
-refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__ hist64, int W, double h,
-                  const u64* __restrict__ keys, int idx_offset, double* __restrict__ out, NewRow64 nr, FinalCopy fc,
-                  PeerGather pg) {
-    __shared__ double spart[RF_THREADS / 32];
-    __shared__ bool last_block;
-    refine_block((int)blockIdx.x, (int)gridDim.x, bank64, N, hist64, W, h, keys, idx_offset, out, nr, fc, pg, spart, &last_block);
-}
-
-// Re-score fused into the K1p launch: n_fin worker CTAs are appended to the scoring grid.  They are dispatched last,
-// wait until the root of the merge tree has published the finalists (flag == seq) and then run refine_block.
-// n_fin = 0 disables it.
-struct FusedRefine {
-    const double* bank64; double* hist64; double h; const u64* keys; double* errs;
-    NewRow64 nr; FinalCopy fc; PeerGather pg; unsigned* flag; unsigned seq; int n_fin;
-};
-
 
 // ---------------------------------------------------------------------------------------------------
 // K1.  grid = (ceil(N / (128/SY)), n_vehicles); block = 128 threads = (128/SY candidates) x (SY window splits).
@@ -258,25 +133,7 @@ template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
 __global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB2_MIN_BLOCKS)
 lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
                         long hist_stride_floats, StepSize z, float* __restrict__ avg_err, u64* __restrict__ best_key,
-                        u64* __restrict__ cta_lists, int idx_offset, NewRow nr, FusedMerge fm, PeerXchg px, TreeMerge tm,
-                        FusedRefine fr) {
-    const int n_score = (int)gridDim.x - fr.n_fin;               // scoring CTAs; the last fr.n_fin CTAs re-score in fp64
-    if ((int)blockIdx.x >= n_score) {                            // uniform over the CTA (single history, tree mode only)
-        __shared__ double rspart[RF_THREADS / 32];
-        __shared__ bool rlast;
-        if (threadIdx.x == 0) {
-            const long long t0 = clock64();
-            while (*reinterpret_cast<volatile unsigned*>(fr.flag) != fr.seq) {
-                if (clock64() - t0 > 4000000000ll) break;        // ~2 s: the scoring grid died; the host sees stale scores
-                __nanosleep(200);
-            }
-            fence_acq_rel_gpu();
-        }
-        __syncthreads();
-        refine_block((int)blockIdx.x - n_score, fr.n_fin, fr.bank64, N, fr.hist64, W, fr.h, fr.keys, idx_offset, fr.errs,
-                     fr.nr, fr.fc, fr.pg, rspart, &rlast);
-        return;
-    }
+                        u64* __restrict__ cta_lists, int idx_offset, NewRow nr, FusedMerge fm, PeerXchg px, TreeMerge tm) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     __shared__ __align__(8) uint64_t mbar;
     __shared__ u64 skeys[LB_THREADS];
@@ -367,9 +224,7 @@ lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const 
     if (tm.K > 0) {                                // uniform over the grid: tree finish (single history), one launch per tick
         __shared__ u64 mrows[BAL_FAN][BAL_ROW_PAD];
         key = cta_select32<KW, true>(key, skeys);
-        if (tid < 32)
-            tree_merge(key, tid, (int)blockIdx.x, n_score, tm.K, tm.ws, mrows, tm.out, px,
-                       fr.n_fin > 0 ? fr.flag : nullptr, fr.seq);
+        if (tid < 32) tree_merge(key, tid, (int)blockIdx.x, (int)gridDim.x, tm.K, tm.ws, mrows, tm.out, px);
         return;
     }
     cta_select_emit<KW, true>(key, skeys, v, best_key, cta_lists);
@@ -546,6 +401,111 @@ topk_kernel(const float* __restrict__ err, int N, int idx_offset, int K, int per
 }
 
 // ---------------------------------------------------------------------------------------------------
+// fp64 re-score of finalists: one warp per finalist, lanes stride over the window.
+// ---------------------------------------------------------------------------------------------------
+struct NewRow64 { double v[LLAMPC_HIST64_ROW]; int slot; };
+
+// Optional zero-copy hand-off of the tick result: the last re-score block to retire copies `words` result words to
+// mapped pinned host memory and then publishes `seq` in the word after them; the host polls that word instead of
+// paying for a D2H copy launch plus a stream synchronisation.
+struct FinalCopy { const u64* src; volatile u64* dst_host; unsigned* ticket; int words; u64 seq; };
+
+// Optional multi-GPU finalist all-gather over NVLink peer memory, carried by the last re-score block: every rank
+// owns a symmetric buffer [2 parities][world][wpr] (wpr = 2 Kt + 1: Kt keys, Kt fp64 scores, sequence word); the block
+// stores its finalists into slot `rank` of every peer, waits until its own buffer holds all `world` contributions of
+// this tick, and hands the whole set (world * 2 Kt words after the local arg-min key) to the host.
+struct PeerGather { u64* const* peers; int world; int rank; unsigned seq; int kt; };
+
+constexpr int RF_THREADS = 128;                   // 64 window rows at a time x 2 lanes (front / rear tyre) per row
+
+__global__ void __launch_bounds__(RF_THREADS)
+refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__ hist64, int W, double h,
+                  const u64* __restrict__ keys, int idx_offset, double* __restrict__ out, NewRow64 nr, FinalCopy fc,
+                  PeerGather pg) {
+    __shared__ double spart[RF_THREADS / 32];
+    __shared__ bool last_block;
+    const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    if (nr.slot >= 0 && f == 0 && tid < LLAMPC_HIST64_ROW) hist64[(size_t)nr.slot * LLAMPC_HIST64_ROW + tid] = nr.v[tid];
+    const long long ci = (long long)(unsigned)(keys[f] & 0xffffffffull) - idx_offset;
+    double result = __longlong_as_double(0x7ff8000000000000ll);       // padded key (~0) or foreign shard -> NaN
+    if (ci >= 0 && ci < N) {                       // uniform over the block
+        Params64 p;
+        double* pp = reinterpret_cast<double*>(&p);
+#pragma unroll
+        for (int j = 0; j < LLAMPC_NPARAM; ++j) pp[j] = bank64[(size_t)j * N + ci];
+        double acc = 0.0;
+        const bool rear = tid & 1;                 // lane pair (2k, 2k+1) shares window row w
+        for (int w0 = 0; w0 < W; w0 += RF_THREADS / 2) {      // uniform trip count: the pair shuffles need full warps
+            const int w = w0 + (tid >> 1);
+            const int wc = w < W ? w : W - 1;
+            double r[LLAMPC_HIST64_ROW];
+#pragma unroll
+            for (int i = 0; i < LLAMPC_HIST64_ROW; ++i)
+                r[i] = (wc == nr.slot) ? nr.v[i] : hist64[(size_t)wc * LLAMPC_HIST64_ROW + i];
+            double y1[6];
+            rk4_step64_pair(p, r, r[6], r[7], h, rear, y1);
+            double e = 0.0;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) { double d = y1[i] - r[8 + i]; e += d * d; }
+            if (w < W && !rear) acc += e / 4;
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if (lane == 0) spart[tid >> 5] = acc;
+        __syncthreads();
+        result = ((spart[0] + spart[1]) + (spart[2] + spart[3])) / W;
+    }
+    if (tid == 0) out[f] = result;
+    if (fc.dst_host) {                             // uniform over the grid
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) last_block = atomicAdd(fc.ticket, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!last_block) return;
+        __threadfence();
+        int words = fc.words;
+        if (pg.world > 1) {
+            // fc.src = [arg-min key | Kt keys | Kt scores]; exchange the 2 Kt finalist words with every peer
+            const int wpr = 2 * pg.kt + 1, parity = pg.seq & 1;
+            const size_t my_slot = ((size_t)parity * pg.world + pg.rank) * wpr;
+            for (int i = tid; i < 2 * pg.kt * pg.world; i += RF_THREADS) {
+                const int q = i / (2 * pg.kt), j = i % (2 * pg.kt);
+                reinterpret_cast<volatile u64*>(pg.peers[q])[my_slot + j] = __ldcg(fc.src + 1 + j);
+            }
+            __threadfence_system();
+            __syncthreads();
+            if (tid < pg.world) {
+                reinterpret_cast<volatile u64*>(pg.peers[tid])[my_slot + 2 * pg.kt] = (u64)pg.seq;
+                volatile u64* own = pg.peers[pg.rank] + ((size_t)parity * pg.world + tid) * wpr;
+                const long long t0 = clock64();
+                while (own[2 * pg.kt] != (u64)pg.seq) {
+                    if (clock64() - t0 > 2000000000ll) break;         // ~1 s: give up, the host sees a stale slot
+                    __nanosleep(64);
+                }
+            }
+            __threadfence_system();
+            __syncthreads();
+            fc.dst_host[0] = __ldcg(fc.src);
+            volatile u64* own = pg.peers[pg.rank] + (size_t)parity * pg.world * wpr;
+            for (int i = tid; i < 2 * pg.kt * pg.world; i += RF_THREADS) {
+                const int q = i / (2 * pg.kt), j = i % (2 * pg.kt);
+                fc.dst_host[1 + i] = own[(size_t)q * wpr + j];
+            }
+            words = 1 + 2 * pg.kt * pg.world;
+        } else {
+            for (int i = tid; i < words; i += RF_THREADS) fc.dst_host[i] = __ldcg(fc.src + i);
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (tid == 0) {
+            *fc.ticket = 0;
+            fc.dst_host[words] = fc.seq;
+            __threadfence_system();
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
 // One RK4 step / one RHS evaluation for N (model, state, input) triples, f64 in/out, fp32 increments.
 // ---------------------------------------------------------------------------------------------------
 template <int MODE>   // 0: RK4 step, 1: right-hand side, 2: forces and slip angles
@@ -627,38 +587,18 @@ template <int SY, bool GEOM, bool MUFU>
 static int launch_lookback(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
                            int hist_stride_rows, double Ts, float* avg_err, u64* best_key, u64* cta_lists,
                            int idx_offset, const NewRow& nr, const FusedMerge& fm, const PeerXchg& px, const TreeMerge& tm,
-                           const FusedRefine& fr, cudaStream_t st) {
+                           cudaStream_t st) {
     const bool packed = k1_packed(N);
-    if (packed) {
-        auto kern2 = lookback_window2_kernel<SY, GEOM, MUFU>;
-        const size_t smem2 = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 * 2 : 0);
-        if (smem2 > 48 * 1024) {
-            static bool raised2 = false;         // idempotent attribute, benign if two threads race
-            if (!raised2) {
-                LLAMPC_CUDA_TRY(cudaFuncSetAttribute(kern2, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-                raised2 = true;
-            }
-        }
-        const int cpb2 = 2 * LB_THREADS / SY;
-        const int n_fin = (tm.K > 0 && n_vehicles == 1) ? fr.n_fin : 0;     // re-score workers ride on the tree-mode launch
-        FusedRefine frk = fr;
-        frk.n_fin = n_fin;
-        dim3 grid2((N + cpb2 - 1) / cpb2 + n_fin, n_vehicles);
-        kern2<<<grid2, LB_THREADS, smem2, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, hist, W,
-                                                (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key,
-                                                cta_lists, idx_offset, nr, fm, px, tm, frk);
-        return (int)cudaGetLastError();
-    }
-    auto kern = lookback_window_kernel<SY, GEOM, MUFU>;
-    const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 : 0);
+    auto kern = packed ? lookback_window2_kernel<SY, GEOM, MUFU> : lookback_window_kernel<SY, GEOM, MUFU>;
+    const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 * (packed ? 2 : 1) : 0);
     if (smem > 48 * 1024) {
-        static bool raised = false;              // idempotent attribute, benign if two threads race
-        if (!raised) {
+        static bool raised[2] = {false, false};  // per kernel (scalar / packed); idempotent attribute, benign if two threads race
+        if (!raised[packed]) {
             LLAMPC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            raised = true;
+            raised[packed] = true;
         }
     }
-    const int CPB = LB_THREADS / SY;
+    const int CPB = (packed ? 2 * LB_THREADS : LB_THREADS) / SY;
     dim3 grid((N + CPB - 1) / CPB, n_vehicles);
     kern<<<grid, LB_THREADS, smem, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, hist, W,
                                          (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key, cta_lists,
@@ -671,10 +611,7 @@ static int lookback_window_impl(const float* bank, int N, int Npad, const float*
                                 llampc_key_t* cta_lists, int idx_offset, int geom_shared, int split,
                                 const NewRow& nr, const FusedMerge& fm, llampc_stream_t stream,
                                 const PeerXchg& px = PeerXchg{nullptr, 0, 0, 0},
-                                const TreeMerge& tm = TreeMerge{{nullptr, nullptr, nullptr, nullptr, nullptr}, nullptr, 0},
-                                const FusedRefine* frp = nullptr) {
-    FusedRefine fr;
-    if (frp) fr = *frp; else { memset(&fr, 0, sizeof(fr)); }
+                                const TreeMerge& tm = TreeMerge{{nullptr, nullptr, nullptr, nullptr, nullptr}, nullptr, 0}) {
     if (!bank || !hist || (!best_key && !cta_lists && !avg_err && tm.K <= 0) || N <= 0 || Npad < N || n_vehicles <= 0 || hist_stride_rows < W) return LLAMPC_E_ARG;
     if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
     if (!aligned16(bank) || !aligned16(hist) || (hist_stride_rows * LLAMPC_HIST_ROW * 4) % 16) return LLAMPC_E_ALIGN;
@@ -685,10 +622,10 @@ static int lookback_window_impl(const float* bank, int N, int Npad, const float*
     if (split > W) split = 1;
 #define LB_CASE(SYV)                                                                                                  \
     case SYV:                                                                                                         \
-        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, fr, st)   \
-                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, fr, st); \
-        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, fr, st)            \
-                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, fr, st);
+        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, st)   \
+                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, st); \
+        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, st)            \
+                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, st);
     switch (split) {
         LB_CASE(1)
         LB_CASE(2)
@@ -918,9 +855,7 @@ extern "C" int llampc_forces_batch_f32(const float* bank, int N, int Npad, const
 static int lookback_tree_dispatch(const float* bank, int N, int Npad, const float* hist, int W, double Ts, float* avg_err,
                                   int idx_offset, int geom_shared, int split, int K, void* workspace,
                                   unsigned long long workspace_bytes, llampc_key_t* out, const NewRow& nr,
-                                  const PeerXchg& px, llampc_stream_t stream, FusedRefine* fr = nullptr,
-                                  bool* refine_fused = nullptr) {
-    if (refine_fused) *refine_fused = false;
+                                  const PeerXchg& px, llampc_stream_t stream) {
     if (!workspace || !out) return LLAMPC_E_ARG;
     if (K <= 0 || K > LLAMPC_LIST_LEN) return LLAMPC_E_RANGE;
     const int n_lists = llampc_lookback_num_lists(N, W, split);
@@ -941,15 +876,8 @@ static int lookback_tree_dispatch(const float* bank, int N, int Npad, const floa
     if (workspace_bytes < lay.bytes) return LLAMPC_E_ARG;
     TreeMerge tm = {tree_workspace(static_cast<unsigned char*>(workspace), lay), out, K};
     FusedMerge none = {nullptr, nullptr, 0};
-    static int fuse_env = -1;                                    // LLAMPC_FUSED_REFINE=0: always launch the re-score kernel
-    if (fuse_env < 0) { const char* e = getenv("LLAMPC_FUSED_REFINE"); fuse_env = (e && e[0] == '0') ? 0 : 1; }
-    const bool fuse = fr != nullptr && fuse_env && k1_packed(N) && fr->n_fin > 0 && fr->n_fin <= LLAMPC_LIST_LEN;
-    if (fuse) {
-        fr->flag = tree_done_flag(tm.ws);
-        if (refine_fused) *refine_fused = true;
-    }
     return lookback_window_impl(bank, N, Npad, hist, W, 1, W, Ts, avg_err, nullptr, nullptr, idx_offset, geom_shared, split,
-                                nr, none, stream, px, tm, fuse ? fr : nullptr);
+                                nr, none, stream, px, tm);
 }
 
 extern "C" long long llampc_lookback_balanced_workspace_bytes(int N, int W) {
@@ -991,51 +919,6 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
         for (int i = 0; i < LLAMPC_HIST_ROW; ++i) nr.v[i] = t->row32_h[i];
         nr.slot = t->slot;
     }
-    // ---- fp64 re-score descriptors (built first: the packed kernel can carry the re-score in its own launch)
-    const bool refine = Kt > 0 && t->n_refine > 0;
-    const bool filling = t->rolling > 1;
-    t->pending_seq = 0;
-    t->pending_words = 0;
-    NewRow64 nr64;
-    nr64.slot = -1;
-    FinalCopy fc = {nullptr, nullptr, nullptr, 0, 0};
-    PeerGather pg = {nullptr, 0, 0, 0, 0};
-    if (refine && !filling) {
-        if (!t->bank64 || !t->hist64) return LLAMPC_E_ARG;
-        if (t->row64_h) {
-            for (int i = 0; i < LLAMPC_HIST64_ROW; ++i) nr64.v[i] = t->row64_h[i];
-            nr64.slot = t->slot;
-        }
-        // zero-copy hand-off: needs the ticket word after the K1 ticket and a host buffer with one spare word
-        const bool gather = t->peer_world > 1 && t->peer_bufs != nullptr;
-        const int words = gather ? 1 + 2 * Kt * t->peer_world : 1 + 2 * Kt;
-        if (gather) {
-            if (!(t->zero_copy && t->ticket)) return LLAMPC_E_ARG;     // the gather rides on the zero-copy hand-off
-            pg.peers = t->peer_bufs; pg.world = t->peer_world; pg.rank = t->peer_rank; pg.seq = t->peer_seq; pg.kt = Kt;
-        }
-        if (t->zero_copy && t->ticket) {
-            void* dptr = t->mapped_for == t->result_h ? t->mapped_dev : nullptr;
-            if (!dptr && cudaHostGetDevicePointer(&dptr, t->result_h, 0) == cudaSuccess && dptr) {
-                t->mapped_dev = dptr;
-                t->mapped_for = t->result_h;
-            }
-            if (dptr) {
-                static unsigned long long seq_counter = 1;
-                fc.src = t->result;
-                fc.dst_host = static_cast<volatile u64*>(dptr);
-                fc.ticket = t->ticket + 1;
-                fc.words = 1 + 2 * Kt;
-                fc.seq = ++seq_counter;
-                reinterpret_cast<volatile llampc_key_t*>(t->result_h)[words] = 0;
-                t->pending_seq = fc.seq;
-                t->pending_words = words;
-            } else {
-                (void)cudaGetLastError();                            // result_h is not mapped: use the copy path
-                if (gather) return LLAMPC_E_ARG;
-            }
-        }
-    }
-    bool refine_fused = false;
     int rc;
     if (t->rolling) {
         // the reference's rolling bookkeeping: one new error column + ring re-sum, then the list merge
@@ -1059,17 +942,9 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
         }
     } else if (fused && t->workspace && Kt > 0) {
         // K1 (or K1b for small grids) with the tree merge, one launch; writes keys[0..LIST_LEN] itself (best_key stays armed)
-        FusedRefine fr;
-        memset(&fr, 0, sizeof(fr));
-        if (refine) {                              // K1p appends Kt re-score CTAs to its grid: one launch per tick
-            static unsigned fuse_seq = 0;
-            fr.bank64 = t->bank64; fr.hist64 = t->hist64; fr.h = t->Ts; fr.keys = keys + 1; fr.errs = errs;
-            fr.nr = nr64; fr.fc = fc; fr.pg = pg; fr.seq = ++fuse_seq; fr.n_fin = Kt;
-            if (fuse_seq == 0xffffffffu) fuse_seq = 0;
-        }
         rc = lookback_tree_dispatch(t->bank, t->N, t->Npad, t->hist, t->W, t->Ts, t->avg_err, t->idx_offset,
                                     t->geom_shared, t->split, Kt, t->workspace, t->workspace_bytes, keys, nr,
-                                    PeerXchg{nullptr, 0, 0, 0}, stream, refine ? &fr : nullptr, &refine_fused);
+                                    PeerXchg{nullptr, 0, 0, 0}, stream);
         if (rc) return rc;
     } else if (fused) {
         // K1 (block arg-min + per-CTA sorted lists) -> list merge (also moves best_key to keys[0] and re-arms it)
@@ -1098,7 +973,47 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
             if (rc) return rc;
         }
     }
-    if (refine && !refine_fused) {
+    const bool refine = Kt > 0 && t->n_refine > 0;
+    t->pending_seq = 0;
+    t->pending_words = 0;
+    if (refine) {
+        if (!t->bank64 || !t->hist64) return LLAMPC_E_ARG;
+        NewRow64 nr64;
+        nr64.slot = -1;
+        if (t->row64_h) {
+            for (int i = 0; i < LLAMPC_HIST64_ROW; ++i) nr64.v[i] = t->row64_h[i];
+            nr64.slot = t->slot;
+        }
+        // zero-copy hand-off: needs the ticket word after the K1 ticket and a host buffer with one spare word
+        const bool gather = t->peer_world > 1 && t->peer_bufs != nullptr;
+        const int words = gather ? 1 + 2 * Kt * t->peer_world : 1 + 2 * Kt;
+        FinalCopy fc = {nullptr, nullptr, nullptr, 0, 0};
+        PeerGather pg = {nullptr, 0, 0, 0, 0};
+        if (gather) {
+            if (!(t->zero_copy && t->ticket)) return LLAMPC_E_ARG;     // the gather rides on the zero-copy hand-off
+            pg.peers = t->peer_bufs; pg.world = t->peer_world; pg.rank = t->peer_rank; pg.seq = t->peer_seq; pg.kt = Kt;
+        }
+        if (t->zero_copy && t->ticket) {
+            void* dptr = t->mapped_for == t->result_h ? t->mapped_dev : nullptr;
+            if (!dptr && cudaHostGetDevicePointer(&dptr, t->result_h, 0) == cudaSuccess && dptr) {
+                t->mapped_dev = dptr;
+                t->mapped_for = t->result_h;
+            }
+            if (dptr) {
+                static unsigned long long seq_counter = 1;
+                fc.src = t->result;
+                fc.dst_host = static_cast<volatile u64*>(dptr);
+                fc.ticket = t->ticket + 1;
+                fc.words = 1 + 2 * Kt;
+                fc.seq = ++seq_counter;
+                reinterpret_cast<volatile llampc_key_t*>(t->result_h)[words] = 0;
+                t->pending_seq = fc.seq;
+                t->pending_words = words;
+            } else {
+                (void)cudaGetLastError();                            // result_h is not mapped: use the copy path
+                if (gather) return LLAMPC_E_ARG;
+            }
+        }
         refine_f64_kernel<<<Kt, RF_THREADS, 0, st>>>(t->bank64, t->N, t->hist64, t->W, t->Ts, keys + 1, t->idx_offset, errs, nr64, fc,
                                                      pg);
         LLAMPC_CUDA_TRY(cudaGetLastError());
@@ -1232,42 +1147,15 @@ extern "C" int llampc_lookback_push(llampc_tick_t* t, const double* x_k, const d
                                     double lf_shared, double lr_shared, long long* idx_out, double* score_out,
                                     int* n_valid, llampc_stream_t stream) {
     if (!t || !x_k || !u_k || !x_k1 || !idx_out || !score_out || !n_valid || !t->row32_h) return LLAMPC_E_ARG;
-#ifdef LLAMPC_PUSH_PROFILE
-    // experiments build: where the host time of a push goes (printed every 10 pushes)
-    static double acc[4] = {0, 0, 0, 0};
-    static int cnt = 0;
-    auto now = []() { timespec ts; clock_gettime(CLOCK_MONOTONIC, &ts); return ts.tv_sec * 1e6 + ts.tv_nsec * 1e-3; };
-    const double t0 = now();
-#endif
     int rc = llampc_hist_row_pack_h(x_k, u_k, x_k1, t->Ts, lf_shared, lr_shared, const_cast<float*>(t->row32_h),
                                     const_cast<double*>(t->row64_h));
     if (rc) return rc;
-#ifdef LLAMPC_PUSH_PROFILE
-    const double t1 = now();
-    t->sync = 0;
-    rc = llampc_lookback_tick(t, stream);
-    const double t2 = now();
-    if (!rc) rc = llampc_lookback_finish(t, stream);
-    const double t3 = now();
-    t->sync = 1;
-    if (rc) return rc;
-    rc = llampc_lookback_decode(t, idx_out, score_out, n_valid);
-    const double t4 = now();
-    acc[0] += t1 - t0; acc[1] += t2 - t1; acc[2] += t3 - t2; acc[3] += t4 - t3;
-    if (++cnt == 10) {
-        fprintf(stderr, "push profile (us): pack %.2f  enqueue (2 launches) %.2f  wait for the result %.2f  decode %.2f\n",
-                acc[0] / 10, acc[1] / 10, acc[2] / 10, acc[3] / 10);
-        cnt = 0; acc[0] = acc[1] = acc[2] = acc[3] = 0;
-    }
-    return rc;
-#else
     const int sync_was = t->sync;
     t->sync = 1;
     rc = llampc_lookback_tick(t, stream);
     t->sync = sync_was;
     if (rc) return rc;
     return llampc_lookback_decode(t, idx_out, score_out, n_valid);
-#endif
 }
 
 // layout probes for FFI bindings that mirror llampc_tick_t by hand

@@ -106,8 +106,7 @@ struct BalWs {
 // this warp is the last arrival of its node; the warp that produces the root writes `out` (and runs the NVLink
 // min-loc when several GPUs share the bank).
 __device__ __forceinline__ void tree_merge(u64 key, int lane, int idx, int n, int K, const BalWs& ws,
-                                               u64 (*mrows)[BAL_ROW_PAD], u64* __restrict__ out, const PeerXchg& px,
-                                               unsigned* done_flag = nullptr, unsigned done_seq = 0) {
+                                               u64 (*mrows)[BAL_ROW_PAD], u64* __restrict__ out, const PeerXchg& px) {
     u64* lists = ws.lists;
     unsigned* cnt = ws.mcount;
     const int rounds = K > 0 ? K : 1;              // every level keeps the K smallest keys (the rest padded with ~0)
@@ -158,11 +157,6 @@ __device__ __forceinline__ void tree_merge(u64 key, int lane, int idx, int n, in
         *ws.next = 0;                              // every CTA has left its task loop: re-arm the counter for the next launch
     }
     if (lane < LLAMPC_LIST_LEN) out[1 + lane] = lane < K ? key : ~0ull;
-    if (done_flag) {                               // wakes the re-score workers appended to the same launch
-        fence_acq_rel_gpu();
-        __syncwarp();
-        if (lane == 0) *reinterpret_cast<volatile unsigned*>(done_flag) = done_seq;
-    }
 }
 
 constexpr int TREE_MAX_CTAS_PER_SM = 8;
@@ -224,7 +218,6 @@ static inline BalWs tree_workspace(unsigned char* wsb, const TreeLayout& l) {
 
 // Optional tree finish of K1 (single history): warp 0 of every CTA enters tree_merge with the CTA's list.  K = 0 disables it.
 struct TreeMerge { BalWs ws; u64* out; int K; };
-inline unsigned* tree_done_flag(const BalWs& ws) { return ws.next + 2; }     // spare counter word of the workspace
 
 // K1b (lookback_balanced.cu): internal launcher shared with the one-call tick in lookback.cu.
 long long lookback_balanced_workspace_bytes(int N, int W);
