@@ -124,6 +124,7 @@ __device__ __forceinline__ float atan_full(float z) {
 
 // np.arctan2(y, avx) for avx >= 0, ANY magnitudes, branch-free: q = min/max in [0, 1] (one MUFU.RCP),
 // octant fix-up, sign of y.  atan2(0, 0) = 0 like NumPy; a NaN input gives NaN.
+template <bool RESTORE_NAN = true>
 __device__ __forceinline__ float atan2_pos_full(float y, float avx) {
     const float ay = fabsf(y);
     const float mx = fmaxf(fmaxf(ay, avx), 1e-30f), mn = fminf(ay, avx);
@@ -131,6 +132,7 @@ __device__ __forceinline__ float atan2_pos_full(float y, float avx) {
     float a = atan_unit(q);
     a = (ay > avx) ? (LLAMPC_PIO2_HI - a) : a;
     a = copysignf(a, y);
+    if (!RESTORE_NAN) return a;                                // caller detects NaN inputs elsewhere (see accel_fast)
     return (y != y || avx != avx) ? (y + avx) : a;             // fmaxf/fminf drop NaN operands: restore them
 }
 

@@ -121,9 +121,11 @@ __device__ __forceinline__ Deriv accel_fast(const Cand& p, const Ctl& u, const D
                                             float& guard) {
     float af, ar;
     if (FULL_SLIP) {
+        // no NaN restoration inside the slip angles: a NaN vx, vy or w also reaches the result through the drivetrain
+        // force and the vy * w / vx * w terms below, and the rollout kernel re-does any step whose increments are NaN
         const float avx = fabsf(vx);
-        af = u.delta - atan2_pos_full(fmaf(p.lf, w, vy), avx);
-        ar = atan2_pos_full(fmaf(p.lr, w, -vy), avx);
+        af = u.delta - atan2_pos_full<false>(fmaf(p.lf, w, vy), avx);
+        ar = atan2_pos_full<false>(fmaf(p.lr, w, -vy), avx);
     } else {
         const float inv = rcp_approx(fabsf(vx));        // 1 ulp: the tangents are small, |error| <= 1.2e-7 |t|
         const float tf = fmaf(p.lf, w, vy) * inv, tr = fmaf(p.lr, w, -vy) * inv;
