@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LLAMPC_ABI_VERSION 2
+#define LLAMPC_ABI_VERSION 3
 
 #define LLAMPC_E_ARG   (-1)  /* null pointer / non-positive size / size not supported       */
 #define LLAMPC_E_ALIGN (-2)  /* pointer or stride not 16-byte aligned                        */
@@ -235,9 +235,15 @@ typedef struct llampc_tick {
                                        (llampc_lookback_window_balanced_f32) instead of K1 + list merge            */
     unsigned long long workspace_bytes;
     void* mapped_dev; const void* mapped_for;   /* internal: device alias of result_h (cudaHostGetDevicePointer), cached */
+    void* graph_state;              /* internal, NULL-initialised: the tick's scoring kernel and fp64 re-score are replayed
+                                       as one CUDA graph whose kernel nodes are re-parameterised every tick (2 us of host
+                                       enqueue time instead of 8 us); freed by llampc_lookback_tick_release            */
 } llampc_tick_t;
 
 int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream);
+
+/* Releases the resources llampc_lookback_tick attached to the struct (graph_state).  Call before discarding it. */
+int llampc_lookback_tick_release(llampc_tick_t* t);
 
 /* Asynchronous use: llampc_lookback_tick with t->sync = 0 only enqueues the work; llampc_lookback_finish waits for
  * the result (polling the zero-copy sequence word, else synchronising the stream) and orders the finalists;

@@ -34,7 +34,7 @@ class Tick(C.Structure):
                 ("pending_seq", C.c_ulonglong), ("pending_words", _i),
                 ("err_ring", _vp), ("rolling", _i),
                 ("workspace", _vp), ("workspace_bytes", C.c_ulonglong),
-                ("mapped_dev", _vp), ("mapped_for", _vp)]
+                ("mapped_dev", _vp), ("mapped_for", _vp), ("graph_state", _vp)]
 
 
 # name -> (restype, argtypes); every symbol declared in include/llampc_b200.h
@@ -60,6 +60,7 @@ PROTOTYPES = {
     "llampc_topk_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "llampc_refine_f64": (_i, [_vp, _i, _vp, _i, _d, _vp, _i, _i, _vp, _vp]),
     "llampc_lookback_tick": (_i, [C.POINTER(Tick), _vp]),
+    "llampc_lookback_tick_release": (_i, [C.POINTER(Tick)]),
     "llampc_lookback_finish": (_i, [C.POINTER(Tick), _vp]),
     "llampc_lookback_decode": (_i, [C.POINTER(Tick), _vp, _vp, _vp]),
     "llampc_tick_sizeof": (_i, []),
@@ -98,7 +99,7 @@ def lib():
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(handle, name)           # AttributeError if the library lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if handle.llampc_abi_version() != 2:
+        if handle.llampc_abi_version() != 3:
             raise LlampcError("libllampc_b200.so ABI version mismatch")
         if handle.llampc_tick_sizeof() != C.sizeof(Tick):
             raise LlampcError("llampc_tick_t layout mismatch between _lib.py and libllampc_b200.so (rebuild the library)")

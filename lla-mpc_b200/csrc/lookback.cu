@@ -17,6 +17,82 @@ namespace llampc {
 constexpr int NUM_SMS = 148;
 
 // ---------------------------------------------------------------------------------------------------
+// Launch helper.  Normally issue() is kern<<<...>>>(...).  While llampc_lookback_tick collects (g_collect set), the
+// launch is recorded instead -- function, shape and a copy of every argument -- and the tick replays its two kernels
+// (scoring + fp64 re-score) as ONE CUDA graph whose kernel nodes are re-parameterised every tick: measured with
+// tools/ubench/graph_launch.cu, 2.0 us of host enqueue time instead of 7.6 us and 3.9 us less from enqueue to the
+// host-visible result.
+// ---------------------------------------------------------------------------------------------------
+struct PendingLaunch {
+    void* func; dim3 grid, block; size_t smem; void* args[24]; int n_args; size_t used;
+    alignas(16) unsigned char store[2048];
+};
+constexpr int TICK_GRAPH_MAX_NODES = 2;
+static thread_local PendingLaunch* g_collect = nullptr;
+static thread_local int g_collect_n = 0;
+
+template <class T>
+static inline void pending_push(PendingLaunch& pl, const T& v) {
+    const size_t off = (pl.used + alignof(T) - 1) & ~(alignof(T) - 1);
+    memcpy(pl.store + off, &v, sizeof(T));
+    pl.args[pl.n_args++] = pl.store + off;
+    pl.used = off + sizeof(T);
+}
+
+template <class... KArgs, class... Args>
+static int issue(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static_assert(sizeof...(KArgs) == sizeof...(Args), "argument count");
+    if (g_collect && g_collect_n < TICK_GRAPH_MAX_NODES) {
+        PendingLaunch& pl = g_collect[g_collect_n++];
+        pl.func = reinterpret_cast<void*>(kern);
+        pl.grid = grid; pl.block = block; pl.smem = smem; pl.n_args = 0; pl.used = 0;
+        (pending_push<KArgs>(pl, static_cast<KArgs>(args)), ...);
+        return 0;
+    }
+    kern<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
+    return (int)cudaGetLastError();
+}
+
+struct TickGraph {
+    cudaGraph_t graph; cudaGraphExec_t exec; cudaGraphNode_t node[TICK_GRAPH_MAX_NODES];
+    void* func[TICK_GRAPH_MAX_NODES]; int n_nodes;
+};
+
+static void tick_graph_destroy(TickGraph* tg) {
+    if (!tg) return;
+    if (tg->exec) cudaGraphExecDestroy(tg->exec);
+    if (tg->graph) cudaGraphDestroy(tg->graph);
+    tg->exec = nullptr; tg->graph = nullptr; tg->n_nodes = 0;
+}
+
+// replays the collected launches as one graph on `st` (created on first use, re-parameterised afterwards)
+static int tick_graph_launch(TickGraph* tg, PendingLaunch* pl, int n, cudaStream_t st) {
+    cudaKernelNodeParams kp[TICK_GRAPH_MAX_NODES];
+    bool same = tg->exec != nullptr && tg->n_nodes == n;
+    for (int i = 0; i < n; ++i) {
+        memset(&kp[i], 0, sizeof(kp[i]));
+        kp[i].func = pl[i].func; kp[i].gridDim = pl[i].grid; kp[i].blockDim = pl[i].block;
+        kp[i].sharedMemBytes = (unsigned)pl[i].smem; kp[i].kernelParams = pl[i].args;
+        same = same && tg->func[i] == pl[i].func;
+    }
+    if (same) {
+        for (int i = 0; i < n && same; ++i)
+            if (cudaGraphExecKernelNodeSetParams(tg->exec, tg->node[i], &kp[i]) != cudaSuccess) { (void)cudaGetLastError(); same = false; }
+    }
+    if (!same) {
+        tick_graph_destroy(tg);
+        LLAMPC_CUDA_TRY(cudaGraphCreate(&tg->graph, 0));
+        for (int i = 0; i < n; ++i) {
+            LLAMPC_CUDA_TRY(cudaGraphAddKernelNode(&tg->node[i], tg->graph, i ? &tg->node[i - 1] : nullptr, i ? 1 : 0, &kp[i]));
+            tg->func[i] = pl[i].func;
+        }
+        LLAMPC_CUDA_TRY(cudaGraphInstantiate(&tg->exec, tg->graph, 0));
+        tg->n_nodes = n;
+    }
+    return (int)cudaGraphLaunch(tg->exec, st);
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K1.  grid = (ceil(N / (128/SY)), n_vehicles); block = 128 threads = (128/SY candidates) x (SY window splits).
 // The W history rows (80 B each) are staged once per CTA with one TMA bulk copy; every warp then reads
 // the same row at the same time (shared-memory broadcast).  Thread (c, sy) integrates window rows
@@ -600,10 +676,9 @@ static int launch_lookback(const float* bank, int N, int Npad, const float* hist
     }
     const int CPB = (packed ? 2 * LB_THREADS : LB_THREADS) / SY;
     dim3 grid((N + CPB - 1) / CPB, n_vehicles);
-    kern<<<grid, LB_THREADS, smem, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, hist, W,
-                                         (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key, cta_lists,
-                                         idx_offset, nr, fm, px, tm);
-    return (int)cudaGetLastError();
+    return issue(kern, grid, dim3(LB_THREADS), smem, st, reinterpret_cast<const float4*>(bank), N, Npad, hist, W,
+                 (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key, cta_lists, idx_offset, nr, fm, px,
+                 tm);
 }
 
 static int lookback_window_impl(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
@@ -686,14 +761,10 @@ static int lookback_rolling_impl(const float* bank, int N, int Npad, const float
     const dim3 grid((N + LB_THREADS - 1) / LB_THREADS, n_vehicles);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     if (geom_shared)
-        lookback_rolling_kernel<true><<<grid, LB_THREADS, 0, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, W,
-                                                                   make_step(Ts), nr, hist, err_ring, avg_err, best_key,
-                                                                   cta_lists, idx_offset, emit, fm);
-    else
-        lookback_rolling_kernel<false><<<grid, LB_THREADS, 0, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, W,
-                                                                    make_step(Ts), nr, hist, err_ring, avg_err, best_key,
-                                                                    cta_lists, idx_offset, emit, fm);
-    return (int)cudaGetLastError();
+        return issue(lookback_rolling_kernel<true>, grid, dim3(LB_THREADS), 0, st, reinterpret_cast<const float4*>(bank), N,
+                     Npad, W, make_step(Ts), nr, hist, err_ring, avg_err, best_key, cta_lists, idx_offset, emit, fm);
+    return issue(lookback_rolling_kernel<false>, grid, dim3(LB_THREADS), 0, st, reinterpret_cast<const float4*>(bank), N, Npad,
+                 W, make_step(Ts), nr, hist, err_ring, avg_err, best_key, cta_lists, idx_offset, emit, fm);
 }
 
 static int merge_lists_impl(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K, llampc_key_t* best_key,
@@ -919,6 +990,27 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
         for (int i = 0; i < LLAMPC_HIST_ROW; ++i) nr.v[i] = t->row32_h[i];
         nr.slot = t->slot;
     }
+    // ---- the two kernels of a tick (scoring + fp64 re-score) are replayed as one re-parameterised CUDA graph when the
+    // tick is a one-launch scoring kernel followed by the re-score (LLAMPC_TICK_GRAPH=0: plain stream launches)
+    static int graph_env = -1;
+    if (graph_env < 0) { const char* e = getenv("LLAMPC_TICK_GRAPH"); graph_env = (e && e[0] == '0') ? 0 : 1; }
+    const int n_lists_roll = (t->N + LB_THREADS - 1) / LB_THREADS;
+    const bool roll_one_launch = t->rolling == 1 && t->ticket != nullptr && Kt > 0 && n_lists_roll <= LB_THREADS * MERGE_LPT &&
+                                 t->err_ring && t->row32_h && fused;
+    const bool tree_one_launch = !t->rolling && fused && t->workspace && Kt > 0;
+    PendingLaunch pending[TICK_GRAPH_MAX_NODES];
+    struct CollectGuard {                                            // never leave the collector armed on an error return
+        bool on;
+        ~CollectGuard() { if (on) { g_collect = nullptr; g_collect_n = 0; } }
+    } guard = {false};
+    if (graph_env && Kt > 0 && t->n_refine > 0 && (roll_one_launch || tree_one_launch)) {
+        if (!t->graph_state) t->graph_state = calloc(1, sizeof(TickGraph));
+        if (t->graph_state) {
+            g_collect = pending;
+            g_collect_n = 0;
+            guard.on = true;
+        }
+    }
     int rc;
     if (t->rolling) {
         // the reference's rolling bookkeeping: one new error column + ring re-sum, then the list merge
@@ -1014,9 +1106,19 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
                 if (gather) return LLAMPC_E_ARG;
             }
         }
-        refine_f64_kernel<<<Kt, RF_THREADS, 0, st>>>(t->bank64, t->N, t->hist64, t->W, t->Ts, keys + 1, t->idx_offset, errs, nr64, fc,
-                                                     pg);
-        LLAMPC_CUDA_TRY(cudaGetLastError());
+        rc = issue(refine_f64_kernel, dim3(Kt), dim3(RF_THREADS), 0, st, t->bank64, t->N, t->hist64, t->W, t->Ts,
+                   static_cast<const u64*>(keys + 1), t->idx_offset, errs, nr64, fc, pg);
+        if (rc) return rc;
+    }
+    if (guard.on) {                                                  // replay what was collected as one graph
+        const int n = g_collect_n;
+        g_collect = nullptr;
+        g_collect_n = 0;
+        guard.on = false;
+        if (n > 0) {
+            rc = tick_graph_launch(static_cast<TickGraph*>(t->graph_state), pending, n, st);
+            if (rc) return rc;
+        }
     }
     if (t->pending_seq == 0)
         LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->result_h, t->result, (size_t)(1 + Kt + (refine ? Kt : 0)) * 8,
@@ -1156,6 +1258,17 @@ extern "C" int llampc_lookback_push(llampc_tick_t* t, const double* x_k, const d
     t->sync = sync_was;
     if (rc) return rc;
     return llampc_lookback_decode(t, idx_out, score_out, n_valid);
+}
+
+// Frees what llampc_lookback_tick attached to the struct (the CUDA graph of the tick).  Safe to call more than once.
+extern "C" int llampc_lookback_tick_release(llampc_tick_t* t) {
+    if (!t) return LLAMPC_E_ARG;
+    if (t->graph_state) {
+        tick_graph_destroy(static_cast<TickGraph*>(t->graph_state));
+        free(t->graph_state);
+        t->graph_state = nullptr;
+    }
+    return 0;
 }
 
 // layout probes for FFI bindings that mirror llampc_tick_t by hand

@@ -168,6 +168,12 @@ class LookBack:
         self._get_device = get_dev if get_dev is not None else torch.cuda.current_device
         self._get_raw_stream = get_raw if get_raw is not None else (lambda i: torch.cuda.current_stream(i).cuda_stream)
 
+    def __del__(self):
+        try:                                                     # frees the CUDA graph the C tick attached to the struct
+            self._L.llampc_lookback_tick_release(self._tick_ref)
+        except Exception:
+            pass
+
     # ------------------------------------------------------------------ history ring
     def _pack_row(self, slot, x_k, u_k, x_k1):
         self._xk[:] = x_k
