@@ -398,6 +398,119 @@ lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W,
 }
 
 // ---------------------------------------------------------------------------------------------------
+// K1v rolling window, ONE CTA PER VEHICLE (Monte-Carlo layout: thousands of vehicles, a bank of <= 2,048 candidates
+// each).  Same arithmetic as K1r (one RK4 step per candidate, ring column `slot` replaced, window re-summed in ring
+// order: scores bit-identical to K1r); what changes is the selection.  K1r sorts every key (a 15-stage register
+// bitonic network per warp, three merges per CTA, a list round trip through L2 and a last-CTA merge per vehicle):
+// ncu showed ~800 of its ~1,200 instructions per candidate-tick in that selection (ALU pipe 48 %, FMA 27 %, HBM 19 %).
+// Here the vehicle's keys stay in shared memory and are FILTERED, not sorted:
+//   1  every (warp, pass) group of 32 keys leaves its minimum (two REDUX) -- <= 64 group minima per vehicle;
+//   2  warp 0 sorts the group minima; T = the K-th smallest.  At least K keys are <= T (those minima themselves), so
+//      the top-K is a subset of {key <= T} -- about K .. 3K keys of the N;
+//   3  the survivors are compacted with a shared-memory counter and warp 0 sorts them 32 at a time
+//      (sort + bitonic merge into the running 32 smallest).  Keys are unique (index in the low word), so the result
+//      does not depend on the compaction order.
+// The W ring lines a warp will re-sum are prefetched into L2 before the RK4 step of the pass (one PREFETCH per warp
+// and pass: lane w asks for row w), so the re-sum loads hit L2 instead of waiting on HBM after the step.
+// ---------------------------------------------------------------------------------------------------
+constexpr int RV_THREADS = 256;
+constexpr int RV_WARPS = RV_THREADS / 32;
+constexpr int RV_MAX_CPT = 8;                      // passes (candidates per thread): N <= 2,048
+constexpr int RV_MAX_N = RV_THREADS * RV_MAX_CPT;
+
+__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+
+template <bool GEOM_SHARED>
+__global__ void __launch_bounds__(RV_THREADS, 3)
+lookback_rolling_vehicle_kernel(const float4* __restrict__ bank, int N, int Npad, int W, StepSize z, int slot,
+                                const float* __restrict__ hist, float* __restrict__ err_ring,
+                                float* __restrict__ avg_err, int idx_offset, int emit, int K, u64* __restrict__ out) {
+    __shared__ float4 srow[5];
+    __shared__ u64 s_key[RV_MAX_N];
+    __shared__ u64 s_cand[RV_MAX_N];
+    __shared__ u64 s_group[RV_WARPS * RV_MAX_CPT];
+    __shared__ u64 s_thr;
+    __shared__ int s_count;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int v = blockIdx.x;
+    const int cpt = (N + RV_THREADS - 1) / RV_THREADS;
+    if (tid < 5) srow[tid] = __ldg(reinterpret_cast<const float4*>(hist + ((size_t)v * W + slot) * LLAMPC_HIST_ROW) + tid);
+    err_ring += (size_t)v * W * Npad;
+    __syncthreads();
+#pragma unroll 1
+    for (int j = 0; j < cpt; ++j) {
+        const int base = j * RV_THREADS + warp * 32;               // first candidate of this warp in this pass
+        const int cand = base + lane;
+        const bool valid = cand < N;
+        const int ci = valid ? cand : N - 1;
+        if (emit && base < N)
+            for (int w = lane; w < W; w += 32)
+                if (w != slot) prefetch_l2(err_ring + (size_t)w * Npad + base);
+        const Cand p = load_cand(bank, Npad, ci);
+        HistRow r;
+        r.q0 = srow[0]; r.q1 = srow[1]; r.q2 = srow[2]; r.q3 = srow[3]; r.q4 = srow[4];
+        bool ok;
+        float e = lookback_step_fast<GEOM_SHARED, false>(p, r, z, ok);
+        if (!ok) e = lookback_step<GEOM_SHARED, false>(p, r, z);
+        e *= 0.25f;                                                // errors of rt.py:349 (mean over the 4 scored states)
+        if (valid) err_ring[(size_t)slot * Npad + cand] = e;
+        if (!emit) continue;                                       // uniform
+        float sum = 0.0f;                                          // window re-sum in ring order, as K1r
+        const float* col = err_ring + ci;
+        int w = 0;
+        for (; w + 8 <= W; w += 8) {
+            float vq[8];
+#pragma unroll
+            for (int q = 0; q < 8; ++q) vq[q] = __ldcg(col + (size_t)(w + q) * Npad);
+#pragma unroll
+            for (int q = 0; q < 8; ++q) sum += (w + q == slot) ? e : vq[q];
+        }
+        for (; w < W; ++w) sum += (w == slot) ? e : __ldcg(col + (size_t)w * Npad);
+        const float err = sum / (float)W;
+        u64 key = ~0ull;
+        if (valid) {
+            if (avg_err) avg_err[(size_t)v * N + cand] = err;
+            key = pack_key(err, (unsigned)(idx_offset + cand));
+        }
+        s_key[j * RV_THREADS + tid] = key;
+        const u64 gmin = warp_min_key(key);
+        if (lane == 0) s_group[j * RV_WARPS + warp] = gmin;
+    }
+    if (!emit) return;
+    __syncthreads();
+    if (warp == 0) {                                               // threshold = K-th smallest group minimum
+        const int ng = RV_WARPS * cpt;
+        u64 a = lane < ng ? s_group[lane] : ~0ull;
+        a = warp_sort_u64(a, lane);
+        if (ng > 32) {
+            u64 b = lane + 32 < ng ? s_group[lane + 32] : ~0ull;
+            b = warp_sort_u64(b, lane);
+            a = warp_merge_low32(a, __shfl_sync(0xffffffffu, b, 31 - lane), lane);
+        }
+        const u64 t = __shfl_sync(0xffffffffu, a, K - 1);          // ~0 when fewer than K groups hold a key: keep all
+        if (lane == 0) { s_thr = t; s_count = 0; }
+    }
+    __syncthreads();
+    const u64 T = s_thr;
+    for (int j = 0; j < cpt; ++j) {
+        const u64 k = s_key[j * RV_THREADS + tid];
+        if (k <= T && k != ~0ull) s_cand[atomicAdd(&s_count, 1)] = k;
+    }
+    __syncthreads();
+    if (warp != 0) return;
+    const int n = s_count;
+    u64 run = ~0ull;
+    for (int c = 0; c < n; c += 32) {
+        u64 k = c + lane < n ? s_cand[c + lane] : ~0ull;
+        k = warp_sort_u64(k, lane);
+        run = c == 0 ? k : warp_merge_low32(run, __shfl_sync(0xffffffffu, k, 31 - lane), lane);
+    }
+    u64* o = out + (size_t)v * (LLAMPC_LIST_LEN + 1);              // out[0] = arg-min key, out[1..K] = ascending top-K
+    if (lane == 0) o[0] = run;
+    if (lane < K) o[1 + lane] = run;
+}
+
+// ---------------------------------------------------------------------------------------------------
 // K4' stand-alone merge of the per-CTA sorted lists written by K1 / K1r into the global top-K (K <= LLAMPC_LIST_LEN),
 // one CTA per vehicle; the algorithm is merge_lists_device (llampc_common.cuh).  Used when a launch produces more
 // than 1,024 lists (otherwise the last CTA of K1 runs the same routine itself); optionally carries the NVLink
@@ -811,6 +924,22 @@ extern "C" int llampc_lookback_rolling_multi_f32(const float* bank, int N, int N
                                                  llampc_stream_t stream) {
     if (!hist) return LLAMPC_E_ARG;
     if (emit && (K < 0 || K > LLAMPC_LIST_LEN)) return LLAMPC_E_RANGE;
+    // banks of <= 2,048 candidates: one CTA per vehicle, top-K by threshold filter in shared memory (K1v; scores and
+    // keys identical to the K1r path below; best_key / cta_lists / ticket are not touched).  LLAMPC_K1R_CTA=0 keeps K1r.
+    const char* sw = getenv("LLAMPC_K1R_CTA");                   // read per call: the parity test flips it
+    if (N > 0 && N <= RV_MAX_N && (!emit || (K > 0 && out)) && !(sw && sw[0] == '0')) {
+        if (!bank || !err_ring || Npad < N || slot < 0 || slot >= W || n_vehicles <= 0) return LLAMPC_E_ARG;
+        if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
+        if (!aligned16(bank) || !aligned16(hist)) return LLAMPC_E_ALIGN;
+        cudaStream_t st = static_cast<cudaStream_t>(stream);
+        if (geom_shared)
+            return issue(lookback_rolling_vehicle_kernel<true>, dim3(n_vehicles), dim3(RV_THREADS), 0, st,
+                         reinterpret_cast<const float4*>(bank), N, Npad, W, make_step(Ts), slot, hist, err_ring, avg_err,
+                         idx_offset, emit, K, out);
+        return issue(lookback_rolling_vehicle_kernel<false>, dim3(n_vehicles), dim3(RV_THREADS), 0, st,
+                     reinterpret_cast<const float4*>(bank), N, Npad, W, make_step(Ts), slot, hist, err_ring, avg_err,
+                     idx_offset, emit, K, out);
+    }
     const int n_lists = (N + LB_THREADS - 1) / LB_THREADS;
     const bool in_kernel = emit && K > 0 && ticket && out && cta_lists && best_key && n_lists <= LB_THREADS * MERGE_LPT;
     FusedMerge fm = {in_kernel ? ticket : nullptr, in_kernel ? out : nullptr, in_kernel ? K : 0};

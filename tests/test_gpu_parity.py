@@ -278,6 +278,73 @@ def test_multi_vehicle_histories(history):
         assert list((oo[v, 1:11] & np.uint64(0xFFFFFFFF)).astype(np.int64)) == list(np.argsort(ref)[:10])
 
 
+@pytest.mark.parametrize("N,W,K", [(1024, 20, 10), (2048, 7, 16), (777, 33, 10), (300, 5, 10), (40, 4, 16), (5, 3, 10),
+                                   (1, 2, 1), (2300, 6, 10)])
+def test_rolling_multi_vehicle_cta_path(history, N, W, K, monkeypatch):
+    """llampc_lookback_rolling_multi_f32, Monte-Carlo layout.  Banks of <= 2,048 candidates run K1v (one CTA per
+    vehicle, top-K by threshold filter); LLAMPC_K1R_CTA=0 keeps K1r (per-CTA sorted lists + last-CTA merge).  Both
+    must give the oracle's window means (rt.py:349-358), arg-min and top-K, and bit-identical scores and keys; the
+    windows fill for W ticks (emit = 0) and then roll for W + 2 more (every ring slot is replaced once)."""
+    import torch
+    from llampc_b200 import _lib
+    from llampc_b200.bank import ModelBank
+    S, U, Ts = history
+    L = _lib.lib()
+    bank_p = orc.make_bank(N, seed=3)
+    bank = ModelBank(bank_p)
+    V = 6
+    t0s = [60, 300, 650, 900, 1300, 1650]
+    n_ticks = 2 * W + 2
+    st = torch.cuda.current_stream().cuda_stream
+    n_lists = (N + 127) // 128
+    res = {}
+    for mode in ("1", "0"):
+        monkeypatch.setenv("LLAMPC_K1R_CTA", mode)
+        hist = torch.zeros((V, W, 20), dtype=torch.float32, device="cuda")
+        ring = torch.zeros((V, W, bank.Npad), dtype=torch.float32, device="cuda")
+        avg = torch.zeros((V, N), dtype=torch.float32, device="cuda")
+        keys = torch.full((V,), -1, dtype=torch.int64, device="cuda")
+        lists = torch.empty((V, n_lists, 16), dtype=torch.int64, device="cuda")
+        ticket = torch.zeros(V, dtype=torch.int32, device="cuda")
+        out = torch.zeros((V, 17), dtype=torch.int64, device="cuda")
+        got = []
+        for i in range(n_ticks):
+            slot = i % W
+            rows = np.zeros((V, 20), dtype=np.float32)
+            for v, t0 in enumerate(t0s):
+                t = t0 + i
+                xk, uk, xk1 = (np.ascontiguousarray(a) for a in (S[:, t], U[:, t], S[:, t + 1]))
+                L.llampc_hist_row_pack_h(xk.ctypes.data, uk.ctypes.data, xk1.ctypes.data, Ts, bank.lf_shared, bank.lr_shared,
+                                         rows[v].ctypes.data, None)
+            hist[:, slot, :] = torch.from_numpy(rows).cuda()
+            full = i + 1 >= W
+            _lib.check(L.llampc_lookback_rolling_multi_f32(bank.packed.data_ptr(), N, bank.Npad, hist.data_ptr(), V, slot, W,
+                                                           Ts, ring.data_ptr(), avg.data_ptr(), keys.data_ptr(),
+                                                           lists.data_ptr(), 0, int(bank.geom_shared), int(full), K,
+                                                           ticket.data_ptr(), out.data_ptr(), st))
+            if full:
+                got.append((i, avg.cpu().numpy().copy(), out.cpu().numpy().view(np.uint64).copy()))
+        res[mode] = got
+    for (i, avg, oo), (_, avg0, oo0) in zip(res["1"], res["0"]):
+        assert np.array_equal(avg, avg0, equal_nan=True), "tick %d: K1v and K1r scores differ" % i
+        assert np.array_equal(oo[:, :K + 1], oo0[:, :K + 1]), "tick %d: K1v and K1r keys differ" % i
+        if i % 3 and i != n_ticks - 1:
+            continue                                               # the oracle on every third tick and the last one
+        for v, t0 in enumerate(t0s):
+            ref = np.mean(orc.window_errors(bank_p, S, U, t0 + i, W, Ts), axis=1)
+            _assert_scores(avg[v].astype(np.float64), ref, "tick %d vehicle %d" % (i, v))
+            kk = min(K, N)
+            idx = (oo[v, 1:1 + kk] & np.uint64(0xFFFFFFFF)).astype(np.int64)
+            order = np.argsort(avg[v], kind="stable")[:kk]          # the kernel ranks its own fp32 scores
+            assert list(idx) == list(order)
+            assert int(oo[v, 0] & np.uint64(0xFFFFFFFF)) == int(order[0])
+            assert (oo[v, 1 + kk:K + 1] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
+            # against the float64 oracle: same arg-min unless the two best scores are closer than the tolerance
+            o64 = np.argsort(ref, kind="stable")
+            if N == 1 or ref[o64[1]] - ref[o64[0]] > 2 * REL_TOL * ref[o64[0]]:
+                assert int(order[0]) == int(o64[0])
+
+
 # ------------------------------------------------------------------------------------------- look-ahead
 def test_lookahead_golden():
     from llampc_b200.mpc import LookAhead
