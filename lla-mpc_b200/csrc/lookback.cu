@@ -332,7 +332,7 @@ lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const 
 // the last column), and the window mean is re-summed from the ring -- N steps and N*W*4 bytes per tick instead
 // of N*W steps.  emit = 0 while the window is filling (columns stored, no decision).
 // ---------------------------------------------------------------------------------------------------
-template <bool GEOM_SHARED>
+template <bool GEOM_SHARED, bool MUFU_SIN>
 __global__ void __launch_bounds__(LB_THREADS)
 lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W, StepSize z, NewRow nr,
                         const float* __restrict__ hist, float* __restrict__ err_ring, float* __restrict__ avg_err,
@@ -357,8 +357,8 @@ lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W,
     }
     err_ring += (size_t)v * W * Npad;
     bool ok;
-    float e = lookback_step_fast<GEOM_SHARED, false>(p, r, z, ok);
-    if (!ok) e = lookback_step<GEOM_SHARED, false>(p, r, z);
+    float e = lookback_step_fast<GEOM_SHARED, MUFU_SIN>(p, r, z, ok);
+    if (!ok) e = lookback_step<GEOM_SHARED, MUFU_SIN>(p, r, z);
     e *= 0.25f;                                    // errors of rt.py:349 (mean over the 4 scored states)
     if (valid) err_ring[(size_t)nr.slot * Npad + cand] = e;
     if (!emit) return;                             // uniform
@@ -400,86 +400,116 @@ lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W,
 // ---------------------------------------------------------------------------------------------------
 // K1v rolling window, ONE CTA PER VEHICLE (Monte-Carlo layout: thousands of vehicles, a bank of <= 2,048 candidates
 // each).  Same arithmetic as K1r (one RK4 step per candidate, ring column `slot` replaced, window re-summed in ring
-// order: scores bit-identical to K1r); what changes is the selection.  K1r sorts every key (a 15-stage register
-// bitonic network per warp, three merges per CTA, a list round trip through L2 and a last-CTA merge per vehicle):
-// ncu showed ~800 of its ~1,200 instructions per candidate-tick in that selection (ALU pipe 48 %, FMA 27 %, HBM 19 %).
-// Here the vehicle's keys stay in shared memory and are FILTERED, not sorted:
-//   1  every (warp, pass) group of 32 keys leaves its minimum (two REDUX) -- <= 64 group minima per vehicle;
-//   2  warp 0 sorts the group minima; T = the K-th smallest.  At least K keys are <= T (those minima themselves), so
-//      the top-K is a subset of {key <= T} -- about K .. 3K keys of the N;
-//   3  the survivors are compacted with a shared-memory counter and warp 0 sorts them 32 at a time
-//      (sort + bitonic merge into the running 32 smallest).  Keys are unique (index in the low word), so the result
-//      does not depend on the compaction order.
-// The W ring lines a warp will re-sum are prefetched into L2 before the RK4 step of the pass (one PREFETCH per warp
-// and pass: lane w asks for row w), so the re-sum loads hit L2 instead of waiting on HBM after the step.
+// order: scores bit-identical to K1r); what changes is everything around the step.  ncu on K1r at 4,096 x 1,024 x 20:
+// ~1,200 instructions per candidate-tick, ~800 of them selection (a 15-stage register bitonic network per warp, three
+// merges per CTA, a list round trip through L2, a last-CTA merge per vehicle: ALU pipe 48 %, FMA 27 %, HBM 19 %).
+//   * Every thread owns FOUR ADJACENT candidates: the ring is re-summed with LDG.128 (5 loads and 10 address
+//     instructions per candidate instead of 20 and 40), the new column is read back by the thread that stored it.
+//   * The vehicle's keys stay in shared memory and are FILTERED, not sorted:
+//       1  every group of 32 keys (warp x candidate slot) leaves its minimum (two REDUX): <= 64 minima per vehicle;
+//       2  warp 0 sorts the minima; T = the K-th smallest.  At least K keys are <= T (those minima themselves), so
+//          the top-K is a subset of {key <= T} -- about K .. 3K keys of the N;
+//       3  the survivors are compacted with a shared-memory counter and warp 0 sorts them 32 at a time (sort +
+//          bitonic merge into the running 32 smallest).  Keys are unique (index in the low word), so the result
+//          does not depend on the compaction order.
+//   * The ring lines a warp will re-sum are prefetched into L2 before its RK4 steps (lane w asks for row w).
+// Needs Npad % 4 == 0 and a 16-byte aligned ring (the entry point falls back to K1r otherwise).
 // ---------------------------------------------------------------------------------------------------
 constexpr int RV_THREADS = 256;
 constexpr int RV_WARPS = RV_THREADS / 32;
-constexpr int RV_MAX_CPT = 8;                      // passes (candidates per thread): N <= 2,048
-constexpr int RV_MAX_N = RV_THREADS * RV_MAX_CPT;
+constexpr int RV_CPP = RV_THREADS * 4;             // candidates per pass
+constexpr int RV_MAX_PASSES = 2;
+constexpr int RV_MAX_N = RV_CPP * RV_MAX_PASSES;   // 2,048
 
-__device__ __forceinline__ void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+__device__ __forceinline__ void prefetch_l2_4lines(const void* p, int n_lines) {
+    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
+    if (n_lines > 1) asm volatile("prefetch.global.L2 [%0+128];" ::"l"(p));
+    if (n_lines > 2) asm volatile("prefetch.global.L2 [%0+256];" ::"l"(p));
+    if (n_lines > 3) asm volatile("prefetch.global.L2 [%0+384];" ::"l"(p));
+}
 
+#ifndef LLAMPC_RV_MIN_BLOCKS
+#define LLAMPC_RV_MIN_BLOCKS 4
+#endif
 template <bool GEOM_SHARED>
-__global__ void __launch_bounds__(RV_THREADS, 3)
+__global__ void __launch_bounds__(RV_THREADS, LLAMPC_RV_MIN_BLOCKS)
 lookback_rolling_vehicle_kernel(const float4* __restrict__ bank, int N, int Npad, int W, StepSize z, int slot,
                                 const float* __restrict__ hist, float* __restrict__ err_ring,
                                 float* __restrict__ avg_err, int idx_offset, int emit, int K, u64* __restrict__ out) {
     __shared__ float4 srow[5];
     __shared__ u64 s_key[RV_MAX_N];
     __shared__ u64 s_cand[RV_MAX_N];
-    __shared__ u64 s_group[RV_WARPS * RV_MAX_CPT];
+    __shared__ u64 s_group[RV_MAX_PASSES * RV_WARPS * 4];
     __shared__ u64 s_thr;
     __shared__ int s_count;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int v = blockIdx.x;
-    const int cpt = (N + RV_THREADS - 1) / RV_THREADS;
+    const int passes = (N + RV_CPP - 1) / RV_CPP;
     if (tid < 5) srow[tid] = __ldg(reinterpret_cast<const float4*>(hist + ((size_t)v * W + slot) * LLAMPC_HIST_ROW) + tid);
     err_ring += (size_t)v * W * Npad;
     __syncthreads();
 #pragma unroll 1
-    for (int j = 0; j < cpt; ++j) {
-        const int base = j * RV_THREADS + warp * 32;               // first candidate of this warp in this pass
-        const int cand = base + lane;
-        const bool valid = cand < N;
-        const int ci = valid ? cand : N - 1;
-        if (emit && base < N)
+    for (int j = 0; j < passes; ++j) {
+        const int wbase = j * RV_CPP + warp * 128;                 // first candidate of this warp in this pass
+        const int c0 = wbase + lane * 4;                           // this thread's candidates c0 .. c0 + 3
+        if (emit && wbase < N) {
+            const int n_lines = min(4, (Npad - wbase) >> 5);
             for (int w = lane; w < W; w += 32)
-                if (w != slot) prefetch_l2(err_ring + (size_t)w * Npad + base);
-        const Cand p = load_cand(bank, Npad, ci);
-        HistRow r;
-        r.q0 = srow[0]; r.q1 = srow[1]; r.q2 = srow[2]; r.q3 = srow[3]; r.q4 = srow[4];
-        bool ok;
-        float e = lookback_step_fast<GEOM_SHARED, false>(p, r, z, ok);
-        if (!ok) e = lookback_step<GEOM_SHARED, false>(p, r, z);
-        e *= 0.25f;                                                // errors of rt.py:349 (mean over the 4 scored states)
-        if (valid) err_ring[(size_t)slot * Npad + cand] = e;
+                if (w != slot) prefetch_l2_4lines(err_ring + (size_t)w * Npad + wbase, n_lines);
+        }
+        u64 key[4] = {~0ull, ~0ull, ~0ull, ~0ull};
+        if (c0 < N) {
+            float* mine = err_ring + (size_t)slot * Npad + c0;
+#pragma unroll 1
+            for (int q = 0; q < 4; ++q) {
+                if (c0 + q >= N) break;
+                const Cand p = load_cand(bank, Npad, c0 + q);
+                HistRow r;
+                r.q0 = srow[0]; r.q1 = srow[1]; r.q2 = srow[2]; r.q3 = srow[3]; r.q4 = srow[4];
+                bool ok;
+                float e = lookback_step_fast<GEOM_SHARED, true>(p, r, z, ok);
+                if (!ok) e = lookback_step<GEOM_SHARED, true>(p, r, z);
+                __stcg(mine + q, 0.25f * e);                       // errors of rt.py:349 (mean over the 4 scored states)
+            }
+            if (emit) {
+                // window re-sum in ring order, as K1r; the new column is read back by the thread that just stored it
+                // (program order), so the loop is loads and adds only.  Columns N .. Npad - 1 are padding.
+                float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                const float* col = err_ring + c0;
+                int w = 0;
+                for (; w + 4 <= W; w += 4, col += (size_t)4 * Npad) {
+                    float4 vq[4];
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) vq[i] = __ldcg(reinterpret_cast<const float4*>(col + (size_t)i * Npad));
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) { sum.x += vq[i].x; sum.y += vq[i].y; sum.z += vq[i].z; sum.w += vq[i].w; }
+                }
+                for (; w < W; ++w, col += Npad) {
+                    const float4 vq = __ldcg(reinterpret_cast<const float4*>(col));
+                    sum.x += vq.x; sum.y += vq.y; sum.z += vq.z; sum.w += vq.w;
+                }
+                const float fw = (float)W;
+                const float err[4] = {sum.x / fw, sum.y / fw, sum.z / fw, sum.w / fw};
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (c0 + q < N) {
+                        if (avg_err) avg_err[(size_t)v * N + c0 + q] = err[q];
+                        key[q] = pack_key(err[q], (unsigned)(idx_offset + c0 + q));
+                    }
+            }
+        }
         if (!emit) continue;                                       // uniform
-        float sum = 0.0f;                                          // window re-sum in ring order, as K1r
-        const float* col = err_ring + ci;
-        int w = 0;
-        for (; w + 8 <= W; w += 8) {
-            float vq[8];
 #pragma unroll
-            for (int q = 0; q < 8; ++q) vq[q] = __ldcg(col + (size_t)(w + q) * Npad);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) sum += (w + q == slot) ? e : vq[q];
+        for (int q = 0; q < 4; ++q) {
+            s_key[j * RV_CPP + q * RV_THREADS + tid] = key[q];     // any order: the filter below scans them all
+            const u64 gmin = warp_min_key(key[q]);
+            if (lane == 0) s_group[(j * RV_WARPS + warp) * 4 + q] = gmin;
         }
-        for (; w < W; ++w) sum += (w == slot) ? e : __ldcg(col + (size_t)w * Npad);
-        const float err = sum / (float)W;
-        u64 key = ~0ull;
-        if (valid) {
-            if (avg_err) avg_err[(size_t)v * N + cand] = err;
-            key = pack_key(err, (unsigned)(idx_offset + cand));
-        }
-        s_key[j * RV_THREADS + tid] = key;
-        const u64 gmin = warp_min_key(key);
-        if (lane == 0) s_group[j * RV_WARPS + warp] = gmin;
     }
     if (!emit) return;
     __syncthreads();
     if (warp == 0) {                                               // threshold = K-th smallest group minimum
-        const int ng = RV_WARPS * cpt;
+        const int ng = passes * RV_WARPS * 4;
         u64 a = lane < ng ? s_group[lane] : ~0ull;
         a = warp_sort_u64(a, lane);
         if (ng > 32) {
@@ -492,8 +522,8 @@ lookback_rolling_vehicle_kernel(const float4* __restrict__ bank, int N, int Npad
     }
     __syncthreads();
     const u64 T = s_thr;
-    for (int j = 0; j < cpt; ++j) {
-        const u64 k = s_key[j * RV_THREADS + tid];
+    for (int i = tid; i < passes * RV_CPP; i += RV_THREADS) {
+        const u64 k = s_key[i];
         if (k <= T && k != ~0ull) s_cand[atomicAdd(&s_count, 1)] = k;
     }
     __syncthreads();
@@ -873,11 +903,12 @@ static int lookback_rolling_impl(const float* bank, int N, int Npad, const float
     nr.slot = slot;
     const dim3 grid((N + LB_THREADS - 1) / LB_THREADS, n_vehicles);
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    if (geom_shared)
-        return issue(lookback_rolling_kernel<true>, grid, dim3(LB_THREADS), 0, st, reinterpret_cast<const float4*>(bank), N,
-                     Npad, W, make_step(Ts), nr, hist, err_ring, avg_err, best_key, cta_lists, idx_offset, emit, fm);
-    return issue(lookback_rolling_kernel<false>, grid, dim3(LB_THREADS), 0, st, reinterpret_cast<const float4*>(bank), N, Npad,
-                 W, make_step(Ts), nr, hist, err_ring, avg_err, best_key, cta_lists, idx_offset, emit, fm);
+    // the single loop keeps the polynomial tyre sine (its tick is latency-bound anyway); the Monte-Carlo layout runs the
+    // SFU sine of the default K1 tick (MUFU.SIN: scores within 2.2e-5 of the oracle)
+    auto kern = hist ? (geom_shared ? lookback_rolling_kernel<true, true> : lookback_rolling_kernel<false, true>)
+                     : (geom_shared ? lookback_rolling_kernel<true, false> : lookback_rolling_kernel<false, false>);
+    return issue(kern, grid, dim3(LB_THREADS), 0, st, reinterpret_cast<const float4*>(bank), N, Npad, W, make_step(Ts), nr,
+                 hist, err_ring, avg_err, best_key, cta_lists, idx_offset, emit, fm);
 }
 
 static int merge_lists_impl(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K, llampc_key_t* best_key,
@@ -927,7 +958,7 @@ extern "C" int llampc_lookback_rolling_multi_f32(const float* bank, int N, int N
     // banks of <= 2,048 candidates: one CTA per vehicle, top-K by threshold filter in shared memory (K1v; scores and
     // keys identical to the K1r path below; best_key / cta_lists / ticket are not touched).  LLAMPC_K1R_CTA=0 keeps K1r.
     const char* sw = getenv("LLAMPC_K1R_CTA");                   // read per call: the parity test flips it
-    if (N > 0 && N <= RV_MAX_N && (!emit || (K > 0 && out)) && !(sw && sw[0] == '0')) {
+    if (N > 0 && N <= RV_MAX_N && Npad % 4 == 0 && aligned16(err_ring) && (!emit || (K > 0 && out)) && !(sw && sw[0] == '0')) {
         if (!bank || !err_ring || Npad < N || slot < 0 || slot >= W || n_vehicles <= 0) return LLAMPC_E_ARG;
         if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
         if (!aligned16(bank) || !aligned16(hist)) return LLAMPC_E_ALIGN;
