@@ -100,7 +100,10 @@ int llampc_lookback_window_topk_f32(const float* bank, int N, int Npad, const fl
 /* K1r for many vehicles (Monte-Carlo layout): the newest row of vehicle v is ring slot `slot` of hist [V][W][20]
  * (written by llampc_pack_rows_f64), err_ring is [V][W][Npad], avg_err [V][N] or NULL, best_key [V] (armed),
  * cta_lists [V][ceil(N/128)][LLAMPC_LIST_LEN], ticket [V] zeroed, out [V][LLAMPC_LIST_LEN + 1].  emit = 0 only stores
- * the error columns (windows still filling); K = 0 skips the top-K. */
+ * the error columns (windows still filling); K = 0 skips the top-K.
+ * Banks of N <= 2,048 with Npad % 4 == 0, K > 0 and out != NULL run K1v (one CTA per vehicle, top-K by threshold filter in
+ * shared memory, SFU tyre sine): same scores and keys, but best_key / cta_lists / ticket are then neither read nor written
+ * (out[0] is the arg-min key either way).  The environment switch LLAMPC_K1R_CTA=0 keeps K1r. */
 int llampc_lookback_rolling_multi_f32(const float* bank, int N, int Npad, const float* hist, int n_vehicles,
                                       int slot, int W, double Ts, float* err_ring, float* avg_err,
                                       llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
