@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LLAMPC_ABI_VERSION 3
+#define LLAMPC_ABI_VERSION 4
 
 #define LLAMPC_E_ARG   (-1)  /* null pointer / non-positive size / size not supported       */
 #define LLAMPC_E_ALIGN (-2)  /* pointer or stride not 16-byte aligned                        */
@@ -361,6 +361,17 @@ int llampc_sample_controls_f32(const float* nominal, const float* eps, int V, in
  * nominal [V][H][2] = that sequence shifted by one step (last input repeated). */
 int llampc_apply_best_f32(const float* U, const int* best_k, int V, int K, int H, float* nominal, float* uprev,
                           double* u_applied, llampc_stream_t stream);
+
+/* Monte-Carlo scenario glue (one launch each instead of a dozen element-wise framework launches per tick).
+ * friction schedule, 'sudden' style of run_nmpc_orca_llampc_nrt_avg_runs.py:163-166: while drop_start[v] < *t_dev <
+ * drop_start[v] + drop_len, columns col0 .. col0 + ncols - 1 (Df, Dr = 8, 9) of plant [V][LLAMPC_NPARAM] doubles are
+ * multiplied by 1 - drop_rate.
+ * advance: model_idx[v] = low word of topk[v * topk_stride] (skipped when topk or model_idx is NULL), x <- x_next
+ * ([V][6] doubles), *t_dev += Ts. */
+int llampc_mc_friction_schedule_f64(double* plant, int V, int col0, int ncols, const double* drop_start,
+                                    double drop_len, double drop_rate, const double* t_dev, llampc_stream_t stream);
+int llampc_mc_advance_tick_f64(const llampc_key_t* topk, int topk_stride, int* model_idx, double* x,
+                               const double* x_next, int V, double* t_dev, double Ts, llampc_stream_t stream);
 
 /* Bank generation / resampling on the device (run_nmpc_orca_llampc_rt.py:145-179: parameter = centre x (1 + sigma
  * randn) for every varied parameter of every model).  center_h / sigma_h: HOST arrays of LLAMPC_NPARAM doubles

@@ -77,6 +77,8 @@ PROTOTYPES = {
     "llampc_mu_estimate_f64": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp]),
     "llampc_sample_controls_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "llampc_apply_best_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
+    "llampc_mc_friction_schedule_f64": (_i, [_vp, _i, _i, _i, _vp, _d, _d, _vp, _vp]),
+    "llampc_mc_advance_tick_f64": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _d, _vp]),
     "llampc_bank_generate_f32": (_i, [_vp, _vp, _i, _i, C.c_ulonglong, _vp, _vp, _vp]),
     "llampc_clock_probe": (_i, [_i, _vp, _vp, _vp]),
     "llampc_plant_rk6_f64": (_i, [_vp, _i, _vp, _vp, _d, _vp, _vp]),
@@ -99,7 +101,7 @@ def lib():
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(handle, name)           # AttributeError if the library lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if handle.llampc_abi_version() != 3:
+        if handle.llampc_abi_version() != 4:
             raise LlampcError("libllampc_b200.so ABI version mismatch")
         if handle.llampc_tick_sizeof() != C.sizeof(Tick):
             raise LlampcError("llampc_tick_t layout mismatch between _lib.py and libllampc_b200.so (rebuild the library)")

@@ -165,6 +165,31 @@ clock_probe_kernel(int iters, unsigned long long* out, float* sink) {
     if (a + c + d == 123.456f) *sink = a;          // keeps the loop alive
 }
 
+// Friction schedule of the Monte-Carlo scenarios ('sudden' style of run_nmpc_orca_llampc_nrt_avg_runs.py:163-166):
+// while drop_start[v] < t < drop_start[v] + drop_len the plant's Df, Dr (columns col0 .. col0 + ncols - 1 of the
+// [V][LLAMPC_NPARAM] table) are multiplied by 1 - drop_rate every tick.  t lives on the device (graph replay).
+__global__ void __launch_bounds__(128)
+friction_schedule_kernel(double* __restrict__ plant, int V, int col0, int ncols, const double* __restrict__ drop_start,
+                         double drop_len, double drop_rate, const double* __restrict__ t_dev) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    const double t = *t_dev, t0 = drop_start[v];
+    if (!(t0 < t && t < t0 + drop_len)) return;
+    const double f = 1.0 - drop_rate;
+    for (int j = 0; j < ncols; ++j) plant[(size_t)v * LLAMPC_NPARAM + col0 + j] *= f;
+}
+
+// End of a closed-loop tick: the selected model of every vehicle (low word of the arg-min key, when `topk` is given),
+// x <- x_next, t <- t + Ts.
+__global__ void __launch_bounds__(128)
+advance_tick_kernel(const u64* __restrict__ topk, int topk_stride, int* __restrict__ model_idx, double* __restrict__ x,
+                    const double* __restrict__ x_next, int V, double* __restrict__ t_dev, double Ts) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i == 0) *t_dev += Ts;
+    if (i < V * 6) x[i] = x_next[i];
+    if (topk && model_idx && i < V) model_idx[i] = (int)(unsigned)(topk[(size_t)i * topk_stride] & 0xffffffffull);
+}
+
 }  // namespace llampc
 
 using namespace llampc;
@@ -220,5 +245,22 @@ extern "C" int llampc_apply_best_f32(const float* U, const int* best_k, int V, i
     apply_best_kernel<<<(V + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
         reinterpret_cast<const float2*>(U), best_k, V, K, H, reinterpret_cast<float2*>(nominal),
         reinterpret_cast<float2*>(uprev), u_applied);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_mc_friction_schedule_f64(double* plant, int V, int col0, int ncols, const double* drop_start,
+                                               double drop_len, double drop_rate, const double* t_dev,
+                                               llampc_stream_t stream) {
+    if (!plant || !drop_start || !t_dev || V <= 0 || col0 < 0 || ncols <= 0 || col0 + ncols > LLAMPC_NPARAM) return LLAMPC_E_ARG;
+    friction_schedule_kernel<<<(V + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(plant, V, col0, ncols, drop_start,
+                                                                                             drop_len, drop_rate, t_dev);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_mc_advance_tick_f64(const llampc_key_t* topk, int topk_stride, int* model_idx, double* x,
+                                          const double* x_next, int V, double* t_dev, double Ts, llampc_stream_t stream) {
+    if (!x || !x_next || !t_dev || V <= 0 || (topk && topk_stride <= 0)) return LLAMPC_E_ARG;
+    advance_tick_kernel<<<(V * 6 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(topk, topk_stride, model_idx, x,
+                                                                                            x_next, V, t_dev, Ts);
     return (int)cudaGetLastError();
 }

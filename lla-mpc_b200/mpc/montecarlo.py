@@ -141,9 +141,8 @@ class MonteCarlo:
                                         self.uprev.data_ptr(), self.u_applied.data_ptr(), st), "apply_best")
             # friction schedule ('sudden' style of run_nmpc_orca_llampc_nrt_avg_runs.py:163-166): Df, Dr decay while the
             # vehicle's drop interval is active
-            t = self.t_dev
-            active = ((self.drop_start < t) & (t < self.drop_start + self.drop_len)).to(torch.float64)
-            self.plant[:, 8:10] *= (1.0 - self.drop_rate * active)[:, None]
+            chk(L.llampc_mc_friction_schedule_f64(self.plant.data_ptr(), V, 8, 2, self.drop_start.data_ptr(), self.drop_len,
+                                                  self.drop_rate, self.t_dev.data_ptr(), st), "friction schedule")
             chk(L.llampc_plant_rk6_f64(self.plant.data_ptr(), V, self.x.data_ptr(), self.u_applied.data_ptr(), self.Ts,
                                        self.x_next.data_ptr(), st), "plant")
             slot = self.tick_count % self.W
@@ -165,9 +164,10 @@ class MonteCarlo:
                 chk(L.llampc_mu_estimate_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.Km, 0, bank.bank64.data_ptr(),
                                              bank.N, V, self.smoothing, self.mu_alpha, 0.95, 9.81, self.mu_state.data_ptr(),
                                              self.curr_mu.data_ptr(), st), "mu_estimate")
-                self.model_idx.copy_((self.topk[:, 0] & 0xFFFFFFFF).to(torch.int32))
-            self.x.copy_(self.x_next)                             # fixed addresses (graph replay)
-            self.t_dev += self.Ts
+            # selected model, x <- x_next, t += Ts in one launch (fixed addresses: graph replay)
+            chk(L.llampc_mc_advance_tick_f64(self.topk.data_ptr() if full else None, _lib.LIST_LEN + 1,
+                                             self.model_idx.data_ptr(), self.x.data_ptr(), self.x_next.data_ptr(), V,
+                                             self.t_dev.data_ptr(), self.Ts, st), "advance tick")
 
     def run(self, n):
         for _ in range(n):

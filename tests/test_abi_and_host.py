@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
         assert n in _lib.PROTOTYPES, "ctypes prototype missing for %s" % n
-    assert lib.llampc_abi_version() == 3
+    assert lib.llampc_abi_version() == 4
     assert b"aligned" in lib.llampc_error_string(-2)
 
 
