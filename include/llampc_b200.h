@@ -366,8 +366,8 @@ int llampc_apply_best_f32(const float* U, const int* best_k, int V, int K, int H
  * friction schedule, 'sudden' style of run_nmpc_orca_llampc_nrt_avg_runs.py:163-166: while drop_start[v] < *t_dev <
  * drop_start[v] + drop_len, columns col0 .. col0 + ncols - 1 (Df, Dr = 8, 9) of plant [V][LLAMPC_NPARAM] doubles are
  * multiplied by 1 - drop_rate.
- * advance: model_idx[v] = low word of topk[v * topk_stride] (skipped when topk or model_idx is NULL), x <- x_next
- * ([V][6] doubles), *t_dev += Ts. */
+ * advance, every part optional: model_idx[v] = low word of topk[v * topk_stride] (skipped when topk or model_idx is
+ * NULL), x <- x_next ([V][6] doubles; both NULL skips it), *t_dev += Ts (NULL skips it). */
 int llampc_mc_friction_schedule_f64(double* plant, int V, int col0, int ncols, const double* drop_start,
                                     double drop_len, double drop_rate, const double* t_dev, llampc_stream_t stream);
 int llampc_mc_advance_tick_f64(const llampc_key_t* topk, int topk_stride, int* model_idx, double* x,

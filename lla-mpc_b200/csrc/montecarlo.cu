@@ -179,14 +179,14 @@ friction_schedule_kernel(double* __restrict__ plant, int V, int col0, int ncols,
     for (int j = 0; j < ncols; ++j) plant[(size_t)v * LLAMPC_NPARAM + col0 + j] *= f;
 }
 
-// End of a closed-loop tick: the selected model of every vehicle (low word of the arg-min key, when `topk` is given),
-// x <- x_next, t <- t + Ts.
+// End of a closed-loop tick, every part optional (NULL skips it): the selected model of every vehicle (low word of the
+// arg-min key), x <- x_next, t <- t + Ts.
 __global__ void __launch_bounds__(128)
 advance_tick_kernel(const u64* __restrict__ topk, int topk_stride, int* __restrict__ model_idx, double* __restrict__ x,
                     const double* __restrict__ x_next, int V, double* __restrict__ t_dev, double Ts) {
     const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i == 0) *t_dev += Ts;
-    if (i < V * 6) x[i] = x_next[i];
+    if (t_dev && i == 0) *t_dev += Ts;
+    if (x && i < V * 6) x[i] = x_next[i];
     if (topk && model_idx && i < V) model_idx[i] = (int)(unsigned)(topk[(size_t)i * topk_stride] & 0xffffffffull);
 }
 
@@ -259,8 +259,8 @@ extern "C" int llampc_mc_friction_schedule_f64(double* plant, int V, int col0, i
 
 extern "C" int llampc_mc_advance_tick_f64(const llampc_key_t* topk, int topk_stride, int* model_idx, double* x,
                                           const double* x_next, int V, double* t_dev, double Ts, llampc_stream_t stream) {
-    if (!x || !x_next || !t_dev || V <= 0 || (topk && topk_stride <= 0)) return LLAMPC_E_ARG;
-    advance_tick_kernel<<<(V * 6 + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(topk, topk_stride, model_idx, x,
+    if (V <= 0 || (topk && topk_stride <= 0) || ((x == nullptr) != (x_next == nullptr))) return LLAMPC_E_ARG;
+    advance_tick_kernel<<<((x ? V * 6 : V) + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(topk, topk_stride, model_idx, x,
                                                                                             x_next, V, t_dev, Ts);
     return (int)cudaGetLastError();
 }

@@ -2,16 +2,21 @@
 tick -- planner, look-ahead over sampled control sequences, plant step, look-back adaptation, friction estimate --
 with every array resident in HBM and no host round trip inside a tick (BASELINE config 4).
 
-Per tick and vehicle (reference loop: run_nmpc_orca_llampc_rt.py:269-389):
+Per tick and vehicle, in the reference's own order (loop body run_nmpc_orca_llampc_rt.py:269-389):
   1. xref   = ConstantSpeed(x[:2], vx, track, H, Ts, projidx, curr_mu, scale)          planner.py:12-67   (rt.py:278-282)
   2. U      = clip(nominal + eps)                K sampled control sequences around the previous best one
   3. J, k*  = look-ahead rollout of the vehicle's CURRENT best model over U, NMPC cost  (replaces the IPOPT solve rt.py:305:
               there is no NLP solver on this path; the controller is best-of-K)
   4. u      = U[k*][0]; nominal = shift(U[k*])
   5. plant: x+ = RK6(x, u; true parameters with the vehicle's friction schedule)         rt.py:274,311
-  6. push (x, u, x+) into the vehicle's history ring; once W transitions are in: score the whole bank over the
-     window, arg-min + top-K per vehicle                                                 rt.py:347-366
-  7. mu estimate from the top-K models                                                   rt.py:326-344
+  6. mu estimate from the top-K models of the PREVIOUS tick's look-back                  rt.py:326-344
+  7. push (x, u, x+) into the vehicle's history ring; once W transitions are in: score the whole bank over the
+     window, arg-min + top-K per vehicle -> the model of the next tick's look-ahead       rt.py:347-366
+
+Because the friction estimate of a tick only needs the previous tick's top-K (that is the reference's order: estimate at
+rt.py:326-344, look-back at :347-366), the look-back of tick t and steps 1-2 of tick t + 1 are independent: `tick()` runs
+them concurrently on two streams (fork after the estimate, join before returning), so after `tick()` the plan (`xref`,
+`U`, `projidx`) is already the one of the NEXT tick; the constructor plans for tick 0.
 """
 import numpy as np
 
@@ -90,6 +95,11 @@ class MonteCarlo:
         self.t_dev = torch.zeros((), dtype=f64, device=dev)
         self.use_graphs = bool(use_graphs)
         self._graphs = {}                                          # ring slot -> captured tick (steady state only)
+        # planner + control sampling of the next tick run beside the look-back of this one (high-priority side stream: the
+        # planner's few latency-bound CTAs must get their SM slots before the look-back fills the machine)
+        self._side = torch.cuda.Stream(device=dev, priority=-1)
+        with torch.cuda.device(self.dev):
+            self._plan(torch.cuda.current_stream().cuda_stream)   # the plan of tick 0
 
     # ------------------------------------------------------------------ one tick, asynchronous on the current stream
     def tick(self):
@@ -120,19 +130,24 @@ class MonteCarlo:
         self.lookahead_steps += V * self.Ks * self.H
         self.tick_count += 1
 
+    def _plan(self, st):
+        """Steps 1-2 for the coming tick: reference path + sampled control sequences (reads x, projidx, curr_mu, nominal)."""
+        L, V, chk = self.L, self.V, _lib.check
+        dev, s, xy, coef, mus = self.table.device_tables()
+        chk(L.llampc_planner_constant_speed_f64(s.data_ptr(), xy.data_ptr(), coef.data_ptr(), mus.data_ptr(), self.table.n,
+                                                self.table.n_mu, self.x.data_ptr(), V, self.projidx.data_ptr(),
+                                                self.curr_mu.data_ptr(), 0, self.H, self.Ts, self.scale,
+                                                self.xref32.data_ptr(), None, self.projidx.data_ptr(), None, st), "planner")
+        chk(L.llampc_sample_controls_f32(self.nominal.data_ptr(), self.eps.data_ptr(), V, self.Ks, self.H,
+                                         self.box.ctypes.data, self.U.data_ptr(), st), "sample_controls")
+
     def _tick_body(self):
         torch, L, V = self.torch, self.L, self.V
-        st = torch.cuda.current_stream().cuda_stream
-        dev, s, xy, coef, mus = self.table.device_tables()
+        main = torch.cuda.current_stream()
+        st = main.cuda_stream
         bank = self.bank
         chk = _lib.check
         with torch.cuda.device(self.dev):
-            chk(L.llampc_planner_constant_speed_f64(s.data_ptr(), xy.data_ptr(), coef.data_ptr(), mus.data_ptr(), self.table.n,
-                                                    self.table.n_mu, self.x.data_ptr(), V, self.projidx.data_ptr(),
-                                                    self.curr_mu.data_ptr(), 0, self.H, self.Ts, self.scale,
-                                                    self.xref32.data_ptr(), None, self.projidx.data_ptr(), None, st), "planner")
-            chk(L.llampc_sample_controls_f32(self.nominal.data_ptr(), self.eps.data_ptr(), V, self.Ks, self.H,
-                                             self.box.ctypes.data, self.U.data_ptr(), st), "sample_controls")
             chk(L.llampc_lookahead_rollout_f32(bank.packed.data_ptr(), bank.Npad, self.model_idx.data_ptr(), V,
                                                self.x.data_ptr(), V, self.U.data_ptr(), self.Ks, self.H,
                                                self.xref32.data_ptr(), self.uprev.data_ptr(), 1 | 2 | 4, self.qrp.ctypes.data,
@@ -148,6 +163,18 @@ class MonteCarlo:
             slot = self.tick_count % self.W
             chk(L.llampc_pack_rows_f64(self.x.data_ptr(), self.u_applied.data_ptr(), self.x_next.data_ptr(), V, self.Ts,
                                        bank.lf_shared, bank.lr_shared, slot, self.W, self.hist.data_ptr(), None, st), "pack_rows")
+            if self.tick_count >= self.W:                          # the previous tick's look-back produced a top-K
+                chk(L.llampc_mu_estimate_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.Km, 0, bank.bank64.data_ptr(),
+                                             bank.N, V, self.smoothing, self.mu_alpha, 0.95, 9.81, self.mu_state.data_ptr(),
+                                             self.curr_mu.data_ptr(), st), "mu_estimate")
+            # fork: x <- x_next, t += Ts, plan of the next tick on the side stream (launched first) ...
+            side = self._side
+            side.wait_stream(main)
+            ss = side.cuda_stream
+            chk(L.llampc_mc_advance_tick_f64(None, 0, None, self.x.data_ptr(), self.x_next.data_ptr(), V,
+                                             self.t_dev.data_ptr(), self.Ts, ss), "advance tick")
+            self._plan(ss)
+            # ... beside the look-back of this tick on the main stream
             full = self.tick_count + 1 >= self.W
             if self.rolling:
                 chk(L.llampc_lookback_rolling_multi_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), V, slot,
@@ -160,14 +187,10 @@ class MonteCarlo:
                                                       V, self.W, self.Ts, None, self.best_key.data_ptr(),
                                                       self.cta_lists.data_ptr(), 0, int(bank.geom_shared), 32, self.Km,
                                                       self.ticket.data_ptr(), self.topk.data_ptr(), st), "lookback+merge")
-            if full:
-                chk(L.llampc_mu_estimate_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.Km, 0, bank.bank64.data_ptr(),
-                                             bank.N, V, self.smoothing, self.mu_alpha, 0.95, 9.81, self.mu_state.data_ptr(),
-                                             self.curr_mu.data_ptr(), st), "mu_estimate")
-            # selected model, x <- x_next, t += Ts in one launch (fixed addresses: graph replay)
-            chk(L.llampc_mc_advance_tick_f64(self.topk.data_ptr() if full else None, _lib.LIST_LEN + 1,
-                                             self.model_idx.data_ptr(), self.x.data_ptr(), self.x_next.data_ptr(), V,
-                                             self.t_dev.data_ptr(), self.Ts, st), "advance tick")
+            if full:                                               # the model of the next tick's look-ahead
+                chk(L.llampc_mc_advance_tick_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.model_idx.data_ptr(), None,
+                                                 None, V, None, self.Ts, st), "model index")
+            main.wait_stream(side)                                 # join
 
     def run(self, n):
         for _ in range(n):

@@ -520,7 +520,9 @@ def test_lookahead_tolerance_tracks_conditioning(history):
 def test_montecarlo_closed_loop_stagewise_parity(lookback_mode):
     """Config C4 at test size: every stage of the device-resident tick is checked against the oracle on the same
     inputs (planner, control sampling, look-ahead cost, controller step, plant RK6, history rows -> look-back
-    arg-min / top-K, friction estimate)."""
+    arg-min / top-K, friction estimate).  The tick follows the reference's order (rt.py:269-366): the friction estimate
+    of a tick uses the PREVIOUS tick's top-K, and the plan (reference path + control samples) of tick t + 1 is made
+    inside tick t beside the look-back, so the plan a tick consumes is the one visible BEFORE the tick."""
     from llampc_b200.mpc.montecarlo import MonteCarlo
     from llampc_b200.tracks import RacelineTable
     from oracle import planner_oracle as po
@@ -545,42 +547,53 @@ def test_montecarlo_closed_loop_stagewise_parity(lookback_mode):
     eps = mc.eps.cpu().numpy().astype(np.float64)
     mus = [orc.MuEstimatorOracle(mass=nominal["mass"]) for _ in range(V)]
     trans = []
-    for tick in range(W + 3):
+    projidx_before_plan = start.copy()                              # what the planner of the coming tick started from
+    prev_order = None                                              # top-K of the previous tick's look-back
+    for tick in range(W + 4):
         pre = mc.host()
         mc.tick()
         post = mc.host()
         x_pre, x_post = pre["x"], post["x"]
         for v in range(V):
-            # 1 planner (float32 output of a float64 computation)
-            xref, pout, _ = po.constant_speed(x_pre[v, :2], x_pre[v, 3], trk, H, Ts, int(pre["projidx"][v]), scale=0.9,
+            # 1 planner (float32 output of a float64 computation): the plan of this tick, made before it
+            xref, pout, _ = po.constant_speed(x_pre[v, :2], x_pre[v, 3], trk, H, Ts, int(projidx_before_plan[v]), scale=0.9,
                                               curr_mu=float(pre["curr_mu"][v]))
-            np.testing.assert_allclose(post["xref"][v], xref, rtol=0, atol=3e-7)
-            assert post["projidx"][v] == pout
+            np.testing.assert_allclose(pre["xref"][v], xref, rtol=0, atol=3e-7)
+            assert pre["projidx"][v] == pout
             # 2 control samples
             Uv = pre["nominal"][v].astype(np.float64)[None] + eps
             Uv[..., 0] = np.clip(Uv[..., 0], -0.1, 1.0)
             Uv[..., 1] = np.clip(Uv[..., 1], -0.35, 0.35)
-            np.testing.assert_allclose(post["U"][v], Uv, rtol=0, atol=1e-6)
+            np.testing.assert_allclose(pre["U"][v], Uv, rtol=0, atol=1e-6)
             # 3 look-ahead cost of the vehicle's current model (inputs as the kernel saw them: float32 tables)
             m = int(pre["model_idx"][v])
             pm = {k: (bank[k][m:m + 1] if np.ndim(bank[k]) else bank[k]) for k in orc.PARAM_NAMES}
-            Jr, bkr = orc.lookahead_rollout(pm, x_pre[v], post["U"][v].astype(np.float64), post["xref"][v].astype(np.float64),
+            Jr, bkr = orc.lookahead_rollout(pm, x_pre[v], pre["U"][v].astype(np.float64), pre["xref"][v].astype(np.float64),
                                             pre["uprev"][v].astype(np.float64), Ts)
             np.testing.assert_allclose(post["J"][v], Jr[0], rtol=2e-4, atol=1e-9)
             bk = int(post["best_k"][v])
             assert post["J"][v][bk] == post["J"][v].min()
             # 4 controller step
-            np.testing.assert_allclose(post["u_applied"][v], post["U"][v][bk][0], rtol=0, atol=0)
-            np.testing.assert_allclose(post["nominal"][v][:-1], post["U"][v][bk][1:], rtol=0, atol=0)
+            np.testing.assert_allclose(post["u_applied"][v], pre["U"][v][bk][0], rtol=0, atol=0)
+            np.testing.assert_allclose(post["nominal"][v][:-1], pre["U"][v][bk][1:], rtol=0, atol=0)
             # 5 plant (true parameters after this tick's friction update)
             pl = dict(zip(orc.PARAM_NAMES, post["plant"][v]))
             np.testing.assert_allclose(x_post[v], orc.rk6_step(pl, x_pre[v], post["u_applied"][v], 0, Ts), rtol=0, atol=1e-12)
         t = tick * Ts
         act = (drop < t) & (t < drop + 0.2)
         np.testing.assert_allclose(post["plant"][:, 8], pre["plant"][:, 8] * np.where(act, 1 - 1 / 22.0, 1.0), rtol=1e-15)
+        np.testing.assert_allclose(post["plant"][:, 9], pre["plant"][:, 9] * np.where(act, 1 - 1 / 22.0, 1.0), rtol=1e-15)
         trans.append((x_pre.copy(), post["u_applied"].copy(), x_post.copy()))
-        # 6-7 look-back and friction estimate once the window is full
+        # 6 friction estimate from the previous tick's top-K (rt.py:326-344 runs before the look-back of the tick)
+        if prev_order is not None:
+            for v in range(V):
+                mu_ref = mus[v].update(bank["Dr"][prev_order[v]], bank["Df"][prev_order[v]])
+                np.testing.assert_allclose(post["curr_mu"][v], mu_ref, rtol=1e-12)
+        else:
+            assert np.array_equal(post["curr_mu"], pre["curr_mu"])
+        # 7 look-back once the window is full: arg-min / top-K, the model of the next tick's look-ahead
         if tick + 1 >= W:
+            prev_order = []
             for v in range(V):
                 errs = np.stack([orc.onestep_errors(bank, a[v], b[v], c[v], Ts) for a, b, c in trans[-W:]], axis=1)
                 avg = errs.mean(axis=1)
@@ -588,10 +601,10 @@ def test_montecarlo_closed_loop_stagewise_parity(lookback_mode):
                 assert post["best_idx"][v] == order[0]
                 assert list(post["topk_idx"][v][:Km]) == list(order[:Km])
                 assert post["model_idx"][v] == order[0]
-                mu_ref = mus[v].update(bank["Dr"][order[:Km]], bank["Df"][order[:Km]])
-                np.testing.assert_allclose(post["curr_mu"][v], mu_ref, rtol=1e-12)
+                prev_order.append(order[:Km])
         else:
             assert np.array_equal(post["model_idx"], pre["model_idx"])
+        projidx_before_plan = pre["projidx"].copy()
 
 
 def test_one_launch_tick_matches_two_launch(history):
