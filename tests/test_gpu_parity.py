@@ -410,6 +410,39 @@ def test_error_codes_without_launch():
     assert L.llampc_lookback_window_f32(d.data_ptr(), 8, 8, d.data_ptr(), 2000, 1, 2000, 0.02, None, k.data_ptr(), None, 0, 1, 0, st) == -3
     assert L.llampc_lookback_window_f32(d.data_ptr() + 4, 8, 8, d.data_ptr(), 2, 1, 2, 0.02, None, k.data_ptr(), None, 0, 1, 0, st) == -2
     assert L.llampc_topk_f32(d.data_ptr(), 10, 0, 100, k.data_ptr(), k.data_ptr(), k.data_ptr(), st) == -3
+    # Monte-Carlo glue (ABI v4): argument checks, and the optional parts of the tick advance
+    d64 = torch.zeros(64, dtype=torch.float64, device="cuda")
+    assert L.llampc_mc_friction_schedule_f64(None, 4, 8, 2, d64.data_ptr(), 0.2, 0.1, d64.data_ptr(), st) == -1
+    assert L.llampc_mc_friction_schedule_f64(d64.data_ptr(), 4, 13, 2, d64.data_ptr(), 0.2, 0.1, d64.data_ptr(), st) == -1
+    assert L.llampc_mc_advance_tick_f64(None, 0, None, d64.data_ptr(), None, 4, d64.data_ptr(), 0.02, st) == -1
+    assert L.llampc_mc_advance_tick_f64(k.data_ptr(), 0, k.data_ptr(), None, None, 1, None, 0.02, st) == -1
+    # rolling look-back, Monte-Carlo layout: same checks on the K1v and the K1r route
+    for n in (8, 4096):
+        assert L.llampc_lookback_rolling_multi_f32(d.data_ptr(), n, n, None, 1, 0, 4, 0.02, d.data_ptr(), None, k.data_ptr(),
+                                                   k.data_ptr(), 0, 1, 1, 10, k.data_ptr(), k.data_ptr(), st) == -1
+        assert L.llampc_lookback_rolling_multi_f32(d.data_ptr(), n, n, d.data_ptr(), 1, 4, 4, 0.02, d.data_ptr(), None,
+                                                   k.data_ptr(), k.data_ptr(), 0, 1, 1, 10, k.data_ptr(), k.data_ptr(), st) == -1
+        assert L.llampc_lookback_rolling_multi_f32(d.data_ptr(), n, n, d.data_ptr(), 1, 0, 4, 0.02, d.data_ptr(), None,
+                                                   k.data_ptr(), k.data_ptr(), 0, 1, 1, 17, k.data_ptr(), k.data_ptr(), st) == -3
+        assert L.llampc_lookback_rolling_multi_f32(d.data_ptr() + 4, n, n, d.data_ptr(), 1, 0, 4, 0.02, d.data_ptr(), None,
+                                                   k.data_ptr(), k.data_ptr(), 0, 1, 1, 10, k.data_ptr(), k.data_ptr(), st) == -2
+    # the advance: model index from the key's low word, state copy, clock -- each part alone
+    keys = torch.tensor([(7 << 32) | 5, (9 << 32) | 3], dtype=torch.int64, device="cuda")
+    mi = torch.zeros(2, dtype=torch.int32, device="cuda")
+    x = torch.zeros((2, 6), dtype=torch.float64, device="cuda")
+    xn = torch.arange(12, dtype=torch.float64, device="cuda").reshape(2, 6)
+    t = torch.zeros((), dtype=torch.float64, device="cuda")
+    assert L.llampc_mc_advance_tick_f64(keys.data_ptr(), 1, mi.data_ptr(), None, None, 2, None, 0.02, st) == 0
+    assert mi.tolist() == [5, 3] and float(t) == 0.0 and float(x.abs().sum()) == 0.0
+    assert L.llampc_mc_advance_tick_f64(None, 0, None, x.data_ptr(), xn.data_ptr(), 2, t.data_ptr(), 0.02, st) == 0
+    assert torch.equal(x, xn) and float(t) == 0.02
+    # the friction schedule multiplies Df, Dr (columns 8, 9) only inside the drop interval
+    plant = torch.ones((3, 14), dtype=torch.float64, device="cuda")
+    t0 = torch.tensor([0.0, 0.015, 0.5], dtype=torch.float64, device="cuda")
+    assert L.llampc_mc_friction_schedule_f64(plant.data_ptr(), 3, 8, 2, t0.data_ptr(), 0.2, 0.25, t.data_ptr(), st) == 0
+    ref = torch.ones((3, 14), dtype=torch.float64)
+    ref[0:2, 8:10] = 0.75                                       # t = 0.02: vehicles 0 and 1 are inside (t0, t0 + 0.2)
+    assert torch.equal(plant.cpu(), ref)
 
 
 def test_lookback_rolling_mode_matches_reference_loop(history):
