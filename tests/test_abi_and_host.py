@@ -158,3 +158,27 @@ def test_tick_struct_layout_matches_c():
     assert lib.llampc_tick_sizeof() == C.sizeof(_lib.Tick)
     for which, field in enumerate(("Ts", "cta_lists", "result_h", "peer_seq", "rolling")):
         assert lib.llampc_tick_offsetof(which) == getattr(_lib.Tick, field).offset, field
+
+
+def test_threshold_filter_selection_argument():
+    """The selection rule of K1v (lookback_rolling_vehicle_kernel) restated in NumPy: keys are split
+    into groups of 32 (warp x candidate slot), T = the K-th smallest group minimum (all ones when fewer than K groups hold a
+    key), and the top-K of the survivors {key <= T} must be the top-K of all keys -- for any bank size, with ties in the
+    score word, missing candidates (all-ones keys) and K up to LLAMPC_LIST_LEN."""
+    rng = np.random.RandomState(7)
+    EMPTY = np.uint64(0xFFFFFFFFFFFFFFFF)
+    for trial in range(300):
+        n = int(rng.choice([1, 2, 5, 31, 32, 33, 300, 512, 777, 1024, 1500, 2048]))
+        K = int(rng.randint(1, 17))
+        passes = (n + 1023) // 1024
+        scores = rng.randint(0, 50 if trial % 3 == 0 else 2 ** 31, size=n).astype(np.uint64)    # trial % 3 == 0: many ties
+        keys = np.full(passes * 1024, EMPTY, dtype=np.uint64)
+        keys[:n] = (scores << np.uint64(32)) | np.arange(n, dtype=np.uint64)
+        # thread t of pass j owns candidates j*1024 + 4t .. + 3; group (j, warp, q) = the q-th candidates of a warp's threads
+        grid = keys.reshape(passes, 8, 32, 4)
+        minima = np.sort(grid.min(axis=2).reshape(-1))
+        T = minima[K - 1]
+        survivors = np.sort(keys[(keys <= T) & (keys != EMPTY)])
+        want = np.sort(keys[:n])[:K]
+        assert len(survivors) >= min(K, n)
+        assert np.array_equal(survivors[:K], want), (n, K)
