@@ -103,7 +103,10 @@ int llampc_lookback_window_topk_f32(const float* bank, int N, int Npad, const fl
  * the error columns (windows still filling); K = 0 skips the top-K.
  * Banks of N <= 2,048 with Npad % 4 == 0, K > 0 and out != NULL run K1v (one CTA per vehicle, top-K by threshold filter in
  * shared memory, SFU tyre sine): same scores and keys, but best_key / cta_lists / ticket are then neither read nor written
- * (out[0] is the arg-min key either way).  The environment switch LLAMPC_K1R_CTA=0 keeps K1r. */
+ * (out[0] is the arg-min key either way).  The environment switch LLAMPC_K1R_CTA=0 keeps K1r.
+ * geom_shared: bit 0 = lf, lr bank-wide (stage-1 slip angles ride in the rows); bit 1 = strict mode, the FMA-pipe polynomial
+ * tyre sine instead of MUFU.SIN (for banks as wide as sigma = 2, plot_comp_time.py:178-192, where single candidates with
+ * C > 9 reach a relative score error of 1.2e-4 with the SFU sine against 3.6e-5 strict: tools/gpu_wide_bank_check.py). */
 int llampc_lookback_rolling_multi_f32(const float* bank, int N, int Npad, const float* hist, int n_vehicles,
                                       int slot, int W, double Ts, float* err_ring, float* avg_err,
                                       llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,

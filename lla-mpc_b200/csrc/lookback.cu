@@ -431,7 +431,7 @@ __device__ __forceinline__ void prefetch_l2_4lines(const void* p, int n_lines) {
 #ifndef LLAMPC_RV_MIN_BLOCKS
 #define LLAMPC_RV_MIN_BLOCKS 4
 #endif
-template <bool GEOM_SHARED>
+template <bool GEOM_SHARED, bool MUFU_SIN>
 __global__ void __launch_bounds__(RV_THREADS, LLAMPC_RV_MIN_BLOCKS)
 lookback_rolling_vehicle_kernel(const float4* __restrict__ bank, int N, int Npad, int W, StepSize z, int slot,
                                 const float* __restrict__ hist, float* __restrict__ err_ring,
@@ -467,8 +467,8 @@ lookback_rolling_vehicle_kernel(const float4* __restrict__ bank, int N, int Npad
                 HistRow r;
                 r.q0 = srow[0]; r.q1 = srow[1]; r.q2 = srow[2]; r.q3 = srow[3]; r.q4 = srow[4];
                 bool ok;
-                float e = lookback_step_fast<GEOM_SHARED, true>(p, r, z, ok);
-                if (!ok) e = lookback_step<GEOM_SHARED, true>(p, r, z);
+                float e = lookback_step_fast<GEOM_SHARED, MUFU_SIN>(p, r, z, ok);
+                if (!ok) e = lookback_step<GEOM_SHARED, MUFU_SIN>(p, r, z);
                 __stcg(mine + q, 0.25f * e);                       // errors of rt.py:349 (mean over the 4 scored states)
             }
             if (emit) {
@@ -905,8 +905,10 @@ static int lookback_rolling_impl(const float* bank, int N, int Npad, const float
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // the single loop keeps the polynomial tyre sine (its tick is latency-bound anyway); the Monte-Carlo layout runs the
     // SFU sine of the default K1 tick (MUFU.SIN: scores within 2.2e-5 of the oracle)
-    auto kern = hist ? (geom_shared ? lookback_rolling_kernel<true, true> : lookback_rolling_kernel<false, true>)
-                     : (geom_shared ? lookback_rolling_kernel<true, false> : lookback_rolling_kernel<false, false>);
+    // (bit 1 of geom_shared asks for the polynomial sine there as well: wide banks, see include/llampc_b200.h)
+    const bool geom = geom_shared & 1, mufu = hist && !(geom_shared & 2);
+    auto kern = mufu ? (geom ? lookback_rolling_kernel<true, true> : lookback_rolling_kernel<false, true>)
+                     : (geom ? lookback_rolling_kernel<true, false> : lookback_rolling_kernel<false, false>);
     return issue(kern, grid, dim3(LB_THREADS), 0, st, reinterpret_cast<const float4*>(bank), N, Npad, W, make_step(Ts), nr,
                  hist, err_ring, avg_err, best_key, cta_lists, idx_offset, emit, fm);
 }
@@ -963,13 +965,11 @@ extern "C" int llampc_lookback_rolling_multi_f32(const float* bank, int N, int N
         if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
         if (!aligned16(bank) || !aligned16(hist)) return LLAMPC_E_ALIGN;
         cudaStream_t st = static_cast<cudaStream_t>(stream);
-        if (geom_shared)
-            return issue(lookback_rolling_vehicle_kernel<true>, dim3(n_vehicles), dim3(RV_THREADS), 0, st,
-                         reinterpret_cast<const float4*>(bank), N, Npad, W, make_step(Ts), slot, hist, err_ring, avg_err,
-                         idx_offset, emit, K, out);
-        return issue(lookback_rolling_vehicle_kernel<false>, dim3(n_vehicles), dim3(RV_THREADS), 0, st,
-                     reinterpret_cast<const float4*>(bank), N, Npad, W, make_step(Ts), slot, hist, err_ring, avg_err,
-                     idx_offset, emit, K, out);
+        const bool geom = geom_shared & 1, strict = geom_shared & 2;
+        auto kern = geom ? (strict ? lookback_rolling_vehicle_kernel<true, false> : lookback_rolling_vehicle_kernel<true, true>)
+                         : (strict ? lookback_rolling_vehicle_kernel<false, false> : lookback_rolling_vehicle_kernel<false, true>);
+        return issue(kern, dim3(n_vehicles), dim3(RV_THREADS), 0, st, reinterpret_cast<const float4*>(bank), N, Npad, W,
+                     make_step(Ts), slot, hist, err_ring, avg_err, idx_offset, emit, K, out);
     }
     const int n_lists = (N + LB_THREADS - 1) / LB_THREADS;
     const bool in_kernel = emit && K > 0 && ticket && out && cta_lists && best_key && n_lists <= LB_THREADS * MERGE_LPT;

@@ -18,6 +18,8 @@ rt.py:326-344, look-back at :347-366), the look-back of tick t and steps 1-2 of 
 them concurrently on two streams (fork after the estimate, join before returning), so after `tick()` the plan (`xref`,
 `U`, `projidx`) is already the one of the NEXT tick; the constructor plans for tick 0.
 """
+import os
+
 import numpy as np
 
 from .. import _lib
@@ -29,7 +31,7 @@ class MonteCarlo:
     def __init__(self, bank_params, table, x_init, projidx_init, plant_params, drop_start, V=None, W=20, K_models=10,
                  K_seq=32, H=20, Ts=0.02, scale=0.9, mu_init=1.0, seed=4, sigma_pwm=0.1, sigma_steer=0.05,
                  drop_rate=1.0 / 22.0, drop_len=0.2, initial_model=0, smoothing_mu=20, mu_alpha=0.08, limits=None,
-                 lookback_mode="rolling", use_graphs=False):
+                 lookback_mode="rolling", use_graphs=False, fast_sin=None):
         torch = _lib.require_cuda()
         self.torch, self.L = torch, _lib.lib()
         self.bank = bank_params if isinstance(bank_params, ModelBank) else ModelBank(bank_params)
@@ -94,6 +96,11 @@ class MonteCarlo:
         # the time of the friction schedule lives on the device so that a whole tick can be replayed as a CUDA graph
         self.t_dev = torch.zeros((), dtype=f64, device=dev)
         self.use_graphs = bool(use_graphs)
+        # tyre sine of the rolling look-back: MUFU.SIN as in the default LookBack tick, or the polynomial (strict mode:
+        # fast_sin=False or LLAMPC_FAST_SIN=0; banks as wide as sigma = 2 hold candidates that need it for the 1e-4 tolerance)
+        if fast_sin is None:
+            fast_sin = os.environ.get("LLAMPC_FAST_SIN", "1") == "1"
+        self.fast_sin = bool(fast_sin)
         self._graphs = {}                                          # ring slot -> captured tick (steady state only)
         # planner + control sampling of the next tick run beside the look-back of this one (high-priority side stream: the
         # planner's few latency-bound CTAs must get their SM slots before the look-back fills the machine)
@@ -180,7 +187,8 @@ class MonteCarlo:
                 chk(L.llampc_lookback_rolling_multi_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), V, slot,
                                                         self.W, self.Ts, self.err_ring.data_ptr(), None,
                                                         self.best_key.data_ptr(), self.cta_lists.data_ptr(), 0,
-                                                        int(bank.geom_shared), int(full), self.Km, self.ticket.data_ptr(),
+                                                        int(bank.geom_shared) | (0 if self.fast_sin else 2), int(full), self.Km,
+                                                        self.ticket.data_ptr(),
                                                         self.topk.data_ptr(), st), "lookback (rolling)")
             elif full:
                 chk(L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), self.W,

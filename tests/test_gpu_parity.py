@@ -278,9 +278,10 @@ def test_multi_vehicle_histories(history):
         assert list((oo[v, 1:11] & np.uint64(0xFFFFFFFF)).astype(np.int64)) == list(np.argsort(ref)[:10])
 
 
-@pytest.mark.parametrize("N,W,K", [(1024, 20, 10), (2048, 7, 16), (777, 33, 10), (300, 5, 10), (40, 4, 16), (5, 3, 10),
-                                   (1, 2, 1), (2300, 6, 10)])
-def test_rolling_multi_vehicle_cta_path(history, N, W, K, monkeypatch):
+@pytest.mark.parametrize("N,W,K,kind", [(1024, 20, 10, "rt"), (2048, 7, 16, "rt"), (777, 33, 10, "rt"), (300, 5, 10, "rt"),
+                                        (40, 4, 16, "rt"), (5, 3, 10, "rt"), (1, 2, 1, "rt"), (2300, 6, 10, "rt"),
+                                        (1024, 8, 10, "wide"), (600, 6, 10, "all14")])
+def test_rolling_multi_vehicle_cta_path(history, N, W, K, kind, monkeypatch):
     """llampc_lookback_rolling_multi_f32, Monte-Carlo layout.  Banks of <= 2,048 candidates run K1v (one CTA per
     vehicle, top-K by threshold filter); LLAMPC_K1R_CTA=0 keeps K1r (per-CTA sorted lists + last-CTA merge).  Both
     must give the oracle's window means (rt.py:349-358), arg-min and top-K, and bit-identical scores and keys; the
@@ -290,8 +291,19 @@ def test_rolling_multi_vehicle_cta_path(history, N, W, K, monkeypatch):
     from llampc_b200.bank import ModelBank
     S, U, Ts = history
     L = _lib.lib()
-    bank_p = orc.make_bank(N, seed=3)
+    if kind == "wide":      # sigma = 2.0 bank of plot_comp_time.py:178-192 (negative / huge B, C, D: guard fallbacks)
+        bank_p = orc.make_bank(N, seed=3, variation=tuple((k, 2.0) for k in ("Br", "Cr", "Dr", "Bf", "Cf", "Df")))
+    elif kind == "all14":   # lf, lr varied: the kernels' generic stage-1 slip path (GEOM_SHARED = false)
+        rng = np.random.RandomState(9)
+        p0 = orc.orca_params()
+        bank_p = {k: p0[k] * (1 + 0.1 * rng.randn(N)) for k in orc.PARAM_NAMES}
+    else:
+        bank_p = orc.make_bank(N, seed=3)
     bank = ModelBank(bank_p)
+    assert bool(bank.geom_shared) == (kind != "all14")
+    # bit 1 = strict mode (polynomial tyre sine): with the SFU sine one candidate of the sigma = 2 bank (C = 9.7) is off by
+    # 1.2e-4 on one of these windows (tools/gpu_wide_bank_check.py), strict stays below 4e-5
+    flags = int(bank.geom_shared) | (2 if kind == "wide" else 0)
     V = 6
     t0s = [60, 300, 650, 900, 1300, 1650]
     n_ticks = 2 * W + 2
@@ -320,7 +332,7 @@ def test_rolling_multi_vehicle_cta_path(history, N, W, K, monkeypatch):
             full = i + 1 >= W
             _lib.check(L.llampc_lookback_rolling_multi_f32(bank.packed.data_ptr(), N, bank.Npad, hist.data_ptr(), V, slot, W,
                                                            Ts, ring.data_ptr(), avg.data_ptr(), keys.data_ptr(),
-                                                           lists.data_ptr(), 0, int(bank.geom_shared), int(full), K,
+                                                           lists.data_ptr(), 0, flags, int(full), K,
                                                            ticket.data_ptr(), out.data_ptr(), st))
             if full:
                 got.append((i, avg.cpu().numpy().copy(), out.cpu().numpy().view(np.uint64).copy()))
