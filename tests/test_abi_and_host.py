@@ -33,9 +33,21 @@ def test_no_compute_without_gpu():
     import torch
     if torch.cuda.is_available():
         pytest.skip("GPU present")
-    from llampc_b200.mpc import LookBack
+    from llampc_b200.mpc import LookBack, LookAhead
+    from llampc_b200.mpc.montecarlo import MonteCarlo
+    from llampc_b200.mpc.evaluate_models_vectorized import evaluate_models_vectorized
+    from llampc_b200.models import Dynamic
+    from llampc_b200.params import ORCA
+    bank = orc.make_bank(16, 0)
     with pytest.raises(_lib.LlampcError):
-        LookBack(orc.make_bank(16, 0), W=4)
+        LookBack(bank, W=4)
+    with pytest.raises(_lib.LlampcError):
+        LookAhead(bank, Ts=0.02)
+    with pytest.raises(_lib.LlampcError):
+        MonteCarlo(bank, None, np.zeros((2, 6)), np.zeros(2, dtype=np.int32), orc.orca_params(), np.zeros(2))
+    with pytest.raises(_lib.LlampcError):                     # the reference's own call (rt.py:349): no CPU fallback either
+        evaluate_models_vectorized([Dynamic(**ORCA())] * 16, 16, np.zeros(6), np.zeros(2), 0.02,
+                                   tuple(bank[k] for k in ("Bf", "Cf", "Df", "Br", "Cr", "Dr")))
 
 
 def _pack(params, N, Npad):
