@@ -24,6 +24,7 @@ extern "C" {
 #define LLAMPC_E_ARG   (-1)  /* null pointer / non-positive size / size not supported       */
 #define LLAMPC_E_ALIGN (-2)  /* pointer or stride not 16-byte aligned                        */
 #define LLAMPC_E_RANGE (-3)  /* W, K, H ... outside the compiled limits                      */
+#define LLAMPC_E_PEER  (-4)  /* multi-GPU exchange: a peer did not deliver within ~1 s; the tick has NO decision */
 
 #define LLAMPC_NPARAM        14   /* lf lr mass Iz Bf Br Cf Cr Df Dr Cm1 Cm2 Cr0 Cr2 (Dynamic.__init__, llampc/models/dynamic.py:24-57) */
 #define LLAMPC_BANK_GROUPS    4   /* packed bank = 4 float4 groups per candidate                */
@@ -118,7 +119,7 @@ int llampc_lookback_rolling_multi_f32(const float* bank, int N, int Npad, const 
  *              4 * world u64 words ([2 parities][world][key, sequence]), zero-initialised, mapped into this process
  *              (CUDA IPC / torch symmetric memory); peer_bufs[rank] is this rank's own buffer
  *   seq        tick counter, identical on every rank, incremented by the caller every call (>= 1)
- * After the launch out[0] holds the GLOBAL arg-min key on every rank (0 if a peer did not arrive within ~1 s);
+ * After the launch out[0] holds the GLOBAL arg-min key on every rank (~0ull = no decision: a peer did not arrive within ~1 s);
  * out[1..K] stay the rank-local top-K.  With more than 1,024 per-CTA lists (shards above 131,072 candidates per
  * split) the exchange is carried by the stand-alone merge kernel instead (two launches, still no NCCL call); the
  * limit is 8,192 lists. */
@@ -347,13 +348,20 @@ int llampc_pack_rows_f64(const double* x_k, const double* u_k, const double* x_k
                          double lf_shared, double lr_shared, int slot, int W, float* hist, double* hist64,
                          llampc_stream_t stream);
 
-/* Friction estimate from the K best candidates (run_nmpc_orca_llampc_rt.py:326-344): mean Dr, Df of the top-K,
- * `smoothing`-tick moving average, / (g m), exponential smoother alpha, x gain.
- *   topk [V][topk_stride] keys as written by llampc_topk_merge_lists ([0] arg-min, [1..K] top-K)
- *   state [V][2*smoothing+3] doubles, zero-initialised by the caller; mu_out [V]. */
+/* Friction estimate from the K best candidates (run_nmpc_orca_llampc_rt.py:326-344): mean Dr, Df of the top-K appended
+ * to the per-vehicle lists Drs_preds / Dfs_preds, MU_pred = (mean of the last `smoothing` entries of each) / (g m) (:341),
+ * display value = exponential smoother (alpha, :103-113) x gain (:344).
+ *   topk [V][topk_stride] keys ([0] arg-min, [1..K] top-K) of the PREVIOUS tick's look-back (ind_best_KM, :360)
+ *   state [V][2*smoothing+3] doubles, zeroed by the caller, then seeded once with llampc_mu_seed_f64
+ *   mu_raw [V]      MU_pred, the raw moving average: what ConstantSpeed receives as curr_mu from tick W + 2 on (:278-280)
+ *   mu_display [V]  or NULL: smoothed x gain, the value the reference only logs / plots (MU_preds, :344, :465)
+ * llampc_mu_seed_f64 appends the n_seed = W + 1 warm-up entries of :326-330 (seed_dr = mu_init m 9.8 lr / (lf + lr),
+ * seed_df = mu_init m 9.8 lf / (lf + lr): note g = 9.8 there and 9.81 in the estimate). */
 int llampc_mu_estimate_f64(const llampc_key_t* topk, int topk_stride, int K, int idx_offset,
                            const double* bank64, int N, int V, int smoothing, double alpha, double gain,
-                           double g, double* state, double* mu_out, llampc_stream_t stream);
+                           double g, double* state, double* mu_raw, double* mu_display, llampc_stream_t stream);
+int llampc_mu_seed_f64(double* state, int V, int smoothing, int n_seed, double seed_dr, double seed_df,
+                       llampc_stream_t stream);
 
 /* Control samples U [V][K][H][2] = clip(nominal [V][H][2] + eps [K][H][2]); box_h (HOST) = pwm_min pwm_max steer_min steer_max
  * (limits of llampc/params/orca.py:29-35). */

@@ -74,7 +74,8 @@ PROTOTYPES = {
     "llampc_planner_constant_speed_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _i, _d, _d,
                                                _vp, _vp, _vp, _vp, _vp]),
     "llampc_pack_rows_f64": (_i, [_vp, _vp, _vp, _i, _d, _d, _d, _i, _i, _vp, _vp, _vp]),
-    "llampc_mu_estimate_f64": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp]),
+    "llampc_mu_estimate_f64": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp]),
+    "llampc_mu_seed_f64": (_i, [_vp, _i, _i, _i, _d, _d, _vp]),
     "llampc_sample_controls_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp]),
     "llampc_apply_best_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "llampc_mc_friction_schedule_f64": (_i, [_vp, _i, _i, _i, _vp, _d, _d, _vp, _vp]),

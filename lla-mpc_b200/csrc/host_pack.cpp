@@ -13,6 +13,7 @@ extern "C" const char* llampc_error_string(int code) {
         case LLAMPC_E_ARG: return "llampc: null pointer or non-positive / unsupported size";
         case LLAMPC_E_ALIGN: return "llampc: pointer or stride is not 16-byte aligned";
         case LLAMPC_E_RANGE: return "llampc: W, K or H outside the compiled limits";
+        case LLAMPC_E_PEER: return "llampc: multi-GPU exchange timed out (a peer rank did not deliver within ~1 s): no decision for this tick";
         default: return code > 0 ? "llampc: CUDA runtime error (value is the cudaError_t)" : "llampc: unknown error";
     }
 }

@@ -634,6 +634,7 @@ struct FinalCopy { const u64* src; volatile u64* dst_host; unsigned* ticket; int
 // stores its finalists into slot `rank` of every peer, waits until its own buffer holds all `world` contributions of
 // this tick, and hands the whole set (world * 2 Kt words after the local arg-min key) to the host.
 struct PeerGather { u64* const* peers; int world; int rank; unsigned seq; int kt; };
+constexpr u64 PEER_FAIL_BIT = 1ull << 63;         // set in the published sequence word when a peer timed out
 
 constexpr int RF_THREADS = 128;                   // 64 window rows at a time x 2 lanes (front / rear tyre) per row
 
@@ -643,6 +644,7 @@ refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__
                   PeerGather pg) {
     __shared__ double spart[RF_THREADS / 32];
     __shared__ bool last_block;
+    __shared__ int peer_fail;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
     if (nr.slot >= 0 && f == 0 && tid < LLAMPC_HIST64_ROW) hist64[(size_t)nr.slot * LLAMPC_HIST64_ROW + tid] = nr.v[tid];
     const long long ci = (long long)(unsigned)(keys[f] & 0xffffffffull) - idx_offset;
@@ -693,12 +695,14 @@ refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__
             }
             __threadfence_system();
             __syncthreads();
+            if (tid == 0) peer_fail = 0;
+            __syncthreads();
             if (tid < pg.world) {
                 reinterpret_cast<volatile u64*>(pg.peers[tid])[my_slot + 2 * pg.kt] = (u64)pg.seq;
                 volatile u64* own = pg.peers[pg.rank] + ((size_t)parity * pg.world + tid) * wpr;
                 const long long t0 = clock64();
                 while (own[2 * pg.kt] != (u64)pg.seq) {
-                    if (clock64() - t0 > 2000000000ll) break;         // ~1 s: give up, the host sees a stale slot
+                    if (clock64() - t0 > 2000000000ll) { peer_fail = 1; break; }   // ~1 s: the peer never arrived
                     __nanosleep(64);
                 }
             }
@@ -706,9 +710,10 @@ refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__
             __syncthreads();
             fc.dst_host[0] = __ldcg(fc.src);
             volatile u64* own = pg.peers[pg.rank] + (size_t)parity * pg.world * wpr;
+            const bool failed = peer_fail != 0;                    // poison: keys ~0, scores NaN, and the flag below
             for (int i = tid; i < 2 * pg.kt * pg.world; i += RF_THREADS) {
                 const int q = i / (2 * pg.kt), j = i % (2 * pg.kt);
-                fc.dst_host[1 + i] = own[(size_t)q * wpr + j];
+                fc.dst_host[1 + i] = failed ? ~0ull : own[(size_t)q * wpr + j];
             }
             words = 1 + 2 * pg.kt * pg.world;
         } else {
@@ -718,7 +723,8 @@ refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__
         __syncthreads();
         if (tid == 0) {
             *fc.ticket = 0;
-            fc.dst_host[words] = fc.seq;
+            // a peer that never arrived is reported in the sequence word (llampc_lookback_finish -> LLAMPC_E_PEER)
+            fc.dst_host[words] = (pg.world > 1 && peer_fail) ? (fc.seq | PEER_FAIL_BIT) : fc.seq;
             __threadfence_system();
         }
     }
@@ -1300,10 +1306,10 @@ extern "C" int llampc_lookback_finish(llampc_tick_t* t, llampc_stream_t stream) 
     if (t->pending_seq != 0) {
         volatile llampc_key_t* flag = reinterpret_cast<volatile llampc_key_t*>(t->result_h) + t->pending_words;
         long spins = 0;
-        while (*flag != t->pending_seq) {
+        while ((*flag & ~PEER_FAIL_BIT) != t->pending_seq) {
             if (++spins > 20000000L) {                               // tens of ms: something is wrong, stop spinning
                 LLAMPC_CUDA_TRY(cudaStreamSynchronize(st));
-                if (*flag != t->pending_seq) return (int)cudaErrorUnknown;
+                if ((*flag & ~PEER_FAIL_BIT) != t->pending_seq) return (int)cudaErrorUnknown;
                 break;
             }
 #if defined(__x86_64__)
@@ -1312,6 +1318,7 @@ extern "C" int llampc_lookback_finish(llampc_tick_t* t, llampc_stream_t stream) 
         }
         __asm__ __volatile__("" ::: "memory");                         // the result words are read after the flag
         t->pending_seq = 0;
+        if (*flag & PEER_FAIL_BIT) return LLAMPC_E_PEER;             // a peer never delivered its finalists: no decision
         if (gather) {
             // host: pick the Kt best of the world * Kt finalists (fp64 score, ties by index; NaN / padding last)
             // and compact them into the single-GPU layout [arg-min | Kt keys | Kt scores]

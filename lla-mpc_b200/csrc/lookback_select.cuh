@@ -63,9 +63,12 @@ struct FusedMerge { unsigned* ticket; u64* out; int K; };
 // host increments identically on every rank each tick.  world = 0 disables it.
 struct PeerXchg { u64* const* peers; int world; int rank; unsigned seq; };
 
+// A peer that never arrives (~1 s) POISONS the result: every lane then returns ~0ull -- "no candidate", which no valid
+// key equals -- instead of a plausible wrong winner; the host side turns it into LLAMPC_E_PEER.
 __device__ __forceinline__ u64 peer_minloc(const PeerXchg& px, u64 my_key, int lane) {
     const int parity = px.seq & 1;
     u64 got = ~0ull;
+    bool ok = true;
     if (lane < px.world) {
         volatile u64* dst = px.peers[lane] + ((size_t)parity * px.world + px.rank) * 2;
         dst[0] = my_key;
@@ -73,14 +76,14 @@ __device__ __forceinline__ u64 peer_minloc(const PeerXchg& px, u64 my_key, int l
         dst[1] = (u64)px.seq;
         volatile u64* src = px.peers[px.rank] + ((size_t)parity * px.world + lane) * 2;
         const long long t0 = clock64();
-        bool ok = true;
         while (src[1] != (u64)px.seq) {
-            if (clock64() - t0 > 2000000000ll) { ok = false; break; }     // ~1 s: a peer never arrived; poison the result
+            if (clock64() - t0 > 2000000000ll) { ok = false; break; }     // ~1 s: a peer never arrived
             __nanosleep(64);
         }
         __threadfence_system();
-        got = ok ? src[0] : 0ull;
+        if (ok) got = src[0];
     }
+    if (!__all_sync(0xffffffffu, ok)) return ~0ull;
     return warp_min_key(got);
 }
 

@@ -25,20 +25,24 @@ pack_rows_kernel(const double* __restrict__ x_k, const double* __restrict__ u_k,
     }
 }
 
-// Friction estimate, one thread per vehicle (rt.py:326-344 + ExponentialSmoother rt.py:100-110):
-//   mean Dr, Df of the K best candidates -> per-vehicle rings of the last `smoothing` ticks ->
-//   mu = (mean(Dr ring) + mean(Df ring)) / (g m) -> exponential smoother (alpha) -> x gain.
-// state [V][2*smoothing + 3] doubles: Dr ring, Df ring, count, smooth value, initialised flag (all zero at start).
+// Friction estimate, one thread per vehicle (run_nmpc_orca_llampc_rt.py:326-344 + ExponentialSmoother :103-113):
+//   mean Dr, Df of the K best candidates are APPENDED to the per-vehicle lists Drs_preds / Dfs_preds (kept as rings of the
+//   last `smoothing` entries), MU_pred = (mean(Drs_preds[-smoothing:]) + mean(Dfs_preds[-smoothing:])) / (g m)  (:341),
+//   MU_preds[-1] = smoother.update(MU_pred) * gain  (:344).
+// The reference feeds the planner with MU_pred, the RAW moving average (:278-280); the smoothed x 0.95 value is only
+// logged and plotted (:344, :465).  Both are written: mu_raw [V] (planner), mu_display [V] (or NULL).
+// state [V][2*smoothing + 3] doubles: Dr ring, Df ring, list length, smooth value, smoother-initialised flag; all zero
+// at start, then seeded by mu_seed_kernel with the warm-up entries of :326-330.
 __global__ void __launch_bounds__(128)
 mu_estimate_kernel(const u64* __restrict__ topk, int topk_stride, int K, int idx_offset, const double* __restrict__ bank64,
                    int N, int V, int smoothing, double alpha, double gain, double g, double* __restrict__ state,
-                   double* __restrict__ mu_out) {
+                   double* __restrict__ mu_raw, double* __restrict__ mu_display) {
     const int v = blockIdx.x * blockDim.x + threadIdx.x;
     if (v >= V) return;
     const u64* keys = topk + (size_t)v * topk_stride + 1;          // [0] is the arg-min key
     const double* Dr = bank64 + (size_t)9 * N;                     // LLAMPC_NPARAM order: ... Df = 8, Dr = 9
     const double* Df = bank64 + (size_t)8 * N;
-    const double mass = bank64[(size_t)2 * N];                     // bank-wide mass (models[0].mass in the reference)
+    const double mass = bank64[(size_t)2 * N];                     // bank-wide mass (params['mass'] in the reference)
     double sdr = 0.0, sdf = 0.0;
     int cnt = 0;
     for (int j = 0; j < K; ++j) {
@@ -61,7 +65,24 @@ mu_estimate_kernel(const u64* __restrict__ topk, int topk_stride, int K, int idx
     sm = (st[2 * smoothing + 2] == 0.0) ? mu : alpha * mu + (1.0 - alpha) * sm;
     st[2 * smoothing + 1] = sm;
     st[2 * smoothing + 2] = 1.0;
-    mu_out[v] = sm * gain;
+    mu_raw[v] = mu;
+    if (mu_display) mu_display[v] = sm * gain;
+}
+
+// Warm-up entries of the friction lists (rt.py:326-330): while idt <= LookBack_W the reference appends the prior
+// Dr = mu_init m 9.8 lr / (lf + lr), Df = mu_init m 9.8 lf / (lf + lr) -- n_seed = W + 1 entries that stay inside the
+// `smoothing`-tick moving average for the first `smoothing` estimates.  Appends n_seed copies to every vehicle's lists.
+__global__ void __launch_bounds__(128)
+mu_seed_kernel(double* __restrict__ state, int V, int smoothing, int n_seed, double seed_dr, double seed_df) {
+    const int v = blockIdx.x * blockDim.x + threadIdx.x;
+    if (v >= V) return;
+    double* st = state + (size_t)v * (2 * smoothing + 3);
+    int n = (int)st[2 * smoothing];
+    for (int j = 0; j < n_seed; ++j, ++n) {
+        st[n % smoothing] = seed_dr;
+        st[smoothing + n % smoothing] = seed_df;
+    }
+    st[2 * smoothing] = (double)n;
 }
 
 // U[v][k][h] = clip(nominal[v][h] + eps[k][h], box)   (control samples around each vehicle's nominal sequence)
@@ -222,10 +243,17 @@ extern "C" int llampc_pack_rows_f64(const double* x_k, const double* u_k, const 
 
 extern "C" int llampc_mu_estimate_f64(const llampc_key_t* topk, int topk_stride, int K, int idx_offset,
                                       const double* bank64, int N, int V, int smoothing, double alpha, double gain,
-                                      double g, double* state, double* mu_out, llampc_stream_t stream) {
-    if (!topk || !bank64 || !state || !mu_out || V <= 0 || K <= 0 || smoothing <= 0 || N <= 0) return LLAMPC_E_ARG;
+                                      double g, double* state, double* mu_raw, double* mu_display, llampc_stream_t stream) {
+    if (!topk || !bank64 || !state || !mu_raw || V <= 0 || K <= 0 || smoothing <= 0 || N <= 0) return LLAMPC_E_ARG;
     mu_estimate_kernel<<<(V + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(
-        topk, topk_stride, K, idx_offset, bank64, N, V, smoothing, alpha, gain, g, state, mu_out);
+        topk, topk_stride, K, idx_offset, bank64, N, V, smoothing, alpha, gain, g, state, mu_raw, mu_display);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int llampc_mu_seed_f64(double* state, int V, int smoothing, int n_seed, double seed_dr, double seed_df,
+                                  llampc_stream_t stream) {
+    if (!state || V <= 0 || smoothing <= 0 || n_seed < 0) return LLAMPC_E_ARG;
+    mu_seed_kernel<<<(V + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(state, V, smoothing, n_seed, seed_dr, seed_df);
     return (int)cudaGetLastError();
 }
 

@@ -2,16 +2,21 @@
 tick -- planner, look-ahead over sampled control sequences, plant step, look-back adaptation, friction estimate --
 with every array resident in HBM and no host round trip inside a tick (BASELINE config 4).
 
-Per tick and vehicle, in the reference's own order (loop body run_nmpc_orca_llampc_rt.py:269-389):
-  1. xref   = ConstantSpeed(x[:2], vx, track, H, Ts, projidx, curr_mu, scale)          planner.py:12-67   (rt.py:278-282)
+Per tick ``idt`` and vehicle, in the reference's own order (loop body run_nmpc_orca_llampc_rt.py:269-389):
+  1. xref   = ConstantSpeed(x[:2], vx, track, H, Ts, projidx[, curr_mu=MU_pred, scale=v_factor])   planner.py:12-67
+              -- the friction estimate and the speed scale only from tick W + 2 on, the planner's defaults
+              (curr_mu = 1, scale = 1) before (rt.py:278-282)
   2. U      = clip(nominal + eps)                K sampled control sequences around the previous best one
   3. J, k*  = look-ahead rollout of the vehicle's CURRENT best model over U, NMPC cost  (replaces the IPOPT solve rt.py:305:
               there is no NLP solver on this path; the controller is best-of-K)
   4. u      = U[k*][0]; nominal = shift(U[k*])
   5. plant: x+ = RK6(x, u; true parameters with the vehicle's friction schedule)         rt.py:274,311
-  6. mu estimate from the top-K models of the PREVIOUS tick's look-back                  rt.py:326-344
-  7. push (x, u, x+) into the vehicle's history ring; once W transitions are in: score the whole bank over the
-     window, arg-min + top-K per vehicle -> the model of the next tick's look-ahead       rt.py:347-366
+  6. friction lists: the W + 1 warm-up seeds while idt <= W (written once at construction), afterwards the mean Dr, Df
+     of the top-K models of the PREVIOUS tick's look-back; MU_pred = raw `smoothing_mu`-tick moving average (feeds the
+     planner), smoothed x 0.95 = the logged value                                          rt.py:326-344
+  7. from tick 1 on (the reference skips the transition of tick 0, rt.py:346): push (x, u, x+) into the vehicle's
+     history ring; once W transitions are in (tick W): score the whole bank over the window, arg-min + top-K per
+     vehicle -> the model of the next tick's look-ahead                                    rt.py:347-366
 
 Because the friction estimate of a tick only needs the previous tick's top-K (that is the reference's order: estimate at
 rt.py:326-344, look-back at :347-366), the look-back of tick t and steps 1-2 of tick t + 1 are independent: `tick()` runs
@@ -56,10 +61,21 @@ class MonteCarlo:
         self.drop_start = dv(np.broadcast_to(np.asarray(drop_start, dtype=np.float64), (V,)), f64)
         self.drop_rate, self.drop_len = float(drop_rate), float(drop_len)
         self.projidx = dv(np.broadcast_to(np.asarray(projidx_init), (V,)).astype(np.int32), i32)
-        self.curr_mu = torch.full((V,), float(mu_init), dtype=f64, device=dev)
+        # friction estimate (rt.py:326-344): mu_pred = MU_pred, the raw moving average the planner receives from tick
+        # W + 2 on (rt.py:278-280); mu_display = smoothed x 0.95, the value the reference logs (MU_preds); mu_default = the
+        # planner's default curr_mu = 1 used before (planner.py:12)
+        self.mu_pred = torch.full((V,), float("nan"), dtype=f64, device=dev)
+        self.mu_display = torch.full((V,), float(mu_init), dtype=f64, device=dev)
+        self.mu_default = torch.ones((V,), dtype=f64, device=dev)
         self.smoothing = int(smoothing_mu)
         self.mu_alpha = float(mu_alpha)
         self.mu_state = torch.zeros((V, 2 * self.smoothing + 3), dtype=f64, device=dev)
+        m0, lf0, lr0 = (float(np.ravel(self.bank.param(k, 0))[0]) for k in ("mass", "lf", "lr"))
+        with torch.cuda.device(dev):                               # the W + 1 warm-up entries of rt.py:326-330 (g = 9.8)
+            _lib.check(self.L.llampc_mu_seed_f64(self.mu_state.data_ptr(), V, self.smoothing, W + 1,
+                                                 float(mu_init) * m0 * 9.8 * lr0 / (lf0 + lr0),
+                                                 float(mu_init) * m0 * 9.8 * lf0 / (lf0 + lr0),
+                                                 torch.cuda.current_stream().cuda_stream), "mu_seed")
         lim = limits or {"min_pwm": -0.1, "max_pwm": 1.0, "min_steer": -0.35, "max_steer": 0.35}
         self.box = np.array([lim["min_pwm"], lim["max_pwm"], lim["min_steer"], lim["max_steer"]], dtype=np.float32)
         rng = np.random.RandomState(seed)
@@ -106,7 +122,7 @@ class MonteCarlo:
         # planner's few latency-bound CTAs must get their SM slots before the look-back fills the machine)
         self._side = torch.cuda.Stream(device=dev, priority=-1)
         with torch.cuda.device(self.dev):
-            self._plan(torch.cuda.current_stream().cuda_stream)   # the plan of tick 0
+            self._plan(torch.cuda.current_stream().cuda_stream, 0)   # the plan of tick 0
 
     # ------------------------------------------------------------------ one tick, asynchronous on the current stream
     def tick(self):
@@ -131,19 +147,22 @@ class MonteCarlo:
     def _after_tick(self):
         V, bank = self.V, self.bank
         if self.rolling:
-            self.lookback_steps += V * bank.N
-        elif self.tick_count + 1 >= self.W:
+            self.lookback_steps += V * bank.N if self.tick_count >= 1 else 0
+        elif self.tick_count >= self.W:
             self.lookback_steps += V * bank.N * self.W
         self.lookahead_steps += V * self.Ks * self.H
         self.tick_count += 1
 
-    def _plan(self, st):
-        """Steps 1-2 for the coming tick: reference path + sampled control sequences (reads x, projidx, curr_mu, nominal)."""
+    def _plan(self, st, idt):
+        """Steps 1-2 for tick `idt`: reference path + sampled control sequences (reads x, projidx, mu_pred, nominal).  The
+        planner gets MU_pred and scale = v_factor only when idt > W + 1, its defaults (1, 1) before (rt.py:278-282)."""
         L, V, chk = self.L, self.V, _lib.check
         dev, s, xy, coef, mus = self.table.device_tables()
+        fed = idt > self.W + 1
         chk(L.llampc_planner_constant_speed_f64(s.data_ptr(), xy.data_ptr(), coef.data_ptr(), mus.data_ptr(), self.table.n,
                                                 self.table.n_mu, self.x.data_ptr(), V, self.projidx.data_ptr(),
-                                                self.curr_mu.data_ptr(), 0, self.H, self.Ts, self.scale,
+                                                (self.mu_pred if fed else self.mu_default).data_ptr(), 0, self.H, self.Ts,
+                                                self.scale if fed else 1.0,
                                                 self.xref32.data_ptr(), None, self.projidx.data_ptr(), None, st), "planner")
         chk(L.llampc_sample_controls_f32(self.nominal.data_ptr(), self.eps.data_ptr(), V, self.Ks, self.H,
                                          self.box.ctypes.data, self.U.data_ptr(), st), "sample_controls")
@@ -167,30 +186,33 @@ class MonteCarlo:
                                                   self.drop_rate, self.t_dev.data_ptr(), st), "friction schedule")
             chk(L.llampc_plant_rk6_f64(self.plant.data_ptr(), V, self.x.data_ptr(), self.u_applied.data_ptr(), self.Ts,
                                        self.x_next.data_ptr(), st), "plant")
-            slot = self.tick_count % self.W
-            chk(L.llampc_pack_rows_f64(self.x.data_ptr(), self.u_applied.data_ptr(), self.x_next.data_ptr(), V, self.Ts,
-                                       bank.lf_shared, bank.lr_shared, slot, self.W, self.hist.data_ptr(), None, st), "pack_rows")
-            if self.tick_count >= self.W:                          # the previous tick's look-back produced a top-K
+            idt = self.tick_count
+            pushing = idt > 0                                      # rt.py:346: the transition of tick 0 is not scored
+            slot = (idt - 1) % self.W
+            if pushing:
+                chk(L.llampc_pack_rows_f64(self.x.data_ptr(), self.u_applied.data_ptr(), self.x_next.data_ptr(), V, self.Ts,
+                                           bank.lf_shared, bank.lr_shared, slot, self.W, self.hist.data_ptr(), None, st), "pack_rows")
+            if idt > self.W:                                       # rt.py:331-344: the previous tick's look-back left a top-K
                 chk(L.llampc_mu_estimate_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.Km, 0, bank.bank64.data_ptr(),
                                              bank.N, V, self.smoothing, self.mu_alpha, 0.95, 9.81, self.mu_state.data_ptr(),
-                                             self.curr_mu.data_ptr(), st), "mu_estimate")
+                                             self.mu_pred.data_ptr(), self.mu_display.data_ptr(), st), "mu_estimate")
             # fork: x <- x_next, t += Ts, plan of the next tick on the side stream (launched first) ...
             side = self._side
             side.wait_stream(main)
             ss = side.cuda_stream
             chk(L.llampc_mc_advance_tick_f64(None, 0, None, self.x.data_ptr(), self.x_next.data_ptr(), V,
                                              self.t_dev.data_ptr(), self.Ts, ss), "advance tick")
-            self._plan(ss)
+            self._plan(ss, idt + 1)
             # ... beside the look-back of this tick on the main stream
-            full = self.tick_count + 1 >= self.W
-            if self.rolling:
+            full = idt >= self.W
+            if pushing and self.rolling:
                 chk(L.llampc_lookback_rolling_multi_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), V, slot,
                                                         self.W, self.Ts, self.err_ring.data_ptr(), None,
                                                         self.best_key.data_ptr(), self.cta_lists.data_ptr(), 0,
                                                         int(bank.geom_shared) | (0 if self.fast_sin else 2), int(full), self.Km,
                                                         self.ticket.data_ptr(),
                                                         self.topk.data_ptr(), st), "lookback (rolling)")
-            elif full:
+            elif pushing and full:
                 chk(L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), self.W,
                                                       V, self.W, self.Ts, None, self.best_key.data_ptr(),
                                                       self.cta_lists.data_ptr(), 0, int(bank.geom_shared), 32, self.Km,
@@ -210,7 +232,8 @@ class MonteCarlo:
         c = lambda t: t.cpu().numpy()
         keys = c(self.topk).view(np.uint64)
         return {
-            "x": c(self.x), "projidx": c(self.projidx), "curr_mu": c(self.curr_mu), "model_idx": c(self.model_idx),
+            "x": c(self.x), "projidx": c(self.projidx), "mu_pred": c(self.mu_pred), "mu_display": c(self.mu_display),
+            "model_idx": c(self.model_idx),
             "xref": np.swapaxes(c(self.xref32)[:V * (H + 1) * 2].reshape(V, H + 1, 2), 1, 2),
             "U": c(self.U)[:V * Ks * H * 2].reshape(V, Ks, H, 2), "J": c(self.J), "best_k": c(self.best_k),
             "u_applied": c(self.u_applied), "nominal": c(self.nominal), "uprev": c(self.uprev), "plant": c(self.plant),

@@ -234,23 +234,43 @@ class LookBackOracle:
 
 
 # --------------------------------------------------------------------------------------
-# llampc/mpc/run_nmpc_orca_llampc_rt.py:326-344 -- friction estimate from the K best models
+# llampc/mpc/run_nmpc_orca_llampc_rt.py:326-344 -- friction estimate from the K best models, and which value the
+# planner call :278-282 receives.  Pinned against tests/golden/mu_replay.npz (the reference's own lines executed over the
+# recorded dataset by tests/golden/make_golden_mu.py).
 # --------------------------------------------------------------------------------------
 class MuEstimatorOracle:
-    def __init__(self, mass, smoothing_mu=20, alpha=0.08, gain=0.95):
-        self.mass, self.smoothing_mu, self.alpha, self.gain = mass, smoothing_mu, alpha, gain
-        self.Drs_preds, self.Dfs_preds, self.smooth_value = [], [], None
+    """Per-tick restatement.  ``tick(idt, ind_best_KM, Dr_bank, Df_bank)`` is the block :326-344 of tick ``idt``;
+    ``MU_pred`` is the raw moving average of :341 (NaN until tick W + 1), ``MU_preds`` the logged list of :330/:344."""
 
-    def update(self, best_Dr, best_Df):
-        self.Drs_preds.append(np.mean(best_Dr))
-        self.Dfs_preds.append(np.mean(best_Df))
-        mu = (np.mean(np.array(self.Drs_preds)[-self.smoothing_mu:])
-              + np.mean(np.array(self.Dfs_preds)[-self.smoothing_mu:])) / (9.81 * self.mass)
-        if self.smooth_value is None:          # rt.py:105-110 ExponentialSmoother
-            self.smooth_value = mu
-        else:
-            self.smooth_value = self.alpha * mu + (1 - self.alpha) * self.smooth_value
-        return self.smooth_value * self.gain
+    def __init__(self, mass, lf, lr, W, smoothing_mu=20, alpha=0.08, mu_init=1.0, v_factor=0.9):
+        self.mass, self.lf, self.lr, self.W = mass, lf, lr, W
+        self.smoothing_mu, self.alpha, self.mu_init, self.v_factor = smoothing_mu, alpha, mu_init, v_factor
+        self.Drs_preds, self.Dfs_preds, self.MU_preds = [], [], []
+        self.MU_pred = np.nan
+        self.smooth_value = None                # ExponentialSmoother state, rt.py:103-113
+
+    def tick(self, idt, ind_best_KM=None, Dr_bank=None, Df_bank=None):
+        if idt <= self.W:                                                   # :326-330 (g = 9.8 here)
+            self.Drs_preds.append(self.mu_init * self.mass * 9.8 * self.lr / (self.lf + self.lr))
+            self.Dfs_preds.append(self.mu_init * self.mass * 9.8 * self.lf / (self.lf + self.lr))
+            self.MU_preds.append(self.mu_init)
+        else:                                                               # :331-344 (g = 9.81 here)
+            bestKDr = [Dr_bank[i] for i in ind_best_KM]
+            bestKDf = [Df_bank[i] for i in ind_best_KM]
+            self.Drs_preds.append(np.mean(bestKDr))
+            self.Dfs_preds.append(np.mean(bestKDf))
+            self.MU_pred = (np.mean(np.array(self.Drs_preds)[-self.smoothing_mu:])
+                            + np.mean(np.array(self.Dfs_preds)[-self.smoothing_mu:])) / (9.81 * self.mass)
+            if self.smooth_value is None:
+                self.smooth_value = self.MU_pred
+            else:
+                self.smooth_value = self.alpha * self.MU_pred + (1 - self.alpha) * self.smooth_value
+            self.MU_preds.append(self.smooth_value * .95)
+        return self.MU_pred
+
+    def planner_mu_scale(self, idt):
+        """(curr_mu, scale) of the ConstantSpeed call of tick idt, rt.py:278-282 (defaults of planner.py:12 before W + 2)."""
+        return (self.MU_pred, self.v_factor) if idt > self.W + 1 else (1., 1.)
 
 
 # --------------------------------------------------------------------------------------

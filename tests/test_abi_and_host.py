@@ -115,13 +115,30 @@ def test_orca_matches_oracle_constants():
         ORCA(control="torque")
 
 
-def test_mu_estimator_matches_oracle():
+@pytest.mark.parametrize("tag", ["a", "b"])
+def test_mu_estimator_matches_reference_replay(tag):
+    """Host MuEstimator against the golden made by the reference's own lines (rt.py:278-282, :326-344): raw MU_pred for
+    the planner, smoothed x 0.95 for logging, W + 1 warm-up seeds, planner fed from tick W + 2 on -- to 1e-12 from tick 0."""
+    from conftest import load_golden
     from llampc_b200.mpc.mu_estimator import MuEstimator
-    a, b = MuEstimator(mass=0.041), orc.MuEstimatorOracle(mass=0.041)
-    rng = np.random.RandomState(0)
-    for _ in range(40):
-        dr, df = 0.17 + 0.01 * rng.randn(10), 0.19 + 0.01 * rng.randn(10)
-        assert a.update(dr, df) == b.update(dr, df)
+    g = load_golden("mu_replay.npz")
+    G = {k[2:]: g[k] for k in g.files if k.startswith(tag + "_")}
+    W = int(G["LookBack_W"])
+    est = MuEstimator(mass=float(G["mass"]), lf=float(G["lf"]), lr=float(G["lr"]), W=W, smoothing_mu=int(G["smoothing_mu"]),
+                      alpha=float(G["mu_alpha"]), mu_init=float(G["mu_init"]), v_factor=float(G["v_factor"]))
+    for idt in range(int(G["n_ticks"])):
+        kw = est.planner_args(idt)
+        assert kw.get("scale", 1.0) == G["planner_scale"][idt]
+        np.testing.assert_allclose(kw.get("curr_mu", 1.0), G["planner_mu"][idt], rtol=1e-12, atol=0)
+        top = G["ind_best_KM"][idt - 1] if idt > 0 else None
+        mu = est.tick(idt, None if idt <= W else G["Dr_bank"][top], None if idt <= W else G["Df_bank"][top])
+        if idt <= W:
+            assert mu is None and est.MU_pred is None
+        else:
+            np.testing.assert_allclose(mu, G["MU_pred"][idt], rtol=1e-12, atol=0)
+        np.testing.assert_allclose(est.mu_display, G["MU_preds"][idt], rtol=1e-12, atol=0)
+    with pytest.raises(ValueError):
+        est.tick(W + 50)                                            # past warm-up the top-K parameters are required
 
 
 def test_raceline_table_coefficients_match_reference_splines():

@@ -590,19 +590,26 @@ def test_montecarlo_closed_loop_stagewise_parity(lookback_mode):
     mc = MonteCarlo(bank, tab, x_init, start, nominal, drop, W=W, K_models=Km, K_seq=Ks, H=H, Ts=Ts, seed=4,
                     lookback_mode=lookback_mode)
     eps = mc.eps.cpu().numpy().astype(np.float64)
-    mus = [orc.MuEstimatorOracle(mass=nominal["mass"]) for _ in range(V)]
+    mus = [orc.MuEstimatorOracle(mass=nominal["mass"], lf=nominal["lf"], lr=nominal["lr"], W=W) for _ in range(V)]
     trans = []
     projidx_before_plan = start.copy()                              # what the planner of the coming tick started from
     prev_order = None                                              # top-K of the previous tick's look-back
-    for tick in range(W + 4):
+    for tick in range(W + 6):
         pre = mc.host()
         mc.tick()
         post = mc.host()
         x_pre, x_post = pre["x"], post["x"]
         for v in range(V):
-            # 1 planner (float32 output of a float64 computation): the plan of this tick, made before it
-            xref, pout, _ = po.constant_speed(x_pre[v, :2], x_pre[v, 3], trk, H, Ts, int(projidx_before_plan[v]), scale=0.9,
-                                              curr_mu=float(pre["curr_mu"][v]))
+            # 1 planner (float32 output of a float64 computation): the plan of this tick, made before it.  The raw
+            # moving average MU_pred and scale = v_factor only from tick W + 2 on, the planner's defaults before
+            # (rt.py:278-282)
+            mu_ref, scale_ref = mus[v].planner_mu_scale(tick)
+            if tick > W + 1:
+                np.testing.assert_allclose(pre["mu_pred"][v], mu_ref, rtol=1e-12)
+                assert scale_ref == 0.9
+                mu_ref = pre["mu_pred"][v]                          # the planner consumed the device value
+            xref, pout, _ = po.constant_speed(x_pre[v, :2], x_pre[v, 3], trk, H, Ts, int(projidx_before_plan[v]),
+                                              scale=scale_ref, curr_mu=float(mu_ref))
             np.testing.assert_allclose(pre["xref"][v], xref, rtol=0, atol=3e-7)
             assert pre["projidx"][v] == pout
             # 2 control samples
@@ -628,16 +635,20 @@ def test_montecarlo_closed_loop_stagewise_parity(lookback_mode):
         act = (drop < t) & (t < drop + 0.2)
         np.testing.assert_allclose(post["plant"][:, 8], pre["plant"][:, 8] * np.where(act, 1 - 1 / 22.0, 1.0), rtol=1e-15)
         np.testing.assert_allclose(post["plant"][:, 9], pre["plant"][:, 9] * np.where(act, 1 - 1 / 22.0, 1.0), rtol=1e-15)
-        trans.append((x_pre.copy(), post["u_applied"].copy(), x_post.copy()))
-        # 6 friction estimate from the previous tick's top-K (rt.py:326-344 runs before the look-back of the tick)
-        if prev_order is not None:
-            for v in range(V):
-                mu_ref = mus[v].update(bank["Dr"][prev_order[v]], bank["Df"][prev_order[v]])
-                np.testing.assert_allclose(post["curr_mu"][v], mu_ref, rtol=1e-12)
-        else:
-            assert np.array_equal(post["curr_mu"], pre["curr_mu"])
-        # 7 look-back once the window is full: arg-min / top-K, the model of the next tick's look-ahead
-        if tick + 1 >= W:
+        if tick > 0:                                                # rt.py:346: the transition of tick 0 is not scored
+            trans.append((x_pre.copy(), post["u_applied"].copy(), x_post.copy()))
+        # 6 friction estimate (rt.py:326-344, before the look-back of the tick): W + 1 warm-up seeds, then the previous
+        # tick's top-K; mu_pred = raw moving average (planner), mu_display = smoothed x 0.95 (logged)
+        for v in range(V):
+            mus[v].tick(tick, None if prev_order is None else prev_order[v], bank["Dr"], bank["Df"])
+            if tick > W:
+                np.testing.assert_allclose(post["mu_pred"][v], mus[v].MU_pred, rtol=1e-12)
+                assert abs(post["mu_pred"][v] - post["mu_display"][v]) > 0.03
+            else:
+                assert np.isnan(post["mu_pred"][v])
+            np.testing.assert_allclose(post["mu_display"][v], mus[v].MU_preds[-1], rtol=1e-12)
+        # 7 look-back once the window is full (tick W): arg-min / top-K, the model of the next tick's look-ahead
+        if tick >= W:
             prev_order = []
             for v in range(V):
                 errs = np.stack([orc.onestep_errors(bank, a[v], b[v], c[v], Ts) for a, b, c in trans[-W:]], axis=1)
@@ -887,10 +898,10 @@ def test_c4_full_size_properties():
     mc = MonteCarlo(bank, tab, x_init, start, orc.orca_params(), drop, W=20, K_models=10, K_seq=32, H=20)
     mc.run(30)
     full = mc.host()
-    assert np.isfinite(full["x"]).all() and np.isfinite(full["curr_mu"]).all()
+    assert np.isfinite(full["x"]).all() and np.isfinite(full["mu_pred"]).all()
     assert (full["projidx"] >= start).all() and (full["projidx"] > start).mean() > 0.9
     assert (full["plant"][:, 8] < 0.192).all()                     # every vehicle went through its friction drop
-    assert ((full["curr_mu"] > 0.2) & (full["curr_mu"] < 1.5)).all()
+    assert ((full["mu_pred"] > 0.2) & (full["mu_pred"] < 1.5)).all()
     sel = np.arange(0, V, 137)
     # ... and replaying the tick as CUDA graphs (one per ring slot) changes nothing
     mc2 = MonteCarlo(bank, tab, x_init[sel], start[sel], orc.orca_params(), drop[sel], W=20, K_models=10, K_seq=32, H=20,
@@ -898,7 +909,7 @@ def test_c4_full_size_properties():
     mc2.run(30)
     assert len(mc2._graphs) == 8
     part = mc2.host()
-    for k in ("x", "projidx", "curr_mu", "model_idx", "u_applied"):
+    for k in ("x", "projidx", "mu_pred", "mu_display", "model_idx", "u_applied"):
         assert np.array_equal(part[k], full[k][sel]), k
 
 
@@ -937,13 +948,56 @@ def test_replay_reference_loop_settings(history):
             best, topk, avg = self.o.push(a, b, c)
             return best, topk, None
 
-    gi, gm = rp.replay(S2, U2, Ts, bank, 400, lambda b, W, ts, K: LookBack(b, W=W, Ts=ts, K=K),
-                       lambda m: MuEstimator(mass=m, smoothing_mu=rp.smoothing_mu, alpha=rp.mu_alpha))
-    ri, rm = rp.replay(S2, U2, Ts, bank, 400, OracleLB,
-                       lambda m: orc.MuEstimatorOracle(mass=m, smoothing_mu=rp.smoothing_mu, alpha=rp.mu_alpha))
-    assert np.array_equal(gi, ri)
-    np.testing.assert_allclose(gm, rm, rtol=1e-13)
-    assert len(np.unique(gi)) > 3                                   # the friction decay makes the loop switch models
+    class OracleMu:
+        def __init__(self, m, lf, lr, W):
+            self.o = orc.MuEstimatorOracle(mass=m, lf=lf, lr=lr, W=W, smoothing_mu=rp.smoothing_mu, alpha=rp.mu_alpha)
+
+        def planner_args(self, idt):
+            mu, sc = self.o.planner_mu_scale(idt)
+            return {"curr_mu": mu, "scale": sc}
+
+        def tick(self, idt, dr=None, df=None):
+            mu = self.o.tick(idt, None if dr is None else range(len(dr)), dr, df)
+            return None if idt <= self.o.W else mu
+
+        mu_display = property(lambda self: self.o.MU_preds[-1])
+
+    g = rp.replay(S2, U2, Ts, bank, 400, lambda b, W, ts, K: LookBack(b, W=W, Ts=ts, K=K),
+                  lambda m, lf, lr, W: MuEstimator(mass=m, lf=lf, lr=lr, W=W, smoothing_mu=rp.smoothing_mu, alpha=rp.mu_alpha))
+    r = rp.replay(S2, U2, Ts, bank, 400, OracleLB, OracleMu)
+    assert np.array_equal(g["current_model_idx"], r["current_model_idx"])
+    for k in ("MU_pred", "MU_preds", "planner_mu", "planner_scale"):
+        np.testing.assert_allclose(g[k], r[k], rtol=1e-13, equal_nan=True)
+    assert len(np.unique(g["current_model_idx"])) > 3              # the friction decay makes the loop switch models
+
+
+@pytest.mark.parametrize("mode", ["recompute", "rolling"])
+def test_replay_matches_reference_own_lines_golden(mode):
+    """LookBack (GPU) + MuEstimator driven like the reference loop against mu_replay.npz, the outputs of the reference's
+    OWN lines rt.py:278-282 / :326-366 executed over the recorded dataset (tests/golden/make_golden_mu.py): the selected
+    model and top-10 of every tick are identical, MU_pred (planner), MU_preds (logged) and the planner gating agree to 1e-12
+    from tick 0."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "examples"))
+    import replay_lookback as rp
+    from llampc_b200.mpc import LookBack, MuEstimator
+    g = load_golden("mu_replay.npz")
+    h = load_golden("ethz_history.npz")
+    S, U, Ts = h["states"], h["inputs"], float(h["Ts"])
+    for tag in ("a", "b"):
+        G = {k[2:]: g[k] for k in g.files if k.startswith(tag + "_")}
+        W, t0, n = int(G["LookBack_W"]), int(G["t0"]), int(G["n_ticks"])
+        bank = orc.make_bank(int(G["N_MODELS"]), seed=int(G["seed"]))
+        assert np.array_equal(bank["Dr"], G["Dr_bank"])
+        r = rp.replay(S[:, t0:], U[:, t0:], Ts, bank, n, lambda b, w, ts, K: LookBack(b, W=w, Ts=ts, K=K, mode=mode),
+                      lambda m, lf, lr, w: MuEstimator(mass=m, lf=lf, lr=lr, W=w, smoothing_mu=int(G["smoothing_mu"]),
+                                                       alpha=float(G["mu_alpha"]), mu_init=float(G["mu_init"]),
+                                                       v_factor=float(G["v_factor"])), W=W, K=int(G["smoothing_mu_over_mod"]))
+        assert np.array_equal(r["current_model_idx"], G["current_model_idx"])
+        assert np.array_equal(r["ind_best_KM"], G["ind_best_KM"])
+        assert np.array_equal(r["planner_scale"], G["planner_scale"])
+        for k in ("MU_pred", "MU_preds", "planner_mu"):
+            np.testing.assert_allclose(r[k], G[k], rtol=1e-12, atol=0, equal_nan=True)
 
 
 def test_lookahead_warm_start_layout(history):
