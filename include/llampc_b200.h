@@ -3,7 +3,7 @@
  * The reference (tianhao-stan-wu/LLA-MPC) is 100 % Python and has no FFI of its own; the boundary it
  * exposes for this path is a set of Python call signatures.  Each entry point below names the
  * reference interface it replaces (paths relative to the reference root).  The Python host in
- * lla-mpc_b200/ binds these symbols with ctypes (see INTEGRATION.md for the reference-side stub).
+ * llampc_b200/ binds these symbols with ctypes (see INTEGRATION.md for the reference-side stub).
  *
  * Conventions
  *   - plain pointers and sizes only; pointers are DEVICE pointers unless the name ends in _h;

@@ -1,8 +1,12 @@
-"""Import alias: the product package lives in the directory ``lla-mpc_b200/`` (not a valid Python
-identifier), so ``import llampc_b200`` resolves its sub-modules there."""
-import os as _os
+"""B200-native look-back / look-ahead hot path of LLA-MPC behind the reference's Python API.
 
-_pkg_dir = _os.path.join(_os.path.dirname(_os.path.dirname(_os.path.abspath(__file__))), "lla-mpc_b200")
-__path__ = [_pkg_dir]
-with open(_os.path.join(_pkg_dir, "__init__.py")) as _f:
-    exec(compile(_f.read(), _os.path.join(_pkg_dir, "__init__.py"), "exec"))
+    from llampc_b200.params import ORCA
+    from llampc_b200.models import Dynamic
+    from llampc_b200.mpc.evaluate_models_vectorized import evaluate_models_vectorized
+    from llampc_b200.mpc import LookBack, LookAhead
+
+All arithmetic of the hot path runs in hand-written sm_100a kernels inside ``libllampc_b200.so`` (C ABI in
+``include/llampc_b200.h``).  There is no CPU fallback: compute calls raise if the library or a CUDA device
+is missing.
+"""
+__version__ = "0.1.0"

@@ -1,6 +1,6 @@
 """ctypes binding of libllampc_b200.so (C ABI: include/llampc_b200.h).
 
-The library is built in-tree by ``__graft_entry__.build()`` / ``make -C lla-mpc_b200/csrc``.  There is no
+The library is built in-tree by ``__graft_entry__.build()`` / ``make -C llampc_b200/csrc``.  There is no
 fallback of any kind: if the shared object is missing, importing a compute module raises.
 """
 import ctypes as C
@@ -97,7 +97,7 @@ def lib():
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise LlampcError("%s not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
-                              "or `make -C lla-mpc_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
+                              "or `make -C llampc_b200/csrc` (there is no CPU fallback)" % LIB_PATH)
         handle = C.CDLL(LIB_PATH)
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(handle, name)           # AttributeError if the library lacks a declared symbol

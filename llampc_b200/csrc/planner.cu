@@ -3,7 +3,7 @@
 // (llampc/tracks/track.py:147-160) with Projection (llampc/utils/projection.py:11-38) over a 10-point window of
 // the raceline, arc-length march with the mu-interpolated speed profile, Spline / Spline2D evaluation
 // (llampc/utils/pycubicspline.py:47-65,155-162; bisect index, a + b dx + c dx^2 + d dx^3).
-// The spline coefficient tables are produced once on the host (lla-mpc_b200/tracks.py).
+// The spline coefficient tables are produced once on the host (llampc_b200/tracks.py).
 // Compiled with --fmad=false semantics where it matters (explicit __dmul_rn/__dadd_rn) so the arithmetic follows
 // the reference's operation order.
 #include "llampc_common.cuh"

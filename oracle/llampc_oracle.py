@@ -2,7 +2,7 @@
 
 TEST INFRASTRUCTURE ONLY.  This file is a restatement of the reference's algorithm,
 used as the checker in ``tests/``, ``__graft_entry__.smoke()`` and the ``cpu_baseline`` /
-``--impl reference`` legs of ``bench.py``.  Nothing under ``lla-mpc_b200/`` (the product)
+``--impl reference`` legs of ``bench.py``.  Nothing under ``llampc_b200/`` (the product)
 imports it; the product path fails loudly when the CUDA library is missing.
 
 Parity pinning: the reference (tianhao-stan-wu/LLA-MPC) ships no tests, golden vectors or

@@ -10,7 +10,7 @@ import torch
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 os.environ["LLAMPC_BAL_TRACE"] = "1"
-os.environ.setdefault("LLAMPC_LIB", os.path.join(ROOT, "lla-mpc_b200", "libllampc_b200_trace.so"))
+os.environ.setdefault("LLAMPC_LIB", os.path.join(ROOT, "llampc_b200", "libllampc_b200_trace.so"))
 from llampc_b200 import _lib                       # noqa: E402
 from llampc_b200.mpc import LookBack                # noqa: E402
 from oracle import llampc_oracle as orc             # noqa: E402
