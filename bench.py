@@ -7,12 +7,15 @@ Metric (BASELINE.json): candidate-model RK4 steps/s.  One bench "step" = one MPC
 one pass of the hot path over the whole bank and window:
     N = 1 : config C2  - 65,536 candidates (6 Pacejka + mass varied) x 50-step window, per-tick arg-min + top-10
     N > 1 : config C5  - 1,048,576 candidates x 50-step window sharded by contiguous index range over N GPUs,
-            local reduce + ONE NCCL min-loc all-reduce (packed 64-bit key) per tick
+            local reduce + ONE min-loc exchange (packed 64-bit key) per tick, fused into the launch over NVLink peer
+            memory (LLAMPC_BENCH_NCCL=1: NCCL MIN all-reduce); the line carries a `parity` block (all ranks agree, equal
+            to the NCCL variant and to the float64 oracle) and the C5-on-1-GPU rate the scaling is to be read against
 `value` is measured with the inputs resident in HBM (CUDA events on the launching stream, L2 flushed between
 ticks); `e2e` goes through the public Python API (LookBack.push) with host NumPy inputs: host packing,
 pinned H2D of the history row, kernels, D2H of the selected indices, every tick.
-`--impl reference` times the reference algorithm's CPU path (the NumPy oracle port of
-evaluate_models_vectorized + scoring, float64) on all host cores.
+`--impl reference` times the reference's own CPU path on all host cores: the unmodified evaluate_models_vectorized
+(imported from the reference package when it resolves -- baseline/_ref on the GPU box -- kind "reference"; else the
+NumPy oracle port, kind "port") + scoring, float64, on the full 65,536-candidate bank per step.
 """
 import argparse
 import json
@@ -128,30 +131,63 @@ class ClockSampler:
 
 
 # ----------------------------------------------------------------------------------------------------------
-# CPU reference arm: the oracle port of the reference NumPy path (float64), sharded over host processes
+# CPU reference arm: the reference's own evaluate_models_vectorized + scoring (float64 NumPy) when the reference package
+# resolves (oracle/reference_adapter.py: LLAMPC_REFERENCE_ROOT, /root/reference, or the offline install under
+# baseline/_ref), else the oracle port of the same lines; sharded over host processes
 # ----------------------------------------------------------------------------------------------------------
+_REF = {"ns": None, "m0": None}
+
+
+def reference_kind():
+    try:
+        from oracle import reference_adapter as ra
+        if ra.available():
+            ra.load()
+            return "reference"
+    except Exception as e:                                      # broken tree: fall back to the port and say so
+        sys.stderr.write("reference package not usable (%r): timing the oracle port\n" % (e,))
+    return "port"
+
+
 def _cpu_worker(args):
-    bank, S, U, W = args
-    from oracle import llampc_oracle as orc
+    bank, S, U, W, kind = args
     t0 = time.perf_counter()
-    ew = orc.window_errors(bank, S, U, W - 1, W, TS)
-    avg = ew.mean(axis=1)
-    best, topk = orc.select(avg, 10)
+    if kind == "reference":
+        # the reference's own per-tick lines (rt.py:349 + :357-360), once per window row: the model list only supplies
+        # len() and models[0] (evaluate_models_vectorized.py:6,16-19), so one Dynamic repeated stands for the bank
+        from oracle import reference_adapter as ra
+        ref = ra.load()
+        if _REF["m0"] is None:
+            _REF["m0"] = ref.Dynamic(**ref.ORCA(control='pwm'))
+        n = len(bank["Bf"])
+        models = [_REF["m0"]] * n
+        pp = tuple(bank[k] for k in ("Bf", "Cf", "Df", "Br", "Cr", "Dr"))
+        ew = np.empty((n, W))
+        for j in range(W):
+            pred = ref.evaluate_models_vectorized(models, n, S[:, j], U[:, j], TS, pp)
+            ew[:, j] = np.mean((pred - S[0:4, j + 1]) ** 2, axis=1)
+        avg = np.mean(ew, axis=1)
+        best, topk = int(np.argmin(avg)), avg.argsort()[:10]
+    else:
+        from oracle import llampc_oracle as orc
+        ew = orc.window_errors(bank, S, U, W - 1, W, TS)
+        avg = ew.mean(axis=1)
+        best, topk = orc.select(avg, 10)
     return time.perf_counter() - t0, best
 
 
 class CpuReference:
-    """The reference algorithm (NumPy port, float64) on `procs` host processes over contiguous candidate shards."""
+    """The reference algorithm (float64 NumPy) on `procs` host processes over contiguous candidate shards."""
 
-    def __init__(self, n_cand, W, procs, S, U):
+    def __init__(self, n_cand, W, procs, S, U, kind):
         import multiprocessing as mp
         bank = make_bank(n_cand, seed=1)
-        self.n_cand, self.W, self.shards = n_cand, W, []
+        self.n_cand, self.W, self.shards, self.kind = n_cand, W, [], kind
         per = (n_cand + procs - 1) // procs
         for r in range(procs):
             lo, hi = r * per, min(n_cand, (r + 1) * per)
             if lo < hi:
-                self.shards.append(({k: (v[lo:hi] if np.ndim(v) else v) for k, v in bank.items()}, S[:, :W + 1], U[:, :W], W))
+                self.shards.append(({k: (v[lo:hi] if np.ndim(v) else v) for k, v in bank.items()}, S[:, :W + 1], U[:, :W], W, kind))
         self.pool = mp.get_context("fork").Pool(len(self.shards)) if len(self.shards) > 1 else None
 
     def step(self):
@@ -168,8 +204,8 @@ class CpuReference:
             self.pool.terminate()
 
 
-def cpu_reference_rate(n_cand, W, procs, S, U, repeats=1):
-    ref = CpuReference(n_cand, W, procs, S, U)
+def cpu_reference_rate(n_cand, W, procs, S, U, kind, repeats=1):
+    ref = CpuReference(n_cand, W, procs, S, U, kind)
     ref.step()                                                 # warm-up (imports, page-in)
     best_t = min(ref.step() for _ in range(repeats))
     ref.close()
@@ -181,27 +217,43 @@ def cpu_history():
     return synthetic_history(W_C2 + 2, lambda p, x, u: orc.rk6_step(p, x, u, 0, TS))
 
 
+REF_WHAT = {"reference": "the reference's own evaluate_models_vectorized (llampc/mpc/evaluate_models_vectorized.py, imported "
+                         "unmodified) called once per window row + errors / mean / argmin / argsort()[:10] (rt.py:349-360), "
+                         "float64 NumPy; mass from models[0] as that signature dictates",
+            "port": "float64 NumPy port of evaluate_models_vectorized + scoring (oracle/llampc_oracle.py; the reference "
+                    "package did not resolve on this box)"}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     cores = os.cpu_count() or 1
+    kind = reference_kind()
     S, U = cpu_history()
-    n_sample = int(min(N_C2, max(16384, 2048 * cores)))
-    ref = CpuReference(n_sample, W_C2, cores, S, U)
-    for _ in range(max(args.warmup, 1)):
+    n_total = N_C2 if args.gpus == 1 else N_C5
+    n_sample = N_C2                                             # the whole C2 bank per step (C5: a 65,536-candidate sample)
+    ref = CpuReference(n_sample, W_C2, cores, S, U, kind)
+    t_first = ref.step()                                        # also the first warm-up step
+    budget = 150.0                                              # seconds for warm-up + timed steps
+    if t_first * (args.steps + max(args.warmup, 1)) > budget and n_sample > 16384:
+        ref.close()                                             # a slow box: bound the sample so the run ends in minutes
+        n_sample = int(max(16384, n_sample * budget / (t_first * (args.steps + max(args.warmup, 1)))) // 1024 * 1024)
+        ref = CpuReference(n_sample, W_C2, cores, S, U, kind)
+        ref.step()
+    for _ in range(max(args.warmup, 1) - 1):
         ref.step()
     total = sum(ref.step() for _ in range(args.steps))
     ref.close()
     value = n_sample * W_C2 * args.steps / total
-    sample = "%d of %d candidates x %d-step window per step (bounded sample of the same bank), float64 NumPy" % (
-        n_sample, N_C2 if args.gpus == 1 else N_C5, W_C2)
+    sample = "%d of %d candidates x %d-step window per step; %s; %d processes over contiguous candidate shards" % (
+        n_sample, n_total, W_C2, REF_WHAT[kind], cores)
     line = {"impl": "reference", "metric": "candidate-model RK4 steps/s (look-back window)", "value": value,
             "unit": "steps/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": 1e3 * total / args.steps, "higher_is_better": True, "scaling": "weak" if args.gpus == 1 else "strong",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args.gpus),
-            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -221,14 +273,14 @@ def workload_config(gpus):
 def cpu_baseline_leg():
     """Reference algorithm on the host cores (bounded sample), run BEFORE CUDA is initialised (fork safety)."""
     cores = os.cpu_count() or 1
+    kind = reference_kind()
     Sc, Uc = cpu_history()
     n_all = N_C2 if cores >= 8 else int(max(16384, 2048 * cores))      # ~10-30 s of CPU work in total
-    r1, _ = cpu_reference_rate(16384, W_C2, 1, Sc, Uc, repeats=2)
-    rall, _ = cpu_reference_rate(n_all, W_C2, cores, Sc, Uc, repeats=8)
-    return {"value": rall, "unit": "steps/s", "cores": cores, "kind": "port",
-            "sample": "%d of the 65,536 C2 candidates x 50-step window (best of 8 passes), float64 NumPy port of "
-                      "evaluate_models_vectorized + scoring, sharded over %d processes; 1-core figure: 16,384 candidates"
-                      % (n_all, cores),
+    r1, _ = cpu_reference_rate(16384, W_C2, 1, Sc, Uc, kind, repeats=1)
+    rall, _ = cpu_reference_rate(n_all, W_C2, cores, Sc, Uc, kind, repeats=4)
+    return {"value": rall, "unit": "steps/s", "cores": cores, "kind": kind,
+            "sample": "%d of the 65,536 C2 candidates x 50-step window (best of 4 passes); %s; sharded over %d processes; "
+                      "1-core figure: 16,384 candidates" % (n_all, REF_WHAT[kind], cores),
             "value_1core_as_reference_runs_it": r1}
 
 
@@ -242,6 +294,7 @@ def run_b200(args):
     from llampc_b200.bank import ModelBank
     from llampc_b200.models import Dynamic
     from llampc_b200.mpc import LookBack
+    from llampc_b200.mpc.lookback import LookbackLaunch, decode_keys
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
@@ -263,25 +316,22 @@ def run_b200(args):
     n_total = N_C2 if world == 1 else N_C5
     per = (n_total + world - 1) // world
     lo, hi = rank * per, min(n_total, (rank + 1) * per)
-    bank_p = make_bank(n_total, seed=1 if world == 1 else 5, lo=lo, hi=hi)
+    bank = ModelBank(make_bank(n_total, seed=1 if world == 1 else 5, lo=lo, hi=hi))
     n_local = hi - lo
-    lb = LookBack(bank_p, W=W_C2, Ts=TS, K=10, refine=0, idx_offset=lo)
-    ts = np.arange(0, W_C2)
-    lb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
     st = torch.cuda.current_stream().cuda_stream
-    bank = lb.bank
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-    flush_sink = torch.zeros((), dtype=torch.int64, device=dev)
-    clean_l2 = os.environ.get("LLAMPC_BENCH_CLEAN_L2", "0") == "1"
 
-    n_lists = L.llampc_lookback_num_lists(n_local, W_C2, 0)
-    assert lb.fused and n_lists > 0
+    def window_rows(b, t0=0):
+        rows = np.zeros((W_C2, _lib.HIST_ROW), dtype=np.float32)
+        for j in range(W_C2):
+            xk, uk, xk1 = (np.ascontiguousarray(a) for a in (S[:, t0 + j], U[:, t0 + j], S[:, t0 + j + 1]))
+            L.llampc_hist_row_pack_h(xk.ctypes.data, uk.ctypes.data, xk1.ctypes.data, TS, b.lf_shared, b.lr_shared,
+                                     rows[j].ctypes.data, None)
+        return torch.from_numpy(rows).to(dev)
 
-    ticket = torch.zeros(1, dtype=torch.int32, device=dev)
-    one_launch = True                                            # K1 + in-kernel tree merge: one launch per tick at any N
-    tree_ws = lb.workspace
-    peer_ptrs = lambda: None
-    # N > 1: the min-loc across GPUs is fused into the same kernels over NVLink peer memory (symmetric buffers);
+    hist = window_rows(bank)
+    avg_err = torch.empty(n_local, dtype=torch.float32, device=dev)
+    # N > 1: the min-loc across GPUs is fused into the same launch over NVLink peer memory (symmetric buffers);
     # LLAMPC_BENCH_NCCL=1 times the NCCL MIN all-reduce variant instead
     peer = None
     if world > 1 and os.environ.get("LLAMPC_BENCH_NCCL", "0") != "1":
@@ -295,34 +345,20 @@ def run_b200(args):
         td.all_reduce(ok, op=td.ReduceOp.MIN)                   # every rank must take the same path
         if int(ok.item()) == 0:
             peer = None
-
-    legacy_tick = os.environ.get("LLAMPC_BENCH_LEGACY_TICK", "0") == "1"   # K1 + last-CTA list merge (the earlier tick)
+    # the tick: ONE launch (scores + per-CTA lists + in-kernel merge tree -> arg-min and top-10; for N > 1 the root of the
+    # tree also runs the NVLink min-loc); sine mode and kernel are the library's automatic choices, reported below
+    tick = LookbackLaunch(bank, hist, W_C2, TS, K=10, idx_offset=lo, avg_err=avg_err, peer=peer)
+    scores_only = LookbackLaunch(bank, hist, W_C2, TS, K=0, idx_offset=lo, avg_err=avg_err)
+    assert tick.plan.launches == 1
 
     def tick_device():
-        """One look-back tick with device-resident inputs, ONE launch: K1 (scores + per-CTA sorted lists) with the
-        top-10 finished by the in-kernel tree of warp merges (+ for N > 1 the min-loc across GPUs, written by the
-        root of the tree over NVLink peer memory, or an NCCL MIN all-reduce)."""
-        if legacy_tick:
-            rc = L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1,
-                                                   W_C2, TS, lb.avg_err.data_ptr(), lb.best_key.data_ptr(),
-                                                   lb.cta_lists.data_ptr(), lo, int(bank.geom_shared), lb.split, 10,
-                                                   ticket.data_ptr(), lb.result.data_ptr(), st)
-            _lib.check(rc, "K1+K4'")
-        else:
-            rc = L.llampc_lookback_window_balanced_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, TS,
-                                                       lb.avg_err.data_ptr(), lo, int(bank.geom_shared), int(lb.fast_sin), 10,
-                                                       tree_ws.data_ptr(), tree_ws.numel(), lb.result.data_ptr(),
-                                                       peer.peer_ptrs.data_ptr() if peer is not None else None,
-                                                       world if peer is not None else 0, rank,
-                                                       peer.next_seq() if peer is not None else 0, st)
-            _lib.check(rc, "K1 + tree merge" + (" + NVLink min-loc" if peer is not None else ""))
+        tick.launch()
         if world > 1 and peer is None:
-            td.all_reduce(lb.result[:1], op=td.ReduceOp.MIN)
+            td.all_reduce(tick.out[0, :1], op=td.ReduceOp.MIN)
 
-    def k1_only():
-        L.llampc_lookback_window_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, 1, W_C2, TS,
-                                     lb.avg_err.data_ptr(), lb.best_key.data_ptr(), lb.cta_lists.data_ptr(), lo,
-                                     int(bank.geom_shared), lb.split, st)
+    def tick_kernel_only():
+        """the same launch without the cross-GPU exchange: the kernel the roofline is quoted on"""
+        tick.launch(use_peer=False)
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
@@ -333,9 +369,7 @@ def run_b200(args):
         torch.cuda.synchronize()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
         for a, b in evs:
-            flush.fill_(1)                                     # evict L2 between timed iterations (not timed) ...
-            if clean_l2:
-                flush_sink.copy_(flush[:1 << 20].sum())        # ... and read it back so the lines left in L2 are clean
+            flush.fill_(1)                                     # evict L2 between timed iterations (not timed)
             a.record()
             fn()
             b.record()
@@ -349,22 +383,50 @@ def run_b200(args):
             td.all_reduce(tot, op=td.ReduceOp.MAX)
         return float(tot.item()), ms
 
-    def tick_kernel_only():
-        """the same launch without the cross-GPU exchange: the kernel the roofline is quoted on"""
-        rc = L.llampc_lookback_window_balanced_f32(bank.packed.data_ptr(), n_local, bank.Npad, lb.hist.data_ptr(), W_C2, TS,
-                                                   lb.avg_err.data_ptr(), lo, int(bank.geom_shared), int(lb.fast_sin), 10,
-                                                   tree_ws.data_ptr(), tree_ws.numel(), lb.result.data_ptr(), None, 0, 0, 0, st)
-        _lib.check(rc, "K1 + tree merge")
-
     with ClockSampler(local) as clk:
         total_ms, per_ms = timed(tick_device, args.steps, max(args.warmup, 3))
         k1_total_ms, k1_ms = timed(tick_kernel_only, args.steps, 3)
-        _, k1_bare_ms = timed(k1_only, args.steps, 3)
+        _, k1_bare_ms = timed(scores_only.launch, args.steps, 3)
     clocks = clk.summary()
     steps_per_tick = n_total * W_C2
     value = steps_per_tick * args.steps / (total_ms * 1e-3)
     k1_avg_s = float(np.mean(k1_ms)) * 1e-3
     k1_rate = n_local * W_C2 / k1_avg_s
+
+    # ---- parity of the timed path: the key the timed launch leaves in out[0] must be the same on every rank, equal the
+    # NCCL variant (MIN all-reduce of the rank-local arg-min keys) and the arg-min of the float64 oracle on a sample
+    parity = None
+    tick_device()
+    torch.cuda.synchronize()
+    key_dev = tick.out[0, 0:1].clone()
+    local_key = tick.out[0, 1:2].clone()                        # rank-local arg-min = head of the local top-10
+    if world > 1:
+        gathered = torch.zeros(world, dtype=torch.int64, device=dev)
+        td.all_gather_into_tensor(gathered, key_dev)
+        nccl_key = local_key.clone()
+        td.all_reduce(nccl_key, op=td.ReduceOp.MIN)
+        allk = gathered.cpu().numpy()
+        ranks_agree = bool((allk == allk[0]).all())
+        vs_nccl = bool(int(key_dev.item()) == int(nccl_key.item()))
+    else:
+        ranks_agree, vs_nccl = True, None
+    gkey = np.array([int(key_dev.item())], dtype=np.int64).view(np.uint64)
+    g_err, g_idx = decode_keys(gkey)
+    # float64 oracle (checker) on the winner + a random sample of this rank's shard: the winner must beat the sample
+    from oracle import llampc_oracle as orc
+    bank_h = make_bank(n_total, seed=1 if world == 1 else 5)
+    rng = np.random.RandomState(123)
+    samp = np.unique(np.concatenate([rng.randint(0, n_total, 2048), g_idx]))
+    sub = {k: (v[samp] if np.ndim(v) else v) for k, v in bank_h.items()}
+    ref = np.mean(orc.window_errors(sub, S, U, W_C2 - 1, W_C2, TS), axis=1)
+    w = int(np.flatnonzero(samp == g_idx[0])[0])
+    oracle_ok = bool(int(np.argmin(ref)) == w and abs(float(g_err[0]) - ref[w]) <= 1e-4 * ref[w])
+    parity = {"ranks_agree": ranks_agree, "vs_nccl": vs_nccl, "key": "0x%016x" % int(gkey[0]), "index": int(g_idx[0]),
+              "vs_oracle_f64": oracle_ok,
+              "how": "out[0] of the timed launch all-gathered over the ranks; NCCL MIN all-reduce of the rank-local arg-min "
+                     "keys; float64 oracle on the winner + 2,048 random candidates of the whole bank"}
+    if not (ranks_agree and oracle_ok and vs_nccl in (True, None)):
+        raise SystemExit("bench: parity of the timed path FAILED: %r" % (parity,))
 
     # ---- roofline of the dominant kernel (K1): FP32 pipe, plus the SFU and HBM readings for context
     peaks = {}
@@ -376,12 +438,15 @@ def run_b200(args):
     fp32_peak = 148 * 128 * 2 * sm_max * 1e6 / 1e12                       # TFLOP/s at the max SM clock
     achieved = k1_rate * F_ALG / 1e12
     hbm_bytes = n_local * (NPARAM_PACKED * 4 + 4) + W_C2 * 80
+    kname = {"K1": "lookback_window_kernel", "K1p": "lookback_window2_kernel", "K1b": "lookback_balanced_kernel"}.get(tick.kernel_name, tick.kernel_name)
     roofline = {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": achieved / fp32_peak,
-                # dram__bytes_read.sum + dram__bytes_write.sum of one tick launch at C2 from the committed ncu --set full
-                # capture (profiles/r01_k1p_ncu.md: 4,264,448 B read, 0 B written back within the launch -- the scores
-                # stay in L2); not captured for the sharded C5 launches
+                # dram__bytes_read.sum + dram__bytes_write.sum of one tick launch at C2: NOT measured in this run, taken
+                # from the committed ncu --set full capture named in traffic_source
                 "traffic": 4264448 if world == 1 else None,
-                "kernel": "lookback_window2_kernel (K1p: scores + selection + in-kernel tree merge = the whole tick)",
+                "traffic_source": "ncu --set full capture profiles/r01_k1p_ncu.md (4,264,448 B read, 0 B written back within "
+                                  "the launch: the scores stay in L2); not captured for the sharded C5 launches",
+                "kernel": "%s (%s: scores + selection + in-kernel tree merge = the whole tick), window split %d, tyre sine %s"
+                          % (kname, tick.kernel_name, tick.plan.split, tick.sine_name),
                 "kernel_us": k1_avg_s * 1e6, "kernel_us_scores_only": float(np.mean(k1_bare_ms)) * 1e3,
                 "peak_source": "148 SM x 128 FP32 lanes x 2 x %.0f MHz (sm_max_mhz of MEASURED_PEAKS.json; tensor/HBM peaks do not bound this elementwise ODE kernel)" % sm_max,
                 "flop_per_step": F_ALG, "steps_per_launch": n_local * W_C2,
@@ -405,54 +470,62 @@ def run_b200(args):
         roofline["sm_clock_under_fma_load_mhz"] = repr(e)
 
     # ---- end to end through the public API (rank-local bank; host inputs every tick)
-    e2e = None
-    lat = None
-    if True:
-        lbe = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=16, idx_offset=lo, group=(td.group.WORLD if world > 1 else None))
-        for t in range(W_C2):
-            lbe.push(S[:, t], U[:, t], S[:, t + 1])
-        for t in range(W_C2, W_C2 + max(args.warmup, 3)):
-            lbe.push(S[:, t], U[:, t], S[:, t + 1])
-        torch.cuda.synchronize()
-        if world > 1:
-            td.barrier()
-        lats = []
-        t_base = W_C2 + max(args.warmup, 3)
-        t0 = time.perf_counter()
+    lbe = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=16, idx_offset=lo, group=(td.group.WORLD if world > 1 else None))
+    for t in range(W_C2 + max(args.warmup, 3)):
+        lbe.push(S[:, t], U[:, t], S[:, t + 1])
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    lats = []
+    t_base = W_C2 + max(args.warmup, 3)
+    t0 = time.perf_counter()
+    e2e_best = None
+    for i in range(args.steps):
+        t = t_base + i
+        a = time.perf_counter()
+        e2e_best, topk, err = lbe.push(S[:, t], U[:, t], S[:, t + 1])
+        lats.append(time.perf_counter() - a)
+    wall = time.perf_counter() - t0
+    if world > 1:
+        wt = torch.tensor([wall], dtype=torch.float64, device=dev)
+        td.all_reduce(wt, op=td.ReduceOp.MAX)
+        wall = float(wt.item())
+        eb = torch.tensor([e2e_best], dtype=torch.int64, device=dev)
+        ebs = torch.zeros(world, dtype=torch.int64, device=dev)
+        td.all_gather_into_tensor(ebs, eb)
+        parity["e2e_ranks_agree"] = bool((ebs == ebs[0]).all().item())
+    h2d = _lib.HIST_ROW * 4 + _lib.HIST64_ROW * 8          # the row travels as kernel parameters
+    d2h = (1 + 2 * lbe.Kt * (world if world > 1 else 1)) * 8
+    e2e = {"value": steps_per_tick * args.steps / wall, "unit": "steps/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h, "api": "LookBack.push (host NumPy transition in; fp64 re-score of the 16 finalists and, for N > 1, the finalist all-gather over NVLink included; arg-min + top-10 indices out)"}
+    lat = {"p50_us": float(np.percentile(lats, 50) * 1e6), "p95_us": float(np.percentile(lats, 95) * 1e6),
+           "mode": "recompute (the whole 50-row window re-integrated every tick)"}
+    if world == 1:
+        # the reference's own rolling bookkeeping (one new error column per tick): same decisions, 1/W of the work
+        lbr = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=16, mode="rolling")
+        for t in range(W_C2 + 5):
+            lbr.push(S[:, t], U[:, t], S[:, t + 1])
+        lr = []
         for i in range(args.steps):
-            t = t_base + i
+            t = W_C2 + 5 + i
             a = time.perf_counter()
-            best, topk, err = lbe.push(S[:, t], U[:, t], S[:, t + 1])
-            lats.append(time.perf_counter() - a)
-        wall = time.perf_counter() - t0
-        if world > 1:
-            wt = torch.tensor([wall], dtype=torch.float64, device=dev)
-            td.all_reduce(wt, op=td.ReduceOp.MAX)
-            wall = float(wt.item())
-        h2d = _lib.HIST_ROW * 4 + _lib.HIST64_ROW * 8          # the row travels as kernel parameters
-        d2h = (1 + 2 * lbe.Kt) * 8
-        e2e = {"value": steps_per_tick * args.steps / wall, "unit": "steps/s", "h2d_bytes_per_step": h2d,
-               "d2h_bytes_per_step": d2h, "api": "LookBack.push (host NumPy transition in; fp64 re-score of the 16 finalists and, for N > 1, the finalist all-gather included; arg-min + top-10 indices out)"}
-        lat = {"p50_us": float(np.percentile(lats, 50) * 1e6), "p95_us": float(np.percentile(lats, 95) * 1e6),
-               "mode": "recompute (the whole 50-row window re-integrated every tick)"}
-        if world == 1:
-            # the reference's own rolling bookkeeping (one new error column per tick): same decisions, 1/W of the work
-            lbr = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=16, mode="rolling")
-            for t in range(W_C2 + 5):
-                lbr.push(S[:, t], U[:, t], S[:, t + 1])
-            lr = []
-            for i in range(args.steps):
-                t = W_C2 + 5 + i
-                a = time.perf_counter()
-                lbr.push(S[:, t], U[:, t], S[:, t + 1])
-                lr.append(time.perf_counter() - a)
-            lat["rolling_mode_p50_us"] = float(np.percentile(lr, 50) * 1e6)
-            lat["rolling_mode_p95_us"] = float(np.percentile(lr, 95) * 1e6)
-            del lbr
+            lbr.push(S[:, t], U[:, t], S[:, t + 1])
+            lr.append(time.perf_counter() - a)
+        lat["rolling_mode_p50_us"] = float(np.percentile(lr, 50) * 1e6)
+        lat["rolling_mode_p95_us"] = float(np.percentile(lr, 95) * 1e6)
+        del lbr
+    del lbe
 
     extras = {}
+    scaling_base = None
     if world == 1 and not args.no_extras:
         extras = secondary_configs(torch, L, _lib, S, U, st, flush)
+    elif world > 1 and rank == 0:
+        # the same workload (C5, 1,048,576 x 50) on ONE GPU, measured in this run on rank 0: the base the strong-scaling
+        # efficiency of this line is to be read against (N = 1 of the driver's sweep runs C2, a different workload)
+        scaling_base = c5_single_gpu(torch, _lib, S, U, flush)
+    if world > 1:
+        td.barrier()
 
     if rank != 0:
         if world > 1:
@@ -462,13 +535,17 @@ def run_b200(args):
     line = {"metric": "candidate-model RK4 steps/s (look-back window)", "value": value, "unit": "steps/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": total_ms / args.steps,
             "higher_is_better": True, "scaling": "weak" if world == 1 else "strong", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": dict(workload_config(world), tyre_sine="MUFU.SIN (default; strict polynomial mode reported under other_configs)"),
-            "gpu_launches": args.steps * (1 if one_launch else 2), "clocks": clocks, "roofline": roofline}
+            "dtype": "f32", "data": "synthetic", "config": workload_config(world),
+            "tyre_sine": "%s (chosen by the library from the bank: max |C| pi/2 = %.2f rad <= pi)" % (tick.sine_name, bank.sin_arg_max),
+            "gpu_launches": args.steps * tick.plan.launches, "clocks": clocks, "roofline": roofline, "parity": parity}
     if world > 1:
         line["exchange"] = "nvlink-peer-memory min-loc inside the kernel" if peer is not None else "nccl all_reduce(MIN) of the packed key"
-    if e2e:
-        line["e2e"] = e2e
-        line["tick_latency"] = lat
+        if scaling_base:
+            line["scaling_base_value"] = scaling_base["steps_per_s"]
+            line["scaling_base"] = scaling_base
+            line["strong_scaling_efficiency_vs_c5_on_1_gpu"] = value / (world * scaling_base["steps_per_s"])
+    line["e2e"] = e2e
+    line["tick_latency"] = lat
     if extras:
         line["other_configs"] = extras
     if cpu_base:
@@ -478,69 +555,80 @@ def run_b200(args):
         td.destroy_process_group()
 
 
-def secondary_configs(torch, L, _lib, S, U, st, flush):
-    """Device-timed throughput of the other BASELINE configs on one GPU (same units: RK4 steps/s)."""
-    from llampc_b200.mpc import LookBack, LookAhead
-    out = {}
+def _time_it(torch, flush, fn, reps):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
+    for a, b in evs:
+        flush.fill_(1)
+        a.record()
+        fn()
+        b.record()
+    torch.cuda.synchronize()
+    return float(np.mean([a.elapsed_time(b) for a, b in evs])) * 1e-3
 
-    def time_it(fn, reps):
-        for _ in range(3):
-            fn()
-        torch.cuda.synchronize()
-        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
-        for a, b in evs:
-            flush.fill_(1)
-            a.record()
-            fn()
-            b.record()
-        torch.cuda.synchronize()
-        return float(np.mean([a.elapsed_time(b) for a, b in evs])) * 1e-3
 
-    # strict mode of the headline config: FMA-pipe polynomial tyre sine instead of MUFU.SIN
-    lbs = LookBack(make_bank(N_C2, seed=1), W=W_C2, Ts=TS, K=10, refine=0, fast_sin=False)
-    ts = np.arange(0, W_C2)
-    lbs.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
-    nls = L.llampc_lookback_num_lists(N_C2, W_C2, 0)
-
-    def c2_strict():
-        L.llampc_lookback_window_balanced_f32(lbs.bank.packed.data_ptr(), N_C2, lbs.bank.Npad, lbs.hist.data_ptr(), W_C2, TS,
-                                              lbs.avg_err.data_ptr(), 0, int(lbs.bank.geom_shared), 0, 10,
-                                              lbs.workspace.data_ptr(), lbs.workspace.numel(), lbs.result.data_ptr(),
-                                              None, 0, 0, 0, st)
-    dt = time_it(c2_strict, 50)
-    out["C2_strict_polynomial_sin"] = {"steps_per_s": N_C2 * W_C2 / dt, "us_per_tick": dt * 1e6}
-    del lbs
-
-    # C5 on one GPU: 1,048,576 candidates x 50 (the sharded sweep's single-GPU reference point)
-    lb = LookBack(make_bank(N_C5, seed=5), W=W_C2, Ts=TS, K=10, refine=0)
+def c5_single_gpu(torch, _lib, S, U, flush, with_push=False):
+    """C5 on one GPU: 1,048,576 candidates x 50 (the sharded sweep's single-GPU reference point), device-timed tick and
+    optionally the end-to-end push."""
+    from llampc_b200.bank import ModelBank
+    from llampc_b200.mpc import LookBack
+    from llampc_b200.mpc.lookback import LookbackLaunch
+    bank = ModelBank(make_bank(N_C5, seed=5))
+    lb = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=16)
     ts = np.arange(0, W_C2)
     lb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
-    n_lists = L.llampc_lookback_num_lists(N_C5, W_C2, 0)
+    ll = LookbackLaunch(bank, lb.hist, W_C2, TS, K=10, avg_err=lb.avg_err)
+    dt = _time_it(torch, flush, ll.launch, 20)
+    out = {"steps_per_s": N_C5 * W_C2 / dt, "ms_per_tick": dt * 1e3, "kernel": ll.kernel_name, "split": ll.plan.split,
+           "tyre_sine": ll.sine_name, "roofline_frac": N_C5 * W_C2 / dt * F_ALG / (148 * 128 * 2 * 1965e6)}
+    if with_push:
+        lat = []
+        for t in range(W_C2, W_C2 + 23):
+            a0 = time.perf_counter()
+            lb.push(S[:, t], U[:, t], S[:, t + 1])
+            lat.append(time.perf_counter() - a0)
+        p50 = float(np.percentile(lat[3:], 50))
+        out["e2e_push_p50_us"] = p50 * 1e6
+        out["e2e_steps_per_s"] = N_C5 * W_C2 / p50
+    del lb, ll
+    return out
 
-    def c5():
-        L.llampc_lookback_window_balanced_f32(lb.bank.packed.data_ptr(), N_C5, lb.bank.Npad, lb.hist.data_ptr(), W_C2, TS,
-                                              lb.avg_err.data_ptr(), 0, int(lb.bank.geom_shared), int(lb.fast_sin), 10,
-                                              lb.workspace.data_ptr(), lb.workspace.numel(), lb.result.data_ptr(),
-                                              None, 0, 0, 0, st)
-    dt = time_it(c5, 20)
-    out["C5_1gpu_lookback_1048576x50"] = {"steps_per_s": N_C5 * W_C2 / dt, "ms_per_tick": dt * 1e3}
-    del lb
+
+def secondary_configs(torch, L, _lib, S, U, st, flush):
+    """Device-timed throughput of the other BASELINE configs on one GPU (same units: RK4 steps/s), each with an end-to-end
+    figure through the public API with host arrays in and out."""
+    from llampc_b200.bank import ModelBank
+    from llampc_b200.mpc import LookBack, LookAhead
+    from llampc_b200.mpc.lookback import LookbackLaunch
+    out = {}
+    time_it = lambda fn, reps: _time_it(torch, flush, fn, reps)
+    peak_rate = 148 * 128 * 2 * 1965e6 / F_ALG
+
+    # strict mode of the headline config: FMA-pipe polynomial tyre sine instead of MUFU.SIN
+    bank2 = ModelBank(make_bank(N_C2, seed=1))
+    lbs = LookBack(bank2, W=W_C2, Ts=TS, K=10, refine=0)
+    ts = np.arange(0, W_C2)
+    lbs.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
+    ll = LookbackLaunch(bank2, lbs.hist, W_C2, TS, K=10, avg_err=lbs.avg_err, fast_sin=False)
+    dt = time_it(ll.launch, 50)
+    out["C2_strict_polynomial_sin"] = {"steps_per_s": N_C2 * W_C2 / dt, "us_per_tick": dt * 1e6, "roofline_frac": N_C2 * W_C2 / dt / peak_rate}
+    del lbs, ll, bank2
+
+    out["C5_1gpu_lookback_1048576x50"] = c5_single_gpu(torch, _lib, S, U, flush, with_push=True)
 
     # C1: 1,024 candidates x 20 (the reference's own CPU-runnable case): latency-bound
-    lb1 = LookBack(make_bank(1024, seed=0), W=20, Ts=TS, K=10, refine=0)
+    bank1 = ModelBank(make_bank_rt(1024, seed=0))
+    lb1 = LookBack(bank1, W=20, Ts=TS, K=10, refine=0)
     ts = np.arange(0, 20)
     lb1.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
-    nl1 = L.llampc_lookback_num_lists(1024, 20, 0)
-
-    def c1():
-        L.llampc_lookback_window_balanced_f32(lb1.bank.packed.data_ptr(), 1024, lb1.bank.Npad, lb1.hist.data_ptr(), 20, TS,
-                                              lb1.avg_err.data_ptr(), 0, int(lb1.bank.geom_shared), int(lb1.fast_sin), 10,
-                                              lb1.workspace.data_ptr(), lb1.workspace.numel(), lb1.result.data_ptr(),
-                                              None, 0, 0, 0, st)
-    dt = time_it(c1, 50)
-    out["C1_lookback_1024x20"] = {"steps_per_s": 1024 * 20 / dt, "us_per_tick": dt * 1e6}
+    ll = LookbackLaunch(bank1, lb1.hist, 20, TS, K=10, avg_err=lb1.avg_err)
+    dt = time_it(ll.launch, 50)
+    out["C1_lookback_1024x20"] = {"steps_per_s": 1024 * 20 / dt, "us_per_tick": dt * 1e6, "kernel": ll.kernel_name, "split": ll.plan.split}
+    del lb1, ll
     for mode in ("recompute", "rolling"):                        # the same case end to end (LookBack.push, host in / out)
-        lbp = LookBack(make_bank_rt(1024, seed=0), W=20, Ts=TS, K=10, refine=16, mode=mode)
+        lbp = LookBack(bank1, W=20, Ts=TS, K=10, refine=16, mode=mode)
         for t in range(30):
             lbp.push(S[:, t], U[:, t], S[:, t + 1])
         lat = []
@@ -570,7 +658,17 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
     del lbm
     plan = la.plan(S[:, t0], Useq, xref, U[:, t0 - 1])
     dt = time_it(plan.run, 20)
-    out["C3_lookahead_16384x32x20"] = {"steps_per_s": M * K * H / dt, "ms_per_call": dt * 1e3}
+    out["C3_lookahead_16384x32x20"] = {"steps_per_s": M * K * H / dt, "ms_per_call": dt * 1e3, "roofline_frac": M * K * H / dt / peak_rate}
+    # end to end: LookAhead.rollout with host arrays in (x0, U, xref, uprev: 5.3 KB) and J (M, K) + best_k (M) back on the host
+    lat = []
+    for _ in range(8):
+        a0 = time.perf_counter()
+        J, bk = la.rollout(S[:, t0], Useq, xref, U[:, t0 - 1])
+        lat.append(time.perf_counter() - a0)
+    p50 = float(np.percentile(lat[2:], 50))
+    out["C3_lookahead_16384x32x20"].update({"e2e_rollout_p50_ms": p50 * 1e3, "e2e_steps_per_s": M * K * H / p50,
+                                            "e2e_h2d_bytes": int(Useq.size * 4 + xref.size * 4 + 6 * 8 + 2 * 4),
+                                            "e2e_d2h_bytes": int(M * K * 4 + M * 4)})
     del la, plan
 
     # C4 Monte-Carlo closed loop: 4,096 vehicles x (look-back 1,024 candidates x 20 window + look-ahead 32 x 20 + planner,
@@ -602,8 +700,16 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
             torch.cuda.synchronize()
             dt = a.elapsed_time(b) * 1e-3 / n_t
             steps = (mc.lookback_steps - s0_lb + mc.lookahead_steps - s0_la) / n_t
+            # the look-back launch of the tick alone (L2 flushed): the kernel the C4 roofline fraction is quoted on
+            lb_dt = time_it((lambda: mc.lb.launch(slot=3, emit=1)) if mode == "rolling" else mc.lb.launch, 10)
+            lb_steps = Vn * 1024 * (1 if mode == "rolling" else 20)
             out["C4_montecarlo_4096veh_" + mode] = {"steps_per_s": steps / dt, "ms_per_tick": dt * 1e3,
-                                                     "rk4_steps_per_tick": steps, "vehicle_ticks_per_s": Vn / dt}
+                                                     "rk4_steps_per_tick": steps, "vehicle_ticks_per_s": Vn / dt,
+                                                     "roofline_frac_tick": steps / dt / peak_rate,
+                                                     "lookback_kernel": mc.lb.kernel_name, "lookback_sine": mc.lb.sine_name,
+                                                     "lookback_launch_us": lb_dt * 1e6,
+                                                     "lookback_launch_steps_per_s": lb_steps / lb_dt,
+                                                     "lookback_launch_roofline_frac": lb_steps / lb_dt / peak_rate}
             del mc
     except Exception as e:                                       # the secondary configs never block the main line
         out["C4_montecarlo_4096veh"] = {"error": repr(e)}

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LLAMPC_ABI_VERSION 4
+#define LLAMPC_ABI_VERSION 5
 
 #define LLAMPC_E_ARG   (-1)  /* null pointer / non-positive size / size not supported       */
 #define LLAMPC_E_ALIGN (-2)  /* pointer or stride not 16-byte aligned                        */
@@ -51,7 +51,9 @@ const char* llampc_error_string(int code);
  * packed_h receives 4 groups of Npad float4 (group-major: [g][i] at float offset (g*Npad+i)*4):
  *   g0 = Bf Cf Df Br | g1 = Cr Dr 1/mass lf | g2 = lr lf/Iz lr/Iz Cm1 | g3 = Cm2 Cr0 Cr2 0
  * derived quantities are formed in fp64 and rounded once.  Npad >= N; rows N..Npad-1 repeat row N-1. */
-int llampc_bank_pack_h(const double* const* params_h, const int* is_array, int N, int Npad, float* packed_h);
+int llampc_bank_pack_h(const double* const* params_h, const int* is_array, int N, int Npad, float* packed_h,
+                       float* sin_arg_max_h /* or NULL: receives max(|Cf|, |Cr|) pi/2 over the bank, the bound of the tyre-sine
+                                               argument C atan(B alpha) that LLAMPC_SIN_AUTO compares with pi */);
 
 /* One history row from one measured transition (x_k, u_k) -> x_k1 (the tick body of
  * run_nmpc_orca_llampc_rt.py:347-349 needs exactly these three vectors).  All trigonometry and the
@@ -63,117 +65,93 @@ int llampc_hist_row_pack_h(const double* x_k, const double* u_k, const double* x
                            double lf_shared, double lr_shared, float* row32_h, double* row64_h);
 
 /* ---------------------------------------------------------------------------------------------
- * K1  look-back window: for every candidate, W one-step RK4 predictions re-anchored at the measured
- * states, mean squared error over (x, y, psi, vx) and over the window, fused block arg-min.
- * Replaces evaluate_models_vectorized (llampc/mpc/evaluate_models_vectorized.py:4-23) called once per
- * tick + errors / error_windows / mean / argmin of run_nmpc_orca_llampc_rt.py:349-358.
- *   bank      packed bank (llampc_bank_pack_h layout) on the device, 16-byte aligned
- *   hist      [n_vehicles][hist_stride_rows][LLAMPC_HIST_ROW] floats; the first W rows of each vehicle are used
- *   avg_err   [n_vehicles][N] or NULL
- *   best_key  [n_vehicles] or NULL; MUST be preset to ~0ull by the caller (llampc_fill_keys); receives the
- *             min over candidates of (float_bits(avg_err)<<32 | idx_offset+i)  (np.argmin tie-break)
- *   cta_lists [n_vehicles][n_lists][LLAMPC_LIST_LEN] or NULL, n_lists = llampc_lookback_num_lists(N, W, split):
- *             the ascending LLAMPC_LIST_LEN smallest keys of every CTA (input of llampc_topk_merge_lists)
- *   geom_shared  non-zero: rows carry valid stage-1 slip angles (lf, lr identical for all candidates)
- *   split     window splits per candidate inside a CTA (1, 2, 4, 8, 16) or 0 = choose from N, W; + 32 selects the
- *             MUFU.SIN (SFU) tyre sine instead of the FMA-pipe polynomial (faster, ~2x the fp32 score error)
- * Banks of >= 8,192 candidates run the packed kernel K1p: two candidates per thread in f32x2 arithmetic (FFMA2 /
- * FMUL2 / FADD2), i.e. 256 / split candidates per CTA instead of 128 / split; llampc_lookback_num_lists accounts for
- * it.  Same operations per candidate, so the scores differ from the scalar kernel's only by re-association of a few
- * signs (LLAMPC_K1_PACKED=0 / 1 in the environment forces the scalar / packed kernel for every size).
+ * LOOK-BACK.  Three entry points:
+ *   llampc_lookback_launch   the scoring + selection launch on device-resident inputs (any layout / mode / GPU count)
+ *   llampc_lookback_tick     one MPC tick around it: newest row in, launch, fp64 re-score, result to the host
+ *   llampc_lookback_push     the tick from three fp64 host vectors (one FFI crossing per MPC tick)
+ * (+ the helpers llampc_lookback_plan, ..._finish, ..._decode, ..._tick_release, ..._tick_workspace_bytes).
+ *
+ * For every candidate: W one-step RK4 predictions re-anchored at the measured states, mean squared error over
+ * (x, y, psi, vx) and over the window, arg-min and top-K.  Replaces evaluate_models_vectorized
+ * (llampc/mpc/evaluate_models_vectorized.py:4-23) called once per tick + errors / error_windows / mean / argmin /
+ * argsort()[:K] of run_nmpc_orca_llampc_rt.py:349-360.
  * ------------------------------------------------------------------------------------------- */
-int llampc_lookback_window_f32(const float* bank, int N, int Npad,
-                               const float* hist, int W, int n_vehicles, int hist_stride_rows, double Ts,
-                               float* avg_err, llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
-                               int geom_shared, int split, llampc_stream_t stream);
-int llampc_lookback_num_lists(int N, int W, int split);
+#define LLAMPC_LB_RECOMPUTE 0   /* re-integrate the whole W-row window every call (N*W steps, stateless w.r.t. the bank)  */
+#define LLAMPC_LB_ROLLING   1   /* the reference's own bookkeeping (rt.py:352-354): integrate only the newest row, replace
+                                   column `slot` of err_ring [n_vehicles][W][Npad], re-sum the ring (N steps per call)     */
 
-/* K1 with the top-K finished inside the same launch: the last CTA of each vehicle to retire (atomic ticket) merges
- * the per-CTA lists.  ticket [n_vehicles] unsigned, zero before the first call (self-resetting);
- * out [n_vehicles][LLAMPC_LIST_LEN + 1] as llampc_topk_merge_lists.  With more than 1,024 lists per vehicle the call
- * falls back to two launches (K1 + llampc_topk_merge_lists). */
-int llampc_lookback_window_topk_f32(const float* bank, int N, int Npad, const float* hist, int W,
-                                    int n_vehicles, int hist_stride_rows, double Ts, float* avg_err,
-                                    llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
-                                    int geom_shared, int split, int K, unsigned* ticket, llampc_key_t* out,
-                                    llampc_stream_t stream);
+#define LLAMPC_SIN_AUTO     0   /* MUFU.SIN while sin_arg_max <= pi (its rated range), else the polynomial; 0 / unknown
+                                   sin_arg_max selects the polynomial                                                      */
+#define LLAMPC_SIN_SFU      1   /* tyre sine on the SFU (MUFU.SIN): abs. error 2^-21.4 on [-pi, pi], growing beyond        */
+#define LLAMPC_SIN_STRICT   2   /* Cody-Waite reduction + polynomial on the FMA pipe: ~17 % slower, range-independent      */
 
-/* K1r for many vehicles (Monte-Carlo layout): the newest row of vehicle v is ring slot `slot` of hist [V][W][20]
- * (written by llampc_pack_rows_f64), err_ring is [V][W][Npad], avg_err [V][N] or NULL, best_key [V] (armed),
- * cta_lists [V][ceil(N/128)][LLAMPC_LIST_LEN], ticket [V] zeroed, out [V][LLAMPC_LIST_LEN + 1].  emit = 0 only stores
- * the error columns (windows still filling); K = 0 skips the top-K.
- * Banks of N <= 2,048 with Npad % 4 == 0, K > 0 and out != NULL run K1v (one CTA per vehicle, top-K by threshold filter in
- * shared memory, SFU tyre sine): same scores and keys, but best_key / cta_lists / ticket are then neither read nor written
- * (out[0] is the arg-min key either way).  The environment switch LLAMPC_K1R_CTA=0 keeps K1r.
- * geom_shared: bit 0 = lf, lr bank-wide (stage-1 slip angles ride in the rows); bit 1 = strict mode, the FMA-pipe polynomial
- * tyre sine instead of MUFU.SIN (for banks as wide as sigma = 2, plot_comp_time.py:178-192, where single candidates with
- * C > 9 reach a relative score error of 1.2e-4 with the SFU sine against 3.6e-5 strict: tools/gpu_wide_bank_check.py). */
-int llampc_lookback_rolling_multi_f32(const float* bank, int N, int Npad, const float* hist, int n_vehicles,
-                                      int slot, int W, double Ts, float* err_ring, float* avg_err,
-                                      llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
-                                      int geom_shared, int emit, int K, unsigned* ticket, llampc_key_t* out,
-                                      llampc_stream_t stream);
+#define LLAMPC_KERNEL_AUTO  0   /* chosen from the shape (llampc_lookback_plan reports the choice)                         */
+#define LLAMPC_KERNEL_K1    1   /* window kernel, one candidate per thread                                                  */
+#define LLAMPC_KERNEL_K1P   2   /* window kernel, two candidates per thread in packed f32x2 (FFMA2 / FMUL2 / FADD2)        */
+#define LLAMPC_KERNEL_K1B   3   /* persistent warp-task window kernel (single history, few CTAs x long windows)            */
+#define LLAMPC_KERNEL_K1PV  4   /* window kernel, one CTA per vehicle (n_vehicles > 1, N <= 2,048), packed, in-CTA top-K   */
+#define LLAMPC_KERNEL_K1R   5   /* rolling kernel, grid over (candidates, vehicles)                                         */
+#define LLAMPC_KERNEL_K1V   6   /* rolling kernel, one CTA per vehicle (N <= 2,048, Npad % 4 == 0), in-CTA top-K           */
 
-/* K1 + top-K + multi-GPU min-loc in ONE launch per rank, over NVLink peer memory (no NCCL on the path).
- *   peer_bufs  device array [world] of pointers: peer_bufs[q] = rank q's symmetric exchange buffer of
- *              4 * world u64 words ([2 parities][world][key, sequence]), zero-initialised, mapped into this process
- *              (CUDA IPC / torch symmetric memory); peer_bufs[rank] is this rank's own buffer
- *   seq        tick counter, identical on every rank, incremented by the caller every call (>= 1)
- * After the launch out[0] holds the GLOBAL arg-min key on every rank (~0ull = no decision: a peer did not arrive within ~1 s);
- * out[1..K] stay the rank-local top-K.  With more than 1,024 per-CTA lists (shards above 131,072 candidates per
- * split) the exchange is carried by the stand-alone merge kernel instead (two launches, still no NCCL call); the
- * limit is 8,192 lists. */
-int llampc_lookback_window_topk_peer_f32(const float* bank, int N, int Npad, const float* hist, int W,
-                                         int hist_stride_rows, double Ts, float* avg_err,
-                                         llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
-                                         int geom_shared, int split, int K, unsigned* ticket,
-                                         llampc_key_t* out, llampc_key_t* const* peer_bufs, int world,
-                                         int rank, unsigned seq, llampc_stream_t stream);
+typedef struct llampc_lookback_desc {
+    /* bank: packed (llampc_bank_pack_h layout), device, 16-byte aligned; keys carry idx_offset + i */
+    const float* bank; int N; int Npad; int idx_offset;
+    int geom_shared;             /* non-zero: lf, lr identical for all candidates (rows carry valid stage-1 slip angles)   */
+    float sin_arg_max;           /* max |C| pi/2 over the bank (llampc_bank_pack_h / llampc_bank_generate_f32 report it)   */
+    int sine;                    /* LLAMPC_SIN_*                                                                            */
+    /* history: [n_vehicles][hist_stride_rows][LLAMPC_HIST_ROW] floats; RECOMPUTE reads rows 0..W-1 of every vehicle,
+       ROLLING reads row `slot` (unless row32_h is given)                                                                   */
+    const float* hist; int W; int n_vehicles; int hist_stride_rows; double Ts;
+    int mode;                    /* LLAMPC_LB_*                                                                              */
+    int slot;                    /* ROLLING: ring slot of the newest row / error column; RECOMPUTE with row32_h: the slot
+                                    the row is patched into (and stored to `hist`, which must then be writable)            */
+    int emit;                    /* ROLLING: 0 = only store the error column (window still filling), no selection          */
+    const float* row32_h;        /* HOST row (LLAMPC_HIST_ROW floats) riding in the kernel parameters, or NULL; single
+                                    vehicle only                                                                            */
+    float* err_ring;             /* ROLLING: [n_vehicles][W][Npad] floats                                                   */
+    /* results */
+    int K;                       /* 1..LLAMPC_LIST_LEN; 0 with out = NULL: scores only (needs avg_err)                      */
+    float* avg_err;              /* [n_vehicles][N] or NULL                                                                 */
+    llampc_key_t* out;           /* [n_vehicles][LLAMPC_LIST_LEN + 1]: out[0] = arg-min key, out[1..K] = ascending top-K,
+                                    the remaining slots ~0ull                                                               */
+    void* workspace;             /* llampc_lookback_plan(...).workspace_bytes bytes, device, 16-byte aligned, ZEROED once by
+                                    the caller (the kernels leave their counters at zero); one workspace per stream         */
+    unsigned long long workspace_bytes;
+    /* multi-GPU (single history, RECOMPUTE): min-loc of out[0] across the GPUs of the box over NVLink peer memory, done by
+       the warp that finishes the rank's merge tree, inside the same launch (no NCCL call on the path).
+       peer_bufs: device array [world] of pointers, peer_bufs[q] = rank q's symmetric exchange buffer of 4 * world u64 words
+       ([2 parities][world][key, sequence]), zero-initialised and mapped into this process (CUDA IPC / torch symmetric
+       memory).  seq: tick counter >= 1, identical on every rank, incremented by the caller every call.  After the launch
+       out[0] is the GLOBAL arg-min key on every rank (~0ull = no decision: a peer did not arrive within ~1 s);
+       out[1..K] stay the rank-local top-K.  NULL = single GPU.                                                             */
+    llampc_key_t* const* peer_bufs; int world; int rank; unsigned seq;
+    /* overrides (0 = automatic) */
+    int kernel;                  /* LLAMPC_KERNEL_*: force a kernel the shape supports (else LLAMPC_E_ARG)                  */
+    int split;                   /* window splits per candidate inside a CTA: 1, 2, 4, 8, 16 (K1 / K1P)                     */
+} llampc_lookback_desc_t;
 
-/* One-launch look-back tick (single history, any N and W): same scores and same selection as
- * llampc_lookback_window_topk_f32, with the top-K finished INSIDE the launch by a tree of 32-way warp merges: warp 0 of
- * every CTA publishes the CTA's 16 smallest keys, the last arrival of every 32 lists merges them (heads in registers,
- * REDUX minima) and climbs one level, the warp that produces the root writes `out`.  The merges overlap the
- * integration; the serial tail after the last RK4 step is the two or three merges on the path to the root instead of
- * one CTA walking every list, and there is no list-count limit (1,048,576 candidates: one launch).
- * The kernel underneath is chosen from the shape: K1 (llampc_lookback_window_f32's kernel, bit-identical scores), or
- * K1b when K1's tiling would leave SMs idle while every thread walks a long window (fewer CTAs than SMs and >= 64 rows
- * per thread): K1b runs persistent CTAs whose warps pull warp-tasks (32 candidates x R window rows) from an atomic
- * counter; the row chunks of a warp-group are combined in row order by the last task to arrive (deterministic).
- *   workspace  llampc_lookback_balanced_workspace_bytes(N, W) bytes of device memory, 16-byte aligned, ZEROED once by
- *              the caller before the first call (the kernels leave their counters at zero; the counter offsets depend
- *              on N only, so W may change between calls); one workspace per stream
- *   fast_sin   non-zero: MUFU.SIN tyre sine (as split + 32 of llampc_lookback_window_f32)
- *   K          1..LLAMPC_LIST_LEN;  out [LLAMPC_LIST_LEN + 1]: out[0] = arg-min key, out[1..K] = ascending top-K,
- *              the remaining slots ~0ull
- *   peer_bufs / world / rank / seq   as llampc_lookback_window_topk_peer_f32 (NVLink min-loc of out[0], done by the
- *              root warp inside the launch); peer_bufs = NULL: single GPU
- * Replaces evaluate_models_vectorized (llampc/mpc/evaluate_models_vectorized.py:4-23) + errors / mean / argmin /
- * argsort[:K] of run_nmpc_orca_llampc_rt.py:349-360. */
-long long llampc_lookback_balanced_workspace_bytes(int N, int W);
-int llampc_lookback_window_balanced_f32(const float* bank, int N, int Npad, const float* hist, int W, double Ts,
-                                        float* avg_err, int idx_offset, int geom_shared, int fast_sin, int K,
-                                        void* workspace, unsigned long long workspace_bytes, llampc_key_t* out,
-                                        llampc_key_t* const* peer_bufs, int world, int rank, unsigned seq,
-                                        llampc_stream_t stream);
+typedef struct llampc_lookback_plan {
+    int kernel;                  /* LLAMPC_KERNEL_* that a launch of this descriptor runs                                   */
+    int split;                   /* window splits per candidate (K1 / K1P), rows per task (K1B), else 1                     */
+    int sine;                    /* LLAMPC_SIN_SFU or LLAMPC_SIN_STRICT after resolving LLAMPC_SIN_AUTO                     */
+    int grid_x, grid_y, block;
+    int launches;                /* kernel launches per call: 1, or 2 when a vehicle has more than 1,024 per-CTA lists      */
+    unsigned long long workspace_bytes;
+} llampc_lookback_plan_t;
 
-/* K1r  rolling window, the reference's own bookkeeping (error_windows = np.roll(...); [:, -1] = errors; mean,
- * run_nmpc_orca_llampc_rt.py:349-358): one RK4 step per candidate for the newest transition (row32_h, HOST pointer,
- * passed as kernel parameter), error column `slot` of err_ring [W][Npad] replaced, window mean re-summed from the
- * ring.  emit = 0: only store the column (window not full yet).  CTA lists: ceil(N/128) lists. */
-int llampc_lookback_rolling_f32(const float* bank, int N, int Npad, const float* row32_h, int slot, int W,
-                                double Ts, float* err_ring, float* avg_err, llampc_key_t* best_key,
-                                llampc_key_t* cta_lists, int idx_offset, int geom_shared, int emit,
-                                llampc_stream_t stream);
+/* Resolves the automatic choices for this descriptor on the current device (needs a CUDA context for K1B's occupancy
+ * query) without launching anything; desc->workspace may be NULL here. */
+int llampc_lookback_plan(const llampc_lookback_desc_t* desc, llampc_lookback_plan_t* plan);
 
-/* Fused top-K (K <= LLAMPC_LIST_LEN): K-way merge of the per-CTA lists of K1.  Per vehicle v:
- *   out[v][0] = best_key[v] (which is then re-armed to ~0ull for the next tick; skipped if best_key is NULL),
- *   out[v][1..K] = ascending top-K keys; out has LLAMPC_LIST_LEN + 1 keys per vehicle.
- * Replaces avg_errors.argsort()[:K] (run_nmpc_orca_llampc_rt.py:360) without re-reading avg_err. */
-int llampc_topk_merge_lists(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K,
-                            llampc_key_t* best_key, llampc_key_t* out, llampc_stream_t stream);
-
-int llampc_fill_keys(llampc_key_t* keys, int n, llampc_stream_t stream);   /* keys[i] = ~0ull */
+/* The launch.  Kernel choice (LLAMPC_KERNEL_AUTO):
+ *   RECOMPUTE, one history       K1P when N >= 8,192 else K1, top-K finished INSIDE the launch by a tree of 32-way warp
+ *                                merges that overlaps the integration (the root writes `out` and runs the NVLink min-loc);
+ *                                K1B when that tiling would leave SMs idle while every thread walks >= 64 rows
+ *   RECOMPUTE, many vehicles     K1PV (one CTA per vehicle, in-CTA top-K) when N <= 2,048 and the vehicles fill the GPU;
+ *                                else K1 / K1P over (candidate tiles, vehicles), packed when N * n_vehicles >= 8,192, the
+ *                                last CTA of a vehicle to retire merges its lists
+ *   ROLLING                      K1V when N <= 2,048, Npad % 4 == 0 and rows come from `hist`; else K1R */
+int llampc_lookback_launch(const llampc_lookback_desc_t* desc, llampc_stream_t stream);
 
 /* K4  top-K (replaces avg_errors.argsort()[:K], run_nmpc_orca_llampc_rt.py:360).
  *   err [N] -> out_keys [K] ascending packed keys.  scratch: [n_ctas*K] keys with
@@ -191,61 +169,60 @@ int llampc_refine_f64(const double* bank64, int N, const double* hist64, int W, 
                       llampc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * One MPC tick of the look-back step in ONE call (the body of run_nmpc_orca_llampc_rt.py:347-360):
- * upload the newest history row into ring slot `slot`, K1 over the whole window, K4 top-Kt with
- * Kt = max(K, n_refine), optional fp64 re-score of the Kt finalists, results to pinned host memory.
- * Every buffer is caller-owned; the struct only carries pointers (device unless suffixed _h).
+ * One MPC tick of the look-back step in ONE call (the body of run_nmpc_orca_llampc_rt.py:347-360): newest history row
+ * into ring slot `slot`, llampc_lookback_launch over the window, Kt = max(K, n_refine) finalists, optional fp64 re-score
+ * of the finalists, results to pinned host memory.  Every buffer is caller-owned; the struct only carries pointers
+ * (device unless suffixed _h).
  * ------------------------------------------------------------------------------------------- */
 typedef struct llampc_tick {
     const float* bank; int N; int Npad;
     float* hist;                    /* device ring [W][LLAMPC_HIST_ROW]                                    */
     const float* row32_h;           /* HOST row (LLAMPC_HIST_ROW floats) for ring slot `slot`, or NULL: it is
-                                       passed to K1 as a kernel parameter (no separate H2D copy)           */
+                                       passed to the kernel as a parameter (no separate H2D copy)          */
     int slot; int W; double Ts;
-    int geom_shared; int split; int idx_offset;
-    float* avg_err;                 /* [N] or NULL (fused path only)                                       */
-    llampc_key_t* best_key;         /* [1]; armed (~0ull) once by the caller with llampc_fill_keys         */
+    int geom_shared;                /* as llampc_lookback_desc_t                                            */
+    float sin_arg_max; int sine;    /* as llampc_lookback_desc_t                                            */
+    int kernel; int split;          /* overrides, as llampc_lookback_desc_t (0 = automatic)                 */
+    int idx_offset;
+    float* avg_err;                 /* [N] or NULL (required when Kt > LLAMPC_LIST_LEN)                     */
     int K;                          /* top-K wanted by the caller (rt.py:360 uses 10)                      */
     int n_refine;                   /* 0 = no fp64 re-score; Kt = max(K, n_refine) finalists are produced  */
-    llampc_key_t* cta_lists;        /* [n_lists][LLAMPC_LIST_LEN] or NULL; with Kt <= LLAMPC_LIST_LEN selects the
-                                       fused path (K1 + list merge: two launches per tick)                 */
-    llampc_key_t* topk_scratch; unsigned* topk_counter;   /* only for the unfused path (Kt > LLAMPC_LIST_LEN)    */
     const double* bank64;           /* [LLAMPC_NPARAM][N] (n_refine > 0)                                   */
     double* hist64;                 /* device ring [W][LLAMPC_HIST64_ROW] (n_refine > 0)                   */
     const double* row64_h;          /* HOST row for hist64 (kernel parameter of the re-score), or NULL     */
-    llampc_key_t* result;           /* device, 1 + 2*Kt words: best key | Kt finalist keys | Kt fp64 scores */
-    llampc_key_t* result_h;         /* pinned host, same layout; with sync != 0 the finalists come back
+    llampc_key_t* result;           /* device, max(1 + 2*Kt, LLAMPC_LIST_LEN + 1) words:
+                                       best key | Kt finalist keys | Kt fp64 scores                         */
+    llampc_key_t* result_h;         /* pinned host, same layout + 1 word; with sync != 0 the finalists come back
                                        ordered by score (fp64 if re-scored), ties by lower index           */
-    int sync;                       /* non-zero: cudaStreamSynchronize + host ordering before returning    */
-    unsigned* ticket;               /* [2], zero-initialised: finish the top-K inside K1 (one launch per tick) when
-                                       the bank yields <= 1,024 per-CTA lists; NULL = always use the merge kernel */
-    int zero_copy;                  /* non-zero (with sync, n_refine > 0, ticket): the last re-score block writes the
-                                       result straight into result_h (mapped pinned memory, 2 + 2*Kt words) and the
-                                       host polls a sequence word instead of a D2H copy + stream synchronisation  */
-    llampc_key_t* const* peer_bufs; /* multi-GPU finalist all-gather over NVLink peer memory (needs n_refine > 0, sync,
+    int sync;                       /* non-zero: wait for the result + host ordering before returning      */
+    int zero_copy;                  /* non-zero (with n_refine > 0): the last re-score block writes the result straight
+                                       into result_h (mapped pinned memory, 2 + 2*Kt words) and the host polls a sequence
+                                       word instead of a D2H copy + stream synchronisation                        */
+    llampc_key_t* const* peer_bufs; /* multi-GPU finalist all-gather over NVLink peer memory (needs n_refine > 0 and
                                        zero_copy): device array [peer_world] of every rank's symmetric buffer of
                                        2 * peer_world * (2*Kt + 1) zeroed words; result_h then needs 2 + 2*Kt*peer_world
-                                       words.  The ordered finalists returned are the GLOBAL ones.  NULL = single GPU */
+                                       words.  The ordered finalists returned are the GLOBAL ones; a peer that does not
+                                       deliver within ~1 s makes llampc_lookback_finish return LLAMPC_E_PEER.  NULL = single GPU */
     int peer_world; int peer_rank;
     unsigned peer_seq;              /* tick counter >= 1, identical on all ranks, incremented by the caller  */
     unsigned long long pending_seq; /* internal: state between llampc_lookback_tick (sync = 0) and ..._finish        */
     int pending_words;
     float* err_ring;                /* [W][Npad] per-tick error columns (rolling mode only)                */
-    int rolling;                    /* 0: recompute the whole window from the history ring (K1);
-                                       1: rolling mode (K1r): integrate only the newest row, replace ring column
-                                          `slot`, re-sum the ring; needs row32_h, cta_lists and Kt <= LLAMPC_LIST_LEN
-                                          (the fp64 re-score still walks the whole hist64 ring);
+    int rolling;                    /* 0: LLAMPC_LB_RECOMPUTE; 1: LLAMPC_LB_ROLLING (needs row32_h, err_ring and
+                                       Kt <= LLAMPC_LIST_LEN; the fp64 re-score still walks the whole hist64 ring);
                                        2: rolling mode while the window is filling: store the column, no decision */
-    void* workspace;                /* device scratch of llampc_lookback_balanced_workspace_bytes(N, W) bytes, zeroed once by
-                                       the caller, or NULL.  Non-NULL (with cta_lists, rolling = 0, 0 < Kt <=
-                                       LLAMPC_LIST_LEN) runs the one-launch tick with the in-kernel tree merge
-                                       (llampc_lookback_window_balanced_f32) instead of K1 + list merge            */
+    void* workspace;                /* llampc_lookback_tick_workspace_bytes(t) bytes of device memory, 16-byte aligned,
+                                       ZEROED once by the caller (counters, per-CTA lists, merge tree, top-K scratch) */
     unsigned long long workspace_bytes;
     void* mapped_dev; const void* mapped_for;   /* internal: device alias of result_h (cudaHostGetDevicePointer), cached */
     void* graph_state;              /* internal, NULL-initialised: the tick's scoring kernel and fp64 re-score are replayed
                                        as one CUDA graph whose kernel nodes are re-parameterised every tick (2 us of host
                                        enqueue time instead of 8 us); freed by llampc_lookback_tick_release            */
 } llampc_tick_t;
+
+/* Bytes of t->workspace for this tick configuration (bank, N, W, K, n_refine, rolling, overrides must be filled in);
+ * needs a CUDA context.  Negative = LLAMPC_E_* / -1000 - cudaError_t. */
+long long llampc_lookback_tick_workspace_bytes(const llampc_tick_t* t);
 
 int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream);
 
@@ -260,9 +237,10 @@ int llampc_lookback_finish(llampc_tick_t* t, llampc_stream_t stream);
 int llampc_lookback_decode(const llampc_tick_t* t, long long* idx_out, double* score_out, int* n_valid);
 
 /* Layout probes for bindings that mirror llampc_tick_t by hand: sizeof, and offsetof of
- * Ts (0), cta_lists (1), result_h (2), peer_seq (3), rolling (4). */
+ * Ts (0), avg_err (1), result_h (2), peer_seq (3), rolling (4), workspace (5). */
 int llampc_tick_sizeof(void);
 int llampc_tick_offsetof(int which);
+int llampc_lookback_desc_sizeof(void);
 
 /* The whole body of run_nmpc_orca_llampc_rt.py:347-360 in one call from three fp64 host vectors: packs the
  * transition (x_k, u_k) -> x_k1 into t->row32_h / t->row64_h (which must point to writable host scratch), runs
@@ -340,7 +318,7 @@ int llampc_plant_rk6_f64(const double* params64, int V, const double* x64, const
 /* ---------------------------------------------------------------------------------------------
  * Monte-Carlo closed loop (thousands of independent vehicles, everything device-resident, no host round trip
  * per tick).  Layouts: per-vehicle history rings hist [V][W][LLAMPC_HIST_ROW] / hist64 [V][W][LLAMPC_HIST64_ROW]
- * (use llampc_lookback_window_f32 with n_vehicles = V, hist_stride_rows = W).
+ * (llampc_lookback_launch with n_vehicles = V, hist_stride_rows = W).
  * ------------------------------------------------------------------------------------------- */
 
 /* Device twin of llampc_hist_row_pack_h for V vehicles: x_k [V][6], u_k [V][2], x_k1 [V][6] -> ring slot `slot`. */
@@ -390,7 +368,9 @@ int llampc_mc_advance_tick_f64(const llampc_key_t* topk, int topk_stride, int* m
  * draw for a given seed whatever the launch.  Writes the packed bank [4][Npad] float4 and, if not NULL, bank64
  * [LLAMPC_NPARAM][N].  Re-centring the bank on a selected candidate = calling it with that candidate's parameters. */
 int llampc_bank_generate_f32(const double* center_h, const double* sigma_h, int N, int Npad,
-                             unsigned long long seed, float* packed, double* bank64, llampc_stream_t stream);
+                             unsigned long long seed, float* packed, double* bank64,
+                             float* sin_arg_max /* DEVICE float, zeroed by the caller, or NULL: max(|Cf|, |Cr|) pi/2 */,
+                             llampc_stream_t stream);
 
 /* Measurement helper: runs an FMA-bound loop of `iters` iterations on every SM and stores, for one thread,
  * out2[0] = elapsed SM cycles (clock64) and out2[1] = elapsed nanoseconds (globaltimer): the SM clock actually

@@ -25,11 +25,10 @@ class Tick(C.Structure):
     """llampc_tick_t"""
     _fields_ = [("bank", _vp), ("N", _i), ("Npad", _i),
                 ("hist", _vp), ("row32_h", _vp), ("slot", _i), ("W", _i), ("Ts", _d),
-                ("geom_shared", _i), ("split", _i), ("idx_offset", _i),
-                ("avg_err", _vp), ("best_key", _vp), ("K", _i), ("n_refine", _i),
-                ("cta_lists", _vp), ("topk_scratch", _vp), ("topk_counter", _vp),
+                ("geom_shared", _i), ("sin_arg_max", _f), ("sine", _i), ("kernel", _i), ("split", _i), ("idx_offset", _i),
+                ("avg_err", _vp), ("K", _i), ("n_refine", _i),
                 ("bank64", _vp), ("hist64", _vp), ("row64_h", _vp),
-                ("result", _vp), ("result_h", _vp), ("sync", _i), ("ticket", _vp), ("zero_copy", _i),
+                ("result", _vp), ("result_h", _vp), ("sync", _i), ("zero_copy", _i),
                 ("peer_bufs", _vp), ("peer_world", _i), ("peer_rank", _i), ("peer_seq", C.c_uint),
                 ("pending_seq", C.c_ulonglong), ("pending_words", _i),
                 ("err_ring", _vp), ("rolling", _i),
@@ -37,34 +36,50 @@ class Tick(C.Structure):
                 ("mapped_dev", _vp), ("mapped_for", _vp), ("graph_state", _vp)]
 
 
+class LookbackDesc(C.Structure):
+    """llampc_lookback_desc_t"""
+    _fields_ = [("bank", _vp), ("N", _i), ("Npad", _i), ("idx_offset", _i),
+                ("geom_shared", _i), ("sin_arg_max", _f), ("sine", _i),
+                ("hist", _vp), ("W", _i), ("n_vehicles", _i), ("hist_stride_rows", _i), ("Ts", _d),
+                ("mode", _i), ("slot", _i), ("emit", _i), ("row32_h", _vp), ("err_ring", _vp),
+                ("K", _i), ("avg_err", _vp), ("out", _vp),
+                ("workspace", _vp), ("workspace_bytes", C.c_ulonglong),
+                ("peer_bufs", _vp), ("world", _i), ("rank", _i), ("seq", C.c_uint),
+                ("kernel", _i), ("split", _i)]
+
+
+class LookbackPlan(C.Structure):
+    """llampc_lookback_plan_t"""
+    _fields_ = [("kernel", _i), ("split", _i), ("sine", _i), ("grid_x", _i), ("grid_y", _i), ("block", _i),
+                ("launches", _i), ("workspace_bytes", C.c_ulonglong)]
+
+
+LB_RECOMPUTE, LB_ROLLING = 0, 1
+SIN_AUTO, SIN_SFU, SIN_STRICT = 0, 1, 2
+KERNEL_AUTO, KERNEL_K1, KERNEL_K1P, KERNEL_K1B, KERNEL_K1PV, KERNEL_K1R, KERNEL_K1V = range(7)
+KERNEL_NAMES = ("auto", "K1", "K1p", "K1b", "K1pv", "K1r", "K1v")
+SIN_NAMES = ("auto", "MUFU.SIN", "strict polynomial")
+E_PEER = -4
+
 # name -> (restype, argtypes); every symbol declared in include/llampc_b200.h
 PROTOTYPES = {
     "llampc_abi_version": (_i, []),
     "llampc_error_string": (C.c_char_p, [_i]),
-    "llampc_bank_pack_h": (_i, [_vp, _vp, _i, _i, _vp]),
+    "llampc_bank_pack_h": (_i, [_vp, _vp, _i, _i, _vp, _vp]),
     "llampc_hist_row_pack_h": (_i, [_vp, _vp, _vp, _d, _d, _d, _vp, _vp]),
-    "llampc_lookback_window_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "llampc_lookback_num_lists": (_i, [_i, _i, _i]),
-    "llampc_lookback_window_topk_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp, _vp]),
-    "llampc_lookback_window_topk_peer_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _i, _i, _i, _i, _vp, _vp,
-                                                  _vp, _i, _i, C.c_uint, _vp]),
-    "llampc_lookback_balanced_workspace_bytes": (C.c_longlong, [_i, _i]),
-    "llampc_lookback_window_balanced_f32": (_i, [_vp, _i, _i, _vp, _i, _d, _vp, _i, _i, _i, _i, _vp, C.c_ulonglong, _vp,
-                                                 _vp, _i, _i, C.c_uint, _vp]),
-    "llampc_lookback_rolling_multi_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _i,
-                                               _vp, _vp, _vp]),
-    "llampc_lookback_rolling_f32": (_i, [_vp, _i, _i, _vp, _i, _i, _d, _vp, _vp, _vp, _vp, _i, _i, _i, _vp]),
-    "llampc_topk_merge_lists": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp]),
-    "llampc_fill_keys": (_i, [_vp, _i, _vp]),
+    "llampc_lookback_plan": (_i, [C.POINTER(LookbackDesc), C.POINTER(LookbackPlan)]),
+    "llampc_lookback_launch": (_i, [C.POINTER(LookbackDesc), _vp]),
     "llampc_topk_scratch_ctas": (_i, [_i]),
     "llampc_topk_f32": (_i, [_vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "llampc_refine_f64": (_i, [_vp, _i, _vp, _i, _d, _vp, _i, _i, _vp, _vp]),
+    "llampc_lookback_tick_workspace_bytes": (C.c_longlong, [C.POINTER(Tick)]),
     "llampc_lookback_tick": (_i, [C.POINTER(Tick), _vp]),
     "llampc_lookback_tick_release": (_i, [C.POINTER(Tick)]),
     "llampc_lookback_finish": (_i, [C.POINTER(Tick), _vp]),
     "llampc_lookback_decode": (_i, [C.POINTER(Tick), _vp, _vp, _vp]),
     "llampc_tick_sizeof": (_i, []),
     "llampc_tick_offsetof": (_i, [_i]),
+    "llampc_lookback_desc_sizeof": (_i, []),
     "llampc_lookback_push": (_i, [C.POINTER(Tick), _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp]),
     "llampc_rk4_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _d, _vp, _i, _vp]),
     "llampc_rhs_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
@@ -80,7 +95,7 @@ PROTOTYPES = {
     "llampc_apply_best_f32": (_i, [_vp, _vp, _i, _i, _i, _vp, _vp, _vp, _vp]),
     "llampc_mc_friction_schedule_f64": (_i, [_vp, _i, _i, _i, _vp, _d, _d, _vp, _vp]),
     "llampc_mc_advance_tick_f64": (_i, [_vp, _i, _vp, _vp, _vp, _i, _vp, _d, _vp]),
-    "llampc_bank_generate_f32": (_i, [_vp, _vp, _i, _i, C.c_ulonglong, _vp, _vp, _vp]),
+    "llampc_bank_generate_f32": (_i, [_vp, _vp, _i, _i, C.c_ulonglong, _vp, _vp, _vp, _vp]),
     "llampc_clock_probe": (_i, [_i, _vp, _vp, _vp]),
     "llampc_plant_rk6_f64": (_i, [_vp, _i, _vp, _vp, _d, _vp, _vp]),
 }
@@ -102,10 +117,11 @@ def lib():
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(handle, name)           # AttributeError if the library lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if handle.llampc_abi_version() != 4:
+        if handle.llampc_abi_version() != 5:
             raise LlampcError("libllampc_b200.so ABI version mismatch")
-        if handle.llampc_tick_sizeof() != C.sizeof(Tick):
-            raise LlampcError("llampc_tick_t layout mismatch between _lib.py and libllampc_b200.so (rebuild the library)")
+        if handle.llampc_tick_sizeof() != C.sizeof(Tick) or handle.llampc_lookback_desc_sizeof() != C.sizeof(LookbackDesc):
+            raise LlampcError("llampc_tick_t / llampc_lookback_desc_t layout mismatch between _lib.py and "
+                              "libllampc_b200.so (rebuild the library)")
         _lib = handle
     return _lib
 

@@ -45,10 +45,14 @@ class ModelBank:
         self.lr_shared = float(c[1]) if self.geom_shared else float("nan")
         self.packed = torch.empty((4, self.Npad, 4), dtype=torch.float32, device=self.device)
         self._bank64 = torch.empty((_lib.NPARAM, self.N), dtype=torch.float64, device=self.device)
+        arg_max = torch.zeros(1, dtype=torch.float32, device=self.device)
         with torch.cuda.device(self.device):
             _lib.check(_lib.lib().llampc_bank_generate_f32(c.ctypes.data, sg.ctypes.data, self.N, self.Npad, int(seed),
                                                            self.packed.data_ptr(), self._bank64.data_ptr(),
-                                                           _lib.stream_ptr(torch)), "llampc_bank_generate_f32")
+                                                           arg_max.data_ptr(), _lib.stream_ptr(torch)),
+                       "llampc_bank_generate_f32")
+        # max(|Cf|, |Cr|) pi/2 over the bank: bound of the tyre-sine argument (sine mode "auto", include/llampc_b200.h)
+        self.sin_arg_max = float(arg_max.item())
         self._params = None
         self._varied = sg != 0.0
         return self
@@ -81,8 +85,11 @@ class ModelBank:
         ptrs = (C.c_void_p * _lib.NPARAM)(*[self.params[k].ctypes.data for k in PARAM_NAMES])
         flags = (C.c_int * _lib.NPARAM)(*[int(self.params[k].ndim == 1) for k in PARAM_NAMES])
         packed_h = torch.empty((4, self.Npad, 4), dtype=torch.float32, pin_memory=True)
+        arg_max = C.c_float(0.0)
         _lib.check(_lib.lib().llampc_bank_pack_h(C.cast(ptrs, C.c_void_p), C.cast(flags, C.c_void_p), self.N, self.Npad,
-                                                 packed_h.data_ptr()), "llampc_bank_pack_h")
+                                                 packed_h.data_ptr(), C.addressof(arg_max)), "llampc_bank_pack_h")
+        # max(|Cf|, |Cr|) pi/2 over the bank: bound of the tyre-sine argument (sine mode "auto", include/llampc_b200.h)
+        self.sin_arg_max = float(arg_max.value)
         self.packed = packed_h.to(self.device, non_blocking=False)
         self._bank64 = None
 

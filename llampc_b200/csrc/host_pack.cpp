@@ -18,16 +18,21 @@ extern "C" const char* llampc_error_string(int code) {
     }
 }
 
-extern "C" int llampc_bank_pack_h(const double* const* params_h, const int* is_array, int N, int Npad, float* packed_h) {
+extern "C" int llampc_bank_pack_h(const double* const* params_h, const int* is_array, int N, int Npad, float* packed_h,
+                                  float* sin_arg_max_h) {
     if (!params_h || !is_array || !packed_h || N <= 0 || Npad < N) return LLAMPC_E_ARG;
     for (int j = 0; j < LLAMPC_NPARAM; ++j)
         if (!params_h[j]) return LLAMPC_E_ARG;
+    double cmax = 0.0;                             // max(|Cf|, |Cr|): bounds the tyre-sine argument C atan(B alpha) by cmax pi/2
     for (int i = 0; i < Npad; ++i) {
         const int s = i < N ? i : N - 1;
         double v[LLAMPC_NPARAM];
         for (int j = 0; j < LLAMPC_NPARAM; ++j) v[j] = params_h[j][is_array[j] ? s : 0];
         llampc::pack_candidate(v, packed_h, Npad, i);
+        const double c = fmax(fabs(v[6]), fabs(v[7]));
+        if (!(c <= cmax)) cmax = c == c ? c : INFINITY;      // a NaN parameter forces the range-independent sine
     }
+    if (sin_arg_max_h) *sin_arg_max_h = (float)(cmax * 1.5707963267948966);
     return 0;
 }
 

@@ -104,7 +104,7 @@ __device__ __forceinline__ u64 warp_min_key(u64 k) {
 //   A1  every warp selects the K smallest heads of the lists it owns (heads in registers, K REDUX rounds);
 //   A2  warp 0 merges the per-warp selections -> the K lists with the globally smallest heads;
 //   B   warp 0 loads those <= K lists (one coalesced wave of loads) and K-way merges them from shared memory.
-// out[0] = *best_key (then re-armed to ~0 for the next tick), out[1..K] = ascending top-K.
+// out[0] = arg-min key (= out[1]), out[1..K] = ascending top-K, out[K+1..LIST_LEN] = ~0.
 // Capacity: THREADS * MERGE_LPT lists.  Shared memory: MergeSmem<THREADS>.
 constexpr int MERGE_LPT = 8;
 
@@ -118,8 +118,7 @@ struct MergeSmem {
 
 template <int THREADS>
 __device__ __forceinline__ void merge_lists_device(const u64* __restrict__ lists, int n_lists, int K,
-                                                   u64* __restrict__ best_key, u64* __restrict__ out,
-                                                   MergeSmem<THREADS>& sm) {
+                                                   u64* __restrict__ out, MergeSmem<THREADS>& sm) {
     constexpr int NW = THREADS / 32;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     u64 head[MERGE_LPT];
@@ -127,10 +126,6 @@ __device__ __forceinline__ void merge_lists_device(const u64* __restrict__ lists
     for (int j = 0; j < MERGE_LPT; ++j) {
         const int l = threadIdx.x + j * THREADS;
         head[j] = l < n_lists ? __ldcg(lists + (size_t)l * LLAMPC_LIST_LEN) : ~0ull;
-    }
-    if (threadIdx.x == 0 && best_key) {
-        out[0] = __ldcg(best_key);
-        *best_key = ~0ull;
     }
     // A1: per-warp K smallest heads
     for (int r = 0; r < LLAMPC_LIST_LEN; ++r) {
@@ -176,9 +171,12 @@ __device__ __forceinline__ void merge_lists_device(const u64* __restrict__ lists
     {
         int p = 0;
         u64 h = lane < LLAMPC_LIST_LEN ? sm.rows[lane][0] : ~0ull;
-        for (int r = 0; r < K; ++r) {
-            const u64 sel = warp_min_key(h);
-            if (lane == 0) out[1 + r] = sel;
+        for (int r = 0; r < LLAMPC_LIST_LEN; ++r) {
+            const u64 sel = r < K ? warp_min_key(h) : ~0ull;
+            if (lane == 0) {
+                out[1 + r] = sel;
+                if (r == 0) out[0] = sel;                          // arg-min key = head of the top-K
+            }
             if (sel != ~0ull && h == sel) {
                 ++p;
                 h = p < LLAMPC_LIST_LEN ? sm.rows[lane][p] : ~0ull;

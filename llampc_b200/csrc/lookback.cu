@@ -1,56 +1,44 @@
-// K1 look-back window kernel, K4 top-K, fp64 finalist re-score, one-step batch kernels.  sm_100a.
+// Look-back C ABI (llampc_lookback_plan / _launch / _tick / _push), the list-merge, top-K and fp64 re-score kernels, and
+// the one-step batch kernels.  sm_100a.  The scoring kernels live in lookback_k1.cu (K1), lookback_k1p.cu (K1p, K1pv),
+// lookback_rolling.cu (K1r, K1v) and lookback_balanced.cu (K1b).
 //
 // Reference behaviour being replaced: evaluate_models_vectorized (llampc/mpc/evaluate_models_vectorized.py:4-23)
 // + the scoring / selection block of run_nmpc_orca_llampc_rt.py:347-360.
-#include "llampc_common.cuh"
-#include "llampc_model.cuh"
+#include "lookback_kernels.cuh"
 #include "llampc_model_f64.cuh"
-#include "llampc_packed.cuh"
-#include "lookback_select.cuh"
 #include <math.h>
 #include <stddef.h>
-#include <string.h>
 #include <stdlib.h>
 
 namespace llampc {
 
-constexpr int NUM_SMS = 148;
-
-// ---------------------------------------------------------------------------------------------------
-// Launch helper.  Normally issue() is kern<<<...>>>(...).  While llampc_lookback_tick collects (g_collect set), the
-// launch is recorded instead -- function, shape and a copy of every argument -- and the tick replays its two kernels
-// (scoring + fp64 re-score) as ONE CUDA graph whose kernel nodes are re-parameterised every tick: measured with
-// tools/ubench/graph_launch.cu, 2.0 us of host enqueue time instead of 7.6 us and 3.9 us less from enqueue to the
-// host-visible result.
-// ---------------------------------------------------------------------------------------------------
-struct PendingLaunch {
-    void* func; dim3 grid, block; size_t smem; void* args[24]; int n_args; size_t used;
-    alignas(16) unsigned char store[2048];
-};
-constexpr int TICK_GRAPH_MAX_NODES = 2;
-static thread_local PendingLaunch* g_collect = nullptr;
-static thread_local int g_collect_n = 0;
-
-template <class T>
-static inline void pending_push(PendingLaunch& pl, const T& v) {
-    const size_t off = (pl.used + alignof(T) - 1) & ~(alignof(T) - 1);
-    memcpy(pl.store + off, &v, sizeof(T));
-    pl.args[pl.n_args++] = pl.store + off;
-    pl.used = off + sizeof(T);
+LaunchCollector& launch_collector() {
+    static thread_local LaunchCollector lc = {nullptr, 0};
+    return lc;
 }
 
-template <class... KArgs, class... Args>
-static int issue(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
-    static_assert(sizeof...(KArgs) == sizeof...(Args), "argument count");
-    if (g_collect && g_collect_n < TICK_GRAPH_MAX_NODES) {
-        PendingLaunch& pl = g_collect[g_collect_n++];
-        pl.func = reinterpret_cast<void*>(kern);
-        pl.grid = grid; pl.block = block; pl.smem = smem; pl.n_args = 0; pl.used = 0;
-        (pending_push<KArgs>(pl, static_cast<KArgs>(args)), ...);
-        return 0;
-    }
-    kern<<<grid, block, smem, st>>>(static_cast<KArgs>(args)...);
-    return (int)cudaGetLastError();
+static long long env_ll(const char* name, long long dflt) {
+    const char* e = getenv(name);
+    if (!e || !*e) return dflt;
+    const long long v = atoll(e);
+    return v > 0 ? v : dflt;
+}
+
+const LibEnv& lib_env() {
+    static const LibEnv env = [] {
+        LibEnv e;
+        const char* g = getenv("LLAMPC_TICK_GRAPH");
+        e.tick_graph = (g && g[0] == '0') ? 0 : 1;
+        e.bal_ctas = env_ll("LLAMPC_BAL_CTAS", 0);
+        e.bal_tpw = env_ll("LLAMPC_BAL_TPW", 6);
+        e.bal_rmin = env_ll("LLAMPC_BAL_RMIN", 1);
+        e.bal_rmax = env_ll("LLAMPC_BAL_RMAX", 10);
+        e.bal_verbose = getenv("LLAMPC_BAL_VERBOSE") != nullptr;
+        e.bal_trace = getenv("LLAMPC_BAL_TRACE") != nullptr;
+        e.bal_nofence = getenv("LLAMPC_BAL_NOFENCE") != nullptr;
+        return e;
+    }();
+    return env;
 }
 
 struct TickGraph {
@@ -93,479 +81,24 @@ static int tick_graph_launch(TickGraph* tg, PendingLaunch* pl, int n, cudaStream
 }
 
 // ---------------------------------------------------------------------------------------------------
-// K1.  grid = (ceil(N / (128/SY)), n_vehicles); block = 128 threads = (128/SY candidates) x (SY window splits).
-// The W history rows (80 B each) are staged once per CTA with one TMA bulk copy; every warp then reads
-// the same row at the same time (shared-memory broadcast).  Thread (c, sy) integrates window rows
-// sy, sy+SY, ...; partial sums are combined in a fixed order so the result is run-to-run deterministic.
-// (CTA-level selection, NewRow, FusedMerge, PeerXchg: lookback_select.cuh)
-// ---------------------------------------------------------------------------------------------------
-template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
-__global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB_MIN_BLOCKS)
-lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
-                       long hist_stride_floats, StepSize z, float* __restrict__ avg_err, u64* __restrict__ best_key,
-                       u64* __restrict__ cta_lists, int idx_offset, NewRow nr, FusedMerge fm, PeerXchg px, TreeMerge tm) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ u64 skeys[LB_THREADS];
-    float4* srow = reinterpret_cast<float4*>(smem_raw);
-    float* spart = reinterpret_cast<float*>(smem_raw + (size_t)W * (LLAMPC_HIST_ROW * 4));
-
-    constexpr int CPB = LB_THREADS / SY;
-    const int tid = threadIdx.x;
-    const int v = blockIdx.y;
-    const unsigned bytes = (unsigned)W * (LLAMPC_HIST_ROW * 4);
-
-    if (tid == 0) {                                // one thread arms the barrier and starts the bulk copy right away
-        mbar_init(&mbar, 1);
-        mbar_expect_tx(&mbar, bytes);
-        tma_bulk_g2s(srow, hist + (size_t)v * hist_stride_floats, bytes, &mbar);
-    }
-    __syncthreads();                               // the initialised barrier is visible to the waiting threads
-
-    const int c = tid % CPB, sy = tid / CPB;
-    const int cand = blockIdx.x * CPB + c;
-    const bool valid = cand < N;
-    const Cand p = load_cand(bank, Npad, valid ? cand : N - 1);   // overlaps the bulk copy
-
-    mbar_wait(&mbar, 0);
-    if (nr.slot >= 0) {                            // uniform over the grid
-        if (tid < LLAMPC_HIST_ROW / 4) {
-            const float4 q = make_float4(nr.v[4 * tid], nr.v[4 * tid + 1], nr.v[4 * tid + 2], nr.v[4 * tid + 3]);
-            srow[nr.slot * 5 + tid] = q;
-            if (blockIdx.x == 0 && blockIdx.y == 0)
-                reinterpret_cast<float4*>(const_cast<float*>(hist))[nr.slot * 5 + tid] = q;
-        }
-        __syncthreads();
-    }
-
-    float acc = 0.0f;
-    for (int w = sy; w < W; w += SY) {
-        HistRow r;
-        r.q0 = srow[w * 5 + 0];
-        r.q1 = srow[w * 5 + 1];
-        r.q2 = srow[w * 5 + 2];
-        r.q3 = srow[w * 5 + 3];
-        r.q4 = srow[w * 5 + 4];
-        bool ok;
-        float e = lookback_step_fast<GEOM_SHARED, MUFU_SIN>(p, r, z, ok);
-        if (!ok) e = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, valid ? cand : N - 1, srow + w * 5, z);
-        acc += e;
-    }
-
-    if (SY > 1) {
-        spart[sy * CPB + c] = acc;
-        __syncthreads();
-        if (sy == 0) {
-#pragma unroll
-            for (int j = 1; j < SY; ++j) acc += spart[j * CPB + c];
-        }
-    }
-    // errors = mean over the 4 scored states (rt.py:349); avg = mean over the window (rt.py:357)
-    const float err = acc * (0.25f / (float)W);
-    u64 key = ~0ull;
-    if (sy == 0 && valid) {
-        if (avg_err) avg_err[(size_t)v * N + cand] = err;
-        key = pack_key(err, (unsigned)(idx_offset + cand));
-    }
-    if (tm.K > 0) {                                // uniform over the grid: tree finish (single history), one launch per tick
-        __shared__ u64 mrows[BAL_FAN][BAL_ROW_PAD];
-        key = cta_select32<(CPB >= 32 ? CPB / 32 : 1)>(key, skeys);
-        if (tid < 32) tree_merge(key, tid, (int)blockIdx.x, (int)gridDim.x, tm.K, tm.ws, mrows, tm.out, px);
-        return;
-    }
-    cta_select_emit<(CPB >= 32 ? CPB / 32 : 1)>(key, skeys, v, best_key, cta_lists);   // CPB < 32: part of warp 0 holds keys
-    if (fm.K > 0) {                                // uniform over the grid
-        __shared__ bool is_last;
-        __shared__ MergeSmem<LB_THREADS> msm;
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) is_last = atomicAdd(fm.ticket + v, 1u) == gridDim.x - 1;
-        __syncthreads();
-        if (!is_last) return;
-        __threadfence();
-        u64* outv = fm.out + (size_t)v * (LLAMPC_LIST_LEN + 1);
-        merge_lists_device<LB_THREADS>(cta_lists + (size_t)v * gridDim.x * LLAMPC_LIST_LEN, gridDim.x, fm.K,
-                                       best_key ? best_key + v : nullptr, outv, msm);
-        if (tid == 0) fm.ticket[v] = 0;            // ready for the next launch on the same stream
-        if (px.world > 1 && tid < 32) {            // warp 0: min-loc across the GPUs of the box, in this launch
-            __syncwarp();
-            const u64 mine = __shfl_sync(0xffffffffu, tid == 0 ? *reinterpret_cast<volatile u64*>(outv) : 0ull, 0);
-            const u64 g = peer_minloc(px, mine, tid);
-            if (tid == 0) outv[0] = g;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// K1p.  K1 with TWO candidates per thread in packed f32x2 arithmetic (llampc_packed.cuh): FFMA2 / FMUL2 / FADD2 carry
-// both candidates through one issue slot, the history-row values are broadcast scalar operands.  Same tiling as K1
-// with twice the candidates per CTA: block = 128 threads = (128/SY candidate pairs) x (SY window splits); thread
-// (c, sy) owns candidates base + c and base + 128/SY + c (both bank loads stay coalesced).
-// ---------------------------------------------------------------------------------------------------
-#ifndef LLAMPC_LB2_MIN_BLOCKS
-#define LLAMPC_LB2_MIN_BLOCKS 4
-#endif
-template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
-__global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB2_MIN_BLOCKS)
-lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
-                        long hist_stride_floats, StepSize z, float* __restrict__ avg_err, u64* __restrict__ best_key,
-                        u64* __restrict__ cta_lists, int idx_offset, NewRow nr, FusedMerge fm, PeerXchg px, TreeMerge tm) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ u64 skeys[LB_THREADS];
-    float4* srow = reinterpret_cast<float4*>(smem_raw);
-    float* spart = reinterpret_cast<float*>(smem_raw + (size_t)W * (LLAMPC_HIST_ROW * 4));
-
-    constexpr int CPB = LB_THREADS / SY;           // candidate pairs per CTA
-    const int tid = threadIdx.x;
-    const int v = blockIdx.y;
-    const unsigned bytes = (unsigned)W * (LLAMPC_HIST_ROW * 4);
-
-    if (tid == 0) {
-        mbar_init(&mbar, 1);
-        mbar_expect_tx(&mbar, bytes);
-        tma_bulk_g2s(srow, hist + (size_t)v * hist_stride_floats, bytes, &mbar);
-    }
-    __syncthreads();
-
-    const int c = tid % CPB, sy = tid / CPB;
-    const int cand0 = blockIdx.x * (2 * CPB) + c, cand1 = cand0 + CPB;
-    const bool valid0 = cand0 < N, valid1 = cand1 < N;
-    const int i0 = valid0 ? cand0 : N - 1, i1 = valid1 ? cand1 : N - 1;
-    const Cand2 p = load_cand2(bank, Npad, i0, i1);              // overlaps the bulk copy
-
-    mbar_wait(&mbar, 0);
-    if (nr.slot >= 0) {                            // uniform over the grid
-        if (tid < LLAMPC_HIST_ROW / 4) {
-            const float4 q = make_float4(nr.v[4 * tid], nr.v[4 * tid + 1], nr.v[4 * tid + 2], nr.v[4 * tid + 3]);
-            srow[nr.slot * 5 + tid] = q;
-            if (blockIdx.x == 0 && blockIdx.y == 0)
-                reinterpret_cast<float4*>(const_cast<float*>(hist))[nr.slot * 5 + tid] = q;
-        }
-        __syncthreads();
-    }
-
-    float acc0 = 0.0f, acc1 = 0.0f;
-    for (int w = sy; w < W; w += SY) {
-        HistRow r;
-        r.q0 = srow[w * 5 + 0];
-        r.q1 = srow[w * 5 + 1];
-        r.q2 = srow[w * 5 + 2];
-        r.q3 = srow[w * 5 + 3];
-        r.q4 = srow[w * 5 + 4];
-        bool ok0, ok1;
-        const F2 e = lookback_step_fast2<GEOM_SHARED, MUFU_SIN>(p, r, z, ok0, ok1);
-        float e0, e1;
-        up(e, e0, e1);
-        if (!ok0) e0 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i0, srow + w * 5, z);
-        if (!ok1) e1 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i1, srow + w * 5, z);
-        acc0 += e0;
-        acc1 += e1;
-    }
-
-    if (SY > 1) {
-        spart[(sy * 2) * CPB + c] = acc0;
-        spart[(sy * 2 + 1) * CPB + c] = acc1;
-        __syncthreads();
-        if (sy == 0) {
-#pragma unroll
-            for (int j = 1; j < SY; ++j) {
-                acc0 += spart[(j * 2) * CPB + c];
-                acc1 += spart[(j * 2 + 1) * CPB + c];
-            }
-        }
-    }
-    // errors = mean over the 4 scored states (rt.py:349); avg = mean over the window (rt.py:357)
-    const float scale = 0.25f / (float)W;
-    const float err0 = acc0 * scale, err1 = acc1 * scale;
-    u64 k0 = ~0ull, k1 = ~0ull;
-    if (sy == 0) {
-        if (valid0) {
-            if (avg_err) avg_err[(size_t)v * N + cand0] = err0;
-            k0 = pack_key(err0, (unsigned)(idx_offset + cand0));
-        }
-        if (valid1) {
-            if (avg_err) avg_err[(size_t)v * N + cand1] = err1;
-            k1 = pack_key(err1, (unsigned)(idx_offset + cand1));
-        }
-    }
-    constexpr int KW = CPB >= 32 ? CPB / 32 : 1;   // CPB < 32: part of warp 0 holds keys
-    u64 key = ~0ull;
-    if ((tid >> 5) < KW) {                         // two keys per lane -> the 32 smallest of the warp's 64
-        const int lane = tid & 31;
-        k0 = warp_sort_u64(k0, lane);
-        k1 = warp_sort_u64(k1, lane);
-        key = warp_merge_low32(k0, __shfl_sync(0xffffffffu, k1, 31 - lane), lane);
-    }
-    if (tm.K > 0) {                                // uniform over the grid: tree finish (single history), one launch per tick
-        __shared__ u64 mrows[BAL_FAN][BAL_ROW_PAD];
-        key = cta_select32<KW, true>(key, skeys);
-        if (tid < 32) tree_merge(key, tid, (int)blockIdx.x, (int)gridDim.x, tm.K, tm.ws, mrows, tm.out, px);
-        return;
-    }
-    cta_select_emit<KW, true>(key, skeys, v, best_key, cta_lists);
-    if (fm.K > 0) {                                // uniform over the grid
-        __shared__ bool is_last;
-        __shared__ MergeSmem<LB_THREADS> msm;
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) is_last = atomicAdd(fm.ticket + v, 1u) == gridDim.x - 1;
-        __syncthreads();
-        if (!is_last) return;
-        __threadfence();
-        u64* outv = fm.out + (size_t)v * (LLAMPC_LIST_LEN + 1);
-        merge_lists_device<LB_THREADS>(cta_lists + (size_t)v * gridDim.x * LLAMPC_LIST_LEN, gridDim.x, fm.K,
-                                       best_key ? best_key + v : nullptr, outv, msm);
-        if (tid == 0) fm.ticket[v] = 0;
-        if (px.world > 1 && tid < 32) {
-            __syncwarp();
-            const u64 mine = __shfl_sync(0xffffffffu, tid == 0 ? *reinterpret_cast<volatile u64*>(outv) : 0ull, 0);
-            const u64 g = peer_minloc(px, mine, tid);
-            if (tid == 0) outv[0] = g;
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// K1r rolling window (the reference's own bookkeeping, rt.py:349-358): only the newest transition is integrated
-// (one RK4 step per candidate), its error replaces ring column `slot` of err_ring [W][Npad] (np.roll + write of
-// the last column), and the window mean is re-summed from the ring -- N steps and N*W*4 bytes per tick instead
-// of N*W steps.  emit = 0 while the window is filling (columns stored, no decision).
-// ---------------------------------------------------------------------------------------------------
-template <bool GEOM_SHARED, bool MUFU_SIN>
-__global__ void __launch_bounds__(LB_THREADS)
-lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W, StepSize z, NewRow nr,
-                        const float* __restrict__ hist, float* __restrict__ err_ring, float* __restrict__ avg_err,
-                        u64* __restrict__ best_key, u64* __restrict__ cta_lists, int idx_offset, int emit, FusedMerge fm) {
-    __shared__ u64 skeys[LB_THREADS];
-    const int tid = threadIdx.x;
-    const int v = blockIdx.y;                      // vehicle (Monte-Carlo layout); 0 for a single loop
-    const int cand = blockIdx.x * LB_THREADS + tid;
-    const bool valid = cand < N;
-    const int ci = valid ? cand : N - 1;
-    const Cand p = load_cand(bank, Npad, ci);
-    HistRow r;
-    if (hist) {                                    // rows of many vehicles: ring slot `slot` of hist [V][W][20]
-        const float4* hr = reinterpret_cast<const float4*>(hist + ((size_t)v * W + nr.slot) * LLAMPC_HIST_ROW);
-        r.q0 = __ldg(hr); r.q1 = __ldg(hr + 1); r.q2 = __ldg(hr + 2); r.q3 = __ldg(hr + 3); r.q4 = __ldg(hr + 4);
-    } else {                                       // single loop: the row rides in the kernel parameters
-        r.q0 = make_float4(nr.v[0], nr.v[1], nr.v[2], nr.v[3]);
-        r.q1 = make_float4(nr.v[4], nr.v[5], nr.v[6], nr.v[7]);
-        r.q2 = make_float4(nr.v[8], nr.v[9], nr.v[10], nr.v[11]);
-        r.q3 = make_float4(nr.v[12], nr.v[13], nr.v[14], nr.v[15]);
-        r.q4 = make_float4(nr.v[16], nr.v[17], nr.v[18], nr.v[19]);
-    }
-    err_ring += (size_t)v * W * Npad;
-    bool ok;
-    float e = lookback_step_fast<GEOM_SHARED, MUFU_SIN>(p, r, z, ok);
-    if (!ok) e = lookback_step<GEOM_SHARED, MUFU_SIN>(p, r, z);
-    e *= 0.25f;                                    // errors of rt.py:349 (mean over the 4 scored states)
-    if (valid) err_ring[(size_t)nr.slot * Npad + cand] = e;
-    if (!emit) return;                             // uniform
-    // window re-sum in ring order (deterministic); the loads of 8 columns are issued before the first add so that
-    // enough bytes are in flight per SM for HBM (the ring of 4,096 vehicles is 335 MB: this kernel is HBM-bound there)
-    float sum = 0.0f;
-    const float* col = err_ring + ci;
-    int w = 0;
-    for (; w + 8 <= W; w += 8) {
-        float vq[8];
-#pragma unroll
-        for (int j = 0; j < 8; ++j) vq[j] = __ldcg(col + (size_t)(w + j) * Npad);
-#pragma unroll
-        for (int j = 0; j < 8; ++j) sum += (w + j == nr.slot) ? e : vq[j];
-    }
-    for (; w < W; ++w) sum += (w == nr.slot) ? e : __ldcg(col + (size_t)w * Npad);
-    const float err = sum / (float)W;
-    u64 key = ~0ull;
-    if (valid) {
-        if (avg_err) avg_err[(size_t)v * N + cand] = err;
-        key = pack_key(err, (unsigned)(idx_offset + cand));
-    }
-    cta_select_emit<LB_THREADS / 32>(key, skeys, v, best_key, cta_lists);
-    if (fm.K > 0) {                                // last CTA of the vehicle merges its lists (one launch per tick)
-        __shared__ bool is_last;
-        __shared__ MergeSmem<LB_THREADS> msm;
-        __threadfence();
-        __syncthreads();
-        if (tid == 0) is_last = atomicAdd(fm.ticket + v, 1u) == gridDim.x - 1;
-        __syncthreads();
-        if (!is_last) return;
-        __threadfence();
-        merge_lists_device<LB_THREADS>(cta_lists + (size_t)v * gridDim.x * LLAMPC_LIST_LEN, gridDim.x, fm.K,
-                                       best_key ? best_key + v : nullptr, fm.out + (size_t)v * (LLAMPC_LIST_LEN + 1), msm);
-        if (tid == 0) fm.ticket[v] = 0;
-    }
-}
-
-// ---------------------------------------------------------------------------------------------------
-// K1v rolling window, ONE CTA PER VEHICLE (Monte-Carlo layout: thousands of vehicles, a bank of <= 2,048 candidates
-// each).  Same arithmetic as K1r (one RK4 step per candidate, ring column `slot` replaced, window re-summed in ring
-// order: scores bit-identical to K1r); what changes is everything around the step.  ncu on K1r at 4,096 x 1,024 x 20:
-// ~1,200 instructions per candidate-tick, ~800 of them selection (a 15-stage register bitonic network per warp, three
-// merges per CTA, a list round trip through L2, a last-CTA merge per vehicle: ALU pipe 48 %, FMA 27 %, HBM 19 %).
-//   * Every thread owns FOUR ADJACENT candidates: the ring is re-summed with LDG.128 (5 loads and 10 address
-//     instructions per candidate instead of 20 and 40), the new column is read back by the thread that stored it.
-//   * The vehicle's keys stay in shared memory and are FILTERED, not sorted:
-//       1  every group of 32 keys (warp x candidate slot) leaves its minimum (two REDUX): <= 64 minima per vehicle;
-//       2  warp 0 sorts the minima; T = the K-th smallest.  At least K keys are <= T (those minima themselves), so
-//          the top-K is a subset of {key <= T} -- about K .. 3K keys of the N;
-//       3  the survivors are compacted with a shared-memory counter and warp 0 sorts them 32 at a time (sort +
-//          bitonic merge into the running 32 smallest).  Keys are unique (index in the low word), so the result
-//          does not depend on the compaction order.
-//   * The ring lines a warp will re-sum are prefetched into L2 before its RK4 steps (lane w asks for row w).
-// Needs Npad % 4 == 0 and a 16-byte aligned ring (the entry point falls back to K1r otherwise).
-// ---------------------------------------------------------------------------------------------------
-constexpr int RV_THREADS = 256;
-constexpr int RV_WARPS = RV_THREADS / 32;
-constexpr int RV_CPP = RV_THREADS * 4;             // candidates per pass
-constexpr int RV_MAX_PASSES = 2;
-constexpr int RV_MAX_N = RV_CPP * RV_MAX_PASSES;   // 2,048
-
-__device__ __forceinline__ void prefetch_l2_4lines(const void* p, int n_lines) {
-    asm volatile("prefetch.global.L2 [%0];" ::"l"(p));
-    if (n_lines > 1) asm volatile("prefetch.global.L2 [%0+128];" ::"l"(p));
-    if (n_lines > 2) asm volatile("prefetch.global.L2 [%0+256];" ::"l"(p));
-    if (n_lines > 3) asm volatile("prefetch.global.L2 [%0+384];" ::"l"(p));
-}
-
-#ifndef LLAMPC_RV_MIN_BLOCKS
-#define LLAMPC_RV_MIN_BLOCKS 4
-#endif
-template <bool GEOM_SHARED, bool MUFU_SIN>
-__global__ void __launch_bounds__(RV_THREADS, LLAMPC_RV_MIN_BLOCKS)
-lookback_rolling_vehicle_kernel(const float4* __restrict__ bank, int N, int Npad, int W, StepSize z, int slot,
-                                const float* __restrict__ hist, float* __restrict__ err_ring,
-                                float* __restrict__ avg_err, int idx_offset, int emit, int K, u64* __restrict__ out) {
-    __shared__ float4 srow[5];
-    __shared__ u64 s_key[RV_MAX_N];
-    __shared__ u64 s_cand[RV_MAX_N];
-    __shared__ u64 s_group[RV_MAX_PASSES * RV_WARPS * 4];
-    __shared__ u64 s_thr;
-    __shared__ int s_count;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int v = blockIdx.x;
-    const int passes = (N + RV_CPP - 1) / RV_CPP;
-    if (tid < 5) srow[tid] = __ldg(reinterpret_cast<const float4*>(hist + ((size_t)v * W + slot) * LLAMPC_HIST_ROW) + tid);
-    err_ring += (size_t)v * W * Npad;
-    __syncthreads();
-#pragma unroll 1
-    for (int j = 0; j < passes; ++j) {
-        const int wbase = j * RV_CPP + warp * 128;                 // first candidate of this warp in this pass
-        const int c0 = wbase + lane * 4;                           // this thread's candidates c0 .. c0 + 3
-        if (emit && wbase < N) {
-            const int n_lines = min(4, (Npad - wbase) >> 5);
-            for (int w = lane; w < W; w += 32)
-                if (w != slot) prefetch_l2_4lines(err_ring + (size_t)w * Npad + wbase, n_lines);
-        }
-        u64 key[4] = {~0ull, ~0ull, ~0ull, ~0ull};
-        if (c0 < N) {
-            float* mine = err_ring + (size_t)slot * Npad + c0;
-#pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
-                if (c0 + q >= N) break;
-                const Cand p = load_cand(bank, Npad, c0 + q);
-                HistRow r;
-                r.q0 = srow[0]; r.q1 = srow[1]; r.q2 = srow[2]; r.q3 = srow[3]; r.q4 = srow[4];
-                bool ok;
-                float e = lookback_step_fast<GEOM_SHARED, MUFU_SIN>(p, r, z, ok);
-                if (!ok) e = lookback_step<GEOM_SHARED, MUFU_SIN>(p, r, z);
-                __stcg(mine + q, 0.25f * e);                       // errors of rt.py:349 (mean over the 4 scored states)
-            }
-            if (emit) {
-                // window re-sum in ring order, as K1r; the new column is read back by the thread that just stored it
-                // (program order), so the loop is loads and adds only.  Columns N .. Npad - 1 are padding.
-                float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                const float* col = err_ring + c0;
-                int w = 0;
-                for (; w + 4 <= W; w += 4, col += (size_t)4 * Npad) {
-                    float4 vq[4];
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) vq[i] = __ldcg(reinterpret_cast<const float4*>(col + (size_t)i * Npad));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { sum.x += vq[i].x; sum.y += vq[i].y; sum.z += vq[i].z; sum.w += vq[i].w; }
-                }
-                for (; w < W; ++w, col += Npad) {
-                    const float4 vq = __ldcg(reinterpret_cast<const float4*>(col));
-                    sum.x += vq.x; sum.y += vq.y; sum.z += vq.z; sum.w += vq.w;
-                }
-                const float fw = (float)W;
-                const float err[4] = {sum.x / fw, sum.y / fw, sum.z / fw, sum.w / fw};
-#pragma unroll
-                for (int q = 0; q < 4; ++q)
-                    if (c0 + q < N) {
-                        if (avg_err) avg_err[(size_t)v * N + c0 + q] = err[q];
-                        key[q] = pack_key(err[q], (unsigned)(idx_offset + c0 + q));
-                    }
-            }
-        }
-        if (!emit) continue;                                       // uniform
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-            s_key[j * RV_CPP + q * RV_THREADS + tid] = key[q];     // any order: the filter below scans them all
-            const u64 gmin = warp_min_key(key[q]);
-            if (lane == 0) s_group[(j * RV_WARPS + warp) * 4 + q] = gmin;
-        }
-    }
-    if (!emit) return;
-    __syncthreads();
-    if (warp == 0) {                                               // threshold = K-th smallest group minimum
-        const int ng = passes * RV_WARPS * 4;
-        u64 a = lane < ng ? s_group[lane] : ~0ull;
-        a = warp_sort_u64(a, lane);
-        if (ng > 32) {
-            u64 b = lane + 32 < ng ? s_group[lane + 32] : ~0ull;
-            b = warp_sort_u64(b, lane);
-            a = warp_merge_low32(a, __shfl_sync(0xffffffffu, b, 31 - lane), lane);
-        }
-        const u64 t = __shfl_sync(0xffffffffu, a, K - 1);          // ~0 when fewer than K groups hold a key: keep all
-        if (lane == 0) { s_thr = t; s_count = 0; }
-    }
-    __syncthreads();
-    const u64 T = s_thr;
-    for (int i = tid; i < passes * RV_CPP; i += RV_THREADS) {
-        const u64 k = s_key[i];
-        if (k <= T && k != ~0ull) s_cand[atomicAdd(&s_count, 1)] = k;
-    }
-    __syncthreads();
-    if (warp != 0) return;
-    const int n = s_count;
-    u64 run = ~0ull;
-    for (int c = 0; c < n; c += 32) {
-        u64 k = c + lane < n ? s_cand[c + lane] : ~0ull;
-        k = warp_sort_u64(k, lane);
-        run = c == 0 ? k : warp_merge_low32(run, __shfl_sync(0xffffffffu, k, 31 - lane), lane);
-    }
-    u64* o = out + (size_t)v * (LLAMPC_LIST_LEN + 1);              // out[0] = arg-min key, out[1..K] = ascending top-K
-    if (lane == 0) o[0] = run;
-    if (lane < K) o[1 + lane] = run;
-}
-
-// ---------------------------------------------------------------------------------------------------
 // K4' stand-alone merge of the per-CTA sorted lists written by K1 / K1r into the global top-K (K <= LLAMPC_LIST_LEN),
 // one CTA per vehicle; the algorithm is merge_lists_device (llampc_common.cuh).  Used when a launch produces more
 // than 1,024 lists (otherwise the last CTA of K1 runs the same routine itself); optionally carries the NVLink
-// min-loc exchange.  out[0] = *best_key (then re-armed to ~0 for the next tick), out[1..K] = ascending top-K.
+// min-loc exchange.  out[0] = arg-min key, out[1..K] = ascending top-K.
 // ---------------------------------------------------------------------------------------------------
 template <int MERGE_THREADS>
 __global__ void __launch_bounds__(MERGE_THREADS)
-topk_merge_lists_kernel(const u64* __restrict__ lists, int n_lists, int K, u64* __restrict__ best_key,
-                        u64* __restrict__ out, PeerXchg px) {
+topk_merge_lists_kernel(const u64* __restrict__ lists, int n_lists, int K, u64* __restrict__ out, PeerXchg px) {
     __shared__ MergeSmem<MERGE_THREADS> sm;
     const int v = blockIdx.x;                      // vehicle
     u64* outv = out + (size_t)v * (LLAMPC_LIST_LEN + 1);
-    merge_lists_device<MERGE_THREADS>(lists + (size_t)v * n_lists * LLAMPC_LIST_LEN, n_lists, K,
-                                      best_key ? best_key + v : nullptr, outv, sm);
+    merge_lists_device<MERGE_THREADS>(lists + (size_t)v * n_lists * LLAMPC_LIST_LEN, n_lists, K, outv, sm);
     if (px.world > 1 && threadIdx.x < 32) {        // warp 0: min-loc across the GPUs of the box (single vehicle)
         __syncwarp();
         const u64 mine = __shfl_sync(0xffffffffu, threadIdx.x == 0 ? *reinterpret_cast<volatile u64*>(outv) : 0ull, 0);
         const u64 g = peer_minloc(px, mine, threadIdx.x);
         if (threadIdx.x == 0) outv[0] = g;
     }
-}
-
-__global__ void fill_keys_kernel(u64* keys, int n) {
-    int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) keys[i] = ~0ull;
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -780,246 +313,225 @@ using namespace llampc;
 // ===================================================================================================
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
-// K1p (two candidates per thread, packed f32x2) is the default for banks that can fill the GPU with pair-threads;
-// small banks keep one candidate per thread (twice the threads: measured 12.4 us against 14.2 us per tick at
-// 1,024 x 20).  LLAMPC_K1_PACKED=0 / 1 forces the scalar / packed kernel for every size.
-constexpr int K1P_MIN_CANDIDATES = 8192;
-static bool k1_packed(int N) {
-    static int v = -1;
-    if (v < 0) {
-        const char* e = getenv("LLAMPC_K1_PACKED");
-        v = !e ? 2 : (e[0] == '0' ? 0 : 1);
-    }
-    return v == 2 ? N >= K1P_MIN_CANDIDATES : v != 0;
-}
-static inline int k1_cands_per_cta(int N) { return k1_packed(N) ? 2 * LB_THREADS : LB_THREADS; }
+// K1p (two candidates per thread, packed f32x2) is the default for launches that can fill the GPU with pair-threads;
+// small problems keep one candidate per thread (twice the threads: measured 12.4 us against 14.2 us per tick at
+// 1,024 x 20).  The count that matters is candidates x vehicles of the launch.
+constexpr long K1P_MIN_CANDIDATES = 8192;
+constexpr int MAX_MERGE_LISTS = LB_THREADS * MERGE_LPT;          // lists one CTA can merge in-kernel (1,024)
 
-static int choose_split(int N, int W) {
+static int choose_split(int N, int W, int n_vehicles, bool packed) {
     // SM time ~ (CTAs on the busiest SM) x (rows per thread) while the FMA pipe is the limiter.
+    const int sms = device_sms();
     int best = 1;
     long best_cost = -1;
-    for (int sy = 1; sy <= 16; sy *= 2) {          // 8 and 16 only pay off for banks too small to fill the GPU
+    for (int sy = 1; sy <= 16; sy *= 2) {          // 8 and 16 only pay off for launches too small to fill the GPU
         if (sy > W) break;
-        long ctas = ((long)N * sy + k1_cands_per_cta(N) - 1) / k1_cands_per_cta(N);
-        long cost = ((ctas + NUM_SMS - 1) / NUM_SMS) * ((W + sy - 1) / sy);
+        const int cpc = k1_cands_per_cta(packed, sy);
+        const long ctas = (long)n_vehicles * ((N + cpc - 1) / cpc);
+        const long cost = ((ctas + sms - 1) / sms) * ((W + sy - 1) / sy);
         // a finer split must win by > 3 %: it doubles the number of per-CTA lists the top-K merge has to read
         if (best_cost < 0 || cost * 100 < best_cost * 97) { best_cost = cost; best = sy; }
     }
     return best;
 }
 
-template <int SY, bool GEOM, bool MUFU>
-static int launch_lookback(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
-                           int hist_stride_rows, double Ts, float* avg_err, u64* best_key, u64* cta_lists,
-                           int idx_offset, const NewRow& nr, const FusedMerge& fm, const PeerXchg& px, const TreeMerge& tm,
-                           cudaStream_t st) {
-    const bool packed = k1_packed(N);
-    auto kern = packed ? lookback_window2_kernel<SY, GEOM, MUFU> : lookback_window_kernel<SY, GEOM, MUFU>;
-    const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 * (packed ? 2 : 1) : 0);
-    if (smem > 48 * 1024) {
-        static bool raised[2] = {false, false};  // per kernel (scalar / packed); idempotent attribute, benign if two threads race
-        if (!raised[packed]) {
-            LLAMPC_CUDA_TRY(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-            raised[packed] = true;
-        }
-    }
-    const int CPB = (packed ? 2 * LB_THREADS : LB_THREADS) / SY;
-    dim3 grid((N + CPB - 1) / CPB, n_vehicles);
-    return issue(kern, grid, dim3(LB_THREADS), smem, st, reinterpret_cast<const float4*>(bank), N, Npad, hist, W,
-                 (long)hist_stride_rows * LLAMPC_HIST_ROW, make_step(Ts), avg_err, best_key, cta_lists, idx_offset, nr, fm, px,
-                 tm);
-}
+// Everything llampc_lookback_launch decides before launching; llampc_lookback_plan reports the public part.
+struct LbPlan {
+    int kernel, split, sine, launches;
+    int grid_x, grid_y, block;
+    int n_lists;                 // per vehicle, grid path
+    bool in_kernel_merge;        // grid path: the last CTA of a vehicle merges its lists
+    bool tree;                   // single history: in-kernel merge tree (K1 / K1P / K1B)
+    size_t off_lists;            // grid path workspace: [n_vehicles] tickets, then the lists
+    size_t bytes;
+    TreeLayout lay;
+};
 
-static int lookback_window_impl(const float* bank, int N, int Npad, const float* hist, int W, int n_vehicles,
-                                int hist_stride_rows, double Ts, float* avg_err, llampc_key_t* best_key,
-                                llampc_key_t* cta_lists, int idx_offset, int geom_shared, int split,
-                                const NewRow& nr, const FusedMerge& fm, llampc_stream_t stream,
-                                const PeerXchg& px = PeerXchg{nullptr, 0, 0, 0},
-                                const TreeMerge& tm = TreeMerge{{nullptr, nullptr, nullptr, nullptr, nullptr}, nullptr, 0}) {
-    if (!bank || !hist || (!best_key && !cta_lists && !avg_err && tm.K <= 0) || N <= 0 || Npad < N || n_vehicles <= 0 || hist_stride_rows < W) return LLAMPC_E_ARG;
-    if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
-    if (!aligned16(bank) || !aligned16(hist) || (hist_stride_rows * LLAMPC_HIST_ROW * 4) % 16) return LLAMPC_E_ALIGN;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    int mufu = 0;
-    if (split >= 32) { mufu = 1; split -= 32; }   // bit 5: MUFU.SIN tyre sine (LookBack(fast_sin=True))
-    if (split == 0) split = choose_split(N, W);
-    if (split > W) split = 1;
-#define LB_CASE(SYV)                                                                                                  \
-    case SYV:                                                                                                         \
-        if (mufu) return geom_shared ? launch_lookback<SYV, true, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, st)   \
-                                     : launch_lookback<SYV, false, true>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, st); \
-        return geom_shared ? launch_lookback<SYV, true, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, st)            \
-                           : launch_lookback<SYV, false, false>(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset, nr, fm, px, tm, st);
-    switch (split) {
-        LB_CASE(1)
-        LB_CASE(2)
-        LB_CASE(4)
-        LB_CASE(8)
-        LB_CASE(16)
+static inline size_t up256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+static int resolve_plan(const llampc_lookback_desc_t& d, LbPlan& p) {
+    if (!d.bank || d.N <= 0 || d.Npad < d.N || d.n_vehicles <= 0) return LLAMPC_E_ARG;
+    if (d.W <= 0 || d.W > LLAMPC_MAX_W || d.n_vehicles > 65535 || d.K < 0 || d.K > LLAMPC_LIST_LEN) return LLAMPC_E_RANGE;
+    if (!aligned16(d.bank) || (d.hist && !aligned16(d.hist))) return LLAMPC_E_ALIGN;
+    if ((d.K > 0) != (d.out != nullptr)) return LLAMPC_E_ARG;
+    if (d.K == 0 && !d.avg_err && !(d.mode == LLAMPC_LB_ROLLING && !d.emit)) return LLAMPC_E_ARG;
+    if (d.row32_h && d.n_vehicles != 1) return LLAMPC_E_ARG;
+    if (d.peer_bufs && (d.world < 2 || d.world > 32 || d.rank < 0 || d.rank >= d.world)) return LLAMPC_E_RANGE;
+    p = LbPlan{};
+    p.block = LB_THREADS;
+    p.launches = 1;
+    p.split = 1;
+    switch (d.sine) {
+        case LLAMPC_SIN_SFU: case LLAMPC_SIN_STRICT: p.sine = d.sine; break;
+        // MUFU.SIN holds its rated absolute error (2^-21.4) on [-pi, pi]; beyond it the error grows with the argument
+        // (DESIGN.md section 4), so banks whose tyre-sine argument |C atan(.)| <= |C| pi/2 can leave that range run strict
+        case LLAMPC_SIN_AUTO: p.sine = (d.sin_arg_max > 0.0f && d.sin_arg_max <= 3.14159274f) ? LLAMPC_SIN_SFU : LLAMPC_SIN_STRICT; break;
         default: return LLAMPC_E_ARG;
     }
-#undef LB_CASE
-}
-
-extern "C" int llampc_lookback_window_f32(const float* bank, int N, int Npad, const float* hist, int W,
-                                          int n_vehicles, int hist_stride_rows, double Ts, float* avg_err,
-                                          llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
-                                          int geom_shared, int split, llampc_stream_t stream) {
-    NewRow nr;
-    nr.slot = -1;
-    FusedMerge fm = {nullptr, nullptr, 0};
-    return lookback_window_impl(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists,
-                                idx_offset, geom_shared, split, nr, fm, stream);
-}
-
-extern "C" int llampc_lookback_window_topk_f32(const float* bank, int N, int Npad, const float* hist, int W,
-                                               int n_vehicles, int hist_stride_rows, double Ts, float* avg_err,
-                                               llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
-                                               int geom_shared, int split, int K, unsigned* ticket, llampc_key_t* out,
-                                               llampc_stream_t stream) {
-    if (!cta_lists || !out || !ticket || !best_key) return LLAMPC_E_ARG;
-    if (K <= 0 || K > LLAMPC_LIST_LEN) return LLAMPC_E_RANGE;
-    const int n_lists = llampc_lookback_num_lists(N, W, split);
-    if (n_lists <= 0) return LLAMPC_E_ARG;
-    NewRow nr;
-    nr.slot = -1;
-    if (n_lists > LB_THREADS * MERGE_LPT) {          // too many lists for one CTA: K1, then the stand-alone merge kernel
-        FusedMerge none = {nullptr, nullptr, 0};
-        int rc = lookback_window_impl(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists,
-                                      idx_offset, geom_shared, split, nr, none, stream);
-        if (rc) return rc;
-        return llampc_topk_merge_lists(cta_lists, n_lists, n_vehicles, K, best_key, out, stream);
+    if (d.mode == LLAMPC_LB_ROLLING) {
+        if (!d.err_ring || d.slot < 0 || d.slot >= d.W || (!d.hist && !d.row32_h) || d.peer_bufs) return LLAMPC_E_ARG;
+        const bool selecting = d.emit && d.K > 0;
+        const bool k1v_ok = !d.row32_h && d.N <= RV_MAX_N && d.Npad % 4 == 0 && aligned16(d.err_ring) && (!d.emit || selecting);
+        p.kernel = d.kernel ? d.kernel : (k1v_ok ? LLAMPC_KERNEL_K1V : LLAMPC_KERNEL_K1R);
+        if (p.kernel == LLAMPC_KERNEL_K1V) {
+            if (!k1v_ok) return LLAMPC_E_ARG;
+            p.grid_x = d.n_vehicles; p.grid_y = 1; p.block = RV_THREADS;
+            p.bytes = 0;
+            return 0;
+        }
+        if (p.kernel != LLAMPC_KERNEL_K1R) return LLAMPC_E_ARG;
+        p.n_lists = (d.N + LB_THREADS - 1) / LB_THREADS;
+        if (p.n_lists > MAX_MERGE_LISTS * MERGE_LPT) return LLAMPC_E_RANGE;
+        p.in_kernel_merge = selecting && p.n_lists <= MAX_MERGE_LISTS;
+        if (selecting && !p.in_kernel_merge) p.launches = 2;
+        p.grid_x = p.n_lists; p.grid_y = d.n_vehicles;
+        p.off_lists = up256((size_t)d.n_vehicles * sizeof(unsigned));
+        p.bytes = p.off_lists + up256((size_t)d.n_vehicles * p.n_lists * LLAMPC_LIST_LEN * sizeof(u64));
+        return 0;
     }
-    FusedMerge fm = {ticket, out, K};
-    return lookback_window_impl(bank, N, Npad, hist, W, n_vehicles, hist_stride_rows, Ts, avg_err, best_key, cta_lists,
-                                idx_offset, geom_shared, split, nr, fm, stream);
-}
-
-static int lookback_rolling_impl(const float* bank, int N, int Npad, const float* row32_h, const float* hist, int n_vehicles,
-                                 int slot, int W, double Ts, float* err_ring, float* avg_err, llampc_key_t* best_key,
-                                 llampc_key_t* cta_lists, int idx_offset, int geom_shared, int emit, const FusedMerge& fm,
-                                 llampc_stream_t stream) {
-    if (!bank || (!row32_h && !hist) || !err_ring || N <= 0 || Npad < N || slot < 0 || slot >= W || n_vehicles <= 0)
-        return LLAMPC_E_ARG;
-    if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
-    if (!aligned16(bank) || (hist && !aligned16(hist))) return LLAMPC_E_ALIGN;
-    NewRow nr;
-    if (!hist)
-        for (int i = 0; i < LLAMPC_HIST_ROW; ++i) nr.v[i] = row32_h[i];
-    nr.slot = slot;
-    const dim3 grid((N + LB_THREADS - 1) / LB_THREADS, n_vehicles);
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
-    // the single loop keeps the polynomial tyre sine (its tick is latency-bound anyway); the Monte-Carlo layout runs the
-    // SFU sine of the default K1 tick (MUFU.SIN: scores within 2.2e-5 of the oracle)
-    // (bit 1 of geom_shared asks for the polynomial sine there as well: wide banks, see include/llampc_b200.h)
-    const bool geom = geom_shared & 1, mufu = hist && !(geom_shared & 2);
-    auto kern = mufu ? (geom ? lookback_rolling_kernel<true, true> : lookback_rolling_kernel<false, true>)
-                     : (geom ? lookback_rolling_kernel<true, false> : lookback_rolling_kernel<false, false>);
-    return issue(kern, grid, dim3(LB_THREADS), 0, st, reinterpret_cast<const float4*>(bank), N, Npad, W, make_step(Ts), nr,
-                 hist, err_ring, avg_err, best_key, cta_lists, idx_offset, emit, fm);
-}
-
-static int merge_lists_impl(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K, llampc_key_t* best_key,
-                            llampc_key_t* out, const PeerXchg& px, llampc_stream_t stream);
-
-extern "C" int llampc_lookback_window_topk_peer_f32(const float* bank, int N, int Npad, const float* hist, int W,
-                                                    int hist_stride_rows, double Ts, float* avg_err,
-                                                    llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
-                                                    int geom_shared, int split, int K, unsigned* ticket,
-                                                    llampc_key_t* out, llampc_key_t* const* peer_bufs, int world,
-                                                    int rank, unsigned seq, llampc_stream_t stream) {
-    if (!cta_lists || !out || !ticket || !best_key || !peer_bufs) return LLAMPC_E_ARG;
-    if (K <= 0 || K > LLAMPC_LIST_LEN || world < 2 || world > 32 || rank < 0 || rank >= world) return LLAMPC_E_RANGE;
-    const int n_lists = llampc_lookback_num_lists(N, W, split);
-    if (n_lists <= 0) return LLAMPC_E_ARG;
-    NewRow nr;
-    nr.slot = -1;
-    PeerXchg px = {peer_bufs, world, rank, seq};
-    if (n_lists > LB_THREADS * MERGE_LPT) {          // big shard: K1, then the merge kernel carries the exchange
-        FusedMerge none = {nullptr, nullptr, 0};
-        int rc = lookback_window_impl(bank, N, Npad, hist, W, 1, hist_stride_rows, Ts, avg_err, best_key, cta_lists,
-                                      idx_offset, geom_shared, split, nr, none, stream);
-        if (rc) return rc;
-        return merge_lists_impl(cta_lists, n_lists, 1, K, best_key, out, px, stream);
+    if (d.mode != LLAMPC_LB_RECOMPUTE) return LLAMPC_E_ARG;
+    if (!d.hist || d.hist_stride_rows < d.W) return LLAMPC_E_ARG;
+    if (((long)d.hist_stride_rows * LLAMPC_HIST_ROW * 4) % 16) return LLAMPC_E_ALIGN;
+    const long total = (long)d.N * d.n_vehicles;
+    if (d.n_vehicles > 1 && d.peer_bufs) return LLAMPC_E_ARG;
+    // ---- many vehicles: one CTA per vehicle when a vehicle's bank fits a CTA and the vehicles alone fill the GPU
+    const bool pv_ok = d.n_vehicles > 1 && d.N <= PV_MAX_N && d.K > 0;
+    int kernel = d.kernel;
+    if (!kernel && pv_ok && d.n_vehicles >= 2 * device_sms()) kernel = LLAMPC_KERNEL_K1PV;
+    if (kernel == LLAMPC_KERNEL_K1PV) {
+        if (!pv_ok) return LLAMPC_E_ARG;
+        p.kernel = kernel;
+        p.grid_x = d.n_vehicles; p.grid_y = 1;
+        p.bytes = 0;
+        return 0;
     }
-    FusedMerge fm = {ticket, out, K};
-    return lookback_window_impl(bank, N, Npad, hist, W, 1, hist_stride_rows, Ts, avg_err, best_key, cta_lists, idx_offset,
-                                geom_shared, split, nr, fm, stream, px);
-}
-
-extern "C" int llampc_lookback_rolling_f32(const float* bank, int N, int Npad, const float* row32_h, int slot, int W,
-                                           double Ts, float* err_ring, float* avg_err, llampc_key_t* best_key,
-                                           llampc_key_t* cta_lists, int idx_offset, int geom_shared, int emit,
-                                           llampc_stream_t stream) {
-    FusedMerge none = {nullptr, nullptr, 0};
-    return lookback_rolling_impl(bank, N, Npad, row32_h, nullptr, 1, slot, W, Ts, err_ring, avg_err, best_key, cta_lists,
-                                 idx_offset, geom_shared, emit, none, stream);
-}
-
-extern "C" int llampc_lookback_rolling_multi_f32(const float* bank, int N, int Npad, const float* hist, int n_vehicles,
-                                                 int slot, int W, double Ts, float* err_ring, float* avg_err,
-                                                 llampc_key_t* best_key, llampc_key_t* cta_lists, int idx_offset,
-                                                 int geom_shared, int emit, int K, unsigned* ticket, llampc_key_t* out,
-                                                 llampc_stream_t stream) {
-    if (!hist) return LLAMPC_E_ARG;
-    if (emit && (K < 0 || K > LLAMPC_LIST_LEN)) return LLAMPC_E_RANGE;
-    // banks of <= 2,048 candidates: one CTA per vehicle, top-K by threshold filter in shared memory (K1v; scores and
-    // keys identical to the K1r path below; best_key / cta_lists / ticket are not touched).  LLAMPC_K1R_CTA=0 keeps K1r.
-    const char* sw = getenv("LLAMPC_K1R_CTA");                   // read per call: the parity test flips it
-    if (N > 0 && N <= RV_MAX_N && Npad % 4 == 0 && aligned16(err_ring) && (!emit || (K > 0 && out)) && !(sw && sw[0] == '0')) {
-        if (!bank || !err_ring || Npad < N || slot < 0 || slot >= W || n_vehicles <= 0) return LLAMPC_E_ARG;
-        if (W <= 0 || W > LLAMPC_MAX_W || n_vehicles > 65535) return LLAMPC_E_RANGE;
-        if (!aligned16(bank) || !aligned16(hist)) return LLAMPC_E_ALIGN;
-        cudaStream_t st = static_cast<cudaStream_t>(stream);
-        const bool geom = geom_shared & 1, strict = geom_shared & 2;
-        auto kern = geom ? (strict ? lookback_rolling_vehicle_kernel<true, false> : lookback_rolling_vehicle_kernel<true, true>)
-                         : (strict ? lookback_rolling_vehicle_kernel<false, false> : lookback_rolling_vehicle_kernel<false, true>);
-        return issue(kern, dim3(n_vehicles), dim3(RV_THREADS), 0, st, reinterpret_cast<const float4*>(bank), N, Npad, W,
-                     make_step(Ts), slot, hist, err_ring, avg_err, idx_offset, emit, K, out);
+    bool packed = kernel ? kernel == LLAMPC_KERNEL_K1P : total >= K1P_MIN_CANDIDATES;
+    int sy = d.split ? d.split : choose_split(d.N, d.W, d.n_vehicles, packed);
+    if (sy > d.W) sy = 1;
+    if (sy != 1 && sy != 2 && sy != 4 && sy != 8 && sy != 16) return LLAMPC_E_ARG;
+    const int cpc = k1_cands_per_cta(packed, sy);
+    p.n_lists = (d.N + cpc - 1) / cpc;
+    p.split = sy;
+    p.grid_x = p.n_lists; p.grid_y = d.n_vehicles;
+    if (d.n_vehicles == 1 && d.K > 0) {
+        // ---- one history: in-kernel merge tree.  K1b pays off only where K1 leaves SMs idle AND every K1 thread has a
+        // long serial walk (measured on B200: 4,096 candidates x 1,024 rows 115 us against 133 us)
+        p.tree = true;
+        if (!kernel) kernel = (p.n_lists < device_sms() && (d.W + sy - 1) / sy >= 64) ? LLAMPC_KERNEL_K1B
+                                                                                     : (packed ? LLAMPC_KERNEL_K1P : LLAMPC_KERNEL_K1);
+        if (kernel == LLAMPC_KERNEL_K1B) {
+            const long long b = lookback_balanced_workspace_bytes(d.N, d.W);
+            if (b < 0) return b <= -1000 ? (int)(-1000 - b) : (int)b;
+            p.kernel = kernel;
+            p.bytes = (size_t)b;
+            p.grid_x = 0;                          // persistent grid: SMs x resident CTAs
+            return 0;
+        }
+        if (kernel != LLAMPC_KERNEL_K1 && kernel != LLAMPC_KERNEL_K1P) return LLAMPC_E_ARG;
+        p.kernel = kernel;
+        p.lay = tree_layout(d.N, 0);
+        p.bytes = p.lay.bytes;
+        return 0;
     }
-    const int n_lists = (N + LB_THREADS - 1) / LB_THREADS;
-    const bool in_kernel = emit && K > 0 && ticket && out && cta_lists && best_key && n_lists <= LB_THREADS * MERGE_LPT;
-    FusedMerge fm = {in_kernel ? ticket : nullptr, in_kernel ? out : nullptr, in_kernel ? K : 0};
-    int rc = lookback_rolling_impl(bank, N, Npad, nullptr, hist, n_vehicles, slot, W, Ts, err_ring, avg_err, best_key,
-                                   cta_lists, idx_offset, geom_shared, emit, fm, stream);
-    if (rc || !emit || K == 0 || in_kernel) return rc;
-    if (!cta_lists || !out) return LLAMPC_E_ARG;
-    return llampc_topk_merge_lists(cta_lists, n_lists, n_vehicles, K, best_key, out, stream);
+    if (d.peer_bufs) return LLAMPC_E_ARG;          // the exchange rides on the merge tree
+    if (!kernel) kernel = packed ? LLAMPC_KERNEL_K1P : LLAMPC_KERNEL_K1;
+    if (kernel != LLAMPC_KERNEL_K1 && kernel != LLAMPC_KERNEL_K1P) return LLAMPC_E_ARG;
+    p.kernel = kernel;
+    if (d.K > 0) {
+        if (p.n_lists > MAX_MERGE_LISTS * MERGE_LPT) return LLAMPC_E_RANGE;
+        p.in_kernel_merge = p.n_lists <= MAX_MERGE_LISTS;
+        if (!p.in_kernel_merge) p.launches = 2;
+        p.off_lists = up256((size_t)d.n_vehicles * sizeof(unsigned));
+        p.bytes = p.off_lists + up256((size_t)d.n_vehicles * p.n_lists * LLAMPC_LIST_LEN * sizeof(u64));
+    }
+    return 0;
 }
 
-extern "C" int llampc_lookback_num_lists(int N, int W, int split) {
-    if (N <= 0 || W <= 0) return LLAMPC_E_ARG;
-    if (split >= 32) split -= 32;
-    if (split == 0) split = choose_split(N, W);
-    if (split > W) split = 1;
-    if (split != 1 && split != 2 && split != 4 && split != 8 && split != 16) return LLAMPC_E_ARG;
-    const int cpb = k1_cands_per_cta(N) / split;
-    return (N + cpb - 1) / cpb;
+extern "C" int llampc_lookback_plan(const llampc_lookback_desc_t* desc, llampc_lookback_plan_t* plan) {
+    if (!desc || !plan) return LLAMPC_E_ARG;
+    LbPlan p;
+    const int rc = resolve_plan(*desc, p);
+    if (rc) return rc;
+    plan->kernel = p.kernel; plan->split = p.split; plan->sine = p.sine;
+    plan->grid_x = p.grid_x; plan->grid_y = p.grid_y; plan->block = p.block;
+    plan->launches = p.launches;
+    plan->workspace_bytes = p.bytes;
+    return 0;
 }
 
-static int merge_lists_impl(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K, llampc_key_t* best_key,
-                            llampc_key_t* out, const PeerXchg& px, llampc_stream_t stream) {
-    if (!cta_lists || !out || n_lists <= 0 || n_vehicles <= 0) return LLAMPC_E_ARG;
-    if (K < 0 || K > LLAMPC_LIST_LEN || n_lists > 1024 * MERGE_LPT) return LLAMPC_E_RANGE;
-    cudaStream_t st = static_cast<cudaStream_t>(stream);
+static int merge_lists_launch(const u64* cta_lists, int n_lists, int n_vehicles, int K, u64* out, cudaStream_t st) {
+    const PeerXchg none = {nullptr, 0, 0, 0};
     if (n_lists <= 128 * MERGE_LPT)
-        topk_merge_lists_kernel<128><<<n_vehicles, 128, 0, st>>>(cta_lists, n_lists, K, best_key, out, px);
+        topk_merge_lists_kernel<128><<<n_vehicles, 128, 0, st>>>(cta_lists, n_lists, K, out, none);
     else if (n_lists <= 256 * MERGE_LPT)
-        topk_merge_lists_kernel<256><<<n_vehicles, 256, 0, st>>>(cta_lists, n_lists, K, best_key, out, px);
+        topk_merge_lists_kernel<256><<<n_vehicles, 256, 0, st>>>(cta_lists, n_lists, K, out, none);
     else
-        topk_merge_lists_kernel<1024><<<n_vehicles, 1024, 0, st>>>(cta_lists, n_lists, K, best_key, out, px);
+        topk_merge_lists_kernel<1024><<<n_vehicles, 1024, 0, st>>>(cta_lists, n_lists, K, out, none);
     return (int)cudaGetLastError();
 }
 
-extern "C" int llampc_topk_merge_lists(const llampc_key_t* cta_lists, int n_lists, int n_vehicles, int K,
-                                       llampc_key_t* best_key, llampc_key_t* out, llampc_stream_t stream) {
-    return merge_lists_impl(cta_lists, n_lists, n_vehicles, K, best_key, out, PeerXchg{nullptr, 0, 0, 0}, stream);
+static int lookback_launch_planned(const llampc_lookback_desc_t& d, const LbPlan& p, cudaStream_t st) {
+    if (p.bytes > 0) {
+        if (!d.workspace || d.workspace_bytes < p.bytes) return LLAMPC_E_ARG;
+        if (!aligned16(d.workspace)) return LLAMPC_E_ALIGN;
+    }
+    unsigned char* wsb = static_cast<unsigned char*>(d.workspace);
+    const bool geom = d.geom_shared != 0, mufu = p.sine == LLAMPC_SIN_SFU;
+    const float4* bank = reinterpret_cast<const float4*>(d.bank);
+    NewRow nr;
+    nr.slot = -1;
+    if (d.row32_h) {
+        for (int i = 0; i < LLAMPC_HIST_ROW; ++i) nr.v[i] = d.row32_h[i];
+        nr.slot = d.slot;
+    }
+    PeerXchg px = {nullptr, 0, 0, 0};
+    if (d.peer_bufs) { px.peers = d.peer_bufs; px.world = d.world; px.rank = d.rank; px.seq = d.seq; }
+    const StepSize z = make_step(d.Ts);
+    if (p.kernel == LLAMPC_KERNEL_K1V)
+        return launch_k1v(bank, d.N, d.Npad, d.W, z, d.slot, d.hist, d.n_vehicles, d.err_ring, d.avg_err, d.idx_offset,
+                          d.emit, d.K, d.out, geom, mufu, st);
+    if (p.kernel == LLAMPC_KERNEL_K1R) {
+        nr.slot = d.slot;                          // the kernel reads the slot from here in both row modes
+        unsigned* ticket = reinterpret_cast<unsigned*>(wsb);
+        u64* lists = reinterpret_cast<u64*>(wsb + p.off_lists);
+        const FusedMerge fm = {p.in_kernel_merge ? ticket : nullptr, p.in_kernel_merge ? d.out : nullptr,
+                               p.in_kernel_merge ? d.K : 0};
+        const int rc = launch_k1r(bank, d.N, d.Npad, d.W, z, nr, d.row32_h ? nullptr : d.hist, d.n_vehicles, d.err_ring,
+                                  d.avg_err, lists, d.idx_offset, d.emit, fm, geom, mufu, st);
+        if (rc || p.launches == 1) return rc;
+        return merge_lists_launch(lists, p.n_lists, d.n_vehicles, d.K, d.out, st);
+    }
+    if (p.kernel == LLAMPC_KERNEL_K1PV)
+        return launch_k1pv(bank, d.N, d.Npad, d.hist, d.W, (long)d.hist_stride_rows * LLAMPC_HIST_ROW, d.n_vehicles, z,
+                           d.avg_err, d.idx_offset, d.K, d.out, geom, mufu, st);
+    if (p.kernel == LLAMPC_KERNEL_K1B)
+        return lookback_balanced_launch(d.bank, d.N, d.Npad, d.hist, d.W, d.Ts, d.avg_err, d.idx_offset, geom, mufu, d.K,
+                                        d.workspace, d.workspace_bytes, d.out, nr, px, st);
+    LbArgs a;
+    a.bank = bank; a.N = d.N; a.Npad = d.Npad;
+    a.hist = d.hist; a.W = d.W; a.hist_stride_floats = (long)d.hist_stride_rows * LLAMPC_HIST_ROW; a.n_vehicles = d.n_vehicles;
+    a.z = z; a.avg_err = d.avg_err; a.cta_lists = nullptr; a.idx_offset = d.idx_offset; a.nr = nr;
+    a.fm = FusedMerge{nullptr, nullptr, 0};
+    a.px = px;
+    a.tm = TreeMerge{{nullptr, nullptr, nullptr, nullptr, nullptr}, nullptr, 0};
+    const bool packed = p.kernel == LLAMPC_KERNEL_K1P;
+    if (p.tree) {
+        a.tm = TreeMerge{tree_workspace(wsb, p.lay), d.out, d.K};
+    } else if (d.K > 0) {
+        a.cta_lists = reinterpret_cast<u64*>(wsb + p.off_lists);
+        if (p.in_kernel_merge) a.fm = FusedMerge{reinterpret_cast<unsigned*>(wsb), d.out, d.K};
+    }
+    const int rc = packed ? launch_k1_packed(a, p.split, geom, mufu, st) : launch_k1_scalar(a, p.split, geom, mufu, st);
+    if (rc || p.launches == 1) return rc;
+    return merge_lists_launch(a.cta_lists, p.n_lists, d.n_vehicles, d.K, d.out, st);
 }
 
-extern "C" int llampc_fill_keys(llampc_key_t* keys, int n, llampc_stream_t stream) {
-    if (!keys || n <= 0) return LLAMPC_E_ARG;
-    fill_keys_kernel<<<(n + 255) / 256, 256, 0, static_cast<cudaStream_t>(stream)>>>(keys, n);
-    return (int)cudaGetLastError();
+extern "C" int llampc_lookback_launch(const llampc_lookback_desc_t* desc, llampc_stream_t stream) {
+    if (!desc) return LLAMPC_E_ARG;
+    LbPlan p;
+    const int rc = resolve_plan(*desc, p);
+    if (rc) return rc;
+    return lookback_launch_planned(*desc, p, static_cast<cudaStream_t>(stream));
 }
 
 static int topk_per_cta(int N) {
@@ -1087,151 +599,118 @@ extern "C" int llampc_forces_batch_f32(const float* bank, int N, int Npad, const
     return (int)cudaGetLastError();
 }
 
-// One-launch tick with the tree finish: K1b (persistent warp tasks) when K1's tiling cannot fill the SMs (fewer CTAs
-// than SMs: small banks, or few candidates with a long window), else K1 with the tree merge.
-static int lookback_tree_dispatch(const float* bank, int N, int Npad, const float* hist, int W, double Ts, float* avg_err,
-                                  int idx_offset, int geom_shared, int split, int K, void* workspace,
-                                  unsigned long long workspace_bytes, llampc_key_t* out, const NewRow& nr,
-                                  const PeerXchg& px, llampc_stream_t stream) {
-    if (!workspace || !out) return LLAMPC_E_ARG;
-    if (K <= 0 || K > LLAMPC_LIST_LEN) return LLAMPC_E_RANGE;
-    const int n_lists = llampc_lookback_num_lists(N, W, split);
-    if (n_lists <= 0) return n_lists ? n_lists : LLAMPC_E_ARG;
-    // K1b pays off only where K1 leaves SMs idle AND every K1 thread has a long serial walk (measured on B200: 4,096
-    // candidates x 1,024 rows 115 us against 133 us; everywhere else K1 + tree is equal or faster)
-    int sy = split & 31;
-    if (sy == 0) sy = choose_split(N, W);
-    if (sy > W) sy = 1;
-    const char* force = getenv("LLAMPC_TREE_KERNEL");            // experiments: "k1" / "k1b"
-    const bool k1b = force ? (force[0] == 'k' && force[1] == '1' && force[2] == 'b')
-                           : (n_lists < device_sms() && (W + sy - 1) / sy >= 64);
-    if (k1b)
-        return lookback_balanced_launch(bank, N, Npad, hist, W, Ts, avg_err, idx_offset, geom_shared, (split & 32) != 0, K,
-                                        workspace, workspace_bytes, out, nr, px, static_cast<cudaStream_t>(stream));
-    if (reinterpret_cast<uintptr_t>(workspace) & 15u) return LLAMPC_E_ALIGN;
-    const TreeLayout lay = tree_layout(N, 0);
-    if (workspace_bytes < lay.bytes) return LLAMPC_E_ARG;
-    TreeMerge tm = {tree_workspace(static_cast<unsigned char*>(workspace), lay), out, K};
-    FusedMerge none = {nullptr, nullptr, 0};
-    return lookback_window_impl(bank, N, Npad, hist, W, 1, W, Ts, avg_err, nullptr, nullptr, idx_offset, geom_shared, split,
-                                nr, none, stream, px, tm);
+// ---------------------------------------------------------------------------------------------------
+// The tick: workspace = [256 B of tick counters | look-back workspace | 17-key scratch | stand-alone top-K scratch]
+// ---------------------------------------------------------------------------------------------------
+constexpr size_t TICK_WS_HEAD = 256;               // word 0: re-score ticket, word 1: stand-alone top-K counter
+
+struct TickLayout { llampc_lookback_desc_t d; LbPlan p; int Kt; bool fused; size_t off_lb, off_tmp, off_scratch, bytes; };
+
+static int tick_layout(const llampc_tick_t* t, TickLayout& L) {
+    if (!t || !t->bank || t->K < 0 || t->n_refine < 0) return LLAMPC_E_ARG;
+    L.Kt = t->K > t->n_refine ? t->K : t->n_refine;
+    if (L.Kt > LLAMPC_MAX_K) return LLAMPC_E_RANGE;
+    L.fused = L.Kt <= LLAMPC_LIST_LEN;
+    llampc_lookback_desc_t& d = L.d;
+    memset(&d, 0, sizeof(d));
+    d.bank = t->bank; d.N = t->N; d.Npad = t->Npad; d.idx_offset = t->idx_offset;
+    d.geom_shared = t->geom_shared; d.sin_arg_max = t->sin_arg_max; d.sine = t->sine;
+    d.hist = t->hist; d.W = t->W; d.n_vehicles = 1; d.hist_stride_rows = t->W; d.Ts = t->Ts;
+    d.mode = t->rolling ? LLAMPC_LB_ROLLING : LLAMPC_LB_RECOMPUTE;
+    d.slot = t->slot; d.emit = t->rolling == 2 ? 0 : 1;
+    d.row32_h = t->row32_h; d.err_ring = t->err_ring;
+    d.K = L.fused ? (L.Kt > 0 ? L.Kt : 1) : 1;
+    d.avg_err = t->avg_err; d.out = t->result;
+    d.kernel = t->kernel; d.split = t->split;
+    if (t->rolling == 2) { d.K = 0; d.out = nullptr; }
+    // a rolling tick always carries its row in the kernel parameters (checked by the tick); while only the workspace is
+    // being sized the row pointer may not be set yet, and the plan must not depend on that
+    static const float planning_row[LLAMPC_HIST_ROW] = {0.0f};
+    if (t->rolling && !t->row32_h) d.row32_h = planning_row;
+    const int rc = resolve_plan(d, L.p);
+    if (rc) return rc;
+    L.off_lb = TICK_WS_HEAD;
+    L.off_tmp = L.off_lb + up256(L.p.bytes);
+    L.off_scratch = L.off_tmp + up256((LLAMPC_LIST_LEN + 1) * sizeof(u64));
+    size_t scratch = 0;
+    if (!L.fused) scratch = (size_t)llampc_topk_scratch_ctas(t->N) * L.Kt * sizeof(u64);
+    L.bytes = L.off_scratch + up256(scratch);
+    return 0;
 }
 
-extern "C" long long llampc_lookback_balanced_workspace_bytes(int N, int W) {
-    if (N <= 0 || W <= 0) return LLAMPC_E_ARG;
-    if (W > LLAMPC_MAX_W) return LLAMPC_E_RANGE;
-    return lookback_balanced_workspace_bytes(N, W);
-}
-
-extern "C" int llampc_lookback_window_balanced_f32(const float* bank, int N, int Npad, const float* hist, int W, double Ts,
-                                                   float* avg_err, int idx_offset, int geom_shared, int fast_sin, int K,
-                                                   void* workspace, unsigned long long workspace_bytes, llampc_key_t* out,
-                                                   llampc_key_t* const* peer_bufs, int world, int rank, unsigned seq,
-                                                   llampc_stream_t stream) {
-    NewRow nr;
-    nr.slot = -1;
-    PeerXchg px = {nullptr, 0, 0, 0};
-    if (peer_bufs) {
-        if (world < 2 || world > 32 || rank < 0 || rank >= world) return LLAMPC_E_RANGE;
-        px.peers = peer_bufs; px.world = world; px.rank = rank; px.seq = seq;
-    }
-    return lookback_tree_dispatch(bank, N, Npad, hist, W, Ts, avg_err, idx_offset, geom_shared, fast_sin ? 32 : 0, K,
-                                  workspace, workspace_bytes, out, nr, px, stream);
+extern "C" long long llampc_lookback_tick_workspace_bytes(const llampc_tick_t* t) {
+    TickLayout L;
+    llampc_tick_t probe;
+    if (!t) return LLAMPC_E_ARG;
+    probe = *t;
+    // the rolling layout is the larger of the two rolling phases and does not depend on the phase
+    if (probe.rolling == 2) probe.rolling = 1;
+    if (!probe.result) probe.result = reinterpret_cast<llampc_key_t*>(&probe);   // planning only: any non-NULL value
+    if (probe.rolling && !probe.err_ring) return LLAMPC_E_ARG;
+    if (probe.slot < 0 || probe.slot >= probe.W) probe.slot = 0;
+    const int rc = tick_layout(&probe, L);
+    if (rc) return rc > 0 ? -1000 - rc : rc;
+    return (long long)L.bytes;
 }
 
 extern "C" int llampc_lookback_finish(llampc_tick_t* t, llampc_stream_t stream);
 
 extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
-    if (!t || !t->bank || !t->hist || !t->best_key || !t->result || !t->result_h) return LLAMPC_E_ARG;
-    if (t->slot < 0 || t->slot >= t->W || t->K < 0 || t->n_refine < 0) return LLAMPC_E_ARG;
+    if (!t || !t->bank || !t->hist || !t->result || !t->result_h || !t->workspace) return LLAMPC_E_ARG;
+    if (t->slot < 0 || t->slot >= t->W) return LLAMPC_E_ARG;
+    if (!aligned16(t->workspace)) return LLAMPC_E_ALIGN;
     cudaStream_t st = static_cast<cudaStream_t>(stream);
-    const int Kt = t->K > t->n_refine ? t->K : t->n_refine;
-    if (Kt > LLAMPC_MAX_K) return LLAMPC_E_RANGE;
-    const bool fused = t->cta_lists != nullptr && Kt <= LLAMPC_LIST_LEN;
+    TickLayout L;
+    int rc = tick_layout(t, L);
+    if (rc) return rc;
+    if (t->workspace_bytes < L.bytes) return LLAMPC_E_ARG;
+    if (t->rolling && (!t->err_ring || !t->row32_h || !L.fused)) return LLAMPC_E_ARG;
+    const int Kt = L.Kt;
+    unsigned char* wsb = static_cast<unsigned char*>(t->workspace);
+    unsigned* counters = reinterpret_cast<unsigned*>(wsb);
     llampc_key_t* keys = t->result;                                  // [0] best, [1..Kt] finalists
     double* errs = reinterpret_cast<double*>(t->result + 1 + Kt);    // [Kt] fp64 scores
-    NewRow nr;
-    nr.slot = -1;
-    if (t->row32_h) {                                                // the row rides in the kernel parameters
-        for (int i = 0; i < LLAMPC_HIST_ROW; ++i) nr.v[i] = t->row32_h[i];
-        nr.slot = t->slot;
-    }
+    L.d.workspace = wsb + L.off_lb;
+    L.d.workspace_bytes = L.p.bytes;
+    const bool refine = Kt > 0 && t->n_refine > 0 && t->rolling != 2;
     // ---- the two kernels of a tick (scoring + fp64 re-score) are replayed as one re-parameterised CUDA graph when the
     // tick is a one-launch scoring kernel followed by the re-score (LLAMPC_TICK_GRAPH=0: plain stream launches)
-    static int graph_env = -1;
-    if (graph_env < 0) { const char* e = getenv("LLAMPC_TICK_GRAPH"); graph_env = (e && e[0] == '0') ? 0 : 1; }
-    const int n_lists_roll = (t->N + LB_THREADS - 1) / LB_THREADS;
-    const bool roll_one_launch = t->rolling == 1 && t->ticket != nullptr && Kt > 0 && n_lists_roll <= LB_THREADS * MERGE_LPT &&
-                                 t->err_ring && t->row32_h && fused;
-    const bool tree_one_launch = !t->rolling && fused && t->workspace && Kt > 0;
     PendingLaunch pending[TICK_GRAPH_MAX_NODES];
+    LaunchCollector& lc = launch_collector();
     struct CollectGuard {                                            // never leave the collector armed on an error return
-        bool on;
-        ~CollectGuard() { if (on) { g_collect = nullptr; g_collect_n = 0; } }
-    } guard = {false};
-    if (graph_env && Kt > 0 && t->n_refine > 0 && (roll_one_launch || tree_one_launch)) {
+        LaunchCollector& lc; bool on;
+        ~CollectGuard() { if (on) { lc.slots = nullptr; lc.n = 0; } }
+    } guard = {lc, false};
+    if (lib_env().tick_graph && refine && L.fused && L.p.launches == 1) {
         if (!t->graph_state) t->graph_state = calloc(1, sizeof(TickGraph));
         if (t->graph_state) {
-            g_collect = pending;
-            g_collect_n = 0;
+            lc.slots = pending;
+            lc.n = 0;
             guard.on = true;
         }
     }
-    int rc;
-    if (t->rolling) {
-        // the reference's rolling bookkeeping: one new error column + ring re-sum, then the list merge
-        if (!t->err_ring || !t->row32_h || !fused) return LLAMPC_E_ARG;
-        const int n_lists_r = (t->N + LB_THREADS - 1) / LB_THREADS;
-        const bool in_kernel_r = t->rolling == 1 && t->ticket != nullptr && Kt > 0 && n_lists_r <= LB_THREADS * MERGE_LPT;
-        FusedMerge fmr = {in_kernel_r ? t->ticket : nullptr, in_kernel_r ? keys : nullptr, in_kernel_r ? Kt : 0};
-        rc = lookback_rolling_impl(t->bank, t->N, t->Npad, t->row32_h, nullptr, 1, t->slot, t->W, t->Ts, t->err_ring,
-                                   t->avg_err, t->best_key, t->cta_lists, t->idx_offset, t->geom_shared,
-                                   t->rolling > 1 ? 0 : 1, fmr, stream);
+    if (L.fused) {
+        // K1 / K1p / K1b with the merge tree (or K1r with the last-CTA merge): writes keys[0..LIST_LEN] itself
+        rc = lookback_launch_planned(L.d, L.p, st);
         if (rc) return rc;
-        if (t->rolling > 1) {                                        // window still filling: column stored, no decision
+        if (t->rolling == 2) {                                       // window still filling: column stored, no decision
             if (t->n_refine > 0 && t->row64_h && t->hist64)
                 LLAMPC_CUDA_TRY(cudaMemcpyAsync(t->hist64 + (size_t)t->slot * LLAMPC_HIST64_ROW, t->row64_h,
                                                 LLAMPC_HIST64_ROW * sizeof(double), cudaMemcpyHostToDevice, st));
             return 0;
         }
-        if (!in_kernel_r) {
-            rc = llampc_topk_merge_lists(t->cta_lists, n_lists_r, 1, Kt, t->best_key, keys, stream);
-            if (rc) return rc;
-        }
-    } else if (fused && t->workspace && Kt > 0) {
-        // K1 (or K1b for small grids) with the tree merge, one launch; writes keys[0..LIST_LEN] itself (best_key stays armed)
-        rc = lookback_tree_dispatch(t->bank, t->N, t->Npad, t->hist, t->W, t->Ts, t->avg_err, t->idx_offset,
-                                    t->geom_shared, t->split, Kt, t->workspace, t->workspace_bytes, keys, nr,
-                                    PeerXchg{nullptr, 0, 0, 0}, stream);
-        if (rc) return rc;
-    } else if (fused) {
-        // K1 (block arg-min + per-CTA sorted lists) -> list merge (also moves best_key to keys[0] and re-arms it)
-        const int n_lists = llampc_lookback_num_lists(t->N, t->W, t->split);
-        const bool in_kernel = t->ticket != nullptr && Kt > 0 && n_lists <= LB_THREADS * MERGE_LPT;
-        FusedMerge fm = {in_kernel ? t->ticket : nullptr, in_kernel ? keys : nullptr, in_kernel ? Kt : 0};
-        rc = lookback_window_impl(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key,
-                                  t->cta_lists, t->idx_offset, t->geom_shared, t->split, nr, fm, stream);
-        if (rc) return rc;
-        if (!in_kernel) {
-            rc = llampc_topk_merge_lists(t->cta_lists, n_lists, 1, Kt, t->best_key, keys, stream);
-            if (rc) return rc;
-        }
     } else {
+        // more finalists than a CTA list holds: scores + arg-min from the launch, then the stand-alone top-K over avg_err
         if (!t->avg_err) return LLAMPC_E_ARG;
-        rc = llampc_fill_keys(t->best_key, 1, stream);
+        llampc_key_t* tmp = reinterpret_cast<llampc_key_t*>(wsb + L.off_tmp);
+        L.d.out = tmp;
+        rc = lookback_launch_planned(L.d, L.p, st);
         if (rc) return rc;
-        FusedMerge none = {nullptr, nullptr, 0};
-        rc = lookback_window_impl(t->bank, t->N, t->Npad, t->hist, t->W, 1, t->W, t->Ts, t->avg_err, t->best_key, nullptr,
-                                  t->idx_offset, t->geom_shared, t->split, nr, none, stream);
+        LLAMPC_CUDA_TRY(cudaMemcpyAsync(keys, tmp, sizeof(llampc_key_t), cudaMemcpyDeviceToDevice, st));
+        rc = llampc_topk_f32(t->avg_err, t->N, t->idx_offset, Kt, reinterpret_cast<llampc_key_t*>(wsb + L.off_scratch),
+                             counters + 1, keys + 1, stream);
         if (rc) return rc;
-        LLAMPC_CUDA_TRY(cudaMemcpyAsync(keys, t->best_key, sizeof(llampc_key_t), cudaMemcpyDeviceToDevice, st));
-        if (Kt > 0) {
-            if (!t->topk_scratch || !t->topk_counter) return LLAMPC_E_ARG;
-            rc = llampc_topk_f32(t->avg_err, t->N, t->idx_offset, Kt, t->topk_scratch, t->topk_counter, keys + 1, stream);
-            if (rc) return rc;
-        }
     }
-    const bool refine = Kt > 0 && t->n_refine > 0;
     t->pending_seq = 0;
     t->pending_words = 0;
     if (refine) {
@@ -1242,16 +721,16 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
             for (int i = 0; i < LLAMPC_HIST64_ROW; ++i) nr64.v[i] = t->row64_h[i];
             nr64.slot = t->slot;
         }
-        // zero-copy hand-off: needs the ticket word after the K1 ticket and a host buffer with one spare word
+        // zero-copy hand-off: the last re-score block writes the result into mapped pinned memory
         const bool gather = t->peer_world > 1 && t->peer_bufs != nullptr;
         const int words = gather ? 1 + 2 * Kt * t->peer_world : 1 + 2 * Kt;
         FinalCopy fc = {nullptr, nullptr, nullptr, 0, 0};
         PeerGather pg = {nullptr, 0, 0, 0, 0};
         if (gather) {
-            if (!(t->zero_copy && t->ticket)) return LLAMPC_E_ARG;     // the gather rides on the zero-copy hand-off
+            if (!t->zero_copy) return LLAMPC_E_ARG;                  // the gather rides on the zero-copy hand-off
             pg.peers = t->peer_bufs; pg.world = t->peer_world; pg.rank = t->peer_rank; pg.seq = t->peer_seq; pg.kt = Kt;
         }
-        if (t->zero_copy && t->ticket) {
+        if (t->zero_copy) {
             void* dptr = t->mapped_for == t->result_h ? t->mapped_dev : nullptr;
             if (!dptr && cudaHostGetDevicePointer(&dptr, t->result_h, 0) == cudaSuccess && dptr) {
                 t->mapped_dev = dptr;
@@ -1261,7 +740,7 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
                 static unsigned long long seq_counter = 1;
                 fc.src = t->result;
                 fc.dst_host = static_cast<volatile u64*>(dptr);
-                fc.ticket = t->ticket + 1;
+                fc.ticket = counters;
                 fc.words = 1 + 2 * Kt;
                 fc.seq = ++seq_counter;
                 reinterpret_cast<volatile llampc_key_t*>(t->result_h)[words] = 0;
@@ -1277,9 +756,9 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
         if (rc) return rc;
     }
     if (guard.on) {                                                  // replay what was collected as one graph
-        const int n = g_collect_n;
-        g_collect = nullptr;
-        g_collect_n = 0;
+        const int n = lc.n;
+        lc.slots = nullptr;
+        lc.n = 0;
         guard.on = false;
         if (n > 0) {
             rc = tick_graph_launch(static_cast<TickGraph*>(t->graph_state), pending, n, st);
@@ -1443,10 +922,12 @@ extern "C" int llampc_tick_sizeof(void) { return (int)sizeof(llampc_tick_t); }
 extern "C" int llampc_tick_offsetof(int which) {
     switch (which) {
         case 0: return (int)offsetof(llampc_tick_t, Ts);
-        case 1: return (int)offsetof(llampc_tick_t, cta_lists);
+        case 1: return (int)offsetof(llampc_tick_t, avg_err);
         case 2: return (int)offsetof(llampc_tick_t, result_h);
         case 3: return (int)offsetof(llampc_tick_t, peer_seq);
         case 4: return (int)offsetof(llampc_tick_t, rolling);
+        case 5: return (int)offsetof(llampc_tick_t, workspace);
         default: return -1;
     }
 }
+extern "C" int llampc_lookback_desc_sizeof(void) { return (int)sizeof(llampc_lookback_desc_t); }

@@ -18,8 +18,8 @@
 #include "llampc_common.cuh"
 #include "llampc_model.cuh"
 #include "lookback_select.cuh"
+#include "llampc_launch.cuh"
 #include <stdio.h>
-#include <stdlib.h>
 
 namespace llampc {
 
@@ -179,10 +179,15 @@ lookback_balanced_kernel(const float4* __restrict__ bank, int N, int Npad, const
     tree_merge(run, lane, (int)blockIdx.x, (int)gridDim.x, K, ws, mrows, out, px);
 }
 
-// resident CTAs per SM for a window of W rows (all four kernel variants have the same footprint)
+// resident CTAs per SM for a window of W rows (all four kernel variants have the same footprint); cached per device
 static int bal_occupancy(int W, int* occ_out) {
-    static int cache_w = -1, cache_occ = 0;
-    if (W != cache_w) {
+    struct Entry { int w, occ; };
+    static Entry cache[64] = {};                   // one entry per device, keyed by the last W seen there (w = 0: empty)
+    int dev = 0;
+    LLAMPC_CUDA_TRY(cudaGetDevice(&dev));
+    Entry local = {0, 0};
+    Entry& e = (dev >= 0 && dev < 64) ? cache[dev] : local;
+    if (W != e.w) {
         const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4);
         if (smem > 32 * 1024) {
             LLAMPC_CUDA_TRY(cudaFuncSetAttribute(lookback_balanced_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
@@ -193,10 +198,10 @@ static int bal_occupancy(int W, int* occ_out) {
         int o = 0;
         LLAMPC_CUDA_TRY(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&o, lookback_balanced_kernel<true, true>, LB_THREADS, smem));
         if (o <= 0) return LLAMPC_E_RANGE;
-        cache_occ = o < TREE_MAX_CTAS_PER_SM ? o : TREE_MAX_CTAS_PER_SM;
-        cache_w = W;
+        e.occ = o < TREE_MAX_CTAS_PER_SM ? o : TREE_MAX_CTAS_PER_SM;
+        e.w = W;
     }
-    *occ_out = cache_occ;
+    *occ_out = e.occ;
     return 0;
 }
 
@@ -206,17 +211,18 @@ static int bal_plan(int N, int W, BalPlan& pl) {
     const int rc = bal_occupancy(W, &occ);
     if (rc) return rc;
     long long G = (long long)device_sms() * occ;
-    const long long e = env_ll("LLAMPC_BAL_CTAS", 0);           // experiments: CTAs per SM x 100
+    const LibEnv& env = lib_env();
+    const long long e = env.bal_ctas;                            // experiments (LLAMPC_BAL_CTAS): CTAs per SM x 100
     if (e > 0) G = (long long)device_sms() * e / 100;
     if (G < 1) G = 1;
     if (G > (long long)device_sms() * TREE_MAX_CTAS_PER_SM) G = (long long)device_sms() * TREE_MAX_CTAS_PER_SM;
-    const long long tpw = env_ll("LLAMPC_BAL_TPW", 6);           // target number of tasks per resident warp
-    const long long rmin = env_ll("LLAMPC_BAL_RMIN", 1);
+    const long long tpw = env.bal_tpw;                           // target number of tasks per resident warp
+    const long long rmin = env.bal_rmin;
     BalSched& s = pl.sch;
     s.n_wg = (N + 31) / 32;
     const long long warp_rows = (long long)s.n_wg * W;
     long long R = (warp_rows + G * 4 * tpw - 1) / (G * 4 * tpw);
-    const long long rmax = env_ll("LLAMPC_BAL_RMAX", 10);        // bounds what a starved warp can hold back at the end
+    const long long rmax = env.bal_rmax;                         // bounds what a starved warp can hold back at the end
     if (R > rmax) R = rmax;
     if (R < rmin) R = rmin;
     if (R > W) R = W;
@@ -239,11 +245,12 @@ static int launch_balanced(const float* bank, int N, int Npad, const float* hist
     auto kern = lookback_balanced_kernel<GEOM, MUFU>;
     const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4);
     const BalWs ws = tree_workspace(wsb, pl.lay);
-    if (getenv("LLAMPC_BAL_VERBOSE"))
+    const LibEnv& env = lib_env();
+    if (env.bal_verbose)
         fprintf(stderr, "K1b grid=%d R=%d SY=%d tasks=%d lists=%d\n", pl.grid, pl.sch.R, pl.sch.SY, pl.sch.n_tasks, pl.sch.n_wg);
     kern<<<(unsigned)pl.grid, LB_THREADS, smem, st>>>(reinterpret_cast<const float4*>(bank), N, Npad, hist, W, make_step(Ts),
                                                       avg_err, idx_offset, nr, K, ws, pl.sch, out, px,
-                                                      (getenv("LLAMPC_BAL_TRACE") != nullptr ? 1 : 0) | (getenv("LLAMPC_BAL_NOFENCE") != nullptr ? 2 : 0));
+                                                      (env.bal_trace ? 1 : 0) | (env.bal_nofence ? 2 : 0));
     return (int)cudaGetLastError();
 }
 

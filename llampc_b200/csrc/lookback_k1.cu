@@ -1,0 +1,141 @@
+// K1 look-back window kernel, scalar form (one candidate per thread).  sm_100a.
+//
+// Reference behaviour being replaced: evaluate_models_vectorized (llampc/mpc/evaluate_models_vectorized.py:4-23)
+// + the scoring / selection block of run_nmpc_orca_llampc_rt.py:347-360.
+#include "lookback_kernels.cuh"
+
+namespace llampc {
+
+// ---------------------------------------------------------------------------------------------------
+// K1.  grid = (ceil(N / (128/SY)), n_vehicles); block = 128 threads = (128/SY candidates) x (SY window splits).
+// The W history rows (80 B each) are staged once per CTA with one TMA bulk copy; every warp then reads
+// the same row at the same time (shared-memory broadcast).  Thread (c, sy) integrates window rows
+// sy, sy+SY, ...; partial sums are combined in a fixed order so the result is run-to-run deterministic.
+// (CTA-level selection, NewRow, FusedMerge, PeerXchg: lookback_select.cuh)
+// ---------------------------------------------------------------------------------------------------
+template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
+__global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB_MIN_BLOCKS)
+lookback_window_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
+                       long hist_stride_floats, StepSize z, float* __restrict__ avg_err,
+                       u64* __restrict__ cta_lists, int idx_offset, NewRow nr, FusedMerge fm, PeerXchg px, TreeMerge tm) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ u64 skeys[LB_THREADS];
+    float4* srow = reinterpret_cast<float4*>(smem_raw);
+    float* spart = reinterpret_cast<float*>(smem_raw + (size_t)W * (LLAMPC_HIST_ROW * 4));
+
+    constexpr int CPB = LB_THREADS / SY;
+    const int tid = threadIdx.x;
+    const int v = blockIdx.y;
+    const unsigned bytes = (unsigned)W * (LLAMPC_HIST_ROW * 4);
+
+    if (tid == 0) {                                // one thread arms the barrier and starts the bulk copy right away
+        mbar_init(&mbar, 1);
+        mbar_expect_tx(&mbar, bytes);
+        tma_bulk_g2s(srow, hist + (size_t)v * hist_stride_floats, bytes, &mbar);
+    }
+    __syncthreads();                               // the initialised barrier is visible to the waiting threads
+
+    const int c = tid % CPB, sy = tid / CPB;
+    const int cand = blockIdx.x * CPB + c;
+    const bool valid = cand < N;
+    const Cand p = load_cand(bank, Npad, valid ? cand : N - 1);   // overlaps the bulk copy
+
+    mbar_wait(&mbar, 0);
+    if (nr.slot >= 0) {                            // uniform over the grid
+        if (tid < LLAMPC_HIST_ROW / 4) {
+            const float4 q = make_float4(nr.v[4 * tid], nr.v[4 * tid + 1], nr.v[4 * tid + 2], nr.v[4 * tid + 3]);
+            srow[nr.slot * 5 + tid] = q;
+            if (blockIdx.x == 0 && blockIdx.y == 0)
+                reinterpret_cast<float4*>(const_cast<float*>(hist))[nr.slot * 5 + tid] = q;
+        }
+        __syncthreads();
+    }
+
+    float acc = 0.0f;
+    for (int w = sy; w < W; w += SY) {
+        HistRow r;
+        r.q0 = srow[w * 5 + 0];
+        r.q1 = srow[w * 5 + 1];
+        r.q2 = srow[w * 5 + 2];
+        r.q3 = srow[w * 5 + 3];
+        r.q4 = srow[w * 5 + 4];
+        bool ok;
+        float e = lookback_step_fast<GEOM_SHARED, MUFU_SIN>(p, r, z, ok);
+        if (!ok) e = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, valid ? cand : N - 1, srow + w * 5, z);
+        acc += e;
+    }
+
+    if (SY > 1) {
+        spart[sy * CPB + c] = acc;
+        __syncthreads();
+        if (sy == 0) {
+#pragma unroll
+            for (int j = 1; j < SY; ++j) acc += spart[j * CPB + c];
+        }
+    }
+    // errors = mean over the 4 scored states (rt.py:349); avg = mean over the window (rt.py:357)
+    const float err = acc * (0.25f / (float)W);
+    u64 key = ~0ull;
+    if (sy == 0 && valid) {
+        if (avg_err) avg_err[(size_t)v * N + cand] = err;
+        key = pack_key(err, (unsigned)(idx_offset + cand));
+    }
+    if (tm.K > 0) {                                // uniform over the grid: tree finish (single history), one launch per tick
+        __shared__ u64 mrows[BAL_FAN][BAL_ROW_PAD];
+        key = cta_select32<(CPB >= 32 ? CPB / 32 : 1)>(key, skeys);
+        if (tid < 32) tree_merge(key, tid, (int)blockIdx.x, (int)gridDim.x, tm.K, tm.ws, mrows, tm.out, px);
+        return;
+    }
+    cta_select_emit<(CPB >= 32 ? CPB / 32 : 1)>(key, skeys, v, cta_lists);   // CPB < 32: part of warp 0 holds keys
+    if (fm.K > 0) {                                // uniform over the grid
+        __shared__ bool is_last;
+        __shared__ MergeSmem<LB_THREADS> msm;
+        __threadfence();
+        __syncthreads();
+        if (tid == 0) is_last = atomicAdd(fm.ticket + v, 1u) == gridDim.x - 1;
+        __syncthreads();
+        if (!is_last) return;
+        __threadfence();
+        u64* outv = fm.out + (size_t)v * (LLAMPC_LIST_LEN + 1);
+        merge_lists_device<LB_THREADS>(cta_lists + (size_t)v * gridDim.x * LLAMPC_LIST_LEN, gridDim.x, fm.K, outv, msm);
+        if (tid == 0) fm.ticket[v] = 0;            // ready for the next launch on the same stream
+        if (px.world > 1 && tid < 32) {            // warp 0: min-loc across the GPUs of the box, in this launch
+            __syncwarp();
+            const u64 mine = __shfl_sync(0xffffffffu, tid == 0 ? *reinterpret_cast<volatile u64*>(outv) : 0ull, 0);
+            const u64 g = peer_minloc(px, mine, tid);
+            if (tid == 0) outv[0] = g;
+        }
+    }
+}
+
+template <int SY, bool GEOM, bool MUFU>
+static int launch_one(const LbArgs& a, cudaStream_t st) {
+    auto kern = lookback_window_kernel<SY, GEOM, MUFU>;
+    const size_t smem = (size_t)a.W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 * 1 : 0);
+    const int rc = raise_dynamic_smem(kern, smem);
+    if (rc) return rc;
+    const int CPB = (1 * LB_THREADS) / SY;
+    dim3 grid((a.N + CPB - 1) / CPB, a.n_vehicles);
+    return issue(kern, grid, dim3(LB_THREADS), smem, st, a.bank, a.N, a.Npad, a.hist, a.W, a.hist_stride_floats, a.z, a.avg_err,
+                 a.cta_lists, a.idx_offset, a.nr, a.fm, a.px, a.tm);
+}
+
+template <int SY>
+static int launch_sy(const LbArgs& a, bool geom, bool mufu, cudaStream_t st) {
+    if (mufu) return geom ? launch_one<SY, true, true>(a, st) : launch_one<SY, false, true>(a, st);
+    return geom ? launch_one<SY, true, false>(a, st) : launch_one<SY, false, false>(a, st);
+}
+
+int launch_k1_scalar(const LbArgs& a, int sy, bool geom, bool mufu, cudaStream_t st) {
+    switch (sy) {
+        case 1: return launch_sy<1>(a, geom, mufu, st);
+        case 2: return launch_sy<2>(a, geom, mufu, st);
+        case 4: return launch_sy<4>(a, geom, mufu, st);
+        case 8: return launch_sy<8>(a, geom, mufu, st);
+        case 16: return launch_sy<16>(a, geom, mufu, st);
+        default: return LLAMPC_E_ARG;
+    }
+}
+
+}  // namespace llampc

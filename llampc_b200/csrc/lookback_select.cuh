@@ -2,7 +2,6 @@
 // row that rides in the kernel parameters, the in-kernel list merge descriptor and the NVLink peer min-loc.
 #pragma once
 #include "llampc_common.cuh"
-#include <stdlib.h>
 
 namespace llampc {
 
@@ -35,16 +34,14 @@ __device__ __forceinline__ u64 cta_select32(u64 key, u64* skeys) {
     return key;
 }
 
-// K1 / K1r: lane 0 of warp 0 = block arg-min (one atomicMin per CTA); lanes 0..15 = this CTA's list for the top-K merge.
+// K1 / K1r grid path: lanes 0..15 of warp 0 write this CTA's ascending list for the per-vehicle top-K merge.
 template <int KW, bool PRESORTED = false>
-__device__ __forceinline__ void cta_select_emit(u64 key, u64* skeys, int v, u64* __restrict__ best_key,
-                                                u64* __restrict__ cta_lists) {
+__device__ __forceinline__ void cta_select_emit(u64 key, u64* skeys, int v, u64* __restrict__ cta_lists) {
     key = cta_select32<KW, PRESORTED>(key, skeys);
     if ((threadIdx.x >> 5) == 0) {
         const int lane = threadIdx.x & 31;
         if (cta_lists && lane < LLAMPC_LIST_LEN)
             cta_lists[((size_t)v * gridDim.x + blockIdx.x) * LLAMPC_LIST_LEN + lane] = key;
-        if (lane == 0 && best_key && key != ~0ull) atomicMin(best_key + v, key);
     }
 }
 
@@ -165,23 +162,18 @@ __device__ __forceinline__ void tree_merge(u64 key, int lane, int idx, int n, in
 constexpr int TREE_MAX_CTAS_PER_SM = 8;
 
 static inline int device_sms() {
-    static int sms = 0;
-    if (sms == 0) {
-        int dev = 0, v = 0;
-        if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
+    static int sms[64] = {0};                      // per device (one process may drive several GPUs)
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) { (void)cudaGetLastError(); return 148; }
+    if (sms[dev] == 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) {
             (void)cudaGetLastError();
             v = 148;                               // B200
         }
-        sms = v;
+        sms[dev] = v;
     }
-    return sms;
-}
-
-static inline long long env_ll(const char* name, long long dflt) {
-    const char* e = getenv(name);
-    if (!e || !*e) return dflt;
-    const long long v = atoll(e);
-    return v > 0 ? v : dflt;
+    return sms[dev];
 }
 
 // Workspace layout.  Counters come first at offsets that depend on N only, so a workspace zeroed once stays valid when
@@ -222,7 +214,7 @@ static inline BalWs tree_workspace(unsigned char* wsb, const TreeLayout& l) {
 // Optional tree finish of K1 (single history): warp 0 of every CTA enters tree_merge with the CTA's list.  K = 0 disables it.
 struct TreeMerge { BalWs ws; u64* out; int K; };
 
-// K1b (lookback_balanced.cu): internal launcher shared with the one-call tick in lookback.cu.
+// K1b (lookback_balanced.cu): internal launcher shared with the C ABI in lookback.cu.
 long long lookback_balanced_workspace_bytes(int N, int W);
 int lookback_balanced_launch(const float* bank, int N, int Npad, const float* hist, int W, double Ts, float* avg_err,
                              int idx_offset, int geom_shared, int mufu_sin, int K, void* workspace,

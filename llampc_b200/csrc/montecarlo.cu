@@ -133,8 +133,8 @@ __device__ __forceinline__ void philox4x32_10(unsigned c0, unsigned c1, unsigned
 
 __global__ void __launch_bounds__(128)
 bank_generate_kernel(BankGenArgs a, int N, int Npad, unsigned long long seed, float* __restrict__ packed,
-                     double* __restrict__ bank64) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+                     double* __restrict__ bank64, float* __restrict__ sin_arg_max) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;     // Npad is a multiple of the warp size for every caller: full warps
     if (i >= Npad) return;
     const int src = i < N ? i : N - 1;             // padding rows repeat the last candidate
     double v[LLAMPC_NPARAM];
@@ -159,6 +159,16 @@ bank_generate_kernel(BankGenArgs a, int N, int Npad, unsigned long long seed, fl
         }
     }
     pack_candidate(v, packed, Npad, i);
+    if (sin_arg_max) {                             // bound of the tyre-sine argument |C atan(.)| <= max(|Cf|, |Cr|) pi/2
+        float m = (float)(fmax(fabs(v[6]), fabs(v[7])) * 1.5707963267948966);
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 16));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 8));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 4));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 2));
+        m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, 1));
+        // non-negative floats order like their bit patterns; NaN (a NaN parameter) maps above every finite value
+        if ((threadIdx.x & 31) == 0) atomicMax(reinterpret_cast<unsigned*>(sin_arg_max), __float_as_uint(m == m ? m : __int_as_float(0x7f800000)));
+    }
     if (bank64 && i < N) {
 #pragma unroll
         for (int j = 0; j < LLAMPC_NPARAM; ++j) bank64[(size_t)j * N + i] = v[j];
@@ -216,12 +226,14 @@ advance_tick_kernel(const u64* __restrict__ topk, int topk_stride, int* __restri
 using namespace llampc;
 
 extern "C" int llampc_bank_generate_f32(const double* center_h, const double* sigma_h, int N, int Npad,
-                                        unsigned long long seed, float* packed, double* bank64, llampc_stream_t stream) {
+                                        unsigned long long seed, float* packed, double* bank64, float* sin_arg_max,
+                                        llampc_stream_t stream) {
     if (!center_h || !sigma_h || !packed || N <= 0 || Npad < N) return LLAMPC_E_ARG;
+    if (sin_arg_max && Npad % 32) return LLAMPC_E_ARG;           // the warp reduction wants full warps
     if (reinterpret_cast<uintptr_t>(packed) & 15u) return LLAMPC_E_ALIGN;
     BankGenArgs a;
     for (int j = 0; j < LLAMPC_NPARAM; ++j) { a.center[j] = center_h[j]; a.sigma[j] = sigma_h[j]; }
-    bank_generate_kernel<<<(Npad + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, N, Npad, seed, packed, bank64);
+    bank_generate_kernel<<<(Npad + 127) / 128, 128, 0, static_cast<cudaStream_t>(stream)>>>(a, N, Npad, seed, packed, bank64, sin_arg_max);
     return (int)cudaGetLastError();
 }
 

@@ -8,6 +8,9 @@ model of the bank over the last W transitions and returns the arg-min and the K 
 Window semantics (= the reference): W independent one-step RK4 predictions, each re-anchored at the measured
 state; no decision until W transitions have been seen (rt.py:354-357).  The window is recomputed from the
 device-resident history ring every tick (stateless w.r.t. the bank, so the bank may be replaced at any time).
+
+``LookbackLaunch`` wraps the device-resident launch underneath (``llampc_lookback_launch``: many vehicles, rolling rings,
+NVLink min-loc across GPUs); ``LookBack`` is the per-tick object a controller loop holds.
 """
 import ctypes as C
 import os
@@ -27,32 +30,122 @@ def decode_keys(keys):
     return err, idx
 
 
+_SINE = {None: _lib.SIN_AUTO, "auto": _lib.SIN_AUTO, "sfu": _lib.SIN_SFU, "strict": _lib.SIN_STRICT,
+         True: _lib.SIN_SFU, False: _lib.SIN_STRICT}
+_KERNEL = {None: 0, "auto": 0, "k1": _lib.KERNEL_K1, "k1p": _lib.KERNEL_K1P, "k1b": _lib.KERNEL_K1B,
+           "k1pv": _lib.KERNEL_K1PV, "k1r": _lib.KERNEL_K1R, "k1v": _lib.KERNEL_K1V}
+
+
+def sine_mode(fast_sin):
+    """``fast_sin`` argument of the host classes -> LLAMPC_SIN_*: None / "auto" lets the library pick MUFU.SIN while the
+    bank's tyre-sine argument stays within [-pi, pi] (else the polynomial); True / "sfu" and False / "strict" force a
+    mode; the environment variable LLAMPC_FAST_SIN=1 / 0 overrides the automatic choice (experiments)."""
+    if fast_sin is None or fast_sin == "auto":
+        env = os.environ.get("LLAMPC_FAST_SIN")
+        if env is not None:
+            return _lib.SIN_SFU if env == "1" else _lib.SIN_STRICT
+    return _SINE[fast_sin]
+
+
+class LookbackLaunch:
+    """One ``llampc_lookback_desc_t`` plus the workspace it needs: the device-resident scoring + selection launch
+    (``llampc_lookback_launch``) for any layout -- one history or many vehicles, recompute or rolling, one GPU or the
+    NVLink min-loc across several.  ``plan`` holds the library's choices (kernel, window split, sine mode, launches).
+
+    bank      ModelBank;  hist: float32 CUDA tensor [n_vehicles][stride_rows][20] (or [W][20])
+    out       int64 CUDA tensor [n_vehicles][17] (allocated when K > 0 and not given)
+    """
+
+    def __init__(self, bank, hist, W, Ts, K=10, n_vehicles=1, hist_stride_rows=None, idx_offset=0, mode="recompute",
+                 err_ring=None, avg_err=None, out=None, fast_sin=None, kernel=None, split=0, peer=None):
+        torch = _lib.require_cuda()
+        self.torch, self.bank, self.hist, self.peer = torch, bank, hist, peer
+        self._L = _lib.lib()
+        d = _lib.LookbackDesc()
+        d.bank, d.N, d.Npad, d.idx_offset = bank.packed.data_ptr(), bank.N, bank.Npad, int(idx_offset)
+        d.geom_shared, d.sin_arg_max, d.sine = int(bank.geom_shared), float(bank.sin_arg_max), sine_mode(fast_sin)
+        d.hist, d.W, d.n_vehicles = (hist.data_ptr() if hist is not None else None), int(W), int(n_vehicles)
+        d.hist_stride_rows, d.Ts = int(W if hist_stride_rows is None else hist_stride_rows), float(Ts)
+        d.mode = _lib.LB_ROLLING if mode == "rolling" else _lib.LB_RECOMPUTE
+        d.emit = 1
+        self.err_ring, self.avg_err = err_ring, avg_err
+        d.err_ring = err_ring.data_ptr() if err_ring is not None else None
+        d.avg_err = avg_err.data_ptr() if avg_err is not None else None
+        d.K = int(K)
+        if K > 0 and out is None:
+            out = torch.zeros((n_vehicles, _lib.LIST_LEN + 1), dtype=torch.int64, device=bank.device)
+        self.out = out
+        d.out = out.data_ptr() if out is not None else None
+        d.kernel, d.split = _KERNEL[kernel] if not isinstance(kernel, int) else kernel, int(split)
+        if peer is not None:
+            d.peer_bufs, d.world, d.rank, d.seq = peer.peer_ptrs.data_ptr(), peer.world, peer.rank, 1
+        self.desc = d
+        self.plan = _lib.LookbackPlan()
+        with torch.cuda.device(bank.device):
+            if mode == "rolling":
+                d.slot = 0
+            _lib.check(self._L.llampc_lookback_plan(C.byref(d), C.byref(self.plan)), "llampc_lookback_plan")
+        nbytes = int(self.plan.workspace_bytes)
+        self.workspace = torch.zeros(max(nbytes, 16), dtype=torch.uint8, device=bank.device)
+        d.workspace, d.workspace_bytes = self.workspace.data_ptr(), nbytes
+        d.peer_bufs = peer.peer_ptrs.data_ptr() if peer is not None else None
+        self._ref = C.byref(d)
+
+    @property
+    def kernel_name(self):
+        return _lib.KERNEL_NAMES[self.plan.kernel]
+
+    @property
+    def sine_name(self):
+        return _lib.SIN_NAMES[self.plan.sine]
+
+    def launch(self, stream=None, slot=None, emit=None, row32_h=None, use_peer=True):
+        """Enqueue the launch on `stream` (raw cudaStream_t; default: torch's current stream)."""
+        d = self.desc
+        if slot is not None:
+            d.slot = int(slot)
+        if emit is not None:
+            d.emit = int(emit)
+        d.row32_h = row32_h
+        if self.peer is not None:
+            if use_peer:
+                d.peer_bufs, d.seq = self.peer.peer_ptrs.data_ptr(), self.peer.next_seq()
+            else:
+                d.peer_bufs = None
+        st = self.torch.cuda.current_stream().cuda_stream if stream is None else stream
+        rc = self._L.llampc_lookback_launch(self._ref, st)
+        if rc:
+            _lib.check(rc, "llampc_lookback_launch")
+
+    def keys(self):
+        """out as uint64 ndarray [n_vehicles][17] (synchronises)."""
+        return self.out.cpu().numpy().view(np.uint64)
+
+
 class LookBack:
     """bank_params: dict of the 14 ``Dynamic`` parameters (scalar or (N,) arrays) or a ``ModelBank``.
 
     W        look-back window length (LookBack_W, rt.py:67)
     K        number of best candidates returned (smoothing_mu_over_mod = 10, rt.py:69,360)
-    refine   re-score the max(K, refine) best fp32 candidates in fp64 on the device and order them by the
-             fp64 score: the returned indices and errors are then exact in the reference's arithmetic
-             (0 = fp32 scores only).  max(K, refine) <= 16 uses the fused two-launch tick (K1 writes per-CTA
-             sorted lists, a K-way merge kernel finishes); larger values use the stand-alone top-K kernel.
-    fast_sin evaluate the tyre sine with MUFU.SIN (SFU) instead of the FMA-pipe polynomial: ~17 % faster; measured
-             worst per-candidate score error 2.2e-5 (C1) / 8.8e-6 (C2) / 3.8e-5 (sigma = 2 bank) instead of
-             8.7e-6 / 9.8e-6 / 6.7e-5 relative -- both inside the 1e-4 tolerance, and the fp64 re-score makes the
-             returned indices exact either way.  Default: on (strict mode: fast_sin=False or LLAMPC_FAST_SIN=0).
+    refine   re-score the max(K, refine) best fp32 candidates in fp64 on the device and order them by the fp64 score:
+             ordering and scores among the fp32 finalists are then exact in the reference's arithmetic (membership in
+             the finalist set is decided by the fp32 scores; 0 = fp32 scores only).  max(K, refine) <= 16 finishes the
+             top-K inside the scoring launch (merge tree); larger values add the stand-alone top-K kernel.
+    fast_sin tyre sine: None / "auto" (default) = MUFU.SIN (SFU) while the bank's tyre-sine argument |C| pi/2 stays
+             within [-pi, pi], where MUFU.SIN keeps its rated 2^-21.4 absolute error, else the FMA-pipe polynomial
+             (~17 % slower, range-independent).  True / False force the SFU / polynomial
+             (LLAMPC_FAST_SIN=1 / 0 does the same for every object).  ``sine_name`` reports what runs.
     mode     "recompute" (default): every tick re-integrates the whole W-row window from the history ring (N*W RK4
              steps, stateless w.r.t. the bank); "rolling": the reference's own bookkeeping (rt.py:352-354) -- only the
              newest transition is integrated and its error column replaces the oldest one in a device-resident
              (W, N) ring, the window mean is re-summed (N steps + N*W*4 bytes per tick)
-    balanced recompute mode with max(K, refine) <= 16: run the work-balanced kernel K1b (equal contiguous ranges of
-             (candidate group, window row) units over exactly SMs x resident CTAs persistent CTAs, top-K finished by an
-             in-kernel tree of warp merges) instead of K1 + list merge.  Default: on (LLAMPC_BALANCED=0 disables).
+    kernel / split   overrides of the library's kernel choice (None / 0 = automatic; "k1", "k1p", "k1b")
     idx_offset / group   multi-GPU: this rank's bank is the slice starting at global index idx_offset;
              `group` is a torch.distributed process group (None = single GPU)
     """
 
     def __init__(self, bank_params, W, Ts=0.02, K=10, refine=16, device=None, idx_offset=0, group=None, split=0,
-                 mode="recompute", fast_sin=None, balanced=None):
+                 mode="recompute", fast_sin=None, kernel=None):
         torch = _lib.require_cuda()
         self.torch = torch
         self.bank = bank_params if isinstance(bank_params, ModelBank) else ModelBank(bank_params, device)
@@ -63,13 +156,9 @@ class LookBack:
         self.Kt = max(self.K, self.n_refine)
         if self.Kt > _lib.MAX_K:
             raise ValueError("max(K, refine) must be <= %d" % _lib.MAX_K)
-        if fast_sin is None:
-            fast_sin = os.environ.get("LLAMPC_FAST_SIN", "1") == "1"
-        self.fast_sin = bool(fast_sin)
-        if balanced is None:
-            balanced = os.environ.get("LLAMPC_BALANCED", "1") == "1"
-        # bit 5 (+32) of `split` selects the MUFU.SIN tyre sine in K1 (include/llampc_b200.h)
-        self.idx_offset, self.group, self.split = int(idx_offset), group, int(split) | (32 if self.fast_sin else 0)
+        self.sine = sine_mode(fast_sin)
+        self.idx_offset, self.group, self.split = int(idx_offset), group, int(split)
+        self.kernel = _KERNEL[kernel] if not isinstance(kernel, int) else kernel
         if mode not in ("recompute", "rolling"):
             raise ValueError("mode must be 'recompute' or 'rolling'")
         self.rolling = mode == "rolling"
@@ -78,22 +167,11 @@ class LookBack:
         self.hist = torch.zeros((self.W, _lib.HIST_ROW), dtype=torch.float32, device=dev)
         self.hist64 = torch.zeros((self.W, _lib.HIST64_ROW), dtype=torch.float64, device=dev)
         self.avg_err = torch.empty(N, dtype=torch.float32, device=dev)
-        self.best_key = torch.empty(1, dtype=torch.int64, device=dev)
-        self.best_key.fill_(-1)                                   # armed once; the merge kernel re-arms it every tick
-        n_lists = L.llampc_lookback_num_lists(N, self.W, self.split)
-        if self.rolling:
-            n_lists = max(n_lists, (N + 127) // 128)
-        self.fused = self.Kt <= _lib.LIST_LEN and 0 < n_lists <= 8192
+        self.fused = self.Kt <= _lib.LIST_LEN
         if self.rolling and not self.fused:
-            raise ValueError("rolling mode needs max(K, refine) <= %d and N <= 1,048,576" % _lib.LIST_LEN)
+            raise ValueError("rolling mode needs max(K, refine) <= %d" % _lib.LIST_LEN)
         self.err_ring = torch.zeros((self.W, self.bank.Npad), dtype=torch.float32, device=dev) if self.rolling else None
-        self.n_lists = n_lists
-        self.cta_lists = torch.empty(max(1, n_lists) * _lib.LIST_LEN, dtype=torch.int64, device=dev) if self.fused else None
-        if not self.fused:
-            ctas = L.llampc_topk_scratch_ctas(N)
-            self.topk_scratch = torch.empty(max(1, ctas * max(self.Kt, 1)), dtype=torch.int64, device=dev)
-            self.topk_counter = torch.zeros(1, dtype=torch.int32, device=dev)
-        # result: best key | Kt finalist keys | Kt fp64 scores  (the merge kernel writes LIST_LEN + 1 words)
+        # result: best key | Kt finalist keys | Kt fp64 scores  (the scoring launch writes LIST_LEN + 1 words)
         words = max(2 + 2 * self.Kt, _lib.LIST_LEN + 2)           # + 1 spare word: zero-copy sequence flag
         self._peer = None
         if group is not None and self.n_refine > 0 and os.environ.get("LLAMPC_PEER_GATHER", "1") == "1":
@@ -126,32 +204,26 @@ class LookBack:
         t = _lib.Tick()
         t.bank, t.N, t.Npad = self.bank.packed.data_ptr(), N, self.bank.Npad
         t.hist, t.W, t.Ts = self.hist.data_ptr(), self.W, self.Ts
-        t.geom_shared, t.split, t.idx_offset = int(self.bank.geom_shared), self.split, self.idx_offset
-        t.avg_err, t.best_key = self.avg_err.data_ptr(), self.best_key.data_ptr()
+        t.geom_shared, t.sin_arg_max, t.sine = int(self.bank.geom_shared), float(self.bank.sin_arg_max), self.sine
+        t.kernel, t.split, t.idx_offset = self.kernel, self.split, self.idx_offset
+        t.avg_err = self.avg_err.data_ptr()
         t.K, t.n_refine = self.K, self.n_refine
-        t.cta_lists = self.cta_lists.data_ptr() if self.fused else None
-        if not self.fused:
-            t.topk_scratch, t.topk_counter = self.topk_scratch.data_ptr(), self.topk_counter.data_ptr()
         if self.n_refine > 0:
             t.bank64, t.hist64 = self.bank.bank64.data_ptr(), self.hist64.data_ptr()
         t.result, t.result_h = self.result.data_ptr(), self.result_h.data_ptr()
         t.sync = 1
-        self.ticket = torch.zeros(2, dtype=torch.int32, device=dev)
-        t.ticket = self.ticket.data_ptr()
         t.zero_copy = int(os.environ.get("LLAMPC_ZERO_COPY", "1") == "1")
         if self._peer is not None:
             t.zero_copy = 1
             t.peer_bufs, t.peer_world, t.peer_rank = self._peer.peer_ptrs.data_ptr(), self._peer.world, self._peer.rank
         if self.rolling:
             t.err_ring, t.rolling = self.err_ring.data_ptr(), 1
-        # K1b: work-balanced persistent kernel with the in-kernel tree merge (one launch per tick)
-        self.balanced = bool(balanced) and self.fused and not self.rolling and self.Kt > 0
-        if self.balanced:
-            nbytes = int(L.llampc_lookback_balanced_workspace_bytes(N, self.W))
-            if nbytes <= 0:
-                _lib.check(nbytes if nbytes > -1000 else -1000 - nbytes, "llampc_lookback_balanced_workspace_bytes")
-            self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
-            t.workspace, t.workspace_bytes = self.workspace.data_ptr(), nbytes
+        with torch.cuda.device(dev):
+            nbytes = int(L.llampc_lookback_tick_workspace_bytes(C.byref(t)))
+        if nbytes < 0:
+            _lib.check(nbytes if nbytes > -1000 else -1000 - nbytes, "llampc_lookback_tick_workspace_bytes")
+        self.workspace = torch.zeros(nbytes, dtype=torch.uint8, device=dev)
+        t.workspace, t.workspace_bytes = self.workspace.data_ptr(), nbytes
         self._tick = t
         self._tick_ref = C.byref(t)
         self._L = L
@@ -167,6 +239,32 @@ class LookBack:
         get_raw = getattr(torch._C, "_cuda_getCurrentRawStream", None)
         self._get_device = get_dev if get_dev is not None else torch.cuda.current_device
         self._get_raw_stream = get_raw if get_raw is not None else (lambda i: torch.cuda.current_stream(i).cuda_stream)
+
+    def plan(self):
+        """The library's choices for this object's scoring launch: dict(kernel, split, sine, launches, grid)."""
+        d = _lib.LookbackDesc()
+        t = self._tick
+        d.bank, d.N, d.Npad, d.idx_offset = t.bank, t.N, t.Npad, t.idx_offset
+        d.geom_shared, d.sin_arg_max, d.sine = t.geom_shared, t.sin_arg_max, t.sine
+        d.hist, d.W, d.n_vehicles, d.hist_stride_rows, d.Ts = t.hist, t.W, 1, t.W, t.Ts
+        d.mode = _lib.LB_ROLLING if self.rolling else _lib.LB_RECOMPUTE
+        d.emit, d.err_ring, d.row32_h = 1, t.err_ring, (self._r32_base if self.rolling else None)
+        d.K, d.avg_err, d.out = (min(max(self.Kt, 1), _lib.LIST_LEN)), t.avg_err, t.result
+        d.kernel, d.split = t.kernel, t.split
+        p = _lib.LookbackPlan()
+        with self._stream_dev:
+            _lib.check(self._L.llampc_lookback_plan(C.byref(d), C.byref(p)), "llampc_lookback_plan")
+        return {"kernel": _lib.KERNEL_NAMES[p.kernel], "split": p.split, "sine": _lib.SIN_NAMES[p.sine],
+                "launches": p.launches, "grid": (p.grid_x, p.grid_y), "block": p.block}
+
+    @property
+    def sine_name(self):
+        return self.plan()["sine"]
+
+    @property
+    def fast_sin(self):
+        """True when the scoring launch runs the SFU (MUFU.SIN) tyre sine."""
+        return self.plan()["sine"] == _lib.SIN_NAMES[_lib.SIN_SFU]
 
     def __del__(self):
         try:                                                     # frees the CUDA graph the C tick attached to the struct
@@ -189,6 +287,9 @@ class LookBack:
 
     def load_window(self, x_k, u_k, x_k1):
         """Replace the whole ring by W transitions: x_k (W,6), u_k (W,2), x_k1 (W,>=4) (oldest first)."""
+        if self.rolling:                                         # the (W, N) error ring would stay empty
+            raise _lib.LlampcError("load_window() only fills the history ring; in mode='rolling' push the W transitions "
+                                   "(or use mode='recompute')")
         x_k, u_k, x_k1 = np.asarray(x_k), np.asarray(u_k), np.asarray(x_k1)
         if x_k.shape[0] != self.W:
             raise ValueError("load_window needs exactly W transitions")
@@ -364,7 +465,7 @@ class LookBack:
             raise ValueError("set_bank needs a bank of the same size on the same device")
         self.bank = bank
         t = self._tick
-        t.bank, t.geom_shared = bank.packed.data_ptr(), int(bank.geom_shared)
+        t.bank, t.geom_shared, t.sin_arg_max = bank.packed.data_ptr(), int(bank.geom_shared), float(bank.sin_arg_max)
         if self.n_refine > 0:
             t.bank64 = bank.bank64.data_ptr()
         if self.rolling:

@@ -23,20 +23,20 @@ rt.py:326-344, look-back at :347-366), the look-back of tick t and steps 1-2 of 
 them concurrently on two streams (fork after the estimate, join before returning), so after `tick()` the plan (`xref`,
 `U`, `projidx`) is already the one of the NEXT tick; the constructor plans for tick 0.
 """
-import os
 
 import numpy as np
 
 from .. import _lib
 from ..bank import ModelBank, PARAM_NAMES
 from ..tracks import RacelineTable
+from .lookback import LookbackLaunch
 
 
 class MonteCarlo:
     def __init__(self, bank_params, table, x_init, projidx_init, plant_params, drop_start, V=None, W=20, K_models=10,
                  K_seq=32, H=20, Ts=0.02, scale=0.9, mu_init=1.0, seed=4, sigma_pwm=0.1, sigma_steer=0.05,
                  drop_rate=1.0 / 22.0, drop_len=0.2, initial_model=0, smoothing_mu=20, mu_alpha=0.08, limits=None,
-                 lookback_mode="rolling", use_graphs=False, fast_sin=None):
+                 lookback_mode="rolling", use_graphs=False, fast_sin=None, lookback_kernel=None):
         torch = _lib.require_cuda()
         self.torch, self.L = torch, _lib.lib()
         self.bank = bank_params if isinstance(bank_params, ModelBank) else ModelBank(bank_params)
@@ -100,11 +100,13 @@ class MonteCarlo:
         # tick; "recompute" re-integrates every vehicle's whole window every tick (W times the look-back work)
         self.rolling = lookback_mode == "rolling"
         self.err_ring = torch.zeros((V, W, self.bank.Npad), dtype=f32, device=dev) if self.rolling else None
-        self.n_lists = (N + 127) // 128 if self.rolling else self.L.llampc_lookback_num_lists(N, W, 0)
-        self.cta_lists = torch.empty((V, self.n_lists, _lib.LIST_LEN), dtype=i64, device=dev)
-        self.best_key = torch.full((V,), -1, dtype=i64, device=dev)
         self.topk = torch.zeros((V, _lib.LIST_LEN + 1), dtype=i64, device=dev)
-        self.ticket = torch.zeros(V, dtype=i32, device=dev)
+        # the look-back launch of every tick (llampc_lookback_launch): rolling -> K1v (one CTA per vehicle), recompute ->
+        # K1pv (one CTA per vehicle, packed step) or the (candidate tile, vehicle) grid; tyre sine None = automatic (SFU
+        # while the bank's tyre-sine argument stays within [-pi, pi]), True / False force a mode
+        self.lb = LookbackLaunch(self.bank, self.hist, W, self.Ts, K=K_models, n_vehicles=V, hist_stride_rows=W,
+                                 mode=lookback_mode, err_ring=self.err_ring, out=self.topk, fast_sin=fast_sin,
+                                 kernel=lookback_kernel)
         self.qrp = np.array([1.0, 1.0, 5e-3, 1.0, 0.0, 0.0], dtype=np.float32)
         self.tick_count = 0
         self.lookback_steps = 0
@@ -112,11 +114,6 @@ class MonteCarlo:
         # the time of the friction schedule lives on the device so that a whole tick can be replayed as a CUDA graph
         self.t_dev = torch.zeros((), dtype=f64, device=dev)
         self.use_graphs = bool(use_graphs)
-        # tyre sine of the rolling look-back: MUFU.SIN as in the default LookBack tick, or the polynomial (strict mode:
-        # fast_sin=False or LLAMPC_FAST_SIN=0; banks as wide as sigma = 2 hold candidates that need it for the 1e-4 tolerance)
-        if fast_sin is None:
-            fast_sin = os.environ.get("LLAMPC_FAST_SIN", "1") == "1"
-        self.fast_sin = bool(fast_sin)
         self._graphs = {}                                          # ring slot -> captured tick (steady state only)
         # planner + control sampling of the next tick run beside the look-back of this one (high-priority side stream: the
         # planner's few latency-bound CTAs must get their SM slots before the look-back fills the machine)
@@ -206,17 +203,9 @@ class MonteCarlo:
             # ... beside the look-back of this tick on the main stream
             full = idt >= self.W
             if pushing and self.rolling:
-                chk(L.llampc_lookback_rolling_multi_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), V, slot,
-                                                        self.W, self.Ts, self.err_ring.data_ptr(), None,
-                                                        self.best_key.data_ptr(), self.cta_lists.data_ptr(), 0,
-                                                        int(bank.geom_shared) | (0 if self.fast_sin else 2), int(full), self.Km,
-                                                        self.ticket.data_ptr(),
-                                                        self.topk.data_ptr(), st), "lookback (rolling)")
+                self.lb.launch(st, slot=slot, emit=int(full))
             elif pushing and full:
-                chk(L.llampc_lookback_window_topk_f32(bank.packed.data_ptr(), bank.N, bank.Npad, self.hist.data_ptr(), self.W,
-                                                      V, self.W, self.Ts, None, self.best_key.data_ptr(),
-                                                      self.cta_lists.data_ptr(), 0, int(bank.geom_shared), 32, self.Km,
-                                                      self.ticket.data_ptr(), self.topk.data_ptr(), st), "lookback+merge")
+                self.lb.launch(st)
             if full:                                               # the model of the next tick's look-ahead
                 chk(L.llampc_mc_advance_tick_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.model_idx.data_ptr(), None,
                                                  None, V, None, self.Ts, st), "model index")

@@ -15,13 +15,33 @@ import sys
 import types
 import warnings
 
-REFERENCE_ROOT = os.environ.get("LLAMPC_REFERENCE_ROOT", "/root/reference")
+_HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+def _resolve_root():
+    """LLAMPC_REFERENCE_ROOT, else the reference checkout of the build container, else the offline install of the
+    UNMODIFIED reference package under baseline/_ref (pip install --no-deps --target baseline/_ref; git-ignored, travels to
+    the GPU box; it holds the Python package only, not the recorded dataset / raceline files)."""
+    cands = [os.environ.get("LLAMPC_REFERENCE_ROOT"), "/root/reference",
+             os.path.join(os.path.dirname(_HERE), "baseline", "_ref")]
+    for c in cands:
+        if c and os.path.isdir(os.path.join(c, "llampc", "models")):
+            return c
+    return cands[0] or cands[1]
+
+
+REFERENCE_ROOT = _resolve_root()
 
 _loaded = None
 
 
 def available() -> bool:
     return os.path.isdir(os.path.join(REFERENCE_ROOT, "llampc", "models"))
+
+
+def has_data() -> bool:
+    """True when the tree also carries the reference's data files (recorded dataset, raceline tables)."""
+    return os.path.isfile(os.path.join(REFERENCE_ROOT, "llampc", "data", "DYN-GPMPC-NOCONS-with_var_speedsETHZ.npz"))
 
 
 def load():
@@ -42,8 +62,11 @@ def load():
         from llampc.params import ORCA
         from llampc.models import Dynamic
         from llampc.mpc.evaluate_models_vectorized import evaluate_models_vectorized
-        from llampc.mpc.planner import ConstantSpeed
-        from llampc.tracks import ETHZ, ETHZMobil
+        try:                                         # planner / tracks need the raceline data files next to the package
+            from llampc.mpc.planner import ConstantSpeed
+            from llampc.tracks import ETHZ, ETHZMobil
+        except Exception:
+            ConstantSpeed = ETHZ = ETHZMobil = None
     ns = types.SimpleNamespace(ORCA=ORCA, Dynamic=Dynamic, ETHZ=ETHZ, ETHZMobil=ETHZMobil,
                                evaluate_models_vectorized=evaluate_models_vectorized,
                                ConstantSpeed=ConstantSpeed, root=REFERENCE_ROOT)

@@ -25,7 +25,13 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
         assert n in _lib.PROTOTYPES, "ctypes prototype missing for %s" % n
-    assert lib.llampc_abi_version() == 4
+    assert lib.llampc_abi_version() == 5
+    lookback = [n for n in names if n.startswith('llampc_lookback_')]
+    assert {'llampc_lookback_launch', 'llampc_lookback_tick', 'llampc_lookback_push'} <= set(lookback)
+    # three look-back entry points + helpers (plan / finish / decode / release / sizes); the six overlapping launch
+    # functions of ABI v4 are gone
+    assert not [n for n in lookback if 'window' in n or 'rolling' in n or 'balanced' in n]
+    assert b'peer' in lib.llampc_error_string(-4)
     assert b"aligned" in lib.llampc_error_string(-2)
 
 
@@ -54,8 +60,13 @@ def _pack(params, N, Npad):
     ptrs = (C.c_void_p * 14)(*[params[k].ctypes.data for k in _lib.PARAM_NAMES])
     flags = (C.c_int * 14)(*[int(params[k].ndim == 1) for k in _lib.PARAM_NAMES])
     out = np.zeros((4, Npad, 4), dtype=np.float32)
-    rc = _lib.lib().llampc_bank_pack_h(C.cast(ptrs, C.c_void_p), C.cast(flags, C.c_void_p), N, Npad, out.ctypes.data)
+    arg_max = C.c_float(-1.0)
+    rc = _lib.lib().llampc_bank_pack_h(C.cast(ptrs, C.c_void_p), C.cast(flags, C.c_void_p), N, Npad, out.ctypes.data,
+                                       C.addressof(arg_max))
     assert rc == 0
+    # bound of the tyre-sine argument C atan(B alpha): max(|Cf|, |Cr|) pi/2 (sine mode "auto")
+    want = max(np.abs(params["Cf"]).max(), np.abs(params["Cr"]).max()) * np.pi / 2
+    assert arg_max.value == np.float32(want)
     return out
 
 
@@ -73,7 +84,7 @@ def test_bank_pack_layout():
     assert np.all(out[3, :300, 0] == np.float32(bank["Cm2"]))
     # padding rows repeat the last candidate
     assert np.array_equal(out[:, 300:, :], np.broadcast_to(out[:, 299:300, :], (4, 84, 4)))
-    assert _lib.lib().llampc_bank_pack_h(None, None, 1, 1, None) == -1
+    assert _lib.lib().llampc_bank_pack_h(None, None, 1, 1, None, None) == -1
 
 
 def test_hist_row_pack(history):
@@ -185,8 +196,28 @@ def test_ctypes_prototypes_match_header_arity():
 def test_tick_struct_layout_matches_c():
     lib = _lib.lib()
     assert lib.llampc_tick_sizeof() == C.sizeof(_lib.Tick)
-    for which, field in enumerate(("Ts", "cta_lists", "result_h", "peer_seq", "rolling")):
+    for which, field in enumerate(("Ts", "avg_err", "result_h", "peer_seq", "rolling", "workspace")):
         assert lib.llampc_tick_offsetof(which) == getattr(_lib.Tick, field).offset, field
+    assert lib.llampc_lookback_desc_sizeof() == C.sizeof(_lib.LookbackDesc)
+
+
+def test_lookback_desc_argument_errors_need_no_gpu():
+    """llampc_lookback_plan validates the descriptor before touching the device: argument errors come back as LLAMPC_E_*."""
+    lib = _lib.lib()
+    d, p = _lib.LookbackDesc(), _lib.LookbackPlan()
+    assert lib.llampc_lookback_plan(None, C.byref(p)) == -1
+    assert lib.llampc_lookback_plan(C.byref(d), C.byref(p)) == -1             # no bank
+    buf = np.zeros(64, dtype=np.float32)
+    base = buf.ctypes.data + (-buf.ctypes.data) % 16
+    d.bank, d.N, d.Npad, d.n_vehicles, d.W = base, 8, 8, 1, 2000
+    assert lib.llampc_lookback_plan(C.byref(d), C.byref(p)) == -3             # W beyond LLAMPC_MAX_W
+    d.W, d.K = 4, 17
+    assert lib.llampc_lookback_plan(C.byref(d), C.byref(p)) == -3             # K beyond LLAMPC_LIST_LEN
+    d.K, d.bank = 4, base + 4
+    assert lib.llampc_lookback_plan(C.byref(d), C.byref(p)) == -2             # bank not 16-byte aligned
+    d.bank = base
+    assert lib.llampc_lookback_plan(C.byref(d), C.byref(p)) == -1             # K > 0 without out
+    assert lib.llampc_lookback_launch(None, None) == -1
 
 
 def test_threshold_filter_selection_argument():

@@ -6,7 +6,7 @@ import pytest
 from oracle import llampc_oracle as orc
 from oracle import reference_adapter as ra
 
-pytestmark = pytest.mark.skipif(not ra.available(), reason="/root/reference not present (GPU box)")
+pytestmark = pytest.mark.skipif(not ra.available(), reason="no reference tree (/root/reference or baseline/_ref)")
 
 
 def test_rhs_and_rk4_random_banks():

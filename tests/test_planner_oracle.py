@@ -51,7 +51,7 @@ def test_survey_lookahead_kat(tracks):
     assert np.array_equal(xref, g["xref"])
 
 
-@pytest.mark.skipif(not ra.available(), reason="/root/reference not present (GPU box)")
+@pytest.mark.skipif(not (ra.available() and ra.has_data()), reason="reference tree with its raceline data not present (GPU box)")
 def test_against_imported_reference_random(tracks):
     ref = ra.load()
     trk_ref = ref.ETHZMobil(reference='optimal', longer=True)

@@ -37,16 +37,16 @@ def run_case(name, bank, W, t_end, split=0):
 
 
 def time_kernel(lb, split, reps=50):
-    st = torch.cuda.current_stream().cuda_stream
+    """scores-only launch (no selection) of the kernel the LookBack object would run"""
+    from llampc_b200.mpc.lookback import LookbackLaunch
+    ll = LookbackLaunch(lb.bank, lb.hist, lb.W, lb.Ts, K=0, avg_err=lb.avg_err, split=split)
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
     for _ in range(5):
-        L.llampc_lookback_window_f32(lb.bank.packed.data_ptr(), lb.bank.N, lb.bank.Npad, lb.hist.data_ptr(), lb.W, 1, lb.W,
-                                     lb.Ts, lb.avg_err.data_ptr(), lb.best_key.data_ptr(), None, 0, int(lb.bank.geom_shared), split, st)
+        ll.launch()
     torch.cuda.synchronize()
     ev[0].record()
     for _ in range(reps):
-        L.llampc_lookback_window_f32(lb.bank.packed.data_ptr(), lb.bank.N, lb.bank.Npad, lb.hist.data_ptr(), lb.W, 1, lb.W,
-                                     lb.Ts, lb.avg_err.data_ptr(), lb.best_key.data_ptr(), None, 0, int(lb.bank.geom_shared), split, st)
+        ll.launch()
     ev[1].record()
     torch.cuda.synchronize()
     ms = ev[0].elapsed_time(ev[1]) / reps
