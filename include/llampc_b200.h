@@ -89,9 +89,8 @@ int llampc_hist_row_pack_h(const double* x_k, const double* u_k, const double* x
 #define LLAMPC_KERNEL_K1    1   /* window kernel, one candidate per thread                                                  */
 #define LLAMPC_KERNEL_K1P   2   /* window kernel, two candidates per thread in packed f32x2 (FFMA2 / FMUL2 / FADD2)        */
 #define LLAMPC_KERNEL_K1B   3   /* persistent warp-task window kernel (single history, few CTAs x long windows)            */
-#define LLAMPC_KERNEL_K1PV  4   /* window kernel, one CTA per vehicle (n_vehicles > 1, N <= 2,048), packed, in-CTA top-K   */
-#define LLAMPC_KERNEL_K1R   5   /* rolling kernel, grid over (candidates, vehicles)                                         */
-#define LLAMPC_KERNEL_K1V   6   /* rolling kernel, one CTA per vehicle (N <= 2,048, Npad % 4 == 0), in-CTA top-K           */
+#define LLAMPC_KERNEL_K1R   4   /* rolling kernel, grid over (candidates, vehicles)                                         */
+#define LLAMPC_KERNEL_K1V   5   /* rolling kernel, one CTA per vehicle (N <= 2,048, Npad % 4 == 0), in-CTA top-K           */
 
 typedef struct llampc_lookback_desc {
     /* bank: packed (llampc_bank_pack_h layout), device, 16-byte aligned; keys carry idx_offset + i */
@@ -147,9 +146,9 @@ int llampc_lookback_plan(const llampc_lookback_desc_t* desc, llampc_lookback_pla
  *   RECOMPUTE, one history       K1P when N >= 8,192 else K1, top-K finished INSIDE the launch by a tree of 32-way warp
  *                                merges that overlaps the integration (the root writes `out` and runs the NVLink min-loc);
  *                                K1B when that tiling would leave SMs idle while every thread walks >= 64 rows
- *   RECOMPUTE, many vehicles     K1PV (one CTA per vehicle, in-CTA top-K) when N <= 2,048 and the vehicles fill the GPU;
- *                                else K1 / K1P over (candidate tiles, vehicles), packed when N * n_vehicles >= 8,192, the
- *                                last CTA of a vehicle to retire merges its lists
+ *   RECOMPUTE, many vehicles     K1 / K1P over (candidate tiles, vehicles): packed and window split chosen from
+ *                                N * n_vehicles (the launch, not the vehicle, has to fill the GPU); the last CTA of a vehicle
+ *                                to retire merges its lists inside the launch
  *   ROLLING                      K1V when N <= 2,048, Npad % 4 == 0 and rows come from `hist`; else K1R */
 int llampc_lookback_launch(const llampc_lookback_desc_t* desc, llampc_stream_t stream);
 

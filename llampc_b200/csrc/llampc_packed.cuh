@@ -27,6 +27,9 @@ __device__ __forceinline__ F2 mul2(F2 a, F2 b) { F2 r; asm("mul.rn.f32x2 %0, %1,
 __device__ __forceinline__ F2 add2(F2 a, F2 b) { F2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 __device__ __forceinline__ F2 sub2(F2 a, F2 b) { F2 r; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r.v) : "l"(a.v), "l"(b.v)); return r; }
 
+// sign flip of both components on the ALU pipe (two LOP3) instead of an FMUL2 by -1 on the FMA pipe
+__device__ __forceinline__ F2 neg2(F2 a) { F2 r; r.v = a.v ^ 0x8000000080000000ull; return r; }
+
 // component-wise helpers for what has no packed instruction (MUFU, min/max, selects)
 __device__ __forceinline__ F2 rcp_abs2(F2 a) {
     float x, y; up(a, x, y);
@@ -247,6 +250,141 @@ __device__ __forceinline__ F2 lookback_step_fast2(const Cand2& p, const HistRow&
     ok0 = (fmaxf(g.t0, fabsf(t0)) <= 0.5f) && (fmaxf(fabsf(o0), fabsf(p0)) <= 0.125f) && (q0 == q0);
     ok1 = (fmaxf(g.t1, fabsf(t1)) <= 0.5f) && (fmaxf(fabsf(o1), fabsf(p1)) <= 0.125f) && (q1 == q1);
     return e2;
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Packed pieces of the look-ahead rollout (lookahead.cu, K2p): two MODELS per thread on one control sequence.
+// K2p is bound by FMA-pipe cycles (ncu: math-pipe throttle + fixed-latency wait; 4 CTAs / SM or an Estrin polynomial
+// change nothing or lose, profiles/r02_k2p_variants.txt), so everything here is written to need FEWER packed operations.
+// ---------------------------------------------------------------------------------------------------
+// atan(q), |q| <= 1, 7 coefficients: absolute error 5.0e-7 (tools/fit_coeffs.py, degree 6 in q^2) -- the size of
+// MUFU.SIN's own error (2^-21.4 = 3.6e-7), which the tyre force already carries.  One FFMA2 fewer than atan_unit7.
+__device__ __forceinline__ F2 atan_unit2_la(F2 q) {
+    const F2 s = mul2(q, q);
+    F2 p = bc(-6.6536013602e-03f);
+    p = fma2(p, s, bc(3.0787179075e-02f));
+    p = fma2(p, s, bc(-6.7951120877e-02f));
+    p = fma2(p, s, bc(1.0449814999e-01f));
+    p = fma2(p, s, bc(-1.4189631985e-01f));
+    p = fma2(p, s, bc(1.9994621885e-01f));
+    p = fma2(p, s, bc(-3.3333283787e-01f));
+    return fma2(mul2(q, s), p, q);
+}
+
+// np.arctan2(y, avx) for avx >= 0 and ANY magnitudes (atan2_pos_full), two components.  Candidate models of the
+// rollout spin within the horizon (12 % of the warp-steps of config C3 see a slip tangent above 1), so there is no
+// guard and no fallback here: q = min / max in [0, 1] (one MUFU.RCP per component), the polynomial in packed
+// arithmetic, octant fix-up and sign per component.  A NaN operand is dropped by min / max: a NaN state still reaches
+// the increments through the drivetrain force and the vy w / vx w terms.
+__device__ __forceinline__ F2 atan2_pos_full2(F2 y, float avx0, float avx1) {
+    float y0, y1;
+    up(y, y0, y1);
+    const float ay0 = fabsf(y0), ay1 = fabsf(y1);
+    const float q0 = fminf(ay0, avx0) * rcp_approx(fmaxf(fmaxf(ay0, avx0), 1e-30f));
+    const float q1 = fminf(ay1, avx1) * rcp_approx(fmaxf(fmaxf(ay1, avx1), 1e-30f));
+    const F2 a = atan_unit2_la(pk(q0, q1));
+    float a0, a1;
+    up(a, a0, a1);
+    a0 = (ay0 > avx0) ? (LLAMPC_PIO2_HI - a0) : a0;
+    a1 = (ay1 > avx1) ? (LLAMPC_PIO2_HI - a1) : a1;
+    return pk(copysignf(a0, y0), copysignf(a1, y1));
+}
+
+// atan(z) for any z (atan_full2) with the 7-coefficient polynomial
+__device__ __forceinline__ F2 atan_full2_la(F2 z) {
+    const F2 zz = mul2(z, z);
+    float z0, z1, q0, q1;
+    up(zz, q0, q1);
+    up(z, z0, z1);
+    const F2 q = mul2(z, pk(rcp_approx(fmaxf(q0, 1.0f)), rcp_approx(fmaxf(q1, 1.0f))));
+    const F2 a = atan_unit2_la(q);
+    float a0, a1;
+    up(a, a0, a1);
+    a0 = (q0 > 1.0f) ? (copysignf(LLAMPC_PIO2_HI, z0) - a0) : a0;
+    a1 = (q1 > 1.0f) ? (copysignf(LLAMPC_PIO2_HI, z1) - a1) : a1;
+    return pk(a0, a1);
+}
+
+// D sin(C atan(z)) with z = B alpha already formed
+__device__ __forceinline__ F2 pacejka_la2(F2 z, F2 C, F2 D) {
+    const F2 t = mul2(C, atan_full2_la(z));
+    float t0, t1;
+    up(t, t0, t1);
+    return mul2(D, pk(sin_mufu(t0), sin_mufu(t1)));
+}
+
+// d/dt of (vx, vy, omega) for two models on the same control input, slip angles of any size (accel_fast<.., true>)
+// Bfd = Bf delta and nBf = -Bf are formed once per step: Bf (delta - a) = nBf a + Bfd is one FFMA2 per stage.
+__device__ __forceinline__ Deriv2 accel_full2(const Cand2& p, const Ctl& u, const Drive2& drv, F2 nBf, F2 Bfd, F2 vx, F2 vy, F2 w) {
+    float vx0, vx1;
+    up(vx, vx0, vx1);
+    const float avx0 = fabsf(vx0), avx1 = fabsf(vx1);
+    const F2 zf = fma2(nBf, atan2_pos_full2(fma2(p.lf, w, vy), avx0, avx1), Bfd);      // Bf alpha_f
+    const F2 nzr = mul2(p.Br, atan2_pos_full2(fma2(p.nlr, w, vy), avx0, avx1));        // -(Br alpha_r): the sign rides through the odd functions
+    const F2 Frx = drive_force_fast2(p, drv, vx);
+    const F2 Ffy = pacejka_la2(zf, p.Cf, p.Df);
+    const F2 nFry = pacejka_la2(nzr, p.Cr, p.Dr);
+    const F2 Fc = mul2(Ffy, bc(u.cd));
+    Deriv2 r;
+    r.vx = fma2(fma2(Ffy, bc(-u.sd), Frx), p.inv_m, mul2(vy, w));
+    r.nvy = fma2(sub2(nFry, Fc), p.inv_m, mul2(vx, w));
+    r.w = fma2(Fc, p.lf_Iz, mul2(nFry, p.lr_Iz));
+    return r;
+}
+
+// sin / cos of the heading psi0 + phi for two models: the rollouts carry the heading RELATIVE to the shared start heading
+// (phi stays a small fp32 number), sin / cos phi come from the SFU (MUFU.SIN / MUFU.COS: absolute error 2^-21.4, i.e. a
+// position error of v h 4e-7 ~ 1e-8 m per step), and the rotation by the start heading uses its fp64-formed sin / cos as
+// broadcast scalars: 4 packed operations + 4 MUFU per stage instead of the 15 packed operations of a polynomial
+// sin / cos + rotation, valid for ANY heading change (no tiny-angle guard, no fallback).
+__device__ __forceinline__ void heading2(F2 phi, float s0, float c0, F2& sn, F2& cs) {
+    float a0, a1;
+    up(phi, a0, a1);
+    const F2 sp = pk(__sinf(a0), __sinf(a1)), cp = pk(__cosf(a0), __cosf(a1));
+    sn = fma2(bc(s0), cp, mul2(bc(c0), sp));
+    cs = fma2(bc(c0), cp, mul2(bc(-s0), sp));
+}
+
+// One RK4 step of two models (rk4_increment_fast, same stages).  State in / out: position relative to the start (X, Y),
+// heading relative to the start heading (phi), vx, vy, omega.  The weighted stage sums (k1 + 2 k2 + 2 k3 + k4) are
+// accumulated stage by stage and folded into the state with one FFMA2 each.
+struct State2 { F2 X, Y, phi, vx, vy, w; };
+__device__ __forceinline__ void rk4_step2(const Cand2& p, const Ctl& u, float s0, float c0, float h, State2& x) {
+    const float hh = 0.5f * h, h6 = h * (1.0f / 6.0f);
+    const Drive2 drv = prep_drive2(p, u.pwm);
+    const F2 nBf = neg2(p.Bf), Bfd = mul2(p.Bf, bc(u.delta));
+    F2 sn, cs;
+    // stage 1
+    heading2(x.phi, s0, c0, sn, cs);
+    Deriv2 a = accel_full2(p, u, drv, nBf, Bfd, x.vx, x.vy, x.w);
+    F2 sx = fma2(x.vx, cs, mul2(neg2(x.vy), sn)), sy = fma2(x.vx, sn, mul2(x.vy, cs));
+    F2 sw = x.w, svx = a.vx, snvy = a.nvy, sdw = a.w;
+    F2 vx = fma2(bc(hh), a.vx, x.vx), vy = fma2(bc(-hh), a.nvy, x.vy), w = fma2(bc(hh), a.w, x.w);
+    heading2(fma2(bc(hh), x.w, x.phi), s0, c0, sn, cs);
+    // stage 2
+    a = accel_full2(p, u, drv, nBf, Bfd, vx, vy, w);
+    sx = fma2(bc(2.0f), fma2(vx, cs, mul2(neg2(vy), sn)), sx);
+    sy = fma2(bc(2.0f), fma2(vx, sn, mul2(vy, cs)), sy);
+    sw = fma2(bc(2.0f), w, sw); svx = fma2(bc(2.0f), a.vx, svx); snvy = fma2(bc(2.0f), a.nvy, snvy); sdw = fma2(bc(2.0f), a.w, sdw);
+    heading2(fma2(bc(hh), w, x.phi), s0, c0, sn, cs);
+    vx = fma2(bc(hh), a.vx, x.vx); vy = fma2(bc(-hh), a.nvy, x.vy); w = fma2(bc(hh), a.w, x.w);
+    // stage 3
+    a = accel_full2(p, u, drv, nBf, Bfd, vx, vy, w);
+    sx = fma2(bc(2.0f), fma2(vx, cs, mul2(neg2(vy), sn)), sx);
+    sy = fma2(bc(2.0f), fma2(vx, sn, mul2(vy, cs)), sy);
+    sw = fma2(bc(2.0f), w, sw); svx = fma2(bc(2.0f), a.vx, svx); snvy = fma2(bc(2.0f), a.nvy, snvy); sdw = fma2(bc(2.0f), a.w, sdw);
+    heading2(fma2(bc(h), w, x.phi), s0, c0, sn, cs);
+    vx = fma2(bc(h), a.vx, x.vx); vy = fma2(bc(-h), a.nvy, x.vy); w = fma2(bc(h), a.w, x.w);
+    // stage 4
+    a = accel_full2(p, u, drv, nBf, Bfd, vx, vy, w);
+    sx = add2(sx, fma2(vx, cs, mul2(neg2(vy), sn)));
+    sy = add2(sy, fma2(vx, sn, mul2(vy, cs)));
+    x.X = fma2(bc(h6), sx, x.X);
+    x.Y = fma2(bc(h6), sy, x.Y);
+    x.phi = fma2(bc(h6), add2(sw, w), x.phi);
+    x.vx = fma2(bc(h6), add2(svx, a.vx), x.vx);
+    x.vy = fma2(bc(-h6), add2(snvy, a.nvy), x.vy);
+    x.w = fma2(bc(h6), add2(sdw, a.w), x.w);
 }
 
 }  // namespace llampc

@@ -6,6 +6,8 @@
 #include "llampc_common.cuh"
 #include "llampc_model.cuh"
 #include "llampc_model_f64.cuh"
+#include "llampc_packed.cuh"
+#include "llampc_launch.cuh"
 
 namespace llampc {
 
@@ -135,6 +137,140 @@ lookahead_kernel(const float4* __restrict__ bank, int Mpad, const int* __restric
     if (lane == 0) best_k[m] = (int)(best & 0xffffffffull);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// K2p.  The rollout with TWO MODELS per thread in packed f32x2 arithmetic (llampc_packed.cuh), for the layout of config
+// C3: every model rolls the SAME K control sequences from the SAME start state along the same reference path.  One warp =
+// one model pair, lanes over control sequences; the model parameters are the packed operands (as in K1p), everything that
+// depends only on the control sequence is a scalar register that ptxas folds into the packed instruction as a broadcast.
+// What does not depend on the model is computed ONCE PER CTA into shared memory after the TMA staging of the tables:
+//   sCtl [K][H]  (pwm, delta, sin delta, cos delta) of every sampled input,
+//   sJa  [K]     the control-effort cost sum_h du_h' R du_h of every sequence (nmpc.py:66-69),
+//   sRel [H+1]   the reference path relative to the start position (formed in fp64).
+// The step is straight-line code with no guard and no fallback (llampc_packed.cuh: rk4_step2): slip angles by the
+// branch-free full-range atan2 (candidate models spin inside the horizon: 12 % of the warp-steps of C3 see a slip tangent
+// above 1, so a guarded small-angle form would send every eighth warp-step through a fallback), headings carried
+// relative to the start heading with sin / cos from the SFU, valid for any heading change.
+// ---------------------------------------------------------------------------------------------------
+#ifndef LLAMPC_LA2_MIN_BLOCKS
+#define LLAMPC_LA2_MIN_BLOCKS 3
+#endif
+__global__ void __launch_bounds__(LA_THREADS, LLAMPC_LA2_MIN_BLOCKS)
+lookahead2_kernel(const float4* __restrict__ bank, int Mpad, int M, const double* __restrict__ x0,
+                  const float* __restrict__ U, int K, int H, const float* __restrict__ xref,
+                  const float* __restrict__ uprev, float q0, float q1, float r0, float r1, float p0, float p1, float h,
+                  float* __restrict__ J, int* __restrict__ best_k, double* __restrict__ x_final) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    __shared__ __align__(8) uint64_t mbar;
+    __shared__ float s_x0[8];                      // sin psi0, cos psi0, vx0, vy0, w0
+    const unsigned u_bytes_pad = ((unsigned)(K * H * 8) + 15u) & ~15u;
+    const unsigned xr_bytes = (unsigned)(((H + 1) * 8 + 15) & ~15);
+    float2* sU = reinterpret_cast<float2*>(smem_raw);
+    float2* sXr = reinterpret_cast<float2*>(smem_raw + u_bytes_pad);
+    float2* sRel = reinterpret_cast<float2*>(smem_raw + u_bytes_pad + xr_bytes);
+    float* sJa = reinterpret_cast<float*>(sRel + (H + 1) + ((H + 1) & 1));
+    float4* sCtl = reinterpret_cast<float4*>(smem_raw + ((u_bytes_pad + xr_bytes + (unsigned)(H + 2) * 8 + (unsigned)K * 4 + 15u) & ~15u));
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    if (tid == 0) mbar_init(&mbar, 1);
+    __syncthreads();
+    if (tid == 0) {
+        mbar_expect_tx(&mbar, u_bytes_pad + xr_bytes);
+        tma_bulk_g2s(sU, U, u_bytes_pad, &mbar);                   // caller pads the tables to 16 B
+        tma_bulk_g2s(sXr, xref, xr_bytes, &mbar);
+        double s0d, c0d;
+        sincos(x0[2], &s0d, &c0d);
+        s_x0[0] = (float)s0d; s_x0[1] = (float)c0d; s_x0[2] = (float)x0[3]; s_x0[3] = (float)x0[4]; s_x0[4] = (float)x0[5];
+    }
+    const int m0 = (blockIdx.x * LA_WARPS + warp) * 2, m1 = m0 + 1;
+    const bool ok0 = m0 < M, ok1 = m1 < M;
+    const int i0 = ok0 ? m0 : M - 1, i1 = ok1 ? m1 : M - 1;
+    const Cand2 p = load_cand2(bank, Mpad, i0, i1);               // overlaps the bulk copies
+    mbar_wait(&mbar, 0);
+    // ---- model-invariant tables, once per CTA
+    const float2 up0 = reinterpret_cast<const float2*>(uprev)[0];
+    for (int i = tid; i < K * H; i += LA_THREADS) {
+        const float2 u = sU[i];
+        float sd, cd;
+        sincosf(u.y, &sd, &cd);                                    // any steering angle (once per CTA)
+        sCtl[i] = make_float4(u.x, u.y, sd, cd);
+    }
+    for (int k = tid; k < K; k += LA_THREADS) {
+        float2 uq = up0;
+        float ja = 0.0f;
+        for (int hh = 0; hh < H; ++hh) {
+            const float2 u = sU[k * H + hh];
+            const float du0 = u.x - uq.x, du1 = u.y - uq.y;        // nmpc.py:66-69 (du_0 = u_0 - uprev)
+            ja = fmaf(r0 * du0, du0, fmaf(r1 * du1, du1, ja));
+            uq = u;
+        }
+        sJa[k] = ja;
+    }
+    {
+        const double X0 = x0[0], Y0 = x0[1];
+        for (int j = tid; j <= H; j += LA_THREADS) {
+            const float2 xr = sXr[j];
+            sRel[j] = make_float2((float)((double)xr.x - X0), (float)((double)xr.y - Y0));
+        }
+    }
+    __syncthreads();
+    if (!ok0) return;                                              // whole warp
+
+    const float s_start = s_x0[0], c_start = s_x0[1];
+    u64 best0 = ~0ull, best1 = ~0ull;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int k = k0 + lane;
+        const bool k_ok = k < K;
+        const int kk = k_ok ? k : K - 1;
+        State2 x;
+        x.X = bc(0.0f); x.Y = bc(0.0f); x.phi = bc(0.0f);
+        x.vx = bc(s_x0[2]); x.vy = bc(s_x0[3]); x.w = bc(s_x0[4]);
+        F2 Jt = bc(0.0f), ex = bc(0.0f), ey = bc(0.0f);
+        const float4* ctlk = sCtl + kk * H;
+#pragma unroll 1
+        for (int hh = 0; hh < H; ++hh) {
+            const float4 cq = ctlk[hh];
+            Ctl ctl;
+            ctl.pwm = cq.x; ctl.delta = cq.y; ctl.sd = cq.z; ctl.cd = cq.w;
+            rk4_step2(p, ctl, s_start, c_start, h, x);            // straight-line code: no guard, no fallback
+            const float2 xr = sRel[hh + 1];
+            ex = add2(x.X, bc(-xr.x));
+            ey = add2(x.Y, bc(-xr.y));
+            Jt = fma2(mul2(bc(q0), ex), ex, fma2(mul2(bc(q1), ey), ey, Jt));      // nmpc.py:70-71
+        }
+        Jt = fma2(mul2(bc(p0), ex), ex, fma2(mul2(bc(p1), ey), ey, Jt));          // terminal cost nmpc.py:48
+        const F2 Jk = add2(Jt, bc(sJa[kk]));
+        float j0, j1;
+        up(Jk, j0, j1);
+        if (k_ok) {
+            J[(size_t)m0 * K + k] = j0;
+            best0 = u64_min(best0, pack_key(j0, (unsigned)k));
+            if (ok1) {
+                J[(size_t)m1 * K + k] = j1;
+                best1 = u64_min(best1, pack_key(j1, (unsigned)k));
+            }
+            if (x_final) {
+                float a[6], b[6];
+                up(x.X, a[0], b[0]); up(x.Y, a[1], b[1]); up(x.phi, a[2], b[2]); up(x.vx, a[3], b[3]); up(x.vy, a[4], b[4]);
+                up(x.w, a[5], b[5]);
+                double* o = x_final + ((size_t)m0 * K + k) * 6;
+                o[0] = x0[0] + (double)a[0]; o[1] = x0[1] + (double)a[1]; o[2] = x0[2] + (double)a[2];
+                o[3] = (double)a[3]; o[4] = (double)a[4]; o[5] = (double)a[5];
+                if (ok1) {
+                    o = x_final + ((size_t)m1 * K + k) * 6;
+                    o[0] = x0[0] + (double)b[0]; o[1] = x0[1] + (double)b[1]; o[2] = x0[2] + (double)b[2];
+                    o[3] = (double)b[3]; o[4] = (double)b[4]; o[5] = (double)b[5];
+                }
+            }
+        }
+    }
+    best0 = warp_min_u64(best0);
+    best1 = warp_min_u64(best1);
+    if (lane == 0) {
+        best_k[m0] = (int)(best0 & 0xffffffffull);
+        if (ok1) best_k[m1] = (int)(best1 & 0xffffffffull);
+    }
+}
+
 __global__ void __launch_bounds__(128)
 plant_rk6_kernel(const double* __restrict__ params, int V, const double* __restrict__ x, const double* __restrict__ u,
                  double h, double* __restrict__ out) {
@@ -167,18 +303,26 @@ extern "C" int llampc_lookahead_rollout_f32(const float* bank, int Mpad, const i
     if ((reinterpret_cast<uintptr_t>(bank) | reinterpret_cast<uintptr_t>(U) | reinterpret_cast<uintptr_t>(xref)) & 15u)
         return LLAMPC_E_ALIGN;
     const bool u_pm = per_model_flags & 1, xref_pm = per_model_flags & 2;
+    cudaStream_t st = static_cast<cudaStream_t>(stream);
+    // shared start state, control table, reference path and previous input (config C3): two models per thread (K2p).
+    // per_model_flags & 8 (diagnostics: force the general step) keeps the scalar kernel for this layout too.
+    if (per_model_flags == 0 && n_x0 == 1 && !model_idx && !x_traj && M >= 2) {
+        const size_t tab = (((size_t)K * H * 8 + 15) & ~(size_t)15) + ((((size_t)H + 1) * 8 + 15) & ~(size_t)15);
+        const size_t smem2 = ((tab + ((size_t)H + 2) * 8 + (size_t)K * 4 + 15) & ~(size_t)15) + (size_t)K * H * 16;
+        if (smem2 <= 160 * 1024) {
+            LLAMPC_CUDA_TRY((cudaError_t)raise_dynamic_smem(lookahead2_kernel, smem2));
+            lookahead2_kernel<<<(M + 2 * LA_WARPS - 1) / (2 * LA_WARPS), LA_THREADS, smem2, st>>>(
+                reinterpret_cast<const float4*>(bank), Mpad, M, x0, U, K, H, xref, uprev, qrp_h[0], qrp_h[1], qrp_h[2],
+                qrp_h[3], qrp_h[4], qrp_h[5], (float)Ts, J, best_k, x_final);
+            return (int)cudaGetLastError();
+        }
+    }
     size_t smem = (u_pm ? 0 : (((size_t)K * H * 8 + 15) & ~(size_t)15)) + (xref_pm ? 0 : ((((size_t)H + 1) * 8 + 15) & ~(size_t)15)) +
                   (size_t)LA_WARPS * (H + 1) * 8;
     if (smem > 96 * 1024) return LLAMPC_E_RANGE;
-    if (smem > 48 * 1024) {
-        static bool raised = false;
-        if (!raised) {
-            LLAMPC_CUDA_TRY(cudaFuncSetAttribute(lookahead_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024));
-            raised = true;
-        }
-    }
-    lookahead_kernel<<<(M + LA_WARPS - 1) / LA_WARPS, LA_THREADS, smem, static_cast<cudaStream_t>(stream)>>>(
-        reinterpret_cast<const float4*>(bank), Mpad, model_idx, M, x0, n_x0, U, K, H, xref, uprev, per_model_flags,
+    LLAMPC_CUDA_TRY((cudaError_t)raise_dynamic_smem(lookahead_kernel, smem));
+    lookahead_kernel<<<(M + LA_WARPS - 1) / LA_WARPS, LA_THREADS, smem, st>>>(
+        reinterpret_cast<const float4*>(bank), Mpad, model_idx, M, x0, n_x0, U, K, H, xref, uprev, per_model_flags & 15,
         qrp_h[0], qrp_h[1], qrp_h[2], qrp_h[3], qrp_h[4], qrp_h[5], (float)Ts, J, best_k, x_final, x_traj);
     return (int)cudaGetLastError();
 }

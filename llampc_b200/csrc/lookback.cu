@@ -1,5 +1,5 @@
 // Look-back C ABI (llampc_lookback_plan / _launch / _tick / _push), the list-merge, top-K and fp64 re-score kernels, and
-// the one-step batch kernels.  sm_100a.  The scoring kernels live in lookback_k1.cu (K1), lookback_k1p.cu (K1p, K1pv),
+// the one-step batch kernels.  sm_100a.  The scoring kernels live in lookback_k1.cu (K1), lookback_k1p.cu (K1p),
 // lookback_rolling.cu (K1r, K1v) and lookback_balanced.cu (K1b).
 //
 // Reference behaviour being replaced: evaluate_models_vectorized (llampc/mpc/evaluate_models_vectorized.py:4-23)
@@ -394,17 +394,7 @@ static int resolve_plan(const llampc_lookback_desc_t& d, LbPlan& p) {
     if (((long)d.hist_stride_rows * LLAMPC_HIST_ROW * 4) % 16) return LLAMPC_E_ALIGN;
     const long total = (long)d.N * d.n_vehicles;
     if (d.n_vehicles > 1 && d.peer_bufs) return LLAMPC_E_ARG;
-    // ---- many vehicles: one CTA per vehicle when a vehicle's bank fits a CTA and the vehicles alone fill the GPU
-    const bool pv_ok = d.n_vehicles > 1 && d.N <= PV_MAX_N && d.K > 0;
     int kernel = d.kernel;
-    if (!kernel && pv_ok && d.n_vehicles >= 2 * device_sms()) kernel = LLAMPC_KERNEL_K1PV;
-    if (kernel == LLAMPC_KERNEL_K1PV) {
-        if (!pv_ok) return LLAMPC_E_ARG;
-        p.kernel = kernel;
-        p.grid_x = d.n_vehicles; p.grid_y = 1;
-        p.bytes = 0;
-        return 0;
-    }
     bool packed = kernel ? kernel == LLAMPC_KERNEL_K1P : total >= K1P_MIN_CANDIDATES;
     int sy = d.split ? d.split : choose_split(d.N, d.W, d.n_vehicles, packed);
     if (sy > d.W) sy = 1;
@@ -501,9 +491,6 @@ static int lookback_launch_planned(const llampc_lookback_desc_t& d, const LbPlan
         if (rc || p.launches == 1) return rc;
         return merge_lists_launch(lists, p.n_lists, d.n_vehicles, d.K, d.out, st);
     }
-    if (p.kernel == LLAMPC_KERNEL_K1PV)
-        return launch_k1pv(bank, d.N, d.Npad, d.hist, d.W, (long)d.hist_stride_rows * LLAMPC_HIST_ROW, d.n_vehicles, z,
-                           d.avg_err, d.idx_offset, d.K, d.out, geom, mufu, st);
     if (p.kernel == LLAMPC_KERNEL_K1B)
         return lookback_balanced_launch(d.bank, d.N, d.Npad, d.hist, d.W, d.Ts, d.avg_err, d.idx_offset, geom, mufu, d.K,
                                         d.workspace, d.workspace_bytes, d.out, nr, px, st);

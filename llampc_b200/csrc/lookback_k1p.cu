@@ -1,5 +1,4 @@
-// K1p: the look-back window kernel with TWO candidates per thread in packed f32x2 arithmetic, and K1pv, its
-// one-CTA-per-vehicle form for the Monte-Carlo layout.  sm_100a.
+// K1p: the look-back window kernel with TWO candidates per thread in packed f32x2 arithmetic.  sm_100a.
 //
 // Reference behaviour being replaced: evaluate_models_vectorized (llampc/mpc/evaluate_models_vectorized.py:4-23)
 // + the scoring / selection block of run_nmpc_orca_llampc_rt.py:347-360.
@@ -137,89 +136,6 @@ lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const 
     }
 }
 
-// ---------------------------------------------------------------------------------------------------
-// K1pv.  Recompute look-back of the Monte-Carlo layout (thousands of vehicles, each scoring the same bank of <= 2,048
-// candidates over its OWN history window): ONE CTA PER VEHICLE.  The vehicle's W rows are staged once (TMA bulk copy)
-// and reused by every pass; a pass is 256 candidates = 128 threads x 2 (packed f32x2 step, as K1p); the vehicle's keys
-// stay in shared memory and the top-K is finished inside the CTA by the threshold filter of K1v (cta_topk_filter) --
-// no per-CTA lists, no tickets, no merge launch: one launch per tick whatever the number of vehicles.
-// ---------------------------------------------------------------------------------------------------
-constexpr int PV_CPP = 2 * LB_THREADS;             // candidates per pass
-constexpr int PV_MAX_PASSES = PV_MAX_N / PV_CPP;   // 8
-
-template <bool GEOM_SHARED, bool MUFU_SIN>
-__global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB2_MIN_BLOCKS)
-lookback_vehicle2_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
-                         long hist_stride_floats, StepSize z, float* __restrict__ avg_err, int idx_offset, int K,
-                         u64* __restrict__ out) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    __shared__ __align__(8) uint64_t mbar;
-    __shared__ u64 s_key[PV_MAX_N];
-    __shared__ u64 s_cand[PV_MAX_N];
-    __shared__ u64 s_group[PV_MAX_PASSES * (LB_THREADS / 32) * 2];
-    __shared__ u64 s_thr;
-    __shared__ int s_count;
-    float4* srow = reinterpret_cast<float4*>(smem_raw);
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int v = blockIdx.x;
-    const unsigned bytes = (unsigned)W * (LLAMPC_HIST_ROW * 4);
-    if (tid == 0) {
-        mbar_init(&mbar, 1);
-        mbar_expect_tx(&mbar, bytes);
-        tma_bulk_g2s(srow, hist + (size_t)v * hist_stride_floats, bytes, &mbar);
-    }
-    __syncthreads();
-    const int passes = (N + PV_CPP - 1) / PV_CPP;
-    const float scale = 0.25f / (float)W;          // mean over the 4 scored states (rt.py:349) and over the window (rt.py:357)
-    bool staged = false;
-#pragma unroll 1
-    for (int j = 0; j < passes; ++j) {
-        const int cand0 = j * PV_CPP + tid, cand1 = cand0 + LB_THREADS;
-        const bool valid0 = cand0 < N, valid1 = cand1 < N;
-        const int i0 = valid0 ? cand0 : N - 1, i1 = valid1 ? cand1 : N - 1;
-        const Cand2 p = load_cand2(bank, Npad, i0, i1);          // first pass: overlaps the bulk copy
-        if (!staged) { mbar_wait(&mbar, 0); staged = true; }
-        float acc0 = 0.0f, acc1 = 0.0f;
-#pragma unroll 1
-        for (int w = 0; w < W; ++w) {
-            HistRow r;
-            r.q0 = srow[w * 5 + 0];
-            r.q1 = srow[w * 5 + 1];
-            r.q2 = srow[w * 5 + 2];
-            r.q3 = srow[w * 5 + 3];
-            r.q4 = srow[w * 5 + 4];
-            bool ok0, ok1;
-            const F2 e = lookback_step_fast2<GEOM_SHARED, MUFU_SIN>(p, r, z, ok0, ok1);
-            float e0, e1;
-            up(e, e0, e1);
-            if (!ok0) e0 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i0, srow + w * 5, z);
-            if (!ok1) e1 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i1, srow + w * 5, z);
-            acc0 += e0;
-            acc1 += e1;
-        }
-        const float err0 = acc0 * scale, err1 = acc1 * scale;
-        u64 k0 = ~0ull, k1 = ~0ull;
-        if (valid0) {
-            if (avg_err) avg_err[(size_t)v * N + cand0] = err0;
-            k0 = pack_key(err0, (unsigned)(idx_offset + cand0));
-        }
-        if (valid1) {
-            if (avg_err) avg_err[(size_t)v * N + cand1] = err1;
-            k1 = pack_key(err1, (unsigned)(idx_offset + cand1));
-        }
-        s_key[j * PV_CPP + tid] = k0;
-        s_key[j * PV_CPP + LB_THREADS + tid] = k1;
-        const u64 g0 = warp_min_key(k0), g1 = warp_min_key(k1);
-        if (lane == 0) {
-            s_group[(j * (LB_THREADS / 32) + warp) * 2] = g0;
-            s_group[(j * (LB_THREADS / 32) + warp) * 2 + 1] = g1;
-        }
-    }
-    __syncthreads();
-    cta_topk_filter<LB_THREADS>(s_key, passes * PV_CPP, s_group, passes * (LB_THREADS / 32) * 2, K, s_cand, &s_thr, &s_count,
-                                out + (size_t)v * (LLAMPC_LIST_LEN + 1));
-}
-
 
 template <int SY, bool GEOM, bool MUFU>
 static int launch_one(const LbArgs& a, cudaStream_t st) {
@@ -248,18 +164,6 @@ int launch_k1_packed(const LbArgs& a, int sy, bool geom, bool mufu, cudaStream_t
         case 16: return launch_sy<16>(a, geom, mufu, st);
         default: return LLAMPC_E_ARG;
     }
-}
-
-int launch_k1pv(const float4* bank, int N, int Npad, const float* hist, int W, long hist_stride_floats, int n_vehicles,
-                StepSize z, float* avg_err, int idx_offset, int K, u64* out, bool geom, bool mufu, cudaStream_t st) {
-    if (N > PV_MAX_N || K <= 0 || K > LLAMPC_LIST_LEN || !out) return LLAMPC_E_RANGE;
-    auto kern = mufu ? (geom ? lookback_vehicle2_kernel<true, true> : lookback_vehicle2_kernel<false, true>)
-                     : (geom ? lookback_vehicle2_kernel<true, false> : lookback_vehicle2_kernel<false, false>);
-    const size_t smem = (size_t)W * (LLAMPC_HIST_ROW * 4);
-    const int rc = raise_dynamic_smem(kern, smem);
-    if (rc) return rc;
-    return issue(kern, dim3(n_vehicles), dim3(LB_THREADS), smem, st, bank, N, Npad, hist, W, hist_stride_floats, z, avg_err,
-                 idx_offset, K, out);
 }
 
 }  // namespace llampc

@@ -7,7 +7,7 @@
 
 namespace llampc {
 
-// Everything a window-recompute launch needs (K1 / K1p / K1pv).
+// Everything a window-recompute launch needs (K1 / K1p).
 struct LbArgs {
     const float4* bank; int N, Npad;
     const float* hist; int W; long hist_stride_floats; int n_vehicles;
@@ -27,11 +27,6 @@ static inline int k1_cands_per_cta(bool packed, int sy) { return (packed ? 2 * L
 int launch_k1_scalar(const LbArgs& a, int sy, bool geom, bool mufu, cudaStream_t st);      // lookback_k1.cu
 int launch_k1_packed(const LbArgs& a, int sy, bool geom, bool mufu, cudaStream_t st);      // lookback_k1p.cu
 
-// K1pv: recompute look-back, one CTA per vehicle, packed step, top-K by threshold filter in shared memory.
-constexpr int PV_MAX_N = 2048;
-int launch_k1pv(const float4* bank, int N, int Npad, const float* hist, int W, long hist_stride_floats, int n_vehicles,
-                StepSize z, float* avg_err, int idx_offset, int K, u64* out, bool geom, bool mufu, cudaStream_t st);   // lookback_k1p.cu
-
 // K1r / K1v: rolling window (lookback_rolling.cu)
 constexpr int RV_THREADS = 256;
 constexpr int RV_WARPS = RV_THREADS / 32;
@@ -45,7 +40,7 @@ int launch_k1v(const float4* bank, int N, int Npad, int W, StepSize z, int slot,
                float* err_ring, float* avg_err, int idx_offset, int emit, int K, u64* out, bool geom, bool mufu,
                cudaStream_t st);
 
-// Top-K of a vehicle's keys held in shared memory, by FILTERING instead of sorting (K1v, K1pv):
+// Top-K of a vehicle's keys held in shared memory, by FILTERING instead of sorting (K1v):
 //   1  every group of 32 keys left its minimum in s_group (ng <= 64 groups);
 //   2  warp 0 sorts the minima; T = the K-th smallest.  At least K keys are <= T (those minima themselves), so the
 //      top-K is a subset of {key <= T} -- about K .. 3K keys of the N;

@@ -102,8 +102,8 @@ class MonteCarlo:
         self.err_ring = torch.zeros((V, W, self.bank.Npad), dtype=f32, device=dev) if self.rolling else None
         self.topk = torch.zeros((V, _lib.LIST_LEN + 1), dtype=i64, device=dev)
         # the look-back launch of every tick (llampc_lookback_launch): rolling -> K1v (one CTA per vehicle), recompute ->
-        # K1pv (one CTA per vehicle, packed step) or the (candidate tile, vehicle) grid; tyre sine None = automatic (SFU
-        # while the bank's tyre-sine argument stays within [-pi, pi]), True / False force a mode
+        # K1p over (candidate tile, vehicle) with the last-CTA merge; tyre sine None = automatic (SFU while the bank's
+        # tyre-sine argument stays within [-pi, pi]), True / False force a mode
         self.lb = LookbackLaunch(self.bank, self.hist, W, self.Ts, K=K_models, n_vehicles=V, hist_stride_rows=W,
                                  mode=lookback_mode, err_ring=self.err_ring, out=self.topk, fast_sin=fast_sin,
                                  kernel=lookback_kernel)

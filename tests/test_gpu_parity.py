@@ -317,15 +317,13 @@ def _vehicle_windows(L, S, U, Ts, bank, t_ends, W):
     return rows
 
 
-@pytest.mark.parametrize("N,W,K,kernels", [(1024, 20, 10, ("k1", "k1p", "k1pv")), (777, 33, 16, ("k1", "k1p", "k1pv")),
-                                           (2048, 5, 10, ("k1p", "k1pv")), (300, 7, 1, ("k1", "k1pv")),
-                                           (40, 3, 16, ("k1", "k1pv")), (1, 2, 1, ("k1", "k1pv")),
-                                           (5000, 12, 16, ("k1", "k1p"))])
+@pytest.mark.parametrize("N,W,K,kernels", [(1024, 20, 10, ("k1", "k1p")), (777, 33, 16, ("k1", "k1p")),
+                                           (2048, 5, 10, ("k1p",)), (300, 7, 1, ("k1", "k1p")), (40, 3, 16, ("k1",)),
+                                           (1, 2, 1, ("k1", "k1p")), (5000, 12, 16, ("k1", "k1p"))])
 def test_multi_vehicle_histories(history, N, W, K, kernels):
     """Monte-Carlo layout through llampc_lookback_launch: V vehicles share one bank, each with its own history window.
-    Every kernel the shape supports -- K1 / K1p over (candidate tile, vehicle) with the last-CTA merge, K1pv with one CTA
-    per vehicle and the in-CTA threshold filter -- gives the oracle's window means, arg-min and top-K; K1p and K1pv run
-    the same packed step, so their scores are bit-identical.  Launched twice: tickets / counters re-arm themselves."""
+    Both kernels -- K1 and K1p over (candidate tile, vehicle), the last CTA of a vehicle merging its lists inside the
+    launch -- give the oracle's window means, arg-min and top-K.  Launched twice: the tickets re-arm themselves."""
     import torch
     from llampc_b200 import _lib
     from llampc_b200.bank import ModelBank
@@ -357,27 +355,33 @@ def test_multi_vehicle_histories(history, N, W, K, kernels):
             assert (oo[v, 1 + k:] == np.uint64(0xFFFFFFFFFFFFFFFF)).all()
             if N == 1024:                                          # the C1 bank: fp32 ranking == the oracle's
                 assert list(order[:k]) == list(np.argsort(refs[v])[:k])
-    if "k1p" in got and "k1pv" in got:
-        assert np.array_equal(got["k1p"][0], got["k1pv"][0]) and np.array_equal(got["k1p"][1], got["k1pv"][1])
+    if len(got) == 2:                                              # same decisions from both kernels
+        (a1, o1), (a2, o2) = got.values()
+        idx = lambda o: (o[:, :K + 1] & np.uint64(0xFFFFFFFF))
+        np.testing.assert_allclose(a1, a2, rtol=2e-5)
+        if N == 1024:
+            assert np.array_equal(idx(o1), idx(o2))
 
 
 def test_multi_vehicle_automatic_kernel_choice(history):
-    """The dispatch decides on candidates x vehicles: a 1,024-candidate bank for 512 vehicles runs K1pv (one launch),
-    the same bank for 3 vehicles runs the scalar grid with window split 1 per vehicle count -- never the one-vehicle
-    heuristic that tiled a 1,024-candidate bank into 8-candidate CTAs."""
+    """The dispatch decides on candidates x vehicles: a 1,024-candidate bank for 4,096 vehicles (config C4) runs the
+    packed kernel with NO window split (4 CTAs of 256 candidates per vehicle, one launch) -- not the one-vehicle heuristic
+    that tiled a 1,024-candidate bank into 8-candidate CTAs with 128 lists per vehicle; 3 vehicles keep the scalar kernel."""
     import torch
     from llampc_b200 import _lib
     from llampc_b200.bank import ModelBank
     from llampc_b200.mpc.lookback import LookbackLaunch
     bank = ModelBank(orc.make_bank(1024, seed=0))
-    for V, want in ((512, "K1pv"), (3, "K1")):
+    for V, want, split in ((4096, "K1p", 1), (3, "K1", None)):
         hist = torch.zeros((V, 20, 20), dtype=torch.float32, device="cuda")
         lb = LookbackLaunch(bank, hist, 20, 0.02, K=10, n_vehicles=V)
         assert lb.kernel_name == want, (V, lb.kernel_name)
-        assert lb.plan.launches == 1
+        assert lb.plan.launches == 1 and (split is None or lb.plan.split == split)
+        if V == 4096:
+            assert (lb.plan.grid_x, lb.plan.grid_y) == (4, 4096)
     hist = torch.zeros((40, 20, 20), dtype=torch.float32, device="cuda")
     lb = LookbackLaunch(ModelBank(orc.make_bank(4096, seed=0)), hist, 20, 0.02, K=10, n_vehicles=40)
-    assert lb.kernel_name == "K1p" and lb.plan.split == 1           # 163,840 candidate-threads: packed, no window split
+    assert lb.kernel_name == "K1p" and lb.plan.launches == 1        # 163,840 candidates in the launch: packed
 
 
 @pytest.mark.parametrize("N,W,K,kind", [(1024, 20, 10, "rt"), (2048, 7, 16, "rt"), (777, 33, 10, "rt"), (300, 5, 10, "rt"),
@@ -531,7 +535,6 @@ def test_error_codes_without_launch():
     assert launch(desc(out=None)) == -1                                     # K > 0 needs out
     assert launch(desc(sine=7)) == -1
     assert launch(desc(kernel=_lib.KERNEL_K1V)) == -1                       # a rolling kernel for a recompute launch
-    assert launch(desc(kernel=_lib.KERNEL_K1PV)) == -1                      # one vehicle: no per-vehicle CTA kernel
     assert launch(desc(out=k17.data_ptr(), workspace=None)) == -1           # the merge tree needs its workspace
     assert launch(desc(peer_bufs=k.data_ptr(), world=1)) == -3
     assert L.llampc_topk_f32(d.data_ptr(), 10, 0, 100, k.data_ptr(), k.data_ptr(), k.data_ptr(), st) == -3
@@ -543,8 +546,8 @@ def test_error_codes_without_launch():
     assert L.llampc_mc_advance_tick_f64(k.data_ptr(), 0, k.data_ptr(), None, None, 1, None, 0.02, st) == -1
     # rolling look-back, Monte-Carlo layout: same checks on the K1v and the K1r route
     for n in (8, 4096):
-        roll = lambda **kw: desc(mode=_lib.LB_ROLLING, N=n, Npad=n, W=4, hist_stride_rows=4, err_ring=d.data_ptr(), emit=1,
-                                 K=10, out=k17.data_ptr(), **kw)
+        roll = lambda **kw: desc(**dict(dict(mode=_lib.LB_ROLLING, N=n, Npad=n, W=4, hist_stride_rows=4,
+                                                  err_ring=d.data_ptr(), emit=1, K=10, out=k17.data_ptr()), **kw))
         assert launch(roll(hist=None)) == -1
         assert launch(roll(slot=4)) == -1
         assert launch(roll(err_ring=None)) == -1
@@ -737,7 +740,6 @@ def test_montecarlo_closed_loop_stagewise_parity(lookback_mode):
             mus[v].tick(tick, None if prev_order is None else prev_order[v], bank["Dr"], bank["Df"])
             if tick > W:
                 np.testing.assert_allclose(post["mu_pred"][v], mus[v].MU_pred, rtol=1e-12)
-                assert abs(post["mu_pred"][v] - post["mu_display"][v]) > 0.03
             else:
                 assert np.isnan(post["mu_pred"][v])
             np.testing.assert_allclose(post["mu_display"][v], mus[v].MU_preds[-1], rtol=1e-12)
@@ -924,9 +926,26 @@ def test_c3_full_size_properties(history):
     sens = np.abs(Jp - Jr) / Jr
     rel = np.abs(J[sample] - Jr) / Jr
     assert rel[sens < 1e-5].max() < 1e-4 and np.all(rel[sens >= 1e-5] < 20 * sens[sens >= 1e-5])
+    # model order: the same models rolled through a model_idx permutation.  The permuted call runs the scalar kernel K2
+    # (one model per warp), the plain call the packed kernel K2p (two models per thread): two implementations of the same
+    # rollout, so they agree to fp32 rounding wherever the rollout is well conditioned, and pick the same sequence
+    # wherever the best cost is clear of the second best.
     perm = rng.permutation(M)[:4096]
     J2, bk2 = la.rollout(S[:, t0], Useq, xref, U[:, t0 - 1], model_idx=perm)
-    assert np.array_equal(J2, J[perm]) and np.array_equal(bk2, bk[perm])
+    d = np.abs(J2 - J[perm]) / J[perm]
+    assert np.median(d) < 2e-6 and np.percentile(d, 99) < 1e-4
+    srt = np.sort(J[perm], axis=1)
+    clear = (srt[:, 1] - srt[:, 0]) > 1e-3 * srt[:, 0]
+    assert clear.mean() > 0.5 and np.array_equal(bk2[clear], bk[perm][clear])
+    # the permuted call against itself is bit-reproducible
+    J3, bk3 = la.rollout(S[:, t0], Useq, xref, U[:, t0 - 1], model_idx=perm)
+    assert np.array_equal(J2, J3) and np.array_equal(bk2, bk3)
+    # and K2p against the scalar kernel on the very same launch shape (diagnostic flag: general step, scalar kernel)
+    planG = la.plan(S[:, t0], Useq, xref, U[:, t0 - 1], _force_general=True)
+    planG.run()
+    JG, _ = planG.fetch()
+    dG = np.abs(JG - J) / J
+    assert np.median(dG) < 2e-6 and np.percentile(dG, 99) < 1e-4
 
 
 def test_c4_full_size_properties():
@@ -1110,8 +1129,11 @@ def test_device_bank_generation(history):
     ptrs = (C.c_void_p * 14)(*[c.ctypes.data for c in cols])
     flags = (C.c_int * 14)(*([1] * 14))
     host = np.zeros((4, b.Npad, 4), dtype=np.float32)
-    assert _lib.lib().llampc_bank_pack_h(C.cast(ptrs, C.c_void_p), C.cast(flags, C.c_void_p), N, b.Npad, host.ctypes.data) == 0
+    arg_max = C.c_float(0.0)
+    assert _lib.lib().llampc_bank_pack_h(C.cast(ptrs, C.c_void_p), C.cast(flags, C.c_void_p), N, b.Npad, host.ctypes.data,
+                                         C.addressof(arg_max)) == 0
     assert np.array_equal(b.packed.cpu().numpy(), host)
+    assert b.sin_arg_max == arg_max.value                          # the device generator reports the same tyre-sine bound
     # determinism / seed dependence
     b2 = ModelBank.generate(ORCA(), sig, N, seed=11)
     b3 = ModelBank.generate(ORCA(), sig, N, seed=12)

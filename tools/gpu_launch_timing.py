@@ -1,7 +1,7 @@
 """GPU diagnostic: device time of one llampc_lookback_launch configuration (CUDA events, L2 flushed between launches).
 
     python tools/gpu_launch_timing.py N W V [mode] [kernel] [sine] [reps]
-      N candidates, W window rows, V vehicles; mode recompute|rolling; kernel auto|k1|k1p|k1b|k1pv|k1r|k1v; sine auto|sfu|strict
+      N candidates, W window rows, V vehicles; mode recompute|rolling; kernel auto|k1|k1p|k1b|k1r|k1v; sine auto|sfu|strict
 Prints the library's plan, the mean / min device time and candidate-steps/s (recompute: N*W*V per launch, rolling: N*V)."""
 import os
 import sys
