@@ -293,20 +293,29 @@ int llampc_lookahead_rollout_f32(const float* bank, int Mpad, const int* model_i
                                  double* x_traj, llampc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
- * Planner: ConstantSpeed (llampc/mpc/planner.py:12-67) for V vehicles, fp64.  Tables (device, doubles) come from
- * a raceline (Track._load_raceline, llampc/tracks/track.py:52-83):
- *   s    [n]      cumulative arc length of the raceline points (Spline2D.s)
- *   xy   [n][2]   raceline points
- *   coef [n-1][4*(2+n_mu)]  per segment: a b c d of x(s), of y(s), then of each speed profile v_j(s)
- *   mus  [n_mu]   friction level of each speed profile (ascending)
+ * Planner: ConstantSpeed (llampc/mpc/planner.py:12-67) for V vehicles, fp64.  Tables (device, doubles, 16-byte aligned)
+ * come from a raceline (Track._load_raceline, llampc/tracks/track.py:52-83):
+ *   s        [n]  cumulative arc length of the raceline points (Spline2D.s)
+ *   xy       [n][2]   raceline points
+ *   coef_xy  [n-1][8]            per segment: a b c d of x(s), then a b c d of y(s)
+ *   coef_vp  [n_mu][n-1][8]      per speed-profile PAIR j and segment: a b c d of v_{(j-1) mod n_mu}(s), then of v_j(s)
+ *                                (the two profiles the friction interpolation of planner.py:49-62 blends for
+ *                                mus[j-1] <= mu <= mus[j]; j-1 wraps like Python's spline_v[i-1] for j = 0)
+ *   mus      [n_mu]   friction level of each speed profile (ascending)
+ * PADDING: each vehicle's window of the tables is copied into shared memory by fixed-size bulk copies, so the
+ * allocations must be readable past their last used element: s  n + LLAMPC_PLAN_SPAD doubles,  coef_xy
+ * (n - 1 + LLAMPC_PLAN_WSEG) rows,  coef_vp  n_mu planes of (n - 1 + LLAMPC_PLAN_WSEG) rows each (the plane stride
+ * INCLUDES the padding).  The padding values are never used.
  * states [V][6] (x, y and vx are used), projidx_in [V], curr_mu [V] (or one value if mu_shared).
  * Outputs (any may be NULL): xref32 [V][N+1][2] floats (feeds llampc_lookahead_rollout_f32 with
  * per_model_flags & 2), xref64 [V][N+1][2] doubles, projidx_out [V], vr_out [V].
  * ------------------------------------------------------------------------------------------- */
-int llampc_planner_constant_speed_f64(const double* s, const double* xy, const double* coef, const double* mus,
-                                      int n, int n_mu, const double* states, int V, const int* projidx_in,
-                                      const double* curr_mu, int mu_shared, int N, double Ts, double scale,
-                                      float* xref32, double* xref64, int* projidx_out, double* vr_out,
+#define LLAMPC_PLAN_WSEG 48   /* table segments staged per vehicle (a march leaving them re-stages the window) */
+#define LLAMPC_PLAN_SPAD 66   /* arc-length marks staged per vehicle = padding of the s allocation (WSEG + 18)     */
+int llampc_planner_constant_speed_f64(const double* s, const double* xy, const double* coef_xy, const double* coef_vp,
+                                      const double* mus, int n, int n_mu, const double* states, int V,
+                                      const int* projidx_in, const double* curr_mu, int mu_shared, int N, double Ts,
+                                      double scale, float* xref32, double* xref64, int* projidx_out, double* vr_out,
                                       llampc_stream_t stream);
 
 /* K3  plant step for V independent vehicles: Model._integrate -> odeintRK6 (llampc/models/model.py:18-30,

@@ -16,6 +16,8 @@ MAX_W = 1024
 MAX_K = 64
 LIST_LEN = 16
 MAX_H = 256
+PLAN_WSEG = 48
+PLAN_SPAD = 66
 PARAM_NAMES = ("lf", "lr", "mass", "Iz", "Bf", "Br", "Cf", "Cr", "Df", "Dr", "Cm1", "Cm2", "Cr0", "Cr2")
 
 _vp, _i, _f, _d = C.c_void_p, C.c_int, C.c_float, C.c_double
@@ -86,7 +88,7 @@ PROTOTYPES = {
     "llampc_forces_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "llampc_lookahead_rollout_f32": (_i, [_vp, _i, _vp, _i, _vp, _i, _vp, _i, _i, _vp, _vp, _i, _vp, _d,
                                           _vp, _vp, _vp, _vp, _vp]),
-    "llampc_planner_constant_speed_f64": (_i, [_vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _i, _d, _d,
+    "llampc_planner_constant_speed_f64": (_i, [_vp, _vp, _vp, _vp, _vp, _i, _i, _vp, _i, _vp, _vp, _i, _i, _d, _d,
                                                _vp, _vp, _vp, _vp, _vp]),
     "llampc_pack_rows_f64": (_i, [_vp, _vp, _vp, _i, _d, _d, _d, _i, _i, _vp, _vp, _vp]),
     "llampc_mu_estimate_f64": (_i, [_vp, _i, _i, _i, _vp, _i, _i, _i, _d, _d, _d, _vp, _vp, _vp, _vp]),

@@ -154,9 +154,9 @@ class MonteCarlo:
         """Steps 1-2 for tick `idt`: reference path + sampled control sequences (reads x, projidx, mu_pred, nominal).  The
         planner gets MU_pred and scale = v_factor only when idt > W + 1, its defaults (1, 1) before (rt.py:278-282)."""
         L, V, chk = self.L, self.V, _lib.check
-        dev, s, xy, coef, mus = self.table.device_tables()
+        dev, s, xy, cxy, cvp, mus = self.table.device_tables()
         fed = idt > self.W + 1
-        chk(L.llampc_planner_constant_speed_f64(s.data_ptr(), xy.data_ptr(), coef.data_ptr(), mus.data_ptr(), self.table.n,
+        chk(L.llampc_planner_constant_speed_f64(s.data_ptr(), xy.data_ptr(), cxy.data_ptr(), cvp.data_ptr(), mus.data_ptr(), self.table.n,
                                                 self.table.n_mu, self.x.data_ptr(), V, self.projidx.data_ptr(),
                                                 (self.mu_pred if fed else self.mu_default).data_ptr(), 0, self.H, self.Ts,
                                                 self.scale if fed else 1.0,

@@ -2,7 +2,7 @@
 
 Host-side, one-off: the same data the reference builds in Track._load_raceline (llampc/tracks/track.py:52-83) --
 a natural cubic spline x(s), y(s) over the raceline points (Spline2D, llampc/utils/pycubicspline.py:135-162) and
-one speed spline v_j(s) per friction level mu_j -- flattened into the coefficient table the planner kernel reads.
+one speed spline v_j(s) per friction level mu_j -- flattened into the coefficient tables the planner kernel stages in shared memory.
 The spline system is solved with the O(n) Thomas algorithm instead of the reference's dense np.linalg.solve
 (identical up to rounding, ~1e-15).
 """
@@ -76,19 +76,36 @@ class RacelineTable:
                 pass
         return cached
 
+    def planner_tables(self):
+        """Host arrays in the layout llampc_planner_constant_speed_f64 wants (include/llampc_b200.h): s, coef_xy
+        [n-1][8] and coef_vp [n_mu][n-1][8] (pair j = profiles (j-1) mod n_mu and j), each padded by the window the
+        kernel's bulk copies may read past the end (zeros, never used)."""
+        n, n_mu, pad = self.n, self.n_mu, _lib.PLAN_WSEG
+        s_pad = np.zeros(n + _lib.PLAN_SPAD)
+        s_pad[:n] = self.s
+        cxy = np.zeros((n - 1 + pad, 8))
+        cxy[:n - 1] = self.coef[:, :8]
+        cvp = np.zeros((n_mu, n - 1 + pad, 8))
+        for j in range(n_mu):
+            lo = (j - 1) % n_mu
+            cvp[j, :n - 1, :4] = self.coef[:, 8 + 4 * lo:12 + 4 * lo]
+            cvp[j, :n - 1, 4:] = self.coef[:, 8 + 4 * j:12 + 4 * j]
+        return s_pad, cxy, cvp
+
     def device_tables(self):
         if self._dev is None:
             torch = _lib.require_cuda()
             dev = torch.device("cuda", torch.cuda.current_device()) if self._device is None else torch.device(self._device)
             t = lambda a: torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64)).to(dev)
-            self._dev = (dev, t(self.s), t(self.raceline.T), t(self.coef), t(self.mus))
+            s_pad, cxy, cvp = self.planner_tables()
+            self._dev = (dev, t(s_pad), t(self.raceline.T), t(cxy), t(cvp), t(self.mus))
         return self._dev
 
     def plan(self, states, projidx, curr_mu, N, Ts, scale=1.0, want_f64=True):
         """ConstantSpeed for V vehicles: states (V,6), projidx (V,), curr_mu (V,) or scalar.
         Returns xref (V,2,N+1) float64, projidx_out (V,), vr (V,)."""
         torch = _lib.require_cuda()
-        dev, s, xy, coef, mus = self.device_tables()
+        dev, s, xy, cxy, cvp, mus = self.device_tables()
         states = np.ascontiguousarray(np.atleast_2d(states), dtype=np.float64)
         V = states.shape[0]
         pid = torch.from_numpy(np.ascontiguousarray(np.broadcast_to(projidx, (V,)), dtype=np.int32)).to(dev)
@@ -101,7 +118,7 @@ class RacelineTable:
         vr = torch.empty(V, dtype=torch.float64, device=dev)
         with torch.cuda.device(dev):
             rc = _lib.lib().llampc_planner_constant_speed_f64(
-                s.data_ptr(), xy.data_ptr(), coef.data_ptr(), mus.data_ptr(), self.n, self.n_mu, st.data_ptr(), V,
+                s.data_ptr(), xy.data_ptr(), cxy.data_ptr(), cvp.data_ptr(), mus.data_ptr(), self.n, self.n_mu, st.data_ptr(), V,
                 pid.data_ptr(), mud.data_ptr(), mu_shared, int(N), float(Ts), float(scale), None, xref.data_ptr(),
                 pout.data_ptr(), vr.data_ptr(), _lib.stream_ptr(torch))
         _lib.check(rc, "llampc_planner_constant_speed_f64")

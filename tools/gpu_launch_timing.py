@@ -1,6 +1,6 @@
 """GPU diagnostic: device time of one llampc_lookback_launch configuration (CUDA events, L2 flushed between launches).
 
-    python tools/gpu_launch_timing.py N W V [mode] [kernel] [sine] [reps]
+    python tools/gpu_launch_timing.py N W V [mode] [kernel] [sine] [reps] [split]
       N candidates, W window rows, V vehicles; mode recompute|rolling; kernel auto|k1|k1p|k1b|k1r|k1v; sine auto|sfu|strict
 Prints the library's plan, the mean / min device time and candidate-steps/s (recompute: N*W*V per launch, rolling: N*V)."""
 import os
@@ -21,6 +21,7 @@ mode = sys.argv[4] if len(sys.argv) > 4 else "recompute"
 kernel = sys.argv[5] if len(sys.argv) > 5 else "auto"
 sine = sys.argv[6] if len(sys.argv) > 6 else "auto"
 reps = int(sys.argv[7]) if len(sys.argv) > 7 else 30
+split = int(sys.argv[8]) if len(sys.argv) > 8 else 0
 g = np.load(os.path.join(ROOT, "tests", "golden", "ethz_history.npz"))
 S, U, Ts = g["states"], g["inputs"], float(g["Ts"])
 L = _lib.lib()
@@ -35,7 +36,7 @@ for j in range(W):
 rows[:] = one[None]
 hist = torch.from_numpy(rows).cuda()
 ring = torch.zeros((V, W, bank.Npad), dtype=torch.float32, device="cuda") if mode == "rolling" else None
-lb = LookbackLaunch(bank, hist, W, Ts, K=10, n_vehicles=V, mode=mode, err_ring=ring, kernel=kernel,
+lb = LookbackLaunch(bank, hist, W, Ts, K=10, n_vehicles=V, mode=mode, err_ring=ring, kernel=kernel, split=split,
                     fast_sin={"auto": None, "sfu": True, "strict": False}[sine])
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
 for i in range(W if mode == "rolling" else 3):
