@@ -16,6 +16,24 @@ namespace llampc {
 #ifndef LLAMPC_LB2_MIN_BLOCKS
 #define LLAMPC_LB2_MIN_BLOCKS 4
 #endif
+// Optional per-CTA timeline (experiments only: `make -C llampc_b200/csrc trace`, tools/gpu_k1p_trace.py): global timer at
+// CTA entry, after the history staging, after the RK4 rows, after the CTA-level selection and at the exit of warp 0, + SM id.
+#ifdef LLAMPC_K1P_TRACE
+constexpr int K1P_TRACE_CTAS = 8192;
+__device__ unsigned long long g_k1p_trace[K1P_TRACE_CTAS * 6];
+__device__ __forceinline__ unsigned long long k1p_gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#define K1P_TRACE(slot)                                                                                   \
+    do {                                                                                                  \
+        if (threadIdx.x == 0 && blockIdx.y == 0 && blockIdx.x < K1P_TRACE_CTAS)                           \
+            g_k1p_trace[blockIdx.x * 6 + (slot)] = k1p_gtimer();                                          \
+    } while (0)
+#else
+#define K1P_TRACE(slot) do { } while (0)
+#endif
 template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
 __global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB2_MIN_BLOCKS)
 lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
@@ -31,6 +49,14 @@ lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const 
     const int tid = threadIdx.x;
     const int v = blockIdx.y;
     const unsigned bytes = (unsigned)W * (LLAMPC_HIST_ROW * 4);
+    K1P_TRACE(0);
+#ifdef LLAMPC_K1P_TRACE
+    if (tid == 0 && blockIdx.y == 0 && blockIdx.x < K1P_TRACE_CTAS) {
+        unsigned smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        g_k1p_trace[blockIdx.x * 6 + 5] = smid;
+    }
+#endif
 
     if (tid == 0) {
         mbar_init(&mbar, 1);
@@ -46,6 +72,7 @@ lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const 
     const Cand2 p = load_cand2(bank, Npad, i0, i1);              // overlaps the bulk copy
 
     mbar_wait(&mbar, 0);
+    K1P_TRACE(1);
     if (nr.slot >= 0) {                            // uniform over the grid
         if (tid < LLAMPC_HIST_ROW / 4) {
             const float4 q = make_float4(nr.v[4 * tid], nr.v[4 * tid + 1], nr.v[4 * tid + 2], nr.v[4 * tid + 3]);
@@ -74,6 +101,7 @@ lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const 
         acc1 += e1;
     }
 
+    K1P_TRACE(2);
     if (SY > 1) {
         spart[(sy * 2) * CPB + c] = acc0;
         spart[(sy * 2 + 1) * CPB + c] = acc1;
@@ -111,7 +139,9 @@ lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const 
     if (tm.K > 0) {                                // uniform over the grid: tree finish (single history), one launch per tick
         __shared__ u64 mrows[BAL_FAN][BAL_ROW_PAD];
         key = cta_select32<KW, true>(key, skeys);
+        K1P_TRACE(3);
         if (tid < 32) tree_merge(key, tid, (int)blockIdx.x, (int)gridDim.x, tm.K, tm.ws, mrows, tm.out, px);
+        K1P_TRACE(4);
         return;
     }
     cta_select_emit<KW, true>(key, skeys, v, cta_lists);
@@ -167,3 +197,11 @@ int launch_k1_packed(const LbArgs& a, int sy, bool geom, bool mufu, cudaStream_t
 }
 
 }  // namespace llampc
+
+#ifdef LLAMPC_K1P_TRACE
+// experiments only (not declared in the public header): copies the K1p timeline of the last traced launch
+extern "C" int llampc_debug_k1p_trace(unsigned long long* dst_h, int n_ctas) {
+    if (!dst_h || n_ctas <= 0 || n_ctas > llampc::K1P_TRACE_CTAS) return LLAMPC_E_ARG;
+    return (int)cudaMemcpyFromSymbol(dst_h, llampc::g_k1p_trace, (size_t)n_ctas * 6 * sizeof(unsigned long long));
+}
+#endif
