@@ -78,7 +78,10 @@ int llampc_hist_row_pack_h(const double* x_k, const double* u_k, const double* x
  * ------------------------------------------------------------------------------------------- */
 #define LLAMPC_LB_RECOMPUTE 0   /* re-integrate the whole W-row window every call (N*W steps, stateless w.r.t. the bank)  */
 #define LLAMPC_LB_ROLLING   1   /* the reference's own bookkeeping (rt.py:352-354): integrate only the newest row, replace
-                                   column `slot` of err_ring [n_vehicles][W][Npad], re-sum the ring (N steps per call)     */
+                                   column `slot` of err_ring, re-sum the ring (N steps per call)                           */
+/* rows of an error ring for a window of W: W error columns + ceil(W / 4) rows of partial sums (groups of 4 columns; the
+ * window sum is formed group by group in a fixed order, identical in every rolling kernel).  Zero it before the first call. */
+#define LLAMPC_RING_ROWS(W) ((W) + (((W) + 3) >> 2))
 
 #define LLAMPC_SIN_AUTO     0   /* MUFU.SIN while sin_arg_max <= pi (its rated range), else the polynomial; 0 / unknown
                                    sin_arg_max selects the polynomial                                                      */
@@ -107,7 +110,7 @@ typedef struct llampc_lookback_desc {
     int emit;                    /* ROLLING: 0 = only store the error column (window still filling), no selection          */
     const float* row32_h;        /* HOST row (LLAMPC_HIST_ROW floats) riding in the kernel parameters, or NULL; single
                                     vehicle only                                                                            */
-    float* err_ring;             /* ROLLING: [n_vehicles][W][Npad] floats                                                   */
+    float* err_ring;             /* ROLLING: [n_vehicles][LLAMPC_RING_ROWS(W)][Npad] floats, zeroed by the caller           */
     /* results */
     int K;                       /* 1..LLAMPC_LIST_LEN; 0 with out = NULL: scores only (needs avg_err)                      */
     float* avg_err;              /* [n_vehicles][N] or NULL                                                                 */
@@ -206,7 +209,8 @@ typedef struct llampc_tick {
     unsigned peer_seq;              /* tick counter >= 1, identical on all ranks, incremented by the caller  */
     unsigned long long pending_seq; /* internal: state between llampc_lookback_tick (sync = 0) and ..._finish        */
     int pending_words;
-    float* err_ring;                /* [W][Npad] per-tick error columns (rolling mode only)                */
+    float* err_ring;                /* [LLAMPC_RING_ROWS(W)][Npad] per-tick error columns + partial sums, zeroed by the caller
+                                       (rolling mode only)                                                  */
     int rolling;                    /* 0: LLAMPC_LB_RECOMPUTE; 1: LLAMPC_LB_ROLLING (needs row32_h, err_ring and
                                        Kt <= LLAMPC_LIST_LEN; the fp64 re-score still walks the whole hist64 ring);
                                        2: rolling mode while the window is filling: store the column, no decision */

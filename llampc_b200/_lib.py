@@ -17,6 +17,13 @@ MAX_K = 64
 LIST_LEN = 16
 MAX_H = 256
 PLAN_WSEG = 48
+
+
+def ring_rows(W):
+    """LLAMPC_RING_ROWS: W error columns + ceil(W / 4) partial-sum rows of a rolling-mode error ring."""
+    return W + (W + 3) // 4
+
+
 PLAN_SPAD = 66
 PARAM_NAMES = ("lf", "lr", "mass", "Iz", "Bf", "Br", "Cf", "Cr", "Df", "Dr", "Cm1", "Cm2", "Cr0", "Cr2")
 

@@ -1,14 +1,23 @@
 // K1r / K1v: the reference's rolling error-window bookkeeping on the device (rt.py:349-358).  sm_100a.
 #include "lookback_kernels.cuh"
+#include "llampc_packed.cuh"
 
 namespace llampc {
 
 // ---------------------------------------------------------------------------------------------------
 // K1r rolling window (the reference's own bookkeeping, rt.py:349-358): only the newest transition is integrated
-// (one RK4 step per candidate), its error replaces ring column `slot` of err_ring [W][Npad] (np.roll + write of
-// the last column), and the window mean is re-summed from the ring -- N steps and N*W*4 bytes per tick instead
-// of N*W steps.  emit = 0 while the window is filling (columns stored, no decision).
+// (one RK4 step per candidate), its error replaces ring column `slot` of err_ring (np.roll + write of the last
+// column), and the window mean is re-summed from the ring -- N steps per tick instead of N*W steps.
+// emit = 0 while the window is filling (columns stored, no decision).
+//
+// Ring layout and summation order (shared with K1v, so both give bit-identical means): err_ring [LLAMPC_RING_ROWS(W)][Npad]
+// = W error columns followed by ceil(W / 4) rows of PARTIAL SUMS, partial_j = ((e_4j + e_4j+1) + e_4j+2) + e_4j+3, and
+// the window sum is partial_0 + partial_1 + ... in that order.  A tick changes one column, hence one partial: K1v reads
+// the 3 other columns of that group and the other partials (7 rows instead of 19 at W = 20); K1r, whose tick is
+// latency-bound anyway, re-adds every column in the same order and keeps the partial row up to date.
 // ---------------------------------------------------------------------------------------------------
+__host__ __device__ __forceinline__ int ring_groups(int W) { return (W + 3) >> 2; }
+
 template <bool GEOM_SHARED, bool MUFU_SIN>
 __global__ void __launch_bounds__(LB_THREADS)
 lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W, StepSize z, NewRow nr,
@@ -32,26 +41,33 @@ lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W,
         r.q3 = make_float4(nr.v[12], nr.v[13], nr.v[14], nr.v[15]);
         r.q4 = make_float4(nr.v[16], nr.v[17], nr.v[18], nr.v[19]);
     }
-    err_ring += (size_t)v * W * Npad;
+    err_ring += (size_t)v * (W + ring_groups(W)) * Npad;
     bool ok;
     float e = lookback_step_fast<GEOM_SHARED, MUFU_SIN>(p, r, z, ok);
     if (!ok) e = lookback_step<GEOM_SHARED, MUFU_SIN>(p, r, z);
     e *= 0.25f;                                    // errors of rt.py:349 (mean over the 4 scored states)
     if (valid) err_ring[(size_t)nr.slot * Npad + cand] = e;
-    if (!emit) return;                             // uniform
-    // window re-sum in ring order (deterministic); the loads of 8 columns are issued before the first add so that
-    // enough bytes are in flight per SM for HBM (the ring of 4,096 vehicles is 335 MB: this kernel is HBM-bound there)
+    // window sum in the canonical grouped order; the group of the new column also refreshes its partial-sum row
     float sum = 0.0f;
     const float* col = err_ring + ci;
-    int w = 0;
-    for (; w + 8 <= W; w += 8) {
-        float vq[8];
+    const int gnew = nr.slot >> 2;
+    for (int g0 = emit ? 0 : gnew; g0 < (emit ? ring_groups(W) : gnew + 1); ++g0) {
+        float vq[4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) vq[j] = __ldcg(col + (size_t)(w + j) * Npad);
+        for (int j = 0; j < 4; ++j) {
+            const int w = 4 * g0 + j;
+            vq[j] = (w < W && w != nr.slot) ? __ldcg(col + (size_t)w * Npad) : 0.0f;
+        }
+        float part = 0.0f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) sum += (w + j == nr.slot) ? e : vq[j];
+        for (int j = 0; j < 4; ++j) {
+            const int w = 4 * g0 + j;
+            if (w < W) part = j == 0 ? (w == nr.slot ? e : vq[0]) : part + (w == nr.slot ? e : vq[j]);
+        }
+        if (g0 == gnew && valid) err_ring[(size_t)(W + gnew) * Npad + cand] = part;
+        sum = g0 == 0 ? part : sum + part;
     }
-    for (; w < W; ++w) sum += (w == nr.slot) ? e : __ldcg(col + (size_t)w * Npad);
+    if (!emit) return;                             // uniform
     const float err = sum / (float)W;
     u64 key = ~0ull;
     if (valid) {
@@ -76,16 +92,21 @@ lookback_rolling_kernel(const float4* __restrict__ bank, int N, int Npad, int W,
 
 // ---------------------------------------------------------------------------------------------------
 // K1v rolling window, ONE CTA PER VEHICLE (Monte-Carlo layout: thousands of vehicles, a bank of <= 2,048 candidates
-// each).  Same arithmetic as K1r (one RK4 step per candidate, ring column `slot` replaced, window re-summed in ring
-// order: scores bit-identical to K1r); what changes is everything around the step.  ncu on K1r at 4,096 x 1,024 x 20:
-// ~1,200 instructions per candidate-tick, ~800 of them selection (a 15-stage register bitonic network per warp, three
-// merges per CTA, a list round trip through L2, a last-CTA merge per vehicle: ALU pipe 48 %, FMA 27 %, HBM 19 %).
-//   * Every thread owns FOUR ADJACENT candidates: the ring is re-summed with LDG.128 (5 loads and 10 address
-//     instructions per candidate instead of 20 and 40), the new column is read back by the thread that stored it.
+// each).  Same arithmetic per candidate and same summation order as K1r; what changes is everything around the step
+// (ncu on K1r at 4,096 x 1,024 x 20: ~1,200 instructions per candidate-tick, ~800 of them selection).
+//   * Every thread owns FOUR ADJACENT candidates: ring columns and partial sums move as LDG.128 (the strided row
+//     addresses cannot be immediates), the new column is read back by the thread that stored it.
+//   * The window sum uses the partial-sum rows of the ring (see K1r): the 3 other columns of the new column's group and
+//     the other ceil(W/4) - 1 partials -- 7 LDG.128 per thread instead of 19 at W = 20, 150 MB of ring traffic per tick
+//     instead of 335 MB at 4,096 x 1,024: 103.5 -> 99 us there, 76 -> 64 us at W = 50 (the kernel is bound by the issue
+//     slots of the 397-instruction scalar step, not by HBM).
+//   * The step stays scalar (64 registers, 4 CTAs per SM = 32 warps).  The packed f32x2 step (LLAMPC_RV_PACKED=1: 118-126
+//     registers, 2 CTAs per SM) was measured again with the partial sums in place: 126 us -- sixteen warps do not cover the
+//     latency of the ring reads.
 //   * The vehicle's keys stay in shared memory and are FILTERED, not sorted (cta_topk_filter, lookback_kernels.cuh):
 //     every group of 32 keys (warp x candidate slot) leaves its minimum (two REDUX), <= 64 minima per vehicle; the K-th
 //     smallest minimum is a threshold that at least K keys pass; the survivors (K .. 3K keys) are sorted by warp 0.
-//   * The ring lines a warp will re-sum are prefetched into L2 before its RK4 steps (lane w asks for row w).
+//   * The ring lines a warp will read are prefetched into L2 before its RK4 steps.
 // Needs Npad % 4 == 0 and a 16-byte aligned ring (the entry point falls back to K1r otherwise).
 // ---------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void prefetch_l2_4lines(const void* p, int n_lines) {
@@ -95,8 +116,11 @@ __device__ __forceinline__ void prefetch_l2_4lines(const void* p, int n_lines) {
     if (n_lines > 3) asm volatile("prefetch.global.L2 [%0+384];" ::"l"(p));
 }
 
+#ifndef LLAMPC_RV_PACKED
+#define LLAMPC_RV_PACKED 0
+#endif
 #ifndef LLAMPC_RV_MIN_BLOCKS
-#define LLAMPC_RV_MIN_BLOCKS 4
+#define LLAMPC_RV_MIN_BLOCKS (LLAMPC_RV_PACKED ? 2 : 4)
 #endif
 template <bool GEOM_SHARED, bool MUFU_SIN>
 __global__ void __launch_bounds__(RV_THREADS, LLAMPC_RV_MIN_BLOCKS)
@@ -112,48 +136,71 @@ lookback_rolling_vehicle_kernel(const float4* __restrict__ bank, int N, int Npad
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int v = blockIdx.x;
     const int passes = (N + RV_CPP - 1) / RV_CPP;
+    const int G = ring_groups(W), gnew = slot >> 2;
     if (tid < 5) srow[tid] = __ldg(reinterpret_cast<const float4*>(hist + ((size_t)v * W + slot) * LLAMPC_HIST_ROW) + tid);
-    err_ring += (size_t)v * W * Npad;
+    err_ring += (size_t)v * (W + G) * Npad;
     __syncthreads();
 #pragma unroll 1
     for (int j = 0; j < passes; ++j) {
         const int wbase = j * RV_CPP + warp * 128;                 // first candidate of this warp in this pass
         const int c0 = wbase + lane * 4;                           // this thread's candidates c0 .. c0 + 3
-        if (emit && wbase < N) {
+        if (wbase < N) {                                           // the rows this warp reads after its RK4 steps -> L2
             const int n_lines = min(4, (Npad - wbase) >> 5);
-            for (int w = lane; w < W; w += 32)
-                if (w != slot) prefetch_l2_4lines(err_ring + (size_t)w * Npad + wbase, n_lines);
+            const int n_rows = emit ? 3 + G : 3;                   // the group's other columns (+ the partial rows)
+            if (lane < n_rows) {
+                int row = lane < 3 ? 4 * gnew + lane + (4 * gnew + lane >= slot ? 1 : 0) : W + (lane - 3);
+                if (lane >= 3 || row < min(W, 4 * gnew + 4)) prefetch_l2_4lines(err_ring + (size_t)row * Npad + wbase, n_lines);
+            }
         }
         u64 key[4] = {~0ull, ~0ull, ~0ull, ~0ull};
         if (c0 < N) {
+            HistRow r;
+            r.q0 = srow[0]; r.q1 = srow[1]; r.q2 = srow[2]; r.q3 = srow[3]; r.q4 = srow[4];
             float* mine = err_ring + (size_t)slot * Npad + c0;
+#if !LLAMPC_RV_PACKED
 #pragma unroll 1
-            for (int q = 0; q < 4; ++q) {
+            for (int q = 0; q < 4; ++q) {                          // one candidate at a time: 64 registers, 4 CTAs per SM
                 if (c0 + q >= N) break;
                 const Cand p = load_cand(bank, Npad, c0 + q);
-                HistRow r;
-                r.q0 = srow[0]; r.q1 = srow[1]; r.q2 = srow[2]; r.q3 = srow[3]; r.q4 = srow[4];
                 bool ok;
                 float e = lookback_step_fast<GEOM_SHARED, MUFU_SIN>(p, r, z, ok);
                 if (!ok) e = lookback_step<GEOM_SHARED, MUFU_SIN>(p, r, z);
                 __stcg(mine + q, 0.25f * e);                       // errors of rt.py:349 (mean over the 4 scored states)
             }
-            if (emit) {
-                // window re-sum in ring order, as K1r; the new column is read back by the thread that just stored it
-                // (program order), so the loop is loads and adds only.  Columns N .. Npad - 1 are padding.
-                float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
-                const float* col = err_ring + c0;
-                int w = 0;
-                for (; w + 4 <= W; w += 4, col += (size_t)4 * Npad) {
-                    float4 vq[4];
+#else
+#pragma unroll 1
+            for (int q = 0; q < 2; ++q) {                          // two packed pairs (c0, c0 + 1), (c0 + 2, c0 + 3)
+                const int i0 = min(c0 + 2 * q, N - 1), i1 = min(c0 + 2 * q + 1, N - 1);
+                const Cand2 p = load_cand2(bank, Npad, i0, i1);
+                bool ok0, ok1;
+                const F2 e = lookback_step_fast2<GEOM_SHARED, MUFU_SIN>(p, r, z, ok0, ok1);
+                float e0, e1;
+                up(e, e0, e1);
+                if (!ok0) e0 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i0, srow, z);
+                if (!ok1) e1 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i1, srow, z);
+                __stcg(reinterpret_cast<float2*>(mine + 2 * q), make_float2(0.25f * e0, 0.25f * e1));
+            }
+#endif
+            // the new column is read back by the thread that just stored it (program order; columns N .. Npad - 1 are padding)
+            const float4 enew = __ldcg(reinterpret_cast<const float4*>(mine));
+            // partial sum of the new column's group, canonical order ((e_4g + e_4g+1) + e_4g+2) + e_4g+3
+            float4 part = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
 #pragma unroll
-                    for (int i = 0; i < 4; ++i) vq[i] = __ldcg(reinterpret_cast<const float4*>(col + (size_t)i * Npad));
-#pragma unroll
-                    for (int i = 0; i < 4; ++i) { sum.x += vq[i].x; sum.y += vq[i].y; sum.z += vq[i].z; sum.w += vq[i].w; }
+            for (int i = 0; i < 4; ++i) {
+                const int w = 4 * gnew + i;
+                if (w < W) {
+                    const float4 c = w == slot ? enew : __ldcg(reinterpret_cast<const float4*>(err_ring + (size_t)w * Npad + c0));
+                    if (i == 0) part = c;
+                    else { part.x += c.x; part.y += c.y; part.z += c.z; part.w += c.w; }
                 }
-                for (; w < W; ++w, col += Npad) {
-                    const float4 vq = __ldcg(reinterpret_cast<const float4*>(col));
-                    sum.x += vq.x; sum.y += vq.y; sum.z += vq.z; sum.w += vq.w;
+            }
+            __stcg(reinterpret_cast<float4*>(err_ring + (size_t)(W + gnew) * Npad + c0), part);
+            if (emit) {
+                float4 sum = make_float4(0.0f, 0.0f, 0.0f, 0.0f);
+                for (int g0 = 0; g0 < G; ++g0) {                   // partial_0 + partial_1 + ... in order
+                    const float4 c = g0 == gnew ? part : __ldcg(reinterpret_cast<const float4*>(err_ring + (size_t)(W + g0) * Npad + c0));
+                    if (g0 == 0) sum = c;
+                    else { sum.x += c.x; sum.y += c.y; sum.z += c.z; sum.w += c.w; }
                 }
                 const float fw = (float)W;
                 const float err[4] = {sum.x / fw, sum.y / fw, sum.z / fw, sum.w / fw};

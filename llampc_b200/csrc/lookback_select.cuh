@@ -90,6 +90,11 @@ __device__ __forceinline__ u64 peer_minloc(const PeerXchg& px, u64 my_key, int l
 // release / acquire fence at GPU scope (MEMBAR.ALL.GPU): lighter than __threadfence()'s sequentially consistent fence
 // and sufficient for the store -> count / count -> load message passing of the merge tree
 __device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned atom_add_acq_rel_gpu(unsigned* p, unsigned v) {
+    unsigned old;
+    asm volatile("atom.add.acq_rel.gpu.u32 %0, [%1], %2;" : "=r"(old) : "l"(p), "r"(v) : "memory");
+    return old;
+}
 
 constexpr int BAL_FAN = 32;                        // lists merged per tree node (one per lane)
 constexpr int BAL_ROW_PAD = LLAMPC_LIST_LEN + 1;   // shared-memory row pitch of the merge staging (bank spread)
@@ -116,14 +121,13 @@ __device__ __forceinline__ void tree_merge(u64 key, int lane, int idx, int n, in
         const int node = idx / BAL_FAN;
         const int c = min(BAL_FAN, n - node * BAL_FAN);
         unsigned old = 0;
-        if (lane == 0) {
-            fence_acq_rel_gpu();                   // release (cumulative over the warp barrier): list before count
-            old = atomicAdd(cnt + node, 1u);
-        }
+        // ONE acq_rel atomic instead of fence + atomic + fence: its release half (cumulative over the warp barrier above)
+        // publishes this warp's list before the count, its acquire half orders the loads of the other lists -- which the
+        // other lanes issue after the shuffle below, a warp-level synchronisation -- after the count
+        if (lane == 0) old = atom_add_acq_rel_gpu(cnt + node, 1u);
         old = __shfl_sync(0xffffffffu, old, 0);
         if (old != (unsigned)(c - 1)) return;      // a later arrival merges this node
         if (lane == 0) cnt[node] = 0;              // ready for the next launch on the same stream
-        fence_acq_rel_gpu();                       // acquire: the other lists are read after the count
         const u64* src = lists + (size_t)node * BAL_FAN * LLAMPC_LIST_LEN;
 #pragma unroll
         for (int j = 0; j < LLAMPC_LIST_LEN; ++j) {            // c lists are contiguous: coalesced, one L2 round trip

@@ -170,7 +170,8 @@ class LookBack:
         self.fused = self.Kt <= _lib.LIST_LEN
         if self.rolling and not self.fused:
             raise ValueError("rolling mode needs max(K, refine) <= %d" % _lib.LIST_LEN)
-        self.err_ring = torch.zeros((self.W, self.bank.Npad), dtype=torch.float32, device=dev) if self.rolling else None
+        self.err_ring = (torch.zeros((_lib.ring_rows(self.W), self.bank.Npad), dtype=torch.float32, device=dev)
+                         if self.rolling else None)
         # result: best key | Kt finalist keys | Kt fp64 scores  (the scoring launch writes LIST_LEN + 1 words)
         words = max(2 + 2 * self.Kt, _lib.LIST_LEN + 2)           # + 1 spare word: zero-copy sequence flag
         self._peer = None

@@ -99,7 +99,7 @@ class MonteCarlo:
         # "rolling" = the reference's own bookkeeping (rt.py:352-354): per-vehicle (W, N) error ring, one new column per
         # tick; "recompute" re-integrates every vehicle's whole window every tick (W times the look-back work)
         self.rolling = lookback_mode == "rolling"
-        self.err_ring = torch.zeros((V, W, self.bank.Npad), dtype=f32, device=dev) if self.rolling else None
+        self.err_ring = torch.zeros((V, _lib.ring_rows(W), self.bank.Npad), dtype=f32, device=dev) if self.rolling else None
         self.topk = torch.zeros((V, _lib.LIST_LEN + 1), dtype=i64, device=dev)
         # the look-back launch of every tick (llampc_lookback_launch): rolling -> K1v (one CTA per vehicle), recompute ->
         # K1p over (candidate tile, vehicle) with the last-CTA merge; tyre sine None = automatic (SFU while the bank's

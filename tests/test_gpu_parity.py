@@ -414,7 +414,7 @@ def test_rolling_multi_vehicle_cta_path(history, N, W, K, kind):
     res = {}
     for mode in ("1", "0"):
         hist = torch.zeros((V, W, 20), dtype=torch.float32, device="cuda")
-        ring = torch.zeros((V, W, bank.Npad), dtype=torch.float32, device="cuda")
+        ring = torch.zeros((V, _lib.ring_rows(W), bank.Npad), dtype=torch.float32, device="cuda")
         avg = torch.zeros((V, N), dtype=torch.float32, device="cuda")
         # sine mode left to the library: the sigma = 2 bank (C up to 9.7: tyre-sine arguments of 15 rad, where MUFU.SIN
         # loses the 1e-4 tolerance, tools/gpu_wide_bank_check.py) must come out strict, the reference's spreads on the SFU

@@ -35,7 +35,7 @@ for j in range(W):
                              one[j].ctypes.data, None)
 rows[:] = one[None]
 hist = torch.from_numpy(rows).cuda()
-ring = torch.zeros((V, W, bank.Npad), dtype=torch.float32, device="cuda") if mode == "rolling" else None
+ring = torch.zeros((V, _lib.ring_rows(W), bank.Npad), dtype=torch.float32, device="cuda") if mode == "rolling" else None
 lb = LookbackLaunch(bank, hist, W, Ts, K=10, n_vehicles=V, mode=mode, err_ring=ring, kernel=kernel, split=split,
                     fast_sin={"auto": None, "sfu": True, "strict": False}[sine])
 flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")

@@ -60,7 +60,7 @@ if "c4" in what or "k1v" in what:
             lb4.launch()
         torch.cuda.synchronize()
     if "k1v" in what:
-        ring = torch.zeros((V, 20, bank.Npad), dtype=torch.float32, device="cuda")
+        ring = torch.zeros((V, _lib.ring_rows(20), bank.Npad), dtype=torch.float32, device="cuda")
         lbv = LookbackLaunch(bank, hist, 20, TS, K=10, n_vehicles=V, mode="rolling", err_ring=ring)
         for i in range(24):
             lbv.launch(slot=i % 20, emit=1)
