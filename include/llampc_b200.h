@@ -281,8 +281,9 @@ int llampc_forces_batch_f32(const float* bank, int N, int Npad, const double* x6
  *   x0         [n_x0][6] doubles (n_x0 = 1: shared start state, or M)
  *   U          [K][H][2] floats, or [M][K][H][2] if per_model_flags & 1
  *   xref       [H+1][2] floats (row h = reference position at step h), or [M][H+1][2] if per_model_flags & 2
- *   uprev      [2] floats, or [M][2] if per_model_flags & 4   (per_model_flags & 8: diagnostics, force the
- *              general branchy step instead of the straight-line one)
+ *   uprev      [2] floats, or [M][2] if per_model_flags & 4   (diagnostics: per_model_flags & 8 forces the scalar
+ *              kernel with the general branchy step, & 16 the scalar kernel with its straight-line step, instead of
+ *              the packed two-models-per-thread kernels)
  *              shared U / xref tables are fetched with 16-byte-granular bulk copies: the buffers must be
  *              16-byte aligned and readable up to the next multiple of 16 bytes
  *   qrp_h      HOST pointer, 6 floats = Q00 Q11 R00 R11 P00 P11

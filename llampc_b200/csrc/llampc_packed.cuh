@@ -313,9 +313,24 @@ __device__ __forceinline__ F2 pacejka_la2(F2 z, F2 C, F2 D) {
     return mul2(D, pk(sin_mufu(t0), sin_mufu(t1)));
 }
 
-// d/dt of (vx, vy, omega) for two models on the same control input, slip angles of any size (accel_fast<.., true>)
+// Control input of a packed step.  With one control sequence shared by both models every member is a broadcast pair that
+// ptxas folds into the packed instruction as a scalar operand; with one sequence per model the components differ.
+struct Ctl2 { F2 pwm, npwm, delta, nsd, cd; };    // npwm = -pwm, nsd = -sin(delta)
+__device__ __forceinline__ Ctl2 ctl2_shared(float pwm, float delta, float sd, float cd) {
+    Ctl2 u;
+    u.pwm = bc(pwm); u.npwm = bc(-pwm); u.delta = bc(delta); u.nsd = bc(-sd); u.cd = bc(cd);
+    return u;
+}
+__device__ __forceinline__ Drive2 prep_drive2(const Cand2& p, const Ctl2& u) {
+    Drive2 d;
+    d.A = fma2(p.Cm1, u.pwm, p.nCr0);
+    d.nBq = mul2(p.Cm2, u.npwm);
+    return d;
+}
+
+// d/dt of (vx, vy, omega) for two models, slip angles of any size (accel_fast<.., true>)
 // Bfd = Bf delta and nBf = -Bf are formed once per step: Bf (delta - a) = nBf a + Bfd is one FFMA2 per stage.
-__device__ __forceinline__ Deriv2 accel_full2(const Cand2& p, const Ctl& u, const Drive2& drv, F2 nBf, F2 Bfd, F2 vx, F2 vy, F2 w) {
+__device__ __forceinline__ Deriv2 accel_full2(const Cand2& p, const Ctl2& u, const Drive2& drv, F2 nBf, F2 Bfd, F2 vx, F2 vy, F2 w) {
     float vx0, vx1;
     up(vx, vx0, vx1);
     const float avx0 = fabsf(vx0), avx1 = fabsf(vx1);
@@ -324,9 +339,9 @@ __device__ __forceinline__ Deriv2 accel_full2(const Cand2& p, const Ctl& u, cons
     const F2 Frx = drive_force_fast2(p, drv, vx);
     const F2 Ffy = pacejka_la2(zf, p.Cf, p.Df);
     const F2 nFry = pacejka_la2(nzr, p.Cr, p.Dr);
-    const F2 Fc = mul2(Ffy, bc(u.cd));
+    const F2 Fc = mul2(Ffy, u.cd);
     Deriv2 r;
-    r.vx = fma2(fma2(Ffy, bc(-u.sd), Frx), p.inv_m, mul2(vy, w));
+    r.vx = fma2(fma2(Ffy, u.nsd, Frx), p.inv_m, mul2(vy, w));
     r.nvy = fma2(sub2(nFry, Fc), p.inv_m, mul2(vx, w));
     r.w = fma2(Fc, p.lf_Iz, mul2(nFry, p.lr_Iz));
     return r;
@@ -337,43 +352,44 @@ __device__ __forceinline__ Deriv2 accel_full2(const Cand2& p, const Ctl& u, cons
 // position error of v h 4e-7 ~ 1e-8 m per step), and the rotation by the start heading uses its fp64-formed sin / cos as
 // broadcast scalars: 4 packed operations + 4 MUFU per stage instead of the 15 packed operations of a polynomial
 // sin / cos + rotation, valid for ANY heading change (no tiny-angle guard, no fallback).
-__device__ __forceinline__ void heading2(F2 phi, float s0, float c0, F2& sn, F2& cs) {
+struct Head2 { F2 s0, c0, ns0; };                 // sin, cos, -sin of the start heading (broadcast pairs when it is shared)
+__device__ __forceinline__ void heading2(F2 phi, const Head2& h0, F2& sn, F2& cs) {
     float a0, a1;
     up(phi, a0, a1);
     const F2 sp = pk(__sinf(a0), __sinf(a1)), cp = pk(__cosf(a0), __cosf(a1));
-    sn = fma2(bc(s0), cp, mul2(bc(c0), sp));
-    cs = fma2(bc(c0), cp, mul2(bc(-s0), sp));
+    sn = fma2(h0.s0, cp, mul2(h0.c0, sp));
+    cs = fma2(h0.c0, cp, mul2(h0.ns0, sp));
 }
 
 // One RK4 step of two models (rk4_increment_fast, same stages).  State in / out: position relative to the start (X, Y),
 // heading relative to the start heading (phi), vx, vy, omega.  The weighted stage sums (k1 + 2 k2 + 2 k3 + k4) are
 // accumulated stage by stage and folded into the state with one FFMA2 each.
 struct State2 { F2 X, Y, phi, vx, vy, w; };
-__device__ __forceinline__ void rk4_step2(const Cand2& p, const Ctl& u, float s0, float c0, float h, State2& x) {
+__device__ __forceinline__ void rk4_step2(const Cand2& p, const Ctl2& u, const Head2& h0, float h, State2& x) {
     const float hh = 0.5f * h, h6 = h * (1.0f / 6.0f);
-    const Drive2 drv = prep_drive2(p, u.pwm);
-    const F2 nBf = neg2(p.Bf), Bfd = mul2(p.Bf, bc(u.delta));
+    const Drive2 drv = prep_drive2(p, u);
+    const F2 nBf = neg2(p.Bf), Bfd = mul2(p.Bf, u.delta);
     F2 sn, cs;
     // stage 1
-    heading2(x.phi, s0, c0, sn, cs);
+    heading2(x.phi, h0, sn, cs);
     Deriv2 a = accel_full2(p, u, drv, nBf, Bfd, x.vx, x.vy, x.w);
     F2 sx = fma2(x.vx, cs, mul2(neg2(x.vy), sn)), sy = fma2(x.vx, sn, mul2(x.vy, cs));
     F2 sw = x.w, svx = a.vx, snvy = a.nvy, sdw = a.w;
     F2 vx = fma2(bc(hh), a.vx, x.vx), vy = fma2(bc(-hh), a.nvy, x.vy), w = fma2(bc(hh), a.w, x.w);
-    heading2(fma2(bc(hh), x.w, x.phi), s0, c0, sn, cs);
+    heading2(fma2(bc(hh), x.w, x.phi), h0, sn, cs);
     // stage 2
     a = accel_full2(p, u, drv, nBf, Bfd, vx, vy, w);
     sx = fma2(bc(2.0f), fma2(vx, cs, mul2(neg2(vy), sn)), sx);
     sy = fma2(bc(2.0f), fma2(vx, sn, mul2(vy, cs)), sy);
     sw = fma2(bc(2.0f), w, sw); svx = fma2(bc(2.0f), a.vx, svx); snvy = fma2(bc(2.0f), a.nvy, snvy); sdw = fma2(bc(2.0f), a.w, sdw);
-    heading2(fma2(bc(hh), w, x.phi), s0, c0, sn, cs);
+    heading2(fma2(bc(hh), w, x.phi), h0, sn, cs);
     vx = fma2(bc(hh), a.vx, x.vx); vy = fma2(bc(-hh), a.nvy, x.vy); w = fma2(bc(hh), a.w, x.w);
     // stage 3
     a = accel_full2(p, u, drv, nBf, Bfd, vx, vy, w);
     sx = fma2(bc(2.0f), fma2(vx, cs, mul2(neg2(vy), sn)), sx);
     sy = fma2(bc(2.0f), fma2(vx, sn, mul2(vy, cs)), sy);
     sw = fma2(bc(2.0f), w, sw); svx = fma2(bc(2.0f), a.vx, svx); snvy = fma2(bc(2.0f), a.nvy, snvy); sdw = fma2(bc(2.0f), a.w, sdw);
-    heading2(fma2(bc(h), w, x.phi), s0, c0, sn, cs);
+    heading2(fma2(bc(h), w, x.phi), h0, sn, cs);
     vx = fma2(bc(h), a.vx, x.vx); vy = fma2(bc(-h), a.nvy, x.vy); w = fma2(bc(h), a.w, x.w);
     // stage 4
     a = accel_full2(p, u, drv, nBf, Bfd, vx, vy, w);

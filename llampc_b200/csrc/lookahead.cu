@@ -215,7 +215,8 @@ lookahead2_kernel(const float4* __restrict__ bank, int Mpad, int M, const double
     __syncthreads();
     if (!ok0) return;                                              // whole warp
 
-    const float s_start = s_x0[0], c_start = s_x0[1];
+    Head2 h0;
+    h0.s0 = bc(s_x0[0]); h0.c0 = bc(s_x0[1]); h0.ns0 = bc(-s_x0[0]);
     u64 best0 = ~0ull, best1 = ~0ull;
     for (int k0 = 0; k0 < K; k0 += 32) {
         const int k = k0 + lane;
@@ -229,9 +230,7 @@ lookahead2_kernel(const float4* __restrict__ bank, int Mpad, int M, const double
 #pragma unroll 1
         for (int hh = 0; hh < H; ++hh) {
             const float4 cq = ctlk[hh];
-            Ctl ctl;
-            ctl.pwm = cq.x; ctl.delta = cq.y; ctl.sd = cq.z; ctl.cd = cq.w;
-            rk4_step2(p, ctl, s_start, c_start, h, x);            // straight-line code: no guard, no fallback
+            rk4_step2(p, ctl2_shared(cq.x, cq.y, cq.z, cq.w), h0, h, x);      // straight-line code: no guard, no fallback
             const float2 xr = sRel[hh + 1];
             ex = add2(x.X, bc(-xr.x));
             ey = add2(x.Y, bc(-xr.y));
@@ -258,6 +257,118 @@ lookahead2_kernel(const float4* __restrict__ bank, int Mpad, int M, const double
                 if (ok1) {
                     o = x_final + ((size_t)m1 * K + k) * 6;
                     o[0] = x0[0] + (double)b[0]; o[1] = x0[1] + (double)b[1]; o[2] = x0[2] + (double)b[2];
+                    o[3] = (double)b[3]; o[4] = (double)b[4]; o[5] = (double)b[5];
+                }
+            }
+        }
+    }
+    best0 = warp_min_u64(best0);
+    best1 = warp_min_u64(best1);
+    if (lane == 0) {
+        best_k[m0] = (int)(best0 & 0xffffffffull);
+        if (ok1) best_k[m1] = (int)(best1 & 0xffffffffull);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// K2q.  The packed rollout for the per-model layouts (Monte-Carlo closed loop: one model, start state, control table,
+// reference path and previous input PER VEHICLE): two models per thread as in K2p, but the control input and the start
+// heading now differ between the two components, so they are packed operands too (Ctl2 / Head2) and nothing is hoisted
+// per CTA.  Any of x0 / U / xref / uprev may still be shared (stride 0).  The inputs of the next step are loaded while
+// the current one is integrated; sin / cos of the steering angle come from the SFU.
+// ---------------------------------------------------------------------------------------------------
+// CTA = 2 warps = 4 models, registers capped for 7 CTAs per SM (14 warps): the 4,096-vehicle closed loop is 2,048
+// pair-warps = 13.8 per SM, so every warp is resident in ONE wave (at 3 CTAs of 4 warps the last 1.8 warps per SM ran a
+// second, latency-bound round: 70 us against 58 us for the scalar kernel).
+#ifndef LLAMPC_LQ_MIN_BLOCKS
+#define LLAMPC_LQ_MIN_BLOCKS 7
+#endif
+constexpr int LQ_THREADS = 64;
+constexpr int LQ_WARPS = LQ_THREADS / 32;
+__global__ void __launch_bounds__(LQ_THREADS, LLAMPC_LQ_MIN_BLOCKS)
+lookahead2_permodel_kernel(const float4* __restrict__ bank, int Mpad, const int* __restrict__ model_idx, int M,
+                           const double* __restrict__ x0, int n_x0, const float* __restrict__ U, int K, int H,
+                           const float* __restrict__ xref, const float* __restrict__ uprev, int per_model,
+                           float q0, float q1, float r0, float r1, float p0, float p1, float h,
+                           float* __restrict__ J, int* __restrict__ best_k, double* __restrict__ x_final) {
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const bool u_pm = per_model & 1, xref_pm = per_model & 2, uprev_pm = per_model & 4;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    float2* sRel = reinterpret_cast<float2*>(smem_raw) + (size_t)warp * 2 * (H + 1);      // [2][H+1] per warp
+    const int m0 = (blockIdx.x * LQ_WARPS + warp) * 2, m1 = m0 + 1;
+    if (m0 >= M) return;                                           // whole warp
+    const bool ok1 = m1 < M;
+    const int mm1 = ok1 ? m1 : m0;
+    const int i0 = model_idx ? model_idx[m0] : m0, i1 = model_idx ? model_idx[mm1] : mm1;
+    const Cand2 p = load_cand2(bank, Mpad, i0, i1);
+    const double* xa = x0 + (n_x0 > 1 ? (size_t)m0 * 6 : 0);
+    const double* xb = x0 + (n_x0 > 1 ? (size_t)mm1 * 6 : 0);
+    double sa, ca, sb, cb;
+    sincos(xa[2], &sa, &ca);
+    sincos(xb[2], &sb, &cb);
+    Head2 h0;
+    h0.s0 = pk((float)sa, (float)sb); h0.c0 = pk((float)ca, (float)cb); h0.ns0 = pk(-(float)sa, -(float)sb);
+    const float2* Ua = reinterpret_cast<const float2*>(U) + (u_pm ? (size_t)m0 * K * H : 0);
+    const float2* Ub = reinterpret_cast<const float2*>(U) + (u_pm ? (size_t)mm1 * K * H : 0);
+    const float2* Xa = reinterpret_cast<const float2*>(xref) + (xref_pm ? (size_t)m0 * (H + 1) : 0);
+    const float2* Xb = reinterpret_cast<const float2*>(xref) + (xref_pm ? (size_t)mm1 * (H + 1) : 0);
+    const float2 upa = reinterpret_cast<const float2*>(uprev)[uprev_pm ? m0 : 0];
+    const float2 upb = reinterpret_cast<const float2*>(uprev)[uprev_pm ? mm1 : 0];
+    for (int j = lane; j <= H; j += 32) {                          // reference paths relative to the start positions (fp64)
+        const float2 ra = __ldg(Xa + j), rb = __ldg(Xb + j);
+        sRel[j] = make_float2((float)((double)ra.x - xa[0]), (float)((double)ra.y - xa[1]));
+        sRel[(H + 1) + j] = make_float2((float)((double)rb.x - xb[0]), (float)((double)rb.y - xb[1]));
+    }
+    __syncwarp();
+    u64 best0 = ~0ull, best1 = ~0ull;
+    for (int k0 = 0; k0 < K; k0 += 32) {
+        const int k = k0 + lane;
+        const bool k_ok = k < K;
+        const int kk = k_ok ? k : K - 1;
+        State2 x;
+        x.X = bc(0.0f); x.Y = bc(0.0f); x.phi = bc(0.0f);
+        x.vx = pk((float)xa[3], (float)xb[3]); x.vy = pk((float)xa[4], (float)xb[4]); x.w = pk((float)xa[5], (float)xb[5]);
+        F2 Jt = bc(0.0f), Ja = bc(0.0f), ex = bc(0.0f), ey = bc(0.0f);
+        F2 uq0 = pk(upa.x, upb.x), uq1 = pk(upa.y, upb.y);        // previous input (pwm pair, steer pair)
+        const float2* ua = Ua + (size_t)kk * H;
+        const float2* ub = Ub + (size_t)kk * H;
+        float2 na = __ldg(ua), nb = __ldg(ub);
+#pragma unroll 1
+        for (int hh = 0; hh < H; ++hh) {
+            const float2 a = na, b = nb;
+            if (hh + 1 < H) { na = __ldg(ua + hh + 1); nb = __ldg(ub + hh + 1); }          // next step's inputs in flight
+            Ctl2 u;
+            u.pwm = pk(a.x, b.x); u.npwm = pk(-a.x, -b.x); u.delta = pk(a.y, b.y);
+            u.nsd = pk(-__sinf(a.y), -__sinf(b.y)); u.cd = pk(__cosf(a.y), __cosf(b.y));
+            const F2 du0 = sub2(u.pwm, uq0), du1 = sub2(u.delta, uq1);                     // nmpc.py:66-69 (du_0 = u_0 - uprev)
+            Ja = fma2(mul2(bc(r0), du0), du0, fma2(mul2(bc(r1), du1), du1, Ja));
+            uq0 = u.pwm; uq1 = u.delta;
+            rk4_step2(p, u, h0, h, x);
+            const float2 ra = sRel[hh + 1], rb = sRel[(H + 1) + hh + 1];
+            ex = sub2(x.X, pk(ra.x, rb.x));
+            ey = sub2(x.Y, pk(ra.y, rb.y));
+            Jt = fma2(mul2(bc(q0), ex), ex, fma2(mul2(bc(q1), ey), ey, Jt));               // nmpc.py:70-71
+        }
+        Jt = fma2(mul2(bc(p0), ex), ex, fma2(mul2(bc(p1), ey), ey, Jt));                   // terminal cost nmpc.py:48
+        float j0, j1;
+        up(add2(Jt, Ja), j0, j1);
+        if (k_ok) {
+            J[(size_t)m0 * K + k] = j0;
+            best0 = u64_min(best0, pack_key(j0, (unsigned)k));
+            if (ok1) {
+                J[(size_t)m1 * K + k] = j1;
+                best1 = u64_min(best1, pack_key(j1, (unsigned)k));
+            }
+            if (x_final) {
+                float a[6], b[6];
+                up(x.X, a[0], b[0]); up(x.Y, a[1], b[1]); up(x.phi, a[2], b[2]); up(x.vx, a[3], b[3]); up(x.vy, a[4], b[4]);
+                up(x.w, a[5], b[5]);
+                double* o = x_final + ((size_t)m0 * K + k) * 6;
+                o[0] = xa[0] + (double)a[0]; o[1] = xa[1] + (double)a[1]; o[2] = xa[2] + (double)a[2];
+                o[3] = (double)a[3]; o[4] = (double)a[4]; o[5] = (double)a[5];
+                if (ok1) {
+                    o = x_final + ((size_t)m1 * K + k) * 6;
+                    o[0] = xb[0] + (double)b[0]; o[1] = xb[1] + (double)b[1]; o[2] = xb[2] + (double)b[2];
                     o[3] = (double)b[3]; o[4] = (double)b[4]; o[5] = (double)b[5];
                 }
             }
@@ -306,7 +417,7 @@ extern "C" int llampc_lookahead_rollout_f32(const float* bank, int Mpad, const i
     cudaStream_t st = static_cast<cudaStream_t>(stream);
     // shared start state, control table, reference path and previous input (config C3): two models per thread (K2p).
     // per_model_flags & 8 (diagnostics: force the general step) keeps the scalar kernel for this layout too.
-    if (per_model_flags == 0 && n_x0 == 1 && !model_idx && !x_traj && M >= 2) {
+    if ((per_model_flags & 15) == 0 && !(per_model_flags & 16) && n_x0 == 1 && !model_idx && !x_traj && M >= 2) {
         const size_t tab = (((size_t)K * H * 8 + 15) & ~(size_t)15) + ((((size_t)H + 1) * 8 + 15) & ~(size_t)15);
         const size_t smem2 = ((tab + ((size_t)H + 2) * 8 + (size_t)K * 4 + 15) & ~(size_t)15) + (size_t)K * H * 16;
         if (smem2 <= 160 * 1024) {
@@ -317,6 +428,16 @@ extern "C" int llampc_lookahead_rollout_f32(const float* bank, int Mpad, const i
             return (int)cudaGetLastError();
         }
     }
+    // any per-model layout (Monte-Carlo closed loop: model_idx, per-vehicle x0 / U / xref / uprev): the packed kernel K2q
+    if (!(per_model_flags & (8 | 16)) && !x_traj) {
+        const size_t smemq = (size_t)LQ_WARPS * 2 * (H + 1) * 8;
+        LLAMPC_CUDA_TRY((cudaError_t)raise_dynamic_smem(lookahead2_permodel_kernel, smemq));
+        lookahead2_permodel_kernel<<<(M + 2 * LQ_WARPS - 1) / (2 * LQ_WARPS), LQ_THREADS, smemq, st>>>(
+            reinterpret_cast<const float4*>(bank), Mpad, model_idx, M, x0, n_x0, U, K, H, xref, uprev, per_model_flags & 7,
+            qrp_h[0], qrp_h[1], qrp_h[2], qrp_h[3], qrp_h[4], qrp_h[5], (float)Ts, J, best_k, x_final);
+        return (int)cudaGetLastError();
+    }
+    // the scalar kernel K2 (one model per warp): trajectory output and the diagnostic general-step mode
     size_t smem = (u_pm ? 0 : (((size_t)K * H * 8 + 15) & ~(size_t)15)) + (xref_pm ? 0 : ((((size_t)H + 1) * 8 + 15) & ~(size_t)15)) +
                   (size_t)LA_WARPS * (H + 1) * 8;
     if (smem > 96 * 1024) return LLAMPC_E_RANGE;

@@ -36,7 +36,7 @@ class MonteCarlo:
     def __init__(self, bank_params, table, x_init, projidx_init, plant_params, drop_start, V=None, W=20, K_models=10,
                  K_seq=32, H=20, Ts=0.02, scale=0.9, mu_init=1.0, seed=4, sigma_pwm=0.1, sigma_steer=0.05,
                  drop_rate=1.0 / 22.0, drop_len=0.2, initial_model=0, smoothing_mu=20, mu_alpha=0.08, limits=None,
-                 lookback_mode="rolling", use_graphs=False, fast_sin=None, lookback_kernel=None):
+                 lookback_mode="rolling", use_graphs=False, fast_sin=None, lookback_kernel=None, overlap="lookback_first"):
         torch = _lib.require_cuda()
         self.torch, self.L = torch, _lib.lib()
         self.bank = bank_params if isinstance(bank_params, ModelBank) else ModelBank(bank_params)
@@ -115,9 +115,18 @@ class MonteCarlo:
         self.t_dev = torch.zeros((), dtype=f64, device=dev)
         self.use_graphs = bool(use_graphs)
         self._graphs = {}                                          # ring slot -> captured tick (steady state only)
-        # planner + control sampling of the next tick run beside the look-back of this one (high-priority side stream: the
-        # planner's few latency-bound CTAs must get their SM slots before the look-back fills the machine)
-        self._side = torch.cuda.Stream(device=dev, priority=-1)
+        # planner + control sampling of the next tick run beside the look-back of this one, on a side stream.
+        #   overlap = "lookback_first" (default): the look-back is enqueued first on the main stream, the planner and the
+        #       control sampling follow on a side stream of the same priority and take the SM slots the look-back's last
+        #       wave leaves free (measured, graph replay: 210 us per tick; with a high-priority side stream the planner's
+        #       CTAs displace look-back CTAs and stretch it from 98 to 131 us: 228 us);
+        #   "plan_first": the round-1 order (planner on a high-priority stream ahead of the look-back: right for the old
+        #       32-CTA planner, but the 512-CTA planner then takes every SM's shared memory first and delays the look-back);
+        #   "none": everything on one stream.
+        if overlap not in ("lookback_first", "plan_first", "none"):
+            raise ValueError("overlap must be 'lookback_first', 'plan_first' or 'none'")
+        self.overlap = overlap
+        self._side = torch.cuda.Stream(device=dev, priority=-1 if overlap == "plan_first" else 0)
         with torch.cuda.device(self.dev):
             self._plan(torch.cuda.current_stream().cuda_stream, 0)   # the plan of tick 0
 
@@ -193,23 +202,47 @@ class MonteCarlo:
                 chk(L.llampc_mu_estimate_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.Km, 0, bank.bank64.data_ptr(),
                                              bank.N, V, self.smoothing, self.mu_alpha, 0.95, 9.81, self.mu_state.data_ptr(),
                                              self.mu_pred.data_ptr(), self.mu_display.data_ptr(), st), "mu_estimate")
-            # fork: x <- x_next, t += Ts, plan of the next tick on the side stream (launched first) ...
-            side = self._side
-            side.wait_stream(main)
-            ss = side.cuda_stream
-            chk(L.llampc_mc_advance_tick_f64(None, 0, None, self.x.data_ptr(), self.x_next.data_ptr(), V,
-                                             self.t_dev.data_ptr(), self.Ts, ss), "advance tick")
-            self._plan(ss, idt + 1)
-            # ... beside the look-back of this tick on the main stream
+            # fork: x <- x_next, t += Ts and the plan of the next tick on the side stream, beside the look-back of this tick
+            # on the main stream (the look-back reads the history rings, not x)
+            side = main if self.overlap == "none" else self._side
             full = idt >= self.W
-            if pushing and self.rolling:
-                self.lb.launch(st, slot=slot, emit=int(full))
-            elif pushing and full:
-                self.lb.launch(st)
+
+            def lookback():
+                if pushing and self.rolling:
+                    self.lb.launch(st, slot=slot, emit=int(full))
+                elif pushing and full:
+                    self.lb.launch(st)
+
+            def plan_next():
+                if side is not main:
+                    side.wait_stream(main)
+                ss = side.cuda_stream
+                chk(L.llampc_mc_advance_tick_f64(None, 0, None, self.x.data_ptr(), self.x_next.data_ptr(), V,
+                                                 self.t_dev.data_ptr(), self.Ts, ss), "advance tick")
+                self._plan(ss, idt + 1)
+
+            if self.overlap == "plan_first":
+                plan_next()
+                lookback()
+            else:
+                fork = None
+                if side is not main:                               # the side work depends on the tick so far, not on the look-back
+                    fork = torch.cuda.Event()
+                    fork.record(main)
+                lookback()
+                if fork is not None:
+                    side.wait_event(fork)
+                    ss = side.cuda_stream
+                    chk(L.llampc_mc_advance_tick_f64(None, 0, None, self.x.data_ptr(), self.x_next.data_ptr(), V,
+                                                     self.t_dev.data_ptr(), self.Ts, ss), "advance tick")
+                    self._plan(ss, idt + 1)
+                else:
+                    plan_next()
             if full:                                               # the model of the next tick's look-ahead
                 chk(L.llampc_mc_advance_tick_f64(self.topk.data_ptr(), _lib.LIST_LEN + 1, self.model_idx.data_ptr(), None,
                                                  None, V, None, self.Ts, st), "model index")
-            main.wait_stream(side)                                 # join
+            if side is not main:
+                main.wait_stream(side)                             # join
 
     def run(self, n):
         for _ in range(n):

@@ -36,7 +36,7 @@ class Timed:
 
         def call(*a):
             rc = fn(*a)
-            tag, s = streams.get(a[-1], ("?", None))
+            tag, s = streams.get(a[-1], ("?", None)) if isinstance(a[-1], int) else ("?", None)
             if s is not None:
                 ev = torch.cuda.Event(enable_timing=True)
                 ev.record(s)
@@ -46,6 +46,7 @@ class Timed:
 
 
 mc.L = Timed(mc.L)
+mc.lb._L = Timed(mc.lb._L)                           # the look-back launch goes through LookbackLaunch
 for rep in range(3):
     log.clear()
     t0 = torch.cuda.Event(enable_timing=True)
