@@ -94,6 +94,8 @@ int llampc_hist_row_pack_h(const double* x_k, const double* u_k, const double* x
 #define LLAMPC_KERNEL_K1B   3   /* persistent warp-task window kernel (single history, few CTAs x long windows)            */
 #define LLAMPC_KERNEL_K1R   4   /* rolling kernel, grid over (candidates, vehicles)                                         */
 #define LLAMPC_KERNEL_K1V   5   /* rolling kernel, one CTA per vehicle (N <= 2,048, Npad % 4 == 0), in-CTA top-K           */
+#define LLAMPC_KERNEL_K1E   6   /* packed window kernel on equal warp shares: one 512-thread CTA per SM, every warp the same
+                                   number of (64 candidates x 1 row) steps (single history, merge tree); on request only   */
 
 typedef struct llampc_lookback_desc {
     /* bank: packed (llampc_bank_pack_h layout), device, 16-byte aligned; keys carry idx_offset + i */
@@ -134,7 +136,7 @@ typedef struct llampc_lookback_desc {
 
 typedef struct llampc_lookback_plan {
     int kernel;                  /* LLAMPC_KERNEL_* that a launch of this descriptor runs                                   */
-    int split;                   /* window splits per candidate (K1 / K1P), rows per task (K1B), else 1                     */
+    int split;                   /* window splits per candidate (K1 / K1P), rows per task (K1B), else 1 (K1E: 1)            */
     int sine;                    /* LLAMPC_SIN_SFU or LLAMPC_SIN_STRICT after resolving LLAMPC_SIN_AUTO                     */
     int grid_x, grid_y, block;
     int launches;                /* kernel launches per call: 1, or 2 when a vehicle has more than 1,024 per-CTA lists      */

@@ -65,8 +65,8 @@ class LookbackPlan(C.Structure):
 
 LB_RECOMPUTE, LB_ROLLING = 0, 1
 SIN_AUTO, SIN_SFU, SIN_STRICT = 0, 1, 2
-KERNEL_AUTO, KERNEL_K1, KERNEL_K1P, KERNEL_K1B, KERNEL_K1R, KERNEL_K1V = range(6)
-KERNEL_NAMES = ("auto", "K1", "K1p", "K1b", "K1r", "K1v")
+KERNEL_AUTO, KERNEL_K1, KERNEL_K1P, KERNEL_K1B, KERNEL_K1R, KERNEL_K1V, KERNEL_K1E = range(7)
+KERNEL_NAMES = ("auto", "K1", "K1p", "K1b", "K1r", "K1v", "K1e")
 SIN_NAMES = ("auto", "MUFU.SIN", "strict polynomial")
 E_PEER = -4
 

@@ -53,6 +53,8 @@ struct LibEnv {
     long long bal_tpw;       // LLAMPC_BAL_TPW: K1b target tasks per resident warp
     long long bal_rmin, bal_rmax;   // LLAMPC_BAL_RMIN / RMAX: K1b rows per task bounds
     int bal_verbose, bal_trace, bal_nofence;
+    long long eq_ctas;       // LLAMPC_EQ_CTAS: K1e CTAs per SM x 100 (0 = occupancy)
+    long long eq_stagger;    // LLAMPC_EQ_STAGGER: K1e start offset in clocks between the warps of a scheduler
 };
 const LibEnv& lib_env();                           // defined in lookback.cu
 

@@ -15,17 +15,21 @@ struct Cand {
     float Bf, Cf, Df, Br, Cr, Dr, inv_m, lf, lr, lf_Iz, lr_Iz, Cm1, Cm2, Cr0, Cr2;
 };
 
-__device__ __forceinline__ Cand load_cand(const float4* __restrict__ bank, int Npad, int i) {
-    float4 g0 = __ldg(bank + i);
-    float4 g1 = __ldg(bank + Npad + i);
-    float4 g2 = __ldg(bank + 2 * Npad + i);
-    float4 g3 = __ldg(bank + 3 * Npad + i);
+__device__ __forceinline__ Cand cand_from_groups(const float4& g0, const float4& g1, const float4& g2, const float4& g3) {
     Cand c;
     c.Bf = g0.x; c.Cf = g0.y; c.Df = g0.z; c.Br = g0.w;
     c.Cr = g1.x; c.Dr = g1.y; c.inv_m = g1.z; c.lf = g1.w;
     c.lr = g2.x; c.lf_Iz = g2.y; c.lr_Iz = g2.z; c.Cm1 = g2.w;
     c.Cm2 = g3.x; c.Cr0 = g3.y; c.Cr2 = g3.z;
     return c;
+}
+
+__device__ __forceinline__ Cand load_cand(const float4* __restrict__ bank, int Npad, int i) {
+    float4 g0 = __ldg(bank + i);
+    float4 g1 = __ldg(bank + Npad + i);
+    float4 g2 = __ldg(bank + 2 * Npad + i);
+    float4 g3 = __ldg(bank + 3 * Npad + i);
+    return cand_from_groups(g0, g1, g2, g3);
 }
 
 struct Ctl { float pwm, delta, sd, cd; };      // input and sin/cos of the steering angle

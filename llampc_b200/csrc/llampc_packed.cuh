@@ -42,8 +42,7 @@ struct Cand2 {
     F2 Bf, Cf, Df, Br, Cr, Dr, inv_m, lf, nlr, lf_Iz, lr_Iz, Cm1, Cm2, nCr0, nCr2;
 };
 
-__device__ __forceinline__ Cand2 load_cand2(const float4* __restrict__ bank, int Npad, int i0, int i1) {
-    const Cand a = load_cand(bank, Npad, i0), b = load_cand(bank, Npad, i1);
+__device__ __forceinline__ Cand2 make_cand2(const Cand& a, const Cand& b) {
     Cand2 c;
     c.Bf = pk(a.Bf, b.Bf); c.Cf = pk(a.Cf, b.Cf); c.Df = pk(a.Df, b.Df);
     c.Br = pk(a.Br, b.Br); c.Cr = pk(a.Cr, b.Cr); c.Dr = pk(a.Dr, b.Dr);
@@ -51,6 +50,10 @@ __device__ __forceinline__ Cand2 load_cand2(const float4* __restrict__ bank, int
     c.lf_Iz = pk(a.lf_Iz, b.lf_Iz); c.lr_Iz = pk(a.lr_Iz, b.lr_Iz);
     c.Cm1 = pk(a.Cm1, b.Cm1); c.Cm2 = pk(a.Cm2, b.Cm2); c.nCr0 = pk(-a.Cr0, -b.Cr0); c.nCr2 = pk(-a.Cr2, -b.Cr2);
     return c;
+}
+
+__device__ __forceinline__ Cand2 load_cand2(const float4* __restrict__ bank, int Npad, int i0, int i1) {
+    return make_cand2(load_cand(bank, Npad, i0), load_cand(bank, Npad, i1));
 }
 
 // atan(t), |t| <= 0.5 (atan_half)

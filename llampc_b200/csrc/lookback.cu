@@ -36,6 +36,8 @@ const LibEnv& lib_env() {
         e.bal_verbose = getenv("LLAMPC_BAL_VERBOSE") != nullptr;
         e.bal_trace = getenv("LLAMPC_BAL_TRACE") != nullptr;
         e.bal_nofence = getenv("LLAMPC_BAL_NOFENCE") != nullptr;
+        e.eq_ctas = env_ll("LLAMPC_EQ_CTAS", 0);
+        e.eq_stagger = env_ll("LLAMPC_EQ_STAGGER", 0);
         return e;
     }();
     return env;
@@ -417,6 +419,15 @@ static int resolve_plan(const llampc_lookback_desc_t& d, LbPlan& p) {
             p.grid_x = 0;                          // persistent grid: SMs x resident CTAs
             return 0;
         }
+        if (kernel == LLAMPC_KERNEL_K1E) {
+            size_t b = 0;
+            const int rc = lookback_equal_plan(d.N, d.W, &p.grid_x, &p.block, &b, &p.lay);
+            if (rc) return rc;
+            p.kernel = kernel;
+            p.split = 1;
+            p.bytes = b;
+            return 0;
+        }
         if (kernel != LLAMPC_KERNEL_K1 && kernel != LLAMPC_KERNEL_K1P) return LLAMPC_E_ARG;
         p.kernel = kernel;
         p.lay = tree_layout(d.N, 0);
@@ -491,6 +502,9 @@ static int lookback_launch_planned(const llampc_lookback_desc_t& d, const LbPlan
         if (rc || p.launches == 1) return rc;
         return merge_lists_launch(lists, p.n_lists, d.n_vehicles, d.K, d.out, st);
     }
+    if (p.kernel == LLAMPC_KERNEL_K1E)
+        return lookback_equal_launch(bank, d.N, d.Npad, d.hist, d.W, z, d.avg_err, d.idx_offset, geom, mufu, d.K, d.workspace,
+                                     d.workspace_bytes, d.out, nr, px, st);
     if (p.kernel == LLAMPC_KERNEL_K1B)
         return lookback_balanced_launch(d.bank, d.N, d.Npad, d.hist, d.W, d.Ts, d.avg_err, d.idx_offset, geom, mufu, d.K,
                                         d.workspace, d.workspace_bytes, d.out, nr, px, st);

@@ -27,6 +27,12 @@ static inline int k1_cands_per_cta(bool packed, int sy) { return (packed ? 2 * L
 int launch_k1_scalar(const LbArgs& a, int sy, bool geom, bool mufu, cudaStream_t st);      // lookback_k1.cu
 int launch_k1_packed(const LbArgs& a, int sy, bool geom, bool mufu, cudaStream_t st);      // lookback_k1p.cu
 
+// K1e: packed window kernel on equal warp shares, single history, merge tree (lookback_k1e.cu)
+int lookback_equal_plan(int N, int W, int* grid, int* block, size_t* bytes, TreeLayout* lay);
+int lookback_equal_launch(const float4* bank, int N, int Npad, const float* hist, int W, const StepSize& z, float* avg_err,
+                          int idx_offset, bool geom, bool mufu, int K, void* workspace, unsigned long long workspace_bytes,
+                          u64* out, const NewRow& nr, const PeerXchg& px, cudaStream_t st);
+
 // K1r / K1v: rolling window (lookback_rolling.cu)
 constexpr int RV_THREADS = 256;
 constexpr int RV_WARPS = RV_THREADS / 32;

@@ -33,7 +33,7 @@ def decode_keys(keys):
 _SINE = {None: _lib.SIN_AUTO, "auto": _lib.SIN_AUTO, "sfu": _lib.SIN_SFU, "strict": _lib.SIN_STRICT,
          True: _lib.SIN_SFU, False: _lib.SIN_STRICT}
 _KERNEL = {None: 0, "auto": 0, "k1": _lib.KERNEL_K1, "k1p": _lib.KERNEL_K1P, "k1b": _lib.KERNEL_K1B,
-           "k1r": _lib.KERNEL_K1R, "k1v": _lib.KERNEL_K1V}
+           "k1r": _lib.KERNEL_K1R, "k1v": _lib.KERNEL_K1V, "k1e": _lib.KERNEL_K1E}
 
 
 def sine_mode(fast_sin):

@@ -759,13 +759,13 @@ def test_montecarlo_closed_loop_stagewise_parity(lookback_mode):
         projidx_before_plan = pre["projidx"].copy()
 
 
-@pytest.mark.parametrize("kernel", ["k1", "k1b"])
+@pytest.mark.parametrize("kernel", ["k1", "k1b", "k1e"])
 @pytest.mark.parametrize("N,W,K,t_end", [(1, 1, 10, 600), (5, 3, 10, 100), (300, 7, 16, 600), (777, 1, 10, 1100),
                                          (3000, 50, 10, 1600), (5000, 10, 16, 600), (2049, 33, 1, 900),
                                          (4096, 256, 10, 1200), (40000, 20, 10, 600)])
 def test_tree_tick_kernels_match_oracle(history, kernel, N, W, K, t_end):
-    """llampc_lookback_launch on one history (one launch: K1 with the tree merge, or the persistent warp-task kernel
-    K1b, forced through the descriptor) at ragged sizes: scores within tolerance of the float64 oracle, out[0] ==
+    """llampc_lookback_launch on one history (one launch: K1 with the tree merge, the persistent warp-task kernel K1b, or
+    the packed equal-share kernel K1e, forced through the descriptor) at ragged sizes: scores within tolerance of the float64 oracle, out[0] ==
     out[1], the top-K is exactly the K smallest (score, index) pairs of the kernel's own scores, and a second launch on
     the same workspace (self-resetting counters) reproduces the first bit for bit."""
     import torch
