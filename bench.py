@@ -31,6 +31,8 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
+RF_READS_PER_WARP_STEP = 1231          # register source operands of the K1p loop body (tools/sass_reg_reads.py)
+RF_READS_PER_CLK = 1.86                # measured per scheduler (tools/ubench/ffma2_operands.cu)
 F_ALG = 652.0            # FP32 flop per candidate-RK4-step (SURVEY.md 8(d) convention)
 S_ALG = 40.0             # SFU-class ops per step (same convention)
 NPARAM_PACKED = 16       # floats per candidate in the packed bank
@@ -455,6 +457,19 @@ def run_b200(args):
                         "peak_GBs": peaks.get("hbm_gbs", 6650.0), "peak_kind": "measured" if peaks else "fallback"}}
     if clocks.get("sm_mhz"):
         roofline["frac_at_observed_clock"] = achieved / (148 * 128 * 2 * clocks["sm_mhz"] * 1e6 / 1e12)
+    if tick.kernel_name == "K1p":
+        # What actually binds the packed step (profiles/r02_register_bandwidth.md): a B200 scheduler delivers ~1.86 32-bit
+        # register source operands per clock (tools/ubench/ffma2_operands.cu: FFMA2 with three distinct register pairs
+        # issues every 3.2 clocks, not 2), and the loop body of K1p reads 1,231 of them per warp-step of 64 candidate-steps
+        # (tools/sass_reg_reads.py on the shipped library) against 559 FMA-pipe clocks.
+        reads = n_local * W_C2 / 64.0 * RF_READS_PER_WARP_STEP
+        cap = 148 * 4 * RF_READS_PER_CLK * sm_max * 1e6 * k1_avg_s
+        roofline["register_file"] = {"reads_per_warp_step": RF_READS_PER_WARP_STEP, "peak_reads_per_clk_per_scheduler": RF_READS_PER_CLK,
+                                     "frac_whole_launch": reads / cap,
+                                     "clocks_per_warp_step_bound": RF_READS_PER_WARP_STEP / RF_READS_PER_CLK,
+                                     "fma_pipe_clocks_per_warp_step": 559,
+                                     "source": "tools/sass_reg_reads.py (SASS of the shipped K1p loop) and "
+                                               "tools/ubench/ffma2_operands.cu (profiles/r02_register_bandwidth.md)"}
     # SM clock sustained under an FMA-bound load (clock64 against globaltimer, ~300 us of work on every SM)
     try:
         probe = torch.zeros(2, dtype=torch.int64, device=dev)
