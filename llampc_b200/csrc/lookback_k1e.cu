@@ -42,7 +42,7 @@ constexpr int EQ_STAGE_BYTES = 2 * 8 * 32 * 16;    // per warp: two buffers of 8
 
 struct EqSched {
     long long L;        // warp-steps = groups x W
-    int n_warps;        // resident warps = grid x 4
+    int n_warps;        // warps that take a share (= resident warps unless the problem is tiny)
     int n_groups;       // ceil(N / 64)
     int maxch;          // scratch rows per group (upper bound of the warps a group can be spread over)
     int stagger;        // experiments: warps sharing a scheduler start this many clocks apart
@@ -94,8 +94,9 @@ lookback_equal_kernel(const float4* __restrict__ bank, int N, int Npad, const fl
     __syncthreads();
 
     // this warp's share of the linearised (group, row) space
-    long long lo = (long long)gw * sch.L / sch.n_warps;
-    const long long hi = (long long)(gw + 1) * sch.L / sch.n_warps;
+    // (small problems: only the first n_warps warps of the grid take a share, each of at least four steps)
+    long long lo = gw < sch.n_warps ? (long long)gw * sch.L / sch.n_warps : 0;
+    const long long hi = gw < sch.n_warps ? (long long)(gw + 1) * sch.L / sch.n_warps : 0;
     int g = (int)(lo / W);
     int r = (int)(lo - (long long)g * W);
     Cand2 p;
@@ -286,6 +287,7 @@ static int eq_plan(int N, int W, EqPlan& pl) {
     if (G < 1) G = 1;
     pl.grid = (int)G;
     s.n_warps = pl.grid * EQ_WARPS;
+    if (s.n_warps > s.L / 4) s.n_warps = s.L / 4 > 0 ? (int)(s.L / 4) : 1;      // every sharing warp gets >= 4 steps (or all of them)
     const long long per = s.L / s.n_warps > 0 ? s.L / s.n_warps : 1;      // every warp's range holds >= per steps
     long long maxch = (W + per - 1) / per + 1;
     if (maxch > s.n_warps) maxch = s.n_warps;
