@@ -124,7 +124,8 @@ typedef struct llampc_lookback_desc {
     /* multi-GPU (single history, RECOMPUTE): min-loc of out[0] across the GPUs of the box over NVLink peer memory, done by
        the warp that finishes the rank's merge tree, inside the same launch (no NCCL call on the path).
        peer_bufs: device array [world] of pointers, peer_bufs[q] = rank q's symmetric exchange buffer of 4 * world u64 words
-       ([2 parities][world][key, sequence]), zero-initialised and mapped into this process (CUDA IPC / torch symmetric
+       ([2 parities][world][2]: word 0 = low half of the key | seq << 32, word 1 = high half of the key | seq << 32 -- two
+       self-validating 8-byte remote stores per peer, no system-scope fence), zero-initialised and mapped into this process (CUDA IPC / torch symmetric
        memory).  seq: tick counter >= 1, identical on every rank, incremented by the caller every call.  After the launch
        out[0] is the GLOBAL arg-min key on every rank (~0ull = no decision: a peer did not arrive within ~1 s);
        out[1..K] stay the rank-local top-K.  NULL = single GPU.                                                             */

@@ -54,31 +54,36 @@ struct NewRow { float v[LLAMPC_HIST_ROW]; int slot; };
 struct FusedMerge { unsigned* ticket; u64* out; int K; };
 
 // Optional multi-GPU min-loc fused into the same launch, over NVLink peer memory (no NCCL call on the path): every
-// rank owns a small symmetric buffer [2 parities][world][2] of u64 (key, sequence); the last CTA of rank r stores its
-// packed arg-min key into slot r of EVERY peer's buffer (remote 8-byte stores), then spins on its own buffer until all
-// `world` slots carry the current sequence number and reduces them.  Double-buffered by the parity of `seq`, which the
-// host increments identically on every rank each tick.  world = 0 disables it.
+// rank owns a small symmetric buffer [2 parities][world][2] of u64; the root warp of rank r stores its packed arg-min key
+// into slot r of EVERY peer's buffer, then spins on its own buffer until all `world` slots carry the current sequence
+// number and reduces them.  The two words of a slot are self-validating ("LL" style): word 0 = (low half of the key,
+// sequence), word 1 = (high half of the key, sequence), each an atomic 8-byte remote store -- no system-scope fence between
+// data and flag, so the exchange costs ONE NVLink traversal instead of a fence round trip plus a traversal.
+// Double-buffered by the parity of `seq`, which the host increments identically on every rank each tick (never 0: the
+// buffers start zeroed).  world = 0 disables it.
 struct PeerXchg { u64* const* peers; int world; int rank; unsigned seq; };
 
 // A peer that never arrives (~1 s) POISONS the result: every lane then returns ~0ull -- "no candidate", which no valid
 // key equals -- instead of a plausible wrong winner; the host side turns it into LLAMPC_E_PEER.
 __device__ __forceinline__ u64 peer_minloc(const PeerXchg& px, u64 my_key, int lane) {
     const int parity = px.seq & 1;
+    const u64 tag = (u64)px.seq << 32;
     u64 got = ~0ull;
     bool ok = true;
     if (lane < px.world) {
         volatile u64* dst = px.peers[lane] + ((size_t)parity * px.world + px.rank) * 2;
-        dst[0] = my_key;
-        __threadfence_system();
-        dst[1] = (u64)px.seq;
+        dst[0] = tag | (my_key & 0xffffffffull);
+        dst[1] = tag | (my_key >> 32);
         volatile u64* src = px.peers[px.rank] + ((size_t)parity * px.world + lane) * 2;
         const long long t0 = clock64();
-        while (src[1] != (u64)px.seq) {
+        u64 w0, w1;
+        for (;;) {
+            w0 = src[0];
+            w1 = src[1];
+            if ((w0 >> 32) == (u64)px.seq && (w1 >> 32) == (u64)px.seq) break;
             if (clock64() - t0 > 2000000000ll) { ok = false; break; }     // ~1 s: a peer never arrived
-            __nanosleep(64);
         }
-        __threadfence_system();
-        if (ok) got = src[0];
+        if (ok) got = (w1 << 32) | (w0 & 0xffffffffull);
     }
     if (!__all_sync(0xffffffffu, ok)) return ~0ull;
     return warp_min_key(got);

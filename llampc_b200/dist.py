@@ -74,5 +74,5 @@ class PeerExchange:
         self.seq = 0
 
     def next_seq(self):
-        self.seq += 1
+        self.seq = self.seq % 0xFFFFFFFF + 1                       # 32-bit on the device, never 0 (the buffers start zeroed)
         return self.seq
