@@ -205,7 +205,8 @@ typedef struct llampc_tick {
                                        word instead of a D2H copy + stream synchronisation                        */
     llampc_key_t* const* peer_bufs; /* multi-GPU finalist all-gather over NVLink peer memory (needs n_refine > 0 and
                                        zero_copy): device array [peer_world] of every rank's symmetric buffer of
-                                       2 * peer_world * (2*Kt + 1) zeroed words; result_h then needs 2 + 2*Kt*peer_world
+                                       2 * peer_world * 4*Kt zeroed words (every 64-bit payload travels as two
+                                       self-validating 8-byte words: half | seq << 32); result_h then needs 2 + 2*Kt*peer_world
                                        words.  The ordered finalists returned are the GLOBAL ones; a peer that does not
                                        deliver within ~1 s makes llampc_lookback_finish return LLAMPC_E_PEER.  NULL = single GPU */
     int peer_world; int peer_rank;

@@ -221,34 +221,41 @@ refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__
         __threadfence();
         int words = fc.words;
         if (pg.world > 1) {
-            // fc.src = [arg-min key | Kt keys | Kt scores]; exchange the 2 Kt finalist words with every peer
-            const int wpr = 2 * pg.kt + 1, parity = pg.seq & 1;
+            // fc.src = [arg-min key | Kt keys | Kt scores]; exchange the 2 Kt finalist words with every peer.  Every
+            // 64-bit payload travels as two self-validating 8-byte words (low half | seq << 32, high half | seq << 32):
+            // no system-scope fence between data and flag, the receiver polls the words themselves (one NVLink traversal)
+            const int npay = 2 * pg.kt, wpr = 2 * npay, parity = pg.seq & 1;
             const size_t my_slot = ((size_t)parity * pg.world + pg.rank) * wpr;
-            for (int i = tid; i < 2 * pg.kt * pg.world; i += RF_THREADS) {
-                const int q = i / (2 * pg.kt), j = i % (2 * pg.kt);
-                reinterpret_cast<volatile u64*>(pg.peers[q])[my_slot + j] = __ldcg(fc.src + 1 + j);
-            }
-            __threadfence_system();
-            __syncthreads();
+            const u64 tag = (u64)pg.seq << 32;
             if (tid == 0) peer_fail = 0;
-            __syncthreads();
-            if (tid < pg.world) {
-                reinterpret_cast<volatile u64*>(pg.peers[tid])[my_slot + 2 * pg.kt] = (u64)pg.seq;
-                volatile u64* own = pg.peers[pg.rank] + ((size_t)parity * pg.world + tid) * wpr;
-                const long long t0 = clock64();
-                while (own[2 * pg.kt] != (u64)pg.seq) {
-                    if (clock64() - t0 > 2000000000ll) { peer_fail = 1; break; }   // ~1 s: the peer never arrived
-                    __nanosleep(64);
-                }
+            for (int i = tid; i < npay * pg.world; i += RF_THREADS) {
+                const int q = i / npay, j = i % npay;
+                const u64 v = __ldcg(fc.src + 1 + j);
+                volatile u64* dst = reinterpret_cast<volatile u64*>(pg.peers[q]) + my_slot + 2 * j;
+                dst[0] = tag | (v & 0xffffffffull);
+                dst[1] = tag | (v >> 32);
             }
-            __threadfence_system();
             __syncthreads();
             fc.dst_host[0] = __ldcg(fc.src);
             volatile u64* own = pg.peers[pg.rank] + (size_t)parity * pg.world * wpr;
-            const bool failed = peer_fail != 0;                    // poison: keys ~0, scores NaN, and the flag below
-            for (int i = tid; i < 2 * pg.kt * pg.world; i += RF_THREADS) {
-                const int q = i / (2 * pg.kt), j = i % (2 * pg.kt);
-                fc.dst_host[1 + i] = failed ? ~0ull : own[(size_t)q * wpr + j];
+            for (int i = tid; i < npay * pg.world; i += RF_THREADS) {
+                const int q = i / npay, j = i % npay;
+                volatile u64* src = own + (size_t)q * wpr + 2 * j;
+                const long long t0 = clock64();
+                u64 w0, w1;
+                bool ok = true;
+                for (;;) {
+                    w0 = src[0];
+                    w1 = src[1];
+                    if ((w0 >> 32) == (u64)pg.seq && (w1 >> 32) == (u64)pg.seq) break;
+                    if (clock64() - t0 > 2000000000ll) { ok = false; break; }      // ~1 s: the peer never arrived
+                }
+                if (!ok) peer_fail = 1;
+                fc.dst_host[1 + i] = ok ? ((w1 << 32) | (w0 & 0xffffffffull)) : ~0ull;
+            }
+            __syncthreads();
+            if (peer_fail) {                                           // poison everything: keys ~0, scores NaN
+                for (int i = tid; i < npay * pg.world; i += RF_THREADS) fc.dst_host[1 + i] = ~0ull;
             }
             words = 1 + 2 * pg.kt * pg.world;
         } else {

@@ -180,7 +180,7 @@ class LookBack:
             if td.get_backend(group) == "nccl":
                 try:                                             # NVLink peer-memory finalist gather (no NCCL per tick)
                     w = td.get_world_size(group)
-                    self._peer = _dist.PeerExchange(group, dev, words=2 * w * (2 * self.Kt + 1))
+                    self._peer = _dist.PeerExchange(group, dev, words=2 * w * 4 * self.Kt)
                     words = max(words, 2 + 2 * self.Kt * w)
                 except Exception:                                # symmetric memory unavailable: NCCL all-gather path
                     self._peer = None
