@@ -242,3 +242,31 @@ def test_threshold_filter_selection_argument():
         want = np.sort(keys[:n])[:K]
         assert len(survivors) >= min(K, n)
         assert np.array_equal(survivors[:K], want), (n, K)
+
+
+def test_equal_share_partition_argument():
+    """The work partition of K1e (lookback_equal_kernel) restated in Python: the (group of 64
+    candidates) x (window row) space of L = G W steps is cut into n_warps contiguous ranges [w L / n, (w + 1) L / n); only
+    L / 4 warps take a share on tiny problems.  Checked for every shape: the ranges tile the space exactly, every sharing warp
+    has work, the closed forms the kernel uses for 'first / last warp of a group' -- ((x + 1) n - 1) / L -- name the true
+    owners, every warp between them holds a piece of the group (so the arrival count of a group is wl - wf + 1), and the
+    scratch bound maxch holds."""
+    EQ_WARPS, SMS = 16, 148
+    for G in list(range(1, 24)) + [100, 1024, 2048]:
+        for W in list(range(1, 12)) + [20, 50, 64]:
+            L = G * W
+            grid = max(1, min(SMS, (L + 4 * EQ_WARPS - 1) // (4 * EQ_WARPS)))
+            n = grid * EQ_WARPS
+            if n > L // 4:
+                n = max(1, L // 4)
+            lo = [w * L // n for w in range(n + 1)]
+            assert lo[0] == 0 and lo[-1] == L and all(b > a for a, b in zip(lo, lo[1:]))
+            owner = np.repeat(np.arange(n), np.diff(lo))
+            per = max(L // n, 1)
+            maxch = min((W + per - 1) // per + 1, n)
+            for g in range(G):
+                x0 = g * W
+                wf, wl = ((x0 + 1) * n - 1) // L, ((x0 + W) * n - 1) // L
+                assert owner[x0] == wf and owner[x0 + W - 1] == wl
+                assert wl - wf + 1 <= maxch
+                assert np.array_equal(np.unique(owner[x0:x0 + W]), np.arange(wf, wl + 1))
