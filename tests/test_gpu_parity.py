@@ -1002,6 +1002,25 @@ def test_peer_minloc_two_gpus():
     assert res.stdout.count(": OK") == 2
 
 
+def test_dist_push_two_gpus():
+    """LookBack.push(group=...) on 2 ranks with a sharded bank: the finalist all-gather over NVLink peer memory (self-validating
+    words polled by the receiver, inside the fp64 re-score kernel) must return, on every rank, the arg-min / top-10 / best error
+    of the float64 oracle on the whole bank, in recompute and in rolling mode (tools/gpu_dist_push.py; skipped on single-GPU
+    boxes)."""
+    import os
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29573", os.path.join(root, "tools", "gpu_dist_push.py")]
+    res = subprocess.run(cmd, capture_output=True, text=True, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+    assert res.stdout.count(": OK") >= 4 and "FAIL" not in res.stdout and "MISMATCH" not in res.stdout
+
+
 def test_replay_reference_loop_settings(history):
     """The reference script's own settings (N_MODELS 5000, W 10, top-10 mu estimate) replayed over 400 recorded ticks:
     identical model-selection sequence and friction-estimate sequence as the NumPy loop."""
