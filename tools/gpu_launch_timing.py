@@ -44,7 +44,7 @@ for i in range(W if mode == "rolling" else 3):
 torch.cuda.synchronize()
 evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(reps)]
 for i, (a, b) in enumerate(evs):
-    flush.fill_(1)
+    flush.add_(1)
     a.record()
     lb.launch(slot=i % W) if mode == "rolling" else lb.launch()
     b.record()
