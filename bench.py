@@ -367,7 +367,10 @@ def run_b200(args):
             peer = None
     # the tick: ONE launch (scores + per-CTA lists + in-kernel merge tree -> arg-min and top-10; for N > 1 the root of the
     # tree also runs the NVLink min-loc); sine mode and kernel are the library's automatic choices, reported below
-    tick = LookbackLaunch(bank, hist, W_C2, TS, K=10, idx_offset=lo, avg_err=avg_err, peer=peer)
+    # (programmatic dependent launch: in the back-to-back timed region the bank loads and RK4 rows of tick t + 1 start beside
+    # the selection / merge-tree tail of tick t; LLAMPC_BENCH_PDL=0 turns it off)
+    use_pdl = os.environ.get("LLAMPC_BENCH_PDL", "1") == "1"
+    tick = LookbackLaunch(bank, hist, W_C2, TS, K=10, idx_offset=lo, avg_err=avg_err, peer=peer, pdl=use_pdl)
     scores_only = LookbackLaunch(bank, hist, W_C2, TS, K=0, idx_offset=lo, avg_err=avg_err)
     assert tick.plan.launches == 1
 
@@ -619,6 +622,8 @@ def run_b200(args):
             "dtype": "f32", "data": "synthetic", "config": workload_config(world),
             "tyre_sine": "%s (chosen by the library from the bank: max |C| pi/2 = %.2f rad <= pi)" % (tick.sine_name, bank.sin_arg_max),
             "gpu_launches": args.steps * tick.plan.launches, "clocks": clocks, "roofline": roofline, "parity": parity,
+            "launch_overlap": ("programmatic dependent launch: the bank loads and RK4 rows of tick t + 1 run beside the selection / "
+                               "merge-tree tail of tick t (LLAMPC_LB_FLAG_PDL)") if use_pdl else "none (stream order)",
             "l2_flushed": l2_flushed}
     if world > 1:
         line["exchange"] = "nvlink-peer-memory min-loc inside the kernel" if peer is not None else "nccl all_reduce(MIN) of the packed key"
@@ -663,7 +668,7 @@ def c5_single_gpu(torch, _lib, S, U, flush, with_push=False):
     lb = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=16)
     ts = np.arange(0, W_C2)
     lb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
-    ll = LookbackLaunch(bank, lb.hist, W_C2, TS, K=10, avg_err=lb.avg_err)
+    ll = LookbackLaunch(bank, lb.hist, W_C2, TS, K=10, avg_err=lb.avg_err, pdl=os.environ.get("LLAMPC_BENCH_PDL", "1") == "1")
     dt_flushed = _time_it(torch, flush, ll.launch, 20)
     # the headline protocol: copies of the bank in rotation (larger than L2), ticks back to back between one pair of events
     reps = 20

@@ -19,7 +19,7 @@
 extern "C" {
 #endif
 
-#define LLAMPC_ABI_VERSION 5
+#define LLAMPC_ABI_VERSION 6
 
 #define LLAMPC_E_ARG   (-1)  /* null pointer / non-positive size / size not supported       */
 #define LLAMPC_E_ALIGN (-2)  /* pointer or stride not 16-byte aligned                        */
@@ -133,7 +133,15 @@ typedef struct llampc_lookback_desc {
     /* overrides (0 = automatic) */
     int kernel;                  /* LLAMPC_KERNEL_*: force a kernel the shape supports (else LLAMPC_E_ARG)                  */
     int split;                   /* window splits per candidate inside a CTA: 1, 2, 4, 8, 16 (K1 / K1P)                     */
+    int flags;                   /* LLAMPC_LB_FLAG_*                                                                        */
 } llampc_lookback_desc_t;
+
+/* Programmatic dependent launch (K1P, one history): the launch may begin -- bank loads, history staging, RK4 rows -- while
+   the PREVIOUS launch on the same stream is still in its selection / merge-tree tail (every CTA of a K1P launch signals
+   griddepcontrol.launch_dependents after its last RK4 row, and waits with griddepcontrol.wait for the previous grid to
+   complete before it writes avg_err, the workspace or `out`).  For back-to-back launches that do not depend on each
+   other's results (a sweep over banks); the results are identical. */
+#define LLAMPC_LB_FLAG_PDL 1
 
 typedef struct llampc_lookback_plan {
     int kernel;                  /* LLAMPC_KERNEL_* that a launch of this descriptor runs                                   */

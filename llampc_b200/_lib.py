@@ -54,7 +54,7 @@ class LookbackDesc(C.Structure):
                 ("K", _i), ("avg_err", _vp), ("out", _vp),
                 ("workspace", _vp), ("workspace_bytes", C.c_ulonglong),
                 ("peer_bufs", _vp), ("world", _i), ("rank", _i), ("seq", C.c_uint),
-                ("kernel", _i), ("split", _i)]
+                ("kernel", _i), ("split", _i), ("flags", _i)]
 
 
 class LookbackPlan(C.Structure):
@@ -69,6 +69,7 @@ KERNEL_AUTO, KERNEL_K1, KERNEL_K1P, KERNEL_K1B, KERNEL_K1R, KERNEL_K1V, KERNEL_K
 KERNEL_NAMES = ("auto", "K1", "K1p", "K1b", "K1r", "K1v", "K1e")
 SIN_NAMES = ("auto", "MUFU.SIN", "strict polynomial")
 E_PEER = -4
+LB_FLAG_PDL = 1
 
 # name -> (restype, argtypes); every symbol declared in include/llampc_b200.h
 PROTOTYPES = {
@@ -126,7 +127,7 @@ def lib():
         for name, (res, args) in PROTOTYPES.items():
             fn = getattr(handle, name)           # AttributeError if the library lacks a declared symbol
             fn.restype, fn.argtypes = res, args
-        if handle.llampc_abi_version() != 5:
+        if handle.llampc_abi_version() != 6:
             raise LlampcError("libllampc_b200.so ABI version mismatch")
         if handle.llampc_tick_sizeof() != C.sizeof(Tick) or handle.llampc_lookback_desc_sizeof() != C.sizeof(LookbackDesc):
             raise LlampcError("llampc_tick_t / llampc_lookback_desc_t layout mismatch between _lib.py and "

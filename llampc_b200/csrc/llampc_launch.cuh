@@ -45,6 +45,24 @@ static int issue(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cud
     return (int)cudaGetLastError();
 }
 
+// Launch with the programmatic-stream-serialization attribute: the grid may start while the previous grid on the stream is
+// still running, once every CTA of that grid has executed griddepcontrol.launch_dependents (or exited); the kernel itself
+// orders its first conflicting access behind the previous grid with griddepcontrol.wait.
+template <class... KArgs, class... Args>
+static int issue_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args... args) {
+    static_assert(sizeof...(KArgs) == sizeof...(Args), "argument count");
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = 1;
+    return (int)cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // Experiment switches.  The environment is read once per process (first use); everything a caller may legitimately
 // want to steer per call is a field of llampc_lookback_desc_t instead (kernel, split, sine).
 struct LibEnv {

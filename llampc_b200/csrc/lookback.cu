@@ -523,6 +523,8 @@ static int lookback_launch_planned(const llampc_lookback_desc_t& d, const LbPlan
     a.px = px;
     a.tm = TreeMerge{{nullptr, nullptr, nullptr, nullptr, nullptr}, nullptr, 0};
     const bool packed = p.kernel == LLAMPC_KERNEL_K1P;
+    // PDL only where the kernel orders itself behind its predecessor (K1p), one history, no row patch riding in the launch
+    a.pdl = (d.flags & LLAMPC_LB_FLAG_PDL) && packed && p.tree && nr.slot < 0 && !launch_collector().slots;
     if (p.tree) {
         a.tm = TreeMerge{tree_workspace(wsb, p.lay), d.out, d.K};
     } else if (d.K > 0) {

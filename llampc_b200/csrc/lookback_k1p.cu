@@ -125,6 +125,11 @@ lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const 
     }
 
     K1P_TRACE(2);
+    // Programmatic dependent launch (LLAMPC_LB_FLAG_PDL; both instructions are no-ops in an ordinary launch): the next launch
+    // on the stream may start its bank loads and RK4 rows now, beside this launch's selection / merge-tree tail; this launch
+    // in turn must not write avg_err, the workspace or `out` before the previous one has completed.
+    pdl_launch_dependents();
+    pdl_wait();
     if (SY > 1) {
         spart[(sy * 2) * CPB + c] = acc0;
         spart[(sy * 2 + 1) * CPB + c] = acc1;
@@ -198,6 +203,9 @@ static int launch_one(const LbArgs& a, cudaStream_t st) {
     if (rc) return rc;
     const int CPB = (2 * LB_THREADS) / SY;
     dim3 grid((a.N + CPB - 1) / CPB, a.n_vehicles);
+    if (a.pdl)
+        return issue_pdl(kern, grid, dim3(LB_THREADS), smem, st, a.bank, a.N, a.Npad, a.hist, a.W, a.hist_stride_floats, a.z,
+                         a.avg_err, a.cta_lists, a.idx_offset, a.nr, a.fm, a.px, a.tm);
     return issue(kern, grid, dim3(LB_THREADS), smem, st, a.bank, a.N, a.Npad, a.hist, a.W, a.hist_stride_floats, a.z, a.avg_err,
                  a.cta_lists, a.idx_offset, a.nr, a.fm, a.px, a.tm);
 }

@@ -19,6 +19,7 @@ struct LbArgs {
     FusedMerge fm;               // last-CTA merge per vehicle (K = 0: off)
     PeerXchg px;                 // NVLink min-loc (world = 0: off)
     TreeMerge tm;                // in-kernel tree merge, single history (K = 0: off)
+    bool pdl;                    // programmatic dependent launch (K1p, tree mode)
 };
 
 // candidates per CTA of the grid kernels for a window split of `sy`

@@ -57,7 +57,7 @@ class LookbackLaunch:
     """
 
     def __init__(self, bank, hist, W, Ts, K=10, n_vehicles=1, hist_stride_rows=None, idx_offset=0, mode="recompute",
-                 err_ring=None, avg_err=None, out=None, fast_sin=None, kernel=None, split=0, peer=None):
+                 err_ring=None, avg_err=None, out=None, fast_sin=None, kernel=None, split=0, peer=None, pdl=False):
         torch = _lib.require_cuda()
         self.torch, self.bank, self.hist, self.peer = torch, bank, hist, peer
         self._L = _lib.lib()
@@ -77,6 +77,7 @@ class LookbackLaunch:
         self.out = out
         d.out = out.data_ptr() if out is not None else None
         d.kernel, d.split = _KERNEL[kernel] if not isinstance(kernel, int) else kernel, int(split)
+        d.flags = _lib.LB_FLAG_PDL if pdl else 0
         if peer is not None:
             d.peer_bufs, d.world, d.rank, d.seq = peer.peer_ptrs.data_ptr(), peer.world, peer.rank, 1
         self.desc = d

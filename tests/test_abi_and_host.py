@@ -25,7 +25,7 @@ def test_library_exports_every_declared_symbol():
     for n in names:
         assert hasattr(lib, n), n
         assert n in _lib.PROTOTYPES, "ctypes prototype missing for %s" % n
-    assert lib.llampc_abi_version() == 5
+    assert lib.llampc_abi_version() == 6
     lookback = [n for n in names if n.startswith('llampc_lookback_')]
     assert {'llampc_lookback_launch', 'llampc_lookback_tick', 'llampc_lookback_push'} <= set(lookback)
     # three look-back entry points + helpers (plan / finish / decode / release / sizes); the six overlapping launch

@@ -803,6 +803,47 @@ def test_tree_tick_kernels_match_oracle(history, kernel, N, W, K, t_end):
     assert list(topk) == [int(k & np.uint64(0xFFFFFFFF)) for k in own[:min(lb.K, N)]]
 
 
+def test_pdl_back_to_back_ticks_are_bit_identical(history):
+    """LLAMPC_LB_FLAG_PDL (programmatic dependent launch, the mode bench.py times): eight K1p ticks on eight different windows
+    launched back to back on ONE shared workspace, so that the rows of tick t + 1 run beside the merge-tree tail of tick t --
+    repeated three times.  Every tick's arg-min key, top-10 keys and per-candidate scores must equal, bit for bit, what the
+    same launches produce one at a time without the flag."""
+    import torch
+    from llampc_b200.mpc import LookBack
+    from llampc_b200.mpc.lookback import LookbackLaunch
+    S, U, Ts = history
+    N, W = 20000, 12
+    bank = orc.make_bank(N, seed=23, variation=orc.RT_VARIATION + (("mass", 0.15),))
+    lbs, pdl, ref = [], [], []
+    for i in range(8):
+        lb = LookBack(bank, W=W, Ts=Ts, K=10, refine=0, kernel="k1p")
+        ts = np.arange(500 + 37 * i - W + 1, 500 + 37 * i + 1)
+        lb.load_window(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
+        lbs.append(lb)
+        for flag, dst in ((True, pdl), (False, ref)):
+            avg = torch.zeros(N, dtype=torch.float32, device="cuda")
+            dst.append((LookbackLaunch(lbs[0].bank, lb.hist, W, Ts, K=10, avg_err=avg, kernel="k1p", pdl=flag), avg))
+    assert pdl[0][0].kernel_name == "K1p"
+    shared = pdl[0][0].workspace
+    for ll, _ in pdl:
+        ll.desc.workspace = shared.data_ptr()
+    want = []
+    for ll, avg in ref:
+        ll.launch()
+        torch.cuda.synchronize()
+        want.append((ll.keys()[0].copy(), avg.cpu().numpy().copy()))
+    assert len({int(k[0]) for k, _ in want}) > 1                          # the windows really select different models
+    for rep in range(3):
+        for ll, avg in pdl:
+            ll.out.zero_()
+            avg.zero_()
+        for ll, _ in pdl:
+            ll.launch()
+        torch.cuda.synchronize()
+        for (ll, avg), (k, a) in zip(pdl, want):
+            assert np.array_equal(ll.keys()[0], k) and np.array_equal(avg.cpu().numpy(), a), rep
+
+
 def test_scalar_and_packed_kernels_agree_on_decisions(history):
     """LookBack forced onto the scalar kernel K1 and onto the packed kernel K1p over a replay of the recorded loop: the
     same operations per candidate (the packed form only re-associates a few signs), so decisions and fp64 re-scored
