@@ -636,7 +636,7 @@ def run_b200(args):
     if extras:
         line["other_configs"] = extras
         line["other_configs_protocol"] = ("per-launch CUDA events with a 256 MiB L2 flush before every launch (the l2_flushed protocol), "
-                                          "except C5_1gpu ms_per_tick, which uses the rotation protocol of the headline")
+                                          "except C5_1gpu ms_per_tick and C3 ms_per_call, which use the protocol of the headline (one bank copy per launch, back to back)")
     if cpu_base:
         line["cpu_baseline"] = cpu_base
     print(json.dumps(line), flush=True)
@@ -767,8 +767,27 @@ def secondary_configs(torch, L, _lib, S, U, st, flush):
     la = LookAhead({k: (v[keep] if np.ndim(v) else v) for k, v in big.items()}, Ts=TS)
     del lbm
     plan = la.plan(S[:, t0], Useq, xref, U[:, t0 - 1])
-    dt = time_it(plan.run, 20)
-    out["C3_lookahead_16384x32x20"] = {"steps_per_s": M * K * H / dt, "ms_per_call": dt * 1e3, "roofline_frac": M * K * H / dt / peak_rate}
+    dt_flushed = time_it(plan.run, 20)
+    # sustained, the headline's protocol: every call reads its own copy of the 1 MiB model bank (never read before, 135 MiB in
+    # all against 126 MB of L2), calls back to back between one pair of events, programmatic dependent launch
+    reps = int(np.ceil(1.35 * L2_BYTES / (64.0 * la.bank.Npad)))
+    copies = [la.bank.packed.clone() for _ in range(reps + 3)]
+    flush.add_(1)
+    use_pdl = os.environ.get("LLAMPC_BENCH_PDL", "1") == "1"
+    for c in copies[:3]:
+        plan.run(bank_ptr=c.data_ptr(), pdl=use_pdl)
+    torch.cuda.synchronize()
+    ea, eb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ea.record()
+    for c in copies[3:]:
+        plan.run(bank_ptr=c.data_ptr(), pdl=use_pdl)
+    eb.record()
+    torch.cuda.synchronize()
+    dt = ea.elapsed_time(eb) * 1e-3 / reps
+    del copies
+    out["C3_lookahead_16384x32x20"] = {"steps_per_s": M * K * H / dt, "ms_per_call": dt * 1e3, "roofline_frac": M * K * H / dt / peak_rate,
+                                       "protocol": "one bank copy per call, %d calls back to back, %s" % (reps, "programmatic dependent launch" if use_pdl else "stream order"),
+                                       "ms_per_call_l2_flushed": dt_flushed * 1e3, "roofline_frac_l2_flushed": M * K * H / dt_flushed / peak_rate}
     # end to end: LookAhead.rollout with host arrays in (x0, U, xref, uprev: 5.3 KB) and J (M, K) + best_k (M) back on the host
     lat = []
     for _ in range(8):

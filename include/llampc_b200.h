@@ -295,7 +295,9 @@ int llampc_forces_batch_f32(const float* bank, int N, int Npad, const double* x6
  *   xref       [H+1][2] floats (row h = reference position at step h), or [M][H+1][2] if per_model_flags & 2
  *   uprev      [2] floats, or [M][2] if per_model_flags & 4   (diagnostics: per_model_flags & 8 forces the scalar
  *              kernel with the general branchy step, & 16 the scalar kernel with its straight-line step, instead of
- *              the packed two-models-per-thread kernels)
+ *              the packed two-models-per-thread kernels; & 32: programmatic dependent launch of the shared-layout kernel for
+ *              back-to-back rollouts that do not consume each other's results -- the next launch's rollouts start beside
+ *              this launch's last wave, bit-identical results)
  *              shared U / xref tables are fetched with 16-byte-granular bulk copies: the buffers must be
  *              16-byte aligned and readable up to the next multiple of 16 bytes
  *   qrp_h      HOST pointer, 6 floats = Q00 Q11 R00 R11 P00 P11

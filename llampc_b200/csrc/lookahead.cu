@@ -240,6 +240,10 @@ lookahead2_kernel(const float4* __restrict__ bank, int Mpad, int M, const double
         const F2 Jk = add2(Jt, bc(sJa[kk]));
         float j0, j1;
         up(Jk, j0, j1);
+        // programmatic dependent launch (per_model_flags & 32; no-ops otherwise): after the last rollout of this warp the
+        // next launch on the stream may start its rollouts; nothing is written before the previous launch has completed
+        if (k0 + 32 >= K) pdl_launch_dependents();
+        pdl_wait();
         if (k_ok) {
             J[(size_t)m0 * K + k] = j0;
             best0 = u64_min(best0, pack_key(j0, (unsigned)k));
@@ -422,7 +426,12 @@ extern "C" int llampc_lookahead_rollout_f32(const float* bank, int Mpad, const i
         const size_t smem2 = ((tab + ((size_t)H + 2) * 8 + (size_t)K * 4 + 15) & ~(size_t)15) + (size_t)K * H * 16;
         if (smem2 <= 160 * 1024) {
             LLAMPC_CUDA_TRY((cudaError_t)raise_dynamic_smem(lookahead2_kernel, smem2));
-            lookahead2_kernel<<<(M + 2 * LA_WARPS - 1) / (2 * LA_WARPS), LA_THREADS, smem2, st>>>(
+            const dim3 grid2((M + 2 * LA_WARPS - 1) / (2 * LA_WARPS));
+            if (per_model_flags & 32)              // programmatic dependent launch: back-to-back independent rollouts
+                return issue_pdl(lookahead2_kernel, grid2, dim3(LA_THREADS), smem2, st, reinterpret_cast<const float4*>(bank),
+                                 Mpad, M, x0, U, K, H, xref, uprev, qrp_h[0], qrp_h[1], qrp_h[2], qrp_h[3], qrp_h[4], qrp_h[5],
+                                 (float)Ts, J, best_k, x_final);
+            lookahead2_kernel<<<grid2, LA_THREADS, smem2, st>>>(
                 reinterpret_cast<const float4*>(bank), Mpad, M, x0, U, K, H, xref, uprev, qrp_h[0], qrp_h[1], qrp_h[2],
                 qrp_h[3], qrp_h[4], qrp_h[5], (float)Ts, J, best_k, x_final);
             return (int)cudaGetLastError();

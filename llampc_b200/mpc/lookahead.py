@@ -97,14 +97,16 @@ class LookAhead:
 
 
 class RolloutPlan:
-    def run(self):
+    def run(self, bank_ptr=None, pdl=False):
+        """Enqueue the rollout.  bank_ptr: another packed bank of the same shape (a sweep over banks); pdl: programmatic
+        dependent launch for back-to-back rollouts that do not consume each other's results."""
         o = self.owner
         torch = o.torch
         with torch.cuda.device(o.bank.device):
             rc = _lib.lib().llampc_lookahead_rollout_f32(
-                o.bank.packed.data_ptr(), o.bank.Npad, None if self.midx is None else self.midx.data_ptr(), self.M,
+                o.bank.packed.data_ptr() if bank_ptr is None else bank_ptr, o.bank.Npad, None if self.midx is None else self.midx.data_ptr(), self.M,
                 self.x0.data_ptr(), self.n_x0, self.U.data_ptr(), self.K, self.H, self.xref.data_ptr(),
-                self.uprev.data_ptr(), self.flags, o.qrp.ctypes.data, o.Ts, self.J.data_ptr(), self.best.data_ptr(),
+                self.uprev.data_ptr(), self.flags | (32 if pdl else 0), o.qrp.ctypes.data, o.Ts, self.J.data_ptr(), self.best.data_ptr(),
                 None if self.xf is None else self.xf.data_ptr(), None if self.traj is None else self.traj.data_ptr(),
                 _lib.stream_ptr(torch))
         _lib.check(rc, "llampc_lookahead_rollout_f32")

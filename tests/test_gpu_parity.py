@@ -844,6 +844,36 @@ def test_pdl_back_to_back_ticks_are_bit_identical(history):
             assert np.array_equal(ll.keys()[0], k) and np.array_equal(avg.cpu().numpy(), a), rep
 
 
+def test_lookahead_pdl_back_to_back_is_bit_identical(history):
+    """per_model_flags & 32 (programmatic dependent launch of the shared-layout rollout K2p, the mode bench.py times for C3):
+    six rollouts on six different banks launched back to back into six output buffers, three rounds -- J, best_k and x_final
+    equal, bit for bit, the same rollouts launched one at a time without the flag."""
+    import torch
+    from llampc_b200.mpc import LookAhead
+    S, U, Ts = history
+    M, K, H = 3000, 32, 20
+    rng = np.random.RandomState(5)
+    t0 = 700
+    Useq = U[:, t0:t0 + H].T[None] + np.stack([0.1 * rng.randn(K, H), 0.05 * rng.randn(K, H)], axis=-1)
+    xref = S[:2, t0:t0 + H + 1]
+    las = [LookAhead(orc.make_bank(M, seed=60 + i), Ts=Ts) for i in range(6)]
+    plans = [la.plan(S[:, t0], Useq, xref, U[:, t0 - 1], return_final=True) for la in las]
+    want = []
+    for p in plans:
+        p.run()
+        torch.cuda.synchronize()
+        want.append(tuple(a.copy() for a in p.fetch()))
+    for rep in range(3):
+        for p in plans:
+            p.J.zero_(); p.best.zero_(); p.xf.zero_()
+        for p in plans:
+            p.run(pdl=True)
+        torch.cuda.synchronize()
+        for p, w in zip(plans, want):
+            got = p.fetch()
+            assert all(np.array_equal(a, b) for a, b in zip(got, w)), rep
+
+
 def test_scalar_and_packed_kernels_agree_on_decisions(history):
     """LookBack forced onto the scalar kernel K1 and onto the packed kernel K1p over a replay of the recorded loop: the
     same operations per candidate (the packed form only re-associates a few signs), so decisions and fp64 re-scored
