@@ -226,7 +226,7 @@ REF_WHAT = {"reference": "the reference's own evaluate_models_vectorized (llampc
                     "package did not resolve on this box)"}
 
 
-def run_reference(args):
+def run_reference(args, emit):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
@@ -257,7 +257,7 @@ def run_reference(args):
             "config": workload_config(args.gpus),
             "cpu_baseline": {"value": value, "unit": "steps/s", "cores": cores, "kind": kind, "sample": sample},
             "e2e": {"value": value, "unit": "steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 L2_BYTES = 126e6                       # B200 L2
@@ -304,7 +304,7 @@ def cpu_baseline_leg():
             "value_1core_as_reference_runs_it": r1}
 
 
-def run_b200(args):
+def run_b200(args, emit):
     cpu_base = None
     if int(os.environ.get("WORLD_SIZE", "1")) == 1 and not args.no_cpu:
         cpu_base = cpu_baseline_leg()
@@ -639,7 +639,7 @@ def run_b200(args):
                                           "except C5_1gpu ms_per_tick and C3 ms_per_call, which use the protocol of the headline (one bank copy per launch, back to back)")
     if cpu_base:
         line["cpu_baseline"] = cpu_base
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         td.destroy_process_group()
 
@@ -854,10 +854,24 @@ def main():
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-extras", action="store_true", help="skip the secondary configs (C1, C3, C5 on one GPU)")
     args = ap.parse_args()
+    # stdout carries exactly ONE line (the JSON): anything a library prints there meanwhile (the NCCL version banner of the
+    # first collective, for one) is sent to stderr at the file-descriptor level until the line is written
+    sys.stdout.flush()
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
+
     if args.impl == "reference":
-        run_reference(args)
+        run_reference(args, emit)
     else:
-        run_b200(args)
+        run_b200(args, emit)
+    sys.stdout.flush()
+    os.dup2(real_stdout, 1)
 
 
 if __name__ == "__main__":
