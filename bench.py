@@ -564,11 +564,13 @@ def run_b200(args, emit):
     t_base = W_C2 + max(args.warmup, 3)
     t0 = time.perf_counter()
     e2e_best = None
+    push_outs = []
     for i in range(args.steps):
         t = t_base + i
         a = time.perf_counter()
         e2e_best, topk, err = lbe.push(S[:, t], U[:, t], S[:, t + 1])
         lats.append(time.perf_counter() - a)
+        push_outs.append((e2e_best, list(topk), err))
     wall = time.perf_counter() - t0
     if world > 1:
         wt = torch.tensor([wall], dtype=torch.float64, device=dev)
@@ -580,8 +582,41 @@ def run_b200(args, emit):
         parity["e2e_ranks_agree"] = bool((ebs == ebs[0]).all().item())
     h2d = _lib.HIST_ROW * 4 + _lib.HIST64_ROW * 8          # the row travels as kernel parameters
     d2h = (1 + 2 * lbe.Kt * (world if world > 1 else 1)) * 8
-    e2e = {"value": steps_per_tick * args.steps / wall, "unit": "steps/s", "h2d_bytes_per_step": h2d,
-           "d2h_bytes_per_step": d2h, "api": "LookBack.push (host NumPy transition in; fp64 re-score of the 16 finalists and, for N > 1, the finalist all-gather over NVLink included; arg-min + top-10 indices out)"}
+    # the same K ticks through LookBack.replay: a recorded run handed over as host arrays, up to 4 ticks in flight (every tick
+    # still carries its row in the launch parameters and returns its decision through its own mapped pinned slot)
+    # (the SAME K transitions as the push loop above, on a second object primed with the same window; decisions must agree)
+    lbp = LookBack(bank, W=W_C2, Ts=TS, K=10, refine=16, idx_offset=lo, group=(td.group.WORLD if world > 1 else None))
+    tp = np.arange(0, t_base)
+    lbp.replay(S[:, tp].T, U[:, tp].T, S[:, tp + 1].T)                              # window primed, slots allocated, paths warm
+    ts = np.arange(t_base, t_base + args.steps)
+    torch.cuda.synchronize()
+    if world > 1:
+        td.barrier()
+    t0 = time.perf_counter()
+    outs = lbp.replay(S[:, ts].T, U[:, ts].T, S[:, ts + 1].T)
+    wall_r = time.perf_counter() - t0
+    assert len(outs) == args.steps and all(o[0] is not None for o in outs)
+    replay_equals_push = all(o[0] == q[0] and list(o[1]) == q[1] and o[2] == q[2] for o, q in zip(outs, push_outs))
+    parity["e2e_replay_equals_push"] = bool(replay_equals_push)
+    if not replay_equals_push:
+        raise SystemExit("bench: LookBack.replay and LookBack.push disagree")
+    del lbp
+    if world > 1:
+        wt = torch.tensor([wall_r], dtype=torch.float64, device=dev)
+        td.all_reduce(wt, op=td.ReduceOp.MAX)
+        wall_r = float(wt.item())
+        eb = torch.tensor([outs[-1][0]], dtype=torch.int64, device=dev)
+        ebs = torch.zeros(world, dtype=torch.int64, device=dev)
+        td.all_gather_into_tensor(ebs, eb)
+        parity["e2e_replay_ranks_agree"] = bool((ebs == ebs[0]).all().item())
+    e2e = {"value": steps_per_tick * args.steps / wall_r, "unit": "steps/s", "h2d_bytes_per_step": h2d,
+           "d2h_bytes_per_step": d2h,
+           "api": "LookBack.replay (K recorded transitions as host NumPy arrays in, one decision per tick out: arg-min + top-10 "
+                  "indices + float64 best error; up to 4 ticks in flight; every tick carries its row to the device in the launch "
+                  "parameters, is re-scored in fp64 (16 finalists; for N > 1 the finalist all-gather over NVLink included) and "
+                  "returns through its own mapped pinned slot)",
+           "sync_push_value": steps_per_tick * args.steps / wall,
+           "sync_push_api": "LookBack.push, one tick at a time (the host waits for every decision): the latency of tick_latency"}
     lat = {"p50_us": float(np.percentile(lats, 50) * 1e6), "p95_us": float(np.percentile(lats, 95) * 1e6),
            "mode": "recompute (the whole 50-row window re-integrated every tick)"}
     if world == 1:

@@ -69,6 +69,7 @@ int llampc_hist_row_pack_h(const double* x_k, const double* u_k, const double* x
  *   llampc_lookback_launch   the scoring + selection launch on device-resident inputs (any layout / mode / GPU count)
  *   llampc_lookback_tick     one MPC tick around it: newest row in, launch, fp64 re-score, result to the host
  *   llampc_lookback_push     the tick from three fp64 host vectors (one FFI crossing per MPC tick)
+ *   llampc_lookback_replay   T ticks of a recorded run from host arrays, pipelined (one FFI crossing per run)
  * (+ the helpers llampc_lookback_plan, ..._finish, ..._decode, ..._tick_release, ..._tick_workspace_bytes).
  *
  * For every candidate: W one-step RK4 predictions re-anchored at the measured states, mean squared error over
@@ -264,6 +265,22 @@ int llampc_lookback_desc_sizeof(void);
 int llampc_lookback_push(llampc_tick_t* t, const double* x_k, const double* u_k, const double* x_k1,
                          double lf_shared, double lr_shared, long long* idx_out, double* score_out, int* n_valid,
                          llampc_stream_t stream);
+
+/* T consecutive ticks from host arrays in ONE call, PIPELINED: a replay of a recorded run (the loop of
+ * run_nmpc_orca_llampc_rt.py:347-360 over a dataset).  The look-back's inputs are measurements -- no tick depends on the
+ * decision of an earlier one -- so up to `depth` ticks are in flight: while the GPU works on tick i the host packs and
+ * enqueues ticks i + 1 .. i + depth - 1.  Every tick still carries its own row in the launch parameters and hands its
+ * decision back through its own result slot; decisions are identical to T calls of llampc_lookback_push.
+ *   x_k [T][6], u_k [T][2], x_k1 [T][x1_stride] (x1_stride >= 4) fp64 host arrays, oldest first; tick i uses ring slot
+ *   (first_slot + i) % W.  The window must be full already (t->rolling = 0, or 1 with a primed error ring).
+ *   rows32_h [W][LLAMPC_HIST_ROW], rows64_h [W][LLAMPC_HIST64_ROW]: writable host staging rings (row i is packed into its slot)
+ *   slots_h [depth]: pinned, mapped host result buffers, each as large as t->result_h (t->zero_copy and n_refine > 0 needed)
+ *   peer_seq: in/out, NULL on one GPU: the last tick counter used (incremented once per tick, identically on every rank)
+ *   idx_out / score_out [T][kt] with kt = max(K, n_refine), n_valid [T]. */
+int llampc_lookback_replay(llampc_tick_t* t, const double* x_k, const double* u_k, const double* x_k1, int x1_stride, int T,
+                           int first_slot, double lf_shared, double lr_shared, float* rows32_h, double* rows64_h,
+                           llampc_key_t* const* slots_h, int depth, unsigned* peer_seq, long long* idx_out,
+                           double* score_out, int* n_valid, llampc_stream_t stream);
 
 /* ---------------------------------------------------------------------------------------------
  * One RK4 step for N (model, state, input) triples: Model._integrate_batch (llampc/models/model.py:32-40)

@@ -91,6 +91,8 @@ PROTOTYPES = {
     "llampc_tick_offsetof": (_i, [_i]),
     "llampc_lookback_desc_sizeof": (_i, []),
     "llampc_lookback_push": (_i, [C.POINTER(Tick), _vp, _vp, _vp, _d, _d, _vp, _vp, _vp, _vp]),
+    "llampc_lookback_replay": (_i, [C.POINTER(Tick), _vp, _vp, _vp, _i, _i, _i, _d, _d, _vp, _vp, _vp, _i, _vp, _vp, _vp, _vp,
+                                    _vp]),
     "llampc_rk4_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _d, _vp, _i, _vp]),
     "llampc_rhs_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),
     "llampc_forces_batch_f32": (_i, [_vp, _i, _i, _vp, _i, _vp, _i, _vp, _vp]),

@@ -5,6 +5,8 @@
 // Reference behaviour being replaced: evaluate_models_vectorized (llampc/mpc/evaluate_models_vectorized.py:4-23)
 // + the scoring / selection block of run_nmpc_orca_llampc_rt.py:347-360.
 #include "lookback_kernels.cuh"
+#include <chrono>
+#include <stdio.h>
 #include "llampc_model_f64.cuh"
 #include <math.h>
 #include <stddef.h>
@@ -181,6 +183,10 @@ refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__
     __shared__ bool last_block;
     __shared__ int peer_fail;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    // In a pipelined replay the NEXT tick's scoring kernel is launched with programmatic stream serialization: it may start its
+    // bank loads and RK4 rows beside this re-score (it writes nothing this kernel reads before its own griddepcontrol.wait,
+    // which holds until this grid has completed).  A no-op for ordinary launches.
+    pdl_launch_dependents();
     if (nr.slot >= 0 && f == 0 && tid < LLAMPC_HIST64_ROW) hist64[(size_t)nr.slot * LLAMPC_HIST64_ROW + tid] = nr.v[tid];
     const long long ci = (long long)(unsigned)(keys[f] & 0xffffffffull) - idx_offset;
     double result = __longlong_as_double(0x7ff8000000000000ll);       // padded key (~0) or foreign shard -> NaN
@@ -523,8 +529,10 @@ static int lookback_launch_planned(const llampc_lookback_desc_t& d, const LbPlan
     a.px = px;
     a.tm = TreeMerge{{nullptr, nullptr, nullptr, nullptr, nullptr}, nullptr, 0};
     const bool packed = p.kernel == LLAMPC_KERNEL_K1P;
-    // PDL only where the kernel orders itself behind its predecessor (K1p), one history, no row patch riding in the launch
-    a.pdl = (d.flags & LLAMPC_LB_FLAG_PDL) && packed && p.tree && nr.slot < 0 && !launch_collector().slots;
+    // PDL only where the kernel orders itself behind its predecessor (K1p with the merge tree), and not while a tick records
+    // its launches for the graph.  A row patch riding in the launch is fine: every CTA of a preceding K1p launch has read the
+    // ring (prologue) before it signals, and the re-score kernel does not read the fp32 ring.
+    a.pdl = (d.flags & LLAMPC_LB_FLAG_PDL) && packed && p.tree && !launch_collector().slots;
     if (p.tree) {
         a.tm = TreeMerge{tree_workspace(wsb, p.lay), d.out, d.K};
     } else if (d.K > 0) {
@@ -665,6 +673,10 @@ extern "C" long long llampc_lookback_tick_workspace_bytes(const llampc_tick_t* t
 
 extern "C" int llampc_lookback_finish(llampc_tick_t* t, llampc_stream_t stream);
 
+// Pipelined replays issue plain stream launches: a graph exec has one launch in flight at a time, and re-parameterising it
+// while the previous tick is still running stalls the host (measured: 97 us per tick against 67 us for synchronous pushes).
+static thread_local bool g_plain_launches = false;
+
 extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
     if (!t || !t->bank || !t->hist || !t->result || !t->result_h || !t->workspace) return LLAMPC_E_ARG;
     if (t->slot < 0 || t->slot >= t->W) return LLAMPC_E_ARG;
@@ -691,7 +703,7 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
         LaunchCollector& lc; bool on;
         ~CollectGuard() { if (on) { lc.slots = nullptr; lc.n = 0; } }
     } guard = {lc, false};
-    if (lib_env().tick_graph && refine && L.fused && L.p.launches == 1) {
+    if (lib_env().tick_graph && !g_plain_launches && refine && L.fused && L.p.launches == 1) {
         if (!t->graph_state) t->graph_state = calloc(1, sizeof(TickGraph));
         if (t->graph_state) {
             lc.slots = pending;
@@ -701,6 +713,7 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
     }
     if (L.fused) {
         // K1 / K1p / K1b with the merge tree (or K1r with the last-CTA merge): writes keys[0..LIST_LEN] itself
+        if (g_plain_launches) L.d.flags |= LLAMPC_LB_FLAG_PDL;       // pipelined replay: overlap with the previous tick's re-score
         rc = lookback_launch_planned(L.d, L.p, st);
         if (rc) return rc;
         if (t->rolling == 2) {                                       // window still filling: column stored, no decision
@@ -914,6 +927,71 @@ extern "C" int llampc_lookback_push(llampc_tick_t* t, const double* x_k, const d
     t->sync = sync_was;
     if (rc) return rc;
     return llampc_lookback_decode(t, idx_out, score_out, n_valid);
+}
+
+// T ticks of a recorded run, pipelined (see the header): one C loop instead of T FFI crossings, up to `depth` ticks in flight.
+extern "C" int llampc_lookback_replay(llampc_tick_t* t, const double* x_k, const double* u_k, const double* x_k1, int x1_stride,
+                                      int T, int first_slot, double lf_shared, double lr_shared, float* rows32_h,
+                                      double* rows64_h, llampc_key_t* const* slots_h, int depth, unsigned* peer_seq,
+                                      long long* idx_out, double* score_out, int* n_valid, llampc_stream_t stream) {
+    if (!t || !x_k || !u_k || !x_k1 || !rows32_h || !rows64_h || !slots_h || !idx_out || !score_out || !n_valid) return LLAMPC_E_ARG;
+    if (T < 0 || x1_stride < 4 || depth < 1 || depth > 64 || first_slot < 0 || first_slot >= t->W) return LLAMPC_E_RANGE;
+    if (!t->zero_copy || t->n_refine <= 0 || t->rolling > 1) return LLAMPC_E_ARG;
+    const int kt = t->K > t->n_refine ? t->K : t->n_refine;
+    struct InFlight { llampc_key_t* rh; unsigned long long seq; int words; int tick; } ring[64];
+    void* dev_of[64];
+    for (int j = 0; j < depth; ++j) {
+        if (!slots_h[j]) return LLAMPC_E_ARG;
+        LLAMPC_CUDA_TRY(cudaHostGetDevicePointer(&dev_of[j], slots_h[j], 0));
+    }
+    const llampc_tick_t saved = *t;
+    int head = 0, count = 0, rc = 0;
+    struct PlainGuard { PlainGuard() { g_plain_launches = true; } ~PlainGuard() { g_plain_launches = false; } } plain_guard;
+    auto finish_oldest = [&]() -> int {
+        const InFlight& f = ring[head];
+        t->result_h = f.rh; t->pending_seq = f.seq; t->pending_words = f.words;
+        int r = llampc_lookback_finish(t, stream);
+        if (!r) r = llampc_lookback_decode(t, idx_out + (size_t)f.tick * kt, score_out + (size_t)f.tick * kt, n_valid + f.tick);
+        head = (head + 1) % depth;
+        --count;
+        return r;
+    };
+    const bool trace = getenv("LLAMPC_REPLAY_TRACE") != nullptr;
+    double t_fin = 0, t_pack = 0, t_tick = 0;
+    auto now = [] { return std::chrono::duration<double, std::micro>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+    for (int i = 0; i < T && !rc; ++i) {
+        const double a0 = trace ? now() : 0;
+        if (count == depth) { rc = finish_oldest(); if (rc) break; }
+        const double a1 = trace ? now() : 0;
+        const int slot = (first_slot + i) % t->W, j = i % depth;
+        float* r32 = rows32_h + (size_t)slot * LLAMPC_HIST_ROW;
+        double* r64 = rows64_h + (size_t)slot * LLAMPC_HIST64_ROW;
+        rc = llampc_hist_row_pack_h(x_k + (size_t)i * 6, u_k + (size_t)i * 2, x_k1 + (size_t)i * x1_stride, t->Ts, lf_shared,
+                                    lr_shared, r32, r64);
+        if (rc) break;
+        const double a2 = trace ? now() : 0;
+        t->row32_h = r32; t->row64_h = r64; t->slot = slot;
+        t->result_h = slots_h[j]; t->mapped_for = slots_h[j]; t->mapped_dev = dev_of[j];
+        t->sync = 0;
+        if (peer_seq) { *peer_seq = *peer_seq % 0xFFFFFFFFu + 1u; t->peer_seq = *peer_seq; }
+        rc = llampc_lookback_tick(t, stream);
+        if (rc) break;
+        ring[(head + count) % depth] = InFlight{slots_h[j], t->pending_seq, t->pending_words, i};
+        ++count;
+        if (trace) { const double a3 = now(); t_fin += a1 - a0; t_pack += a2 - a1; t_tick += a3 - a2; }
+    }
+    if (trace && T > 0)
+        fprintf(stderr, "replay T=%d depth=%d: per tick  wait+decode %.1f us  pack %.1f us  enqueue %.1f us  (pending_seq %llu)\n", T, depth,
+                t_fin / T, t_pack / T, t_tick / T, (unsigned long long)t->pending_seq);
+    while (count > 0) {                                              // drain (also after an error: the slots must go quiet)
+        const int r = finish_oldest();
+        if (!rc) rc = r;
+    }
+    void* gs = t->graph_state;                                       // the graph may have been (re)built meanwhile
+    *t = saved;
+    t->graph_state = gs;
+    t->pending_seq = 0; t->pending_words = 0;
+    return rc;
 }
 
 // Frees what llampc_lookback_tick attached to the struct (the CUDA graph of the tick).  Safe to call more than once.

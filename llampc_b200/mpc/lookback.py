@@ -398,6 +398,58 @@ class LookBack:
         idx = self._idx_out[:n]
         return int(idx[0]), idx[:self.K].copy(), float(self._score_out[0])
 
+    def replay(self, x_k, u_k, x_k1, depth=4):
+        """Push T consecutive transitions -- x_k (T,6), u_k (T,2), x_k1 (T,>=4), oldest first, e.g. a recorded run -- and return
+        the list of T decisions, each what ``push`` would have returned.  The ticks are PIPELINED: up to ``depth`` of them are
+        in flight (every tick still carries its own row to the device in the launch parameters and hands its own result back
+        through its own mapped pinned slot), so the host packs and enqueues tick t + 1 .. t + depth while the GPU works on
+        tick t.  Same decisions as T calls of ``push`` (the look-back's inputs are measurements: no tick depends on the result
+        of an earlier one).  Falls back to a loop over ``push`` where the zero-copy hand-off is not in use."""
+        x_k, u_k, x_k1 = np.asarray(x_k, dtype=np.float64), np.asarray(u_k, dtype=np.float64), np.asarray(x_k1, dtype=np.float64)
+        T = x_k.shape[0]
+        out = []
+        t = self._tick
+        piped = bool(t.zero_copy) and self.n_refine > 0 and (self.group is None or self._peer is not None) and depth > 1
+        i = 0
+        while i < T and (self.window_count + 1 < self.W or not piped):
+            out.append(self.push(x_k[i], u_k[i], x_k1[i]))
+            i += 1
+        if i >= T:
+            return out
+        torch = self.torch
+        if len(getattr(self, "_slots", ())) < depth:
+            self._slots = [torch.zeros(self.result_h.numel(), dtype=torch.int64, pin_memory=True) for _ in range(depth)]
+        slot_ptrs = (C.c_void_p * depth)(*[s_.data_ptr() for s_ in self._slots[:depth]])
+        n = T - i
+        xs = np.ascontiguousarray(x_k[i:, :6])
+        us = np.ascontiguousarray(u_k[i:, :2])
+        x1 = np.ascontiguousarray(x_k1[i:])
+        kt = max(self.Kt, 1)
+        idx = np.zeros((n, kt), dtype=np.int64)
+        sc = np.zeros((n, kt), dtype=np.float64)
+        nv = np.zeros(n, dtype=np.int32)
+        seq = C.c_uint(self._peer.seq) if self._peer is not None else None
+        first = self._next_slot
+        with self._stream_dev:
+            rc = self._L.llampc_lookback_replay(self._tick_ref, xs.ctypes.data, us.ctypes.data, x1.ctypes.data, x1.shape[1], n,
+                                                first, self._lf_shared, self._lr_shared, self._r32_base, self._r64_base,
+                                                C.cast(slot_ptrs, C.c_void_p), depth,
+                                                C.addressof(seq) if seq is not None else None, idx.ctypes.data, sc.ctypes.data,
+                                                nv.ctypes.data, torch.cuda.current_stream().cuda_stream)
+        if seq is not None:
+            self._peer.seq = int(seq.value)
+        self._next_slot = (first + n) % self.W
+        self.window_count = self.W
+        if rc:
+            _lib.check(rc, "llampc_lookback_replay")
+        for r in range(n):
+            m = int(nv[r])
+            if m == 0:
+                out.append((None, np.zeros(0, dtype=np.int64), float("nan")))
+            else:
+                out.append((int(idx[r, 0]), idx[r, :min(self.K, m)].copy(), float(sc[r, 0])))
+        return out
+
     def evaluate(self):
         """Score the window currently in the ring (after load_window); same return as push."""
         if self.rolling:

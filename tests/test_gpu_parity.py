@@ -874,6 +874,33 @@ def test_lookahead_pdl_back_to_back_is_bit_identical(history):
             assert all(np.array_equal(a, b) for a, b in zip(got, w)), rep
 
 
+@pytest.mark.parametrize("mode", ["recompute", "rolling"])
+def test_replay_pipelined_matches_push(history, mode):
+    """LookBack.replay (up to `depth` ticks in flight, every tick with its own row in the launch parameters and its own mapped
+    result slot) returns, tick for tick, exactly what a loop over push returns: None while the window fills, then identical
+    arg-min, top-10 and float64 best error -- for several depths, across two consecutive replay calls on the same object."""
+    from llampc_b200.mpc import LookBack
+    S, U, Ts = history
+    bank = orc.make_bank(9000, seed=31, variation=orc.RT_VARIATION + (("mass", 0.15),))
+    W, T = 12, 70
+    ts = np.arange(800, 800 + T)
+    ref_lb = LookBack(bank, W=W, Ts=Ts, K=10, refine=16, mode=mode)
+    want = [ref_lb.push(S[:, t], U[:, t], S[:, t + 1]) for t in ts]
+    assert want[W - 2][0] is None and want[W - 1][0] is not None
+    for depth in (1, 2, 4, 7):
+        lb = LookBack(bank, W=W, Ts=Ts, K=10, refine=16, mode=mode)
+        got = lb.replay(S[:, ts[:25]].T, U[:, ts[:25]].T, S[:, ts[:25] + 1].T, depth=depth)
+        got += lb.replay(S[:, ts[25:]].T, U[:, ts[25:]].T, S[:, ts[25:] + 1].T, depth=depth)
+        assert len(got) == T
+        for g, w in zip(got, want):
+            if w[0] is None:
+                assert g[0] is None
+            else:
+                assert g[0] == w[0] and list(g[1]) == list(w[1]) and g[2] == w[2]
+        # and the object is back in its synchronous state
+        assert lb.push(S[:, ts[-1] + 1], U[:, ts[-1] + 1], S[:, ts[-1] + 2])[0] is not None
+
+
 def test_scalar_and_packed_kernels_agree_on_decisions(history):
     """LookBack forced onto the scalar kernel K1 and onto the packed kernel K1p over a replay of the recorded loop: the
     same operations per candidate (the packed form only re-associates a few signs), so decisions and fp64 re-scored
