@@ -143,6 +143,12 @@ typedef struct llampc_lookback_desc {
    complete before it writes avg_err, the workspace or `out`).  For back-to-back launches that do not depend on each
    other's results (a sweep over banks); the results are identical. */
 #define LLAMPC_LB_FLAG_PDL 1
+/* K1P only: run the instantiation whose RK4 step takes the slip angles from the full-range atan (12 % more FMA-pipe work, no
+   slip-tangent guard) instead of the |tan| <= 0.5 form with its per-candidate fallback.  For windows measured at low speed or
+   in a drift, where most candidates would leave the fast form and be redone one by one (measured on a window at 0.1 - 0.3
+   m/s: 135 us per tick instead of 46).  Scores agree with the default form to rounding; llampc_lookback_tick sets the flag
+   itself from the rows of the ring when t->hard_h is given. */
+#define LLAMPC_LB_FLAG_WIDE 2
 
 typedef struct llampc_lookback_plan {
     int kernel;                  /* LLAMPC_KERNEL_* that a launch of this descriptor runs                                   */
@@ -234,6 +240,11 @@ typedef struct llampc_tick {
     void* graph_state;              /* internal, NULL-initialised: the tick's scoring kernel and fp64 re-score are replayed
                                        as one CUDA graph whose kernel nodes are re-parameterised every tick (2 us of host
                                        enqueue time instead of 8 us); freed by llampc_lookback_tick_release            */
+    unsigned char* hard_h;          /* HOST [W] or NULL: one flag per ring slot, "this row was measured at low speed or in a
+                                       drift" (|vx| < 0.6 m/s or |vy| + 0.06 |w| > 0.4 |vx|).  The tick updates the flag of
+                                       `slot` from row32_h and runs the LLAMPC_LB_FLAG_WIDE form of K1P while at least a tenth
+                                       of the window is flagged (a caller that fills the ring itself sets the flags too)   */
+    int n_hard;                     /* number of flagged slots (maintained with hard_h)                                     */
 } llampc_tick_t;
 
 /* Bytes of t->workspace for this tick configuration (bank, N, W, K, n_refine, rolling, overrides must be filled in);

@@ -42,7 +42,8 @@ class Tick(C.Structure):
                 ("pending_seq", C.c_ulonglong), ("pending_words", _i),
                 ("err_ring", _vp), ("rolling", _i),
                 ("workspace", _vp), ("workspace_bytes", C.c_ulonglong),
-                ("mapped_dev", _vp), ("mapped_for", _vp), ("graph_state", _vp)]
+                ("mapped_dev", _vp), ("mapped_for", _vp), ("graph_state", _vp),
+                ("hard_h", _vp), ("n_hard", _i)]
 
 
 class LookbackDesc(C.Structure):
@@ -70,6 +71,7 @@ KERNEL_NAMES = ("auto", "K1", "K1p", "K1b", "K1r", "K1v", "K1e")
 SIN_NAMES = ("auto", "MUFU.SIN", "strict polynomial")
 E_PEER = -4
 LB_FLAG_PDL = 1
+LB_FLAG_WIDE = 2
 
 # name -> (restype, argtypes); every symbol declared in include/llampc_b200.h
 PROTOTYPES = {

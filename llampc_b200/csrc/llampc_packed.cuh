@@ -167,18 +167,23 @@ __device__ __forceinline__ F2 drive_force_fast2(const Cand2& p, const Drive2& d,
 // guards: gt = max |slip tangent| (must stay <= 0.5), per component
 struct Guard2 { float t0, t1; };
 
-template <bool MUFU_SIN>
+// WIDE: the slip angles come from the full-range atan (any tangent, same 1.2e-8 accuracy as the scalar general step) instead
+// of the |t| <= 0.5 polynomial, and the tangent guard is not needed: the form for windows measured at low speed or in a drift,
+// where most candidates leave the fast form (a separate kernel instantiation, chosen per launch: LLAMPC_LB_FLAG_WIDE).
+template <bool MUFU_SIN, bool WIDE = false>
 __device__ __forceinline__ Deriv2 accel_fast2(const Cand2& p, const Ctl& u, const Drive2& drv, F2 vx, F2 vy, F2 w, Guard2& g) {
     const F2 inv = rcp_abs2(vx);
     const F2 tf = mul2(fma2(p.lf, w, vy), inv);
     const F2 ntr = mul2(fma2(p.nlr, w, vy), inv);             // -(lr w - vy) / |vx|: the sign rides through the odd functions
-    float a, b, c, d;
-    up(tf, a, b);
-    up(ntr, c, d);
-    g.t0 = fmaxf(g.t0, fmaxf(fabsf(a), fabsf(c)));
-    g.t1 = fmaxf(g.t1, fmaxf(fabsf(b), fabsf(d)));
-    const F2 af = sub2(bc(u.delta), atan_half2(tf));
-    const F2 nar = atan_half2(ntr);
+    if (!WIDE) {
+        float a, b, c, d;
+        up(tf, a, b);
+        up(ntr, c, d);
+        g.t0 = fmaxf(g.t0, fmaxf(fabsf(a), fabsf(c)));
+        g.t1 = fmaxf(g.t1, fmaxf(fabsf(b), fabsf(d)));
+    }
+    const F2 af = sub2(bc(u.delta), WIDE ? atan_full2<false>(tf) : atan_half2(tf));
+    const F2 nar = WIDE ? atan_full2<false>(ntr) : atan_half2(ntr);
     const F2 Frx = drive_force_fast2(p, drv, vx);
     const F2 Ffy = pacejka_fast2<MUFU_SIN>(p.Bf, p.Cf, p.Df, af);
     const F2 nFry = pacejka_fast2<MUFU_SIN>(p.Br, p.Cr, p.Dr, nar);
@@ -192,7 +197,7 @@ __device__ __forceinline__ Deriv2 accel_fast2(const Cand2& p, const Ctl& u, cons
 
 // Two candidates, one history row.  e2 = per-candidate squared increment error; ok0 / ok1 false when a guard tripped
 // (the caller redoes that candidate with lookback_step_general).
-template <bool GEOM_SHARED, bool MUFU_SIN>
+template <bool GEOM_SHARED, bool MUFU_SIN, bool WIDE = false>
 __device__ __forceinline__ F2 lookback_step_fast2(const Cand2& p, const HistRow& r, const StepSize& z, bool& ok0, bool& ok1) {
     const float h = z.h, hh = z.hh;
     const float vx0 = r.q1.z, vy0 = r.q1.w, w0 = r.q2.x;
@@ -211,11 +216,11 @@ __device__ __forceinline__ F2 lookback_step_fast2(const Cand2& p, const HistRow&
         a1.nvy = fma2(sub2(nFry, Fc), p.inv_m, bc(vx0 * w0));
         a1.w = fma2(Fc, p.lf_Iz, mul2(nFry, p.lr_Iz));
     } else {
-        a1 = accel_fast2<MUFU_SIN>(p, u, drv, bc(vx0), bc(vy0), bc(w0), g);
+        a1 = accel_fast2<MUFU_SIN, WIDE>(p, u, drv, bc(vx0), bc(vy0), bc(w0), g);
     }
     // stage 2
     const F2 vx2 = fma2(bc(hh), a1.vx, bc(vx0)), vy2 = fma2(bc(-hh), a1.nvy, bc(vy0)), w2 = fma2(bc(hh), a1.w, bc(w0));
-    const Deriv2 a2 = accel_fast2<MUFU_SIN>(p, u, drv, vx2, vy2, w2, g);
+    const Deriv2 a2 = accel_fast2<MUFU_SIN, WIDE>(p, u, drv, vx2, vy2, w2, g);
     F2 xs = fma2(vx2, bc(r.q0.w), mul2(vy2, bc(-r.q0.z))), ys = fma2(vx2, bc(r.q0.z), mul2(vy2, bc(r.q0.w)));
     // stage 3
     const F2 vx3 = fma2(bc(hh), a2.vx, bc(vx0)), vy3 = fma2(bc(-hh), a2.nvy, bc(vy0)), w3 = fma2(bc(hh), a2.w, bc(w0));
@@ -223,7 +228,7 @@ __device__ __forceinline__ F2 lookback_step_fast2(const Cand2& p, const HistRow&
     F2 sd, cd;
     sincos_tiny2(e3, sd, cd);
     const F2 s3 = fma2(bc(r.q0.z), cd, mul2(bc(r.q0.w), sd)), c3 = fma2(bc(r.q0.w), cd, mul2(bc(-r.q0.z), sd));
-    const Deriv2 a3 = accel_fast2<MUFU_SIN>(p, u, drv, vx3, vy3, w3, g);
+    const Deriv2 a3 = accel_fast2<MUFU_SIN, WIDE>(p, u, drv, vx3, vy3, w3, g);
     xs = add2(xs, sub2(mul2(vx3, c3), mul2(vy3, s3)));
     ys = add2(ys, fma2(vx3, s3, mul2(vy3, c3)));
     // stage 4 (front tyre and drivetrain only)
@@ -233,7 +238,7 @@ __device__ __forceinline__ F2 lookback_step_fast2(const Cand2& p, const HistRow&
     const F2 s4 = fma2(bc(r.q1.x), cd, mul2(bc(r.q1.y), sd)), c4 = fma2(bc(r.q1.y), cd, mul2(bc(-r.q1.x), sd));
     const F2 inv4 = rcp_abs2(vx4);
     const F2 tf4 = mul2(fma2(p.lf, w4, vy4), inv4);
-    const F2 Ffy4 = pacejka_fast2<MUFU_SIN>(p.Bf, p.Cf, p.Df, sub2(bc(u.delta), atan_half2(tf4)));
+    const F2 Ffy4 = pacejka_fast2<MUFU_SIN>(p.Bf, p.Cf, p.Df, sub2(bc(u.delta), WIDE ? atan_full2<false>(tf4) : atan_half2(tf4)));
     const F2 a4vx = fma2(fma2(Ffy4, bc(-u.sd), drive_force_fast2(p, drv, vx4)), p.inv_m, mul2(vy4, w4));
     const F2 xd4 = sub2(mul2(vx4, c4), mul2(vy4, s4)), yd4 = fma2(vx4, s4, mul2(vy4, c4));
     // increment errors
@@ -250,8 +255,8 @@ __device__ __forceinline__ F2 lookback_step_fast2(const Cand2& p, const HistRow&
     up(e3, o0, o1);
     up(e4, p0, p1);
     up(e2, q0, q1);
-    ok0 = (fmaxf(g.t0, fabsf(t0)) <= 0.5f) && (fmaxf(fabsf(o0), fabsf(p0)) <= 0.125f) && (q0 == q0);
-    ok1 = (fmaxf(g.t1, fabsf(t1)) <= 0.5f) && (fmaxf(fabsf(o1), fabsf(p1)) <= 0.125f) && (q1 == q1);
+    ok0 = (WIDE || fmaxf(g.t0, fabsf(t0)) <= 0.5f) && (fmaxf(fabsf(o0), fabsf(p0)) <= 0.125f) && (q0 == q0);
+    ok1 = (WIDE || fmaxf(g.t1, fabsf(t1)) <= 0.5f) && (fmaxf(fabsf(o1), fabsf(p1)) <= 0.125f) && (q1 == q1);
     return e2;
 }
 

@@ -533,6 +533,7 @@ static int lookback_launch_planned(const llampc_lookback_desc_t& d, const LbPlan
     // its launches for the graph.  A row patch riding in the launch is fine: every CTA of a preceding K1p launch has read the
     // ring (prologue) before it signals, and the re-score kernel does not read the fp32 ring.
     a.pdl = (d.flags & LLAMPC_LB_FLAG_PDL) && packed && p.tree && !launch_collector().slots;
+    a.wide = (d.flags & LLAMPC_LB_FLAG_WIDE) && packed;
     if (p.tree) {
         a.tm = TreeMerge{tree_workspace(wsb, p.lay), d.out, d.K};
     } else if (d.K > 0) {
@@ -711,6 +712,13 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
             guard.on = true;
         }
     }
+    if (t->hard_h && t->row32_h && !t->rolling) {                    // low-speed / drift rows in the window -> the wide form
+        const float vx = fabsf(t->row32_h[6]), vy = fabsf(t->row32_h[7]), w = fabsf(t->row32_h[8]);
+        const unsigned char hard = (vx < 0.6f || vy + 0.06f * w > 0.4f * vx) ? 1 : 0;
+        t->n_hard += (int)hard - (int)t->hard_h[t->slot];
+        t->hard_h[t->slot] = hard;
+    }
+    if (t->hard_h && !t->rolling && t->n_hard * 10 >= t->W) L.d.flags |= LLAMPC_LB_FLAG_WIDE;
     if (L.fused) {
         // K1 / K1p / K1b with the merge tree (or K1r with the last-CTA merge): writes keys[0..LIST_LEN] itself
         if (g_plain_launches) L.d.flags |= LLAMPC_LB_FLAG_PDL;       // pipelined replay: overlap with the previous tick's re-score
@@ -988,8 +996,10 @@ extern "C" int llampc_lookback_replay(llampc_tick_t* t, const double* x_k, const
         if (!rc) rc = r;
     }
     void* gs = t->graph_state;                                       // the graph may have been (re)built meanwhile
+    const int n_hard = t->n_hard;                                    // ... and the ring's low-speed flags were updated
     *t = saved;
     t->graph_state = gs;
+    t->n_hard = n_hard;
     t->pending_seq = 0; t->pending_words = 0;
     return rc;
 }

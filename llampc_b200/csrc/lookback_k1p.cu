@@ -34,7 +34,7 @@ __device__ __forceinline__ unsigned long long k1p_gtimer() {
 #else
 #define K1P_TRACE(slot) do { } while (0)
 #endif
-template <int SY, bool GEOM_SHARED, bool MUFU_SIN>
+template <int SY, bool GEOM_SHARED, bool MUFU_SIN, bool WIDE>
 __global__ void __launch_bounds__(LB_THREADS, LLAMPC_LB2_MIN_BLOCKS)
 lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const float* __restrict__ hist, int W,
                         long hist_stride_floats, StepSize z, float* __restrict__ avg_err,
@@ -94,8 +94,8 @@ lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const 
         const int wb = w + SY;
         rb.q0 = srow[wb * 5 + 0]; rb.q1 = srow[wb * 5 + 1]; rb.q2 = srow[wb * 5 + 2]; rb.q3 = srow[wb * 5 + 3]; rb.q4 = srow[wb * 5 + 4];
         bool oka0, oka1, okb0, okb1;
-        const F2 ea = lookback_step_fast2<GEOM_SHARED, MUFU_SIN>(p, ra, z, oka0, oka1);
-        const F2 eb = lookback_step_fast2<GEOM_SHARED, MUFU_SIN>(p, rb, z, okb0, okb1);
+        const F2 ea = lookback_step_fast2<GEOM_SHARED, MUFU_SIN, WIDE>(p, ra, z, oka0, oka1);
+        const F2 eb = lookback_step_fast2<GEOM_SHARED, MUFU_SIN, WIDE>(p, rb, z, okb0, okb1);
         float ea0, ea1, eb0, eb1;
         up(ea, ea0, ea1);
         up(eb, eb0, eb1);
@@ -115,7 +115,7 @@ lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const 
         r.q3 = srow[w * 5 + 3];
         r.q4 = srow[w * 5 + 4];
         bool ok0, ok1;
-        const F2 e = lookback_step_fast2<GEOM_SHARED, MUFU_SIN>(p, r, z, ok0, ok1);
+        const F2 e = lookback_step_fast2<GEOM_SHARED, MUFU_SIN, WIDE>(p, r, z, ok0, ok1);
         float e0, e1;
         up(e, e0, e1);
         if (!ok0) e0 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i0, srow + w * 5, z);
@@ -195,9 +195,9 @@ lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const 
 }
 
 
-template <int SY, bool GEOM, bool MUFU>
+template <int SY, bool GEOM, bool MUFU, bool WIDE>
 static int launch_one(const LbArgs& a, cudaStream_t st) {
-    auto kern = lookback_window2_kernel<SY, GEOM, MUFU>;
+    auto kern = lookback_window2_kernel<SY, GEOM, MUFU, WIDE>;
     const size_t smem = (size_t)a.W * (LLAMPC_HIST_ROW * 4) + (SY > 1 ? LB_THREADS * 4 * 2 : 0);
     const int rc = raise_dynamic_smem(kern, smem);
     if (rc) return rc;
@@ -210,10 +210,16 @@ static int launch_one(const LbArgs& a, cudaStream_t st) {
                  a.cta_lists, a.idx_offset, a.nr, a.fm, a.px, a.tm);
 }
 
+template <int SY, bool WIDE>
+static int launch_gm(const LbArgs& a, bool geom, bool mufu, cudaStream_t st) {
+    if (mufu) return geom ? launch_one<SY, true, true, WIDE>(a, st) : launch_one<SY, false, true, WIDE>(a, st);
+    return geom ? launch_one<SY, true, false, WIDE>(a, st) : launch_one<SY, false, false, WIDE>(a, st);
+}
+
+// a.wide: the instantiation whose step takes its slip angles from the full-range atan (windows measured at low speed)
 template <int SY>
 static int launch_sy(const LbArgs& a, bool geom, bool mufu, cudaStream_t st) {
-    if (mufu) return geom ? launch_one<SY, true, true>(a, st) : launch_one<SY, false, true>(a, st);
-    return geom ? launch_one<SY, true, false>(a, st) : launch_one<SY, false, false>(a, st);
+    return a.wide ? launch_gm<SY, true>(a, geom, mufu, st) : launch_gm<SY, false>(a, geom, mufu, st);
 }
 
 int launch_k1_packed(const LbArgs& a, int sy, bool geom, bool mufu, cudaStream_t st) {

@@ -20,6 +20,7 @@ struct LbArgs {
     PeerXchg px;                 // NVLink min-loc (world = 0: off)
     TreeMerge tm;                // in-kernel tree merge, single history (K = 0: off)
     bool pdl;                    // programmatic dependent launch (K1p, tree mode)
+    bool wide;                   // K1p: the full-range slip-angle form of the step (LLAMPC_LB_FLAG_WIDE)
 };
 
 // candidates per CTA of the grid kernels for a window split of `sy`

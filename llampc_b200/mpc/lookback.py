@@ -57,7 +57,7 @@ class LookbackLaunch:
     """
 
     def __init__(self, bank, hist, W, Ts, K=10, n_vehicles=1, hist_stride_rows=None, idx_offset=0, mode="recompute",
-                 err_ring=None, avg_err=None, out=None, fast_sin=None, kernel=None, split=0, peer=None, pdl=False):
+                 err_ring=None, avg_err=None, out=None, fast_sin=None, kernel=None, split=0, peer=None, pdl=False, wide=False):
         torch = _lib.require_cuda()
         self.torch, self.bank, self.hist, self.peer = torch, bank, hist, peer
         self._L = _lib.lib()
@@ -77,7 +77,7 @@ class LookbackLaunch:
         self.out = out
         d.out = out.data_ptr() if out is not None else None
         d.kernel, d.split = _KERNEL[kernel] if not isinstance(kernel, int) else kernel, int(split)
-        d.flags = _lib.LB_FLAG_PDL if pdl else 0
+        d.flags = (_lib.LB_FLAG_PDL if pdl else 0) | (_lib.LB_FLAG_WIDE if wide else 0)
         if peer is not None:
             d.peer_bufs, d.world, d.rank, d.seq = peer.peer_ptrs.data_ptr(), peer.world, peer.rank, 1
         self.desc = d
@@ -220,6 +220,10 @@ class LookBack:
             t.peer_bufs, t.peer_world, t.peer_rank = self._peer.peer_ptrs.data_ptr(), self._peer.world, self._peer.rank
         if self.rolling:
             t.err_ring, t.rolling = self.err_ring.data_ptr(), 1
+        # one flag per ring slot: "measured at low speed or in a drift" -- the tick runs the wide form of K1p while a tenth of
+        # the window is flagged (include/llampc_b200.h, LLAMPC_LB_FLAG_WIDE)
+        self._hard = np.zeros(self.W, dtype=np.uint8)
+        t.hard_h, t.n_hard = self._hard.ctypes.data, 0
         with torch.cuda.device(dev):
             nbytes = int(L.llampc_lookback_tick_workspace_bytes(C.byref(t)))
         if nbytes < 0:
@@ -301,6 +305,9 @@ class LookBack:
         self.hist.copy_(torch.from_numpy(self.rows32_h))
         self.hist64.copy_(torch.from_numpy(self.rows64_h))
         self.window_count, self._next_slot = self.W, 0
+        vx, vy, w = (np.abs(self.rows32_h[:, i]) for i in (6, 7, 8))
+        self._hard[:] = (vx < 0.6) | (vy + 0.06 * w > 0.4 * vx)
+        self._tick.n_hard = int(self._hard.sum())
 
     # ------------------------------------------------------------------ per-tick API
     def push(self, x_k, u_k, x_k1):
@@ -316,6 +323,11 @@ class LookBack:
             if filling:
                 torch = self.torch
                 self.hist[slot].copy_(torch.from_numpy(self.rows32_h[slot]))
+                if not self.rolling:                             # the tick is not called while the window fills: flag the row here
+                    vx, vy, w = (abs(float(v)) for v in self.rows32_h[slot, 6:9])
+                    hard = int(vx < 0.6 or vy + 0.06 * w > 0.4 * vx)
+                    t.n_hard += hard - int(self._hard[slot])
+                    self._hard[slot] = hard
                 if self.rolling:                                 # store the error column, no decision yet
                     t.row32_h, t.row64_h, t.slot, t.rolling = r32, (r64 if self.n_refine > 0 else None), slot, 2
                     with self._stream_dev:

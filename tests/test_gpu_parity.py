@@ -901,6 +901,40 @@ def test_replay_pipelined_matches_push(history, mode):
         assert lb.push(S[:, ts[-1] + 1], U[:, ts[-1] + 1], S[:, ts[-1] + 2])[0] is not None
 
 
+def test_low_speed_window_takes_the_wide_form_and_matches_the_oracle():
+    """A window measured at 0.1 - 0.3 m/s (the bench's synthetic plant after its throttle dip): most candidates leave the
+    |tan| <= 0.5 form of the packed step there.  LookBack flags such rows on the host and runs the LLAMPC_LB_FLAG_WIDE
+    instantiation of K1p while a tenth of the window is flagged; scores stay within tolerance of the float64 oracle, arg-min
+    and top-10 are the oracle's, and the default form (guard fallback, forced through LookbackLaunch) gives the same top-10."""
+    import bench
+    import torch
+    from llampc_b200.mpc import LookBack
+    from llampc_b200.mpc.lookback import LookbackLaunch
+    S, U = bench.synthetic_history(460, lambda p, x, u: orc.rk6_step(p, x, u, 0, bench.TS))
+    N, W = 12000, 30
+    bank = bench.make_bank(N, seed=3)
+    lb = LookBack(bank, W=W, Ts=bench.TS, K=10, refine=16, kernel="k1p")
+    outs = [lb.push(S[:, t], U[:, t], S[:, t + 1]) for t in range(330, 420)]
+    assert lb._tick.n_hard * 10 >= W                                      # the window at ticks 390 - 420 is flagged ...
+    ref = orc.LookBackOracle(bank, W, bench.TS, 10)
+    for t, got in zip(range(330, 420), outs):
+        rbest, rtopk, ravg = ref.push(S[:, t], U[:, t], S[:, t + 1])
+        if rbest is None:
+            assert got[0] is None
+            continue
+        assert got[0] == rbest and list(got[1]) == list(rtopk) and abs(got[2] - ravg[rbest]) <= 1e-9 * ravg[rbest]
+    # the two forms of the kernel on the last window: fp32 scores within tolerance of the oracle, same top-10
+    res = []
+    for wide in (False, True):
+        avg = torch.zeros(N, dtype=torch.float32, device="cuda")
+        ll = LookbackLaunch(lb.bank, lb.hist, W, bench.TS, K=10, avg_err=avg, kernel="k1p", wide=wide)
+        ll.launch()
+        res.append((ll.keys()[0, 1:11] & np.uint64(0xFFFFFFFF), avg.cpu().numpy().astype(np.float64)))
+    _assert_scores(res[0][1], ravg, "default form, low-speed window")
+    _assert_scores(res[1][1], ravg, "wide form, low-speed window")
+    assert np.array_equal(res[0][0], res[1][0])
+
+
 def test_scalar_and_packed_kernels_agree_on_decisions(history):
     """LookBack forced onto the scalar kernel K1 and onto the packed kernel K1p over a replay of the recorded loop: the
     same operations per candidate (the packed form only re-associates a few signs), so decisions and fp64 re-scored
