@@ -85,28 +85,6 @@ lookback_window2_kernel(const float4* __restrict__ bank, int N, int Npad, const 
 
     float acc0 = 0.0f, acc1 = 0.0f;
     int w = sy;
-#ifdef LLAMPC_K1P_ROWS2
-    // two window rows of the same candidate pair in flight: the parameters are shared, the two steps are independent
-    // dependency chains for the instruction scheduler (the errors are still added in row order)
-    for (; w + SY < W; w += 2 * SY) {
-        HistRow ra, rb;
-        ra.q0 = srow[w * 5 + 0]; ra.q1 = srow[w * 5 + 1]; ra.q2 = srow[w * 5 + 2]; ra.q3 = srow[w * 5 + 3]; ra.q4 = srow[w * 5 + 4];
-        const int wb = w + SY;
-        rb.q0 = srow[wb * 5 + 0]; rb.q1 = srow[wb * 5 + 1]; rb.q2 = srow[wb * 5 + 2]; rb.q3 = srow[wb * 5 + 3]; rb.q4 = srow[wb * 5 + 4];
-        bool oka0, oka1, okb0, okb1;
-        const F2 ea = lookback_step_fast2<GEOM_SHARED, MUFU_SIN, WIDE>(p, ra, z, oka0, oka1);
-        const F2 eb = lookback_step_fast2<GEOM_SHARED, MUFU_SIN, WIDE>(p, rb, z, okb0, okb1);
-        float ea0, ea1, eb0, eb1;
-        up(ea, ea0, ea1);
-        up(eb, eb0, eb1);
-        if (!oka0) ea0 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i0, srow + w * 5, z);
-        if (!oka1) ea1 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i1, srow + w * 5, z);
-        if (!okb0) eb0 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i0, srow + wb * 5, z);
-        if (!okb1) eb1 = lookback_step_general<GEOM_SHARED, MUFU_SIN>(bank, Npad, i1, srow + wb * 5, z);
-        acc0 += ea0; acc0 += eb0;
-        acc1 += ea1; acc1 += eb1;
-    }
-#endif
     for (; w < W; w += SY) {
         HistRow r;
         r.q0 = srow[w * 5 + 0];
