@@ -151,6 +151,18 @@ __device__ __forceinline__ void sincos_tiny2(F2 e, F2& sn, F2& cs) {
     cs = fma2(s, pc, bc(1.0f));
 }
 
+// sin / cos of a heading offset |e| <= 0.5 (the WIDE form: truncation errors 5e-9 / 3e-10 at 0.5)
+__device__ __forceinline__ void sincos_mid2(F2 e, F2& sn, F2& cs) {
+    const F2 s = mul2(e, e);
+    F2 ps = fma2(s, bc(-1.9841270e-04f), bc(8.3333333e-03f));
+    ps = fma2(ps, s, bc(-1.6666667e-01f));
+    sn = fma2(mul2(e, s), ps, e);
+    F2 pc = fma2(s, bc(2.4801587e-05f), bc(-1.3888889e-03f));
+    pc = fma2(pc, s, bc(4.1666668e-02f));
+    pc = fma2(pc, s, bc(-0.5f));
+    cs = fma2(s, pc, bc(1.0f));
+}
+
 struct Deriv2 { F2 vx, nvy, w; };                // nvy = MINUS d(vy)/dt: consumers fold the sign into the (scalar) step size
 struct Drive2 { F2 A, nBq; };                     // Frx = A - vx (Cr2 vx + Bq), evaluated as fma(vx, fma(-Cr2, vx, -Bq), A)
 
@@ -226,7 +238,7 @@ __device__ __forceinline__ F2 lookback_step_fast2(const Cand2& p, const HistRow&
     const F2 vx3 = fma2(bc(hh), a2.vx, bc(vx0)), vy3 = fma2(bc(-hh), a2.nvy, bc(vy0)), w3 = fma2(bc(hh), a2.w, bc(w0));
     const F2 e3 = mul2(bc(hh), mul2(bc(hh), a1.w));
     F2 sd, cd;
-    sincos_tiny2(e3, sd, cd);
+    if (WIDE) sincos_mid2(e3, sd, cd); else sincos_tiny2(e3, sd, cd);
     const F2 s3 = fma2(bc(r.q0.z), cd, mul2(bc(r.q0.w), sd)), c3 = fma2(bc(r.q0.w), cd, mul2(bc(-r.q0.z), sd));
     const Deriv2 a3 = accel_fast2<MUFU_SIN, WIDE>(p, u, drv, vx3, vy3, w3, g);
     xs = add2(xs, sub2(mul2(vx3, c3), mul2(vy3, s3)));
@@ -234,7 +246,7 @@ __device__ __forceinline__ F2 lookback_step_fast2(const Cand2& p, const HistRow&
     // stage 4 (front tyre and drivetrain only)
     const F2 vx4 = fma2(bc(h), a3.vx, bc(vx0)), vy4 = fma2(bc(-h), a3.nvy, bc(vy0)), w4 = fma2(bc(h), a3.w, bc(w0));
     const F2 e4 = mul2(bc(h), mul2(bc(hh), a2.w));
-    sincos_tiny2(e4, sd, cd);
+    if (WIDE) sincos_mid2(e4, sd, cd); else sincos_tiny2(e4, sd, cd);
     const F2 s4 = fma2(bc(r.q1.x), cd, mul2(bc(r.q1.y), sd)), c4 = fma2(bc(r.q1.y), cd, mul2(bc(-r.q1.x), sd));
     const F2 inv4 = rcp_abs2(vx4);
     const F2 tf4 = mul2(fma2(p.lf, w4, vy4), inv4);
@@ -250,13 +262,14 @@ __device__ __forceinline__ F2 lookback_step_fast2(const Cand2& p, const HistRow&
     const F2 evx = add2(fma2(bc(z.h6_lo), sv, fma2(bc(z.h6), sv, bc(-r.q4.x))), bc(-r.q4.y));
     const F2 e2 = fma2(ex, ex, fma2(ey, ey, fma2(epsi, epsi, mul2(evx, evx))));
     // guards: slip tangents <= 0.5 (stages 2-4 and, without shared geometry, stage 1), heading offsets <= 0.125
+    // (WIDE: no tangent guard, heading offsets <= 0.5 with the longer sin / cos polynomials)
     float t0, t1, o0, o1, p0, p1, q0, q1;
     up(tf4, t0, t1);
     up(e3, o0, o1);
     up(e4, p0, p1);
     up(e2, q0, q1);
-    ok0 = (WIDE || fmaxf(g.t0, fabsf(t0)) <= 0.5f) && (fmaxf(fabsf(o0), fabsf(p0)) <= 0.125f) && (q0 == q0);
-    ok1 = (WIDE || fmaxf(g.t1, fabsf(t1)) <= 0.5f) && (fmaxf(fabsf(o1), fabsf(p1)) <= 0.125f) && (q1 == q1);
+    ok0 = (WIDE || fmaxf(g.t0, fabsf(t0)) <= 0.5f) && (fmaxf(fabsf(o0), fabsf(p0)) <= (WIDE ? 0.5f : 0.125f)) && (q0 == q0);
+    ok1 = (WIDE || fmaxf(g.t1, fabsf(t1)) <= 0.5f) && (fmaxf(fabsf(o1), fabsf(p1)) <= (WIDE ? 0.5f : 0.125f)) && (q1 == q1);
     return e2;
 }
 
