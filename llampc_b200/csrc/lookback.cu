@@ -183,10 +183,14 @@ refine_f64_kernel(const double* __restrict__ bank64, int N, double* __restrict__
     __shared__ bool last_block;
     __shared__ int peer_fail;
     const int f = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
-    // In a pipelined replay the NEXT tick's scoring kernel is launched with programmatic stream serialization: it may start its
-    // bank loads and RK4 rows beside this re-score (it writes nothing this kernel reads before its own griddepcontrol.wait,
-    // which holds until this grid has completed).  A no-op for ordinary launches.
+    // In a pipelined replay this kernel AND the next tick's scoring kernel are launched with programmatic stream serialization:
+    // this grid may be scheduled as soon as every CTA of its own tick's scoring kernel has finished its RK4 rows; it passes the
+    // permission on at once (launch_dependents: the next tick's scoring kernel starts its bank loads and rows beside the
+    // merge-tree tail of this tick's and beside this re-score) and then waits for its scoring kernel to complete (wait) before
+    // it reads the finalists.  The next scoring kernel writes nothing this kernel reads before its own griddepcontrol.wait,
+    // which holds until this grid has completed.  Both instructions are no-ops in ordinary launches.
     pdl_launch_dependents();
+    pdl_wait();
     if (nr.slot >= 0 && f == 0 && tid < LLAMPC_HIST64_ROW) hist64[(size_t)nr.slot * LLAMPC_HIST64_ROW + tid] = nr.v[tid];
     const long long ci = (long long)(unsigned)(keys[f] & 0xffffffffull) - idx_offset;
     double result = __longlong_as_double(0x7ff8000000000000ll);       // padded key (~0) or foreign shard -> NaN
@@ -782,8 +786,12 @@ extern "C" int llampc_lookback_tick(llampc_tick_t* t, llampc_stream_t stream) {
                 if (gather) return LLAMPC_E_ARG;
             }
         }
-        rc = issue(refine_f64_kernel, dim3(Kt), dim3(RF_THREADS), 0, st, t->bank64, t->N, t->hist64, t->W, t->Ts,
-                   static_cast<const u64*>(keys + 1), t->idx_offset, errs, nr64, fc, pg);
+        if (g_plain_launches && (L.d.flags & LLAMPC_LB_FLAG_PDL) && L.p.kernel == LLAMPC_KERNEL_K1P && L.p.tree)
+            rc = issue_pdl(refine_f64_kernel, dim3(Kt), dim3(RF_THREADS), 0, st, t->bank64, t->N, t->hist64, t->W, t->Ts,
+                           static_cast<const u64*>(keys + 1), t->idx_offset, errs, nr64, fc, pg);
+        else
+            rc = issue(refine_f64_kernel, dim3(Kt), dim3(RF_THREADS), 0, st, t->bank64, t->N, t->hist64, t->W, t->Ts,
+                       static_cast<const u64*>(keys + 1), t->idx_offset, errs, nr64, fc, pg);
         if (rc) return rc;
     }
     if (guard.on) {                                                  // replay what was collected as one graph
