@@ -513,8 +513,10 @@ def run_b200(args, emit):
                 # dram__bytes_read.sum + dram__bytes_write.sum of one tick launch at C2: NOT measured in this run, taken
                 # from the committed ncu --set full capture named in traffic_source
                 "traffic": 4264448 if world == 1 else None,
-                "traffic_source": "ncu --set full capture profiles/r01_k1p_ncu.md (4,264,448 B read, 0 B written back within "
-                                  "the launch: the scores stay in L2); not captured for the sharded C5 launches",
+                "traffic_source": "ncu --set full capture profiles/r02_k1p_c2_ncu.md (4,264,448 B read, 0 B written back within the "
+                                  "launch: the scores stay in L2) and, per timed launch of this very command under ncu "
+                                  "--cache-control none, profiles/r02_bench_dram_per_launch.csv (4.26 MB read by every timed "
+                                  "tick); not captured for the sharded C5 launches",
                 "kernel": "%s (%s: scores + selection + in-kernel tree merge = the whole tick), window split %d, tyre sine %s"
                           % (kname, tick.kernel_name, tick.plan.split, tick.sine_name),
                 "kernel_us": k1_avg_s * 1e6, "kernel_us_l2_flushed": float(np.mean(k1_ms)) * 1e3,
