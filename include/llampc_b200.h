@@ -245,6 +245,8 @@ typedef struct llampc_tick {
                                        `slot` from row32_h and runs the LLAMPC_LB_FLAG_WIDE form of K1P while at least a tenth
                                        of the window is flagged (a caller that fills the ring itself sets the flags too)   */
     int n_hard;                     /* number of flagged slots (maintained with hard_h)                                     */
+    void* replay_state;             /* internal, NULL-initialised: side stream, events and the device result ring of
+                                       llampc_lookback_replay; freed by llampc_lookback_tick_release                       */
 } llampc_tick_t;
 
 /* Bytes of t->workspace for this tick configuration (bank, N, W, K, n_refine, rolling, overrides must be filled in);

@@ -43,7 +43,7 @@ class Tick(C.Structure):
                 ("err_ring", _vp), ("rolling", _i),
                 ("workspace", _vp), ("workspace_bytes", C.c_ulonglong),
                 ("mapped_dev", _vp), ("mapped_for", _vp), ("graph_state", _vp),
-                ("hard_h", _vp), ("n_hard", _i)]
+                ("hard_h", _vp), ("n_hard", _i), ("replay_state", _vp)]
 
 
 class LookbackDesc(C.Structure):
