@@ -289,7 +289,11 @@ int llampc_lookback_push(llampc_tick_t* t, const double* x_k, const double* u_k,
  *   rows32_h [W][LLAMPC_HIST_ROW], rows64_h [W][LLAMPC_HIST64_ROW]: writable host staging rings (row i is packed into its slot)
  *   slots_h [depth]: pinned, mapped host result buffers, each as large as t->result_h (t->zero_copy and n_refine > 0 needed)
  *   peer_seq: in/out, NULL on one GPU: the last tick counter used (incremented once per tick, identically on every rank)
- *   idx_out / score_out [T][kt] with kt = max(K, n_refine), n_valid [T]. */
+ *   idx_out / score_out [T][kt] with kt = max(K, n_refine), n_valid [T].
+ * In recompute mode the scoring kernels follow each other on `stream` with programmatic dependent launch and the fp64
+ * re-score of every tick runs on an internal non-blocking side stream behind an event, on the tick's own device result
+ * buffer (t->replay_state, freed by llampc_lookback_tick_release); before returning, `stream` is made to wait for the side
+ * stream.  LLAMPC_REPLAY_TRACE=1 prints the host-side phase times per tick to stderr. */
 int llampc_lookback_replay(llampc_tick_t* t, const double* x_k, const double* u_k, const double* x_k1, int x1_stride, int T,
                            int first_slot, double lf_shared, double lr_shared, float* rows32_h, double* rows64_h,
                            llampc_key_t* const* slots_h, int depth, unsigned* peer_seq, long long* idx_out,
